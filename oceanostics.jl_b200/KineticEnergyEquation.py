@@ -1,0 +1,104 @@
+"""KineticEnergyEquation: constructors of the KE budget terms (reference: src/KineticEnergyEquation.jl).
+Same names, keyword arguments and error behaviour; each returns a KernelFunctionOperation that `Field`,
+`compute`, `Integral`, `Average` and `FusedDiagnostics` accept."""
+from __future__ import annotations
+
+from . import _lib
+from .fields import as_operand
+from .models import perturbation_velocities, validate_location
+from .operations import Closure, KernelFunctionOperation, SweepOperands, perturbation_split
+
+CCC = ("c", "c", "c")
+
+
+def _vel(velocities):
+    return (velocities.u, velocities.v, velocities.w) if hasattr(velocities, "u") else tuple(velocities)
+
+
+def KineticEnergy(model, u=None, v=None, w=None, location=CCC):
+    """src/KineticEnergyEquation.jl:43-46, 68."""
+    validate_location(location, "KineticEnergy")
+    if u is None:
+        u, v, w = _vel(model.velocities)
+    return KernelFunctionOperation("KE", model.grid, SweepOperands(u=u, v=v, w=w), name="KineticEnergy",
+                                   computes="kinetic energy  ½uᵢuᵢ")
+
+
+def KineticEnergyAdvection(model, velocities=None, location=CCC):
+    """src/KineticEnergyEquation.jl:184-187 (Centered second-order momentum advection)."""
+    validate_location(location, "KineticEnergyAdvection")
+    if getattr(model, "hydrostatic", False):
+        raise TypeError("KineticEnergyAdvection is defined for a NonhydrostaticModel")
+    if str(model.advection) not in ("Centered", "Centered(order=2)"):
+        raise _lib.OcbError(f"advection scheme {model.advection!r}: only Centered second-order momentum advection is "
+                            "evaluated by the CUDA library")
+    u, v, w = _vel(velocities if velocities is not None else model.velocities)
+    return KernelFunctionOperation("ADV", model.grid, SweepOperands(u=u, v=v, w=w), name="KineticEnergyAdvection",
+                                   computes="kinetic energy advection  uᵢ∂ⱼ(uᵢuⱼ)")
+
+
+def KineticEnergyPressureRedistribution(model, velocities=None, pressure=None, location=CCC):
+    """src/KineticEnergyEquation.jl:353-358."""
+    validate_location(location, "KineticEnergyPressureRedistribution")
+    u, v, w = _vel(velocities if velocities is not None else model.velocities)
+    if pressure is None:
+        pressure = model.pressures.pNHS
+        if getattr(model.pressures, "pHY", None) is not None:
+            from .fields import Field
+            pressure = Field(model.pressures.pHY + model.pressures.pNHS)   # sum(model.pressures)
+    return KernelFunctionOperation("PR", model.grid, SweepOperands(u=u, v=v, w=w, p=pressure),
+                                   name="KineticEnergyPressureRedistribution",
+                                   computes="kinetic energy pressure redistribution  uᵢ∂ᵢp")
+
+
+def PotentialEnergyConversion(model, velocities=None, tracers=None, location=CCC):
+    """uᵢbᵢ, src/KineticEnergyEquation.jl:419-422 (BuoyancyTracer; the gravity unit vector may be tilted)."""
+    validate_location(location, "PotentialEnergyConversion")
+    u, v, w = _vel(velocities if velocities is not None else model.velocities)
+    tracers = tracers if tracers is not None else model.tracers
+    gu = model.buoyancy.gravity_unit_vector
+    return KernelFunctionOperation("WB", model.grid, SweepOperands(u=u, v=v, w=w, b=tracers.b, ghat=tuple(-g for g in gu)),
+                                   name="PotentialEnergyConversion", computes="potential to kinetic energy conversion  uᵢbᵢ")
+
+
+def DissipationRate(model, U=None, V=None, W=None, location=CCC):
+    """ε = ∂ⱼuᵢ·τᵢⱼ, src/KineticEnergyEquation.jl:482-493."""
+    validate_location(location, "DissipationRate")
+    ops = perturbation_velocities(model, U, V, W)
+    pert = any(x is not None for x in (U, V, W))
+    return KernelFunctionOperation("EPS", model.grid, SweepOperands(closure=model.closure, **ops),
+                                   flags=_lib.OCB_REQ_PERTURBATION if pert else 0, name="KineticEnergyDissipationRate",
+                                   computes="kinetic energy dissipation rate  ε = ∂ⱼuᵢ·τᵢⱼ")
+
+
+KineticEnergyDissipationRate = DissipationRate
+
+
+def KineticEnergyIsotropicDissipationRate(*args, location=CCC, **kw):
+    """ε = 2νSᵢⱼSᵢⱼ, src/KineticEnergyEquation.jl:540-550.  Call as (model) or (u, v, w, closure, grid=...)."""
+    validate_location(location, "KineticEnergyIsotropicDissipationRate")
+    if len(args) == 1:
+        model = args[0]
+        u, v, w = _vel(model.velocities)
+        closure, grid = model.closure, model.grid
+    else:
+        u, v, w, closure = args[:4]
+        grid = kw.get("grid") or getattr(perturbation_split(u)[0], "grid")
+    if not isinstance(closure, Closure):
+        raise ValueError(f"Cannot calculate dissipation rate for {closure}")
+    flags, ops = 0, {}
+    for name, x in (("u", u), ("v", v), ("w", w)):
+        f, mean = perturbation_split(x)
+        ops[name] = f
+        if mean is not None:
+            ops[name.upper()] = as_operand(mean)
+            flags = _lib.OCB_REQ_PERTURBATION
+    return KernelFunctionOperation("EPS_ISO", grid, SweepOperands(closure=closure, **ops), flags=flags,
+                                   name="KineticEnergyIsotropicDissipationRate",
+                                   computes="isotropic kinetic energy dissipation rate  ε = 2νSᵢⱼSᵢⱼ")
+
+
+Advection = KineticEnergyAdvection
+PressureRedistribution = KineticEnergyPressureRedistribution
+BuoyancyProduction = PotentialEnergyConversion
+IsotropicDissipationRate = KineticEnergyIsotropicDissipationRate

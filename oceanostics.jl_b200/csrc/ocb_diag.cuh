@@ -1,0 +1,539 @@
+// Per-cell evaluation of every diagnostic of the fused stencil sweep (K1), as host+device templates.
+//
+// These are the B200 library's own formulations of the kernel functions the reference evaluates
+// through Oceananigans' operator algebra (file:line of each reference function is given at its
+// evaluator).  They are written on explicit index offsets with reciprocal metrics, each edge / face
+// quantity formed once per evaluation -- mathematically equal to the reference, not bit-equal
+// (the contract is rtol 1e-12 in Float64, BASELINE.json north_star).
+//
+// The same templates are compiled (a) into the generic CUDA sweep kernel (ocb_sweep.cu) and (b), for
+// testing only, into tests/hostcheck/ where they run on the host against the NumPy oracle.
+#pragma once
+#include "ocb_common.cuh"
+
+#define OCB_MAX_REQ 16
+
+template <class T>
+struct SweepIn {
+  HFld<T> u, v, w, b, p, U, V, W, B;
+  HFld<T> aux[OCB_N_AUX];
+  T nu_c; int n_nu; HFld<T> nu_f[OCB_MAX_CLOSURE_FIELDS];
+  T ka_c; int n_ka; HFld<T> ka_f[OCB_MAX_CLOSURE_FIELDS]; T ka_s[OCB_MAX_CLOSURE_FIELDS];
+  T f[3], dir[3], f_dir, ghat[3], ro_bg[6];
+};
+
+struct DReq {
+  int diag, flags;
+  void* out;             // pre-offset: index (i,j,k) lives at out[i*os[0] + j*os[1] + k*os[2]]
+  long long os[3];
+  int lo[3], hi[3];      // inclusive 1-based index window to evaluate
+  int slot;
+  int loc[3];
+};
+
+template <class T>
+struct SweepParams {
+  DGrid<T> g;
+  SweepIn<T> in;
+  int nreq;
+  DReq req[OCB_MAX_REQ];
+  double* partial;       // [nblocks][nslots]
+  int nslots;
+  int lo[3], hi[3];      // union of the request windows
+  int kchunk;
+};
+
+// ---- evaluation context: the operands one request sees ----------------------------------------------
+template <class T>
+struct Ctx {
+  const DGrid<T>& g;
+  const SweepIn<T>& in;
+  bool pert;
+  OCB_X Ctx(const DGrid<T>& g_, const SweepIn<T>& in_, bool p_) : g(g_), in(in_), pert(p_) {}
+  // velocities / tracer as this request sees them (u - U when the perturbation flag is set)
+  OCB_X T u(int i, int j, int k) const { T a = in.u(i, j, k); return pert ? a - in.U(i, j, k) : a; }
+  OCB_X T v(int i, int j, int k) const { T a = in.v(i, j, k); return pert ? a - in.V(i, j, k) : a; }
+  OCB_X T w(int i, int j, int k) const { T a = in.w(i, j, k); return pert ? a - in.W(i, j, k) : a; }
+  OCB_X T c(int i, int j, int k) const { T a = in.b(i, j, k); return pert ? a - in.B(i, j, k) : a; }
+  // z metrics
+  OCB_X T dzc(int k) const { return OCB_LD(g.dzc + k); }
+  OCB_X T dzf(int k) const { return OCB_LD(g.dzf + k); }
+  OCB_X T rdzc(int k) const { return OCB_LD(g.rdzc + k); }
+  OCB_X T rdzf(int k) const { return OCB_LD(g.rdzf + k); }
+  // closure viscosity at the four stress locations: the constant plus the interpolated eddy fields
+  OCB_X T nu_ccc(int i, int j, int k) const {
+    T s = in.nu_c;
+    for (int f = 0; f < in.n_nu; ++f) s += in.nu_f[f](i, j, k);
+    return s;
+  }
+  OCB_X T nu_ffc(int i, int j, int k) const {
+    T s = in.nu_c;
+    for (int f = 0; f < in.n_nu; ++f) {
+      const HFld<T>& n = in.nu_f[f];
+      s += T(0.25) * ((n(i - 1, j - 1, k) + n(i, j - 1, k)) + (n(i - 1, j, k) + n(i, j, k)));
+    }
+    return s;
+  }
+  OCB_X T nu_fcf(int i, int j, int k) const {
+    T s = in.nu_c;
+    for (int f = 0; f < in.n_nu; ++f) {
+      const HFld<T>& n = in.nu_f[f];
+      s += T(0.25) * ((n(i - 1, j, k - 1) + n(i, j, k - 1)) + (n(i - 1, j, k) + n(i, j, k)));
+    }
+    return s;
+  }
+  OCB_X T nu_cff(int i, int j, int k) const {
+    T s = in.nu_c;
+    for (int f = 0; f < in.n_nu; ++f) {
+      const HFld<T>& n = in.nu_f[f];
+      s += T(0.25) * ((n(i, j - 1, k - 1) + n(i, j, k - 1)) + (n(i, j - 1, k) + n(i, j, k)));
+    }
+    return s;
+  }
+  // tracer diffusivity at the three flux faces
+  OCB_X T ka_fcc(int i, int j, int k) const {
+    T s = in.ka_c;
+    for (int f = 0; f < in.n_ka; ++f) s += in.ka_s[f] * (T(0.5) * (in.ka_f[f](i - 1, j, k) + in.ka_f[f](i, j, k)));
+    return s;
+  }
+  OCB_X T ka_cfc(int i, int j, int k) const {
+    T s = in.ka_c;
+    for (int f = 0; f < in.n_ka; ++f) s += in.ka_s[f] * (T(0.5) * (in.ka_f[f](i, j - 1, k) + in.ka_f[f](i, j, k)));
+    return s;
+  }
+  OCB_X T ka_ccf(int i, int j, int k) const {
+    T s = in.ka_c;
+    for (int f = 0; f < in.n_ka; ++f) s += in.ka_s[f] * (T(0.5) * (in.ka_f[f](i, j, k - 1) + in.ka_f[f](i, j, k)));
+    return s;
+  }
+
+  // ---- velocity-gradient building blocks ---------------------------------------------------------------
+  // diagonal strain rates at ccc
+  OCB_X T s11(int i, int j, int k) const { return (u(i + 1, j, k) - u(i, j, k)) * g.rdx; }
+  OCB_X T s22(int i, int j, int k) const { return (v(i, j + 1, k) - v(i, j, k)) * g.rdy; }
+  OCB_X T s33(int i, int j, int k) const { return (w(i, j, k + 1) - w(i, j, k)) * rdzc(k); }
+  // the six cross derivatives at their edges
+  OCB_X T dyu_ffc(int i, int j, int k) const { return (u(i, j, k) - u(i, j - 1, k)) * g.rdy; }
+  OCB_X T dxv_ffc(int i, int j, int k) const { return (v(i, j, k) - v(i - 1, j, k)) * g.rdx; }
+  OCB_X T dzu_fcf(int i, int j, int k) const { return (u(i, j, k) - u(i, j, k - 1)) * rdzf(k); }
+  OCB_X T dxw_fcf(int i, int j, int k) const { return (w(i, j, k) - w(i - 1, j, k)) * g.rdx; }
+  OCB_X T dzv_cff(int i, int j, int k) const { return (v(i, j, k) - v(i, j, k - 1)) * rdzf(k); }
+  OCB_X T dyw_cff(int i, int j, int k) const { return (w(i, j, k) - w(i, j - 1, k)) * g.rdy; }
+  OCB_X T s12(int i, int j, int k) const { return T(0.5) * (dyu_ffc(i, j, k) + dxv_ffc(i, j, k)); }
+  OCB_X T s13(int i, int j, int k) const { return T(0.5) * (dzu_fcf(i, j, k) + dxw_fcf(i, j, k)); }
+  OCB_X T s23(int i, int j, int k) const { return T(0.5) * (dzv_cff(i, j, k) + dyw_cff(i, j, k)); }
+};
+
+// four-point means from an edge location to the cell centre
+#define OCB_MEAN_XY(f, i, j, k) (T(0.25) * (((f)((i), (j), (k)) + (f)((i) + 1, (j), (k))) + ((f)((i), (j) + 1, (k)) + (f)((i) + 1, (j) + 1, (k)))))
+#define OCB_MEAN_XZ(f, i, j, k) (T(0.25) * (((f)((i), (j), (k)) + (f)((i) + 1, (j), (k))) + ((f)((i), (j), (k) + 1) + (f)((i) + 1, (j), (k) + 1))))
+#define OCB_MEAN_YZ(f, i, j, k) (T(0.25) * (((f)((i), (j), (k)) + (f)((i), (j) + 1, (k))) + ((f)((i), (j), (k) + 1) + (f)((i), (j) + 1, (k) + 1))))
+
+template <class T> OCB_X T ocb_sq(T x) { return x * x; }
+
+// =====================================================================================================
+// evaluators: one per OCB_DIAG_* id
+// =====================================================================================================
+template <class T, int DIAG>
+struct Eval;   // Eval<T, DIAG>::at(ctx, flags, i, j, k)
+
+#define OCB_EVAL(DIAG) template <class T> struct Eval<T, DIAG> { static OCB_X T at(const Ctx<T>& X, int flags, int i, int j, int k)
+
+// kinetic_energy_ccc  (src/KineticEnergyEquation.jl:37-39): half the sum of the face-averaged squares
+template <class T> OCB_X T ocb_ke(const Ctx<T>& X, int i, int j, int k) {
+  T a = ocb_sq(X.u(i, j, k)) + ocb_sq(X.u(i + 1, j, k));
+  T b = ocb_sq(X.v(i, j, k)) + ocb_sq(X.v(i, j + 1, k));
+  T c = ocb_sq(X.w(i, j, k)) + ocb_sq(X.w(i, j, k + 1));
+  return T(0.25) * (a + b + c);
+}
+OCB_EVAL(OCB_DIAG_KE) { return ocb_ke(X, i, j, k); } };
+
+// turbulent_kinetic_energy_ccc  (src/TurbulentKineticEnergyEquation.jl:24-30): always about (U, V, W)
+OCB_EVAL(OCB_DIAG_TKE) {
+  Ctx<T> P(X.g, X.in, true);
+  return ocb_ke(P, i, j, k);
+} };
+
+// ---- uᵢ∂ⱼuⱼuᵢᶜᶜᶜ, Centered second order  (src/KineticEnergyEquation.jl:147-152) -----------------------
+// momentum fluxes: (area-weighted advecting velocity averaged to the flux point) x (advected velocity there)
+template <class T> struct AdvFlux {
+  const Ctx<T>& X;
+  OCB_X AdvFlux(const Ctx<T>& x) : X(x) {}
+  OCB_X T axu(int i, int j, int k) const { return X.g.dy * X.dzc(k) * X.u(i, j, k); }   // Ax_fcc u
+  OCB_X T ayv(int i, int j, int k) const { return X.g.dx * X.dzc(k) * X.v(i, j, k); }   // Ay_cfc v
+  OCB_X T azw(int i, int j, int k) const { return X.g.dx * X.g.dy * X.w(i, j, k); }     // Az_ccf w
+  // u-momentum
+  OCB_X T Uu(int i, int j, int k) const { return T(0.25) * (axu(i, j, k) + axu(i + 1, j, k)) * (X.u(i, j, k) + X.u(i + 1, j, k)); }   // ccc
+  OCB_X T Vu(int i, int j, int k) const { return T(0.25) * (ayv(i - 1, j, k) + ayv(i, j, k)) * (X.u(i, j - 1, k) + X.u(i, j, k)); }   // ffc
+  OCB_X T Wu(int i, int j, int k) const { return T(0.25) * (azw(i - 1, j, k) + azw(i, j, k)) * (X.u(i, j, k - 1) + X.u(i, j, k)); }   // fcf
+  // v-momentum
+  OCB_X T Uv(int i, int j, int k) const { return T(0.25) * (axu(i, j - 1, k) + axu(i, j, k)) * (X.v(i - 1, j, k) + X.v(i, j, k)); }   // ffc
+  OCB_X T Vv(int i, int j, int k) const { return T(0.25) * (ayv(i, j, k) + ayv(i, j + 1, k)) * (X.v(i, j, k) + X.v(i, j + 1, k)); }   // ccc
+  OCB_X T Wv(int i, int j, int k) const { return T(0.25) * (azw(i, j - 1, k) + azw(i, j, k)) * (X.v(i, j, k - 1) + X.v(i, j, k)); }   // cff
+  // w-momentum
+  OCB_X T Uw(int i, int j, int k) const { return T(0.25) * (axu(i, j, k - 1) + axu(i, j, k)) * (X.w(i - 1, j, k) + X.w(i, j, k)); }   // fcf
+  OCB_X T Vw(int i, int j, int k) const { return T(0.25) * (ayv(i, j, k - 1) + ayv(i, j, k)) * (X.w(i, j - 1, k) + X.w(i, j, k)); }   // cff
+  OCB_X T Ww(int i, int j, int k) const { return T(0.25) * (azw(i, j, k) + azw(i, j, k + 1)) * (X.w(i, j, k) + X.w(i, j, k + 1)); }   // ccc
+  // flux divergences at the velocity points
+  OCB_X T divu(int i, int j, int k) const {   // fcc
+    T s = (Uu(i, j, k) - Uu(i - 1, j, k)) + (Vu(i, j + 1, k) - Vu(i, j, k)) + (Wu(i, j, k + 1) - Wu(i, j, k));
+    return s * (X.g.rdx * X.g.rdy * X.rdzc(k));
+  }
+  OCB_X T divv(int i, int j, int k) const {   // cfc
+    T s = (Uv(i + 1, j, k) - Uv(i, j, k)) + (Vv(i, j, k) - Vv(i, j - 1, k)) + (Wv(i, j, k + 1) - Wv(i, j, k));
+    return s * (X.g.rdx * X.g.rdy * X.rdzc(k));
+  }
+  OCB_X T divw(int i, int j, int k) const {   // ccf
+    T s = (Uw(i + 1, j, k) - Uw(i, j, k)) + (Vw(i, j + 1, k) - Vw(i, j, k)) + (Ww(i, j, k) - Ww(i, j, k - 1));
+    return s * (X.g.rdx * X.g.rdy * X.rdzf(k));
+  }
+};
+OCB_EVAL(OCB_DIAG_ADV) {
+  AdvFlux<T> A(X);
+  T a = X.u(i, j, k) * A.divu(i, j, k) + X.u(i + 1, j, k) * A.divu(i + 1, j, k);
+  T b = X.v(i, j, k) * A.divv(i, j, k) + X.v(i, j + 1, k) * A.divv(i, j + 1, k);
+  T c = X.w(i, j, k) * A.divw(i, j, k) + X.w(i, j, k + 1) * A.divw(i, j, k + 1);
+  return T(0.5) * (a + b + c);
+} };
+
+// uᵢ∂ᵢpᶜᶜᶜ  (src/KineticEnergyEquation.jl:304-309)
+OCB_EVAL(OCB_DIAG_PR) {
+  const HFld<T>& p = X.in.p;
+  T pc = p(i, j, k);
+  T a = (X.u(i, j, k) * (pc - p(i - 1, j, k)) + X.u(i + 1, j, k) * (p(i + 1, j, k) - pc)) * X.g.rdx;
+  T b = (X.v(i, j, k) * (pc - p(i, j - 1, k)) + X.v(i, j + 1, k) * (p(i, j + 1, k) - pc)) * X.g.rdy;
+  T c = X.w(i, j, k) * ((pc - p(i, j, k - 1)) * X.rdzf(k)) + X.w(i, j, k + 1) * ((p(i, j, k + 1) - pc) * X.rdzf(k + 1));
+  return T(0.5) * (a + b + c);
+} };
+
+// uᵢbᵢᶜᶜᶜ  (src/KineticEnergyEquation.jl:362-367): velocity times the buoyancy projected on each axis
+OCB_EVAL(OCB_DIAG_WB) {
+  const HFld<T>& b = X.in.b;
+  const T* gh = X.in.ghat;
+  T bc = b(i, j, k);
+  T r = T(0);
+  if (gh[0] != T(0)) r += gh[0] * (X.u(i, j, k) * (b(i - 1, j, k) + bc) + X.u(i + 1, j, k) * (bc + b(i + 1, j, k)));
+  if (gh[1] != T(0)) r += gh[1] * (X.v(i, j, k) * (b(i, j - 1, k) + bc) + X.v(i, j + 1, k) * (bc + b(i, j + 1, k)));
+  if (gh[2] != T(0)) r += gh[2] * (X.w(i, j, k) * (b(i, j, k - 1) + bc) + X.w(i, j, k + 1) * (bc + b(i, j, k + 1)));
+  return T(0.25) * r;
+} };
+
+// viscous_dissipation_rate_ccc  (src/KineticEnergyEquation.jl:427-453), conservative A·δu·τ / V form.
+// Per stress location the two symmetric terms are merged:  -(A_a δ_a u_b + A_b δ_b u_a) τ_ab  with
+// τ_ab = -2 ν Σ_ab, and  A_a δ_a u_b + A_b δ_b u_a = 2 V_loc Σ_ab,  so each edge contributes 4 ν V_loc Σ_ab².
+template <class T> struct EpsEdges {
+  const Ctx<T>& X;
+  OCB_X EpsEdges(const Ctx<T>& x) : X(x) {}
+  OCB_X T e12(int i, int j, int k) const { return X.nu_ffc(i, j, k) * ocb_sq(X.s12(i, j, k)); }              // x (4 V_ffc), V_ffc = dx dy dzc(k)
+  OCB_X T e13(int i, int j, int k) const { return X.dzf(k) * (X.nu_fcf(i, j, k) * ocb_sq(X.s13(i, j, k))); }  // x (4 dx dy)
+  OCB_X T e23(int i, int j, int k) const { return X.dzf(k) * (X.nu_cff(i, j, k) * ocb_sq(X.s23(i, j, k))); }  // x (4 dx dy)
+};
+OCB_EVAL(OCB_DIAG_EPS) {
+  EpsEdges<T> E(X);
+  // diagonal terms: -A δu τ = 2 ν V Σ_aa²  -> after /V: 2 ν Σ_aa²
+  T diag = T(2) * X.nu_ccc(i, j, k) * (ocb_sq(X.s11(i, j, k)) + ocb_sq(X.s22(i, j, k)) + ocb_sq(X.s33(i, j, k)));
+  T m12 = OCB_MEAN_XY(E.e12, i, j, k);                    // same dzc(k) at the four corners: cancels with 1/V
+  T m13 = OCB_MEAN_XZ(E.e13, i, j, k) * X.rdzc(k);
+  T m23 = OCB_MEAN_YZ(E.e23, i, j, k) * X.rdzc(k);
+  return diag + T(4) * (m12 + m13 + m23);
+} };
+
+// strain / rotation sums shared by the moduli (src/FlowDiagnostics.jl:429-441, 575-587)
+template <class T> struct SqEdges {
+  const Ctx<T>& X;
+  OCB_X SqEdges(const Ctx<T>& x) : X(x) {}
+  OCB_X T p12(int i, int j, int k) const { return ocb_sq(X.dyu_ffc(i, j, k) + X.dxv_ffc(i, j, k)); }
+  OCB_X T p13(int i, int j, int k) const { return ocb_sq(X.dzu_fcf(i, j, k) + X.dxw_fcf(i, j, k)); }
+  OCB_X T p23(int i, int j, int k) const { return ocb_sq(X.dzv_cff(i, j, k) + X.dyw_cff(i, j, k)); }
+  OCB_X T m12(int i, int j, int k) const { return ocb_sq(X.dyu_ffc(i, j, k) - X.dxv_ffc(i, j, k)); }
+  OCB_X T m13(int i, int j, int k) const { return ocb_sq(X.dzu_fcf(i, j, k) - X.dxw_fcf(i, j, k)); }
+  OCB_X T m23(int i, int j, int k) const { return ocb_sq(X.dzv_cff(i, j, k) - X.dyw_cff(i, j, k)); }
+};
+template <class T> OCB_X T ocb_strain_sq(const Ctx<T>& X, int i, int j, int k) {   // S_ij S_ij
+  SqEdges<T> E(X);
+  T d = ocb_sq(X.s11(i, j, k)) + ocb_sq(X.s22(i, j, k)) + ocb_sq(X.s33(i, j, k));
+  T o = OCB_MEAN_XY(E.p12, i, j, k) + OCB_MEAN_XZ(E.p13, i, j, k) + OCB_MEAN_YZ(E.p23, i, j, k);
+  return d + T(0.5) * o;   // 2 * (mean of (a+b)^2 / 4)
+}
+template <class T> OCB_X T ocb_rotation_sq(const Ctx<T>& X, int i, int j, int k) {   // Ω_ij Ω_ij (each pair twice)
+  SqEdges<T> E(X);
+  T o = OCB_MEAN_XY(E.m12, i, j, k) + OCB_MEAN_XZ(E.m13, i, j, k) + OCB_MEAN_YZ(E.m23, i, j, k);
+  return T(0.5) * o;
+}
+template <class T> OCB_X T ocb_sqrt(T x);
+template <> OCB_X double ocb_sqrt<double>(double x) { return sqrt(x); }
+template <> OCB_X float ocb_sqrt<float>(float x) { return sqrtf(x); }
+
+// isotropic_viscous_dissipation_rate_ccc  (src/KineticEnergyEquation.jl:497-510), ν at ccc summed over the tuple
+OCB_EVAL(OCB_DIAG_EPS_ISO) { return T(2) * X.nu_ccc(i, j, k) * ocb_strain_sq(X, i, j, k); } };
+// strain_rate_tensor_modulus_ccc  (src/FlowDiagnostics.jl:431-441)
+OCB_EVAL(OCB_DIAG_SMOD) { return ocb_sqrt(ocb_strain_sq(X, i, j, k)); } };
+// vorticity_tensor_modulus_ccc  (src/FlowDiagnostics.jl:577-587)
+OCB_EVAL(OCB_DIAG_OMOD) { return ocb_sqrt(ocb_rotation_sq(X, i, j, k)); } };
+// Q_velocity_gradient_tensor_invariant_ccc  (src/FlowDiagnostics.jl:708-712): (|Ω|² - |S|²)/2 through the roots
+OCB_EVAL(OCB_DIAG_Q) {
+  T s = ocb_sqrt(ocb_strain_sq(X, i, j, k)), o = ocb_sqrt(ocb_rotation_sq(X, i, j, k));
+  return T(0.5) * (o * o - s * s);
+} };
+
+// StrainRateTensorKernel{I,J} / VorticityTensorKernel{I,J}  (src/FlowDiagnostics.jl:484-491, 630-634)
+OCB_EVAL(OCB_DIAG_S11) { return X.s11(i, j, k); } };
+OCB_EVAL(OCB_DIAG_S22) { return X.s22(i, j, k); } };
+OCB_EVAL(OCB_DIAG_S33) { return X.s33(i, j, k); } };
+OCB_EVAL(OCB_DIAG_S12) { return X.s12(i, j, k); } };
+OCB_EVAL(OCB_DIAG_S13) { return X.s13(i, j, k); } };
+OCB_EVAL(OCB_DIAG_S23) { return X.s23(i, j, k); } };
+OCB_EVAL(OCB_DIAG_O12) { return T(0.5) * (X.dyu_ffc(i, j, k) - X.dxv_ffc(i, j, k)); } };
+OCB_EVAL(OCB_DIAG_O13) { return T(0.5) * (X.dzu_fcf(i, j, k) - X.dxw_fcf(i, j, k)); } };
+OCB_EVAL(OCB_DIAG_O23) { return T(0.5) * (X.dzv_cff(i, j, k) - X.dyw_cff(i, j, k)); } };
+
+// StressTensorKernel{I,J,Collocated}  (src/FlowDiagnostics.jl:723-733)
+OCB_EVAL(OCB_DIAG_T11) { return ocb_sq(X.u(i, j, k)); } };
+OCB_EVAL(OCB_DIAG_T22) { return ocb_sq(X.v(i, j, k)); } };
+OCB_EVAL(OCB_DIAG_T33) { return ocb_sq(X.w(i, j, k)); } };
+OCB_EVAL(OCB_DIAG_T11C) { return ocb_sq(T(0.5) * (X.u(i, j, k) + X.u(i + 1, j, k))); } };
+OCB_EVAL(OCB_DIAG_T22C) { return ocb_sq(T(0.5) * (X.v(i, j, k) + X.v(i, j + 1, k))); } };
+OCB_EVAL(OCB_DIAG_T33C) { return ocb_sq(T(0.5) * (X.w(i, j, k) + X.w(i, j, k + 1))); } };
+OCB_EVAL(OCB_DIAG_T12) { return (T(0.5) * (X.u(i, j - 1, k) + X.u(i, j, k))) * (T(0.5) * (X.v(i - 1, j, k) + X.v(i, j, k))); } };
+OCB_EVAL(OCB_DIAG_T13) { return (T(0.5) * (X.u(i, j, k - 1) + X.u(i, j, k))) * (T(0.5) * (X.w(i - 1, j, k) + X.w(i, j, k))); } };
+OCB_EVAL(OCB_DIAG_T23) { return (T(0.5) * (X.v(i, j, k - 1) + X.v(i, j, k))) * (T(0.5) * (X.w(i, j - 1, k) + X.w(i, j, k))); } };
+
+// shear_production_rate_{x,y,z}_ccc  (src/TurbulentKineticEnergyEquation.jl:101-117, 163-179, 224-240)
+template <class T> struct MeanGrad {   // gradients of the mean flow at their natural points
+  const Ctx<T>& X;
+  OCB_X MeanGrad(const Ctx<T>& x) : X(x) {}
+  OCB_X T dxV(int i, int j, int k) const { return (X.in.V(i, j, k) - X.in.V(i - 1, j, k)) * X.g.rdx; }   // ffc
+  OCB_X T dxW(int i, int j, int k) const { return (X.in.W(i, j, k) - X.in.W(i - 1, j, k)) * X.g.rdx; }   // fcf
+  OCB_X T dyU(int i, int j, int k) const { return (X.in.U(i, j, k) - X.in.U(i, j - 1, k)) * X.g.rdy; }   // ffc
+  OCB_X T dyW(int i, int j, int k) const { return (X.in.W(i, j, k) - X.in.W(i, j - 1, k)) * X.g.rdy; }   // cff
+  OCB_X T dzU(int i, int j, int k) const { return (X.in.U(i, j, k) - X.in.U(i, j, k - 1)) * X.rdzf(k); } // fcf
+  OCB_X T dzV(int i, int j, int k) const { return (X.in.V(i, j, k) - X.in.V(i, j, k - 1)) * X.rdzf(k); } // cff
+};
+template <class T> OCB_X T ocb_spx(const Ctx<T>& X, int i, int j, int k) {
+  MeanGrad<T> M(X);
+  T uc = T(0.5) * (X.u(i, j, k) + X.u(i + 1, j, k));
+  T vc = T(0.5) * (X.v(i, j, k) + X.v(i, j + 1, k));
+  T wc = T(0.5) * (X.w(i, j, k) + X.w(i, j, k + 1));
+  T uu = T(0.5) * (ocb_sq(X.u(i, j, k)) + ocb_sq(X.u(i + 1, j, k)));
+  T dxU = (X.in.U(i + 1, j, k) - X.in.U(i, j, k)) * X.g.rdx;
+  return -(uu * dxU + (vc * uc) * OCB_MEAN_XY(M.dxV, i, j, k) + (wc * uc) * OCB_MEAN_XZ(M.dxW, i, j, k));
+}
+template <class T> OCB_X T ocb_spy(const Ctx<T>& X, int i, int j, int k) {
+  MeanGrad<T> M(X);
+  T uc = T(0.5) * (X.u(i, j, k) + X.u(i + 1, j, k));
+  T vc = T(0.5) * (X.v(i, j, k) + X.v(i, j + 1, k));
+  T wc = T(0.5) * (X.w(i, j, k) + X.w(i, j, k + 1));
+  T vv = T(0.5) * (ocb_sq(X.v(i, j, k)) + ocb_sq(X.v(i, j + 1, k)));
+  T dyV = (X.in.V(i, j + 1, k) - X.in.V(i, j, k)) * X.g.rdy;
+  return -((uc * vc) * OCB_MEAN_XY(M.dyU, i, j, k) + vv * dyV + (wc * vc) * OCB_MEAN_YZ(M.dyW, i, j, k));
+}
+template <class T> OCB_X T ocb_spz(const Ctx<T>& X, int i, int j, int k) {
+  MeanGrad<T> M(X);
+  T uc = T(0.5) * (X.u(i, j, k) + X.u(i + 1, j, k));
+  T vc = T(0.5) * (X.v(i, j, k) + X.v(i, j + 1, k));
+  T wc = T(0.5) * (X.w(i, j, k) + X.w(i, j, k + 1));
+  T ww = T(0.5) * (ocb_sq(X.w(i, j, k)) + ocb_sq(X.w(i, j, k + 1)));
+  T dzW = (X.in.W(i, j, k + 1) - X.in.W(i, j, k)) * X.rdzc(k);
+  return -((uc * wc) * OCB_MEAN_XZ(M.dzU, i, j, k) + (vc * wc) * OCB_MEAN_YZ(M.dzV, i, j, k) + ww * dzW);
+}
+OCB_EVAL(OCB_DIAG_SPX) { return ocb_spx(X, i, j, k); } };
+OCB_EVAL(OCB_DIAG_SPY) { return ocb_spy(X, i, j, k); } };
+OCB_EVAL(OCB_DIAG_SPZ) { return ocb_spz(X, i, j, k); } };
+OCB_EVAL(OCB_DIAG_SP) { return ocb_spx(X, i, j, k) + ocb_spy(X, i, j, k) + ocb_spz(X, i, j, k); } };   // :285-289
+
+// tracer_variance_dissipation_rate_ccc  (src/TracerVarianceEquation.jl:146-161): 2/V Σ ℑ(A κ δc²/Δ)
+OCB_EVAL(OCB_DIAG_CHI) {
+  T cc = X.c(i, j, k);
+  T fx0 = X.ka_fcc(i, j, k) * ocb_sq(cc - X.c(i - 1, j, k)), fx1 = X.ka_fcc(i + 1, j, k) * ocb_sq(X.c(i + 1, j, k) - cc);
+  T fy0 = X.ka_cfc(i, j, k) * ocb_sq(cc - X.c(i, j - 1, k)), fy1 = X.ka_cfc(i, j + 1, k) * ocb_sq(X.c(i, j + 1, k) - cc);
+  T fz0 = X.ka_ccf(i, j, k) * ocb_sq(cc - X.c(i, j, k - 1)) * X.rdzf(k);
+  T fz1 = X.ka_ccf(i, j, k + 1) * ocb_sq(X.c(i, j, k + 1) - cc) * X.rdzf(k + 1);
+  return (fx0 + fx1) * (X.g.rdx * X.g.rdx) + (fy0 + fy1) * (X.g.rdy * X.g.rdy) + (fz0 + fz1) * X.rdzc(k);
+} };
+
+// c∇_dot_qᶜ  (src/TracerVarianceEquation.jl:93-98): 2 c ∇·q with q = -κ ∇c
+OCB_EVAL(OCB_DIAG_CDIFF) {
+  T cc = X.c(i, j, k);
+  T qx0 = X.ka_fcc(i, j, k) * (cc - X.c(i - 1, j, k)), qx1 = X.ka_fcc(i + 1, j, k) * (X.c(i + 1, j, k) - cc);
+  T qy0 = X.ka_cfc(i, j, k) * (cc - X.c(i, j - 1, k)), qy1 = X.ka_cfc(i, j + 1, k) * (X.c(i, j + 1, k) - cc);
+  T qz0 = X.ka_ccf(i, j, k) * (cc - X.c(i, j, k - 1)) * X.rdzf(k);
+  T qz1 = X.ka_ccf(i, j, k + 1) * (X.c(i, j, k + 1) - cc) * X.rdzf(k + 1);
+  T div = (qx0 - qx1) * (X.g.rdx * X.g.rdx) + (qy0 - qy1) * (X.g.rdy * X.g.rdy) + (qz0 - qz1) * X.rdzc(k);
+  return T(2) * cc * div;
+} };
+
+// ---- richardson_number_ccf  (src/FlowDiagnostics.jl:36-68) -----------------------------------------------
+template <class T> OCB_X T ocb_uh_norm(const Ctx<T>& X, int i, int j, int k) {   // uₕ_norm_ccc, :48-53
+  const T* d = X.in.dir;
+  T u0 = X.u(i, j, k), u1 = X.u(i + 1, j, k), v0 = X.v(i, j, k), v1 = X.v(i, j + 1, k), w0 = X.w(i, j, k), w1 = X.w(i, j, k + 1);
+  T sq = T(0.5) * ((u0 * u0 + u1 * u1) + (v0 * v0 + v1 * v1) + (w0 * w0 + w1 * w1));
+  T along = T(0.5) * ((u0 + u1) * d[0] + (v0 + v1) * d[1] + (w0 + w1) * d[2]);
+  T r = sq - along * along;
+  return ocb_sqrt(r > T(0) ? r : T(0));
+}
+OCB_EVAL(OCB_DIAG_RI) {
+  const T* d = X.in.dir;
+  const HFld<T>& b = X.in.b;
+  T rzf = X.rdzf(k);
+  T db = (b(i, j, k) - b(i, j, k - 1)) * rzf * d[2];
+  T uh0 = ocb_uh_norm(X, i, j, k), uhm = ocb_uh_norm(X, i, j, k - 1);
+  T du = (uh0 - uhm) * rzf * d[2];
+  if (d[0] != T(0)) {   // tilted gravity: x terms (b gradient averaged to ccf, speed gradient left at level k)
+    T bx = T(0.25) * ((b(i + 1, j, k) - b(i - 1, j, k)) + (b(i + 1, j, k - 1) - b(i - 1, j, k - 1))) * X.g.rdx;
+    db += bx * d[0];
+    du += T(0.5) * (ocb_uh_norm(X, i + 1, j, k) - ocb_uh_norm(X, i - 1, j, k)) * X.g.rdx * d[0];
+  }
+  if (d[1] != T(0)) {
+    T by = T(0.25) * ((b(i, j + 1, k) - b(i, j - 1, k)) + (b(i, j + 1, k - 1) - b(i, j - 1, k - 1))) * X.g.rdy;
+    db += by * d[1];
+    du += T(0.5) * (ocb_uh_norm(X, i, j + 1, k) - ocb_uh_norm(X, i, j - 1, k)) * X.g.rdy * d[1];
+  }
+  return db / (du * du);
+} };
+
+// ---- vorticity / potential vorticity at fff ----------------------------------------------------------------
+template <class T> struct Vort {   // the three relative-vorticity components and ∇b, all at fff
+  const Ctx<T>& X;
+  OCB_X Vort(const Ctx<T>& x) : X(x) {}
+  OCB_X T dwdy(int i, int j, int k) const { return T(0.5) * (X.dyw_cff(i - 1, j, k) + X.dyw_cff(i, j, k)); }
+  OCB_X T dvdz(int i, int j, int k) const { return T(0.5) * (X.dzv_cff(i - 1, j, k) + X.dzv_cff(i, j, k)); }
+  OCB_X T dudz(int i, int j, int k) const { return T(0.5) * (X.dzu_fcf(i, j - 1, k) + X.dzu_fcf(i, j, k)); }
+  OCB_X T dwdx(int i, int j, int k) const { return T(0.5) * (X.dxw_fcf(i, j - 1, k) + X.dxw_fcf(i, j, k)); }
+  OCB_X T dvdx(int i, int j, int k) const { return T(0.5) * (X.dxv_ffc(i, j, k - 1) + X.dxv_ffc(i, j, k)); }
+  OCB_X T dudy(int i, int j, int k) const { return T(0.5) * (X.dyu_ffc(i, j, k - 1) + X.dyu_ffc(i, j, k)); }
+  OCB_X T dbdx(int i, int j, int k) const {
+    const HFld<T>& b = X.in.b;
+    return T(0.25) * (((b(i, j - 1, k - 1) - b(i - 1, j - 1, k - 1)) + (b(i, j, k - 1) - b(i - 1, j, k - 1))) +
+                      ((b(i, j - 1, k) - b(i - 1, j - 1, k)) + (b(i, j, k) - b(i - 1, j, k)))) * X.g.rdx;
+  }
+  OCB_X T dbdy(int i, int j, int k) const {
+    const HFld<T>& b = X.in.b;
+    return T(0.25) * (((b(i - 1, j, k - 1) - b(i - 1, j - 1, k - 1)) + (b(i, j, k - 1) - b(i, j - 1, k - 1))) +
+                      ((b(i - 1, j, k) - b(i - 1, j - 1, k)) + (b(i, j, k) - b(i, j - 1, k)))) * X.g.rdy;
+  }
+  OCB_X T dbdz(int i, int j, int k) const {
+    const HFld<T>& b = X.in.b;
+    return T(0.25) * (((b(i - 1, j - 1, k) - b(i - 1, j - 1, k - 1)) + (b(i, j - 1, k) - b(i, j - 1, k - 1))) +
+                      ((b(i - 1, j, k) - b(i - 1, j, k - 1)) + (b(i, j, k) - b(i, j, k - 1)))) * X.rdzf(k);
+  }
+};
+// rossby_number_fff  (src/FlowDiagnostics.jl:124-138); ro_bg = dWdy, dVdz, dUdz, dWdx, dUdy, dVdx
+OCB_EVAL(OCB_DIAG_RO) {
+  Vort<T> Vt(X);
+  const T* bg = X.in.ro_bg; const T* f = X.in.f;
+  T wx = (Vt.dwdy(i, j, k) + bg[0]) - (Vt.dvdz(i, j, k) + bg[1]);
+  T wy = (Vt.dudz(i, j, k) + bg[2]) - (Vt.dwdx(i, j, k) + bg[3]);
+  T wz = (Vt.dvdx(i, j, k) + bg[5]) - (Vt.dudy(i, j, k) + bg[4]);
+  return (wx * f[0] + wy * f[1] + wz * f[2]) / (f[0] * f[0] + f[1] * f[1] + f[2] * f[2]);
+} };
+// ertel_potential_vorticity_fff  (src/FlowDiagnostics.jl:216-233)
+OCB_EVAL(OCB_DIAG_EPV) {
+  Vort<T> Vt(X);
+  const T* f = X.in.f;
+  T px = (f[0] + Vt.dwdy(i, j, k) - Vt.dvdz(i, j, k)) * Vt.dbdx(i, j, k);
+  T py = (f[1] + Vt.dudz(i, j, k) - Vt.dwdx(i, j, k)) * Vt.dbdy(i, j, k);
+  T pz = (f[2] + Vt.dvdx(i, j, k) - Vt.dudy(i, j, k)) * Vt.dbdz(i, j, k);
+  return px + py + pz;
+} };
+// potential_vorticity_in_thermal_wind_fff  (src/FlowDiagnostics.jl:200-214); f = f[2]
+OCB_EVAL(OCB_DIAG_TWPV) {
+  Vort<T> Vt(X);
+  T f = X.in.f[2];
+  T barot = (f + Vt.dvdx(i, j, k) - Vt.dudy(i, j, k)) * Vt.dbdz(i, j, k);
+  T baroc = -f * (ocb_sq(Vt.dudz(i, j, k)) + ocb_sq(Vt.dvdz(i, j, k)));
+  return barot + baroc;
+} };
+// directional_ertel_potential_vorticity_fff  (src/FlowDiagnostics.jl:358-380)
+OCB_EVAL(OCB_DIAG_DEPV) {
+  Vort<T> Vt(X);
+  const T* d = X.in.dir;
+  T ox = Vt.dwdy(i, j, k) - Vt.dvdz(i, j, k), oy = Vt.dudz(i, j, k) - Vt.dwdx(i, j, k), oz = Vt.dvdx(i, j, k) - Vt.dudy(i, j, k);
+  T od = ox * d[0] + oy * d[1] + oz * d[2];
+  T bd = Vt.dbdx(i, j, k) * d[0] + Vt.dbdy(i, j, k) * d[1] + Vt.dbdz(i, j, k) * d[2];
+  return (X.in.f_dir + od) * bd;
+} };
+
+// Oceananigans viscous_flux_uᵢxⱼ = -2 ν Σᵢⱼ at ccc / ffc / fcf / cff (filtered by
+// src/FilteredKineticEnergyEquation.jl:377-387)
+OCB_EVAL(OCB_DIAG_VF11) { return T(-2) * X.nu_ccc(i, j, k) * X.s11(i, j, k); } };
+OCB_EVAL(OCB_DIAG_VF22) { return T(-2) * X.nu_ccc(i, j, k) * X.s22(i, j, k); } };
+OCB_EVAL(OCB_DIAG_VF33) { return T(-2) * X.nu_ccc(i, j, k) * X.s33(i, j, k); } };
+OCB_EVAL(OCB_DIAG_VF12) { return T(-2) * X.nu_ffc(i, j, k) * X.s12(i, j, k); } };
+OCB_EVAL(OCB_DIAG_VF13) { return T(-2) * X.nu_fcf(i, j, k) * X.s13(i, j, k); } };
+OCB_EVAL(OCB_DIAG_VF23) { return T(-2) * X.nu_cff(i, j, k) * X.s23(i, j, k); } };
+
+// filtered_dissipation_rate_ccc  (src/FilteredKineticEnergyEquation.jl:275-299): u, v, w are the
+// filtered velocities, aux[0..5] the filtered fluxes τ̄11, τ̄22, τ̄33, τ̄12(=τ̄21), τ̄13(=τ̄31), τ̄23(=τ̄32).
+template <class T> struct FepsEdges {
+  const Ctx<T>& X;
+  OCB_X FepsEdges(const Ctx<T>& x) : X(x) {}
+  // -(Ay δy ū + Ax δx v̄) τ̄12 = -2 V_ffc S̄12 τ̄12 ; the common dx dy factor is applied by the caller
+  OCB_X T e12(int i, int j, int k) const { return X.s12(i, j, k) * X.in.aux[3](i, j, k); }
+  OCB_X T e13(int i, int j, int k) const { return X.dzf(k) * (X.s13(i, j, k) * X.in.aux[4](i, j, k)); }
+  OCB_X T e23(int i, int j, int k) const { return X.dzf(k) * (X.s23(i, j, k) * X.in.aux[5](i, j, k)); }
+};
+template <class T> OCB_X T ocb_feps(const Ctx<T>& X, int i, int j, int k) {
+  FepsEdges<T> E(X);
+  T diag = X.s11(i, j, k) * X.in.aux[0](i, j, k) + X.s22(i, j, k) * X.in.aux[1](i, j, k) + X.s33(i, j, k) * X.in.aux[2](i, j, k);
+  T m12 = OCB_MEAN_XY(E.e12, i, j, k);
+  T m13 = OCB_MEAN_XZ(E.e13, i, j, k) * X.rdzc(k);
+  T m23 = OCB_MEAN_YZ(E.e23, i, j, k) * X.rdzc(k);
+  return -(diag + T(2) * (m12 + m13 + m23));
+}
+OCB_EVAL(OCB_DIAG_FEPS) { return ocb_feps(X, i, j, k); } };
+// subfilter_ke_dissipation_rate_ccc  (src/SubFilterKineticEnergyEquation.jl:92): filter(ε) - εˡ
+OCB_EVAL(OCB_DIAG_SFEPS) { return X.in.aux[6](i, j, k) - ocb_feps(X, i, j, k); } };
+// subfilter_kinetic_energy_ccc  (src/SubFilterKineticEnergyEquation.jl:29): filter(K) - K(ū)
+OCB_EVAL(OCB_DIAG_SFKE) { return X.in.aux[6](i, j, k) - ocb_ke(X, i, j, k); } };
+
+// cross_scale_ke_flux_ccc  (src/FilteredKineticEnergyEquation.jl:176-188): Π = -Σ wᵢⱼ ⟨τᵢⱼ⟩ᶜ ⟨S̄ᵢⱼ⟩ᶜ with
+// τᵢⱼ = aux_ij - ūᵢūⱼ at its staggered location, every factor brought to ccc by two-point means.
+template <class T> struct PiEdges {
+  const Ctx<T>& X;
+  OCB_X PiEdges(const Ctx<T>& x) : X(x) {}
+  OCB_X T t11(int i, int j, int k) const { return X.in.aux[0](i, j, k) - ocb_sq(X.u(i, j, k)); }   // fcc
+  OCB_X T t22(int i, int j, int k) const { return X.in.aux[1](i, j, k) - ocb_sq(X.v(i, j, k)); }   // cfc
+  OCB_X T t33(int i, int j, int k) const { return X.in.aux[2](i, j, k) - ocb_sq(X.w(i, j, k)); }   // ccf
+  OCB_X T t12(int i, int j, int k) const { return X.in.aux[3](i, j, k) - Eval<T, OCB_DIAG_T12>::at(X, 0, i, j, k); }
+  OCB_X T t13(int i, int j, int k) const { return X.in.aux[4](i, j, k) - Eval<T, OCB_DIAG_T13>::at(X, 0, i, j, k); }
+  OCB_X T t23(int i, int j, int k) const { return X.in.aux[5](i, j, k) - Eval<T, OCB_DIAG_T23>::at(X, 0, i, j, k); }
+  OCB_X T s12(int i, int j, int k) const { return X.s12(i, j, k); }
+  OCB_X T s13(int i, int j, int k) const { return X.s13(i, j, k); }
+  OCB_X T s23(int i, int j, int k) const { return X.s23(i, j, k); }
+};
+OCB_EVAL(OCB_DIAG_PI) {
+  PiEdges<T> E(X);
+  const bool d1 = flags & OCB_REQ_TENSOR_DIM1, d2 = flags & OCB_REQ_TENSOR_DIM2, d3 = flags & OCB_REQ_TENSOR_DIM3;
+  const bool col = flags & OCB_REQ_COLLOCATED;
+  T s = T(0);
+  if (d1) s += (col ? X.in.aux[0](i, j, k) - Eval<T, OCB_DIAG_T11C>::at(X, 0, i, j, k) : T(0.5) * (E.t11(i, j, k) + E.t11(i + 1, j, k))) * X.s11(i, j, k);
+  if (d2) s += (col ? X.in.aux[1](i, j, k) - Eval<T, OCB_DIAG_T22C>::at(X, 0, i, j, k) : T(0.5) * (E.t22(i, j, k) + E.t22(i, j + 1, k))) * X.s22(i, j, k);
+  if (d3) s += (col ? X.in.aux[2](i, j, k) - Eval<T, OCB_DIAG_T33C>::at(X, 0, i, j, k) : T(0.5) * (E.t33(i, j, k) + E.t33(i, j, k + 1))) * X.s33(i, j, k);
+  if (d1 && d2) s += T(2) * OCB_MEAN_XY(E.t12, i, j, k) * OCB_MEAN_XY(E.s12, i, j, k);
+  if (d1 && d3) s += T(2) * OCB_MEAN_XZ(E.t13, i, j, k) * OCB_MEAN_XZ(E.s13, i, j, k);
+  if (d2 && d3) s += T(2) * OCB_MEAN_YZ(E.t23, i, j, k) * OCB_MEAN_YZ(E.s23, i, j, k);
+  return -s;
+} };
+
+// minus_bz✶_ccc  (src/BackgroundPotentialEnergyEquation.jl:852)
+OCB_EVAL(OCB_DIAG_BPE) { return -X.in.b(i, j, k) * X.in.aux[6](i, j, k); } };
+// local_ape_ccc  (src/AvailablePotentialEnergyEquation.jl:42-45): Ψδ - b (z - z✶)
+OCB_EVAL(OCB_DIAG_APE) { return X.in.aux[5](i, j, k) - X.in.b(i, j, k) * (OCB_LD(X.g.zc + k) - X.in.aux[6](i, j, k)); } };
+
+// ---- dispatch -------------------------------------------------------------------------------------------------
+#define OCB_FOR_EACH_DIAG(M) \
+  M(OCB_DIAG_KE) M(OCB_DIAG_ADV) M(OCB_DIAG_PR) M(OCB_DIAG_WB) M(OCB_DIAG_EPS) M(OCB_DIAG_EPS_ISO) M(OCB_DIAG_TKE) \
+  M(OCB_DIAG_SPX) M(OCB_DIAG_SPY) M(OCB_DIAG_SPZ) M(OCB_DIAG_SP) M(OCB_DIAG_CHI) M(OCB_DIAG_CDIFF) M(OCB_DIAG_SMOD) \
+  M(OCB_DIAG_OMOD) M(OCB_DIAG_Q) M(OCB_DIAG_S11) M(OCB_DIAG_S22) M(OCB_DIAG_S33) M(OCB_DIAG_S12) M(OCB_DIAG_S13) \
+  M(OCB_DIAG_S23) M(OCB_DIAG_O12) M(OCB_DIAG_O13) M(OCB_DIAG_O23) M(OCB_DIAG_T11) M(OCB_DIAG_T22) M(OCB_DIAG_T33) \
+  M(OCB_DIAG_T11C) M(OCB_DIAG_T22C) M(OCB_DIAG_T33C) M(OCB_DIAG_T12) M(OCB_DIAG_T13) M(OCB_DIAG_T23) M(OCB_DIAG_RI) \
+  M(OCB_DIAG_RO) M(OCB_DIAG_EPV) M(OCB_DIAG_TWPV) M(OCB_DIAG_DEPV) M(OCB_DIAG_VF11) M(OCB_DIAG_VF22) M(OCB_DIAG_VF33) \
+  M(OCB_DIAG_VF12) M(OCB_DIAG_VF13) M(OCB_DIAG_VF23) M(OCB_DIAG_FEPS) M(OCB_DIAG_SFEPS) M(OCB_DIAG_SFKE) M(OCB_DIAG_PI) \
+  M(OCB_DIAG_BPE) M(OCB_DIAG_APE)
+
+// volume element at a request's location (Integral(op) = Σ op·V, Oceananigans Reduction(sum!, op * V))
+template <class T>
+OCB_X double ocb_cell_volume(const DGrid<T>& g, int locz, int k) {
+  T dz = (locz == OCB_FACE) ? OCB_LD(g.dzf + k) : OCB_LD(g.dzc + k);
+  return (double)g.dx * (double)g.dy * (double)dz;
+}

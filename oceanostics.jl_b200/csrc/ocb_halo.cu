@@ -1,0 +1,227 @@
+// Halo fill (Oceananigans BoundaryConditions.fill_halo_regions! with default boundary conditions), the
+// pointwise Field(a ∘ b) helper, and the y-slab halo pack / unpack used by the multi-GPU exchange.
+// The reference calls fill_halo_regions! after every overridden compute! (src/SpatialFilters/SpatialFilters.jl:375,
+// src/BackgroundPotentialEnergyEquation.jl:615); these kernels are that step for device-resident parents.
+#include "ocb_common.cuh"
+#include <math.h>
+
+// One pass per axis, in x, y, z order (later axes also cover the corners written by earlier ones).
+// mode: 0 periodic wrap of all H layers; 1 mirror the first layer (no-flux, optional gradient in z);
+//       2 wall-normal face: zero the two boundary faces.
+template <class T>
+__global__ void ocb_fill_halo_axis_kernel(T* __restrict__ data, long long s_ax, long long s_a, long long s_b,
+                                          int n_a, int n_b, int H, int ext, int mode, T g_lo, T g_hi, int use_g_lo, int use_g_hi) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= (long long)n_a * n_b) return;
+  const int a = (int)(t % n_a), b = (int)(t / n_a);
+  T* col = data + a * s_a + b * s_b;   // parent-array column along the filled axis (parent index m = 0 .. ext+2H-1)
+  if (mode == 0) {
+    for (int m = 0; m < H; ++m) {
+      col[(long long)(H - 1 - m) * s_ax] = col[(long long)(H + ext - 1 - m) * s_ax];
+      col[(long long)(H + ext + m) * s_ax] = col[(long long)(H + m) * s_ax];
+    }
+  } else if (mode == 1) {
+    const T lo = col[(long long)H * s_ax], hi = col[(long long)(H + ext - 1) * s_ax];
+    col[(long long)(H - 1) * s_ax] = use_g_lo ? lo - g_lo : lo;
+    col[(long long)(H + ext) * s_ax] = use_g_hi ? hi + g_hi : hi;
+  } else {
+    col[(long long)H * s_ax] = T(0);
+    col[(long long)(H + ext - 1) * s_ax] = T(0);
+  }
+}
+
+template <class T>
+static int fill_halo_impl(const ocb_grid* g, const ocb_field* f, int impenetrable, double zg_bot, double zg_top,
+                          const double dzf_bot, const double dzf_top, cudaStream_t st) {
+  for (int d = 0; d < 3; ++d) {
+    if (f->loc[d] == OCB_NOTHING) continue;
+    const int H = f->halo[d];
+    const int ext = f->size[d] - 2 * H;
+    OCB_REQUIRE(H >= 1 && ext >= 1, "fill_halo: bad halo/size along axis %d", d + 1);
+    const int a = d == 0 ? 1 : 0, b = d == 2 ? 1 : 2;   // x-most remaining axis fastest across threads
+    const int n_a = f->size[a], n_b = f->size[b];
+    int mode;
+    if (g->topo[d] == OCB_PERIODIC) mode = 0;
+    else if (f->loc[d] == OCB_CENTER) mode = 1;
+    else { if (!impenetrable) continue; mode = 2; }
+    if (mode == 0) OCB_REQUIRE(ext >= H, "fill_halo: periodic axis %d shorter than its halo", d + 1);
+    const bool glo = (d == 2 && mode == 1 && !isnan(zg_bot)), ghi = (d == 2 && mode == 1 && !isnan(zg_top));
+    const long long total = (long long)n_a * n_b;
+    ocb_fill_halo_axis_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        (T*)f->data, f->stride[d], f->stride[a], f->stride[b], n_a, n_b, H, ext, mode,
+        T(glo ? zg_bot * dzf_bot : 0.0), T(ghi ? zg_top * dzf_top : 0.0), glo, ghi);
+    OCB_CUDA(cudaGetLastError());
+  }
+  return OCB_OK;
+}
+
+extern "C" int ocb_fill_halo(const ocb_grid* grid, const ocb_field* field, int32_t impenetrable, double zgrad_bottom,
+                             double zgrad_top, void* stream) {
+  OCB_REQUIRE(grid && field && field->data && field->kind == OCB_FIELD_ARRAY, "ocb_fill_halo: needs an array field");
+  int rc = ocb_require_device();
+  if (rc != OCB_OK) return rc;
+  // gradient BCs need Δzᶠ at the two boundary faces: uniform spacing, or (stretched) the host passes the
+  // already-multiplied increments by using a uniform-equivalent d[2]; here only the uniform case reads d[2].
+  double dz_bot = grid->d[2], dz_top = grid->d[2];
+  if (grid->dzf && (!isnan(zgrad_bottom) || !isnan(zgrad_top))) {
+    // stretched: fetch Δzᶠ[1] and Δzᶠ[Nz+1] (one small synchronous copy; gradient BCs are a set-up time path)
+    const int Hz = grid->H[2];
+    const size_t es = ocb_sizeof(grid->dtype);
+    char lo[8], hi[8];
+    OCB_CUDA(cudaMemcpy(lo, (const char*)grid->dzf + es * (size_t)Hz, es, cudaMemcpyDeviceToHost));
+    OCB_CUDA(cudaMemcpy(hi, (const char*)grid->dzf + es * (size_t)(Hz + grid->N[2]), es, cudaMemcpyDeviceToHost));
+    dz_bot = grid->dtype == OCB_F64 ? *(double*)lo : (double)*(float*)lo;
+    dz_top = grid->dtype == OCB_F64 ? *(double*)hi : (double)*(float*)hi;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  return grid->dtype == OCB_F64 ? fill_halo_impl<double>(grid, field, impenetrable, zgrad_bottom, zgrad_top, dz_bot, dz_top, st)
+                                : fill_halo_impl<float>(grid, field, impenetrable, zgrad_bottom, zgrad_top, dz_bot, dz_top, st);
+}
+
+// ---- pointwise: dst = alpha * (a ∘ b), each operand brought to dst's location by two-point means ---------
+template <class T>
+struct PwOperand {
+  const T* p; long long s[3]; T c; int shift[3];   // shift: 0 same location, +1 operand is Face & dst Center (mean of i, i+1),
+};                                                  //        -1 operand is Center & dst Face (mean of i-1, i)
+
+template <class T>
+__device__ __forceinline__ T pw_fetch(const PwOperand<T>& o, int i, int j, int k) {
+  if (!o.p) return o.c;
+  T acc = T(0);
+  const int nx = o.shift[0] ? 2 : 1, ny = o.shift[1] ? 2 : 1, nz = o.shift[2] ? 2 : 1;
+  // nested two-point means, x innermost (the order Oceananigans composes ℑx, ℑy, ℑz)
+  T zacc = T(0);
+  for (int c = 0; c < nz; ++c) {
+    const int kk = k + (o.shift[2] > 0 ? c : (o.shift[2] < 0 ? c - 1 : 0));
+    T yacc = T(0);
+    for (int b = 0; b < ny; ++b) {
+      const int jj = j + (o.shift[1] > 0 ? b : (o.shift[1] < 0 ? b - 1 : 0));
+      T xacc = T(0);
+      for (int a = 0; a < nx; ++a) {
+        const int ii = i + (o.shift[0] > 0 ? a : (o.shift[0] < 0 ? a - 1 : 0));
+        xacc += __ldg(o.p + ii * o.s[0] + jj * o.s[1] + kk * o.s[2]);
+      }
+      yacc += nx == 2 ? T(0.5) * xacc : xacc;
+    }
+    zacc += ny == 2 ? T(0.5) * yacc : yacc;
+  }
+  acc = nz == 2 ? T(0.5) * zacc : zacc;
+  return acc;
+}
+
+template <class T>
+__global__ void ocb_pointwise_kernel(int op, T alpha, PwOperand<T> A, PwOperand<T> B, T* __restrict__ dst, long long d0,
+                                     long long d1, long long d2, int nx, int ny, int nz) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  if (i > nx || j > ny) return;
+  for (int k = blockIdx.z + 1; k <= nz; k += gridDim.z) {
+    const T a = pw_fetch(A, i, j, k);
+    T r = a;
+    if (op != OCB_OP_COPY) {
+      const T b = pw_fetch(B, i, j, k);
+      r = op == OCB_OP_ADD ? a + b : (op == OCB_OP_SUB ? a - b : a * b);
+    }
+    dst[i * d0 + j * d1 + k * d2] = alpha * r;
+  }
+}
+
+template <class T>
+static int make_pw_operand(const ocb_field* f, const ocb_field* dst, PwOperand<T>* o, const char* name) {
+  HFld<T> h;
+  int rc = make_fld<T>(*f, &h, name);
+  if (rc != OCB_OK) return rc;
+  o->p = h.p; o->s[0] = h.sx; o->s[1] = h.sy; o->s[2] = h.sz; o->c = h.c;
+  for (int d = 0; d < 3; ++d) {
+    o->shift[d] = 0;
+    if (!h.p || f->loc[d] == OCB_NOTHING || dst->loc[d] == OCB_NOTHING || f->loc[d] == dst->loc[d]) continue;
+    o->shift[d] = (f->loc[d] == OCB_FACE) ? 1 : -1;
+  }
+  return OCB_OK;
+}
+
+template <class T>
+static int pointwise_impl(const ocb_grid* g, int op, double alpha, const ocb_field* a, const ocb_field* b,
+                          const ocb_field* dst, cudaStream_t st) {
+  PwOperand<T> A, B;
+  memset(&B, 0, sizeof(B));
+  int rc = make_pw_operand<T>(a, dst, &A, "a");
+  if (rc != OCB_OK) return rc;
+  if (op != OCB_OP_COPY) {
+    OCB_REQUIRE(b, "ocb_pointwise: binary op needs operand b");
+    rc = make_pw_operand<T>(b, dst, &B, "b");
+    if (rc != OCB_OK) return rc;
+  }
+  HFld<T> D;
+  rc = make_fld<T>(*dst, &D, "dst", false);
+  if (rc != OCB_OK) return rc;
+  OCB_REQUIRE(D.p, "ocb_pointwise: dst must be an array field");
+  int n[3];
+  for (int d = 0; d < 3; ++d) n[d] = dst->loc[d] == OCB_NOTHING ? 1 : dst->size[d] - 2 * dst->halo[d];
+  dim3 block(32, 8, 1), grid((n[0] + 31) / 32, (n[1] + 7) / 8, n[2] < 64 ? n[2] : 64);
+  ocb_pointwise_kernel<T><<<grid, block, 0, st>>>(op, T(alpha), A, B, (T*)D.p, D.sx, D.sy, D.sz, n[0], n[1], n[2]);
+  OCB_CUDA(cudaGetLastError());
+  (void)g;
+  return OCB_OK;
+}
+
+extern "C" int ocb_pointwise(const ocb_grid* grid, int32_t op, double alpha, const ocb_field* a, const ocb_field* b,
+                             const ocb_field* dst, void* stream) {
+  OCB_REQUIRE(grid && a && dst, "ocb_pointwise: null argument");
+  OCB_REQUIRE(op >= OCB_OP_COPY && op <= OCB_OP_MUL, "ocb_pointwise: unknown op %d", op);
+  int rc = ocb_require_device();
+  if (rc != OCB_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  return grid->dtype == OCB_F64 ? pointwise_impl<double>(grid, op, alpha, a, b, dst, st)
+                                : pointwise_impl<float>(grid, op, alpha, a, b, dst, st);
+}
+
+// ---- y-slab halo pack / unpack ---------------------------------------------------------------------------------
+// side 0: the h interior planes next to the low-y edge (pack) / the h halo planes below it (unpack);
+// side 1: likewise at the high-y edge.  Buffer layout: [z][plane][x] contiguous, whole parent rows in x and z.
+template <class T, bool PACK>
+__global__ void ocb_pack_y_kernel(T* __restrict__ data, T* __restrict__ buf, long long sx, long long sy, long long sz,
+                                  int nx, int nz, int h, int j0) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long total = (long long)nx * h * nz;
+  if (t >= total) return;
+  const int x = (int)(t % nx);
+  const int p = (int)((t / nx) % h);
+  const int z = (int)(t / ((long long)nx * h));
+  T* cell = data + x * sx + (long long)(j0 + p) * sy + z * sz;
+  if (PACK) buf[t] = *cell; else *cell = buf[t];
+}
+
+template <class T>
+static int pack_impl(const ocb_field* f, int side, int h, void* buffer, bool pack, cudaStream_t st) {
+  const int Hy = f->halo[1], ext = f->size[1] - 2 * Hy;
+  OCB_REQUIRE(h >= 1 && h <= Hy && h <= ext, "halo pack: h=%d must be within 1..min(halo=%d, extent=%d)", h, Hy, ext);
+  int j0;   // parent index of the first plane
+  if (pack) j0 = side == 0 ? Hy : Hy + ext - h;
+  else      j0 = side == 0 ? Hy - h : Hy + ext;
+  const long long total = (long long)f->size[0] * h * f->size[2];
+  if (pack)
+    ocb_pack_y_kernel<T, true><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((T*)f->data, (T*)buffer, f->stride[0], f->stride[1],
+                                                                               f->stride[2], f->size[0], f->size[2], h, j0);
+  else
+    ocb_pack_y_kernel<T, false><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((T*)f->data, (T*)buffer, f->stride[0], f->stride[1],
+                                                                                f->stride[2], f->size[0], f->size[2], h, j0);
+  OCB_CUDA(cudaGetLastError());
+  return OCB_OK;
+}
+
+extern "C" int ocb_halo_pack_y(int32_t dtype, const ocb_field* field, int32_t side, int32_t h, void* buffer, void* stream) {
+  OCB_REQUIRE(field && field->data && buffer && (side == 0 || side == 1), "ocb_halo_pack_y: bad argument");
+  int rc = ocb_require_device();
+  if (rc != OCB_OK) return rc;
+  return dtype == OCB_F64 ? pack_impl<double>(field, side, h, buffer, true, (cudaStream_t)stream)
+                          : pack_impl<float>(field, side, h, buffer, true, (cudaStream_t)stream);
+}
+
+extern "C" int ocb_halo_unpack_y(int32_t dtype, const ocb_field* field, int32_t side, int32_t h, const void* buffer, void* stream) {
+  OCB_REQUIRE(field && field->data && buffer && (side == 0 || side == 1), "ocb_halo_unpack_y: bad argument");
+  int rc = ocb_require_device();
+  if (rc != OCB_OK) return rc;
+  return dtype == OCB_F64 ? pack_impl<double>(field, side, h, (void*)buffer, false, (cudaStream_t)stream)
+                          : pack_impl<float>(field, side, h, (void*)buffer, false, (cudaStream_t)stream);
+}

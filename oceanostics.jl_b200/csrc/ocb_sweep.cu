@@ -1,0 +1,263 @@
+// K1: the fused multi-diagnostic stencil sweep -- plan object, the generic kernel (any mix of the
+// OCB_DIAG_* requests, any operand kind, stretched z, Float32/Float64) and the dispatch to the
+// register-pipelined budget kernel (ocb_sweep_fused.cu) when a plan matches its envelope.
+//
+// Replaces, per plan, what the reference does with one Oceananigans launch per KernelFunctionOperation
+// (`launch!(arch, grid, params, _compute!, data, op)`) plus one `sum!` sweep per Integral
+// (the explicit form of that recipe is src/SpatialFilters/SpatialFilters.jl:325-330).
+#include "ocb_sweep_plan.cuh"
+#include "ocb_sweep_fused.cuh"
+#include <new>
+
+// ---- z metric tables -------------------------------------------------------------------------------------
+// table entry m <-> k = m + 1 - Hz, m = 0 .. Nz + 2Hz  (Nz + 2Hz + 1 entries per table)
+template <class T>
+__global__ void ocb_ztables_kernel(int n, int Hz, T dz_uniform, T z_bottom, const T* __restrict__ dzc_in,
+                                   const T* __restrict__ dzf_in, const T* __restrict__ zc_in, const T* __restrict__ zf_in,
+                                   T* __restrict__ tab) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n) return;
+  const int k = m + 1 - Hz;
+  T dzc, dzf, zc, zf;
+  if (dzc_in) {
+    const int mc = m < n - 1 ? m : n - 2;   // Δzᵃᵃᶜ / zᵃᵃᶜ have one entry fewer: repeat the last
+    dzc = dzc_in[mc]; zc = zc_in ? zc_in[mc] : T(0);
+    dzf = dzf_in[m];  zf = zf_in ? zf_in[m] : T(0);
+  } else {
+    dzc = dzf = dz_uniform;
+    zf = z_bottom + dz_uniform * T(k - 1);
+    zc = z_bottom + dz_uniform * (T(k) - T(0.5));
+  }
+  tab[0 * n + m] = dzc; tab[1 * n + m] = dzf;
+  tab[2 * n + m] = T(1) / dzc; tab[3 * n + m] = T(1) / dzf;
+  tab[4 * n + m] = zc; tab[5 * n + m] = zf;
+}
+
+// ---- generic kernel --------------------------------------------------------------------------------------
+template <class T, int DIAG>
+__device__ __forceinline__ void ocb_run_request(const SweepParams<T>& P, const DReq& r, int i, int j, int k0, int k1,
+                                                double* sh, int blk) {
+  Ctx<T> X(P.g, P.in, (r.flags & OCB_REQ_PERTURBATION) != 0);
+  const bool in_ij = i >= r.lo[0] && i <= r.hi[0] && j >= r.lo[1] && j <= r.hi[1];
+  const int ka = k0 > r.lo[2] ? k0 : r.lo[2];
+  const int kb = k1 < r.hi[2] ? k1 : r.hi[2];
+  double acc = 0.0;
+  if (in_ij) {
+    T* out = (T*)r.out;
+    const long long base = i * r.os[0] + j * r.os[1];
+    for (int k = ka; k <= kb; ++k) {
+      const T val = Eval<T, DIAG>::at(X, r.flags, i, j, k);
+      if (out) out[base + k * r.os[2]] = val;
+      if (r.slot >= 0) acc += (double)val * ocb_cell_volume(P.g, r.loc[2], k);
+    }
+  }
+  if (r.slot >= 0) {   // uniform across the block
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    __syncthreads();
+    if (lane == 0) sh[warp] = acc;
+    __syncthreads();
+    if (tid == 0) {
+      double s = 0.0;
+      const int nw = (blockDim.x * blockDim.y) >> 5;
+      for (int w = 0; w < nw; ++w) s += sh[w];
+      P.partial[(size_t)blk * P.nslots + r.slot] = s;
+    }
+  }
+}
+
+template <class T>
+__global__ void __launch_bounds__(256) ocb_sweep_generic_kernel(const __grid_constant__ SweepParams<T> P) {
+  __shared__ double sh[8];
+  const int i = P.lo[0] + blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = P.lo[1] + blockIdx.y * blockDim.y + threadIdx.y;
+  const int k0 = P.lo[2] + blockIdx.z * P.kchunk;
+  const int k1 = min(k0 + P.kchunk - 1, P.hi[2]);
+  const int blk = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  for (int r = 0; r < P.nreq; ++r) {
+    const DReq& R = P.req[r];
+    switch (R.diag) {
+#define OCB_CASE(D) case D: ocb_run_request<T, D>(P, R, i, j, k0, k1, sh, blk); break;
+      OCB_FOR_EACH_DIAG(OCB_CASE)
+#undef OCB_CASE
+      default: break;
+    }
+  }
+}
+
+// ---- plan ------------------------------------------------------------------------------------------------
+struct ocb_plan {
+  int dtype;
+  int variant;            // 0 = generic kernel, 1 = register-pipelined budget kernel
+  SweepParams<double> p64;
+  SweepParams<float> p32;
+  void* ztab;             // library-owned z metric tables
+  double* partial;        // per-block partial integrals
+  dim3 grid, block;
+  int nblocks;
+  int n_launches;
+  double algorithmic_bytes;
+  ocb_fused_plan* fused;
+};
+
+template <class T>
+static int build_ztables(const ocb_grid* grid, void** ztab_out, ZTables<T>* zt) {
+  const int Hz = grid->H[2], n = grid->N[2] + 2 * Hz + 1;
+  T* tab = nullptr;
+  OCB_CUDA(cudaMalloc(&tab, sizeof(T) * 6 * n));
+  if (grid->dzc || grid->dzf) OCB_REQUIRE(grid->dzc && grid->dzf, "a stretched z axis needs both dzc and dzf");
+  ocb_ztables_kernel<T><<<(n + 127) / 128, 128>>>(n, Hz, T(grid->d[2]), T(grid->z_bottom), (const T*)grid->dzc, (const T*)grid->dzf,
+                                                 (const T*)grid->zc, (const T*)grid->zf, tab);
+  OCB_CUDA(cudaGetLastError());
+  const int off = Hz - 1;   // table[k] = tab[k + Hz - 1]
+  zt->dzc = tab + 0 * n + off; zt->dzf = tab + 1 * n + off; zt->rdzc = tab + 2 * n + off; zt->rdzf = tab + 3 * n + off;
+  zt->zc = tab + 4 * n + off;  zt->zf = tab + 5 * n + off;
+  *ztab_out = tab;
+  return OCB_OK;
+}
+
+static double count_algorithmic_bytes(const ocb_grid* g, const ocb_sweep_inputs* in, const ocb_request* reqs, int n) {
+  // (distinct full-size input fields read + output fields written) * sizeof(FT) * Nx*Ny*Nz
+  bool use[16] = {false};   // u v w b p U V W B aux0..6
+  auto mark_uvw = [&]() { use[0] = use[1] = use[2] = true; };
+  for (int r = 0; r < n; ++r) {
+    const int d = reqs[r].diag;
+    const bool pert = reqs[r].flags & OCB_REQ_PERTURBATION;
+    switch (d) {
+      case OCB_DIAG_PR: mark_uvw(); use[4] = true; break;
+      case OCB_DIAG_WB: mark_uvw(); use[3] = true; break;
+      case OCB_DIAG_CHI: case OCB_DIAG_CDIFF: use[3] = true; if (pert) use[8] = true; break;
+      case OCB_DIAG_RI: case OCB_DIAG_EPV: case OCB_DIAG_DEPV: case OCB_DIAG_TWPV: mark_uvw(); use[3] = true; break;
+      case OCB_DIAG_BPE: use[3] = true; use[15] = true; break;
+      case OCB_DIAG_APE: use[3] = true; use[14] = use[15] = true; break;
+      case OCB_DIAG_FEPS: case OCB_DIAG_PI: mark_uvw(); for (int a = 0; a < 6; ++a) use[9 + a] = true; break;
+      case OCB_DIAG_SFEPS: mark_uvw(); for (int a = 0; a < 7; ++a) use[9 + a] = true; break;
+      case OCB_DIAG_SFKE: mark_uvw(); use[15] = true; break;
+      default: mark_uvw(); break;
+    }
+    if (pert || d == OCB_DIAG_TKE || (d >= OCB_DIAG_SPX && d <= OCB_DIAG_SP)) use[5] = use[6] = use[7] = true;
+  }
+  const ocb_field* f[16] = {&in->u, &in->v, &in->w, &in->b, &in->p, &in->U, &in->V, &in->W, &in->B,
+                            &in->aux[0], &in->aux[1], &in->aux[2], &in->aux[3], &in->aux[4], &in->aux[5], &in->aux[6]};
+  int nin = 0;
+  for (int a = 0; a < 16; ++a) {
+    if (!use[a] || f[a]->kind != OCB_FIELD_ARRAY || !f[a]->data) continue;
+    bool full = true;
+    for (int d = 0; d < 3; ++d) if (f[a]->loc[d] == OCB_NOTHING) full = false;
+    if (full) ++nin;
+  }
+  bool eddy = false;
+  for (int r = 0; r < n; ++r) {
+    const int d = reqs[r].diag;
+    if (d == OCB_DIAG_EPS || d == OCB_DIAG_EPS_ISO || d == OCB_DIAG_CHI || d == OCB_DIAG_CDIFF || (d >= OCB_DIAG_VF11 && d <= OCB_DIAG_VF23)) eddy = true;
+  }
+  if (eddy) {   // count each distinct eddy field once
+    const void* seen[2 * OCB_MAX_CLOSURE_FIELDS]; int ns = 0;
+    auto add = [&](const ocb_field& fld) { for (int s = 0; s < ns; ++s) if (seen[s] == fld.data) return; seen[ns++] = fld.data; ++nin; };
+    for (int a = 0; a < in->closure.n_nu_fields; ++a) add(in->closure.nu_fields[a]);
+    for (int a = 0; a < in->closure.n_kappa_fields; ++a) add(in->closure.kappa_fields[a]);
+  }
+  int nout = 0;
+  for (int r = 0; r < n; ++r) if (reqs[r].out) ++nout;
+  return (double)(nin + nout) * (double)ocb_sizeof(g->dtype) * (double)g->N[0] * (double)g->N[1] * (double)g->N[2];
+}
+
+template <class T>
+static int finish_plan(ocb_plan* pl, const ocb_grid* grid, const ocb_sweep_inputs* in, const ocb_request* reqs, int n,
+                       SweepParams<T>* P) {
+  ZTables<T> zt;
+  int rc = build_ztables<T>(grid, &pl->ztab, &zt);
+  if (rc != OCB_OK) return rc;
+  rc = ocb_build_sweep_params<T>(grid, in, reqs, n, zt, P);
+  if (rc != OCB_OK) return rc;
+  // launch geometry of the generic kernel
+  const int ni = P->hi[0] - P->lo[0] + 1, nj = P->hi[1] - P->lo[1] + 1, nk = P->hi[2] - P->lo[2] + 1;
+  pl->block = dim3(32, 8, 1);
+  const int gx = (ni + 31) / 32, gy = (nj + 7) / 8;
+  const int target = ocb_sm_count() * 16;
+  int gz = (target + gx * gy - 1) / (gx * gy);
+  if (gz > nk) gz = nk;
+  if (gz < 1) gz = 1;
+  int kchunk = (nk + gz - 1) / gz;
+  if (kchunk > 128) kchunk = 128;
+  gz = (nk + kchunk - 1) / kchunk;
+  P->kchunk = kchunk;
+  pl->grid = dim3(gx, gy, gz);
+  pl->nblocks = gx * gy * gz;
+  pl->variant = 0;
+  pl->n_launches = 1 + (P->nslots > 0 ? 1 : 0);
+  // the register-pipelined budget kernel takes the plan when it fits its envelope
+  pl->fused = nullptr;
+  rc = ocb_fused_try_create(grid, in, reqs, n, *P, &pl->fused);
+  if (rc != OCB_OK) return rc;
+  int nblocks = pl->nblocks;
+  if (pl->fused) {
+    pl->variant = 1;
+    nblocks = ocb_fused_nblocks(pl->fused);
+    pl->nblocks = nblocks;
+  }
+  if (P->nslots > 0) {
+    OCB_CUDA(cudaMalloc(&pl->partial, sizeof(double) * (size_t)nblocks * P->nslots));
+    OCB_CUDA(cudaMemset(pl->partial, 0, sizeof(double) * (size_t)nblocks * P->nslots));
+    P->partial = pl->partial;
+  }
+  OCB_CUDA(cudaDeviceSynchronize());   // plan creation (not execution) may block: tables are ready afterwards
+  return OCB_OK;
+}
+
+extern "C" int ocb_plan_create(const ocb_grid* grid, const ocb_sweep_inputs* inputs, const ocb_request* requests,
+                               int32_t n_requests, ocb_plan** plan_out) {
+  OCB_REQUIRE(grid && inputs && requests && plan_out, "ocb_plan_create: null argument");
+  OCB_REQUIRE(grid->dtype == OCB_F32 || grid->dtype == OCB_F64, "grid dtype must be OCB_F32 or OCB_F64");
+  int rc = ocb_require_device();
+  if (rc != OCB_OK) return rc;
+  ocb_plan* pl = new (std::nothrow) ocb_plan();
+  if (!pl) OCB_FAIL(OCB_ERR_ALLOC, "out of host memory");
+  memset((void*)pl, 0, sizeof(*pl));
+  pl->dtype = grid->dtype;
+  pl->algorithmic_bytes = count_algorithmic_bytes(grid, inputs, requests, n_requests);
+  rc = (grid->dtype == OCB_F64) ? finish_plan<double>(pl, grid, inputs, requests, n_requests, &pl->p64)
+                                : finish_plan<float>(pl, grid, inputs, requests, n_requests, &pl->p32);
+  if (rc != OCB_OK) { ocb_plan_destroy(pl); return rc; }
+  *plan_out = pl;
+  return OCB_OK;
+}
+
+extern "C" int ocb_plan_execute(ocb_plan* pl, double* integrals, void* stream) {
+  OCB_REQUIRE(pl, "ocb_plan_execute: null plan");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nslots = pl->dtype == OCB_F64 ? pl->p64.nslots : pl->p32.nslots;
+  OCB_REQUIRE(nslots == 0 || integrals, "this plan integrates %d slot(s): `integrals` must be a device double[%d]", nslots, nslots);
+  if (pl->variant == 1) {
+    int rc = ocb_fused_execute(pl->fused, pl->partial, st);
+    if (rc != OCB_OK) return rc;
+  } else if (pl->dtype == OCB_F64) {
+    ocb_sweep_generic_kernel<double><<<pl->grid, pl->block, 0, st>>>(pl->p64);
+  } else {
+    ocb_sweep_generic_kernel<float><<<pl->grid, pl->block, 0, st>>>(pl->p32);
+  }
+  OCB_CUDA(cudaGetLastError());
+  if (nslots > 0) {
+    ocb_launch_finalize_partials(pl->partial, pl->nblocks, nslots, integrals, st);
+    OCB_CUDA(cudaGetLastError());
+  }
+  return OCB_OK;
+}
+
+extern "C" int ocb_plan_destroy(ocb_plan* pl) {
+  if (!pl) return OCB_OK;
+  if (pl->fused) ocb_fused_destroy(pl->fused);
+  if (pl->ztab) cudaFree(pl->ztab);
+  if (pl->partial) cudaFree(pl->partial);
+  delete pl;
+  return OCB_OK;
+}
+
+extern "C" int ocb_plan_info(const ocb_plan* pl, int32_t* n_launches, int32_t* variant, double* algorithmic_bytes) {
+  OCB_REQUIRE(pl, "ocb_plan_info: null plan");
+  if (n_launches) *n_launches = pl->n_launches;
+  if (variant) *variant = pl->variant;
+  if (algorithmic_bytes) *algorithmic_bytes = pl->algorithmic_bytes;
+  return OCB_OK;
+}

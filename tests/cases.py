@@ -1,0 +1,97 @@
+"""The parity case table: every K1 diagnostic as (name, package constructor, oracle evaluation, location).
+Used by the host-side evaluator check (CPU container) and by the GPU parity tests (through the C ABI)."""
+from __future__ import annotations
+
+import numpy as np
+
+from helpers import ocb, K, State, OConst, OZero, DiffField, average_dims, mirror
+
+KE, TKE, TV, FD = ocb.KineticEnergyEquation, ocb.TurbulentKineticEnergyEquation, ocb.TracerVarianceEquation, ocb.FlowDiagnostics
+
+
+def build_cases(st: State, closure_name="scalar", mean="profile"):
+    """-> list of (name, package op, oracle values [i,j,k], location string)."""
+    oc, pc = st.closures()[closure_name]
+    f_cor = (1e-5, 2e-5, 1e-4)
+    m = st.model(closure=pc, coriolis=ocb.ConstantCartesianCoriolis(*f_cor))
+    og, of = st.og, st.ofields()
+    par = {"closure": oc}
+    ev = K.evaluate
+
+    # mean flow: horizontal-mean profiles U(z), V(z), W(z) (reduced fields), numbers, or none
+    if mean == "profile":
+        oU, oV, oW = average_dims(st.ou, (1, 2)), average_dims(st.ov, (1, 2)), average_dims(st.ow, (1, 2))
+        U, V, W = mirror(oU, st.pg), mirror(oV, st.pg), mirror(oW, st.pg)
+    elif mean == "number":
+        oU, oV, oW = OConst(0.3), OConst(-0.2), OConst(0.0)
+        U, V, W = 0.3, -0.2, 0.0
+    else:
+        oU, oV, oW = OZero(), OZero(), OZero()
+        U = V = W = None
+    oup, ovp, owp = DiffField(st.ou, oU), DiffField(st.ov, oV), DiffField(st.ow, oW)
+    ofp = {"u": oup, "v": ovp, "w": owp, "b": st.ob}
+    sp_args = (oup, ovp, owp, oU, oV, oW)
+    vdir = (0.0, 0.0, 1.0)
+    tilt = (np.sin(0.3), 0.0, np.cos(0.3))
+    ro_bg = dict(dWdy_bg=1e-3, dVdz_bg=2e-3, dUdz_bg=-1e-3, dWdx_bg=5e-4, dUdy_bg=3e-3, dVdx_bg=-2e-3)
+    oro = dict(ro_bg, fx=f_cor[0], fy=f_cor[1], fz=f_cor[2])
+    ddir = (0.6, 0.0, 0.8)
+    odepv = dict(dir_x=ddir[0], dir_y=ddir[1], dir_z=ddir[2], f_dir=sum(a * b for a, b in zip(f_cor, ddir)))
+    m_tilt = st.model(closure=pc, buoyancy=ocb.BuoyancyTracer(gravity_unit_vector=tuple(-t for t in tilt)))
+
+    cases = [
+        ("KineticEnergy", KE.KineticEnergy(m), ev(K.kinetic_energy_ccc, og, "ccc", st.ou, st.ov, st.ow), "ccc"),
+        ("KineticEnergyAdvection", KE.KineticEnergyAdvection(m), ev(K.ke_advection_ccc, og, "ccc", of), "ccc"),
+        ("KineticEnergyPressureRedistribution", KE.KineticEnergyPressureRedistribution(m), ev(K.ke_pressure_ccc, og, "ccc", of, st.op), "ccc"),
+        ("PotentialEnergyConversion", KE.PotentialEnergyConversion(m), ev(K.ke_buoyancy_ccc, og, "ccc", of, (0, 0, 1), st.ob), "ccc"),
+        ("PotentialEnergyConversion_tilted", KE.PotentialEnergyConversion(m_tilt), ev(K.ke_buoyancy_ccc, og, "ccc", of, tilt, st.ob), "ccc"),
+        ("DissipationRate", KE.DissipationRate(m), ev(K.viscous_dissipation_rate_ccc, og, "ccc", None, of, par), "ccc"),
+        ("DissipationRate_perturbation", KE.DissipationRate(m, U=U, V=V, W=W) if U is not None else KE.DissipationRate(m),
+         ev(K.viscous_dissipation_rate_ccc, og, "ccc", None, ofp, par), "ccc"),
+        ("KineticEnergyIsotropicDissipationRate", KE.KineticEnergyIsotropicDissipationRate(m),
+         ev(K.isotropic_viscous_dissipation_rate_ccc, og, "ccc", st.ou, st.ov, st.ow, par), "ccc"),
+        ("TurbulentKineticEnergy", TKE.TurbulentKineticEnergy(m, U=U, V=V, W=W),
+         ev(K.turbulent_kinetic_energy_ccc, og, "ccc", st.ou, st.ov, st.ow, oU, oV, oW), "ccc"),
+        ("TKEIsotropicDissipationRate", TKE.TurbulentKineticEnergyIsotropicDissipationRate(m, U=U, V=V, W=W),
+         ev(K.isotropic_viscous_dissipation_rate_ccc, og, "ccc", oup, ovp, owp, par), "ccc"),
+        ("XShearProductionRate", TKE.XShearProductionRate(m, U=U, V=V, W=W), ev(K.shear_production_rate_x_ccc, og, "ccc", *sp_args), "ccc"),
+        ("YShearProductionRate", TKE.YShearProductionRate(m, U=U, V=V, W=W), ev(K.shear_production_rate_y_ccc, og, "ccc", *sp_args), "ccc"),
+        ("ZShearProductionRate", TKE.ZShearProductionRate(m, U=U, V=V, W=W), ev(K.shear_production_rate_z_ccc, og, "ccc", *sp_args), "ccc"),
+        ("ShearProductionRate", TKE.ShearProductionRate(m, U=U, V=V, W=W), ev(K.shear_production_rate_ccc, og, "ccc", *sp_args), "ccc"),
+        ("TracerVarianceDissipationRate", TV.TracerVarianceDissipationRate(m, "b"),
+         ev(K.tracer_variance_dissipation_rate_ccc, og, "ccc", oc, None, None, st.ob), "ccc"),
+        ("TracerVarianceDiffusion", TV.TracerVarianceDiffusion(m, "b"), ev(K.c_div_q_c, og, "ccc", oc, None, None, st.ob), "ccc"),
+        ("RichardsonNumber", FD.RichardsonNumber(m), ev(K.richardson_number_ccf, og, "ccf", st.ou, st.ov, st.ow, st.ob, vdir), "ccf"),
+        ("RichardsonNumber_tilted", FD.RichardsonNumber(m_tilt), ev(K.richardson_number_ccf, og, "ccf", st.ou, st.ov, st.ow, st.ob, tilt), "ccf"),
+        ("RossbyNumber", FD.RossbyNumber(m, **ro_bg), ev(K.rossby_number_fff, og, "fff", st.ou, st.ov, st.ow, oro), "fff"),
+        ("ErtelPotentialVorticity", FD.ErtelPotentialVorticity(m), ev(K.ertel_potential_vorticity_fff, og, "fff", st.ou, st.ov, st.ow, st.ob, *f_cor), "fff"),
+        ("ErtelPotentialVorticity_thermal_wind", FD.ErtelPotentialVorticity(m, thermal_wind=True),
+         ev(K.potential_vorticity_in_thermal_wind_fff, og, "fff", st.ou, st.ov, st.ob, f_cor[2]), "fff"),
+        ("DirectionalErtelPotentialVorticity", FD.DirectionalErtelPotentialVorticity(m, ddir),
+         ev(K.directional_ertel_potential_vorticity_fff, og, "fff", st.ou, st.ov, st.ow, st.ob, odepv), "fff"),
+        ("StrainRateTensorModulus", FD.StrainRateTensorModulus(m), ev(K.strain_rate_tensor_modulus_ccc, og, "ccc", st.ou, st.ov, st.ow), "ccc"),
+        ("VorticityTensorModulus", FD.VorticityTensorModulus(m), ev(K.vorticity_tensor_modulus_ccc, og, "ccc", st.ou, st.ov, st.ow), "ccc"),
+        ("QVelocityGradientTensorInvariant", FD.QVelocityGradientTensorInvariant(m),
+         ev(K.Q_velocity_gradient_tensor_invariant_ccc, og, "ccc", st.ou, st.ov, st.ow), "ccc"),
+    ]
+    S, O = FD.StrainRateTensor(m), FD.VorticityTensor(m)
+    T, Tc = FD.StressTensor(m), FD.StressTensor(m, collocate_diagonals=True)
+    comp_args = {(1, 1): (st.ou,), (2, 2): (st.ov,), (3, 3): (st.ow,), (1, 2): (st.ou, st.ov), (1, 3): (st.ou, st.ow), (2, 3): (st.ov, st.ow)}
+    comp_loc = {(1, 1): "ccc", (2, 2): "ccc", (3, 3): "ccc", (1, 2): "ffc", (1, 3): "fcf", (2, 3): "cff"}
+    sub = {1: "₁", 2: "₂", 3: "₃"}
+    for (i, j), args in comp_args.items():
+        key = sub[i] + sub[j]
+        cases.append((f"S{i}{j}", getattr(S, "S" + key), ev(K.strain_rate_tensor_component(i, j), og, comp_loc[(i, j)], *args), comp_loc[(i, j)]))
+        if i != j:
+            cases.append((f"O{i}{j}", getattr(O, "Ω" + key), ev(K.vorticity_tensor_component(i, j), og, comp_loc[(i, j)], *args), comp_loc[(i, j)]))
+            cases.append((f"T{i}{j}", getattr(T, "τ" + key), ev(K.stress_tensor_component(i, j), og, comp_loc[(i, j)], *args), comp_loc[(i, j)]))
+        else:
+            nat = {1: "fcc", 2: "cfc", 3: "ccf"}[i]
+            cases.append((f"T{i}{j}", getattr(T, "τ" + key), ev(K.stress_tensor_component(i, j), og, nat, *args), nat))
+            cases.append((f"T{i}{j}c", getattr(Tc, "τ" + key), ev(K.stress_tensor_component(i, j, True), og, "ccc", *args), "ccc"))
+    return cases
+
+
+def integral_scale(og, values, loc):
+    i, j, k = og.indices(loc)
+    return float(np.sum(np.abs(values) * og.V(loc, i, j, k)))
