@@ -1,8 +1,518 @@
-// placeholder: the budget kernel is developed next; until then no plan takes the fused path
+// K1 fast path: the register-pipelined, TMA-fed budget kernel.
+//
+// One sweep over u, v, w, b, p emits any subset of the cell-centred budget terms
+//   K   kinetic_energy_ccc                     (src/KineticEnergyEquation.jl:37-39)
+//   ADV uᵢ∂ⱼuⱼuᵢᶜᶜᶜ, Centered 2nd order         (src/KineticEnergyEquation.jl:147-152)
+//   PR  uᵢ∂ᵢpᶜᶜᶜ                               (src/KineticEnergyEquation.jl:304-309)
+//   WB  uᵢbᵢᶜᶜᶜ (vertical gravity)             (src/KineticEnergyEquation.jl:362-367)
+//   EPS viscous_dissipation_rate_ccc           (src/KineticEnergyEquation.jl:427-453)
+//   CHI tracer_variance_dissipation_rate_ccc   (src/TracerVarianceEquation.jl:146-161)
+//   CDF c∇_dot_qᶜ                              (src/TracerVarianceEquation.jl:93-98)
+// as output fields and/or fused volume integrals, for Float64 array operands on a regularly spaced grid with
+// a constant-coefficient closure.  Everything else goes to the generic kernel (ocb_sweep.cu).
+//
+// Design (B200):
+//  * a block owns a (32 x BR) column of cells and marches in z; each thread owns RY consecutive rows of one x
+//    column, so y neighbours are mostly registers and x neighbours are neighbouring lanes;
+//  * every input plane tile (34 x (BR+2) with the x/y halo ring) is brought into a shared-memory ring by TMA
+//    (cp.async.bulk.tensor.3d straight from the Oceananigans parent arrays, halos included), NS planes ahead,
+//    completion signalled on an mbarrier -- no thread issues a global load;
+//  * each edge (ffc/fcf/cff) and face quantity is formed ONCE by the cell that owns it and shared: along x by
+//    warp shuffle, along y by registers (inside a thread) or a double-buffered shared exchange row (between
+//    warps), along z by the register pipeline.  That removes the 4x corner recomputation of the per-cell
+//    reference formulation;
+//  * tiles overlap by one cell in x and y (lane 31 and the block's last row only produce shared quantities),
+//    so no block ever needs another block's intermediates;
+//  * volume integrals: per-thread Float64 accumulators, warp shuffle + shared reduction, one partial per
+//    block and slot, summed in a fixed order by ocb_finalize_partials_kernel (deterministic run to run).
 #include "ocb_sweep_fused.cuh"
-struct ocb_fused_plan { int nblocks; };
-int ocb_fused_try_create(const ocb_grid*, const ocb_sweep_inputs*, const ocb_request*, int, const SweepParams<double>&, ocb_fused_plan** out) { *out = nullptr; return OCB_OK; }
-int ocb_fused_try_create(const ocb_grid*, const ocb_sweep_inputs*, const ocb_request*, int, const SweepParams<float>&, ocb_fused_plan** out) { *out = nullptr; return OCB_OK; }
+#include <cuda.h>
+#include <new>
+
+namespace {
+
+constexpr int FD_K = 0, FD_ADV = 1, FD_PR = 2, FD_WB = 3, FD_EPS = 4, FD_CHI = 5, FD_CDF = 6, FD_N = 7;
+constexpr int TW = 34;             // tile width: 32 lanes + west/east halo
+
+struct FusedOut { double* out; long long os[3]; int slot; };
+
+struct FusedParams {
+  int Nx, Ny, Nz;
+  int hx, hy, hz;                  // parent index of 1-based index i is i + hx - 1
+  int tiles_x, tiles_y, nchunks, kchunk;
+  double rdx, rdy, rdz, nu, kappa, ghat_z, V;
+  FusedOut o[FD_N];
+  double* partial;
+  int nslots;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  uint32_t done;
+  const uint32_t addr = smem_u32(bar);
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(addr), "r"(phase) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int z) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
+}
+
+template <int NW, int RY>
+struct Geo {
+  static constexpr int BR = NW * RY;                 // rows a block works on (the last one is overlap only)
+  static constexpr int TR = BR + 2;                  // tile rows with the south/north halo
+  static constexpr int TILE = ((TW * TR * 8 + 127) / 128) * 128 / 8;   // doubles per field tile, 128 B aligned
+};
+
+// MASK bit d set <=> diagnostic d is requested.  NS = TMA ring depth.
+template <int MASK, int NW, int RY, int NS>
+__global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 3 : (NW <= 6 ? 2 : 1)))
+ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__ CUtensorMap mu, const __grid_constant__ CUtensorMap mv,
+                  const __grid_constant__ CUtensorMap mw, const __grid_constant__ CUtensorMap mb, const __grid_constant__ CUtensorMap mp) {
+  using G = Geo<NW, RY>;
+  constexpr bool H_K = MASK & (1 << FD_K), H_ADV = MASK & (1 << FD_ADV), H_PR = MASK & (1 << FD_PR), H_WB = MASK & (1 << FD_WB),
+                 H_EPS = MASK & (1 << FD_EPS), H_CHI = MASK & (1 << FD_CHI), H_CDF = MASK & (1 << FD_CDF);
+  constexpr bool NEED_B = H_WB || H_CHI || H_CDF, NEED_P = H_PR;
+  constexpr int NF = 3 + (NEED_B ? 1 : 0) + (NEED_P ? 1 : 0);
+  constexpr int F_B = 3, F_P = NEED_B ? 4 : 3;
+  constexpr int NX = 5;                                // exchanged quantities per column: X12, P12, e23, P23, Fv
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* tiles = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);   // [NS][NF][TILE]
+  double* xch = tiles + (size_t)NS * NF * G::TILE;                             // [2][NW][NX][32]
+  double* red = xch + 2 * NW * NX * 32;                                        // [NW]
+  uint64_t* full = reinterpret_cast<uint64_t*>(red + NW);                      // [NS]
+
+  const int lane = threadIdx.x, warp = threadIdx.y;
+  const int tid = warp * 32 + lane;
+  int bid = blockIdx.x;
+  const int tx = bid % P.tiles_x; bid /= P.tiles_x;
+  const int ty = bid % P.tiles_y; bid /= P.tiles_y;
+  const int chunk = bid;
+  const int i0 = 1 + 31 * tx, j0 = 1 + (G::BR - 1) * ty;
+  const int k0 = 1 + chunk * P.kchunk;
+  const int k1 = min(k0 + P.kchunk - 1, P.Nz);
+  const int n_first = k0 - 1, n_last = k1 + 2;
+  const int i = i0 + lane;
+  const int jr0 = warp * RY;                           // first block-row of this thread
+
+  // ---- TMA ring ------------------------------------------------------------------------------------------
+  constexpr uint32_t STAGE_BYTES = (uint32_t)(NF * TW * G::TR * 8);
+  const int px = i0 - 1 + P.hx - 1, py = j0 - 1 + P.hy - 1;   // parent coordinates of the tile's first element
+  auto issue = [&](int n) {
+    const int s = (n - n_first) % NS;
+    double* dst = tiles + (size_t)s * NF * G::TILE;
+    mbar_expect_tx(&full[s], STAGE_BYTES);
+    const int pz = n + P.hz - 1;
+    tma_load_3d(dst + 0 * G::TILE, &mu, &full[s], px, py, pz);
+    tma_load_3d(dst + 1 * G::TILE, &mv, &full[s], px, py, pz);
+    tma_load_3d(dst + 2 * G::TILE, &mw, &full[s], px, py, pz);
+    if (NEED_B) tma_load_3d(dst + F_B * G::TILE, &mb, &full[s], px, py, pz);
+    if (NEED_P) tma_load_3d(dst + F_P * G::TILE, &mp, &full[s], px, py, pz);
+  };
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int n = n_first; n < n_first + NS && n <= n_last; ++n) issue(n);
+  }
+
+  const double rdx = P.rdx, rdy = P.rdy, rdz = P.rdz;
+  // ---- pipeline state (per owned row) -----------------------------------------------------------------------
+  double up[RY], vp[RY], wp[RY], bp[RY], pp[RY];        // raw, previous plane
+  double P13p[RY], P23p[RY];                            // fcf / cff momentum-flux products at the previous face
+  double dU[RY], dV[RY], dW[RY];                        // in-plane parts of the flux divergences (previous plane)
+  double Wwpp[RY], Fwp[RY], Apart[RY], Fvp[RY];         // ADV pipeline
+  double Eacc[RY], Kacc[RY], PRacc[RY], CHacc[RY], CDacc[RY], hzp[RY];
+#pragma unroll
+  for (int r = 0; r < RY; ++r) {
+    up[r] = vp[r] = wp[r] = bp[r] = pp[r] = 0.0;
+    P13p[r] = P23p[r] = dU[r] = dV[r] = dW[r] = Wwpp[r] = Fwp[r] = Apart[r] = Fvp[r] = 0.0;
+    Eacc[r] = Kacc[r] = PRacc[r] = CHacc[r] = CDacc[r] = hzp[r] = 0.0;
+  }
+  double acc[FD_N];
+#pragma unroll
+  for (int d = 0; d < FD_N; ++d) acc[d] = 0.0;
+
+  const unsigned FULLMASK = 0xffffffffu;
+  const bool lane_out = lane < 31 && i <= P.Nx;
+
+  for (int n = n_first; n <= n_last; ++n) {
+    const int it = n - n_first;
+    const int s = it % NS;
+    mbar_wait(&full[s], (uint32_t)((it / NS) & 1));
+    const double* T = tiles + (size_t)s * NF * G::TILE;
+    const double* Tu = T, *Tv = T + G::TILE, *Tw = T + 2 * G::TILE, *Tb = T + F_B * G::TILE, *Tp = T + F_P * G::TILE;
+    const int par = it & 1;
+
+    // ---- stage 1: quantities owned by this thread's cells at plane n --------------------------------------
+    double uc[RY], vc[RY], wc[RY], bc[RY], pc[RY];
+    double X12[RY], P12[RY], P12E[RY], e23[RY], P23[RY], Y13[RY], P13[RY], P13E[RY];
+    double Uu[RY], UuW[RY], Vv[RY], VvS[RY], inpl[RY], Kxy[RY], PRxy[RY], CHxy[RY], CDxy[RY];
+#pragma unroll
+    for (int r = 0; r < RY; ++r) {
+      const int row = jr0 + 1 + r;                       // tile row of this cell
+      const double* ru = Tu + row * TW + lane;           // ru[0] west, ru[1] centre, ru[2] east
+      const double* rv = Tv + row * TW + lane;
+      const double* rw = Tw + row * TW + lane;
+      uc[r] = ru[1]; vc[r] = rv[1]; wc[r] = rw[1];
+      const double ue = ru[2], uw = ru[0], us = (r == 0) ? ru[1 - TW] : uc[r > 0 ? r - 1 : 0];
+      const double vw = rv[0], vn = rv[1 + TW], vs = (r == 0) ? rv[1 - TW] : vc[r > 0 ? r - 1 : 0];
+      const double ww = rw[0], ws = (r == 0) ? rw[1 - TW] : wc[r > 0 ? r - 1 : 0];
+      // ffc edge (i, j): strain and the (Vu = Uv) momentum-flux product
+      const double s12 = (uc[r] - us) * rdy + (vc[r] - vw) * rdx;
+      const double e12 = s12 * s12;
+      P12[r] = (vw + vc[r]) * (us + uc[r]);
+      // fcf edge (i, j, n) and cff edge
+      const double s13 = (uc[r] - up[r]) * rdz + (wc[r] - ww) * rdx;
+      const double e13 = s13 * s13;
+      P13[r] = (ww + wc[r]) * (up[r] + uc[r]);
+      const double s23 = (vc[r] - vp[r]) * rdz + (wc[r] - ws) * rdy;
+      e23[r] = s23 * s23;
+      P23[r] = (ws + wc[r]) * (vp[r] + vc[r]);
+      // x neighbours' edges by shuffle
+      X12[r] = e12 + __shfl_down_sync(FULLMASK, e12, 1);
+      Y13[r] = e13 + __shfl_down_sync(FULLMASK, e13, 1);
+      if (H_ADV) {
+        P12E[r] = __shfl_down_sync(FULLMASK, P12[r], 1);
+        P13E[r] = __shfl_down_sync(FULLMASK, P13[r], 1);
+        Uu[r] = (uc[r] + ue) * (uc[r] + ue);
+        UuW[r] = (uw + uc[r]) * (uw + uc[r]);
+        Vv[r] = (vc[r] + vn) * (vc[r] + vn);
+        VvS[r] = (vs + vc[r]) * (vs + vc[r]);
+      }
+      const double sxx = (ue - uc[r]) * rdx, syy = (vn - vc[r]) * rdy;
+      inpl[r] = 2.0 * (sxx * sxx + syy * syy);            // x nu later
+      Kxy[r] = (uc[r] * uc[r] + ue * ue) + (vc[r] * vc[r] + vn * vn);
+      if (NEED_P) {
+        const double* rp = Tp + row * TW + lane;
+        pc[r] = rp[1];
+        const double pw = rp[0], pe = rp[2], ps = rp[1 - TW], pn = rp[1 + TW];
+        PRxy[r] = (uc[r] * (pc[r] - pw) + ue * (pe - pc[r])) * rdx + (vc[r] * (pc[r] - ps) + vn * (pn - pc[r])) * rdy;
+      }
+      if (NEED_B) {
+        const double* rb = Tb + row * TW + lane;
+        bc[r] = rb[1];
+        const double dw_ = bc[r] - rb[0], de = rb[2] - bc[r], ds = bc[r] - rb[1 - TW], dn = rb[1 + TW] - bc[r];
+        CHxy[r] = (dw_ * dw_ + de * de) * (rdx * rdx) + (ds * ds + dn * dn) * (rdy * rdy);
+        CDxy[r] = (dw_ - de) * (rdx * rdx) + (ds - dn) * (rdy * rdy);
+      }
+    }
+
+    // ---- y exchange between warps: row 0 of the warp to the north ---------------------------------------------
+    double* myx = xch + ((size_t)(par * NW + warp) * NX) * 32 + lane;
+    myx[0 * 32] = X12[0]; myx[1 * 32] = P12[0]; myx[2 * 32] = e23[0]; myx[3 * 32] = P23[0]; myx[4 * 32] = Fvp[0];
+    __syncthreads();
+    // every thread is done with raw stage s: refill it (plane n + NS)
+    if (tid == 0 && n + NS <= n_last) issue(n + NS);
+    double X12N, P12N, e23N, P23N, FvN;
+    if (warp + 1 < NW) {
+      const double* nx_ = xch + ((size_t)(par * NW + warp + 1) * NX) * 32 + lane;
+      X12N = nx_[0 * 32]; P12N = nx_[1 * 32]; e23N = nx_[2 * 32]; P23N = nx_[3 * 32]; FvN = nx_[4 * 32];
+    } else {
+      X12N = P12N = e23N = P23N = FvN = 0.0;
+    }
+
+    // ---- stage 2 / finalisation, row by row (north neighbour: own row r+1, or the exchanged row) -----------------
+#pragma unroll
+    for (int r = 0; r < RY; ++r) {
+      const bool last = (r == RY - 1);
+      const double x12n = last ? X12N : X12[last ? r : r + 1];
+      const double p12n = last ? P12N : P12[last ? r : r + 1];
+      const double e23n = last ? e23N : e23[last ? r : r + 1];
+      const double p23n = last ? P23N : P23[last ? r : r + 1];
+      const double fvn = last ? FvN : Fvp[last ? r : r + 1];          // Fv(j+1) at plane n-2
+      const int j = j0 + jr0 + r;
+      const bool cell_out = lane_out && (jr0 + r) < G::BR - 1 && j <= P.Ny;
+      const bool v1 = cell_out && (n - 1) >= k0 && (n - 1) <= k1;     // plane n-1 terms
+      const bool v2 = cell_out && (n - 2) >= k0 && (n - 2) <= k1;     // ADV lags one more plane
+      const double Y23 = e23[r] + e23n;
+      const double szz = (wc[r] - wp[r]) * rdz;                        // S33 of cell plane n-1
+      const double wsq = wc[r] * wc[r];
+      // ε(n-1)
+      if (H_EPS) {
+        const double edge_n = 0.25 * (Y13[r] + Y23);
+        const double val = P.nu * (Eacc[r] + 2.0 * szz * szz + edge_n);
+        Eacc[r] = inpl[r] + 0.25 * (X12[r] + x12n) + edge_n;
+        if (v1) {
+          acc[FD_EPS] += val;
+          if (P.o[FD_EPS].out) P.o[FD_EPS].out[i * P.o[FD_EPS].os[0] + j * P.o[FD_EPS].os[1] + (long long)(n - 1) * P.o[FD_EPS].os[2]] = val;
+        }
+      }
+      if (H_K) {
+        const double val = 0.25 * (Kacc[r] + wsq);
+        Kacc[r] = Kxy[r] + wsq;
+        if (v1) {
+          acc[FD_K] += val;
+          if (P.o[FD_K].out) P.o[FD_K].out[i * P.o[FD_K].os[0] + j * P.o[FD_K].os[1] + (long long)(n - 1) * P.o[FD_K].os[2]] = val;
+        }
+      }
+      if (H_PR) {
+        const double fz = wc[r] * (pc[r] - pp[r]) * rdz;
+        const double val = 0.5 * (PRacc[r] + fz);
+        PRacc[r] = PRxy[r] + fz;
+        if (v1) {
+          acc[FD_PR] += val;
+          if (P.o[FD_PR].out) P.o[FD_PR].out[i * P.o[FD_PR].os[0] + j * P.o[FD_PR].os[1] + (long long)(n - 1) * P.o[FD_PR].os[2]] = val;
+        }
+      }
+      if (NEED_B) {
+        const double dbz = bc[r] - bp[r];
+        if (H_WB) {
+          const double hz = wc[r] * (bp[r] + bc[r]);
+          const double val = 0.25 * P.ghat_z * (hzp[r] + hz);
+          hzp[r] = hz;
+          if (v1) {
+            acc[FD_WB] += val;
+            if (P.o[FD_WB].out) P.o[FD_WB].out[i * P.o[FD_WB].os[0] + j * P.o[FD_WB].os[1] + (long long)(n - 1) * P.o[FD_WB].os[2]] = val;
+          }
+        }
+        if (H_CHI) {
+          const double gz = dbz * dbz * (rdz * rdz);
+          const double val = P.kappa * (CHacc[r] + gz);
+          CHacc[r] = CHxy[r] + gz;
+          if (v1) {
+            acc[FD_CHI] += val;
+            if (P.o[FD_CHI].out) P.o[FD_CHI].out[i * P.o[FD_CHI].os[0] + j * P.o[FD_CHI].os[1] + (long long)(n - 1) * P.o[FD_CHI].os[2]] = val;
+          }
+        }
+        if (H_CDF) {
+          const double qz = dbz * (rdz * rdz);
+          const double val = 2.0 * bp[r] * P.kappa * (CDacc[r] - qz);
+          CDacc[r] = CDxy[r] + qz;
+          if (v1) {
+            acc[FD_CDF] += val;
+            if (P.o[FD_CDF].out) P.o[FD_CDF].out[i * P.o[FD_CDF].os[0] + j * P.o[FD_CDF].os[1] + (long long)(n - 1) * P.o[FD_CDF].os[2]] = val;
+          }
+        }
+      }
+      if (H_ADV) {
+        // faces of plane n-1: F = velocity x flux divergence (the common 1/4 of the flux means is applied at the end)
+        const double Fu = up[r] * (dU[r] + (P13[r] - P13p[r]) * rdz);
+        const double Fv = vp[r] * (dV[r] + (P23[r] - P23p[r]) * rdz);
+        const double Wwp = (wp[r] + wc[r]) * (wp[r] + wc[r]);           // Ww at cell plane n-1
+        const double Fw = wp[r] * (dW[r] + (Wwp - Wwpp[r]) * rdz);      // face n-1
+        // ADV(n-2) = 1/8 [Fu + FuE + Fv + FvN + Fw(n-2) + Fw(n-1)]
+        const double val = 0.125 * (Apart[r] + fvn + Fw);
+        const double FuE = __shfl_down_sync(FULLMASK, Fu, 1);
+        Apart[r] = (Fu + FuE) + Fv + Fw;
+        Fvp[r] = Fv;
+        Wwpp[r] = Wwp;
+        dU[r] = (Uu[r] - UuW[r]) * rdx + (p12n - P12[r]) * rdy;
+        dV[r] = (P12E[r] - P12[r]) * rdx + (Vv[r] - VvS[r]) * rdy;
+        dW[r] = (P13E[r] - P13[r]) * rdx + (p23n - P23[r]) * rdy;
+        P13p[r] = P13[r]; P23p[r] = P23[r];
+        if (v2) {
+          acc[FD_ADV] += val;
+          if (P.o[FD_ADV].out) P.o[FD_ADV].out[i * P.o[FD_ADV].os[0] + j * P.o[FD_ADV].os[1] + (long long)(n - 2) * P.o[FD_ADV].os[2]] = val;
+        }
+      }
+      up[r] = uc[r]; vp[r] = vc[r]; wp[r] = wc[r];
+      if (NEED_B) bp[r] = bc[r];
+      if (NEED_P) pp[r] = pc[r];
+    }
+  }
+
+  // ---- volume integrals: warp shuffle, then one partial per block and slot -------------------------------------
+  if (P.nslots > 0) {
+#pragma unroll
+    for (int d = 0; d < FD_N; ++d) {
+      if (!(MASK & (1 << d)) || P.o[d].slot < 0) continue;
+      double v = acc[d];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULLMASK, v, o);
+      __syncthreads();
+      if (lane == 0) red[warp] = v;
+      __syncthreads();
+      if (tid == 0) {
+        double s = 0.0;
+        for (int w = 0; w < NW; ++w) s += red[w];
+        P.partial[(size_t)blockIdx.x * P.nslots + P.o[d].slot] = s * P.V;
+      }
+    }
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = (EncodeTiledFn)p;
+  return fn;
+}
+
+}  // namespace
+
+struct ocb_fused_plan {
+  FusedParams P;
+  CUtensorMap maps[5];
+  int mask, nw, ry, ns;
+  int nblocks;
+  size_t smem;
+  void (*kernel)(FusedParams, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap);
+};
+
+template <int MASK, int NW, int RY, int NS>
+static int setup_variant(ocb_fused_plan* fp) {
+  using G = Geo<NW, RY>;
+  constexpr bool NEED_B = MASK & ((1 << FD_WB) | (1 << FD_CHI) | (1 << FD_CDF)), NEED_P = MASK & (1 << FD_PR);
+  constexpr int NF = 3 + (NEED_B ? 1 : 0) + (NEED_P ? 1 : 0);
+  fp->kernel = ocb_budget_kernel<MASK, NW, RY, NS>;
+  fp->nw = NW; fp->ry = RY; fp->ns = NS; fp->mask = MASK;
+  fp->smem = sizeof(double) * ((size_t)NS * NF * G::TILE + 2 * NW * 5 * 32 + NW) + sizeof(uint64_t) * NS + 128;
+  OCB_CUDA(cudaFuncSetAttribute(ocb_budget_kernel<MASK, NW, RY, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp->smem));
+  return OCB_OK;
+}
+
+static int make_map(EncodeTiledFn enc, const ocb_field& f, int rows, CUtensorMap* map) {
+  cuuint64_t dims[3] = {(cuuint64_t)f.size[0], (cuuint64_t)f.size[1], (cuuint64_t)f.size[2]};
+  cuuint64_t strides[2] = {(cuuint64_t)f.stride[1] * 8, (cuuint64_t)f.stride[2] * 8};
+  cuuint32_t box[3] = {(cuuint32_t)TW, (cuuint32_t)rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, f.data, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) OCB_FAIL(OCB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return OCB_OK;
+}
+
+static bool tma_compatible(const ocb_field& f, const ocb_grid* g) {
+  if (f.kind != OCB_FIELD_ARRAY || !f.data) return false;
+  for (int d = 0; d < 3; ++d) if (f.loc[d] == OCB_NOTHING || f.halo[d] != g->H[d]) return false;
+  if (f.stride[0] != 1) return false;
+  if (((uintptr_t)f.data & 15) || ((f.stride[1] * 8) & 15) || ((f.stride[2] * 8) & 15)) return false;
+  if (f.stride[1] != f.size[0] || f.stride[2] != (long long)f.size[0] * f.size[1]) return false;   // dense parent
+  return true;
+}
+
+int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const ocb_request* reqs, int n,
+                         const SweepParams<float>&, ocb_fused_plan** out) {
+  (void)grid; (void)in; (void)reqs; (void)n;
+  *out = nullptr;      // Float32 plans run on the generic kernel (parent rows are not 16-byte multiples in general)
+  return OCB_OK;
+}
+
+int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const ocb_request* reqs, int n,
+                         const SweepParams<double>& SP, ocb_fused_plan** out) {
+  *out = nullptr;
+  if (getenv("OCB_DISABLE_FUSED")) return OCB_OK;
+  // ---- envelope ------------------------------------------------------------------------------------------
+  if (grid->dzc || grid->dzf) return OCB_OK;                                   // regular z only
+  if (grid->H[0] < 2 || grid->H[1] < 2 || grid->H[2] < 2) return OCB_OK;
+  if (in->closure.n_nu_fields || in->closure.n_kappa_fields) return OCB_OK;    // constant coefficients only
+  int mask = 0;
+  int which[FD_N]; for (int d = 0; d < FD_N; ++d) which[d] = -1;
+  for (int r = 0; r < n; ++r) {
+    int d;
+    switch (reqs[r].diag) {
+      case OCB_DIAG_KE: d = FD_K; break;
+      case OCB_DIAG_ADV: d = FD_ADV; break;
+      case OCB_DIAG_PR: d = FD_PR; break;
+      case OCB_DIAG_WB: d = FD_WB; break;
+      case OCB_DIAG_EPS: d = FD_EPS; break;
+      case OCB_DIAG_CHI: d = FD_CHI; break;
+      case OCB_DIAG_CDIFF: d = FD_CDF; break;
+      default: return OCB_OK;
+    }
+    if (reqs[r].flags & OCB_REQ_PERTURBATION) return OCB_OK;
+    if (which[d] >= 0) return OCB_OK;                                          // one request per diagnostic
+    const DReq& R = SP.req[r];
+    if (R.lo[0] != 1 || R.lo[1] != 1 || R.lo[2] != 1 || R.hi[0] != grid->N[0] || R.hi[1] != grid->N[1] || R.hi[2] != grid->N[2]) return OCB_OK;
+    which[d] = r;
+    mask |= 1 << d;
+  }
+  if ((mask & (1 << FD_WB)) && (in->ghat[0] != 0.0 || in->ghat[1] != 0.0)) return OCB_OK;   // vertical gravity only
+  const bool need_b = mask & ((1 << FD_WB) | (1 << FD_CHI) | (1 << FD_CDF)), need_p = mask & (1 << FD_PR);
+  if (!tma_compatible(in->u, grid) || !tma_compatible(in->v, grid) || !tma_compatible(in->w, grid)) return OCB_OK;
+  if (need_b && !tma_compatible(in->b, grid)) return OCB_OK;
+  if (need_p && !tma_compatible(in->p, grid)) return OCB_OK;
+  if (in->u.loc[0] != OCB_FACE || in->v.loc[1] != OCB_FACE || in->w.loc[2] != OCB_FACE) return OCB_OK;
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return OCB_OK;
+
+  ocb_fused_plan* fp = new (std::nothrow) ocb_fused_plan();
+  if (!fp) OCB_FAIL(OCB_ERR_ALLOC, "out of host memory");
+  memset((void*)fp, 0, sizeof(*fp));
+  // ---- variant: all seven terms, or the dissipation-only kernel ---------------------------------------------
+  constexpr int ALL = (1 << FD_N) - 1;
+  int rc;
+  const char* cfg = getenv("OCB_FUSED_CONFIG");   // tuning hook: "NW,RY,NS"
+  int nw = 6, ry = 2, ns = 3;
+  if (cfg) sscanf(cfg, "%d,%d,%d", &nw, &ry, &ns);
+  if (mask == (1 << FD_EPS)) {
+    rc = setup_variant<(1 << FD_EPS), 6, 2, 3>(fp);
+  } else {
+    if (nw == 4 && ry == 2) rc = setup_variant<ALL, 4, 2, 3>(fp);
+    else if (nw == 8 && ry == 1) rc = setup_variant<ALL, 8, 1, 3>(fp);
+    else if (nw == 8 && ry == 2) rc = setup_variant<ALL, 8, 2, 3>(fp);
+    else if (nw == 12 && ry == 2) rc = setup_variant<ALL, 12, 2, 3>(fp);
+    else if (nw == 6 && ry == 3) rc = setup_variant<ALL, 6, 3, 3>(fp);
+    else rc = setup_variant<ALL, 6, 2, 3>(fp);
+  }
+  if (rc != OCB_OK) { delete fp; return rc; }
+  const bool vneed_b = fp->mask & ((1 << FD_WB) | (1 << FD_CHI) | (1 << FD_CDF)), vneed_p = fp->mask & (1 << FD_PR);
+  if ((vneed_b && !tma_compatible(in->b, grid)) || (vneed_p && !tma_compatible(in->p, grid))) { delete fp; return OCB_OK; }
+
+  FusedParams& P = fp->P;
+  P.Nx = grid->N[0]; P.Ny = grid->N[1]; P.Nz = grid->N[2];
+  P.hx = grid->H[0]; P.hy = grid->H[1]; P.hz = grid->H[2];
+  const int BR = fp->nw * fp->ry;
+  P.tiles_x = (P.Nx + 30) / 31;
+  P.tiles_y = (P.Ny + BR - 2) / (BR - 1);
+  const int tiles = P.tiles_x * P.tiles_y;
+  int nchunks = (ocb_sm_count() * 8 + tiles - 1) / tiles;
+  if (nchunks < 1) nchunks = 1;
+  int kchunk = (P.Nz + nchunks - 1) / nchunks;
+  if (kchunk < 32) kchunk = P.Nz < 32 ? P.Nz : 32;
+  if (const char* kc = getenv("OCB_FUSED_KCHUNK")) kchunk = atoi(kc) > 0 ? atoi(kc) : kchunk;
+  P.kchunk = kchunk;
+  P.nchunks = (P.Nz + kchunk - 1) / kchunk;
+  fp->nblocks = tiles * P.nchunks;
+  P.rdx = 1.0 / grid->d[0]; P.rdy = 1.0 / grid->d[1]; P.rdz = 1.0 / grid->d[2];
+  P.nu = in->closure.nu_const; P.kappa = in->closure.kappa_const; P.ghat_z = in->ghat[2];
+  P.V = grid->d[0] * grid->d[1] * grid->d[2];
+  P.nslots = SP.nslots;
+  for (int d = 0; d < FD_N; ++d) {
+    P.o[d].out = nullptr; P.o[d].slot = -1; P.o[d].os[0] = P.o[d].os[1] = P.o[d].os[2] = 0;
+    if (which[d] >= 0) {
+      const DReq& R = SP.req[which[d]];
+      P.o[d].out = (double*)R.out; P.o[d].slot = R.slot;
+      for (int a = 0; a < 3; ++a) P.o[d].os[a] = R.os[a];
+    }
+  }
+  const ocb_field* f[5] = {&in->u, &in->v, &in->w, vneed_b ? &in->b : &in->u, vneed_p ? &in->p : &in->u};
+  for (int a = 0; a < 5; ++a) {
+    rc = make_map(enc, *f[a], BR + 2, &fp->maps[a]);
+    if (rc != OCB_OK) { delete fp; return rc; }
+  }
+  *out = fp;
+  return OCB_OK;
+}
+
 int ocb_fused_nblocks(const ocb_fused_plan* fp) { return fp->nblocks; }
-int ocb_fused_execute(ocb_fused_plan*, double*, cudaStream_t) { return OCB_OK; }
+
+int ocb_fused_execute(ocb_fused_plan* fp, double* partial, cudaStream_t st) {
+  fp->P.partial = partial;
+  dim3 block(32, fp->nw, 1), grid(fp->nblocks, 1, 1);
+  fp->kernel<<<grid, block, fp->smem, st>>>(fp->P, fp->maps[0], fp->maps[1], fp->maps[2], fp->maps[3], fp->maps[4]);
+  OCB_CUDA(cudaGetLastError());
+  return OCB_OK;
+}
+
 void ocb_fused_destroy(ocb_fused_plan* fp) { delete fp; }

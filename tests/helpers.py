@@ -143,9 +143,18 @@ def run_ops(ops, grid, integrals=False, backend=None, fused=True):
         fields = [ocb.Field(op) for op in ops]
         reds = [ocb.Field(ocb.Integral(op)) for op in ops] if integrals else []
         if fused:
-            members = fields + reds
-            for lo in range(0, len(members), 16):
-                ocb.FusedDiagnostics(*members[lo:lo + 16]).compute()
+            # greedy grouping: a member joins the current sweep while its operands are compatible and there is room
+            groups, cur, cur_ops = [], [], None
+            for mbr in fields + reds:
+                merged = mbr.operand.operands if cur_ops is None else cur_ops.merged_with(mbr.operand.operands)
+                if merged is None or len(cur) == 16:
+                    groups.append(cur)
+                    cur, merged = [], mbr.operand.operands
+                cur.append(mbr)
+                cur_ops = merged
+            groups.append(cur)
+            for g in groups:
+                ocb.FusedDiagnostics(*g).compute()
         else:
             for f in fields + reds:
                 f.compute()

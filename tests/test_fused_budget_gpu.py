@@ -1,0 +1,118 @@
+"""GPU parity tests of the register-pipelined budget kernel (csrc/ocb_sweep_fused.cu): the fused
+KE + tracer-variance budget of BASELINE.json configs[2] against the NumPy oracle (rtol 1e-12), against the generic
+kernel at a size the oracle cannot reach, and through size-independent identities at larger sizes."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import State, assert_close, K, ocb
+from cases import integral_scale
+
+pytestmark = pytest.mark.gpu
+
+
+def budget(st, closure="scalar"):
+    oc, pc = st.closures()[closure]
+    m = st.model(closure=pc)
+    KE, TV = ocb.KineticEnergyEquation, ocb.TracerVarianceEquation
+    ops = [KE.KineticEnergy(m), KE.KineticEnergyAdvection(m), KE.KineticEnergyPressureRedistribution(m),
+           KE.PotentialEnergyConversion(m), KE.DissipationRate(m), TV.TracerVarianceDissipationRate(m, "b"),
+           TV.TracerVarianceDiffusion(m, "b")]
+    return ops, oc
+
+
+def oracle_budget(st, oc):
+    og, f = st.og, st.ofields()
+    ev = K.evaluate
+    return [ev(K.kinetic_energy_ccc, og, "ccc", st.ou, st.ov, st.ow), ev(K.ke_advection_ccc, og, "ccc", f),
+            ev(K.ke_pressure_ccc, og, "ccc", f, st.op), ev(K.ke_buoyancy_ccc, og, "ccc", f, (0, 0, 1), st.ob),
+            ev(K.viscous_dissipation_rate_ccc, og, "ccc", None, f, {"closure": oc}),
+            ev(K.tracer_variance_dissipation_rate_ccc, og, "ccc", oc, None, None, st.ob),
+            ev(K.c_div_q_c, og, "ccc", oc, None, None, st.ob)]
+
+
+def run(ops, fields=True, integrals=True, disable_fused=False):
+    if disable_fused:
+        os.environ["OCB_DISABLE_FUSED"] = "1"
+    try:
+        members = ([ocb.Field(o) for o in ops] if fields else []) + ([ocb.Integral(o) for o in ops] if integrals else [])
+        grp = ocb.FusedDiagnostics(*members)
+    finally:
+        os.environ.pop("OCB_DISABLE_FUSED", None)
+    grp.compute()
+    torch.cuda.synchronize()
+    vals = [m.interior_ijk() for m in grp.members if isinstance(m, ocb.ComputedField)]
+    return grp, vals, grp.integrals()
+
+
+@pytest.mark.parametrize("size", [(64, 64, 64), (70, 45, 37), (31, 11, 5), (33, 12, 3)], ids=str)
+def test_fused_budget_matches_oracle(size):
+    st = State(size=size, device="cuda")
+    ops, oc = budget(st)
+    grp, vals, ints = run(ops)
+    assert grp.plan.variant == 1, "the budget plan must take the fused kernel"
+    want = oracle_budget(st, oc)
+    for op, g, w_, integ in zip(ops, vals, want, ints):
+        assert_close(g, w_, 1e-12, op.name)
+        assert abs(integ - K.integral(w_, st.og, "ccc")) <= 1e-12 * integral_scale(st.og, w_, "ccc"), op.name
+
+
+def test_fused_integrals_only_and_subsets():
+    st = State(size=(48, 40, 20), device="cuda")
+    ops, oc = budget(st)
+    want = oracle_budget(st, oc)
+    grp, _, ints = run(ops, fields=False)
+    assert grp.plan.variant == 1 and grp.plan.algorithmic_bytes == 5 * 8 * 48 * 40 * 20
+    for op, w_, integ in zip(ops, want, ints):
+        assert abs(integ - K.integral(w_, st.og, "ccc")) <= 1e-12 * integral_scale(st.og, w_, "ccc"), op.name
+    # dissipation alone (configs[0]) takes the dissipation-only variant
+    grp, vals, _ = run([ops[4]], integrals=False)
+    assert grp.plan.variant == 1
+    np.testing.assert_allclose(vals[0], want[4], rtol=1e-12, atol=0)
+    # a subset with no pressure operand
+    grp, vals, _ = run([ops[0], ops[1], ops[5]], integrals=False)
+    assert grp.plan.variant == 1
+    for g, w_ in zip(vals, [want[0], want[1], want[5]]):
+        assert_close(g, w_, 1e-12)
+
+
+def test_fused_agrees_with_generic_kernel_at_scale():
+    """Two independent CUDA formulations (shared-intermediate pipeline vs per-cell evaluators) at 200x150x96."""
+    st = State(size=(200, 150, 96), device="cuda")
+    ops, _ = budget(st)
+    g1, v1, i1 = run(ops)
+    g0, v0, i0 = run(ops, disable_fused=True)
+    assert g1.plan.variant == 1 and g0.plan.variant == 0
+    for op, a, b in zip(ops, v1, v0):
+        assert_close(a, b, 1e-12, op.name)
+    for a, b, v in zip(i1, i0, v0):
+        assert abs(a - b) <= 1e-12 * float(np.sum(np.abs(v))) * (1.0 / (200 * 150 * 96))
+
+
+def test_fused_is_deterministic_and_identities_hold():
+    """Size-independent properties at 256x256x128: run-to-run bit equality; <chi> = <2c div F> (the reference's own
+    identity, test/test_tracer_variance_diagnostics.jl:31-34); dissipation is non-negative."""
+    st = State(size=(256, 256, 128), device="cuda")
+    ops, _ = budget(st)
+    grp, _, ints = run(ops, fields=False)
+    for _ in range(3):
+        grp.compute()
+        assert grp.integrals() == ints
+    chi, cdf = ints[5], ints[6]
+    assert abs(chi - cdf) <= 1e-10 * abs(chi)
+    f = ocb.Field(ops[4]).compute()
+    assert float(f.interior.min()) >= 0.0
+
+
+def test_fused_falls_back_to_generic_outside_its_envelope():
+    st = State(size=(40, 24, 18), stretched=True, device="cuda")
+    ops, _ = budget(st)
+    grp, _, _ = run(ops, fields=False)
+    assert grp.plan.variant == 0          # stretched z: generic kernel
+    st = State(size=(40, 24, 18), device="cuda")
+    oc, pc = st.closures()["smagorinsky_like"]
+    m = st.model(closure=pc)
+    grp = ocb.FusedDiagnostics(ocb.Integral(ocb.KineticEnergyEquation.DissipationRate(m)))
+    assert grp.plan.variant == 0          # eddy-viscosity field: generic kernel
