@@ -14,7 +14,7 @@
 // Design (B200):
 //  * a block owns a (32 x BR) column of cells and marches in z; each thread owns RY consecutive rows of one x
 //    column, so y neighbours are mostly registers and x neighbours are neighbouring lanes;
-//  * every input plane tile (34 x (BR+2) with the x/y halo ring) is brought into a shared-memory ring by TMA
+//  * every input plane tile (36 x (BR+2) with the x/y halo ring) is brought into a shared-memory ring by TMA
 //    (cp.async.bulk.tensor.3d straight from the Oceananigans parent arrays, halos included), NS planes ahead,
 //    completion signalled on an mbarrier -- no thread issues a global load;
 //  * each edge (ffc/fcf/cff) and face quantity is formed ONCE by the cell that owns it and shared: along x by
@@ -32,7 +32,7 @@
 namespace {
 
 constexpr int FD_K = 0, FD_ADV = 1, FD_PR = 2, FD_WB = 3, FD_EPS = 4, FD_CHI = 5, FD_CDF = 6, FD_N = 7;
-constexpr int TW = 34;             // tile width: 32 lanes + west/east halo
+constexpr int TW = 36;             // tile width: 32 lanes + west/east halo + 1 (the TMA box must start 16-byte aligned) -> 36
 
 struct FusedOut { double* out; long long os[3]; int slot; };
 
@@ -107,7 +107,10 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
 
   // ---- TMA ring ------------------------------------------------------------------------------------------
   constexpr uint32_t STAGE_BYTES = (uint32_t)(NF * TW * G::TR * 8);
-  const int px = i0 - 1 + P.hx - 1, py = j0 - 1 + P.hy - 1;   // parent coordinates of the tile's first element
+  // parent coordinates of the tile's first element; the TMA box start must be 16-byte aligned in x, so the box
+  // starts at the even element at or before it and every shared-memory column index is shifted by xoff
+  const int px_raw = i0 - 1 + P.hx - 1, py = j0 - 1 + P.hy - 1;
+  const int xoff = px_raw & 1, px = px_raw - xoff;
   auto issue = [&](int n) {
     const int s = (n - n_first) % NS;
     double* dst = tiles + (size_t)s * NF * G::TILE;
@@ -163,9 +166,9 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
 #pragma unroll
     for (int r = 0; r < RY; ++r) {
       const int row = jr0 + 1 + r;                       // tile row of this cell
-      const double* ru = Tu + row * TW + lane;           // ru[0] west, ru[1] centre, ru[2] east
-      const double* rv = Tv + row * TW + lane;
-      const double* rw = Tw + row * TW + lane;
+      const double* ru = Tu + row * TW + lane + xoff;           // ru[0] west, ru[1] centre, ru[2] east
+      const double* rv = Tv + row * TW + lane + xoff;
+      const double* rw = Tw + row * TW + lane + xoff;
       uc[r] = ru[1]; vc[r] = rv[1]; wc[r] = rw[1];
       const double ue = ru[2], uw = ru[0], us = (r == 0) ? ru[1 - TW] : uc[r > 0 ? r - 1 : 0];
       const double vw = rv[0], vn = rv[1 + TW], vs = (r == 0) ? rv[1 - TW] : vc[r > 0 ? r - 1 : 0];
@@ -196,13 +199,13 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
       inpl[r] = 2.0 * (sxx * sxx + syy * syy);            // x nu later
       Kxy[r] = (uc[r] * uc[r] + ue * ue) + (vc[r] * vc[r] + vn * vn);
       if (NEED_P) {
-        const double* rp = Tp + row * TW + lane;
+        const double* rp = Tp + row * TW + lane + xoff;
         pc[r] = rp[1];
         const double pw = rp[0], pe = rp[2], ps = rp[1 - TW], pn = rp[1 + TW];
         PRxy[r] = (uc[r] * (pc[r] - pw) + ue * (pe - pc[r])) * rdx + (vc[r] * (pc[r] - ps) + vn * (pn - pc[r])) * rdy;
       }
       if (NEED_B) {
-        const double* rb = Tb + row * TW + lane;
+        const double* rb = Tb + row * TW + lane + xoff;
         bc[r] = rb[1];
         const double dw_ = bc[r] - rb[0], de = rb[2] - bc[r], ds = bc[r] - rb[1 - TW], dn = rb[1 + TW] - bc[r];
         CHxy[r] = (dw_ * dw_ + de * de) * (rdx * rdx) + (ds * ds + dn * dn) * (rdy * rdy);
@@ -417,7 +420,8 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
   if (grid->H[0] < 2 || grid->H[1] < 2 || grid->H[2] < 2) return OCB_OK;
   if (in->closure.n_nu_fields || in->closure.n_kappa_fields) return OCB_OK;    // constant coefficients only
   int mask = 0;
-  int which[FD_N]; for (int d = 0; d < FD_N; ++d) which[d] = -1;
+  int which_out[FD_N], which_slot[FD_N];     // a diagnostic may appear twice: once as a Field, once as an Integral
+  for (int d = 0; d < FD_N; ++d) which_out[d] = which_slot[d] = -1;
   for (int r = 0; r < n; ++r) {
     int d;
     switch (reqs[r].diag) {
@@ -431,10 +435,10 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
       default: return OCB_OK;
     }
     if (reqs[r].flags & OCB_REQ_PERTURBATION) return OCB_OK;
-    if (which[d] >= 0) return OCB_OK;                                          // one request per diagnostic
     const DReq& R = SP.req[r];
     if (R.lo[0] != 1 || R.lo[1] != 1 || R.lo[2] != 1 || R.hi[0] != grid->N[0] || R.hi[1] != grid->N[1] || R.hi[2] != grid->N[2]) return OCB_OK;
-    which[d] = r;
+    if (R.out) { if (which_out[d] >= 0) return OCB_OK; which_out[d] = r; }
+    if (R.slot >= 0) { if (which_slot[d] >= 0) return OCB_OK; which_slot[d] = r; }
     mask |= 1 << d;
   }
   if ((mask & (1 << FD_WB)) && (in->ghat[0] != 0.0 || in->ghat[1] != 0.0)) return OCB_OK;   // vertical gravity only
@@ -490,11 +494,12 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
   P.nslots = SP.nslots;
   for (int d = 0; d < FD_N; ++d) {
     P.o[d].out = nullptr; P.o[d].slot = -1; P.o[d].os[0] = P.o[d].os[1] = P.o[d].os[2] = 0;
-    if (which[d] >= 0) {
-      const DReq& R = SP.req[which[d]];
-      P.o[d].out = (double*)R.out; P.o[d].slot = R.slot;
+    if (which_out[d] >= 0) {
+      const DReq& R = SP.req[which_out[d]];
+      P.o[d].out = (double*)R.out;
       for (int a = 0; a < 3; ++a) P.o[d].os[a] = R.os[a];
     }
+    if (which_slot[d] >= 0) P.o[d].slot = SP.req[which_slot[d]].slot;
   }
   const ocb_field* f[5] = {&in->u, &in->v, &in->w, vneed_b ? &in->b : &in->u, vneed_p ? &in->p : &in->u};
   for (int a = 0; a < 5; ++a) {

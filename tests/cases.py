@@ -9,6 +9,9 @@ from helpers import ocb, K, State, OConst, OZero, DiffField, average_dims, mirro
 KE, TKE, TV, FD = ocb.KineticEnergyEquation, ocb.TurbulentKineticEnergyEquation, ocb.TracerVarianceEquation, ocb.FlowDiagnostics
 
 
+TILT = (float(np.sin(0.3)), 0.0, float(np.cos(0.3)))
+
+
 def build_cases(st: State, closure_name="scalar", mean="profile"):
     """-> list of (name, package op, oracle values [i,j,k], location string)."""
     oc, pc = st.closures()[closure_name]
@@ -32,7 +35,7 @@ def build_cases(st: State, closure_name="scalar", mean="profile"):
     ofp = {"u": oup, "v": ovp, "w": owp, "b": st.ob}
     sp_args = (oup, ovp, owp, oU, oV, oW)
     vdir = (0.0, 0.0, 1.0)
-    tilt = (np.sin(0.3), 0.0, np.cos(0.3))
+    tilt = TILT
     ro_bg = dict(dWdy_bg=1e-3, dVdz_bg=2e-3, dUdz_bg=-1e-3, dWdx_bg=5e-4, dUdy_bg=3e-3, dVdx_bg=-2e-3)
     oro = dict(ro_bg, fx=f_cor[0], fy=f_cor[1], fz=f_cor[2])
     ddir = (0.6, 0.0, 0.8)
@@ -95,3 +98,40 @@ def build_cases(st: State, closure_name="scalar", mean="profile"):
 def integral_scale(og, values, loc):
     i, j, k = og.indices(loc)
     return float(np.sum(np.abs(values) * og.V(loc, i, j, k)))
+
+
+def richardson_tolerance(st, vdir, want, rtol=1e-12):
+    """Per-point absolute tolerance for Ri = ∂b/∂ẑ / (∂uₕ/∂ẑ)²: the denominator is a difference of nearly equal
+    square roots, so its relative rounding error is eps * (sum of |samples|) / |difference| -- the tolerance is the
+    contract's rtol plus that conditioning term (the largest |Ri| are exactly the worst-conditioned points)."""
+    og = st.og
+    i, j, k = og.indices("ccf")
+    a = (st.ou, st.ov, st.ow, vdir)
+    uh = lambda ii, jj, kk: np.abs(K.uh_norm_ccc(ii, jj, kk, og, *a))
+    rdx, rdy = 1.0 / og.Dx("ccc", i, j, k), 1.0 / og.Dy("ccc", i, j, k)
+    rdz = 1.0 / og.Dz("ccf", i, j, k)
+    mag = (abs(vdir[2]) * rdz * (uh(i, j, k) + uh(i, j, k - 1)) + abs(vdir[0]) * rdx * 0.5 * (uh(i + 1, j, k) + uh(i - 1, j, k))
+           + abs(vdir[1]) * rdy * 0.5 * (uh(i, j + 1, k) + uh(i, j - 1, k)))
+    dudx = K.ix_caa(i, j, k, og, K.ddx_fcc, K.uh_norm_ccc, *a)
+    dudy = K.iy_aca(i, j, k, og, K.ddy_cfc, K.uh_norm_ccc, *a)
+    dudz = K.ddz_ccf(i, j, k, og, K.uh_norm_ccc, *a)
+    total = np.abs(dudx * vdir[0] + dudy * vdir[1] + dudz * vdir[2])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        cond = np.where(total > 0, mag / total, np.inf)
+    eps = np.finfo(og.dtype).eps
+    return np.abs(want) * (rtol + 32 * eps * cond)
+
+
+def check_case(st, name, got, want, rtol=1e-12):
+    """Elementwise parity of one case: |got - want| <= rtol * max|want| (signed transport terms cancel locally, so
+    the scale is the field's magnitude); Richardson numbers get their conditioning-aware per-point bound."""
+    from helpers import assert_close
+    finite = np.isfinite(want)
+    assert finite.mean() > 0.9, name
+    if name.startswith("RichardsonNumber"):
+        tol = richardson_tolerance(st, TILT if name.endswith("tilted") else (0.0, 0.0, 1.0), want, rtol)
+        err = np.abs(np.asarray(got, dtype=np.float64) - want)
+        bad = finite & np.isfinite(tol) & (err > tol)
+        assert not bad.any(), f"{name}: {int(bad.sum())} points beyond tolerance, worst ratio {float(np.max(err[bad] / tol[bad])):.3g}"
+        return
+    assert_close(np.where(finite, got, 0.0), np.where(finite, want, 0.0), rtol, name)

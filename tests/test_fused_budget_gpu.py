@@ -47,12 +47,13 @@ def run(ops, fields=True, integrals=True, disable_fused=False):
     return grp, vals, grp.integrals()
 
 
-@pytest.mark.parametrize("size", [(64, 64, 64), (70, 45, 37), (31, 11, 5), (33, 12, 3)], ids=str)
+@pytest.mark.parametrize("size", [(64, 64, 64), (70, 45, 37), (32, 11, 5), (62, 23, 3), (33, 12, 3)], ids=str)
 def test_fused_budget_matches_oracle(size):
     st = State(size=size, device="cuda")
     ops, oc = budget(st)
     grp, vals, ints = run(ops)
-    assert grp.plan.variant == 1, "the budget plan must take the fused kernel"
+    # TMA needs 16-byte row pitches: an even Nx takes the pipelined kernel, an odd one the generic kernel
+    assert grp.plan.variant == (1 if size[0] % 2 == 0 else 0)
     want = oracle_budget(st, oc)
     for op, g, w_, integ in zip(ops, vals, want, ints):
         assert_close(g, w_, 1e-12, op.name)
