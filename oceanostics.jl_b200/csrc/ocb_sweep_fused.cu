@@ -34,7 +34,7 @@ namespace {
 constexpr int FD_K = 0, FD_ADV = 1, FD_PR = 2, FD_WB = 3, FD_EPS = 4, FD_CHI = 5, FD_CDF = 6, FD_N = 7;
 constexpr int TW = 36;             // tile width: 32 lanes + west/east halo + 1 (the TMA box must start 16-byte aligned) -> 36
 
-struct FusedOut { double* out; long long os[3]; int slot; };
+struct FusedOut { double* out; int slot; };
 
 struct FusedParams {
   int Nx, Ny, Nz;
@@ -42,6 +42,7 @@ struct FusedParams {
   int tiles_x, tiles_y, nchunks, kchunk;
   double rdx, rdy, rdz, nu, kappa, ghat_z, V;
   FusedOut o[FD_N];
+  long long os[3];                 // element strides shared by every output field
   double* partial;
   int nslots;
 };
@@ -73,9 +74,9 @@ struct Geo {
   static constexpr int TILE = ((TW * TR * 8 + 127) / 128) * 128 / 8;   // doubles per field tile, 128 B aligned
 };
 
-// MASK bit d set <=> diagnostic d is requested.  NS = TMA ring depth.
-template <int MASK, int NW, int RY, int NS>
-__global__ void __launch_bounds__(NW * 32, (NW <= 4 ? 3 : (NW <= 6 ? 2 : 1)))
+// MASK bit d set <=> diagnostic d is requested.  NS = TMA ring depth.  OUT: some request materialises a field.
+template <int MASK, int NW, int RY, int NS, bool OUT>
+__global__ void __launch_bounds__(NW * 32, (RY == 1 ? (NW <= 8 ? 2 : 1) : (NW <= 6 ? 2 : 1)))
 ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__ CUtensorMap mu, const __grid_constant__ CUtensorMap mv,
                   const __grid_constant__ CUtensorMap mw, const __grid_constant__ CUtensorMap mb, const __grid_constant__ CUtensorMap mp) {
   using G = Geo<NW, RY>;
@@ -86,9 +87,9 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
   constexpr int F_B = 3, F_P = NEED_B ? 4 : 3;
   constexpr int NX = 5;                                // exchanged quantities per column: X12, P12, e23, P23, Fv
 
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  double* tiles = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);   // [NS][NF][TILE]
-  double* xch = tiles + (size_t)NS * NF * G::TILE;                             // [2][NW][NX][32]
+  extern __shared__ __align__(1024) double smem_d[];
+  double* tiles = smem_d;                                                      // [NS][NF][TILE]
+  double* xch = tiles + NS * NF * G::TILE;                                     // [2][NW][NX][32]
   double* red = xch + 2 * NW * NX * 32;                                        // [NW]
   uint64_t* full = reinterpret_cast<uint64_t*>(red + NW);                      // [NS]
 
@@ -113,7 +114,7 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
   const int xoff = px_raw & 1, px = px_raw - xoff;
   auto issue = [&](int n) {
     const int s = (n - n_first) % NS;
-    double* dst = tiles + (size_t)s * NF * G::TILE;
+    double* dst = tiles + s * (NF * G::TILE);
     mbar_expect_tx(&full[s], STAGE_BYTES);
     const int pz = n + P.hz - 1;
     tma_load_3d(dst + 0 * G::TILE, &mu, &full[s], px, py, pz);
@@ -131,17 +132,25 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
     for (int n = n_first; n < n_first + NS && n <= n_last; ++n) issue(n);
   }
 
+  // metric and closure constants, folded so that every term below is a bare sum of products; the remaining
+  // per-diagnostic scale factor (1/4 for K, 1/8 for ADV, ...) is applied to stored values and to the block partial
   const double rdx = P.rdx, rdy = P.rdy, rdz = P.rdz;
+  const double rdx2 = rdx * rdx, rdy2 = rdy * rdy, rdz2 = rdz * rdz;
+  const double hsn = 0.5 * sqrt(P.nu);                       // strain scale: (hsn * s)^2 = nu/4 * s^2
+  const double ex = rdx * hsn, ey = rdy * hsn, ez = rdz * hsn;
+  const double dx2 = 2.0 * P.nu * rdx2, dy2 = 2.0 * P.nu * rdy2, dz2 = 2.0 * P.nu * rdz2;   // diagonal strain weights
+  const double SC_K = 0.25, SC_ADV = 0.125, SC_PR = 0.5, SC_WB = 0.25 * P.ghat_z, SC_EPS = 1.0, SC_CHI = P.kappa,
+               SC_CDF = 2.0 * P.kappa;
   // ---- pipeline state (per owned row) -----------------------------------------------------------------------
   double up[RY], vp[RY], wp[RY], bp[RY], pp[RY];        // raw, previous plane
   double P13p[RY], P23p[RY];                            // fcf / cff momentum-flux products at the previous face
   double dU[RY], dV[RY], dW[RY];                        // in-plane parts of the flux divergences (previous plane)
-  double Wwpp[RY], Fwp[RY], Apart[RY], Fvp[RY];         // ADV pipeline
+  double Wwpp[RY], Apart[RY], Fvp[RY];                  // ADV pipeline
   double Eacc[RY], Kacc[RY], PRacc[RY], CHacc[RY], CDacc[RY], hzp[RY];
 #pragma unroll
   for (int r = 0; r < RY; ++r) {
     up[r] = vp[r] = wp[r] = bp[r] = pp[r] = 0.0;
-    P13p[r] = P23p[r] = dU[r] = dV[r] = dW[r] = Wwpp[r] = Fwp[r] = Apart[r] = Fvp[r] = 0.0;
+    P13p[r] = P23p[r] = dU[r] = dV[r] = dW[r] = Wwpp[r] = Apart[r] = Fvp[r] = 0.0;
     Eacc[r] = Kacc[r] = PRacc[r] = CHacc[r] = CDacc[r] = hzp[r] = 0.0;
   }
   double acc[FD_N];
@@ -150,14 +159,31 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
 
   const unsigned FULLMASK = 0xffffffffu;
   const bool lane_out = lane < 31 && i <= P.Nx;
+  // per-row output weight (1 for cells this thread reports, 0 for overlap cells) and output offset
+  double wrow[RY];
+  long long orow[RY];
+#pragma unroll
+  for (int r = 0; r < RY; ++r) {
+    const int j = j0 + jr0 + r;
+    wrow[r] = (lane_out && (jr0 + r) < G::BR - 1 && j <= P.Ny) ? 1.0 : 0.0;
+    orow[r] = OUT ? (i * P.os[0] + j * P.os[1]) : 0;
+  }
+  // one predicated accumulate (an FMA with the 0/1 weight) and, for field requests, one predicated store
+  auto emit = [&](int d, double raw, double scale, double w, int plane, int r) {
+    acc[d] = fma(raw, w, acc[d]);
+    if (OUT) {
+      if (w != 0.0 && P.o[d].out) P.o[d].out[orow[r] + (long long)plane * P.os[2]] = raw * scale;
+    }
+  };
 
+  int s = 0;
+  uint32_t phase = 0;
+  int par = 0;
   for (int n = n_first; n <= n_last; ++n) {
-    const int it = n - n_first;
-    const int s = it % NS;
-    mbar_wait(&full[s], (uint32_t)((it / NS) & 1));
-    const double* T = tiles + (size_t)s * NF * G::TILE;
+    mbar_wait(&full[s], phase);
+    const double* T = tiles + s * (NF * G::TILE);
     const double* Tu = T, *Tv = T + G::TILE, *Tw = T + 2 * G::TILE, *Tb = T + F_B * G::TILE, *Tp = T + F_P * G::TILE;
-    const int par = it & 1;
+    if (++s == NS) { s = 0; phase ^= 1; }
 
     // ---- stage 1: quantities owned by this thread's cells at plane n --------------------------------------
     double uc[RY], vc[RY], wc[RY], bc[RY], pc[RY];
@@ -170,18 +196,18 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
       const double* rv = Tv + row * TW + lane + xoff;
       const double* rw = Tw + row * TW + lane + xoff;
       uc[r] = ru[1]; vc[r] = rv[1]; wc[r] = rw[1];
-      const double ue = ru[2], uw = ru[0], us = (r == 0) ? ru[1 - TW] : uc[r > 0 ? r - 1 : 0];
-      const double vw = rv[0], vn = rv[1 + TW], vs = (r == 0) ? rv[1 - TW] : vc[r > 0 ? r - 1 : 0];
+      const double ue = ru[2], us = (r == 0) ? ru[1 - TW] : uc[r > 0 ? r - 1 : 0];
+      const double vw = rv[0], vn = rv[1 + TW];
       const double ww = rw[0], ws = (r == 0) ? rw[1 - TW] : wc[r > 0 ? r - 1 : 0];
-      // ffc edge (i, j): strain and the (Vu = Uv) momentum-flux product
-      const double s12 = (uc[r] - us) * rdy + (vc[r] - vw) * rdx;
+      // ffc edge (i, j): scaled strain (nu/4 folded in) and the (Vu = Uv) momentum-flux product
+      const double s12 = (uc[r] - us) * ey + (vc[r] - vw) * ex;
       const double e12 = s12 * s12;
       P12[r] = (vw + vc[r]) * (us + uc[r]);
       // fcf edge (i, j, n) and cff edge
-      const double s13 = (uc[r] - up[r]) * rdz + (wc[r] - ww) * rdx;
+      const double s13 = (uc[r] - up[r]) * ez + (wc[r] - ww) * ex;
       const double e13 = s13 * s13;
       P13[r] = (ww + wc[r]) * (up[r] + uc[r]);
-      const double s23 = (vc[r] - vp[r]) * rdz + (wc[r] - ws) * rdy;
+      const double s23 = (vc[r] - vp[r]) * ez + (wc[r] - ws) * ey;
       e23[r] = s23 * s23;
       P23[r] = (ws + wc[r]) * (vp[r] + vc[r]);
       // x neighbours' edges by shuffle
@@ -191,41 +217,48 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
         P12E[r] = __shfl_down_sync(FULLMASK, P12[r], 1);
         P13E[r] = __shfl_down_sync(FULLMASK, P13[r], 1);
         Uu[r] = (uc[r] + ue) * (uc[r] + ue);
+        const double uw = ru[0];
         UuW[r] = (uw + uc[r]) * (uw + uc[r]);
         Vv[r] = (vc[r] + vn) * (vc[r] + vn);
-        VvS[r] = (vs + vc[r]) * (vs + vc[r]);
+        if (r == 0) { const double vs = rv[1 - TW]; VvS[r] = (vs + vc[r]) * (vs + vc[r]); }
+        else VvS[r] = Vv[r > 0 ? r - 1 : 0];
       }
-      const double sxx = (ue - uc[r]) * rdx, syy = (vn - vc[r]) * rdy;
-      inpl[r] = 2.0 * (sxx * sxx + syy * syy);            // x nu later
-      Kxy[r] = (uc[r] * uc[r] + ue * ue) + (vc[r] * vc[r] + vn * vn);
+      if (H_EPS) {
+        const double ax = ue - uc[r], ay = vn - vc[r];
+        inpl[r] = fma(ax * ax, dx2, (ay * ay) * dy2);
+      }
+      if (H_K) Kxy[r] = fma(uc[r], uc[r], ue * ue) + fma(vc[r], vc[r], vn * vn);
       if (NEED_P) {
         const double* rp = Tp + row * TW + lane + xoff;
         pc[r] = rp[1];
         const double pw = rp[0], pe = rp[2], ps = rp[1 - TW], pn = rp[1 + TW];
-        PRxy[r] = (uc[r] * (pc[r] - pw) + ue * (pe - pc[r])) * rdx + (vc[r] * (pc[r] - ps) + vn * (pn - pc[r])) * rdy;
+        const double tx_ = fma(ue, pe - pc[r], uc[r] * (pc[r] - pw));
+        const double ty_ = fma(vn, pn - pc[r], vc[r] * (pc[r] - ps));
+        PRxy[r] = fma(ty_, rdy, tx_ * rdx);
       }
       if (NEED_B) {
         const double* rb = Tb + row * TW + lane + xoff;
         bc[r] = rb[1];
         const double dw_ = bc[r] - rb[0], de = rb[2] - bc[r], ds = bc[r] - rb[1 - TW], dn = rb[1 + TW] - bc[r];
-        CHxy[r] = (dw_ * dw_ + de * de) * (rdx * rdx) + (ds * ds + dn * dn) * (rdy * rdy);
-        CDxy[r] = (dw_ - de) * (rdx * rdx) + (ds - dn) * (rdy * rdy);
+        if (H_CHI) CHxy[r] = fma(fma(dw_, dw_, de * de), rdx2, fma(ds, ds, dn * dn) * rdy2);
+        if (H_CDF) CDxy[r] = fma(dw_ - de, rdx2, (ds - dn) * rdy2);
       }
     }
 
     // ---- y exchange between warps: row 0 of the warp to the north ---------------------------------------------
-    double* myx = xch + ((size_t)(par * NW + warp) * NX) * 32 + lane;
+    double* myx = xch + ((par * NW + warp) * NX) * 32 + lane;
     myx[0 * 32] = X12[0]; myx[1 * 32] = P12[0]; myx[2 * 32] = e23[0]; myx[3 * 32] = P23[0]; myx[4 * 32] = Fvp[0];
     __syncthreads();
     // every thread is done with raw stage s: refill it (plane n + NS)
-    if (tid == 0 && n + NS <= n_last) issue(n + NS);
+    if (tid == 0 && n + NS <= n_last) issue(n + NS);   // same ring slot as plane n
     double X12N, P12N, e23N, P23N, FvN;
     if (warp + 1 < NW) {
-      const double* nx_ = xch + ((size_t)(par * NW + warp + 1) * NX) * 32 + lane;
+      const double* nx_ = xch + ((par * NW + warp + 1) * NX) * 32 + lane;
       X12N = nx_[0 * 32]; P12N = nx_[1 * 32]; e23N = nx_[2 * 32]; P23N = nx_[3 * 32]; FvN = nx_[4 * 32];
     } else {
       X12N = P12N = e23N = P23N = FvN = 0.0;
     }
+    const bool p1 = (n - 1) >= k0 && (n - 1) <= k1, p2 = (n - 2) >= k0 && (n - 2) <= k1;
 
     // ---- stage 2 / finalisation, row by row (north neighbour: own row r+1, or the exchanged row) -----------------
 #pragma unroll
@@ -236,95 +269,72 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
       const double e23n = last ? e23N : e23[last ? r : r + 1];
       const double p23n = last ? P23N : P23[last ? r : r + 1];
       const double fvn = last ? FvN : Fvp[last ? r : r + 1];          // Fv(j+1) at plane n-2
-      const int j = j0 + jr0 + r;
-      const bool cell_out = lane_out && (jr0 + r) < G::BR - 1 && j <= P.Ny;
-      const bool v1 = cell_out && (n - 1) >= k0 && (n - 1) <= k1;     // plane n-1 terms
-      const bool v2 = cell_out && (n - 2) >= k0 && (n - 2) <= k1;     // ADV lags one more plane
-      const double Y23 = e23[r] + e23n;
-      const double szz = (wc[r] - wp[r]) * rdz;                        // S33 of cell plane n-1
-      const double wsq = wc[r] * wc[r];
-      // ε(n-1)
+      const double w1 = p1 ? wrow[r] : 0.0;                            // plane n-1 terms
+      const double w2 = p2 ? wrow[r] : 0.0;                            // ADV lags one more plane
+      const double dwz = wc[r] - wp[r];
+      // eps(n-1) = [in-plane + xy edges](n-1) + z strain + the fcf/cff edge sums at faces n-1 and n
       if (H_EPS) {
-        const double edge_n = 0.25 * (Y13[r] + Y23);
-        const double val = P.nu * (Eacc[r] + 2.0 * szz * szz + edge_n);
-        Eacc[r] = inpl[r] + 0.25 * (X12[r] + x12n) + edge_n;
-        if (v1) {
-          acc[FD_EPS] += val;
-          if (P.o[FD_EPS].out) P.o[FD_EPS].out[i * P.o[FD_EPS].os[0] + j * P.o[FD_EPS].os[1] + (long long)(n - 1) * P.o[FD_EPS].os[2]] = val;
-        }
+        const double edge_n = Y13[r] + (e23[r] + e23n);
+        const double raw = fma(dwz * dwz, dz2, Eacc[r] + edge_n);
+        Eacc[r] = (inpl[r] + edge_n) + (X12[r] + x12n);
+        emit(FD_EPS, raw, SC_EPS, w1, n - 1, r);
       }
       if (H_K) {
-        const double val = 0.25 * (Kacc[r] + wsq);
+        const double wsq = wc[r] * wc[r];
+        const double raw = Kacc[r] + wsq;
         Kacc[r] = Kxy[r] + wsq;
-        if (v1) {
-          acc[FD_K] += val;
-          if (P.o[FD_K].out) P.o[FD_K].out[i * P.o[FD_K].os[0] + j * P.o[FD_K].os[1] + (long long)(n - 1) * P.o[FD_K].os[2]] = val;
-        }
+        emit(FD_K, raw, SC_K, w1, n - 1, r);
       }
       if (H_PR) {
-        const double fz = wc[r] * (pc[r] - pp[r]) * rdz;
-        const double val = 0.5 * (PRacc[r] + fz);
-        PRacc[r] = PRxy[r] + fz;
-        if (v1) {
-          acc[FD_PR] += val;
-          if (P.o[FD_PR].out) P.o[FD_PR].out[i * P.o[FD_PR].os[0] + j * P.o[FD_PR].os[1] + (long long)(n - 1) * P.o[FD_PR].os[2]] = val;
-        }
+        const double fz = wc[r] * (pc[r] - pp[r]);
+        const double raw = fma(fz, rdz, PRacc[r]);
+        PRacc[r] = fma(fz, rdz, PRxy[r]);
+        emit(FD_PR, raw, SC_PR, w1, n - 1, r);
       }
       if (NEED_B) {
         const double dbz = bc[r] - bp[r];
         if (H_WB) {
           const double hz = wc[r] * (bp[r] + bc[r]);
-          const double val = 0.25 * P.ghat_z * (hzp[r] + hz);
+          const double raw = hzp[r] + hz;
           hzp[r] = hz;
-          if (v1) {
-            acc[FD_WB] += val;
-            if (P.o[FD_WB].out) P.o[FD_WB].out[i * P.o[FD_WB].os[0] + j * P.o[FD_WB].os[1] + (long long)(n - 1) * P.o[FD_WB].os[2]] = val;
-          }
+          emit(FD_WB, raw, SC_WB, w1, n - 1, r);
         }
         if (H_CHI) {
-          const double gz = dbz * dbz * (rdz * rdz);
-          const double val = P.kappa * (CHacc[r] + gz);
-          CHacc[r] = CHxy[r] + gz;
-          if (v1) {
-            acc[FD_CHI] += val;
-            if (P.o[FD_CHI].out) P.o[FD_CHI].out[i * P.o[FD_CHI].os[0] + j * P.o[FD_CHI].os[1] + (long long)(n - 1) * P.o[FD_CHI].os[2]] = val;
-          }
+          const double gz = dbz * dbz;
+          const double raw = fma(gz, rdz2, CHacc[r]);
+          CHacc[r] = fma(gz, rdz2, CHxy[r]);
+          emit(FD_CHI, raw, SC_CHI, w1, n - 1, r);
         }
         if (H_CDF) {
-          const double qz = dbz * (rdz * rdz);
-          const double val = 2.0 * bp[r] * P.kappa * (CDacc[r] - qz);
-          CDacc[r] = CDxy[r] + qz;
-          if (v1) {
-            acc[FD_CDF] += val;
-            if (P.o[FD_CDF].out) P.o[FD_CDF].out[i * P.o[FD_CDF].os[0] + j * P.o[FD_CDF].os[1] + (long long)(n - 1) * P.o[FD_CDF].os[2]] = val;
-          }
+          const double raw = bp[r] * fma(-dbz, rdz2, CDacc[r]);
+          CDacc[r] = fma(dbz, rdz2, CDxy[r]);
+          emit(FD_CDF, raw, SC_CDF, w1, n - 1, r);
         }
       }
       if (H_ADV) {
-        // faces of plane n-1: F = velocity x flux divergence (the common 1/4 of the flux means is applied at the end)
-        const double Fu = up[r] * (dU[r] + (P13[r] - P13p[r]) * rdz);
-        const double Fv = vp[r] * (dV[r] + (P23[r] - P23p[r]) * rdz);
-        const double Wwp = (wp[r] + wc[r]) * (wp[r] + wc[r]);           // Ww at cell plane n-1
-        const double Fw = wp[r] * (dW[r] + (Wwp - Wwpp[r]) * rdz);      // face n-1
+        // faces of plane n-1: F = velocity x flux divergence (the common 1/8 is the diagnostic's scale factor)
+        const double Fu = up[r] * fma(P13[r] - P13p[r], rdz, dU[r]);
+        const double Fv = vp[r] * fma(P23[r] - P23p[r], rdz, dV[r]);
+        const double wsum = wp[r] + wc[r];
+        const double Wwp = wsum * wsum;                                 // Ww at cell plane n-1
+        const double Fw = wp[r] * fma(Wwp - Wwpp[r], rdz, dW[r]);      // face n-1
         // ADV(n-2) = 1/8 [Fu + FuE + Fv + FvN + Fw(n-2) + Fw(n-1)]
-        const double val = 0.125 * (Apart[r] + fvn + Fw);
+        const double raw = (Apart[r] + fvn) + Fw;
         const double FuE = __shfl_down_sync(FULLMASK, Fu, 1);
-        Apart[r] = (Fu + FuE) + Fv + Fw;
+        Apart[r] = (Fu + FuE) + (Fv + Fw);
         Fvp[r] = Fv;
         Wwpp[r] = Wwp;
-        dU[r] = (Uu[r] - UuW[r]) * rdx + (p12n - P12[r]) * rdy;
-        dV[r] = (P12E[r] - P12[r]) * rdx + (Vv[r] - VvS[r]) * rdy;
-        dW[r] = (P13E[r] - P13[r]) * rdx + (p23n - P23[r]) * rdy;
+        dU[r] = fma(Uu[r] - UuW[r], rdx, (p12n - P12[r]) * rdy);
+        dV[r] = fma(P12E[r] - P12[r], rdx, (Vv[r] - VvS[r]) * rdy);
+        dW[r] = fma(P13E[r] - P13[r], rdx, (p23n - P23[r]) * rdy);
         P13p[r] = P13[r]; P23p[r] = P23[r];
-        if (v2) {
-          acc[FD_ADV] += val;
-          if (P.o[FD_ADV].out) P.o[FD_ADV].out[i * P.o[FD_ADV].os[0] + j * P.o[FD_ADV].os[1] + (long long)(n - 2) * P.o[FD_ADV].os[2]] = val;
-        }
+        emit(FD_ADV, raw, SC_ADV, w2, n - 2, r);
       }
       up[r] = uc[r]; vp[r] = vc[r]; wp[r] = wc[r];
       if (NEED_B) bp[r] = bc[r];
       if (NEED_P) pp[r] = pc[r];
     }
+    par ^= 1;
   }
 
   // ---- volume integrals: warp shuffle, then one partial per block and slot -------------------------------------
@@ -340,7 +350,8 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
       if (tid == 0) {
         double s = 0.0;
         for (int w = 0; w < NW; ++w) s += red[w];
-        P.partial[(size_t)blockIdx.x * P.nslots + P.o[d].slot] = s * P.V;
+        const double scale[FD_N] = {SC_K, SC_ADV, SC_PR, SC_WB, SC_EPS, SC_CHI, SC_CDF};
+        P.partial[(size_t)blockIdx.x * P.nslots + P.o[d].slot] = s * (P.V * scale[d]);
       }
     }
   }
@@ -373,14 +384,22 @@ struct ocb_fused_plan {
 };
 
 template <int MASK, int NW, int RY, int NS>
-static int setup_variant(ocb_fused_plan* fp) {
+static int setup_variant(ocb_fused_plan* fp, bool out) {
   using G = Geo<NW, RY>;
   constexpr bool NEED_B = MASK & ((1 << FD_WB) | (1 << FD_CHI) | (1 << FD_CDF)), NEED_P = MASK & (1 << FD_PR);
   constexpr int NF = 3 + (NEED_B ? 1 : 0) + (NEED_P ? 1 : 0);
-  fp->kernel = ocb_budget_kernel<MASK, NW, RY, NS>;
   fp->nw = NW; fp->ry = RY; fp->ns = NS; fp->mask = MASK;
-  fp->smem = sizeof(double) * ((size_t)NS * NF * G::TILE + 2 * NW * 5 * 32 + NW) + sizeof(uint64_t) * NS + 128;
-  OCB_CUDA(cudaFuncSetAttribute(ocb_budget_kernel<MASK, NW, RY, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp->smem));
+  fp->smem = sizeof(double) * ((size_t)NS * NF * G::TILE + 2 * NW * 5 * 32 + NW) + sizeof(uint64_t) * NS;
+  // ask for the largest shared-memory carveout so that occupancy is set by registers, not by the default split
+  if (out) {
+    cudaFuncSetAttribute(ocb_budget_kernel<MASK, NW, RY, NS, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    fp->kernel = ocb_budget_kernel<MASK, NW, RY, NS, true>;
+    OCB_CUDA(cudaFuncSetAttribute(ocb_budget_kernel<MASK, NW, RY, NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp->smem));
+  } else {
+    cudaFuncSetAttribute(ocb_budget_kernel<MASK, NW, RY, NS, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    fp->kernel = ocb_budget_kernel<MASK, NW, RY, NS, false>;
+    OCB_CUDA(cudaFuncSetAttribute(ocb_budget_kernel<MASK, NW, RY, NS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp->smem));
+  }
   return OCB_OK;
 }
 
@@ -442,6 +461,15 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
     mask |= 1 << d;
   }
   if ((mask & (1 << FD_WB)) && (in->ghat[0] != 0.0 || in->ghat[1] != 0.0)) return OCB_OK;   // vertical gravity only
+  bool any_out = false;
+  long long os[3] = {0, 0, 0};
+  for (int d = 0; d < FD_N; ++d) {
+    if (which_out[d] < 0) continue;
+    const DReq& R = SP.req[which_out[d]];
+    if (any_out && (R.os[0] != os[0] || R.os[1] != os[1] || R.os[2] != os[2])) return OCB_OK;   // one layout for all outputs
+    any_out = true;
+    for (int a = 0; a < 3; ++a) os[a] = R.os[a];
+  }
   const bool need_b = mask & ((1 << FD_WB) | (1 << FD_CHI) | (1 << FD_CDF)), need_p = mask & (1 << FD_PR);
   if (!tma_compatible(in->u, grid) || !tma_compatible(in->v, grid) || !tma_compatible(in->w, grid)) return OCB_OK;
   if (need_b && !tma_compatible(in->b, grid)) return OCB_OK;
@@ -457,17 +485,27 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
   constexpr int ALL = (1 << FD_N) - 1;
   int rc;
   const char* cfg = getenv("OCB_FUSED_CONFIG");   // tuning hook: "NW,RY,NS"
-  int nw = 6, ry = 2, ns = 3;
+  int nw = 12, ry = 1, ns = 3;   // measured best on B200 at 1024^3 (profiles/r1_tuning.md)
   if (cfg) sscanf(cfg, "%d,%d,%d", &nw, &ry, &ns);
+  constexpr int VEL = (1 << FD_K) | (1 << FD_ADV) | (1 << FD_EPS);                 // velocity-only terms
+  constexpr int VELP = VEL | (1 << FD_PR);                                          // + pressure
+  constexpr int VELB = VEL | (1 << FD_WB) | (1 << FD_CHI) | (1 << FD_CDF);          // + tracer
   if (mask == (1 << FD_EPS)) {
-    rc = setup_variant<(1 << FD_EPS), 6, 2, 3>(fp);
+    rc = setup_variant<(1 << FD_EPS), 12, 1, 3>(fp, any_out);
+  } else if ((mask & ~VEL) == 0) {
+    rc = setup_variant<VEL, 12, 1, 3>(fp, any_out);
+  } else if ((mask & ~VELP) == 0) {
+    rc = setup_variant<VELP, 12, 1, 3>(fp, any_out);
+  } else if ((mask & ~VELB) == 0) {
+    rc = setup_variant<VELB, 12, 1, 3>(fp, any_out);
   } else {
-    if (nw == 4 && ry == 2) rc = setup_variant<ALL, 4, 2, 3>(fp);
-    else if (nw == 8 && ry == 1) rc = setup_variant<ALL, 8, 1, 3>(fp);
-    else if (nw == 8 && ry == 2) rc = setup_variant<ALL, 8, 2, 3>(fp);
-    else if (nw == 12 && ry == 2) rc = setup_variant<ALL, 12, 2, 3>(fp);
-    else if (nw == 6 && ry == 3) rc = setup_variant<ALL, 6, 3, 3>(fp);
-    else rc = setup_variant<ALL, 6, 2, 3>(fp);
+    if (nw == 4 && ry == 2) rc = setup_variant<ALL, 4, 2, 3>(fp, any_out);
+    else if (nw == 8 && ry == 1) rc = setup_variant<ALL, 8, 1, 3>(fp, any_out);
+    else if (nw == 8 && ry == 2) rc = setup_variant<ALL, 8, 2, 3>(fp, any_out);
+    else if (nw == 12 && ry == 2) rc = setup_variant<ALL, 12, 2, 3>(fp, any_out);
+    else if (nw == 12 && ry == 1) rc = setup_variant<ALL, 12, 1, 3>(fp, any_out);
+    else if (nw == 6 && ry == 2) rc = setup_variant<ALL, 6, 2, 3>(fp, any_out);
+    else rc = setup_variant<ALL, 12, 1, 3>(fp, any_out);
   }
   if (rc != OCB_OK) { delete fp; return rc; }
   const bool vneed_b = fp->mask & ((1 << FD_WB) | (1 << FD_CHI) | (1 << FD_CDF)), vneed_p = fp->mask & (1 << FD_PR);
@@ -492,13 +530,10 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
   P.nu = in->closure.nu_const; P.kappa = in->closure.kappa_const; P.ghat_z = in->ghat[2];
   P.V = grid->d[0] * grid->d[1] * grid->d[2];
   P.nslots = SP.nslots;
+  for (int a = 0; a < 3; ++a) P.os[a] = os[a];
   for (int d = 0; d < FD_N; ++d) {
-    P.o[d].out = nullptr; P.o[d].slot = -1; P.o[d].os[0] = P.o[d].os[1] = P.o[d].os[2] = 0;
-    if (which_out[d] >= 0) {
-      const DReq& R = SP.req[which_out[d]];
-      P.o[d].out = (double*)R.out;
-      for (int a = 0; a < 3; ++a) P.o[d].os[a] = R.os[a];
-    }
+    P.o[d].out = nullptr; P.o[d].slot = -1;
+    if (which_out[d] >= 0) P.o[d].out = (double*)SP.req[which_out[d]].out;
     if (which_slot[d] >= 0) P.o[d].slot = SP.req[which_slot[d]].slot;
   }
   const ocb_field* f[5] = {&in->u, &in->v, &in->w, vneed_b ? &in->b : &in->u, vneed_p ? &in->p : &in->u};

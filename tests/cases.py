@@ -116,10 +116,19 @@ def richardson_tolerance(st, vdir, want, rtol=1e-12):
     dudy = K.iy_aca(i, j, k, og, K.ddy_cfc, K.uh_norm_ccc, *a)
     dudz = K.ddz_ccf(i, j, k, og, K.uh_norm_ccc, *a)
     total = np.abs(dudx * vdir[0] + dudy * vdir[1] + dudz * vdir[2])
+    # numerator: the projected buoyancy gradient is also a sum of differences that can cancel
+    ab = lambda ii, jj, kk: np.abs(st.ob[ii, jj, kk])
+    magb = (abs(vdir[2]) * rdz * (ab(i, j, k) + ab(i, j, k - 1))
+            + abs(vdir[0]) * rdx * 0.25 * (ab(i + 1, j, k) + ab(i - 1, j, k) + ab(i + 1, j, k - 1) + ab(i - 1, j, k - 1))
+            + abs(vdir[1]) * rdy * 0.25 * (ab(i, j + 1, k) + ab(i, j - 1, k) + ab(i, j + 1, k - 1) + ab(i, j - 1, k - 1)))
+    dbdx = K.ixz_caf(i, j, k, og, K.ddx_fcc, st.ob)
+    dbdy = K.iyz_acf(i, j, k, og, K.ddy_cfc, st.ob)
+    dbdz = K.ddz_ccf(i, j, k, og, st.ob)
+    totalb = np.abs(dbdx * vdir[0] + dbdy * vdir[1] + dbdz * vdir[2])
     with np.errstate(divide="ignore", invalid="ignore"):
-        cond = np.where(total > 0, mag / total, np.inf)
+        cond = np.where(total > 0, mag / total, np.inf) * 2 + np.where(totalb > 0, magb / totalb, np.inf)
     eps = np.finfo(og.dtype).eps
-    return np.abs(want) * (rtol + 32 * eps * cond)
+    return np.abs(want) * (rtol + 16 * eps * cond)
 
 
 def check_case(st, name, got, want, rtol=1e-12):

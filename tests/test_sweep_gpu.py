@@ -76,7 +76,7 @@ def test_windowed_destination_matches_full():
     win.compute()
     torch.cuda.synchronize()
     a = full.interior_ijk()[2:11, 1:9, 4:5]
-    np.testing.assert_array_equal(win.interior_ijk(), a)
+    np.testing.assert_allclose(win.interior_ijk(), a, rtol=1e-13, atol=0)   # full: pipelined kernel, window: generic kernel
     assert float(win.data[0, 0, 0]) == -7.0      # nothing outside the window's interior was touched
 
 
