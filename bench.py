@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--cpu-size", type=int, default=192, help="edge of the CPU-baseline sample cube")
+    ap.add_argument("--cpu-size", type=int, default=256, help="edge of the CPU-baseline sample cube")
     return ap.parse_args()
 
 

@@ -40,6 +40,7 @@ struct FusedParams {
   int Nx, Ny, Nz;
   int hx, hy, hz;                  // parent index of 1-based index i is i + hx - 1
   int tiles_x, tiles_y, nchunks, kchunk;
+  int kz_lo, kz_hi;                // 1-based inclusive z window (the whole interior, or a z slab of it)
   double rdx, rdy, rdz, nu, kappa, ghat_z, V;
   FusedOut o[FD_N];
   long long os[3];                 // element strides shared by every output field
@@ -100,8 +101,8 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
   const int ty = bid % P.tiles_y; bid /= P.tiles_y;
   const int chunk = bid;
   const int i0 = 1 + 31 * tx, j0 = 1 + (G::BR - 1) * ty;
-  const int k0 = 1 + chunk * P.kchunk;
-  const int k1 = min(k0 + P.kchunk - 1, P.Nz);
+  const int k0 = P.kz_lo + chunk * P.kchunk;
+  const int k1 = min(k0 + P.kchunk - 1, P.kz_hi);
   const int n_first = k0 - 1, n_last = k1 + 2;
   const int i = i0 + lane;
   const int jr0 = warp * RY;                           // first block-row of this thread
@@ -455,7 +456,8 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
     }
     if (reqs[r].flags & OCB_REQ_PERTURBATION) return OCB_OK;
     const DReq& R = SP.req[r];
-    if (R.lo[0] != 1 || R.lo[1] != 1 || R.lo[2] != 1 || R.hi[0] != grid->N[0] || R.hi[1] != grid->N[1] || R.hi[2] != grid->N[2]) return OCB_OK;
+    if (R.lo[0] != 1 || R.lo[1] != 1 || R.hi[0] != grid->N[0] || R.hi[1] != grid->N[1]) return OCB_OK;   // full x, y extent
+    if (r > 0 && (R.lo[2] != SP.req[0].lo[2] || R.hi[2] != SP.req[0].hi[2])) return OCB_OK;                 // one z window
     if (R.out) { if (which_out[d] >= 0) return OCB_OK; which_out[d] = r; }
     if (R.slot >= 0) { if (which_slot[d] >= 0) return OCB_OK; which_slot[d] = r; }
     mask |= 1 << d;
@@ -518,13 +520,15 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
   P.tiles_x = (P.Nx + 30) / 31;
   P.tiles_y = (P.Ny + BR - 2) / (BR - 1);
   const int tiles = P.tiles_x * P.tiles_y;
+  P.kz_lo = SP.req[0].lo[2]; P.kz_hi = SP.req[0].hi[2];
+  const int nz_win = P.kz_hi - P.kz_lo + 1;
   int nchunks = (ocb_sm_count() * 8 + tiles - 1) / tiles;
   if (nchunks < 1) nchunks = 1;
-  int kchunk = (P.Nz + nchunks - 1) / nchunks;
-  if (kchunk < 32) kchunk = P.Nz < 32 ? P.Nz : 32;
+  int kchunk = (nz_win + nchunks - 1) / nchunks;
+  if (kchunk < 32) kchunk = nz_win < 32 ? nz_win : 32;
   if (const char* kc = getenv("OCB_FUSED_KCHUNK")) kchunk = atoi(kc) > 0 ? atoi(kc) : kchunk;
   P.kchunk = kchunk;
-  P.nchunks = (P.Nz + kchunk - 1) / kchunk;
+  P.nchunks = (nz_win + kchunk - 1) / kchunk;
   fp->nblocks = tiles * P.nchunks;
   P.rdx = 1.0 / grid->d[0]; P.rdy = 1.0 / grid->d[1]; P.rdz = 1.0 / grid->d[2];
   P.nu = in->closure.nu_const; P.kappa = in->closure.kappa_const; P.ghat_z = in->ghat[2];

@@ -180,6 +180,18 @@ class Field(AbstractField):
                                    current_stream_ptr(self.data.device)))
         return self
 
+    def fill_halo_regions_xz(self):
+        """Halo fill in x and z only: the y halos of a y-slab come from the ring neighbours (distributed.py)."""
+        if self.data.device.type != "cuda":
+            raise _lib.OcbError("fill_halo_regions needs a CUDA field: liboceanostics_b200 has no CPU fallback")
+        import ctypes as C
+        desc, gd = self.descriptor(), self.grid.descriptor()
+        desc.loc[1] = _lib.OCB_NOTHING          # skip the y pass; x and z passes still run over whole rows
+        _lib.check(_lib.lib().ocb_fill_halo(C.byref(gd), C.byref(desc), int(self.boundary["impenetrable"]),
+                                            float(self.boundary["zgrad_bottom"]), float(self.boundary["zgrad_top"]),
+                                            current_stream_ptr(self.data.device)))
+        return self
+
     def __repr__(self):
         loc = ", ".join({Center: "Center", Face: "Face", None: "Nothing"}[l] for l in self.location)
         return f"{self.extent[0]}×{self.extent[1]}×{self.extent[2]} Field at ({loc}) on {self.grid.device}"

@@ -201,20 +201,27 @@ class ComputedField(Field):
 class Reduction(AbstractOperation):
     """`Integral(op)` / `Average(op)` over the whole volume (`dims=:`)."""
 
-    def __init__(self, kind, operand):
+    def __init__(self, kind, operand, indices=None):
         if not isinstance(operand, KernelFunctionOperation):
             raise TypeError("Integral / Average take a KernelFunctionOperation of this library")
         self.kind, self.operand, self.grid = kind, operand, operand.grid
+        # optional 1-based inclusive index window per axis (the reduction of a windowed view of the operand)
+        self.window = None
+        if indices is not None:
+            ext = self.grid.extent_of(operand.location)
+            self.window = [(1, ext[d]) if w is None else (int(w[0]), int(w[1])) for d, w in enumerate(indices)]
 
     def _as_computed_field(self):
         return ReducedField(self)
 
 
-def Integral(op):
-    return Reduction("integral", op)
+def Integral(op, indices=None):
+    return Reduction("integral", op, indices)
 
 
-def Average(op):
+def Average(op, indices=None):
+    if indices is not None:
+        raise ValueError("Average over an index window is not supported; use Integral(op, indices=...)")
     return Reduction("average", op)
 
 
@@ -275,18 +282,22 @@ def assemble_sweep(items):
     """Merge the operands of `items` = [(operation, destination Field or None, integral slot or -1)] and build the
     C descriptors of one fused sweep.  Returns (operands, ocb_sweep_inputs, ocb_request array, number of slots)."""
     operands = SweepOperands()
-    for op, _, _ in items:
-        operands = operands.merged_with(op.operands)
+    for item in items:
+        operands = operands.merged_with(item[0].operands)
         if operands is None:
             raise ValueError("these diagnostics read conflicting operands and cannot share one sweep")
-    n_slots = 1 + max([s for _, _, s in items] + [-1])
+    n_slots = 1 + max([item[2] for item in items] + [-1])
     reqs = (_lib.ocb_request * len(items))()
-    for r, (op, dest, slot) in enumerate(items):
-        fill_request(reqs[r], op, dest, slot)
+    for r, item in enumerate(items):
+        op, dest, slot = item[:3]
+        fill_request(reqs[r], op, dest, slot, item[3] if len(item) > 3 else None)
     return operands, operands.descriptor(), reqs, n_slots
 
 
-def fill_request(req, op: KernelFunctionOperation, dest, slot):
+def fill_request(req, op: KernelFunctionOperation, dest, slot, window=None):
+    if window is not None:
+        for d in range(3):
+            req.window_lo[d], req.window_hi[d] = window[d]
     req.diag = _lib.DIAG[op.diag]
     req.flags = op.flags
     req.integral_slot = slot
@@ -316,7 +327,7 @@ def compute(field, time=None):
         return field
     if isinstance(field, ReducedField):
         if getattr(field, "_plan", None) is None:
-            field._plan = SweepPlan(field.grid, [(field.operand, None, 0)])
+            field._plan = SweepPlan(field.grid, [(field.operand, None, 0, field.reduction.window)])
         _refresh_arguments(field._plan.operands, time)
         field._plan.execute()
         field.result.copy_(field._plan.integrals[:1])
@@ -364,7 +375,7 @@ class FusedDiagnostics:
         items, slot = [], 0
         for m in self.members:
             if isinstance(m, ReducedField):
-                items.append((m.operand, None, slot))
+                items.append((m.operand, None, slot, m.reduction.window))
                 m._slot = slot
                 slot += 1
             else:

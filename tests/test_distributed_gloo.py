@@ -1,0 +1,83 @@
+"""World-size-2 gloo tests (CPU) of the multi-GPU host logic: the slab partition, the ring halo-exchange schedule and
+the all-reduce of the integral vector.  The pack / unpack kernels are CUDA-only, so the CPU test injects
+torch-slicing packers with the same buffer layout; the CUDA packers are tested in test_multigpu_gpu.py."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from helpers import ocb
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _pack_torch(field, side, h, buf):
+    Hy, ext = field.halo[1], field.stored[1]
+    j0 = Hy if side == 0 else Hy + ext - h
+    buf.copy_(field.data[:, j0:j0 + h, :])
+
+
+def _unpack_torch(field, side, h, buf):
+    Hy, ext = field.halo[1], field.stored[1]
+    j0 = Hy - h if side == 0 else Hy + ext
+    field.data[:, j0:j0 + h, :].copy_(buf)
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oceanostics_b200.distributed import SlabHaloExchanger, slab_range, allreduce_integrals
+    Nx, Ny, Nz, H = 6, 8, 4, 3
+    lo, hi = slab_range(Ny, rank, world)
+    g = ocb.RectilinearGrid((Nx, hi - lo + 1, Nz), extent=(1, 1, 1), device="cpu")
+    f = ocb.Field(("c", "c", "c"), g)
+    w = ocb.Field(("c", "c", "f"), g)
+    # value = global linear index of the cell, so halos can be checked against the periodic global field
+    for fld in (f, w):
+        nz = fld.stored[2]
+        kk, jj, ii = torch.meshgrid(torch.arange(nz), torch.arange(lo - 1, hi), torch.arange(Nx), indexing="ij")
+        fld.interior.copy_((kk * 1000 + jj * 10 + ii).double())
+    ex = SlabHaloExchanger(g, [f, w], depth=2, pack=_pack_torch, unpack=_unpack_torch)
+    ex.exchange()
+    ok = True
+    for fld in (f, w):
+        nz = fld.stored[2]
+        for m in range(1, 3):   # two halo planes each side
+            below = ((lo - 1 - m) % Ny)
+            above = ((hi - 1 + m) % Ny)
+            got_lo = fld.data[H:H + nz, H - m, H:H + Nx]
+            got_hi = fld.data[H:H + nz, H + (hi - lo + 1) - 1 + m, H:H + Nx]
+            kk, ii = torch.meshgrid(torch.arange(nz), torch.arange(Nx), indexing="ij")
+            ok &= bool(torch.equal(got_lo, (kk * 1000 + below * 10 + ii).double()))
+            ok &= bool(torch.equal(got_hi, (kk * 1000 + above * 10 + ii).double()))
+    ints = torch.tensor([float(rank + 1), 10.0 * (rank + 1)], dtype=torch.float64)
+    allreduce_integrals(ints)
+    ok &= ints.tolist() == [3.0, 30.0]
+    out[rank] = ok
+    dist.destroy_process_group()
+
+
+def test_slab_ranges_partition_the_axis():
+    from oceanostics_b200.distributed import slab_range
+    for n, world in ((1024, 8), (10, 4), (7, 2)):
+        r = [slab_range(n, k, world) for k in range(world)]
+        assert r[0][0] == 1 and r[-1][1] == n
+        assert all(r[k][1] + 1 == r[k + 1][0] for k in range(world - 1))
+
+
+@pytest.mark.timeout(120)
+def test_ring_halo_exchange_and_allreduce_world2():
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert out[0] and out[1]
