@@ -12,6 +12,7 @@ from .operations import (KernelFunctionOperation, ComputedField, ReducedField, I
                          SweepOperands, SweepPlan, compute, compute_at)
 from .models import (NonhydrostaticModel, HydrostaticFreeSurfaceModel, FPlane, ConstantCartesianCoriolis, BuoyancyTracer,
                      get_coriolis_frequency_components)
-from . import KineticEnergyEquation, TurbulentKineticEnergyEquation, TracerVarianceEquation, FlowDiagnostics
+from . import KineticEnergyEquation, TurbulentKineticEnergyEquation, TracerVarianceEquation, FlowDiagnostics, SpatialFilters, BackgroundPotentialEnergyEquation
+from .SpatialFilters import BoxFilter, GaussianFilter
 
 ScalarDiffusivity = Closure

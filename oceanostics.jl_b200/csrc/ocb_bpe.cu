@@ -1,3 +1,473 @@
+// K3: sort-based reference height z✶ for the background potential energy
+// (reference: compute!(::SortedReferenceHeightField), src/BackgroundPotentialEnergyEquation.jl:610-619, with
+// rank_by_buoyancy! :310-316, slot_centers! :326-331, slot_faces :339-348, reference_potential_function :359-368,
+// fill_reference_potential! :383-397, assign_reference_height! for ThreeDimensionalSort :413-426 and
+// HeavisideIntegral :428-466).
+//
+// The reference calls sortperm! (Base on the CPU, CUDA.jl's on the GPU).  Here the sort is a hand-written stable LSD
+// radix sort (8-bit digits) of order-preserving integer keys with a 32-bit index payload:
+//   per pass   histogram (per-tile digit counts, digit-major table)  ->  exclusive scan of the table  ->
+//              stable scatter (warp match-any ranking, per-warp digit counters, tile offsets from the scan)
+// Stable means ties keep their original (column-major) order, which is what Base.sortperm! does on the CPU; the
+// reference's GPU sort gives no such guarantee, hence only permutation-invariant results are compared.
+// Key transform: flip all bits of negative floats, set the sign bit of non-negative ones -- Julia's isless order on
+// finite values and on ±0 (-0.0 < +0.0).
+//
+// The epilogues (cumulative volume -> slot centres and faces, Ψ by a second scan and a binary search per cell,
+// run detection with max / reversed-min scans for HeavisideIntegral, scatter back through the permutation) are
+// block-scan kernels over the sorted arrays.  All scratch is stream-ordered and owned by the library.
 #include "ocb_common.cuh"
-extern "C" int ocb_bpe_reference_height(const ocb_grid*, const ocb_field*, int32_t, const ocb_field*, const ocb_field*, int64_t*, void*, void*) { OCB_FAIL(OCB_ERR_UNSUPPORTED, "bpe: under construction"); }
-extern "C" int ocb_sort_pairs(int32_t, const void*, void*, uint32_t*, int64_t, void*) { OCB_FAIL(OCB_ERR_UNSUPPORTED, "sort: under construction"); }
+#include <float.h>
+
+namespace {
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;   // keys per block
+constexpr int RS_WARPS = RS_THREADS / 32;
+
+template <class K> struct KeyTraits;
+template <> struct KeyTraits<uint64_t> { using F = double; static constexpr int BITS = 64; };
+template <> struct KeyTraits<uint32_t> { using F = float; static constexpr int BITS = 32; };
+
+__device__ __forceinline__ uint64_t to_key(double v) {
+  uint64_t u = (uint64_t)__double_as_longlong(v);
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double from_key(uint64_t k) {
+  uint64_t u = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+  return __longlong_as_double((long long)u);
+}
+__device__ __forceinline__ uint32_t to_key(float v) {
+  uint32_t u = __float_as_uint(v);
+  return (u >> 31) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float from_key(uint32_t k) {
+  uint32_t u = (k >> 31) ? (k & 0x7fffffffu) : ~k;
+  return __uint_as_float(u);
+}
+
+// keys from a flat float array, payload = 0-based index
+template <class K>
+__global__ void rs_make_keys(const typename KeyTraits<K>::F* __restrict__ v, K* __restrict__ keys, uint32_t* __restrict__ idx, long long n) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t < n) { keys[t] = to_key(v[t]); idx[t] = (uint32_t)t; }
+}
+template <class K>
+__global__ void rs_unmake_keys(const K* __restrict__ keys, typename KeyTraits<K>::F* __restrict__ v, long long n) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t < n) v[t] = from_key(keys[t]);
+}
+
+// per-tile digit histogram, written digit-major: table[digit * nblocks + block]
+template <class K>
+__global__ void __launch_bounds__(RS_THREADS) rs_histogram(const K* __restrict__ keys, long long n, int shift, uint32_t* __restrict__ table, int nblocks) {
+  __shared__ uint32_t h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const long long base = (long long)blockIdx.x * RS_TILE;
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; ++r) {
+    const long long t = base + r * RS_THREADS + threadIdx.x;
+    if (t < n) atomicAdd(&h[(uint32_t)(keys[t] >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  table[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+}
+
+// stable scatter of one tile: warp w owns the contiguous sub-tile [w*512, (w+1)*512), walked in 16 rounds of 32
+template <class K>
+__global__ void __launch_bounds__(RS_THREADS) rs_scatter(const K* __restrict__ keys_in, const uint32_t* __restrict__ idx_in, K* __restrict__ keys_out,
+                                                          uint32_t* __restrict__ idx_out, long long n, int shift,
+                                                          const uint32_t* __restrict__ offsets, int nblocks) {
+  __shared__ uint32_t wcount[RS_WARPS][256];     // per-warp running digit counts -> per-warp digit bases
+  __shared__ uint32_t gbase[256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int d = lane; d < 256; d += 32) wcount[warp][d] = 0;
+  gbase[threadIdx.x] = offsets[(size_t)threadIdx.x * nblocks + blockIdx.x];
+  __syncwarp();
+  const long long wbase = (long long)blockIdx.x * RS_TILE + (long long)warp * (RS_ITEMS * 32);
+  K key[RS_ITEMS];
+  uint32_t rank[RS_ITEMS];
+  const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; ++r) {
+    const long long t = wbase + r * 32 + lane;
+    const bool ok = t < n;
+    key[r] = ok ? keys_in[t] : (K)~(K)0;
+    const uint32_t dig = ok ? ((uint32_t)(key[r] >> shift) & 255u) : 256u;    // 256: out of range, matches only other padding
+    const unsigned peers = __match_any_sync(0xffffffffu, dig);
+    uint32_t prev = 0;
+    if (ok) {
+      prev = wcount[warp][dig];
+      __syncwarp(peers);
+      if ((peers & lt) == 0) wcount[warp][dig] = prev + __popc(peers);       // the lowest lane of each digit group updates
+    }
+    __syncwarp();
+    rank[r] = prev + __popc(peers & lt);
+  }
+  __syncthreads();
+  // exclusive scan across warps for each digit: thread d handles digit d
+  {
+    uint32_t run = 0;
+    const int d = threadIdx.x;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) { const uint32_t c = wcount[w][d]; wcount[w][d] = run; run += c; }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; ++r) {
+    const long long t = wbase + r * 32 + lane;
+    if (t < n) {
+      const uint32_t dig = (uint32_t)(key[r] >> shift) & 255u;
+      const uint32_t pos = gbase[dig] + wcount[warp][dig] + rank[r];
+      keys_out[pos] = key[r];
+      idx_out[pos] = idx_in[t];
+    }
+  }
+}
+
+// ---- block scans ----------------------------------------------------------------------------------------------
+enum { OP_ADD = 0, OP_MAX = 1, OP_MIN = 2 };
+template <class T, int OP> __device__ __forceinline__ T sc_op(T a, T b) { return OP == OP_ADD ? a + b : (OP == OP_MAX ? (a > b ? a : b) : (a < b ? a : b)); }
+template <class T, int OP> __device__ __forceinline__ T sc_identity();
+template <> __device__ __forceinline__ uint32_t sc_identity<uint32_t, OP_ADD>() { return 0u; }
+template <> __device__ __forceinline__ double sc_identity<double, OP_ADD>() { return 0.0; }
+template <> __device__ __forceinline__ double sc_identity<double, OP_MAX>() { return -DBL_MAX; }
+template <> __device__ __forceinline__ double sc_identity<double, OP_MIN>() { return DBL_MAX; }
+
+constexpr int SC_THREADS = 256, SC_ITEMS = 8, SC_CHUNK = SC_THREADS * SC_ITEMS;
+
+// inclusive scan of one chunk held as SC_ITEMS consecutive items per thread; returns the chunk total
+template <class T, int OP>
+__device__ __forceinline__ T block_scan_chunk(T (&x)[SC_ITEMS], T* sh) {
+  T run = x[0];
+#pragma unroll
+  for (int q = 1; q < SC_ITEMS; ++q) { run = sc_op<T, OP>(run, x[q]); x[q] = run; }
+  // scan of the per-thread totals: warp shuffle, then across warps
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  T v = run;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { T u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v = sc_op<T, OP>(u, v); }
+  if (lane == 31) sh[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    T wv = lane < SC_THREADS / 32 ? sh[lane] : sc_identity<T, OP>();
+#pragma unroll
+    for (int o = 1; o < SC_THREADS / 32; o <<= 1) { T u = __shfl_up_sync(0xffffffffu, wv, o); if (lane >= o) wv = sc_op<T, OP>(u, wv); }
+    if (lane < SC_THREADS / 32) sh[lane] = wv;
+  }
+  __syncthreads();
+  const T total = sh[SC_THREADS / 32 - 1];
+  T excl = sc_identity<T, OP>();                 // exclusive prefix of this thread
+  if (warp > 0) excl = sh[warp - 1];
+  T up = __shfl_up_sync(0xffffffffu, v, 1);
+  if (lane > 0) excl = sc_op<T, OP>(excl, up);
+#pragma unroll
+  for (int q = 0; q < SC_ITEMS; ++q) x[q] = sc_op<T, OP>(excl, x[q]);
+  __syncthreads();
+  return total;
+}
+
+// phase 1: chunk totals.  REV: the scan runs from the end of the array (element n-1 first).
+template <class T, int OP, bool REV>
+__global__ void __launch_bounds__(SC_THREADS) sc_chunk_totals(const T* __restrict__ in, long long n, T* __restrict__ totals) {
+  __shared__ T sh[SC_THREADS / 32];
+  T x[SC_ITEMS];
+  const long long base = (long long)blockIdx.x * SC_CHUNK + (long long)threadIdx.x * SC_ITEMS;
+#pragma unroll
+  for (int q = 0; q < SC_ITEMS; ++q) { const long long t = base + q; x[q] = t < n ? in[REV ? n - 1 - t : t] : sc_identity<T, OP>(); }
+  const T total = block_scan_chunk<T, OP>(x, sh);
+  if (threadIdx.x == 0) totals[blockIdx.x] = total;
+}
+// phase 2: exclusive scan of the chunk totals by one block (loops when there are more than SC_CHUNK chunks)
+template <class T, int OP>
+__global__ void __launch_bounds__(SC_THREADS) sc_scan_totals(T* __restrict__ totals, int nchunks) {
+  __shared__ T sh[SC_THREADS / 32];
+  __shared__ T last[SC_THREADS];
+  T carry = sc_identity<T, OP>();
+  for (long long base0 = 0; base0 < nchunks; base0 += SC_CHUNK) {
+    T x[SC_ITEMS];
+    const long long base = base0 + (long long)threadIdx.x * SC_ITEMS;
+#pragma unroll
+    for (int q = 0; q < SC_ITEMS; ++q) { const long long t = base + q; x[q] = t < nchunks ? totals[t] : sc_identity<T, OP>(); }
+    const T total = block_scan_chunk<T, OP>(x, sh);
+    last[threadIdx.x] = x[SC_ITEMS - 1];
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < SC_ITEMS; ++q) {
+      const long long t = base + q;
+      if (t < nchunks) {   // exclusive value = carry (op) inclusive value of the previous element
+        const T prev = q > 0 ? x[q - 1] : (threadIdx.x > 0 ? last[threadIdx.x - 1] : sc_identity<T, OP>());
+        totals[t] = sc_op<T, OP>(carry, prev);
+      }
+    }
+    carry = sc_op<T, OP>(carry, total);
+    __syncthreads();
+  }
+}
+// phase 3: scan each chunk and combine with its prefix.  EXCL: write the exclusive scan.
+template <class T, int OP, bool REV, bool EXCL>
+__global__ void __launch_bounds__(SC_THREADS) sc_apply(const T* __restrict__ in, long long n, const T* __restrict__ totals, T* __restrict__ out) {
+  __shared__ T sh[SC_THREADS / 32];
+  __shared__ T last[SC_THREADS];
+  T x[SC_ITEMS];
+  const long long base = (long long)blockIdx.x * SC_CHUNK + (long long)threadIdx.x * SC_ITEMS;
+#pragma unroll
+  for (int q = 0; q < SC_ITEMS; ++q) { const long long t = base + q; x[q] = t < n ? in[REV ? n - 1 - t : t] : sc_identity<T, OP>(); }
+  block_scan_chunk<T, OP>(x, sh);
+  const T prefix = totals[blockIdx.x];
+  if (EXCL) { last[threadIdx.x] = x[SC_ITEMS - 1]; __syncthreads(); }
+#pragma unroll
+  for (int q = 0; q < SC_ITEMS; ++q) {
+    const long long t = base + q;
+    if (t < n) {
+      T v;
+      if (EXCL) {
+        T prev = q > 0 ? x[q - 1] : (threadIdx.x > 0 ? last[threadIdx.x - 1] : sc_identity<T, OP>());
+        v = sc_op<T, OP>(prefix, prev);
+      } else {
+        v = sc_op<T, OP>(prefix, x[q]);
+      }
+      out[REV ? n - 1 - t : t] = v;
+    }
+  }
+}
+
+template <class T, int OP, bool REV, bool EXCL>
+int device_scan(const T* in, T* out, long long n, T* totals_scratch, cudaStream_t st) {
+  const int nchunks = (int)((n + SC_CHUNK - 1) / SC_CHUNK);
+  sc_chunk_totals<T, OP, REV><<<nchunks, SC_THREADS, 0, st>>>(in, n, totals_scratch);
+  sc_scan_totals<T, OP><<<1, SC_THREADS, 0, st>>>(totals_scratch, nchunks);
+  sc_apply<T, OP, REV, EXCL><<<nchunks, SC_THREADS, 0, st>>>(in, n, totals_scratch, out);
+  OCB_CUDA(cudaGetLastError());
+  return OCB_OK;
+}
+
+template <class K>
+int radix_sort_pairs(K* keys_a, uint32_t* idx_a, K* keys_b, uint32_t* idx_b, long long n, uint32_t* table, uint32_t* table_tot,
+                     int nblocks, cudaStream_t st, K** keys_sorted, uint32_t** idx_sorted) {
+  K* kin = keys_a; K* kout = keys_b;
+  uint32_t* iin = idx_a; uint32_t* iout = idx_b;
+  const long long ntab = 256ll * nblocks;
+  for (int shift = 0; shift < KeyTraits<K>::BITS; shift += 8) {
+    rs_histogram<K><<<nblocks, RS_THREADS, 0, st>>>(kin, n, shift, table, nblocks);
+    int rc = device_scan<uint32_t, OP_ADD, false, true>(table, table, ntab, table_tot, st);
+    if (rc != OCB_OK) return rc;
+    rs_scatter<K><<<nblocks, RS_THREADS, 0, st>>>(kin, iin, kout, iout, n, shift, table, nblocks);
+    K* tk = kin; kin = kout; kout = tk;
+    uint32_t* ti = iin; iin = iout; iout = ti;
+  }
+  OCB_CUDA(cudaGetLastError());
+  *keys_sorted = kin; *idx_sorted = iin;
+  return OCB_OK;
+}
+
+// ---- BPE epilogue kernels ---------------------------------------------------------------------------------------
+template <class T>
+__global__ void bpe_gather_interior(const T* __restrict__ b, long long s0, long long s1, long long s2, int Nx, int Ny, long long n, T* __restrict__ work) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;   // b pre-offset to index (1,1,1) -> element 0
+  if (t >= n) return;
+  const int i = (int)(t % Nx), j = (int)((t / Nx) % Ny), k = (int)(t / ((long long)Nx * Ny));
+  work[t] = b[i * s0 + j * s1 + k * s2];
+}
+// sorted cell volumes: dV[n] = dx*dy*dzc[k(perm[n])]
+template <class T>
+__global__ void bpe_sorted_volumes(const uint32_t* __restrict__ perm, long long n, int Nx, int Ny, T dxdy, const T* __restrict__ dzc1, T dz_uniform,
+                                   double* __restrict__ dV) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const long long k = perm[t] / ((long long)Nx * Ny);
+  const T dz = dzc1 ? dzc1[k] : dz_uniform;
+  dV[t] = (double)(dxdy * dz);
+}
+// ThreeDimensionalSort slot centres: z* = z_bot + (cum - dV/2)/A ; also b*dz for the Ψ scan
+template <class T>
+__global__ void bpe_slot_centres(const double* __restrict__ cum, const double* __restrict__ dV, const T* __restrict__ bs, long long n, double z_bot, double A,
+                                 T* __restrict__ zs_sorted, double* __restrict__ bdz) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  if (zs_sorted) zs_sorted[t] = (T)(z_bot + (cum[t] - dV[t] / 2) / A);
+  // faces[t] = z_bot + cum[t-1]/A, faces[t+1] = z_bot + cum[t]/A  (slot_faces): dz = their difference
+  const double f0 = z_bot + (t > 0 ? cum[t - 1] : 0.0) / A, f1 = z_bot + cum[t] / A;
+  bdz[t] = (double)bs[t] * (f1 - f0);
+}
+// HeavisideIntegral: run starts / ends of equal keys -> masked `below` and `cum` for the max / reversed-min scans
+template <class T>
+__global__ void bpe_heaviside_prepare(const T* __restrict__ bs, const double* __restrict__ cum, const double* __restrict__ dV, long long n,
+                                      double* __restrict__ den_in, double* __restrict__ nol_in) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const bool start = t == 0 || bs[t] != bs[t - 1];
+  const bool end = t == n - 1 || bs[t + 1] != bs[t];
+  den_in[t] = start ? cum[t] - dV[t] : -DBL_MAX;
+  nol_in[t] = end ? cum[t] : DBL_MAX;
+}
+template <class T>
+__global__ void bpe_heaviside_centres(const double* __restrict__ denser, const double* __restrict__ no_lighter, long long n, double z_bot, double A,
+                                      T* __restrict__ zs_sorted) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t < n) zs_sorted[t] = (T)(z_bot + (denser[t] + no_lighter[t]) / (2 * A));
+}
+// Ψ(ζ) = Ψface[k] + b*[k] (ζ - faces[k]),  k = clamp(searchsortedlast(faces, ζ), 1, N)  (1-based), faces[m] = z_bot + cum[m-1]/A
+template <class T>
+__device__ __forceinline__ double bpe_psi(double zeta, const double* cum, const double* psi_incl, const T* bs, long long n, double z_bot, double A) {
+  // faces has n+1 entries f[0..n] (0-based), f[m] = z_bot + (m ? cum[m-1] : 0)/A ; last index with f[m] <= zeta
+  long long lo = -1, hi = n + 1;      // invariant: f[lo] <= zeta < f[hi]  (f[-1] = -inf, f[n+1] = +inf)
+  while (hi - lo > 1) {
+    const long long mid = (lo + hi) >> 1;
+    const double f = z_bot + (mid ? cum[mid - 1] : 0.0) / A;
+    if (f <= zeta) lo = mid; else hi = mid;
+  }
+  long long k = lo + 1;               // 1-based searchsortedlast
+  k = k < 1 ? 1 : (k > n ? n : k);
+  const double fk = z_bot + (k - 1 ? cum[k - 2] : 0.0) / A;
+  const double psi_face = k - 1 ? psi_incl[k - 2] : 0.0;
+  return psi_face + (double)bs[k - 1] * (zeta - fk);
+}
+// scatter z* and Ψδ back through the permutation into the destination fields
+template <class T>
+__global__ void bpe_scatter(const uint32_t* __restrict__ perm, const T* __restrict__ zs_sorted, const double* __restrict__ cum, const double* __restrict__ psi_incl,
+                            const T* __restrict__ bs, long long n, int Nx, int Ny, double z_bot, double A, const T* __restrict__ zc1, T z0, T dz_uniform,
+                            T* __restrict__ zstar, long long zs0, long long zs1, long long zs2, T* __restrict__ psid, long long ps0, long long ps1, long long ps2) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const uint32_t cell = perm[t];
+  const int i = (int)(cell % Nx), j = (int)((cell / Nx) % Ny), k = (int)(cell / ((long long)Nx * Ny));
+  const T zs = zs_sorted[t];
+  zstar[i * zs0 + j * zs1 + k * zs2] = zs;
+  if (psid) {
+    const double zcell = zc1 ? (double)zc1[k] : (double)z0 + (double)dz_uniform * (k + 0.5);
+    const double ps = bpe_psi<T>((double)zs, cum, psi_incl, bs, n, z_bot, A);
+    const double pz = bpe_psi<T>(zcell, cum, psi_incl, bs, n, z_bot, A);
+    psid[i * ps0 + j * ps1 + k * ps2] = (T)(pz - ps);
+  }
+}
+__global__ void bpe_perm_to_int64(const uint32_t* __restrict__ perm, long long n, int64_t* __restrict__ out) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t < n) out[t] = (int64_t)perm[t] + 1;
+}
+
+struct Scratch {
+  cudaStream_t st;
+  void* ptrs[24];
+  int n = 0;
+  explicit Scratch(cudaStream_t s) : st(s) {}
+  template <class T> T* get(size_t count) {
+    void* p = nullptr;
+    if (cudaMallocAsync(&p, count * sizeof(T) + 256, st) != cudaSuccess) return nullptr;
+    ptrs[n++] = p;
+    return (T*)p;
+  }
+  ~Scratch() { for (int i = 0; i < n; ++i) cudaFreeAsync(ptrs[i], st); }
+};
+
+template <class T, class K>
+int sort_impl(const T* keys_in, T* keys_out, uint32_t* perm_out, long long n, cudaStream_t st) {
+  Scratch S(st);
+  const int nblocks = (int)((n + RS_TILE - 1) / RS_TILE);
+  K* ka = S.get<K>(n); K* kb = S.get<K>(n);
+  uint32_t* ia = S.get<uint32_t>(n); uint32_t* ib = S.get<uint32_t>(n);
+  uint32_t* table = S.get<uint32_t>(256ull * nblocks);
+  uint32_t* tot = S.get<uint32_t>((256ull * nblocks + SC_CHUNK - 1) / SC_CHUNK + 1);
+  if (!ka || !kb || !ia || !ib || !table || !tot) OCB_FAIL(OCB_ERR_ALLOC, "out of device memory for the sort scratch");
+  const unsigned g = (unsigned)((n + 255) / 256);
+  rs_make_keys<K><<<g, 256, 0, st>>>(keys_in, ka, ia, n);
+  K* ks; uint32_t* is;
+  int rc = radix_sort_pairs<K>(ka, ia, kb, ib, n, table, tot, nblocks, st, &ks, &is);
+  if (rc != OCB_OK) return rc;
+  if (keys_out) rs_unmake_keys<K><<<g, 256, 0, st>>>(ks, keys_out, n);
+  if (perm_out) OCB_CUDA(cudaMemcpyAsync(perm_out, is, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+  OCB_CUDA(cudaGetLastError());
+  return OCB_OK;
+}
+
+template <class T, class K>
+int bpe_impl(const ocb_grid* g, const ocb_field* b, int method, const ocb_field* zstar, const ocb_field* psid, int64_t* perm_out, void* bs_out,
+             cudaStream_t st) {
+  const int Nx = g->N[0], Ny = g->N[1], Nz = g->N[2];
+  const long long n = (long long)Nx * Ny * Nz;
+  OCB_REQUIRE(n < (1ll << 32), "the sort payload is a 32-bit index: at most 2^32 - 1 cells");
+  Scratch S(st);
+  const int nblocks = (int)((n + RS_TILE - 1) / RS_TILE);
+  T* work = S.get<T>(n); T* bs = S.get<T>(n); T* zs_sorted = S.get<T>(n);
+  K* ka = S.get<K>(n); K* kb = S.get<K>(n);
+  uint32_t* ia = S.get<uint32_t>(n); uint32_t* ib = S.get<uint32_t>(n);
+  uint32_t* table = S.get<uint32_t>(256ull * nblocks);
+  uint32_t* tot = S.get<uint32_t>((256ull * nblocks + SC_CHUNK - 1) / SC_CHUNK + 1);
+  double* dV = S.get<double>(n); double* cum = S.get<double>(n); double* bdz = S.get<double>(n); double* psi = S.get<double>(n);
+  double* dtot = S.get<double>((n + SC_CHUNK - 1) / SC_CHUNK + 1);
+  double *den = nullptr, *nol = nullptr;
+  if (method == OCB_BPE_HEAVISIDE_INTEGRAL) { den = S.get<double>(n); nol = S.get<double>(n); }
+  if (!work || !bs || !zs_sorted || !ka || !kb || !ia || !ib || !table || !tot || !dV || !cum || !bdz || !psi || !dtot ||
+      (method == OCB_BPE_HEAVISIDE_INTEGRAL && (!den || !nol)))
+    OCB_FAIL(OCB_ERR_ALLOC, "out of device memory for the reference-height scratch");
+  const unsigned gr = (unsigned)((n + 255) / 256);
+  // rank_by_buoyancy!: interior -> workspace -> sortperm
+  HFld<T> B, Z, P;
+  int rc = make_fld<T>(*b, &B, "b", false); if (rc != OCB_OK) return rc;
+  rc = make_fld<T>(*zstar, &Z, "zstar", false); if (rc != OCB_OK) return rc;
+  OCB_REQUIRE(B.p && Z.p, "b and zstar must be array fields");
+  P.p = nullptr; P.sx = P.sy = P.sz = 0;
+  if (psid && psid->data) { rc = make_fld<T>(*psid, &P, "psi_delta", false); if (rc != OCB_OK) return rc; }
+  const T* b1 = B.p + (B.sx + B.sy + B.sz);        // element at index (1,1,1)
+  bpe_gather_interior<T><<<gr, 256, 0, st>>>(b1, B.sx, B.sy, B.sz, Nx, Ny, n, work);
+  rs_make_keys<K><<<gr, 256, 0, st>>>(work, ka, ia, n);
+  K* ks; uint32_t* perm;
+  rc = radix_sort_pairs<K>(ka, ia, kb, ib, n, table, tot, nblocks, st, &ks, &perm);
+  if (rc != OCB_OK) return rc;
+  rs_unmake_keys<K><<<gr, 256, 0, st>>>(ks, bs, n);
+  // volumes in sorted order and their cumulative sum (slot_centers!)
+  const T* dzc1 = g->dzc ? (const T*)g->dzc + g->H[2] : nullptr;       // Δzᶜ at k = 1
+  const T* zc1 = g->zc ? (const T*)g->zc + g->H[2] : nullptr;
+  double volume = 0.0;     // A = ΣΔV / Lz ; on a RectilinearGrid ΣΔV = Lx Ly Lz exactly up to rounding of the products
+  volume = g->L[0] * g->L[1] * g->L[2];
+  const double A = volume / g->L[2];
+  bpe_sorted_volumes<T><<<gr, 256, 0, st>>>(perm, n, Nx, Ny, (T)(g->d[0] * g->d[1]), dzc1, (T)g->d[2], dV);
+  rc = device_scan<double, OP_ADD, false, false>(dV, cum, n, dtot, st); if (rc != OCB_OK) return rc;
+  bpe_slot_centres<T><<<gr, 256, 0, st>>>(cum, dV, bs, n, g->z_bottom, A, method == OCB_BPE_THREE_DIMENSIONAL_SORT ? zs_sorted : nullptr, bdz);
+  if (method == OCB_BPE_HEAVISIDE_INTEGRAL) {
+    bpe_heaviside_prepare<T><<<gr, 256, 0, st>>>(bs, cum, dV, n, den, nol);
+    rc = device_scan<double, OP_MAX, false, false>(den, den, n, dtot, st); if (rc != OCB_OK) return rc;
+    rc = device_scan<double, OP_MIN, true, false>(nol, nol, n, dtot, st); if (rc != OCB_OK) return rc;
+    bpe_heaviside_centres<T><<<gr, 256, 0, st>>>(den, nol, n, g->z_bottom, A, zs_sorted);
+  }
+  // Ψ at the slot faces: Ψface[m] = Σ_{q<m} b*[q] dz[q]  (fill_reference_potential!)
+  rc = device_scan<double, OP_ADD, false, false>(bdz, psi, n, dtot, st); if (rc != OCB_OK) return rc;
+  const T* z1 = Z.p + (Z.sx + Z.sy + Z.sz);
+  T* p1 = P.p ? (T*)P.p + (P.sx + P.sy + P.sz) : nullptr;
+  bpe_scatter<T><<<gr, 256, 0, st>>>(perm, zs_sorted, cum, psi, bs, n, Nx, Ny, g->z_bottom, A, zc1, (T)g->z_bottom, (T)g->d[2], (T*)z1, Z.sx, Z.sy, Z.sz,
+                                    p1, P.sx, P.sy, P.sz);
+  if (perm_out) bpe_perm_to_int64<<<gr, 256, 0, st>>>(perm, n, perm_out);
+  if (bs_out) OCB_CUDA(cudaMemcpyAsync(bs_out, bs, n * sizeof(T), cudaMemcpyDeviceToDevice, st));
+  OCB_CUDA(cudaGetLastError());
+  return OCB_OK;
+}
+
+}  // namespace
+
+extern "C" int ocb_sort_pairs(int32_t dtype, const void* keys_in, void* keys_out, uint32_t* perm_out, int64_t n, void* stream) {
+  OCB_REQUIRE(keys_in && n >= 0 && n < (1ll << 32), "ocb_sort_pairs: bad argument");
+  OCB_REQUIRE(dtype == OCB_F32 || dtype == OCB_F64, "bad dtype");
+  int rc = ocb_require_device();
+  if (rc != OCB_OK) return rc;
+  if (n == 0) return OCB_OK;
+  return dtype == OCB_F64 ? sort_impl<double, uint64_t>((const double*)keys_in, (double*)keys_out, perm_out, n, (cudaStream_t)stream)
+                          : sort_impl<float, uint32_t>((const float*)keys_in, (float*)keys_out, perm_out, n, (cudaStream_t)stream);
+}
+
+extern "C" int ocb_bpe_reference_height(const ocb_grid* grid, const ocb_field* b, int32_t method, const ocb_field* zstar, const ocb_field* psi_delta,
+                                        int64_t* perm_out, void* b_sorted_out, void* stream) {
+  OCB_REQUIRE(grid && b && zstar, "ocb_bpe_reference_height: null argument");
+  OCB_REQUIRE(method == OCB_BPE_THREE_DIMENSIONAL_SORT || method == OCB_BPE_HEAVISIDE_INTEGRAL, "unknown reference-height method %d", method);
+  OCB_REQUIRE(b->kind == OCB_FIELD_ARRAY && b->data && zstar->kind == OCB_FIELD_ARRAY && zstar->data, "b and zstar must be array fields");
+  for (int d = 0; d < 3; ++d) OCB_REQUIRE(b->loc[d] == OCB_CENTER && zstar->loc[d] == OCB_CENTER, "b and zstar must be (Center, Center, Center) fields");
+  if (method == OCB_BPE_THREE_DIMENSIONAL_SORT)   // src/BackgroundPotentialEnergyEquation.jl:770-788
+    OCB_REQUIRE(!grid->dzc, "`ThreeDimensionalSort` needs a grid with uniform cell volumes (regular spacing in every direction), but this grid is "
+                            "stretched. Only `HeavisideIntegral()` supports stretched grids.");
+  int rc = ocb_require_device();
+  if (rc != OCB_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  return grid->dtype == OCB_F64 ? bpe_impl<double, uint64_t>(grid, b, method, zstar, psi_delta, perm_out, b_sorted_out, st)
+                                : bpe_impl<float, uint32_t>(grid, b, method, zstar, psi_delta, perm_out, b_sorted_out, st);
+}

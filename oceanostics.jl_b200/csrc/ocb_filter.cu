@@ -1,2 +1,150 @@
+// K2: separable box / Gaussian spatial filters, staged as 1-D passes (reference: _compute_staged_filter!,
+// src/SpatialFilters/SpatialFilters.jl:347-378; kernels box_filter.jl:19-47, gaussian_filter.jl:44-81 and :193-262;
+// boundary policies SpatialFilters.jl:26-149).
+//
+// One pass: out = Σ_t w_t·val_t / Σ_t w_t·cnt_t over the 2w+1 taps t = -w..w, accumulated in tap order and finished
+// with a true division, so the degenerate-width identity (σ << Δ: the result equals the input bit for bit,
+// test/test_spatial_filters.jl:695-712) holds exactly.  Policies: Periodic wraps the index once, Shrink drops
+// out-of-range taps from both sums, Edge clamps, Constant pads with (left, right).  Filters never read halos.
+//
+// Layout: threads run along x (coalesced) for every pass direction; the y and z passes walk rows / planes of
+// the same x segment, each row read coalesced and re-used from L1/L2 by the neighbouring outputs of the block.
+// Intermediates live in stream-ordered scratch owned by the library.
 #include "ocb_common.cuh"
-extern "C" int ocb_filter_execute(int32_t, const ocb_field*, const int32_t*, const ocb_filter_pass*, int32_t, const ocb_field*, const int32_t*, const int32_t*, void*) { OCB_FAIL(OCB_ERR_UNSUPPORTED, "filters: under construction"); }
+#include <math.h>
+
+template <class T>
+struct PassParams {
+  const T* src; long long ss[3];      // source, pre-offset so that the 1-based index (i,j,k) is src[i*ss0 + j*ss1 + k*ss2]
+  T* dst; long long ds[3];            // destination, same convention
+  int lo[3], hi[3];                   // 1-based inclusive output window
+  int dim, kind, width, policy, extent;
+  T left, right, sigma, period;
+  const T* nodes; const T* spacings;  // pre-offset: index m (1-based) -> nodes[m]
+  T weights[2 * OCB_MAX_FILTER_WIDTH + 1];
+};
+
+template <class T> __device__ __forceinline__ T ocb_exp(T x);
+template <> __device__ __forceinline__ double ocb_exp<double>(double x) { return exp(x); }
+template <> __device__ __forceinline__ float ocb_exp<float>(float x) { return expf(x); }
+
+template <class T>
+__global__ void __launch_bounds__(256) ocb_filter_pass_kernel(const __grid_constant__ PassParams<T> P) {
+  const int i = P.lo[0] + blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = P.lo[1] + blockIdx.y * blockDim.y + threadIdx.y;
+  if (i > P.hi[0] || j > P.hi[1]) return;
+  const int n = P.extent, w = P.width;
+  const long long sd = P.ss[P.dim];
+  for (int k = P.lo[2] + blockIdx.z; k <= P.hi[2]; k += gridDim.z) {
+    const int c = P.dim == 0 ? i : (P.dim == 1 ? j : k);                       // index along the filtered axis
+    const T* base = P.src + i * P.ss[0] + j * P.ss[1] + k * P.ss[2] - c * sd;  // column along the filtered axis
+    T s = T(0), wsum = T(0);
+    int cnt_total = 0;
+    T x0 = T(0);
+    if (P.kind == OCB_FILTER_GAUSSIAN_STRETCHED) x0 = __ldg(P.nodes + c);
+    for (int t = -w; t <= w; ++t) {
+      int m = c + t;
+      int cnt = 1;
+      bool below = m < 1, above = m > n;
+      int mr = m;
+      if (P.policy == OCB_POLICY_PERIODIC) mr = m + (below ? n : 0) - (above ? n : 0);
+      else mr = below ? 1 : (above ? n : m);
+      T val = __ldg(base + mr * sd);
+      if (P.policy == OCB_POLICY_SHRINK) { if (below || above) { val = T(0); cnt = 0; } }
+      else if (P.policy == OCB_POLICY_CONSTANT) { if (below) val = P.left; else if (above) val = P.right; }
+      if (P.kind == OCB_FILTER_BOX) {
+        s += val;
+        cnt_total += cnt;
+      } else {
+        T wt;
+        if (P.kind == OCB_FILTER_GAUSSIAN) {
+          wt = P.weights[t + w];
+        } else {
+          T x = __ldg(P.nodes + mr);
+          if (P.policy == OCB_POLICY_PERIODIC) x = x - (below ? P.period : T(0)) + (above ? P.period : T(0));
+          const T dxm = x - x0;
+          wt = __ldg(P.spacings + mr) * ocb_exp<T>(-(dxm * dxm) / (T(2) * P.sigma * P.sigma));
+        }
+        s += wt * val;
+        wsum += wt * T(cnt);
+      }
+    }
+    const T out = (P.kind == OCB_FILTER_BOX) ? s / T(cnt_total) : s / wsum;
+    P.dst[i * P.ds[0] + j * P.ds[1] + k * P.ds[2]] = out;
+  }
+}
+
+template <class T>
+static int filter_impl(const ocb_field* src, const int32_t ext[3], const ocb_filter_pass* passes, int n_pass,
+                       const ocb_field* dst, const int32_t wlo[3], const int32_t whi[3], cudaStream_t st) {
+  // window of the final pass
+  int lo[3], hi[3];
+  for (int d = 0; d < 3; ++d) {
+    lo[d] = (wlo && (wlo[d] || whi[d])) ? wlo[d] : 1;
+    hi[d] = (whi && (wlo[d] || whi[d])) ? whi[d] : ext[d];
+    OCB_REQUIRE(lo[d] >= 1 && hi[d] <= ext[d] && lo[d] <= hi[d], "filter window [%d, %d] outside 1..%d along axis %d", lo[d], hi[d], ext[d], d + 1);
+  }
+  const size_t n_full = (size_t)ext[0] * ext[1] * ext[2];
+  T* tmp[2] = {nullptr, nullptr};
+  for (int t = 0; t < n_pass - 1 && t < 2; ++t) OCB_CUDA(cudaMallocAsync((void**)&tmp[t], n_full * sizeof(T), st));
+  int rc = OCB_OK;
+  for (int ps = 0; ps < n_pass; ++ps) {
+    const ocb_filter_pass& fp = passes[ps];
+    PassParams<T> P;
+    memset(&P, 0, sizeof(P));
+    const bool first = ps == 0, last = ps == n_pass - 1;
+    if (first) {
+      long long off = 0;
+      for (int d = 0; d < 3; ++d) { P.ss[d] = src->stride[d]; off += (long long)(src->halo[d] - 1) * src->stride[d]; }
+      P.src = (const T*)src->data + off;
+    } else {                       // dense scratch indexed from 1
+      P.ss[0] = 1; P.ss[1] = ext[0]; P.ss[2] = (long long)ext[0] * ext[1];
+      P.src = tmp[(ps - 1) & 1] - (P.ss[0] + P.ss[1] + P.ss[2]);
+    }
+    if (last) {
+      long long off = 0;
+      for (int d = 0; d < 3; ++d) { P.ds[d] = dst->stride[d]; off += ((long long)dst->halo[d] - lo[d]) * dst->stride[d]; P.lo[d] = lo[d]; P.hi[d] = hi[d]; }
+      P.dst = (T*)dst->data + off;
+    } else {
+      P.ds[0] = 1; P.ds[1] = ext[0]; P.ds[2] = (long long)ext[0] * ext[1];
+      P.dst = tmp[ps & 1] - (P.ds[0] + P.ds[1] + P.ds[2]);
+      for (int d = 0; d < 3; ++d) { P.lo[d] = 1; P.hi[d] = ext[d]; }
+    }
+    P.dim = fp.dim - 1; P.kind = fp.kind; P.width = fp.width; P.policy = fp.policy; P.extent = fp.extent;
+    P.left = T(fp.left); P.right = T(fp.right); P.sigma = T(fp.sigma); P.period = T(fp.period);
+    if (fp.kind == OCB_FILTER_GAUSSIAN) for (int t = 0; t < 2 * fp.width + 1; ++t) P.weights[t] = T(fp.weights[t]);
+    if (fp.kind == OCB_FILTER_GAUSSIAN_STRETCHED) { P.nodes = (const T*)fp.nodes - 1; P.spacings = (const T*)fp.spacings - 1; }
+    dim3 block(32, 8, 1);
+    const int ni = P.hi[0] - P.lo[0] + 1, nj = P.hi[1] - P.lo[1] + 1, nk = P.hi[2] - P.lo[2] + 1;
+    dim3 grid((ni + 31) / 32, (nj + 7) / 8, nk < 256 ? nk : 256);
+    ocb_filter_pass_kernel<T><<<grid, block, 0, st>>>(P);
+    if (cudaGetLastError() != cudaSuccess) { ocb_set_error("filter pass launch failed"); rc = OCB_ERR_CUDA; break; }
+  }
+  for (int t = 0; t < 2; ++t) if (tmp[t]) cudaFreeAsync(tmp[t], st);
+  return rc;
+}
+
+extern "C" int ocb_filter_execute(int32_t dtype, const ocb_field* src, const int32_t src_extent[3], const ocb_filter_pass* passes,
+                                  int32_t n_pass, const ocb_field* dst, const int32_t window_lo[3], const int32_t window_hi[3], void* stream) {
+  OCB_REQUIRE(src && dst && passes && src_extent, "ocb_filter_execute: null argument");
+  OCB_REQUIRE(src->kind == OCB_FIELD_ARRAY && src->data && dst->kind == OCB_FIELD_ARRAY && dst->data, "filter operands must be array fields");
+  OCB_REQUIRE(n_pass >= 1 && n_pass <= 3, "a staged filter has 1..3 passes; got %d", n_pass);
+  OCB_REQUIRE(dtype == OCB_F32 || dtype == OCB_F64, "bad dtype");
+  for (int p = 0; p < n_pass; ++p) {
+    const ocb_filter_pass& fp = passes[p];
+    OCB_REQUIRE(fp.dim >= 1 && fp.dim <= 3, "pass %d: dim must be 1, 2 or 3", p);
+    for (int q = 0; q < p; ++q) OCB_REQUIRE(passes[q].dim != fp.dim, "passes %d and %d filter the same dim", q, p);
+    OCB_REQUIRE(fp.width >= 1 && fp.width <= OCB_MAX_FILTER_WIDTH, "pass %d: half width %d outside 1..%d", p, fp.width, OCB_MAX_FILTER_WIDTH);
+    OCB_REQUIRE(fp.kind >= OCB_FILTER_BOX && fp.kind <= OCB_FILTER_GAUSSIAN_STRETCHED, "pass %d: unknown filter kind", p);
+    OCB_REQUIRE(fp.policy >= OCB_POLICY_PERIODIC && fp.policy <= OCB_POLICY_CONSTANT, "pass %d: unknown boundary policy", p);
+    OCB_REQUIRE(fp.extent == src_extent[fp.dim - 1], "pass %d: extent %d differs from the operand's length %d", p, fp.extent, src_extent[fp.dim - 1]);
+    if (fp.policy == OCB_POLICY_PERIODIC)   // SpatialFilters.jl:248-257 (a tap wraps at most once)
+      OCB_REQUIRE(fp.width <= fp.extent, "for the periodic direction d=%d, `N` (%d) exceeds the maximum allowed 2*Nd_grid+1 = %d", fp.dim,
+                  2 * fp.width + 1, 2 * fp.extent + 1);
+    if (fp.kind == OCB_FILTER_GAUSSIAN_STRETCHED) OCB_REQUIRE(fp.nodes && fp.spacings && fp.sigma > 0, "pass %d: stretched Gaussian needs nodes, spacings and sigma", p);
+  }
+  int rc = ocb_require_device();
+  if (rc != OCB_OK) return rc;
+  return dtype == OCB_F64 ? filter_impl<double>(src, src_extent, passes, n_pass, dst, window_lo, window_hi, (cudaStream_t)stream)
+                          : filter_impl<float>(src, src_extent, passes, n_pass, dst, window_lo, window_hi, (cudaStream_t)stream);
+}

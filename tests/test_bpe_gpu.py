@@ -1,0 +1,133 @@
+"""GPU parity tests of the sort-based background potential energy (K3): the hand-written radix sort alone, and the
+reference height / Ψδ / E_b against the NumPy oracle on the reference's own analytic cases
+(test/test_ape_diagnostics.jl:85-107 two-cell column, :405-461 scrambled tanh profile with ties, :162-191 method
+agreement, :71 volume-mean height) -- comparing only permutation-invariant quantities, as the reference does."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import ocb, mirror
+from oracle.grid import OGrid, OField
+from oracle import bpe as OB
+
+pytestmark = pytest.mark.gpu
+BPE = ocb.BackgroundPotentialEnergyEquation
+
+
+def sort_pairs(keys: torch.Tensor):
+    n = keys.numel()
+    out = torch.empty_like(keys)
+    perm = torch.empty(n, dtype=torch.int32, device=keys.device)
+    dt = ocb._lib.OCB_F64 if keys.dtype == torch.float64 else ocb._lib.OCB_F32
+    ocb._lib.check(ocb._lib.lib().ocb_sort_pairs(dt, keys.data_ptr(), out.data_ptr(), perm.data_ptr(), n, None))
+    torch.cuda.synchronize()
+    return out, perm.long() & 0xFFFFFFFF
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("n", [1, 31, 4096, 4097, 100_003, 3_000_000])
+def test_radix_sort_is_sorted_stable_and_a_permutation(n, dtype):
+    g = torch.Generator(device="cuda").manual_seed(n)
+    keys = torch.randn(n, generator=g, device="cuda", dtype=dtype)
+    keys[::7] = keys[0]                      # many ties
+    if n > 8:
+        keys[3], keys[5] = 0.0, -0.0         # isless: -0.0 sorts before +0.0
+        keys[1] = -float("inf"); keys[2] = float("inf")
+    out, perm = sort_pairs(keys)
+    kn, pn = keys.cpu().numpy(), perm.cpu().numpy()
+    want = np.argsort(OB.order_key(kn), kind="stable")      # the reference's CPU order: isless + stable
+    np.testing.assert_array_equal(pn, want)
+    np.testing.assert_array_equal(out.cpu().numpy(), kn[want])
+
+
+def _pair(size, zspec, b_values, topology=("P", "P", "B")):
+    topo = {"P": ocb.Periodic, "B": ocb.Bounded, "F": ocb.Flat}
+    og = OGrid(size, x=(0, 1), y=(0, 1), z=zspec, topology=topology)
+    pg = ocb.RectilinearGrid(size, x=(0, 1), y=(0, 1), z=zspec, topology=tuple(topo[t] for t in topology), device="cuda")
+    ob = OField(og, "ccc")
+    ob.interior[...] = b_values
+    ob.fill_halo()
+    return og, pg, ob, mirror(ob, pg)
+
+
+def test_two_cell_column_analytic():
+    """test/test_ape_diagnostics.jl:85-107: light water under dense water in a two-cell column."""
+    og, pg, ob, pb = _pair((1, 1, 2), (-1, 0), np.array([1.0, 0.0]).reshape(1, 1, 2))
+    z = BPE.reference_height(pb)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(z.interior_ijk().ravel(), [-0.25, -0.75], rtol=1e-14)
+    m = ocb.NonhydrostaticModel(pg)
+    m.tracers.b = pb
+    eb = ocb.Field(ocb.Integral(BPE.BackgroundPotentialEnergy(m, z))).compute().value()
+    assert abs(eb - (-(1.0 * -0.25) * 0.5)) < 1e-14          # ∫E_b = -b z✶ ΔV summed = 0.125 ... dense cell at z✶=-0.75 has b=0
+    want = OB.reference_height(ob)
+    np.testing.assert_allclose(z.reference_potential.interior_ijk(), want["psi_delta"], rtol=1e-13, atol=1e-15)
+
+
+@pytest.mark.parametrize("method", ["ThreeDimensionalSort", "HeavisideIntegral"])
+def test_scrambled_tanh_profile_with_ties(method):
+    """test/test_ape_diagnostics.jl:405-461: a horizontally uniform tanh profile, scrambled in z (so whole planes tie)."""
+    Nx, Ny, Nz = 8, 6, 16
+    rng = np.random.default_rng(5)
+    zc = -1 + (np.arange(Nz) + 0.5) / Nz
+    prof = np.tanh(4 * (zc + 0.5))
+    scr = prof[rng.permutation(Nz)]
+    og, pg, ob, pb = _pair((Nx, Ny, Nz), (-1, 0), np.broadcast_to(scr, (Nx, Ny, Nz)))
+    z = BPE.reference_height(pb, method=getattr(BPE, method)())
+    torch.cuda.synchronize()
+    want = OB.reference_height(ob, method)
+    got_z = z.interior_ijk()
+    # permutation-invariant comparisons: sorted b*, the multiset of z*, the volume-mean height, ∫E_b
+    np.testing.assert_array_equal(z.sorted_buoyancy.cpu().numpy(), want["b_sorted"])
+    np.testing.assert_allclose(np.sort(got_z.ravel()), np.sort(want["zstar"].ravel()), rtol=1e-12, atol=1e-15)
+    dV = want["dV"]
+    assert abs(np.sum(got_z * dV) - np.sum(og.node(2, "c", og.indices("ccc")[2]) * dV)) < 1e-12       # :71
+    eb_got, eb_want = np.sum(-ob.interior * got_z * dV), np.sum(-ob.interior * want["zstar"] * dV)
+    assert abs(eb_got - eb_want) <= 1e-12 * abs(eb_want)
+    if method == "HeavisideIntegral":        # tie-free semantics: every cell of a tied plane gets the same height
+        np.testing.assert_allclose(got_z, want["zstar"], rtol=1e-12, atol=1e-15)
+        np.testing.assert_allclose(z.reference_potential.interior_ijk(), want["psi_delta"], rtol=1e-10, atol=1e-13)
+    else:                                    # stable sort == Base.sortperm! on the CPU: even the permutation agrees
+        np.testing.assert_array_equal(z.permutation.cpu().numpy() - 1, want["perm"])
+        np.testing.assert_allclose(got_z, want["zstar"], rtol=1e-12, atol=1e-15)
+        np.testing.assert_allclose(z.reference_potential.interior_ijk(), want["psi_delta"], rtol=1e-10, atol=1e-13)
+
+
+def test_random_field_methods_agree_and_stretched_grid():
+    """:162-191 method agreement on a tie-free field; :368-390 only HeavisideIntegral takes a stretched grid."""
+    from helpers import stretched_faces
+    rng = np.random.default_rng(11)
+    Nx, Ny, Nz = 24, 20, 18
+    vals = rng.standard_normal((Nx, Ny, Nz)) * 1e-6 + 1e-5 * (-1 + (np.arange(Nz) + 0.5) / Nz)
+    og, pg, ob, pb = _pair((Nx, Ny, Nz), (-1, 0), vals)
+    z3 = BPE.reference_height(pb)
+    zh = BPE.reference_height(pb, method=BPE.HeavisideIntegral())
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(z3.interior_ijk(), zh.interior_ijk(), rtol=1e-12)
+    want = OB.reference_height(ob)
+    np.testing.assert_allclose(z3.interior_ijk(), want["zstar"], rtol=1e-12)
+    np.testing.assert_allclose(z3.reference_potential.interior_ijk(), want["psi_delta"], rtol=1e-9, atol=1e-18)
+    zf = stretched_faces(Nz)
+    og, pg, ob, pb = _pair((Nx, Ny, Nz), zf, vals)
+    with pytest.raises(ValueError):
+        BPE.reference_height(pb)
+    zs = BPE.reference_height(pb, method=BPE.HeavisideIntegral())
+    torch.cuda.synchronize()
+    want = OB.reference_height(ob, "HeavisideIntegral")
+    np.testing.assert_allclose(zs.interior_ijk(), want["zstar"], rtol=1e-12)
+
+
+def test_recompute_on_evolution_and_unsupported_methods():
+    rng = np.random.default_rng(2)
+    og, pg, ob, pb = _pair((8, 8, 8), (-1, 0), rng.standard_normal((8, 8, 8)))
+    z = BPE.reference_height(pb)
+    before = z.interior_ijk().copy()
+    pb.interior.mul_(-1.0)                        # flipping the sign reverses the order
+    z.compute(time=1.0)
+    torch.cuda.synchronize()
+    after = z.interior_ijk()
+    np.testing.assert_allclose(after, -1.0 - before, rtol=1e-12)       # slot centres mirror about the mid-depth
+    with pytest.raises(ocb.OcbError):
+        BPE.reference_height(pb, method=BPE.VerticalSort())
