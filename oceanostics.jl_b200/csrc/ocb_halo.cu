@@ -16,9 +16,10 @@ __global__ void ocb_fill_halo_axis_kernel(T* __restrict__ data, long long s_ax, 
   const int a = (int)(t % n_a), b = (int)(t / n_a);
   T* col = data + a * s_a + b * s_b;   // parent-array column along the filled axis (parent index m = 0 .. ext+2H-1)
   if (mode == 0) {
-    for (int m = 0; m < H; ++m) {
-      col[(long long)(H - 1 - m) * s_ax] = col[(long long)(H + ext - 1 - m) * s_ax];
-      col[(long long)(H + ext + m) * s_ax] = col[(long long)(H + m) * s_ax];
+    for (int m = 0; m < H; ++m) {      // wraps as often as needed when the axis is shorter than its halo (e.g. Nx = 1)
+      const int lo_src = ((ext - 1 - m) % ext + ext) % ext, hi_src = m % ext;
+      col[(long long)(H - 1 - m) * s_ax] = col[(long long)(H + lo_src) * s_ax];
+      col[(long long)(H + ext + m) * s_ax] = col[(long long)(H + hi_src) * s_ax];
     }
   } else if (mode == 1) {
     const T lo = col[(long long)H * s_ax], hi = col[(long long)(H + ext - 1) * s_ax];
@@ -44,7 +45,6 @@ static int fill_halo_impl(const ocb_grid* g, const ocb_field* f, int impenetrabl
     if (g->topo[d] == OCB_PERIODIC) mode = 0;
     else if (f->loc[d] == OCB_CENTER) mode = 1;
     else { if (!impenetrable) continue; mode = 2; }
-    if (mode == 0) OCB_REQUIRE(ext >= H, "fill_halo: periodic axis %d shorter than its halo", d + 1);
     const bool glo = (d == 2 && mode == 1 && !isnan(zg_bot)), ghi = (d == 2 && mode == 1 && !isnan(zg_top));
     const long long total = (long long)n_a * n_b;
     ocb_fill_halo_axis_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
