@@ -229,7 +229,7 @@ def main():
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                      "traffic": None, "kernel_ms": round(sweep_ms, 4), "algorithmic_bytes_per_cell": plan.algorithmic_bytes / cells_local,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
-        "gpu_launches": plan.n_launches * args.steps,
+        "gpu_launches": (plan.n_launches + (4 * 5 if exchanger is not None else 0)) * args.steps,
         "clocks": clocks.summary(),
         "integrals": integrals,
     }

@@ -37,6 +37,20 @@ int ocb_sm_count() {
   return cached > 0 ? cached : 148;
 }
 
+// Stream-ordered scratch (cudaMallocAsync) comes from the device's default pool; by default the pool hands memory
+// back to the OS at every synchronisation, which would make each filter / sort call re-allocate gigabytes.  Keep it.
+void ocb_keep_scratch_pool() {
+  static thread_local int done_dev = -1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev == done_dev) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  done_dev = dev;
+}
+
 // One block per integral slot sums the per-block partials in a fixed order (thread t takes blocks
 // t, t+256, ...; then a fixed-shape tree), so a plan gives the same bits run to run.
 __global__ void __launch_bounds__(256) ocb_finalize_partials_kernel(const double* __restrict__ partial, int nblocks,

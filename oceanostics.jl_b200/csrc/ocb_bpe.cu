@@ -452,6 +452,7 @@ extern "C" int ocb_sort_pairs(int32_t dtype, const void* keys_in, void* keys_out
   int rc = ocb_require_device();
   if (rc != OCB_OK) return rc;
   if (n == 0) return OCB_OK;
+  ocb_keep_scratch_pool();
   return dtype == OCB_F64 ? sort_impl<double, uint64_t>((const double*)keys_in, (double*)keys_out, perm_out, n, (cudaStream_t)stream)
                           : sort_impl<float, uint32_t>((const float*)keys_in, (float*)keys_out, perm_out, n, (cudaStream_t)stream);
 }
@@ -467,6 +468,7 @@ extern "C" int ocb_bpe_reference_height(const ocb_grid* grid, const ocb_field* b
                             "stretched. Only `HeavisideIntegral()` supports stretched grids.");
   int rc = ocb_require_device();
   if (rc != OCB_OK) return rc;
+  ocb_keep_scratch_pool();
   cudaStream_t st = (cudaStream_t)stream;
   return grid->dtype == OCB_F64 ? bpe_impl<double, uint64_t>(grid, b, method, zstar, psi_delta, perm_out, b_sorted_out, st)
                                 : bpe_impl<float, uint32_t>(grid, b, method, zstar, psi_delta, perm_out, b_sorted_out, st);

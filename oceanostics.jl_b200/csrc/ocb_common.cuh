@@ -23,6 +23,7 @@ void ocb_set_error(const char* fmt, ...);
 
 int ocb_require_device();   // OCB_OK or OCB_ERR_CUDA ("no CUDA device": there is no CPU fallback)
 int ocb_sm_count();
+void ocb_keep_scratch_pool();   // make the stream-ordered scratch pool retain its memory between calls
 
 // ---- device view of one operand ------------------------------------------------------------------------
 // p is pre-offset so that the 1-based (Oceananigans) index (i, j, k) lives at p[i*sx + j*sy + k*sz];

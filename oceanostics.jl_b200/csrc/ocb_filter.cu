@@ -28,50 +28,95 @@ template <class T> __device__ __forceinline__ T ocb_exp(T x);
 template <> __device__ __forceinline__ double ocb_exp<double>(double x) { return exp(x); }
 template <> __device__ __forceinline__ float ocb_exp<float>(float x) { return expf(x); }
 
-template <class T>
+// One 1-D pass, specialised at compile time on the filter kind and the boundary policy.  Outputs whose whole
+// stencil lies inside the axis (all but 2w planes / rows / columns) take the branch-free path: 2w+1 loads and FMAs
+// against weights staged in shared memory, divided by the weight sum accumulated in the same tap order.  Only the
+// outputs next to a boundary run the per-tap policy logic.
+template <class T, int KIND, int POLICY>
 __global__ void __launch_bounds__(256) ocb_filter_pass_kernel(const __grid_constant__ PassParams<T> P) {
+  __shared__ T wsh[2 * OCB_MAX_FILTER_WIDTH + 1];
+  __shared__ T wtot_sh;
+  const int n = P.extent, w = P.width, ntap = 2 * w + 1;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  if (KIND == OCB_FILTER_GAUSSIAN) {
+    if (tid < ntap) wsh[tid] = P.weights[tid];
+    __syncthreads();
+    if (tid == 0) { T a = T(0); for (int t = 0; t < ntap; ++t) a += wsh[t] * T(1); wtot_sh = a; }
+    __syncthreads();
+  }
+  const T wtot = KIND == OCB_FILTER_GAUSSIAN ? wtot_sh : T(ntap);
   const int i = P.lo[0] + blockIdx.x * blockDim.x + threadIdx.x;
   const int j = P.lo[1] + blockIdx.y * blockDim.y + threadIdx.y;
   if (i > P.hi[0] || j > P.hi[1]) return;
-  const int n = P.extent, w = P.width;
-  const long long sd = P.ss[P.dim];
+  const int dim = P.dim;
+  const long long sd = P.ss[dim];
+  const T sig2 = T(2) * P.sigma * P.sigma;
   for (int k = P.lo[2] + blockIdx.z; k <= P.hi[2]; k += gridDim.z) {
-    const int c = P.dim == 0 ? i : (P.dim == 1 ? j : k);                       // index along the filtered axis
+    const int c = dim == 0 ? i : (dim == 1 ? j : k);                           // index along the filtered axis
     const T* base = P.src + i * P.ss[0] + j * P.ss[1] + k * P.ss[2] - c * sd;  // column along the filtered axis
-    T s = T(0), wsum = T(0);
-    int cnt_total = 0;
-    T x0 = T(0);
-    if (P.kind == OCB_FILTER_GAUSSIAN_STRETCHED) x0 = __ldg(P.nodes + c);
-    for (int t = -w; t <= w; ++t) {
-      int m = c + t;
-      int cnt = 1;
-      bool below = m < 1, above = m > n;
-      int mr = m;
-      if (P.policy == OCB_POLICY_PERIODIC) mr = m + (below ? n : 0) - (above ? n : 0);
-      else mr = below ? 1 : (above ? n : m);
-      T val = __ldg(base + mr * sd);
-      if (P.policy == OCB_POLICY_SHRINK) { if (below || above) { val = T(0); cnt = 0; } }
-      else if (P.policy == OCB_POLICY_CONSTANT) { if (below) val = P.left; else if (above) val = P.right; }
-      if (P.kind == OCB_FILTER_BOX) {
-        s += val;
-        cnt_total += cnt;
+    T out;
+    if (KIND != OCB_FILTER_GAUSSIAN_STRETCHED && c - w >= 1 && c + w <= n) {
+      const T* q = base + (long long)(c - w) * sd;
+      T s = T(0);
+      if (KIND == OCB_FILTER_BOX) {
+        for (int t = 0; t < ntap; ++t, q += sd) s += __ldg(q);
       } else {
-        T wt;
-        if (P.kind == OCB_FILTER_GAUSSIAN) {
-          wt = P.weights[t + w];
-        } else {
-          T x = __ldg(P.nodes + mr);
-          if (P.policy == OCB_POLICY_PERIODIC) x = x - (below ? P.period : T(0)) + (above ? P.period : T(0));
-          const T dxm = x - x0;
-          wt = __ldg(P.spacings + mr) * ocb_exp<T>(-(dxm * dxm) / (T(2) * P.sigma * P.sigma));
-        }
-        s += wt * val;
-        wsum += wt * T(cnt);
+#pragma unroll 4
+        for (int t = 0; t < ntap; ++t, q += sd) s += wsh[t] * __ldg(q);
       }
+      out = s / wtot;
+    } else {
+      T s = T(0), wsum = T(0);
+      int cnt_total = 0;
+      T x0 = T(0);
+      if (KIND == OCB_FILTER_GAUSSIAN_STRETCHED) x0 = __ldg(P.nodes + c);
+      for (int t = -w; t <= w; ++t) {
+        const int m = c + t;
+        int cnt = 1;
+        const bool below = m < 1, above = m > n;
+        int mr;
+        if (POLICY == OCB_POLICY_PERIODIC) mr = m + (below ? n : 0) - (above ? n : 0);
+        else mr = below ? 1 : (above ? n : m);
+        T val = __ldg(base + mr * sd);
+        if (POLICY == OCB_POLICY_SHRINK) { if (below || above) { val = T(0); cnt = 0; } }
+        else if (POLICY == OCB_POLICY_CONSTANT) { if (below) val = P.left; else if (above) val = P.right; }
+        if (KIND == OCB_FILTER_BOX) {
+          s += val;
+          cnt_total += cnt;
+        } else {
+          T wt;
+          if (KIND == OCB_FILTER_GAUSSIAN) {
+            wt = wsh[t + w];
+          } else {
+            T x = __ldg(P.nodes + mr);
+            if (POLICY == OCB_POLICY_PERIODIC) x = x - (below ? P.period : T(0)) + (above ? P.period : T(0));
+            const T dxm = x - x0;
+            wt = __ldg(P.spacings + mr) * ocb_exp<T>(-(dxm * dxm) / sig2);
+          }
+          s += wt * val;
+          wsum += wt * T(cnt);
+        }
+      }
+      out = (KIND == OCB_FILTER_BOX) ? s / T(cnt_total) : s / wsum;
     }
-    const T out = (P.kind == OCB_FILTER_BOX) ? s / T(cnt_total) : s / wsum;
     P.dst[i * P.ds[0] + j * P.ds[1] + k * P.ds[2]] = out;
   }
+}
+
+template <class T, int KIND>
+static void launch_pass_policy(const PassParams<T>& P, dim3 grid, dim3 block, cudaStream_t st) {
+  switch (P.policy) {
+    case OCB_POLICY_PERIODIC: ocb_filter_pass_kernel<T, KIND, OCB_POLICY_PERIODIC><<<grid, block, 0, st>>>(P); break;
+    case OCB_POLICY_SHRINK: ocb_filter_pass_kernel<T, KIND, OCB_POLICY_SHRINK><<<grid, block, 0, st>>>(P); break;
+    case OCB_POLICY_EDGE: ocb_filter_pass_kernel<T, KIND, OCB_POLICY_EDGE><<<grid, block, 0, st>>>(P); break;
+    default: ocb_filter_pass_kernel<T, KIND, OCB_POLICY_CONSTANT><<<grid, block, 0, st>>>(P); break;
+  }
+}
+template <class T>
+static void launch_pass(const PassParams<T>& P, dim3 grid, dim3 block, cudaStream_t st) {
+  if (P.kind == OCB_FILTER_BOX) launch_pass_policy<T, OCB_FILTER_BOX>(P, grid, block, st);
+  else if (P.kind == OCB_FILTER_GAUSSIAN) launch_pass_policy<T, OCB_FILTER_GAUSSIAN>(P, grid, block, st);
+  else launch_pass_policy<T, OCB_FILTER_GAUSSIAN_STRETCHED>(P, grid, block, st);
 }
 
 template <class T>
@@ -117,7 +162,7 @@ static int filter_impl(const ocb_field* src, const int32_t ext[3], const ocb_fil
     dim3 block(32, 8, 1);
     const int ni = P.hi[0] - P.lo[0] + 1, nj = P.hi[1] - P.lo[1] + 1, nk = P.hi[2] - P.lo[2] + 1;
     dim3 grid((ni + 31) / 32, (nj + 7) / 8, nk < 256 ? nk : 256);
-    ocb_filter_pass_kernel<T><<<grid, block, 0, st>>>(P);
+    launch_pass<T>(P, grid, block, st);
     if (cudaGetLastError() != cudaSuccess) { ocb_set_error("filter pass launch failed"); rc = OCB_ERR_CUDA; break; }
   }
   for (int t = 0; t < 2; ++t) if (tmp[t]) cudaFreeAsync(tmp[t], st);
@@ -145,6 +190,7 @@ extern "C" int ocb_filter_execute(int32_t dtype, const ocb_field* src, const int
   }
   int rc = ocb_require_device();
   if (rc != OCB_OK) return rc;
+  ocb_keep_scratch_pool();
   return dtype == OCB_F64 ? filter_impl<double>(src, src_extent, passes, n_pass, dst, window_lo, window_hi, (cudaStream_t)stream)
                           : filter_impl<float>(src, src_extent, passes, n_pass, dst, window_lo, window_hi, (cudaStream_t)stream);
 }

@@ -1,0 +1,73 @@
+"""Run under torchrun on >= 2 GPUs (tests/test_multigpu_gpu.py::test_nccl_slabs_match_single_domain launches it):
+every rank builds the same global synthetic state, keeps its y slab, exchanges halos over NCCL, runs the fused budget
+sweep and all-reduces the integrals; rank 0 compares with the single-domain integrals."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import ocb_loader  # noqa: E402
+
+ocb = ocb_loader.load()
+
+
+def budget_ops(m):
+    KE, TV = ocb.KineticEnergyEquation, ocb.TracerVarianceEquation
+    return [KE.KineticEnergy(m), KE.KineticEnergyAdvection(m), KE.KineticEnergyPressureRedistribution(m),
+            KE.PotentialEnergyConversion(m), KE.DissipationRate(m), TV.TracerVarianceDissipationRate(m, "b"),
+            TV.TracerVarianceDiffusion(m, "b")]
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    from oceanostics_b200.distributed import SlabHaloExchanger, slab_range, allreduce_integrals
+    Nx, Ny, Nz = 128, 96, 64
+    gen = torch.Generator(device=dev).manual_seed(1234)
+    glob = {n: torch.randn((Nz + (1 if n == "w" else 0), Ny, Nx), generator=gen, device=dev, dtype=torch.float64) for n in "uvwbp"}
+    glob["w"][0].zero_(); glob["w"][-1].zero_()
+
+    def model_on(lo, hi, full):
+        g = ocb.RectilinearGrid((Nx, hi - lo + 1, Nz), x=(0, 1), y=((lo - 1) / Ny, hi / Ny), z=(-1, 0), device=dev)
+        m = ocb.NonhydrostaticModel(g, tracers=("b",), closure=ocb.Closure(nu=1e-3, kappa=1e-4))
+        flds = {"u": m.velocities.u, "v": m.velocities.v, "w": m.velocities.w, "b": m.tracers.b, "p": m.pressures.pNHS}
+        for n, f in flds.items():
+            f.interior.copy_(glob[n][:, lo - 1:hi, :])
+        if full:
+            m.fill_halo_regions()
+        return g, m, list(flds.values())
+
+    lo, hi = slab_range(Ny, rank, world)
+    g, m, flds = model_on(lo, hi, full=False)
+    ex = SlabHaloExchanger(g, flds, depth=2, rank=rank, world=world)
+    ex.exchange()
+    for f in flds:
+        f.fill_halo_regions_xz()
+    grp = ocb.FusedDiagnostics(*[ocb.Integral(o) for o in budget_ops(m)])
+    grp.compute()
+    total = grp.plan.integrals.clone()
+    allreduce_integrals(total)
+    ok = True
+    if rank == 0:
+        _, mg, _ = model_on(1, Ny, full=True)
+        ref = ocb.FusedDiagnostics(*[ocb.Integral(o) for o in budget_ops(mg)]).compute()
+        want = ref.plan.integrals.cpu().numpy()
+        got = total.cpu().numpy()
+        scales = [float(ocb.Field(o).compute().interior.abs().sum()) / (Nx * Ny * Nz) for o in budget_ops(mg)]
+        for a, b, s in zip(got, want, scales):
+            ok &= abs(a - b) <= 1e-12 * s
+        print("MULTIGPU_CHECK", "OK" if ok else "FAIL", got.tolist(), want.tolist(), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -88,3 +88,16 @@ def test_host_streamed_budget_matches_resident_sweep():
         scale = float(ocb.Field(o).compute().interior.abs().sum()) / (64 * 40 * 36)
         assert abs(a - b) <= 1e-12 * scale, o.name
     assert hs.h2d_bytes == sum(f.data.numel() * 8 for f in m_fields)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_nccl_slabs_match_single_domain():
+    """torchrun x2: NCCL halo exchange + all-reduced integrals equal the single-domain integrals."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(here, "multigpu_check.py")]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0 and "MULTIGPU_CHECK OK" in r.stdout, r.stdout[-3000:]
