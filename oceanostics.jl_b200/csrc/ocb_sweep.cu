@@ -34,21 +34,29 @@ __global__ void ocb_ztables_kernel(int n, int Hz, T dz_uniform, T z_bottom, cons
 }
 
 // ---- generic kernel --------------------------------------------------------------------------------------
-template <class T, int DIAG>
+template <class T, int DIAG, bool PERT>
 __device__ __forceinline__ void ocb_run_request(const SweepParams<T>& P, const DReq& r, int i, int j, int k0, int k1,
                                                 double* sh, int blk) {
-  Ctx<T> X(P.g, P.in, (r.flags & OCB_REQ_PERTURBATION) != 0);
   const bool in_ij = i >= r.lo[0] && i <= r.hi[0] && j >= r.lo[1] && j <= r.hi[1];
   const int ka = k0 > r.lo[2] ? k0 : r.lo[2];
   const int kb = k1 < r.hi[2] ? k1 : r.hi[2];
   double acc = 0.0;
-  if (in_ij) {
+  if (in_ij && ka <= kb) {
+    // thread-local views shifted to the first cell of this column; the evaluators then run at the literal origin
+    SweepIn<T> L = P.in;
+    DGrid<T> G = P.g;
+    ocb_shift_inputs(L, G, i, j, ka);
+    const Ctx<T> X(G, L, PERT);
     T* out = (T*)r.out;
-    const long long base = i * r.os[0] + j * r.os[1];
+    if (out) out += i * r.os[0] + j * r.os[1] + (long long)ka * r.os[2];
+    const bool integrate = r.slot >= 0;
+    const bool zface = r.loc[2] == OCB_FACE;
+    const double dxdy = (double)P.g.dx * (double)P.g.dy;
     for (int k = ka; k <= kb; ++k) {
-      const T val = Eval<T, DIAG>::at(X, r.flags, i, j, k);
-      if (out) out[base + k * r.os[2]] = val;
-      if (r.slot >= 0) acc += (double)val * ocb_cell_volume(P.g, r.loc[2], k);
+      const T val = Eval<T, DIAG>::at(X, r.flags, 0, 0, 0);
+      if (out) { *out = val; out += r.os[2]; }
+      if (integrate) acc += (double)val * (dxdy * (double)(zface ? G.dzf[0] : G.dzc[0]));
+      ocb_shift_inputs(L, G, 0, 0, 1);
     }
   }
   if (r.slot >= 0) {   // uniform across the block
@@ -67,8 +75,17 @@ __device__ __forceinline__ void ocb_run_request(const SweepParams<T>& P, const D
   }
 }
 
+template <class T, int DIAG>
+__device__ __forceinline__ void ocb_run_request_dispatch(const SweepParams<T>& P, const DReq& r, int i, int j, int k0, int k1,
+                                                         double* sh, int blk) {
+  if constexpr (ocb_diag_takes_perturbation(DIAG)) {
+    if (r.flags & OCB_REQ_PERTURBATION) { ocb_run_request<T, DIAG, true>(P, r, i, j, k0, k1, sh, blk); return; }
+  }
+  ocb_run_request<T, DIAG, false>(P, r, i, j, k0, k1, sh, blk);
+}
+
 template <class T>
-__global__ void __launch_bounds__(256) ocb_sweep_generic_kernel(const __grid_constant__ SweepParams<T> P) {
+__global__ void __launch_bounds__(256, 2) ocb_sweep_generic_kernel(const __grid_constant__ SweepParams<T> P) {
   __shared__ double sh[8];
   const int i = P.lo[0] + blockIdx.x * blockDim.x + threadIdx.x;
   const int j = P.lo[1] + blockIdx.y * blockDim.y + threadIdx.y;
@@ -78,7 +95,7 @@ __global__ void __launch_bounds__(256) ocb_sweep_generic_kernel(const __grid_con
   for (int r = 0; r < P.nreq; ++r) {
     const DReq& R = P.req[r];
     switch (R.diag) {
-#define OCB_CASE(D) case D: ocb_run_request<T, D>(P, R, i, j, k0, k1, sh, blk); break;
+#define OCB_CASE(D) case D: ocb_run_request_dispatch<T, D>(P, R, i, j, k0, k1, sh, blk); break;
       OCB_FOR_EACH_DIAG(OCB_CASE)
 #undef OCB_CASE
       default: break;

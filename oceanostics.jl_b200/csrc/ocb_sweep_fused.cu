@@ -55,6 +55,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
   uint32_t done;
   const uint32_t addr = smem_u32(bar);
@@ -76,8 +79,11 @@ struct Geo {
 };
 
 // MASK bit d set <=> diagnostic d is requested.  NS = TMA ring depth.  OUT: some request materialises a field.
-template <int MASK, int NW, int RY, int NS, bool OUT>
-__global__ void __launch_bounds__(NW * 32, (RY == 1 ? (NW <= 8 ? 2 : 1) : (NW <= 6 ? 2 : 1)))
+// WS: warp-specialised synchronisation -- an extra producer warp feeds the TMA ring through full / empty mbarriers
+// and neighbouring consumer warps hand over their exchange rows through per-pair mbarriers, so no block-wide barrier
+// is executed inside the plane loop (warps drift by up to two planes and overlap their load / FP64 phases).
+template <int MASK, int NW, int RY, int NS, bool OUT, bool WS>
+__global__ void __launch_bounds__((NW + (WS ? 1 : 0)) * 32, (RY == 1 ? (NW <= 8 ? 2 : 1) : (NW <= 6 ? 2 : 1)))
 ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__ CUtensorMap mu, const __grid_constant__ CUtensorMap mv,
                   const __grid_constant__ CUtensorMap mw, const __grid_constant__ CUtensorMap mb, const __grid_constant__ CUtensorMap mp) {
   using G = Geo<NW, RY>;
@@ -91,8 +97,11 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
   extern __shared__ __align__(1024) double smem_d[];
   double* tiles = smem_d;                                                      // [NS][NF][TILE]
   double* xch = tiles + NS * NF * G::TILE;                                     // [2][NW][NX][32]
-  double* red = xch + 2 * NW * NX * 32;                                        // [NW]
-  uint64_t* full = reinterpret_cast<uint64_t*>(red + NW);                      // [NS]
+  double* red = xch + 2 * NW * NX * 32;                                        // [NW + 1]
+  uint64_t* full = reinterpret_cast<uint64_t*>(red + NW + 1);                  // [NS]   TMA bytes have landed
+  uint64_t* empty = full + NS;                                                 // [NS]   every consumer warp is done with the stage
+  uint64_t* xfull = empty + NS;                                                // [2][NW] exchange row written
+  uint64_t* xempty = xfull + 2 * NW;                                           // [2][NW] exchange row consumed
 
   const int lane = threadIdx.x, warp = threadIdx.y;
   const int tid = warp * 32 + lane;
@@ -125,12 +134,24 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
     if (NEED_P) tma_load_3d(dst + F_P * G::TILE, &mp, &full[s], px, py, pz);
   };
   if (tid == 0) {
-    for (int s = 0; s < NS; ++s) mbar_init(&full[s], 1);
+    for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NW); }
+    for (int q = 0; q < 2 * NW; ++q) { mbar_init(&xfull[q], 1); mbar_init(&xempty[q], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (tid == 0) {
-    for (int n = n_first; n < n_first + NS && n <= n_last; ++n) issue(n);
+  if (!WS) {
+    if (tid == 0) {
+      for (int n = n_first; n < n_first + NS && n <= n_last; ++n) issue(n);
+    }
+  } else if (warp == NW) {
+    // producer warp: one lane keeps the ring full, waiting for a stage to be released before refilling it
+    if (lane == 0) {
+      int it = 0;
+      for (int n = n_first; n <= n_last; ++n, ++it) {
+        if (it >= NS) mbar_wait(&empty[it % NS], (uint32_t)(((it / NS) - 1) & 1));
+        issue(n);
+      }
+    }
   }
 
   // metric and closure constants, folded so that every term below is a bare sum of products; the remaining
@@ -180,7 +201,11 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
   int s = 0;
   uint32_t phase = 0;
   int par = 0;
+  const bool consumer = !WS || warp < NW;
+  if (consumer)
   for (int n = n_first; n <= n_last; ++n) {
+    const int it = n - n_first;
+    const int s_cur = s;
     mbar_wait(&full[s], phase);
     const double* T = tiles + s * (NF * G::TILE);
     const double* Tu = T, *Tv = T + G::TILE, *Tw = T + 2 * G::TILE, *Tb = T + F_B * G::TILE, *Tp = T + F_P * G::TILE;
@@ -248,16 +273,34 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
 
     // ---- y exchange between warps: row 0 of the warp to the north ---------------------------------------------
     double* myx = xch + ((par * NW + warp) * NX) * 32 + lane;
-    myx[0 * 32] = X12[0]; myx[1 * 32] = P12[0]; myx[2 * 32] = e23[0]; myx[3 * 32] = P23[0]; myx[4 * 32] = Fvp[0];
-    __syncthreads();
-    // every thread is done with raw stage s: refill it (plane n + NS)
-    if (tid == 0 && n + NS <= n_last) issue(n + NS);   // same ring slot as plane n
     double X12N, P12N, e23N, P23N, FvN;
-    if (warp + 1 < NW) {
-      const double* nx_ = xch + ((par * NW + warp + 1) * NX) * 32 + lane;
-      X12N = nx_[0 * 32]; P12N = nx_[1 * 32]; e23N = nx_[2 * 32]; P23N = nx_[3 * 32]; FvN = nx_[4 * 32];
+    X12N = P12N = e23N = P23N = FvN = 0.0;
+    if (!WS) {
+      myx[0 * 32] = X12[0]; myx[1 * 32] = P12[0]; myx[2 * 32] = e23[0]; myx[3 * 32] = P23[0]; myx[4 * 32] = Fvp[0];
+      __syncthreads();
+      // every thread is done with raw stage s: refill it (plane n + NS)
+      if (tid == 0 && n + NS <= n_last) issue(n + NS);   // same ring slot as plane n
+      if (warp + 1 < NW) {
+        const double* nx_ = xch + ((par * NW + warp + 1) * NX) * 32 + lane;
+        X12N = nx_[0 * 32]; P12N = nx_[1 * 32]; e23N = nx_[2 * 32]; P23N = nx_[3 * 32]; FvN = nx_[4 * 32];
+      }
     } else {
-      X12N = P12N = e23N = P23N = FvN = 0.0;
+      // all raw reads of this warp are in registers: release the TMA stage
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s_cur]);
+      if (warp > 0) {                       // the warp to the south consumes my row 0
+        if (it >= 2) mbar_wait(&xempty[par * NW + warp], (uint32_t)(((it >> 1) & 1) ^ 1));
+        myx[0 * 32] = X12[0]; myx[1 * 32] = P12[0]; myx[2 * 32] = e23[0]; myx[3 * 32] = P23[0]; myx[4 * 32] = Fvp[0];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&xfull[par * NW + warp]);
+      }
+      if (warp + 1 < NW) {
+        mbar_wait(&xfull[par * NW + warp + 1], (uint32_t)((it >> 1) & 1));
+        const double* nx_ = xch + ((par * NW + warp + 1) * NX) * 32 + lane;
+        X12N = nx_[0 * 32]; P12N = nx_[1 * 32]; e23N = nx_[2 * 32]; P23N = nx_[3 * 32]; FvN = nx_[4 * 32];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&xempty[par * NW + warp + 1]);
+      }
     }
     const bool p1 = (n - 1) >= k0 && (n - 1) <= k1, p2 = (n - 2) >= k0 && (n - 2) <= k1;
 
@@ -350,7 +393,7 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
       __syncthreads();
       if (tid == 0) {
         double s = 0.0;
-        for (int w = 0; w < NW; ++w) s += red[w];
+        for (int w = 0; w < NW + (WS ? 1 : 0); ++w) s += red[w];
         const double scale[FD_N] = {SC_K, SC_ADV, SC_PR, SC_WB, SC_EPS, SC_CHI, SC_CDF};
         P.partial[(size_t)blockIdx.x * P.nslots + P.o[d].slot] = s * (P.V * scale[d]);
       }
@@ -378,30 +421,39 @@ EncodeTiledFn get_encode_fn() {
 struct ocb_fused_plan {
   FusedParams P;
   CUtensorMap maps[5];
-  int mask, nw, ry, ns;
+  int mask, nw, ry, ns, ws;
   int nblocks;
   size_t smem;
   void (*kernel)(FusedParams, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap);
 };
 
-template <int MASK, int NW, int RY, int NS>
-static int setup_variant(ocb_fused_plan* fp, bool out) {
+template <int MASK, int NW, int RY, int NS, bool WS>
+static int setup_variant_ws(ocb_fused_plan* fp, bool out) {
   using G = Geo<NW, RY>;
   constexpr bool NEED_B = MASK & ((1 << FD_WB) | (1 << FD_CHI) | (1 << FD_CDF)), NEED_P = MASK & (1 << FD_PR);
   constexpr int NF = 3 + (NEED_B ? 1 : 0) + (NEED_P ? 1 : 0);
-  fp->nw = NW; fp->ry = RY; fp->ns = NS; fp->mask = MASK;
-  fp->smem = sizeof(double) * ((size_t)NS * NF * G::TILE + 2 * NW * 5 * 32 + NW) + sizeof(uint64_t) * NS;
+  fp->nw = NW; fp->ry = RY; fp->ns = NS; fp->mask = MASK; fp->ws = WS ? 1 : 0;
+  fp->smem = sizeof(double) * ((size_t)NS * NF * G::TILE + 2 * NW * 5 * 32 + NW + 1) + sizeof(uint64_t) * (2 * NS + 4 * NW);
   // ask for the largest shared-memory carveout so that occupancy is set by registers, not by the default split
   if (out) {
-    cudaFuncSetAttribute(ocb_budget_kernel<MASK, NW, RY, NS, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    fp->kernel = ocb_budget_kernel<MASK, NW, RY, NS, true>;
-    OCB_CUDA(cudaFuncSetAttribute(ocb_budget_kernel<MASK, NW, RY, NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp->smem));
+    cudaFuncSetAttribute(ocb_budget_kernel<MASK, NW, RY, NS, true, WS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    fp->kernel = ocb_budget_kernel<MASK, NW, RY, NS, true, WS>;
+    OCB_CUDA(cudaFuncSetAttribute(ocb_budget_kernel<MASK, NW, RY, NS, true, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp->smem));
   } else {
-    cudaFuncSetAttribute(ocb_budget_kernel<MASK, NW, RY, NS, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    fp->kernel = ocb_budget_kernel<MASK, NW, RY, NS, false>;
-    OCB_CUDA(cudaFuncSetAttribute(ocb_budget_kernel<MASK, NW, RY, NS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp->smem));
+    cudaFuncSetAttribute(ocb_budget_kernel<MASK, NW, RY, NS, false, WS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    fp->kernel = ocb_budget_kernel<MASK, NW, RY, NS, false, WS>;
+    OCB_CUDA(cudaFuncSetAttribute(ocb_budget_kernel<MASK, NW, RY, NS, false, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp->smem));
   }
   return OCB_OK;
+}
+template <int MASK, int NW, int RY, int NS>
+static int setup_variant(ocb_fused_plan* fp, bool out) {
+  // Measured on B200 (profiles/r1_summary.md): the mbarrier hand-over costs more than the block barrier it removes
+  // (12,1,3: 55.9 vs 66.7 Gcells/s; the extra producer warp also halves the residency of the 8-warp shapes), so the
+  // block-barrier version is the default; OCB_FUSED_WS=1 selects the warp-specialised one for experiments.
+  const char* ws = getenv("OCB_FUSED_WS");
+  if (ws && ws[0] == '1') return setup_variant_ws<MASK, NW, RY, NS, true>(fp, out);
+  return setup_variant_ws<MASK, NW, RY, NS, false>(fp, out);
 }
 
 static int make_map(EncodeTiledFn enc, const ocb_field& f, int rows, CUtensorMap* map) {
@@ -553,7 +605,7 @@ int ocb_fused_nblocks(const ocb_fused_plan* fp) { return fp->nblocks; }
 
 int ocb_fused_execute(ocb_fused_plan* fp, double* partial, cudaStream_t st) {
   fp->P.partial = partial;
-  dim3 block(32, fp->nw, 1), grid(fp->nblocks, 1, 1);
+  dim3 block(32, fp->nw + fp->ws, 1), grid(fp->nblocks, 1, 1);
   fp->kernel<<<grid, block, fp->smem, st>>>(fp->P, fp->maps[0], fp->maps[1], fp->maps[2], fp->maps[3], fp->maps[4]);
   OCB_CUDA(cudaGetLastError());
   return OCB_OK;

@@ -101,6 +101,8 @@ static int ocb_build_sweep_params(const ocb_grid* grid, const ocb_sweep_inputs* 
     DReq& R = P.req[r];
     OCB_REQUIRE(q.diag >= 0 && q.diag < OCB_DIAG_COUNT, "request %d: unknown diagnostic id %d", r, q.diag);
     R.diag = q.diag; R.flags = q.flags; R.slot = q.integral_slot;
+    if ((q.flags & OCB_REQ_PERTURBATION) && !ocb_diag_takes_perturbation(q.diag))
+      OCB_FAIL(OCB_ERR_UNSUPPORTED, "request %d (%s) does not take lazy perturbation operands: materialise Field(u - U) first", r, ocb_diag_name(q.diag));
     ocb_diag_location(q.diag, R.loc);
     OCB_REQUIRE(q.out != nullptr || q.integral_slot >= 0, "request %d (%s) has neither an output field nor an integral slot",
                 r, ocb_diag_name(q.diag));

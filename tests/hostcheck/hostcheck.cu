@@ -37,20 +37,27 @@ static int run(const ocb_grid* grid, const ocb_sweep_inputs* in, const ocb_reque
   if (rc != OCB_OK) return rc;
   for (int r = 0; r < P.nreq; ++r) {
     const DReq& R = P.req[r];
-    Ctx<T> X(P.g, P.in, (R.flags & OCB_REQ_PERTURBATION) != 0);
+    const bool pert = (R.flags & OCB_REQ_PERTURBATION) != 0;
     double acc = 0.0;
-    for (int k = R.lo[2]; k <= R.hi[2]; ++k)
-      for (int j = R.lo[1]; j <= R.hi[1]; ++j)
-        for (int i = R.lo[0]; i <= R.hi[0]; ++i) {
+    // same cell-relative addressing as the CUDA kernel: shift the operand views to the cell, evaluate at the origin
+    for (int j = R.lo[1]; j <= R.hi[1]; ++j)
+      for (int i = R.lo[0]; i <= R.hi[0]; ++i) {
+        SweepIn<T> L = P.in;
+        DGrid<T> G = P.g;
+        ocb_shift_inputs(L, G, i, j, R.lo[2]);
+        const Ctx<T> X(G, L, pert);
+        for (int k = R.lo[2]; k <= R.hi[2]; ++k) {
           T val = T(0);
           switch (R.diag) {
-#define HC_CASE(D) case D: val = Eval<T, D>::at(X, R.flags, i, j, k); break;
+#define HC_CASE(D) case D: val = Eval<T, D>::at(X, R.flags, 0, 0, 0); break;
             OCB_FOR_EACH_DIAG(HC_CASE)
 #undef HC_CASE
           }
           if (R.out) ((T*)R.out)[i * R.os[0] + j * R.os[1] + k * R.os[2]] = val;
-          if (R.slot >= 0) acc += (double)val * ocb_cell_volume(P.g, R.loc[2], k);
+          if (R.slot >= 0) acc += (double)val * ((double)P.g.dx * (double)P.g.dy * (double)(R.loc[2] == OCB_FACE ? G.dzf[0] : G.dzc[0]));
+          ocb_shift_inputs(L, G, 0, 0, 1);
         }
+      }
     if (R.slot >= 0 && integrals) integrals[R.slot] = acc;
   }
   return OCB_OK;
