@@ -85,7 +85,7 @@ __device__ __forceinline__ void ocb_run_request_dispatch(const SweepParams<T>& P
 }
 
 template <class T>
-__global__ void __launch_bounds__(256, 2) ocb_sweep_generic_kernel(const __grid_constant__ SweepParams<T> P) {
+__global__ void __launch_bounds__(256, 3) ocb_sweep_generic_kernel(const __grid_constant__ SweepParams<T> P) {
   __shared__ double sh[8];
   const int i = P.lo[0] + blockIdx.x * blockDim.x + threadIdx.x;
   const int j = P.lo[1] + blockIdx.y * blockDim.y + threadIdx.y;

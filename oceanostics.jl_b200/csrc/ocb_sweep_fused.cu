@@ -41,6 +41,7 @@ struct FusedParams {
   int hx, hy, hz;                  // parent index of 1-based index i is i + hx - 1
   int tiles_x, tiles_y, nchunks, kchunk;
   int kz_lo, kz_hi;                // 1-based inclusive z window (the whole interior, or a z slab of it)
+  int jy_lo, jy_hi;                // 1-based inclusive y window (rows next to a slab edge are swept separately)
   double rdx, rdy, rdz, nu, kappa, ghat_z, V;
   FusedOut o[FD_N];
   long long os[3];                 // element strides shared by every output field
@@ -109,7 +110,7 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
   const int tx = bid % P.tiles_x; bid /= P.tiles_x;
   const int ty = bid % P.tiles_y; bid /= P.tiles_y;
   const int chunk = bid;
-  const int i0 = 1 + 31 * tx, j0 = 1 + (G::BR - 1) * ty;
+  const int i0 = 1 + 31 * tx, j0 = P.jy_lo + (G::BR - 1) * ty;
   const int k0 = P.kz_lo + chunk * P.kchunk;
   const int k1 = min(k0 + P.kchunk - 1, P.kz_hi);
   const int n_first = k0 - 1, n_last = k1 + 2;
@@ -187,7 +188,7 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
 #pragma unroll
   for (int r = 0; r < RY; ++r) {
     const int j = j0 + jr0 + r;
-    wrow[r] = (lane_out && (jr0 + r) < G::BR - 1 && j <= P.Ny) ? 1.0 : 0.0;
+    wrow[r] = (lane_out && (jr0 + r) < G::BR - 1 && j <= P.jy_hi) ? 1.0 : 0.0;
     orow[r] = OUT ? (i * P.os[0] + j * P.os[1]) : 0;
   }
   // one predicated accumulate (an FMA with the 0/1 weight) and, for field requests, one predicated store
@@ -508,8 +509,9 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
     }
     if (reqs[r].flags & OCB_REQ_PERTURBATION) return OCB_OK;
     const DReq& R = SP.req[r];
-    if (R.lo[0] != 1 || R.lo[1] != 1 || R.hi[0] != grid->N[0] || R.hi[1] != grid->N[1]) return OCB_OK;   // full x, y extent
-    if (r > 0 && (R.lo[2] != SP.req[0].lo[2] || R.hi[2] != SP.req[0].hi[2])) return OCB_OK;                 // one z window
+    if (R.lo[0] != 1 || R.hi[0] != grid->N[0]) return OCB_OK;                                               // full x extent
+    if (r > 0 && (R.lo[2] != SP.req[0].lo[2] || R.hi[2] != SP.req[0].hi[2] || R.lo[1] != SP.req[0].lo[1] || R.hi[1] != SP.req[0].hi[1]))
+      return OCB_OK;                                                                                          // one y and z window
     if (R.out) { if (which_out[d] >= 0) return OCB_OK; which_out[d] = r; }
     if (R.slot >= 0) { if (which_slot[d] >= 0) return OCB_OK; which_slot[d] = r; }
     mask |= 1 << d;
@@ -570,7 +572,8 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
   P.hx = grid->H[0]; P.hy = grid->H[1]; P.hz = grid->H[2];
   const int BR = fp->nw * fp->ry;
   P.tiles_x = (P.Nx + 30) / 31;
-  P.tiles_y = (P.Ny + BR - 2) / (BR - 1);
+  P.jy_lo = SP.req[0].lo[1]; P.jy_hi = SP.req[0].hi[1];
+  P.tiles_y = ((P.jy_hi - P.jy_lo + 1) + BR - 2) / (BR - 1);
   const int tiles = P.tiles_x * P.tiles_y;
   P.kz_lo = SP.req[0].lo[2]; P.kz_hi = SP.req[0].hi[2];
   const int nz_win = P.kz_hi - P.kz_lo + 1;

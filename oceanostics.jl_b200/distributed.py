@@ -92,3 +92,42 @@ def allreduce_integrals(integrals: torch.Tensor, group=None):
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(integrals, op=dist.ReduceOp.SUM, group=group)
     return integrals
+
+
+class OverlappedSlabBudget:
+    """One slab's fused budget sweep with the halo exchange hidden behind the interior rows.
+
+    The integrals of rows [1+depth, Ny-depth] need no neighbour data, so that sweep runs on the compute stream
+    while the ring exchange (pack, NCCL send/recv, unpack) runs on a side stream; the two `depth`-row strips next to
+    the slab edges are swept afterwards and the three partial integral vectors are added before the all-reduce."""
+
+    def __init__(self, grid, fields, make_ops, depth=2, rank=None, world=None, group=None):
+        from .operations import FusedDiagnostics, Integral
+        self.grid, self.group = grid, group
+        self.exchanger = SlabHaloExchanger(grid, fields, depth=depth, rank=rank, world=world, group=group)
+        Ny = grid.N[1]
+        if Ny < 4 * depth:
+            raise ValueError("slab too thin to overlap the exchange")
+        ops = make_ops()
+        win = lambda lo, hi: FusedDiagnostics(*[Integral(o, indices=(None, (lo, hi), None)) for o in ops])
+        self.interior = win(1 + depth, Ny - depth)
+        self.low, self.high = win(1, depth), win(Ny - depth + 1, Ny)
+        self.comm_stream = torch.cuda.Stream(device=grid.device)
+        self.done = torch.cuda.Event()
+        self.total = torch.zeros(len(ops), dtype=torch.float64, device=grid.device)
+        self.n = len(ops)
+
+    def step(self):
+        cur = torch.cuda.current_stream(self.grid.device)
+        self.comm_stream.wait_stream(cur)
+        with torch.cuda.stream(self.comm_stream):
+            self.exchanger.exchange()
+            self.done.record(self.comm_stream)
+        self.interior.plan.execute()                      # overlaps the exchange
+        cur.wait_event(self.done)
+        self.low.plan.execute()
+        self.high.plan.execute()
+        torch.add(self.interior.plan.integrals[:self.n], self.low.plan.integrals[:self.n], out=self.total)
+        self.total.add_(self.high.plan.integrals[:self.n])
+        allreduce_integrals(self.total, self.group)
+        return self.total

@@ -54,6 +54,12 @@ def main():
     grp.compute()
     total = grp.plan.integrals.clone()
     allreduce_integrals(total)
+    from oceanostics_b200.distributed import OverlappedSlabBudget
+    ov = OverlappedSlabBudget(g, flds, lambda: budget_ops(m), depth=2, rank=rank, world=world)
+    for f in flds:                       # wipe the y halos: the overlapped step must refill them itself
+        f.data[:, :3, :] = 0.0
+        f.data[:, -3:, :] = 0.0
+    ov_total = ov.step().clone()
     ok = True
     if rank == 0:
         _, mg, _ = model_on(1, Ny, full=True)
@@ -62,6 +68,8 @@ def main():
         got = total.cpu().numpy()
         scales = [float(ocb.Field(o).compute().interior.abs().sum()) / (Nx * Ny * Nz) for o in budget_ops(mg)]
         for a, b, s in zip(got, want, scales):
+            ok &= abs(a - b) <= 1e-12 * s
+        for a, b, s in zip(ov_total.cpu().numpy(), want, scales):
             ok &= abs(a - b) <= 1e-12 * s
         print("MULTIGPU_CHECK", "OK" if ok else "FAIL", got.tolist(), want.tolist(), flush=True)
     dist.barrier()

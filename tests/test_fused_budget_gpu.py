@@ -117,3 +117,22 @@ def test_fused_falls_back_to_generic_outside_its_envelope():
     m = st.model(closure=pc)
     grp = ocb.FusedDiagnostics(ocb.Integral(ocb.KineticEnergyEquation.DissipationRate(m)))
     assert grp.plan.variant == 0          # eddy-viscosity field: generic kernel
+
+
+def test_y_and_z_windows_tile_the_domain():
+    """Integral(op, indices=...) over y strips / z slabs (the pieces the overlapped multi-GPU step and the host-streamed
+    path sweep separately) add up to the whole-domain integrals, all on the pipelined kernel."""
+    st = State(size=(64, 40, 30), device="cuda")
+    ops, _ = budget(st)
+    ref = ocb.FusedDiagnostics(*[ocb.Integral(o) for o in ops]).compute().integrals()
+    for windows in ([(None, (1, 2), None), (None, (3, 38), None), (None, (39, 40), None)],
+                    [(None, None, (1, 7)), (None, None, (8, 30))],
+                    [(None, (1, 13), (1, 11)), (None, (14, 40), (1, 11)), (None, None, (12, 30))]):
+        tot = np.zeros(len(ops))
+        for w in windows:
+            grp = ocb.FusedDiagnostics(*[ocb.Integral(o, indices=w) for o in ops]).compute()
+            assert grp.plan.variant == 1
+            tot += np.array(grp.integrals())
+        for o, a, b in zip(ops, tot, ref):
+            scale = float(ocb.Field(o).compute().interior.abs().sum()) / (64 * 40 * 30)
+            assert abs(a - b) <= 1e-12 * scale, o.name
