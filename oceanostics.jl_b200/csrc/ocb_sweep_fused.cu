@@ -79,12 +79,17 @@ struct Geo {
   static constexpr int TILE = ((TW * TR * 8 + 127) / 128) * 128 / 8;   // doubles per field tile, 128 B aligned
 };
 
-// MASK bit d set <=> diagnostic d is requested.  NS = TMA ring depth.  OUT: some request materialises a field.
-// WS: warp-specialised synchronisation -- an extra producer warp feeds the TMA ring through full / empty mbarriers
-// and neighbouring consumer warps hand over their exchange rows through per-pair mbarriers, so no block-wide barrier
-// is executed inside the plane loop (warps drift by up to two planes and overlap their load / FP64 phases).
-template <int MASK, int NW, int RY, int NS, bool OUT, bool WS>
-__global__ void __launch_bounds__((NW + (WS ? 1 : 0)) * 32, (RY == 1 ? (NW <= 8 ? 2 : 1) : (NW <= 6 ? 2 : 1)))
+// MASK bit d set <=> diagnostic d is requested.  NS = TMA ring depth.
+// OUT = true : some request materialises a field -- every cell value is formed (plane n-1 when plane n arrives,
+//              ADV one plane later) and stored; integrals accumulate the same values.
+// OUT = false: integrals only -- the SAME per-face / per-edge / per-cell terms are accumulated directly, each weighted
+//              by the number of this block's output cells it belongs to (Σ_cells ½(F_i + F_{i+1}) = Σ_faces m_i F_i):
+//              a pure re-ordering of the summation that needs no neighbour's face value, so most shuffles, three of
+//              the five exchanged rows and seven pipeline registers per row disappear.
+// (A warp-specialised variant -- producer warp + per-pair mbarriers instead of the block barrier -- was measured
+//  slower on B200, 55.9 vs 66.7 Gcells/s, and removed; see profiles/r1_summary.md.)
+template <int MASK, int NW, int RY, int NS, bool OUT>
+__global__ void __launch_bounds__(NW * 32, (RY == 1 ? (NW <= 8 ? 2 : 1) : (NW <= 6 ? 2 : 1)))
 ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__ CUtensorMap mu, const __grid_constant__ CUtensorMap mv,
                   const __grid_constant__ CUtensorMap mw, const __grid_constant__ CUtensorMap mb, const __grid_constant__ CUtensorMap mp) {
   using G = Geo<NW, RY>;
@@ -93,16 +98,13 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
   constexpr bool NEED_B = H_WB || H_CHI || H_CDF, NEED_P = H_PR;
   constexpr int NF = 3 + (NEED_B ? 1 : 0) + (NEED_P ? 1 : 0);
   constexpr int F_B = 3, F_P = NEED_B ? 4 : 3;
-  constexpr int NX = 5;                                // exchanged quantities per column: X12, P12, e23, P23, Fv
+  constexpr int NX = 5;                                // exchanged quantities per column: P12, P23, X12, e23, Fv (last 3: OUT only)
 
   extern __shared__ __align__(1024) double smem_d[];
   double* tiles = smem_d;                                                      // [NS][NF][TILE]
   double* xch = tiles + NS * NF * G::TILE;                                     // [2][NW][NX][32]
-  double* red = xch + 2 * NW * NX * 32;                                        // [NW + 1]
-  uint64_t* full = reinterpret_cast<uint64_t*>(red + NW + 1);                  // [NS]   TMA bytes have landed
-  uint64_t* empty = full + NS;                                                 // [NS]   every consumer warp is done with the stage
-  uint64_t* xfull = empty + NS;                                                // [2][NW] exchange row written
-  uint64_t* xempty = xfull + 2 * NW;                                           // [2][NW] exchange row consumed
+  double* red = xch + 2 * NW * NX * 32;                                        // [NW]
+  uint64_t* full = reinterpret_cast<uint64_t*>(red + NW);                      // [NS]
 
   const int lane = threadIdx.x, warp = threadIdx.y;
   const int tid = warp * 32 + lane;
@@ -135,24 +137,12 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
     if (NEED_P) tma_load_3d(dst + F_P * G::TILE, &mp, &full[s], px, py, pz);
   };
   if (tid == 0) {
-    for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NW); }
-    for (int q = 0; q < 2 * NW; ++q) { mbar_init(&xfull[q], 1); mbar_init(&xempty[q], 1); }
+    for (int s = 0; s < NS; ++s) mbar_init(&full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (!WS) {
-    if (tid == 0) {
-      for (int n = n_first; n < n_first + NS && n <= n_last; ++n) issue(n);
-    }
-  } else if (warp == NW) {
-    // producer warp: one lane keeps the ring full, waiting for a stage to be released before refilling it
-    if (lane == 0) {
-      int it = 0;
-      for (int n = n_first; n <= n_last; ++n, ++it) {
-        if (it >= NS) mbar_wait(&empty[it % NS], (uint32_t)(((it / NS) - 1) & 1));
-        issue(n);
-      }
-    }
+  if (tid == 0) {
+    for (int n = n_first; n < n_first + NS && n <= n_last; ++n) issue(n);
   }
 
   // metric and closure constants, folded so that every term below is a bare sum of products; the remaining
@@ -168,8 +158,8 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
   double up[RY], vp[RY], wp[RY], bp[RY], pp[RY];        // raw, previous plane
   double P13p[RY], P23p[RY];                            // fcf / cff momentum-flux products at the previous face
   double dU[RY], dV[RY], dW[RY];                        // in-plane parts of the flux divergences (previous plane)
-  double Wwpp[RY], Apart[RY], Fvp[RY];                  // ADV pipeline
-  double Eacc[RY], Kacc[RY], PRacc[RY], CHacc[RY], CDacc[RY], hzp[RY];
+  double Wwpp[RY], Apart[RY], Fvp[RY];                  // ADV pipeline (Apart, Fvp: OUT only)
+  double Eacc[RY], Kacc[RY], PRacc[RY], CHacc[RY], CDacc[RY], hzp[RY];   // all but CDacc: OUT only
 #pragma unroll
   for (int r = 0; r < RY; ++r) {
     up[r] = vp[r] = wp[r] = bp[r] = pp[r] = 0.0;
@@ -185,13 +175,23 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
   // per-row output weight (1 for cells this thread reports, 0 for overlap cells) and output offset
   double wrow[RY];
   long long orow[RY];
+  // integral-only multiplicities: how many of this block's output cells a face / edge owned by (lane, row) touches
+  double mx[RY], my[RY], mxy[RY];          // x faces & fcf edges, y faces & cff edges, ffc edges
 #pragma unroll
   for (int r = 0; r < RY; ++r) {
-    const int j = j0 + jr0 + r;
-    wrow[r] = (lane_out && (jr0 + r) < G::BR - 1 && j <= P.jy_hi) ? 1.0 : 0.0;
+    const int jr = jr0 + r, j = j0 + jr;
+    const bool row_out = jr < G::BR - 1 && j <= P.jy_hi;
+    const bool south_out = jr >= 1 && (jr - 1) < G::BR - 1 && (j - 1) <= P.jy_hi;          // the cell to the south, same lane
+    wrow[r] = (lane_out && row_out) ? 1.0 : 0.0;
     orow[r] = OUT ? (i * P.os[0] + j * P.os[1]) : 0;
+    const double wsouth = (lane_out && south_out) ? 1.0 : 0.0;
+    const double wwest = __shfl_up_sync(FULLMASK, wrow[r], 1);                              // the cell to the west, same row
+    const double wsw = __shfl_up_sync(FULLMASK, wsouth, 1);
+    mx[r] = wrow[r] + (lane > 0 ? wwest : 0.0);
+    my[r] = wrow[r] + wsouth;
+    mxy[r] = mx[r] + wsouth + (lane > 0 ? wsw : 0.0);
   }
-  // one predicated accumulate (an FMA with the 0/1 weight) and, for field requests, one predicated store
+  // OUT: one predicated accumulate (an FMA with the 0/1 weight) and one predicated store
   auto emit = [&](int d, double raw, double scale, double w, int plane, int r) {
     acc[d] = fma(raw, w, acc[d]);
     if (OUT) {
@@ -202,15 +202,14 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
   int s = 0;
   uint32_t phase = 0;
   int par = 0;
-  const bool consumer = !WS || warp < NW;
-  if (consumer)
   for (int n = n_first; n <= n_last; ++n) {
-    const int it = n - n_first;
-    const int s_cur = s;
     mbar_wait(&full[s], phase);
     const double* T = tiles + s * (NF * G::TILE);
     const double* Tu = T, *Tv = T + G::TILE, *Tw = T + 2 * G::TILE, *Tb = T + F_B * G::TILE, *Tp = T + F_P * G::TILE;
     if (++s == NS) { s = 0; phase ^= 1; }
+    // plane validity (uniform): cells of plane n, n-1, n-2 inside this block's z chunk
+    const double pv0 = (n >= k0 && n <= k1) ? 1.0 : 0.0, pv1 = ((n - 1) >= k0 && (n - 1) <= k1) ? 1.0 : 0.0,
+                 pv2 = ((n - 2) >= k0 && (n - 2) <= k1) ? 1.0 : 0.0;
 
     // ---- stage 1: quantities owned by this thread's cells at plane n --------------------------------------
     double uc[RY], vc[RY], wc[RY], bc[RY], pc[RY];
@@ -228,18 +227,26 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
       const double ww = rw[0], ws = (r == 0) ? rw[1 - TW] : wc[r > 0 ? r - 1 : 0];
       // ffc edge (i, j): scaled strain (nu/4 folded in) and the (Vu = Uv) momentum-flux product
       const double s12 = (uc[r] - us) * ey + (vc[r] - vw) * ex;
-      const double e12 = s12 * s12;
       P12[r] = (vw + vc[r]) * (us + uc[r]);
       // fcf edge (i, j, n) and cff edge
       const double s13 = (uc[r] - up[r]) * ez + (wc[r] - ww) * ex;
-      const double e13 = s13 * s13;
       P13[r] = (ww + wc[r]) * (up[r] + uc[r]);
       const double s23 = (vc[r] - vp[r]) * ez + (wc[r] - ws) * ey;
-      e23[r] = s23 * s23;
       P23[r] = (ws + wc[r]) * (vp[r] + vc[r]);
-      // x neighbours' edges by shuffle
-      X12[r] = e12 + __shfl_down_sync(FULLMASK, e12, 1);
-      Y13[r] = e13 + __shfl_down_sync(FULLMASK, e13, 1);
+      if (OUT) {
+        const double e12 = s12 * s12, e13 = s13 * s13;
+        e23[r] = s23 * s23;
+        X12[r] = e12 + __shfl_down_sync(FULLMASK, e12, 1);      // x neighbours' edges by shuffle
+        Y13[r] = e13 + __shfl_down_sync(FULLMASK, e13, 1);
+      } else if (H_EPS) {
+        // each edge term straight into the integral, weighted by the output cells it belongs to
+        const double pz = pv0 + pv1;
+        double a = acc[FD_EPS];
+        a = fma(s12 * (mxy[r] * pv0), s12, a);
+        a = fma(s13 * (mx[r] * pz), s13, a);
+        a = fma(s23 * (my[r] * pz), s23, a);
+        acc[FD_EPS] = a;
+      }
       if (H_ADV) {
         P12E[r] = __shfl_down_sync(FULLMASK, P12[r], 1);
         P13E[r] = __shfl_down_sync(FULLMASK, P13[r], 1);
@@ -274,106 +281,124 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
 
     // ---- y exchange between warps: row 0 of the warp to the north ---------------------------------------------
     double* myx = xch + ((par * NW + warp) * NX) * 32 + lane;
-    double X12N, P12N, e23N, P23N, FvN;
-    X12N = P12N = e23N = P23N = FvN = 0.0;
-    if (!WS) {
-      myx[0 * 32] = X12[0]; myx[1 * 32] = P12[0]; myx[2 * 32] = e23[0]; myx[3 * 32] = P23[0]; myx[4 * 32] = Fvp[0];
-      __syncthreads();
-      // every thread is done with raw stage s: refill it (plane n + NS)
-      if (tid == 0 && n + NS <= n_last) issue(n + NS);   // same ring slot as plane n
-      if (warp + 1 < NW) {
-        const double* nx_ = xch + ((par * NW + warp + 1) * NX) * 32 + lane;
-        X12N = nx_[0 * 32]; P12N = nx_[1 * 32]; e23N = nx_[2 * 32]; P23N = nx_[3 * 32]; FvN = nx_[4 * 32];
-      }
-    } else {
-      // all raw reads of this warp are in registers: release the TMA stage
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[s_cur]);
-      if (warp > 0) {                       // the warp to the south consumes my row 0
-        if (it >= 2) mbar_wait(&xempty[par * NW + warp], (uint32_t)(((it >> 1) & 1) ^ 1));
-        myx[0 * 32] = X12[0]; myx[1 * 32] = P12[0]; myx[2 * 32] = e23[0]; myx[3 * 32] = P23[0]; myx[4 * 32] = Fvp[0];
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&xfull[par * NW + warp]);
-      }
-      if (warp + 1 < NW) {
-        mbar_wait(&xfull[par * NW + warp + 1], (uint32_t)((it >> 1) & 1));
-        const double* nx_ = xch + ((par * NW + warp + 1) * NX) * 32 + lane;
-        X12N = nx_[0 * 32]; P12N = nx_[1 * 32]; e23N = nx_[2 * 32]; P23N = nx_[3 * 32]; FvN = nx_[4 * 32];
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&xempty[par * NW + warp + 1]);
-      }
+    if (H_ADV) { myx[0 * 32] = P12[0]; myx[1 * 32] = P23[0]; }
+    if (OUT) { myx[2 * 32] = X12[0]; myx[3 * 32] = e23[0]; myx[4 * 32] = Fvp[0]; }
+    __syncthreads();
+    // every thread is done with raw stage s: refill it (plane n + NS)
+    if (tid == 0 && n + NS <= n_last) issue(n + NS);   // same ring slot as plane n
+    double X12N = 0.0, P12N = 0.0, e23N = 0.0, P23N = 0.0, FvN = 0.0;
+    if (warp + 1 < NW) {
+      const double* nx_ = xch + ((par * NW + warp + 1) * NX) * 32 + lane;
+      if (H_ADV) { P12N = nx_[0 * 32]; P23N = nx_[1 * 32]; }
+      if (OUT) { X12N = nx_[2 * 32]; e23N = nx_[3 * 32]; FvN = nx_[4 * 32]; }
     }
-    const bool p1 = (n - 1) >= k0 && (n - 1) <= k1, p2 = (n - 2) >= k0 && (n - 2) <= k1;
 
     // ---- stage 2 / finalisation, row by row (north neighbour: own row r+1, or the exchanged row) -----------------
 #pragma unroll
     for (int r = 0; r < RY; ++r) {
       const bool last = (r == RY - 1);
-      const double x12n = last ? X12N : X12[last ? r : r + 1];
       const double p12n = last ? P12N : P12[last ? r : r + 1];
-      const double e23n = last ? e23N : e23[last ? r : r + 1];
       const double p23n = last ? P23N : P23[last ? r : r + 1];
-      const double fvn = last ? FvN : Fvp[last ? r : r + 1];          // Fv(j+1) at plane n-2
-      const double w1 = p1 ? wrow[r] : 0.0;                            // plane n-1 terms
-      const double w2 = p2 ? wrow[r] : 0.0;                            // ADV lags one more plane
       const double dwz = wc[r] - wp[r];
-      // eps(n-1) = [in-plane + xy edges](n-1) + z strain + the fcf/cff edge sums at faces n-1 and n
-      if (H_EPS) {
-        const double edge_n = Y13[r] + (e23[r] + e23n);
-        const double raw = fma(dwz * dwz, dz2, Eacc[r] + edge_n);
-        Eacc[r] = (inpl[r] + edge_n) + (X12[r] + x12n);
-        emit(FD_EPS, raw, SC_EPS, w1, n - 1, r);
-      }
-      if (H_K) {
-        const double wsq = wc[r] * wc[r];
-        const double raw = Kacc[r] + wsq;
-        Kacc[r] = Kxy[r] + wsq;
-        emit(FD_K, raw, SC_K, w1, n - 1, r);
-      }
-      if (H_PR) {
-        const double fz = wc[r] * (pc[r] - pp[r]);
-        const double raw = fma(fz, rdz, PRacc[r]);
-        PRacc[r] = fma(fz, rdz, PRxy[r]);
-        emit(FD_PR, raw, SC_PR, w1, n - 1, r);
-      }
-      if (NEED_B) {
-        const double dbz = bc[r] - bp[r];
-        if (H_WB) {
-          const double hz = wc[r] * (bp[r] + bc[r]);
-          const double raw = hzp[r] + hz;
-          hzp[r] = hz;
-          emit(FD_WB, raw, SC_WB, w1, n - 1, r);
+      if (OUT) {
+        const double x12n = last ? X12N : X12[last ? r : r + 1];
+        const double e23n = last ? e23N : e23[last ? r : r + 1];
+        const double fvn = last ? FvN : Fvp[last ? r : r + 1];          // Fv(j+1) at plane n-2
+        const double w1 = pv1 * wrow[r];                                 // plane n-1 terms
+        const double w2 = pv2 * wrow[r];                                 // ADV lags one more plane
+        // eps(n-1) = [in-plane + xy edges](n-1) + z strain + the fcf/cff edge sums at faces n-1 and n
+        if (H_EPS) {
+          const double edge_n = Y13[r] + (e23[r] + e23n);
+          const double raw = fma(dwz * dwz, dz2, Eacc[r] + edge_n);
+          Eacc[r] = (inpl[r] + edge_n) + (X12[r] + x12n);
+          emit(FD_EPS, raw, SC_EPS, w1, n - 1, r);
         }
-        if (H_CHI) {
-          const double gz = dbz * dbz;
-          const double raw = fma(gz, rdz2, CHacc[r]);
-          CHacc[r] = fma(gz, rdz2, CHxy[r]);
-          emit(FD_CHI, raw, SC_CHI, w1, n - 1, r);
+        if (H_K) {
+          const double wsq = wc[r] * wc[r];
+          const double raw = Kacc[r] + wsq;
+          Kacc[r] = Kxy[r] + wsq;
+          emit(FD_K, raw, SC_K, w1, n - 1, r);
         }
-        if (H_CDF) {
-          const double raw = bp[r] * fma(-dbz, rdz2, CDacc[r]);
-          CDacc[r] = fma(dbz, rdz2, CDxy[r]);
-          emit(FD_CDF, raw, SC_CDF, w1, n - 1, r);
+        if (H_PR) {
+          const double fz = wc[r] * (pc[r] - pp[r]);
+          const double raw = fma(fz, rdz, PRacc[r]);
+          PRacc[r] = fma(fz, rdz, PRxy[r]);
+          emit(FD_PR, raw, SC_PR, w1, n - 1, r);
         }
-      }
-      if (H_ADV) {
-        // faces of plane n-1: F = velocity x flux divergence (the common 1/8 is the diagnostic's scale factor)
-        const double Fu = up[r] * fma(P13[r] - P13p[r], rdz, dU[r]);
-        const double Fv = vp[r] * fma(P23[r] - P23p[r], rdz, dV[r]);
-        const double wsum = wp[r] + wc[r];
-        const double Wwp = wsum * wsum;                                 // Ww at cell plane n-1
-        const double Fw = wp[r] * fma(Wwp - Wwpp[r], rdz, dW[r]);      // face n-1
-        // ADV(n-2) = 1/8 [Fu + FuE + Fv + FvN + Fw(n-2) + Fw(n-1)]
-        const double raw = (Apart[r] + fvn) + Fw;
-        const double FuE = __shfl_down_sync(FULLMASK, Fu, 1);
-        Apart[r] = (Fu + FuE) + (Fv + Fw);
-        Fvp[r] = Fv;
-        Wwpp[r] = Wwp;
-        dU[r] = fma(Uu[r] - UuW[r], rdx, (p12n - P12[r]) * rdy);
-        dV[r] = fma(P12E[r] - P12[r], rdx, (Vv[r] - VvS[r]) * rdy);
-        dW[r] = fma(P13E[r] - P13[r], rdx, (p23n - P23[r]) * rdy);
-        P13p[r] = P13[r]; P23p[r] = P23[r];
-        emit(FD_ADV, raw, SC_ADV, w2, n - 2, r);
+        if (NEED_B) {
+          const double dbz = bc[r] - bp[r];
+          if (H_WB) {
+            const double hz = wc[r] * (bp[r] + bc[r]);
+            const double raw = hzp[r] + hz;
+            hzp[r] = hz;
+            emit(FD_WB, raw, SC_WB, w1, n - 1, r);
+          }
+          if (H_CHI) {
+            const double gz = dbz * dbz;
+            const double raw = fma(gz, rdz2, CHacc[r]);
+            CHacc[r] = fma(gz, rdz2, CHxy[r]);
+            emit(FD_CHI, raw, SC_CHI, w1, n - 1, r);
+          }
+          if (H_CDF) {
+            const double raw = bp[r] * fma(-dbz, rdz2, CDacc[r]);
+            CDacc[r] = fma(dbz, rdz2, CDxy[r]);
+            emit(FD_CDF, raw, SC_CDF, w1, n - 1, r);
+          }
+        }
+        if (H_ADV) {
+          // faces of plane n-1: F = velocity x flux divergence (the common 1/8 is the diagnostic's scale factor)
+          const double Fu = up[r] * fma(P13[r] - P13p[r], rdz, dU[r]);
+          const double Fv = vp[r] * fma(P23[r] - P23p[r], rdz, dV[r]);
+          const double wsum = wp[r] + wc[r];
+          const double Wwp = wsum * wsum;                                 // Ww at cell plane n-1
+          const double Fw = wp[r] * fma(Wwp - Wwpp[r], rdz, dW[r]);      // face n-1
+          // ADV(n-2) = 1/8 [Fu + FuE + Fv + FvN + Fw(n-2) + Fw(n-1)]
+          const double raw = (Apart[r] + fvn) + Fw;
+          const double FuE = __shfl_down_sync(FULLMASK, Fu, 1);
+          Apart[r] = (Fu + FuE) + (Fv + Fw);
+          Fvp[r] = Fv;
+          Wwpp[r] = Wwp;
+          dU[r] = fma(Uu[r] - UuW[r], rdx, (p12n - P12[r]) * rdy);
+          dV[r] = fma(P12E[r] - P12[r], rdx, (Vv[r] - VvS[r]) * rdy);
+          dW[r] = fma(P13E[r] - P13[r], rdx, (p23n - P23[r]) * rdy);
+          P13p[r] = P13[r]; P23p[r] = P23[r];
+          emit(FD_ADV, raw, SC_ADV, w2, n - 2, r);
+        }
+      } else {
+        // ---- integrals only: every term goes straight into its accumulator with its multiplicity -----------------
+        const double pz = pv0 + pv1;
+        const double wc0 = wrow[r] * pv0, wc1 = wrow[r] * pv1, wcz = wrow[r] * pz;
+        if (H_EPS) acc[FD_EPS] = fma(dwz * dwz, dz2 * wc1, fma(inpl[r], wc0, acc[FD_EPS]));
+        if (H_K) acc[FD_K] = fma(wc[r] * wc[r], wcz, fma(Kxy[r], wc0, acc[FD_K]));
+        if (H_PR) acc[FD_PR] = fma(wc[r] * (pc[r] - pp[r]), rdz * wcz, fma(PRxy[r], wc0, acc[FD_PR]));
+        if (NEED_B) {
+          const double dbz = bc[r] - bp[r];
+          if (H_WB) acc[FD_WB] = fma(wc[r] * (bp[r] + bc[r]), wcz, acc[FD_WB]);
+          if (H_CHI) acc[FD_CHI] = fma(dbz * dbz, rdz2 * wcz, fma(CHxy[r], wc0, acc[FD_CHI]));
+          if (H_CDF) {
+            const double raw = bp[r] * fma(-dbz, rdz2, CDacc[r]);
+            CDacc[r] = fma(dbz, rdz2, CDxy[r]);
+            acc[FD_CDF] = fma(raw, wc1, acc[FD_CDF]);
+          }
+        }
+        if (H_ADV) {
+          // faces of plane n-1, each weighted by the output cells on its two sides
+          const double Fu = up[r] * fma(P13[r] - P13p[r], rdz, dU[r]);
+          const double Fv = vp[r] * fma(P23[r] - P23p[r], rdz, dV[r]);
+          const double wsum = wp[r] + wc[r];
+          const double Wwp = wsum * wsum;
+          const double Fw = wp[r] * fma(Wwp - Wwpp[r], rdz, dW[r]);      // face n-1: cells n-1 and n-2
+          double a = acc[FD_ADV];
+          a = fma(Fu, mx[r] * pv1, a);
+          a = fma(Fv, my[r] * pv1, a);
+          a = fma(Fw, wrow[r] * (pv1 + pv2), a);
+          acc[FD_ADV] = a;
+          Wwpp[r] = Wwp;
+          dU[r] = fma(Uu[r] - UuW[r], rdx, (p12n - P12[r]) * rdy);
+          dV[r] = fma(P12E[r] - P12[r], rdx, (Vv[r] - VvS[r]) * rdy);
+          dW[r] = fma(P13E[r] - P13[r], rdx, (p23n - P23[r]) * rdy);
+          P13p[r] = P13[r]; P23p[r] = P23[r];
+        }
       }
       up[r] = uc[r]; vp[r] = vc[r]; wp[r] = wc[r];
       if (NEED_B) bp[r] = bc[r];
@@ -394,7 +419,7 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
       __syncthreads();
       if (tid == 0) {
         double s = 0.0;
-        for (int w = 0; w < NW + (WS ? 1 : 0); ++w) s += red[w];
+        for (int w = 0; w < NW; ++w) s += red[w];
         const double scale[FD_N] = {SC_K, SC_ADV, SC_PR, SC_WB, SC_EPS, SC_CHI, SC_CDF};
         P.partial[(size_t)blockIdx.x * P.nslots + P.o[d].slot] = s * (P.V * scale[d]);
       }
@@ -422,39 +447,30 @@ EncodeTiledFn get_encode_fn() {
 struct ocb_fused_plan {
   FusedParams P;
   CUtensorMap maps[5];
-  int mask, nw, ry, ns, ws;
+  int mask, nw, ry, ns;
   int nblocks;
   size_t smem;
   void (*kernel)(FusedParams, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap);
 };
 
-template <int MASK, int NW, int RY, int NS, bool WS>
-static int setup_variant_ws(ocb_fused_plan* fp, bool out) {
+template <int MASK, int NW, int RY, int NS>
+static int setup_variant(ocb_fused_plan* fp, bool out) {
   using G = Geo<NW, RY>;
   constexpr bool NEED_B = MASK & ((1 << FD_WB) | (1 << FD_CHI) | (1 << FD_CDF)), NEED_P = MASK & (1 << FD_PR);
   constexpr int NF = 3 + (NEED_B ? 1 : 0) + (NEED_P ? 1 : 0);
-  fp->nw = NW; fp->ry = RY; fp->ns = NS; fp->mask = MASK; fp->ws = WS ? 1 : 0;
-  fp->smem = sizeof(double) * ((size_t)NS * NF * G::TILE + 2 * NW * 5 * 32 + NW + 1) + sizeof(uint64_t) * (2 * NS + 4 * NW);
+  fp->nw = NW; fp->ry = RY; fp->ns = NS; fp->mask = MASK;
+  fp->smem = sizeof(double) * ((size_t)NS * NF * G::TILE + 2 * NW * 5 * 32 + NW) + sizeof(uint64_t) * NS;
   // ask for the largest shared-memory carveout so that occupancy is set by registers, not by the default split
   if (out) {
-    cudaFuncSetAttribute(ocb_budget_kernel<MASK, NW, RY, NS, true, WS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    fp->kernel = ocb_budget_kernel<MASK, NW, RY, NS, true, WS>;
-    OCB_CUDA(cudaFuncSetAttribute(ocb_budget_kernel<MASK, NW, RY, NS, true, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp->smem));
+    cudaFuncSetAttribute(ocb_budget_kernel<MASK, NW, RY, NS, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    fp->kernel = ocb_budget_kernel<MASK, NW, RY, NS, true>;
+    OCB_CUDA(cudaFuncSetAttribute(ocb_budget_kernel<MASK, NW, RY, NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp->smem));
   } else {
-    cudaFuncSetAttribute(ocb_budget_kernel<MASK, NW, RY, NS, false, WS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    fp->kernel = ocb_budget_kernel<MASK, NW, RY, NS, false, WS>;
-    OCB_CUDA(cudaFuncSetAttribute(ocb_budget_kernel<MASK, NW, RY, NS, false, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp->smem));
+    cudaFuncSetAttribute(ocb_budget_kernel<MASK, NW, RY, NS, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    fp->kernel = ocb_budget_kernel<MASK, NW, RY, NS, false>;
+    OCB_CUDA(cudaFuncSetAttribute(ocb_budget_kernel<MASK, NW, RY, NS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp->smem));
   }
   return OCB_OK;
-}
-template <int MASK, int NW, int RY, int NS>
-static int setup_variant(ocb_fused_plan* fp, bool out) {
-  // Measured on B200 (profiles/r1_summary.md): the mbarrier hand-over costs more than the block barrier it removes
-  // (12,1,3: 55.9 vs 66.7 Gcells/s; the extra producer warp also halves the residency of the 8-warp shapes), so the
-  // block-barrier version is the default; OCB_FUSED_WS=1 selects the warp-specialised one for experiments.
-  const char* ws = getenv("OCB_FUSED_WS");
-  if (ws && ws[0] == '1') return setup_variant_ws<MASK, NW, RY, NS, true>(fp, out);
-  return setup_variant_ws<MASK, NW, RY, NS, false>(fp, out);
 }
 
 static int make_map(EncodeTiledFn enc, const ocb_field& f, int rows, CUtensorMap* map) {
@@ -540,29 +556,27 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
   // ---- variant: all seven terms, or the dissipation-only kernel ---------------------------------------------
   constexpr int ALL = (1 << FD_N) - 1;
   int rc;
-  const char* cfg = getenv("OCB_FUSED_CONFIG");   // tuning hook: "NW,RY,NS"
-  int nw = 12, ry = 1, ns = 3;   // measured best on B200 at 1024^3 (profiles/r1_tuning.md)
+  // Shapes measured on B200 at 1024^3 (profiles/r1_summary.md): integrals only -> 12 warps x 2 rows (one 384-thread
+  // block per SM, 23/24 x 31/32 of the lanes produce output); with output fields -> 6 warps x 2 rows, two blocks per SM.
+  // OCB_FUSED_CONFIG="NW,RY,NS" overrides the shape of the all-terms kernel for tuning runs.
+  const char* cfg = getenv("OCB_FUSED_CONFIG");
+  int nw = any_out ? 6 : 12, ry = 2, ns = 3;
   if (cfg) sscanf(cfg, "%d,%d,%d", &nw, &ry, &ns);
   constexpr int VEL = (1 << FD_K) | (1 << FD_ADV) | (1 << FD_EPS);                 // velocity-only terms
   constexpr int VELP = VEL | (1 << FD_PR);                                          // + pressure
   constexpr int VELB = VEL | (1 << FD_WB) | (1 << FD_CHI) | (1 << FD_CDF);          // + tracer
-  if (mask == (1 << FD_EPS)) {
-    rc = setup_variant<(1 << FD_EPS), 12, 1, 3>(fp, any_out);
-  } else if ((mask & ~VEL) == 0) {
-    rc = setup_variant<VEL, 12, 1, 3>(fp, any_out);
-  } else if ((mask & ~VELP) == 0) {
-    rc = setup_variant<VELP, 12, 1, 3>(fp, any_out);
-  } else if ((mask & ~VELB) == 0) {
-    rc = setup_variant<VELB, 12, 1, 3>(fp, any_out);
-  } else {
-    if (nw == 4 && ry == 2) rc = setup_variant<ALL, 4, 2, 3>(fp, any_out);
-    else if (nw == 8 && ry == 1) rc = setup_variant<ALL, 8, 1, 3>(fp, any_out);
-    else if (nw == 8 && ry == 2) rc = setup_variant<ALL, 8, 2, 3>(fp, any_out);
-    else if (nw == 12 && ry == 2) rc = setup_variant<ALL, 12, 2, 3>(fp, any_out);
-    else if (nw == 12 && ry == 1) rc = setup_variant<ALL, 12, 1, 3>(fp, any_out);
-    else if (nw == 6 && ry == 2) rc = setup_variant<ALL, 6, 2, 3>(fp, any_out);
-    else rc = setup_variant<ALL, 12, 1, 3>(fp, any_out);
-  }
+#define OCB_PICK(M) (any_out ? setup_variant<M, 6, 2, 3>(fp, true) : setup_variant<M, 12, 2, 3>(fp, false))
+  if (mask == (1 << FD_EPS)) rc = OCB_PICK((1 << FD_EPS));
+  else if ((mask & ~VEL) == 0) rc = OCB_PICK(VEL);
+  else if ((mask & ~VELP) == 0) rc = OCB_PICK(VELP);
+  else if ((mask & ~VELB) == 0) rc = OCB_PICK(VELB);
+  else if (!cfg) rc = OCB_PICK(ALL);
+#undef OCB_PICK
+  else if (nw == 8 && ry == 1) rc = setup_variant<ALL, 8, 1, 3>(fp, any_out);
+  else if (nw == 12 && ry == 1) rc = setup_variant<ALL, 12, 1, 3>(fp, any_out);
+  else if (nw == 6 && ry == 2) rc = setup_variant<ALL, 6, 2, 3>(fp, any_out);
+  else if (nw == 8 && ry == 2) rc = setup_variant<ALL, 8, 2, 3>(fp, any_out);
+  else rc = setup_variant<ALL, 12, 2, 3>(fp, any_out);
   if (rc != OCB_OK) { delete fp; return rc; }
   const bool vneed_b = fp->mask & ((1 << FD_WB) | (1 << FD_CHI) | (1 << FD_CDF)), vneed_p = fp->mask & (1 << FD_PR);
   if ((vneed_b && !tma_compatible(in->b, grid)) || (vneed_p && !tma_compatible(in->p, grid))) { delete fp; return OCB_OK; }
@@ -608,7 +622,7 @@ int ocb_fused_nblocks(const ocb_fused_plan* fp) { return fp->nblocks; }
 
 int ocb_fused_execute(ocb_fused_plan* fp, double* partial, cudaStream_t st) {
   fp->P.partial = partial;
-  dim3 block(32, fp->nw + fp->ws, 1), grid(fp->nblocks, 1, 1);
+  dim3 block(32, fp->nw, 1), grid(fp->nblocks, 1, 1);
   fp->kernel<<<grid, block, fp->smem, st>>>(fp->P, fp->maps[0], fp->maps[1], fp->maps[2], fp->maps[3], fp->maps[4]);
   OCB_CUDA(cudaGetLastError());
   return OCB_OK;
