@@ -28,6 +28,7 @@
 #include "ocb_sweep_fused.cuh"
 #include <cuda.h>
 #include <new>
+#include <type_traits>
 
 namespace {
 
@@ -202,14 +203,17 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
   int s = 0;
   uint32_t phase = 0;
   int par = 0;
-  for (int n = n_first; n <= n_last; ++n) {
+  // One plane step.  STEADY (a compile-time tag): planes n, n-1 and n-2 all lie inside this block's z chunk, so the
+  // plane-validity factors are the constants 1 and fold away; the few steps at the chunk ends take the general form.
+  auto plane_step = [&](auto steady_tag, const int n) {
+    constexpr bool STEADY = decltype(steady_tag)::value;
     mbar_wait(&full[s], phase);
     const double* T = tiles + s * (NF * G::TILE);
     const double* Tu = T, *Tv = T + G::TILE, *Tw = T + 2 * G::TILE, *Tb = T + F_B * G::TILE, *Tp = T + F_P * G::TILE;
     if (++s == NS) { s = 0; phase ^= 1; }
     // plane validity (uniform): cells of plane n, n-1, n-2 inside this block's z chunk
-    const double pv0 = (n >= k0 && n <= k1) ? 1.0 : 0.0, pv1 = ((n - 1) >= k0 && (n - 1) <= k1) ? 1.0 : 0.0,
-                 pv2 = ((n - 2) >= k0 && (n - 2) <= k1) ? 1.0 : 0.0;
+    const double pv0 = STEADY ? 1.0 : ((n >= k0 && n <= k1) ? 1.0 : 0.0), pv1 = STEADY ? 1.0 : (((n - 1) >= k0 && (n - 1) <= k1) ? 1.0 : 0.0),
+                 pv2 = STEADY ? 1.0 : (((n - 2) >= k0 && (n - 2) <= k1) ? 1.0 : 0.0);
 
     // ---- stage 1: quantities owned by this thread's cells at plane n --------------------------------------
     double uc[RY], vc[RY], wc[RY], bc[RY], pc[RY];
@@ -405,6 +409,13 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
       if (NEED_P) pp[r] = pc[r];
     }
     par ^= 1;
+  };
+  {
+    int n = n_first;
+    const int steady_lo = k0 + 2, steady_hi = k1;
+    for (; n <= n_last && n < steady_lo; ++n) plane_step(std::false_type{}, n);
+    for (; n <= steady_hi; ++n) plane_step(std::true_type{}, n);
+    for (; n <= n_last; ++n) plane_step(std::false_type{}, n);
   }
 
   // ---- volume integrals: warp shuffle, then one partial per block and slot -------------------------------------
@@ -573,6 +584,10 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
   else if (!cfg) rc = OCB_PICK(ALL);
 #undef OCB_PICK
   else if (nw == 8 && ry == 1) rc = setup_variant<ALL, 8, 1, 3>(fp, any_out);
+  else if (nw == 16 && ry == 1) rc = setup_variant<ALL, 16, 1, 3>(fp, any_out);
+  else if (nw == 12 && ry == 2 && ns == 4) rc = setup_variant<ALL, 12, 2, 4>(fp, any_out);
+  else if (nw == 12 && ry == 2 && ns == 2) rc = setup_variant<ALL, 12, 2, 2>(fp, any_out);
+  else if (nw == 10 && ry == 2) rc = setup_variant<ALL, 10, 2, 3>(fp, any_out);
   else if (nw == 12 && ry == 1) rc = setup_variant<ALL, 12, 1, 3>(fp, any_out);
   else if (nw == 6 && ry == 2) rc = setup_variant<ALL, 6, 2, 3>(fp, any_out);
   else if (nw == 8 && ry == 2) rc = setup_variant<ALL, 8, 2, 3>(fp, any_out);
