@@ -236,6 +236,11 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = plan.algorithmic_bytes / (sweep_ms * 1e-3) / 1e9
+    # DRAM traffic of one launch of the sweep kernel, from the committed ncu capture of this exact workload
+    # (profiles/r1_traffic_bench1024_v7.csv: dram__bytes_read.sum + dram__bytes_write.sum); null for other shapes
+    traffic = None
+    if size == (1024, 1024, 1024) and not args.fields and plan.variant == 1:
+        traffic = 45682806272 + 22822144
     integrals = grp.integrals() if overlapped is None else [float(x) for x in overlapped.total.cpu()]
 
     out = {
@@ -250,7 +255,7 @@ def main():
                    "l2": "inputs (5 x %.2f GB per GPU) exceed the 126 MB L2; no flush needed" % (cells_local * 8 / 1e9),
                    "kernel_variant": {0: "generic", 1: "fused-budget"}.get(plan.variant, str(plan.variant))},
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                     "traffic": None, "kernel_ms": round(sweep_ms, 4), "algorithmic_bytes_per_cell": plan.algorithmic_bytes / cells_local,
+                     "traffic": traffic, "kernel_ms": round(sweep_ms, 4), "algorithmic_bytes_per_cell": plan.algorithmic_bytes / cells_local,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
         "gpu_launches": ((3 if overlapped is not None else 1) * plan.n_launches + (4 * 5 if exchanger is not None else 0)) * args.steps,
         "clocks": clocks.summary(),
