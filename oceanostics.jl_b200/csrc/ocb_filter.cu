@@ -12,6 +12,7 @@
 // Intermediates live in stream-ordered scratch owned by the library.
 #include "ocb_common.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 template <class T>
 struct PassParams {
@@ -103,6 +104,102 @@ __global__ void __launch_bounds__(256) ocb_filter_pass_kernel(const __grid_const
   }
 }
 
+// ---- interior fast paths (box and uniform Gaussian, half width W known at compile time) -------------------------
+// Interior outputs (whole stencil inside the axis) need no boundary policy.  With W a template parameter the tap loops
+// unroll completely and the weights are read as constant-bank operands straight from the kernel parameters.
+//
+// (1) x pass: one output per thread, 2W+1 cached loads of consecutive addresses.
+template <class T, int W, bool BOX>
+__global__ void __launch_bounds__(256) ocb_filter_x_kernel(const __grid_constant__ PassParams<T> P) {
+  constexpr int NT = 2 * W + 1;
+  const int i = P.lo[0] + blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = P.lo[1] + blockIdx.y * blockDim.y + threadIdx.y;
+  if (i > P.hi[0] || j > P.hi[1]) return;
+  T wtot = T(0);
+  if (!BOX) {
+#pragma unroll
+    for (int t = 0; t < NT; ++t) wtot += P.weights[t] * T(1);
+  }
+  for (int k = P.lo[2] + blockIdx.z; k <= P.hi[2]; k += gridDim.z) {
+    const T* q = P.src + (long long)(i - W) * P.ss[0] + j * P.ss[1] + k * P.ss[2];
+    T s = T(0);
+#pragma unroll
+    for (int t = 0; t < NT; ++t) s = BOX ? s + __ldg(q + t) : s + P.weights[t] * __ldg(q + t);
+    P.dst[i * P.ds[0] + j * P.ds[1] + k * P.ds[2]] = BOX ? s / T(NT) : s / wtot;
+  }
+}
+
+// (2) y / z pass: a thread slides a register window of 2W+1 inputs along the filtered axis -- one load, 2W+1 FMAs and
+// one store per output.  Threads run along x (coalesced); blockIdx.y walks the third axis, blockIdx.z the segments of
+// the filtered axis.  The window rotates through compile-time slot indices (the loop is unrolled 2W+1 times).
+template <class T, int W, bool BOX>
+__global__ void __launch_bounds__(128) ocb_filter_slide_kernel(const __grid_constant__ PassParams<T> P, int c_lo, int c_hi, int seg) {
+  constexpr int NT = 2 * W + 1;
+  const int dim = P.dim, oth = dim == 1 ? 2 : 1;                 // filtered axis, and the remaining (non-x) axis
+  const int i = P.lo[0] + blockIdx.x * blockDim.x + threadIdx.x;
+  const int o = P.lo[oth] + blockIdx.y;
+  if (i > P.hi[0]) return;
+  const int c0 = c_lo + blockIdx.z * seg;
+  const int c1 = min(c0 + seg - 1, c_hi);
+  if (c0 > c1) return;
+  const long long sd = P.ss[dim], dd = P.ds[dim];
+  const T* in = P.src + i * P.ss[0] + (long long)o * P.ss[oth];
+  T* out = P.dst + i * P.ds[0] + (long long)o * P.ds[oth];
+  T wtot = T(0);
+  if (!BOX) {
+#pragma unroll
+    for (int t = 0; t < NT; ++t) wtot += P.weights[t] * T(1);
+  }
+  T win[NT];
+#pragma unroll
+  for (int m = 0; m < NT - 1; ++m) win[m] = __ldg(in + (long long)(c0 - W + m) * sd);
+  win[NT - 1] = T(0);
+  for (int c = c0; c <= c1; c += NT) {
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      if (c + t <= c1) {
+        win[(2 * W + t) % NT] = __ldg(in + (long long)(c + t + W) * sd);
+        T s = T(0);
+#pragma unroll
+        for (int j = 0; j < NT; ++j) s = BOX ? s + win[(t + j) % NT] : s + P.weights[j] * win[(t + j) % NT];
+        out[(long long)(c + t) * dd] = BOX ? s / T(NT) : s / wtot;
+      }
+    }
+  }
+}
+
+template <class T, int W, bool BOX>
+static void launch_fast_w(const PassParams<T>& P, int c_lo, int c_hi, cudaStream_t st) {
+  PassParams<T> Q = P;
+  if (P.dim == 0) {
+    Q.lo[0] = c_lo; Q.hi[0] = c_hi;
+    const int ni = c_hi - c_lo + 1, nj = P.hi[1] - P.lo[1] + 1, nk = P.hi[2] - P.lo[2] + 1;
+    dim3 block(64, 4, 1), grid((ni + 63) / 64, (nj + 3) / 4, nk < 128 ? nk : 128);
+    ocb_filter_x_kernel<T, W, BOX><<<grid, block, 0, st>>>(Q);
+  } else {
+    const int oth = P.dim == 1 ? 2 : 1;
+    const int ni = P.hi[0] - P.lo[0] + 1, no = P.hi[oth] - P.lo[oth] + 1, nc = c_hi - c_lo + 1;
+    int seg = 128;
+    if (nc < seg) seg = nc;
+    dim3 block(128, 1, 1), grid((ni + 127) / 128, no, (nc + seg - 1) / seg);
+    ocb_filter_slide_kernel<T, W, BOX><<<grid, block, 0, st>>>(Q, c_lo, c_hi, seg);
+  }
+}
+// returns false when no fast instantiation exists for this half width
+template <class T, bool BOX>
+static bool launch_fast(const PassParams<T>& P, int c_lo, int c_hi, cudaStream_t st) {
+  switch (P.width) {
+    case 1: launch_fast_w<T, 1, BOX>(P, c_lo, c_hi, st); return true;
+    case 2: launch_fast_w<T, 2, BOX>(P, c_lo, c_hi, st); return true;
+    case 3: launch_fast_w<T, 3, BOX>(P, c_lo, c_hi, st); return true;
+    case 4: launch_fast_w<T, 4, BOX>(P, c_lo, c_hi, st); return true;
+    case 5: launch_fast_w<T, 5, BOX>(P, c_lo, c_hi, st); return true;
+    case 6: launch_fast_w<T, 6, BOX>(P, c_lo, c_hi, st); return true;
+    case 8: launch_fast_w<T, 8, BOX>(P, c_lo, c_hi, st); return true;
+    default: return false;
+  }
+}
+
 template <class T, int KIND>
 static void launch_pass_policy(const PassParams<T>& P, dim3 grid, dim3 block, cudaStream_t st) {
   switch (P.policy) {
@@ -159,10 +256,28 @@ static int filter_impl(const ocb_field* src, const int32_t ext[3], const ocb_fil
     P.left = T(fp.left); P.right = T(fp.right); P.sigma = T(fp.sigma); P.period = T(fp.period);
     if (fp.kind == OCB_FILTER_GAUSSIAN) for (int t = 0; t < 2 * fp.width + 1; ++t) P.weights[t] = T(fp.weights[t]);
     if (fp.kind == OCB_FILTER_GAUSSIAN_STRETCHED) { P.nodes = (const T*)fp.nodes - 1; P.spacings = (const T*)fp.spacings - 1; }
-    dim3 block(32, 8, 1);
-    const int ni = P.hi[0] - P.lo[0] + 1, nj = P.hi[1] - P.lo[1] + 1, nk = P.hi[2] - P.lo[2] + 1;
-    dim3 grid((ni + 31) / 32, (nj + 7) / 8, nk < 256 ? nk : 256);
-    launch_pass<T>(P, grid, block, st);
+    auto launch_generic = [&](const PassParams<T>& Q) {
+      dim3 block(32, 8, 1);
+      const int ni = Q.hi[0] - Q.lo[0] + 1, nj = Q.hi[1] - Q.lo[1] + 1, nk = Q.hi[2] - Q.lo[2] + 1;
+      if (ni <= 0 || nj <= 0 || nk <= 0) return;
+      dim3 grid((ni + 31) / 32, (nj + 7) / 8, nk < 256 ? nk : 256);
+      launch_pass<T>(Q, grid, block, st);
+    };
+    // interior outputs [w+1, n-w] of the window go to the unrolled fast kernels, the two boundary bands to the
+    // policy-aware kernel
+    const int dm = P.dim;
+    const int c_lo = P.lo[dm] > fp.width + 1 ? P.lo[dm] : fp.width + 1;
+    const int c_hi = P.hi[dm] < fp.extent - fp.width ? P.hi[dm] : fp.extent - fp.width;
+    bool fast = false;
+    if (fp.kind != OCB_FILTER_GAUSSIAN_STRETCHED && c_hi - c_lo + 1 >= 4 * fp.width + 2 && !getenv("OCB_FILTER_NO_FAST"))
+      fast = fp.kind == OCB_FILTER_BOX ? launch_fast<T, true>(P, c_lo, c_hi, st) : launch_fast<T, false>(P, c_lo, c_hi, st);
+    if (fast) {
+      PassParams<T> B = P;
+      B.hi[dm] = c_lo - 1; launch_generic(B);           // low band
+      B = P; B.lo[dm] = c_hi + 1; launch_generic(B);    // high band
+    } else {
+      launch_generic(P);
+    }
     if (cudaGetLastError() != cudaSuccess) { ocb_set_error("filter pass launch failed"); rc = OCB_ERR_CUDA; break; }
   }
   for (int t = 0; t < 2; ++t) if (tmp[t]) cudaFreeAsync(tmp[t], st);
