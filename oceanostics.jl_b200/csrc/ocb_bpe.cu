@@ -325,10 +325,21 @@ __device__ __forceinline__ double bpe_psi(double zeta, const double* cum, const 
   const double psi_face = k - 1 ? psi_incl[k - 2] : 0.0;
   return psi_face + (double)bs[k - 1] * (zeta - fk);
 }
-// scatter z* and Ψδ back through the permutation into the destination fields
+// Ψ at the Nz cell-centre heights: z of a cell depends on k only, so the N per-cell binary searches of the
+// reference (reference_potential_function evaluated at every z, :359-368 / :383-397) collapse to Nz searches.
 template <class T>
+__global__ void bpe_psi_levels(const double* __restrict__ cum, const double* __restrict__ psi_incl, const T* __restrict__ bs, long long n, int Nz,
+                               double z_bot, double A, const T* __restrict__ zc1, T z0, T dz_uniform, double* __restrict__ psi_level) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= Nz) return;
+  const double zcell = zc1 ? (double)zc1[k] : (double)z0 + (double)dz_uniform * (k + 0.5);
+  psi_level[k] = bpe_psi<T>(zcell, cum, psi_incl, bs, n, z_bot, A);
+}
+// scatter z* and Ψδ back through the permutation into the destination fields.  SLOT_KNOWN (ThreeDimensionalSort): the
+// t-th sorted cell sits in slot t, so Ψ(z*) needs no search: Ψface[t] + b*[t] (z* - faces[t]).
+template <class T, bool SLOT_KNOWN>
 __global__ void bpe_scatter(const uint32_t* __restrict__ perm, const T* __restrict__ zs_sorted, const double* __restrict__ cum, const double* __restrict__ psi_incl,
-                            const T* __restrict__ bs, long long n, int Nx, int Ny, double z_bot, double A, const T* __restrict__ zc1, T z0, T dz_uniform,
+                            const T* __restrict__ bs, long long n, int Nx, int Ny, double z_bot, double A, const double* __restrict__ psi_level,
                             T* __restrict__ zstar, long long zs0, long long zs1, long long zs2, T* __restrict__ psid, long long ps0, long long ps1, long long ps2) {
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= n) return;
@@ -337,10 +348,14 @@ __global__ void bpe_scatter(const uint32_t* __restrict__ perm, const T* __restri
   const T zs = zs_sorted[t];
   zstar[i * zs0 + j * zs1 + k * zs2] = zs;
   if (psid) {
-    const double zcell = zc1 ? (double)zc1[k] : (double)z0 + (double)dz_uniform * (k + 0.5);
-    const double ps = bpe_psi<T>((double)zs, cum, psi_incl, bs, n, z_bot, A);
-    const double pz = bpe_psi<T>(zcell, cum, psi_incl, bs, n, z_bot, A);
-    psid[i * ps0 + j * ps1 + k * ps2] = (T)(pz - ps);
+    double ps;
+    if (SLOT_KNOWN) {
+      const double ft = z_bot + (t ? cum[t - 1] : 0.0) / A;
+      ps = (t ? psi_incl[t - 1] : 0.0) + (double)bs[t] * ((double)zs - ft);
+    } else {
+      ps = bpe_psi<T>((double)zs, cum, psi_incl, bs, n, z_bot, A);
+    }
+    psid[i * ps0 + j * ps1 + k * ps2] = (T)(psi_level[k] - ps);
   }
 }
 __global__ void bpe_perm_to_int64(const uint32_t* __restrict__ perm, long long n, int64_t* __restrict__ out) {
@@ -436,8 +451,15 @@ int bpe_impl(const ocb_grid* g, const ocb_field* b, int method, const ocb_field*
   rc = device_scan<double, OP_ADD, false, false>(bdz, psi, n, dtot, st); if (rc != OCB_OK) return rc;
   const T* z1 = Z.p + (Z.sx + Z.sy + Z.sz);
   T* p1 = P.p ? (T*)P.p + (P.sx + P.sy + P.sz) : nullptr;
-  bpe_scatter<T><<<gr, 256, 0, st>>>(perm, zs_sorted, cum, psi, bs, n, Nx, Ny, g->z_bottom, A, zc1, (T)g->z_bottom, (T)g->d[2], (T*)z1, Z.sx, Z.sy, Z.sz,
-                                    p1, P.sx, P.sy, P.sz);
+  double* psi_level = S.get<double>(Nz);
+  if (!psi_level) OCB_FAIL(OCB_ERR_ALLOC, "out of device memory for the reference-height scratch");
+  if (p1) bpe_psi_levels<T><<<(Nz + 127) / 128, 128, 0, st>>>(cum, psi, bs, n, Nz, g->z_bottom, A, zc1, (T)g->z_bottom, (T)g->d[2], psi_level);
+  if (method == OCB_BPE_THREE_DIMENSIONAL_SORT)
+    bpe_scatter<T, true><<<gr, 256, 0, st>>>(perm, zs_sorted, cum, psi, bs, n, Nx, Ny, g->z_bottom, A, psi_level, (T*)z1, Z.sx, Z.sy, Z.sz,
+                                            p1, P.sx, P.sy, P.sz);
+  else
+    bpe_scatter<T, false><<<gr, 256, 0, st>>>(perm, zs_sorted, cum, psi, bs, n, Nx, Ny, g->z_bottom, A, psi_level, (T*)z1, Z.sx, Z.sy, Z.sz,
+                                             p1, P.sx, P.sy, P.sz);
   if (perm_out) bpe_perm_to_int64<<<gr, 256, 0, st>>>(perm, n, perm_out);
   if (bs_out) OCB_CUDA(cudaMemcpyAsync(bs_out, bs, n * sizeof(T), cudaMemcpyDeviceToDevice, st));
   OCB_CUDA(cudaGetLastError());

@@ -170,6 +170,15 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
   double acc[FD_N];
 #pragma unroll
   for (int d = 0; d < FD_N; ++d) acc[d] = 0.0;
+  // integral-only mode: unweighted per-row sums by multiplicity class (x faces / fcf edges: mx, y faces / cff edges: my,
+  // ffc edges: mxy, cell and z-face terms: wrow); the class weights are applied once, after the plane loop
+  double aE_xy[RY], aE_x[RY], aE_y[RY], aE_c[RY], aK_x[RY], aK_y[RY], aK_z[RY], aP_x[RY], aP_y[RY], aP_z[RY];
+  double aC_x[RY], aC_y[RY], aC_z[RY], aW_z[RY], aD_c[RY], aA_x[RY], aA_y[RY], aA_z[RY];
+#pragma unroll
+  for (int r = 0; r < RY; ++r) {
+    aE_xy[r] = aE_x[r] = aE_y[r] = aE_c[r] = aK_x[r] = aK_y[r] = aK_z[r] = aP_x[r] = aP_y[r] = aP_z[r] = 0.0;
+    aC_x[r] = aC_y[r] = aC_z[r] = aW_z[r] = aD_c[r] = aA_x[r] = aA_y[r] = aA_z[r] = 0.0;
+  }
 
   const unsigned FULLMASK = 0xffffffffu;
   const bool lane_out = lane < 31 && i <= P.Nx;
@@ -214,6 +223,12 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
     // plane validity (uniform): cells of plane n, n-1, n-2 inside this block's z chunk
     const double pv0 = STEADY ? 1.0 : ((n >= k0 && n <= k1) ? 1.0 : 0.0), pv1 = STEADY ? 1.0 : (((n - 1) >= k0 && (n - 1) <= k1) ? 1.0 : 0.0),
                  pv2 = STEADY ? 1.0 : (((n - 2) >= k0 && (n - 2) <= k1) ? 1.0 : 0.0);
+    // integral-only accumulation factors: terms of plane n, of plane n-1, of z face n (half-weights at chunk ends),
+    // of z face n-1 -- all exactly 1 in the steady planes
+    const double f0 = pv0, f1 = pv1, fz = 0.5 * (pv0 + pv1), fw = 0.5 * (pv1 + pv2);
+    auto accum = [&](double& a, double x, double y, double f) {     // a += f * x * y  (f folds away when STEADY)
+      if (STEADY) a = fma(x, y, a); else a = fma(x * f, y, a);
+    };
 
     // ---- stage 1: quantities owned by this thread's cells at plane n --------------------------------------
     double uc[RY], vc[RY], wc[RY], bc[RY], pc[RY];
@@ -243,13 +258,10 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
         X12[r] = e12 + __shfl_down_sync(FULLMASK, e12, 1);      // x neighbours' edges by shuffle
         Y13[r] = e13 + __shfl_down_sync(FULLMASK, e13, 1);
       } else if (H_EPS) {
-        // each edge term straight into the integral, weighted by the output cells it belongs to
-        const double pz = pv0 + pv1;
-        double a = acc[FD_EPS];
-        a = fma(s12 * (mxy[r] * pv0), s12, a);
-        a = fma(s13 * (mx[r] * pz), s13, a);
-        a = fma(s23 * (my[r] * pz), s23, a);
-        acc[FD_EPS] = a;
+        // each edge term straight into its class sum (weights mxy, 2 mx, 2 my applied after the loop)
+        accum(aE_xy[r], s12, s12, f0);
+        accum(aE_x[r], s13, s13, fz);
+        accum(aE_y[r], s23, s23, fz);
       }
       if (H_ADV) {
         P12E[r] = __shfl_down_sync(FULLMASK, P12[r], 1);
@@ -261,25 +273,66 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
         if (r == 0) { const double vs = rv[1 - TW]; VvS[r] = (vs + vc[r]) * (vs + vc[r]); }
         else VvS[r] = Vv[r > 0 ? r - 1 : 0];
       }
-      if (H_EPS) {
-        const double ax = ue - uc[r], ay = vn - vc[r];
-        inpl[r] = fma(ax * ax, dx2, (ay * ay) * dy2);
-      }
-      if (H_K) Kxy[r] = fma(uc[r], uc[r], ue * ue) + fma(vc[r], vc[r], vn * vn);
-      if (NEED_P) {
-        const double* rp = Tp + row * TW + lane + xoff;
-        pc[r] = rp[1];
-        const double pw = rp[0], pe = rp[2], ps = rp[1 - TW], pn = rp[1 + TW];
-        const double tx_ = fma(ue, pe - pc[r], uc[r] * (pc[r] - pw));
-        const double ty_ = fma(vn, pn - pc[r], vc[r] * (pc[r] - ps));
-        PRxy[r] = fma(ty_, rdy, tx_ * rdx);
-      }
-      if (NEED_B) {
-        const double* rb = Tb + row * TW + lane + xoff;
-        bc[r] = rb[1];
-        const double dw_ = bc[r] - rb[0], de = rb[2] - bc[r], ds = bc[r] - rb[1 - TW], dn = rb[1 + TW] - bc[r];
-        if (H_CHI) CHxy[r] = fma(fma(dw_, dw_, de * de), rdx2, fma(ds, ds, dn * dn) * rdy2);
-        if (H_CDF) CDxy[r] = fma(dw_ - de, rdx2, (ds - dn) * rdy2);
+      if (OUT) {
+        if (H_EPS) {
+          const double ax = ue - uc[r], ay = vn - vc[r];
+          inpl[r] = fma(ax * ax, dx2, (ay * ay) * dy2);
+        }
+        if (H_K) Kxy[r] = fma(uc[r], uc[r], ue * ue) + fma(vc[r], vc[r], vn * vn);
+        if (NEED_P) {
+          const double* rp = Tp + row * TW + lane + xoff;
+          pc[r] = rp[1];
+          const double pw = rp[0], pe = rp[2], ps = rp[1 - TW], pn = rp[1 + TW];
+          const double tx_ = fma(ue, pe - pc[r], uc[r] * (pc[r] - pw));
+          const double ty_ = fma(vn, pn - pc[r], vc[r] * (pc[r] - ps));
+          PRxy[r] = fma(ty_, rdy, tx_ * rdx);
+        }
+        if (NEED_B) {
+          const double* rb = Tb + row * TW + lane + xoff;
+          bc[r] = rb[1];
+          const double dw_ = bc[r] - rb[0], de = rb[2] - bc[r], ds = bc[r] - rb[1 - TW], dn = rb[1 + TW] - bc[r];
+          if (H_CHI) CHxy[r] = fma(fma(dw_, dw_, de * de), rdx2, fma(ds, ds, dn * dn) * rdy2);
+          if (H_CDF) CDxy[r] = fma(dw_ - de, rdx2, (ds - dn) * rdy2);
+        }
+      } else {
+        // integrals only: every face / cell term of plane n and of z face n goes into its class sum here
+        const double dwz = wc[r] - wp[r];
+        if (H_EPS) {
+          const double ax = ue - uc[r], ay = vn - vc[r];
+          accum(aE_c[r], ax * dx2, ax, f0);
+          accum(aE_c[r], ay * dy2, ay, f0);
+          accum(aE_c[r], dwz * dz2, dwz, f1);               // S33 of the cell below
+        }
+        if (H_K) {
+          accum(aK_x[r], uc[r], uc[r], f0);
+          accum(aK_y[r], vc[r], vc[r], f0);
+          accum(aK_z[r], wc[r], wc[r], fz);
+        }
+        if (NEED_P) {
+          const double* rp = Tp + row * TW + lane + xoff;
+          pc[r] = rp[1];
+          accum(aP_x[r], uc[r], pc[r] - rp[0], f0);
+          accum(aP_y[r], vc[r], pc[r] - rp[1 - TW], f0);
+          accum(aP_z[r], wc[r], pc[r] - pp[r], fz);
+        }
+        if (NEED_B) {
+          const double* rb = Tb + row * TW + lane + xoff;
+          bc[r] = rb[1];
+          const double dw_ = bc[r] - rb[0], ds = bc[r] - rb[1 - TW], dbz = bc[r] - bp[r];
+          if (H_WB) accum(aW_z[r], wc[r], bp[r] + bc[r], fz);
+          if (H_CHI) {
+            accum(aC_x[r], dw_, dw_, f0);
+            accum(aC_y[r], ds, ds, f0);
+            accum(aC_z[r], dbz, dbz, fz);
+          }
+          if (H_CDF) {
+            const double de = rb[2] - bc[r], dn = rb[1 + TW] - bc[r];
+            const double cdxy = fma(dw_ - de, rdx2, (ds - dn) * rdy2);
+            const double lap = fma(-dbz, rdz2, CDacc[r]);   // Laplacian of the cell below, completed by this face
+            accum(aD_c[r], bp[r], lap, f1);
+            CDacc[r] = fma(dbz, rdz2, cdxy);
+          }
+        }
       }
     }
 
@@ -369,34 +422,13 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
           emit(FD_ADV, raw, SC_ADV, w2, n - 2, r);
         }
       } else {
-        // ---- integrals only: every term goes straight into its accumulator with its multiplicity -----------------
-        const double pz = pv0 + pv1;
-        const double wc0 = wrow[r] * pv0, wc1 = wrow[r] * pv1, wcz = wrow[r] * pz;
-        if (H_EPS) acc[FD_EPS] = fma(dwz * dwz, dz2 * wc1, fma(inpl[r], wc0, acc[FD_EPS]));
-        if (H_K) acc[FD_K] = fma(wc[r] * wc[r], wcz, fma(Kxy[r], wc0, acc[FD_K]));
-        if (H_PR) acc[FD_PR] = fma(wc[r] * (pc[r] - pp[r]), rdz * wcz, fma(PRxy[r], wc0, acc[FD_PR]));
-        if (NEED_B) {
-          const double dbz = bc[r] - bp[r];
-          if (H_WB) acc[FD_WB] = fma(wc[r] * (bp[r] + bc[r]), wcz, acc[FD_WB]);
-          if (H_CHI) acc[FD_CHI] = fma(dbz * dbz, rdz2 * wcz, fma(CHxy[r], wc0, acc[FD_CHI]));
-          if (H_CDF) {
-            const double raw = bp[r] * fma(-dbz, rdz2, CDacc[r]);
-            CDacc[r] = fma(dbz, rdz2, CDxy[r]);
-            acc[FD_CDF] = fma(raw, wc1, acc[FD_CDF]);
-          }
-        }
+        // ---- integrals only: what is left after the exchange is the advection faces of plane n-1 ---------------------
         if (H_ADV) {
-          // faces of plane n-1, each weighted by the output cells on its two sides
-          const double Fu = up[r] * fma(P13[r] - P13p[r], rdz, dU[r]);
-          const double Fv = vp[r] * fma(P23[r] - P23p[r], rdz, dV[r]);
           const double wsum = wp[r] + wc[r];
           const double Wwp = wsum * wsum;
-          const double Fw = wp[r] * fma(Wwp - Wwpp[r], rdz, dW[r]);      // face n-1: cells n-1 and n-2
-          double a = acc[FD_ADV];
-          a = fma(Fu, mx[r] * pv1, a);
-          a = fma(Fv, my[r] * pv1, a);
-          a = fma(Fw, wrow[r] * (pv1 + pv2), a);
-          acc[FD_ADV] = a;
+          accum(aA_x[r], up[r], fma(P13[r] - P13p[r], rdz, dU[r]), f1);
+          accum(aA_y[r], vp[r], fma(P23[r] - P23p[r], rdz, dV[r]), f1);
+          accum(aA_z[r], wp[r], fma(Wwp - Wwpp[r], rdz, dW[r]), fw);      // z face n-1: cells n-1 and n-2
           Wwpp[r] = Wwp;
           dU[r] = fma(Uu[r] - UuW[r], rdx, (p12n - P12[r]) * rdy);
           dV[r] = fma(P12E[r] - P12[r], rdx, (Vv[r] - VvS[r]) * rdy);
@@ -418,6 +450,21 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
     for (; n <= n_last; ++n) plane_step(std::false_type{}, n);
   }
 
+  if (!OUT) {
+    // apply the multiplicity of each class once: x faces / fcf edges mx, y faces / cff edges my, ffc edges mxy,
+    // cells wrow, z faces (shared by the cells above and below) 2 wrow
+#pragma unroll
+    for (int r = 0; r < RY; ++r) {
+      const double w2 = 2.0 * wrow[r];
+      if (H_EPS) acc[FD_EPS] += mxy[r] * aE_xy[r] + 2.0 * (mx[r] * aE_x[r] + my[r] * aE_y[r]) + wrow[r] * aE_c[r];
+      if (H_K) acc[FD_K] += mx[r] * aK_x[r] + my[r] * aK_y[r] + w2 * aK_z[r];
+      if (H_PR) acc[FD_PR] += rdx * (mx[r] * aP_x[r]) + rdy * (my[r] * aP_y[r]) + rdz * (w2 * aP_z[r]);
+      if (H_WB) acc[FD_WB] += w2 * aW_z[r];
+      if (H_CHI) acc[FD_CHI] += rdx2 * (mx[r] * aC_x[r]) + rdy2 * (my[r] * aC_y[r]) + rdz2 * (w2 * aC_z[r]);
+      if (H_CDF) acc[FD_CDF] += wrow[r] * aD_c[r];
+      if (H_ADV) acc[FD_ADV] += mx[r] * aA_x[r] + my[r] * aA_y[r] + w2 * aA_z[r];
+    }
+  }
   // ---- volume integrals: warp shuffle, then one partial per block and slot -------------------------------------
   if (P.nslots > 0) {
 #pragma unroll
