@@ -253,7 +253,7 @@ def main():
                    "per_gpu_grid": list(size), "halo": 3, "topology": "Periodic,Periodic,Bounded",
                    "parallelism": f"y-slabs x{world}" if world > 1 else "single GPU",
                    "l2": "inputs (5 x %.2f GB per GPU) exceed the 126 MB L2; no flush needed" % (cells_local * 8 / 1e9),
-                   "kernel_variant": {0: "generic", 1: "fused-budget"}.get(plan.variant, str(plan.variant))},
+                   "kernel_variant": {0: "generic", 1: "fused-budget", 2: "fused-budget + generic"}.get(plan.variant, str(plan.variant))},
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                      "traffic": traffic, "kernel_ms": round(sweep_ms, 4), "algorithmic_bytes_per_cell": plan.algorithmic_bytes / cells_local,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},

@@ -112,7 +112,7 @@ struct ocb_plan {
   void* ztab;             // library-owned z metric tables
   double* partial;        // per-block partial integrals
   dim3 grid, block;
-  int nblocks;
+  int nblocks, fused_blocks, generic_blocks, nslots;
   int n_launches;
   double algorithmic_bytes;
   ocb_fused_plan* fused;
@@ -180,15 +180,9 @@ static double count_algorithmic_bytes(const ocb_grid* g, const ocb_sweep_inputs*
   return (double)(nin + nout) * (double)ocb_sizeof(g->dtype) * (double)g->N[0] * (double)g->N[1] * (double)g->N[2];
 }
 
+// launch geometry of the generic kernel for the requests in *P
 template <class T>
-static int finish_plan(ocb_plan* pl, const ocb_grid* grid, const ocb_sweep_inputs* in, const ocb_request* reqs, int n,
-                       SweepParams<T>* P) {
-  ZTables<T> zt;
-  int rc = build_ztables<T>(grid, &pl->ztab, &zt);
-  if (rc != OCB_OK) return rc;
-  rc = ocb_build_sweep_params<T>(grid, in, reqs, n, zt, P);
-  if (rc != OCB_OK) return rc;
-  // launch geometry of the generic kernel
+static void generic_geometry(ocb_plan* pl, SweepParams<T>* P) {
   const int ni = P->hi[0] - P->lo[0] + 1, nj = P->hi[1] - P->lo[1] + 1, nk = P->hi[2] - P->lo[2] + 1;
   pl->block = dim3(32, 8, 1);
   const int gx = (ni + 31) / 32, gy = (nj + 7) / 8;
@@ -201,23 +195,59 @@ static int finish_plan(ocb_plan* pl, const ocb_grid* grid, const ocb_sweep_input
   gz = (nk + kchunk - 1) / kchunk;
   P->kchunk = kchunk;
   pl->grid = dim3(gx, gy, gz);
-  pl->nblocks = gx * gy * gz;
-  pl->variant = 0;
-  pl->n_launches = 1 + (P->nslots > 0 ? 1 : 0);
-  // the register-pipelined budget kernel takes the plan when it fits its envelope
-  pl->fused = nullptr;
-  rc = ocb_fused_try_create(grid, in, reqs, n, *P, &pl->fused);
+  pl->generic_blocks = gx * gy * gz;
+}
+
+// The planner: every request the register-pipelined budget kernel can evaluate goes to it (one launch), the rest to
+// the generic kernel (one launch); both write per-block partials of the same integral vector.
+//   variant 0: generic only, 1: budget kernel only, 2: split between the two.
+template <class T>
+static int finish_plan(ocb_plan* pl, const ocb_grid* grid, const ocb_sweep_inputs* in, const ocb_request* reqs, int n,
+                       SweepParams<T>* P) {
+  ZTables<T> zt;
+  int rc = build_ztables<T>(grid, &pl->ztab, &zt);
   if (rc != OCB_OK) return rc;
-  int nblocks = pl->nblocks;
-  if (pl->fused) {
-    pl->variant = 1;
-    nblocks = ocb_fused_nblocks(pl->fused);
-    pl->nblocks = nblocks;
+  rc = ocb_build_sweep_params<T>(grid, in, reqs, n, zt, P);      // validates every request, numbers the slots
+  if (rc != OCB_OK) return rc;
+  const int nslots = P->nslots;
+  pl->fused = nullptr;
+  pl->variant = 0;
+  // ---- fused subset ---------------------------------------------------------------------------------------
+  ocb_request fr[OCB_MAX_REQ], gr[OCB_MAX_REQ];
+  int nf = 0, ng = 0;
+  for (int r = 0; r < n; ++r) {
+    if (ocb_fused_handles_diag(reqs[r].diag)) fr[nf++] = reqs[r]; else gr[ng++] = reqs[r];
   }
-  if (P->nslots > 0) {
-    OCB_CUDA(cudaMalloc(&pl->partial, sizeof(double) * (size_t)nblocks * P->nslots));
-    OCB_CUDA(cudaMemset(pl->partial, 0, sizeof(double) * (size_t)nblocks * P->nslots));
-    P->partial = pl->partial;
+  if (nf > 0) {
+    SweepParams<T> Pf;
+    rc = ocb_build_sweep_params<T>(grid, in, fr, nf, zt, &Pf);
+    if (rc != OCB_OK) return rc;
+    Pf.nslots = nslots;
+    rc = ocb_fused_try_create(grid, in, fr, nf, Pf, &pl->fused);
+    if (rc != OCB_OK) return rc;
+  }
+  int fused_blocks = 0;
+  if (pl->fused) {
+    fused_blocks = ocb_fused_nblocks(pl->fused);
+    pl->variant = ng > 0 ? 2 : 1;
+    if (ng > 0) {                                   // the generic kernel takes only what is left
+      rc = ocb_build_sweep_params<T>(grid, in, gr, ng, zt, P);
+      if (rc != OCB_OK) return rc;
+      P->nslots = nslots;
+    }
+  }
+  pl->generic_blocks = 0;
+  if (pl->variant != 1) generic_geometry<T>(pl, P);
+  pl->nblocks = fused_blocks + pl->generic_blocks;
+  pl->fused_blocks = fused_blocks;
+  pl->nslots = nslots;
+  pl->n_launches = (pl->fused ? 1 : 0) + (pl->variant != 1 ? 1 : 0) + (nslots > 0 ? 1 : 0);
+  if (nslots > 0) {
+    // rows [0, fused_blocks) belong to the budget kernel, the rest to the generic kernel; a slot a kernel does not own
+    // stays zero in its rows (the buffer is cleared once, here)
+    OCB_CUDA(cudaMalloc(&pl->partial, sizeof(double) * (size_t)pl->nblocks * nslots));
+    OCB_CUDA(cudaMemset(pl->partial, 0, sizeof(double) * (size_t)pl->nblocks * nslots));
+    P->partial = pl->partial + (size_t)fused_blocks * nslots;
   }
   OCB_CUDA(cudaDeviceSynchronize());   // plan creation (not execution) may block: tables are ready afterwards
   return OCB_OK;
@@ -244,15 +274,15 @@ extern "C" int ocb_plan_create(const ocb_grid* grid, const ocb_sweep_inputs* inp
 extern "C" int ocb_plan_execute(ocb_plan* pl, double* integrals, void* stream) {
   OCB_REQUIRE(pl, "ocb_plan_execute: null plan");
   cudaStream_t st = (cudaStream_t)stream;
-  const int nslots = pl->dtype == OCB_F64 ? pl->p64.nslots : pl->p32.nslots;
+  const int nslots = pl->nslots;
   OCB_REQUIRE(nslots == 0 || integrals, "this plan integrates %d slot(s): `integrals` must be a device double[%d]", nslots, nslots);
-  if (pl->variant == 1) {
+  if (pl->fused) {
     int rc = ocb_fused_execute(pl->fused, pl->partial, st);
     if (rc != OCB_OK) return rc;
-  } else if (pl->dtype == OCB_F64) {
-    ocb_sweep_generic_kernel<double><<<pl->grid, pl->block, 0, st>>>(pl->p64);
-  } else {
-    ocb_sweep_generic_kernel<float><<<pl->grid, pl->block, 0, st>>>(pl->p32);
+  }
+  if (pl->variant != 1) {
+    if (pl->dtype == OCB_F64) ocb_sweep_generic_kernel<double><<<pl->grid, pl->block, 0, st>>>(pl->p64);
+    else ocb_sweep_generic_kernel<float><<<pl->grid, pl->block, 0, st>>>(pl->p32);
   }
   OCB_CUDA(cudaGetLastError());
   if (nslots > 0) {

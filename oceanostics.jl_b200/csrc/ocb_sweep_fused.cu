@@ -8,6 +8,8 @@
 //   EPS viscous_dissipation_rate_ccc           (src/KineticEnergyEquation.jl:427-453)
 //   CHI tracer_variance_dissipation_rate_ccc   (src/TracerVarianceEquation.jl:146-161)
 //   CDF c∇_dot_qᶜ                              (src/TracerVarianceEquation.jl:93-98)
+//   SP  shear_production_rate(_z)_ccc about horizontal-mean profiles U(z), V(z), W(z)
+//                                              (src/TurbulentKineticEnergyEquation.jl:224-240, 285-289)
 // as output fields and/or fused volume integrals, for Float64 array operands on a regularly spaced grid with
 // a constant-coefficient closure.  Everything else goes to the generic kernel (ocb_sweep.cu).
 //
@@ -32,7 +34,8 @@
 
 namespace {
 
-constexpr int FD_K = 0, FD_ADV = 1, FD_PR = 2, FD_WB = 3, FD_EPS = 4, FD_CHI = 5, FD_CDF = 6, FD_N = 7;
+constexpr int FD_K = 0, FD_ADV = 1, FD_PR = 2, FD_WB = 3, FD_EPS = 4, FD_CHI = 5, FD_CDF = 6, FD_SP = 7, FD_N = 8;
+constexpr int FD_BUDGET = 0x7f;   // the seven KE / tracer-variance budget terms
 constexpr int TW = 36;             // tile width: 32 lanes + west/east halo + 1 (the TMA box must start 16-byte aligned) -> 36
 
 struct FusedOut { double* out; int slot; };
@@ -48,6 +51,10 @@ struct FusedParams {
   long long os[3];                 // element strides shared by every output field
   double* partial;
   int nslots;
+  // horizontal-mean profiles U(z), V(z), W(z) (pre-offset: profile[k] with the 1-based k; nullptr = ZeroField) and
+  // whether the dissipation request sees the perturbation velocities u - U (lazy `u - U`, src/Oceanostics.jl:157-173)
+  const double *Uz, *Vz, *Wz;
+  int eps_pert;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -95,7 +102,8 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
                   const __grid_constant__ CUtensorMap mw, const __grid_constant__ CUtensorMap mb, const __grid_constant__ CUtensorMap mp) {
   using G = Geo<NW, RY>;
   constexpr bool H_K = MASK & (1 << FD_K), H_ADV = MASK & (1 << FD_ADV), H_PR = MASK & (1 << FD_PR), H_WB = MASK & (1 << FD_WB),
-                 H_EPS = MASK & (1 << FD_EPS), H_CHI = MASK & (1 << FD_CHI), H_CDF = MASK & (1 << FD_CDF);
+                 H_EPS = MASK & (1 << FD_EPS), H_CHI = MASK & (1 << FD_CHI), H_CDF = MASK & (1 << FD_CDF), H_SP = MASK & (1 << FD_SP);
+  constexpr bool PZ = H_SP;                            // kernels with the shear-production term carry the mean profiles
   constexpr bool NEED_B = H_WB || H_CHI || H_CDF, NEED_P = H_PR;
   constexpr int NF = 3 + (NEED_B ? 1 : 0) + (NEED_P ? 1 : 0);
   constexpr int F_B = 3, F_P = NEED_B ? 4 : 3;
@@ -161,11 +169,14 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
   double dU[RY], dV[RY], dW[RY];                        // in-plane parts of the flux divergences (previous plane)
   double Wwpp[RY], Apart[RY], Fvp[RY];                  // ADV pipeline (Apart, Fvp: OUT only)
   double Eacc[RY], Kacc[RY], PRacc[RY], CHacc[RY], CDacc[RY], hzp[RY];   // all but CDacc: OUT only
+  double ucp[RY], vcp[RY];                              // centred perturbation velocities of the previous plane (SP)
+  double aS_c[RY];
 #pragma unroll
   for (int r = 0; r < RY; ++r) {
     up[r] = vp[r] = wp[r] = bp[r] = pp[r] = 0.0;
     P13p[r] = P23p[r] = dU[r] = dV[r] = dW[r] = Wwpp[r] = Apart[r] = Fvp[r] = 0.0;
     Eacc[r] = Kacc[r] = PRacc[r] = CHacc[r] = CDacc[r] = hzp[r] = 0.0;
+    ucp[r] = vcp[r] = aS_c[r] = 0.0;
   }
   double acc[FD_N];
 #pragma unroll
@@ -226,6 +237,15 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
     // integral-only accumulation factors: terms of plane n, of plane n-1, of z face n (half-weights at chunk ends),
     // of z face n-1 -- all exactly 1 in the steady planes
     const double f0 = pv0, f1 = pv1, fz = 0.5 * (pv0 + pv1), fw = 0.5 * (pv1 + pv2);
+    // mean-flow profiles at this plane and the two below (uniform loads; zero without profiles)
+    double Un = 0.0, Un1 = 0.0, Un2 = 0.0, Vn = 0.0, Vn1 = 0.0, Vn2 = 0.0, Wn = 0.0, Wn1 = 0.0;
+    if (PZ) {
+      if (P.Uz) { Un = __ldg(P.Uz + n); Un1 = __ldg(P.Uz + n - 1); Un2 = __ldg(P.Uz + n - 2); }
+      if (P.Vz) { Vn = __ldg(P.Vz + n); Vn1 = __ldg(P.Vz + n - 1); Vn2 = __ldg(P.Vz + n - 2); }
+      if (P.Wz) { Wn = __ldg(P.Wz + n); Wn1 = __ldg(P.Wz + n - 1); }
+    }
+    const bool ep = PZ && P.eps_pert;                   // dissipation of u - U: only the z differences change
+    const double dUz = ep ? Un - Un1 : 0.0, dVz = ep ? Vn - Vn1 : 0.0, dWz = ep ? Wn - Wn1 : 0.0;
     auto accum = [&](double& a, double x, double y, double f) {     // a += f * x * y  (f folds away when STEADY)
       if (STEADY) a = fma(x, y, a); else a = fma(x * f, y, a);
     };
@@ -233,7 +253,7 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
     // ---- stage 1: quantities owned by this thread's cells at plane n --------------------------------------
     double uc[RY], vc[RY], wc[RY], bc[RY], pc[RY];
     double X12[RY], P12[RY], P12E[RY], e23[RY], P23[RY], Y13[RY], P13[RY], P13E[RY];
-    double Uu[RY], UuW[RY], Vv[RY], VvS[RY], inpl[RY], Kxy[RY], PRxy[RY], CHxy[RY], CDxy[RY];
+    double Uu[RY], UuW[RY], Vv[RY], VvS[RY], inpl[RY], Kxy[RY], PRxy[RY], CHxy[RY], CDxy[RY], ucn[RY], vcn[RY];
 #pragma unroll
     for (int r = 0; r < RY; ++r) {
       const int row = jr0 + 1 + r;                       // tile row of this cell
@@ -248,9 +268,9 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
       const double s12 = (uc[r] - us) * ey + (vc[r] - vw) * ex;
       P12[r] = (vw + vc[r]) * (us + uc[r]);
       // fcf edge (i, j, n) and cff edge
-      const double s13 = (uc[r] - up[r]) * ez + (wc[r] - ww) * ex;
+      const double s13 = (PZ ? (uc[r] - up[r]) - dUz : (uc[r] - up[r])) * ez + (wc[r] - ww) * ex;
       P13[r] = (ww + wc[r]) * (up[r] + uc[r]);
-      const double s23 = (vc[r] - vp[r]) * ez + (wc[r] - ws) * ey;
+      const double s23 = (PZ ? (vc[r] - vp[r]) - dVz : (vc[r] - vp[r])) * ez + (wc[r] - ws) * ey;
       P23[r] = (ws + wc[r]) * (vp[r] + vc[r]);
       if (OUT) {
         const double e12 = s12 * s12, e13 = s13 * s13;
@@ -274,6 +294,7 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
         else VvS[r] = Vv[r > 0 ? r - 1 : 0];
       }
       if (OUT) {
+        if (H_SP) { ucn[r] = 0.5 * (uc[r] + ue) - Un; vcn[r] = 0.5 * (vc[r] + vn) - Vn; }   // raw tiles are recycled after the barrier
         if (H_EPS) {
           const double ax = ue - uc[r], ay = vn - vc[r];
           inpl[r] = fma(ax * ax, dx2, (ay * ay) * dy2);
@@ -296,7 +317,16 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
         }
       } else {
         // integrals only: every face / cell term of plane n and of z face n goes into its class sum here
-        const double dwz = wc[r] - wp[r];
+        const double dwz = PZ ? (wc[r] - wp[r]) - dWz : (wc[r] - wp[r]);
+        if (H_SP) {
+          // shear production of the cell below (plane n-1) about the profiles: -(u'w' dU/dz + v'w' dV/dz + w'w' dW/dz)
+          const double wq1 = wc[r] - Wn, wq0 = wp[r] - Wn1;
+          const double wcen = 0.5 * (wq0 + wq1), ww2 = 0.5 * fma(wq0, wq0, wq1 * wq1);
+          const double spv = -(fma(ucp[r] * wcen, 0.5 * (Un - Un2) * rdz, fma(vcp[r] * wcen, 0.5 * (Vn - Vn2) * rdz, ww2 * ((Wn - Wn1) * rdz))));
+          accum(aS_c[r], spv, 1.0, f1);
+          ucp[r] = 0.5 * (uc[r] + ue) - Un;
+          vcp[r] = 0.5 * (vc[r] + vn) - Vn;
+        }
         if (H_EPS) {
           const double ax = ue - uc[r], ay = vn - vc[r];
           accum(aE_c[r], ax * dx2, ax, f0);
@@ -356,7 +386,7 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
       const bool last = (r == RY - 1);
       const double p12n = last ? P12N : P12[last ? r : r + 1];
       const double p23n = last ? P23N : P23[last ? r : r + 1];
-      const double dwz = wc[r] - wp[r];
+      const double dwz = PZ ? (wc[r] - wp[r]) - dWz : (wc[r] - wp[r]);
       if (OUT) {
         const double x12n = last ? X12N : X12[last ? r : r + 1];
         const double e23n = last ? e23N : e23[last ? r : r + 1];
@@ -401,6 +431,14 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
             CDacc[r] = fma(dbz, rdz2, CDxy[r]);
             emit(FD_CDF, raw, SC_CDF, w1, n - 1, r);
           }
+        }
+        if (H_SP) {
+          const double wq1 = wc[r] - Wn, wq0 = wp[r] - Wn1;
+          const double wcen = 0.5 * (wq0 + wq1), ww2 = 0.5 * fma(wq0, wq0, wq1 * wq1);
+          const double raw = -(fma(ucp[r] * wcen, 0.5 * (Un - Un2) * rdz, fma(vcp[r] * wcen, 0.5 * (Vn - Vn2) * rdz, ww2 * ((Wn - Wn1) * rdz))));
+          ucp[r] = ucn[r];
+          vcp[r] = vcn[r];
+          emit(FD_SP, raw, 1.0, w1, n - 1, r);
         }
         if (H_ADV) {
           // faces of plane n-1: F = velocity x flux divergence (the common 1/8 is the diagnostic's scale factor)
@@ -463,6 +501,7 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
       if (H_CHI) acc[FD_CHI] += rdx2 * (mx[r] * aC_x[r]) + rdy2 * (my[r] * aC_y[r]) + rdz2 * (w2 * aC_z[r]);
       if (H_CDF) acc[FD_CDF] += wrow[r] * aD_c[r];
       if (H_ADV) acc[FD_ADV] += mx[r] * aA_x[r] + my[r] * aA_y[r] + w2 * aA_z[r];
+      if (H_SP) acc[FD_SP] += wrow[r] * aS_c[r];
     }
   }
   // ---- volume integrals: warp shuffle, then one partial per block and slot -------------------------------------
@@ -478,7 +517,7 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
       if (tid == 0) {
         double s = 0.0;
         for (int w = 0; w < NW; ++w) s += red[w];
-        const double scale[FD_N] = {SC_K, SC_ADV, SC_PR, SC_WB, SC_EPS, SC_CHI, SC_CDF};
+        const double scale[FD_N] = {SC_K, SC_ADV, SC_PR, SC_WB, SC_EPS, SC_CHI, SC_CDF, 1.0};
         P.partial[(size_t)blockIdx.x * P.nslots + P.o[d].slot] = s * (P.V * scale[d]);
       }
     }
@@ -542,6 +581,32 @@ static int make_map(EncodeTiledFn enc, const ocb_field& f, int rows, CUtensorMap
   return OCB_OK;
 }
 
+static int fused_diag_index(int diag) {
+  switch (diag) {
+    case OCB_DIAG_KE: return FD_K;
+    case OCB_DIAG_ADV: return FD_ADV;
+    case OCB_DIAG_PR: return FD_PR;
+    case OCB_DIAG_WB: return FD_WB;
+    case OCB_DIAG_EPS: return FD_EPS;
+    case OCB_DIAG_CHI: return FD_CHI;
+    case OCB_DIAG_CDIFF: return FD_CDF;
+    case OCB_DIAG_SP: case OCB_DIAG_SPZ: return FD_SP;   // equal for z-profile means (the x and y parts vanish)
+    default: return -1;
+  }
+}
+bool ocb_fused_handles_diag(int diag) { return fused_diag_index(diag) >= 0; }
+
+// a mean-flow operand usable by the profile kernels: ZeroField (-> nullptr) or a field reduced over x and y whose z
+// axis is contiguous; *out is pre-offset so that out[k] is the value at the 1-based level k
+static bool profile_pointer(const ocb_field& f, int zloc, const double** out) {
+  *out = nullptr;
+  if (f.kind == OCB_FIELD_ZERO || (f.kind == OCB_FIELD_ARRAY && !f.data)) return true;
+  if (f.kind != OCB_FIELD_ARRAY) return false;
+  if (f.loc[0] != OCB_NOTHING || f.loc[1] != OCB_NOTHING || f.loc[2] != zloc || f.stride[2] != 1) return false;
+  *out = (const double*)f.data + (f.halo[2] - 1);
+  return true;
+}
+
 static bool tma_compatible(const ocb_field& f, const ocb_grid* g) {
   if (f.kind != OCB_FIELD_ARRAY || !f.data) return false;
   for (int d = 0; d < 3; ++d) if (f.loc[d] == OCB_NOTHING || f.halo[d] != g->H[d]) return false;
@@ -569,19 +634,23 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
   int mask = 0;
   int which_out[FD_N], which_slot[FD_N];     // a diagnostic may appear twice: once as a Field, once as an Integral
   for (int d = 0; d < FD_N; ++d) which_out[d] = which_slot[d] = -1;
+  bool eps_pert = false, any_pert = false;
+  int sp_diag = -1;
   for (int r = 0; r < n; ++r) {
-    int d;
-    switch (reqs[r].diag) {
-      case OCB_DIAG_KE: d = FD_K; break;
-      case OCB_DIAG_ADV: d = FD_ADV; break;
-      case OCB_DIAG_PR: d = FD_PR; break;
-      case OCB_DIAG_WB: d = FD_WB; break;
-      case OCB_DIAG_EPS: d = FD_EPS; break;
-      case OCB_DIAG_CHI: d = FD_CHI; break;
-      case OCB_DIAG_CDIFF: d = FD_CDF; break;
-      default: return OCB_OK;
+    const int d = fused_diag_index(reqs[r].diag);
+    if (d < 0) return OCB_OK;
+    const bool pert = reqs[r].flags & OCB_REQ_PERTURBATION;
+    if (d == FD_SP) {
+      if (!pert) return OCB_OK;                       // u' handed over as fields: generic kernel
+      if (sp_diag >= 0 && sp_diag != reqs[r].diag) return OCB_OK;
+      sp_diag = reqs[r].diag;
+    } else if (d == FD_EPS) {
+      if (which_out[d] >= 0 || which_slot[d] >= 0) { if (pert != eps_pert) return OCB_OK; }
+      eps_pert = pert;
+    } else if (pert) {
+      return OCB_OK;
     }
-    if (reqs[r].flags & OCB_REQ_PERTURBATION) return OCB_OK;
+    any_pert = any_pert || pert;
     const DReq& R = SP.req[r];
     if (R.lo[0] != 1 || R.hi[0] != grid->N[0]) return OCB_OK;                                               // full x extent
     if (r > 0 && (R.lo[2] != SP.req[0].lo[2] || R.hi[2] != SP.req[0].hi[2] || R.lo[1] != SP.req[0].lo[1] || R.hi[1] != SP.req[0].hi[1]))
@@ -589,6 +658,13 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
     if (R.out) { if (which_out[d] >= 0) return OCB_OK; which_out[d] = r; }
     if (R.slot >= 0) { if (which_slot[d] >= 0) return OCB_OK; which_slot[d] = r; }
     mask |= 1 << d;
+  }
+  const double *Uz = nullptr, *Vz = nullptr, *Wz = nullptr;
+  if (any_pert) {
+    // perturbations about horizontal-mean profiles only (Average(u, dims=(1,2)) reduced fields, or ZeroField)
+    if (grid->H[2] < 3) return OCB_OK;
+    if (!profile_pointer(in->U, OCB_CENTER, &Uz) || !profile_pointer(in->V, OCB_CENTER, &Vz) || !profile_pointer(in->W, OCB_FACE, &Wz)) return OCB_OK;
+    mask |= 1 << FD_SP;                               // the profile-carrying kernels are the ones with the SP term
   }
   if ((mask & (1 << FD_WB)) && (in->ghat[0] != 0.0 || in->ghat[1] != 0.0)) return OCB_OK;   // vertical gravity only
   bool any_out = false;
@@ -612,7 +688,7 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
   if (!fp) OCB_FAIL(OCB_ERR_ALLOC, "out of host memory");
   memset((void*)fp, 0, sizeof(*fp));
   // ---- variant: all seven terms, or the dissipation-only kernel ---------------------------------------------
-  constexpr int ALL = (1 << FD_N) - 1;
+  constexpr int ALL = FD_BUDGET;
   int rc;
   // Shapes measured on B200 at 1024^3 (profiles/r1_summary.md): integrals only -> 12 warps x 2 rows (one 384-thread
   // block per SM, 23/24 x 31/32 of the lanes produce output); with output fields -> 6 warps x 2 rows, two blocks per SM.
@@ -624,7 +700,11 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
   constexpr int VELP = VEL | (1 << FD_PR);                                          // + pressure
   constexpr int VELB = VEL | (1 << FD_WB) | (1 << FD_CHI) | (1 << FD_CDF);          // + tracer
 #define OCB_PICK(M) (any_out ? setup_variant<M, 6, 2, 3>(fp, true) : setup_variant<M, 12, 2, 3>(fp, false))
-  if (mask == (1 << FD_EPS)) rc = OCB_PICK((1 << FD_EPS));
+  constexpr int TKEM = (1 << FD_EPS) | (1 << FD_SP) | (1 << FD_PR) | (1 << FD_K);  // TKE budget about mean profiles
+  if (mask & (1 << FD_SP)) {
+    if (mask & ~TKEM) { delete fp; return OCB_OK; }
+    rc = OCB_PICK(TKEM);
+  } else if (mask == (1 << FD_EPS)) rc = OCB_PICK((1 << FD_EPS));
   else if ((mask & ~VEL) == 0) rc = OCB_PICK(VEL);
   else if ((mask & ~VELP) == 0) rc = OCB_PICK(VELP);
   else if ((mask & ~VELB) == 0) rc = OCB_PICK(VELB);
@@ -665,6 +745,7 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
   P.nu = in->closure.nu_const; P.kappa = in->closure.kappa_const; P.ghat_z = in->ghat[2];
   P.V = grid->d[0] * grid->d[1] * grid->d[2];
   P.nslots = SP.nslots;
+  P.Uz = Uz; P.Vz = Vz; P.Wz = Wz; P.eps_pert = eps_pert ? 1 : 0;
   for (int a = 0; a < 3; ++a) P.os[a] = os[a];
   for (int d = 0; d < FD_N; ++d) {
     P.o[d].out = nullptr; P.o[d].slot = -1;

@@ -11,6 +11,7 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
                          const SweepParams<double>& P, ocb_fused_plan** out);
 int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const ocb_request* reqs, int n,
                          const SweepParams<float>& P, ocb_fused_plan** out);
+bool ocb_fused_handles_diag(int diag);     // a diagnostic the budget kernel can evaluate (plans may be split on this)
 int ocb_fused_nblocks(const ocb_fused_plan* fp);
 int ocb_fused_execute(ocb_fused_plan* fp, double* partial, cudaStream_t st);
 void ocb_fused_destroy(ocb_fused_plan* fp);

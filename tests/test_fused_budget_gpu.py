@@ -136,3 +136,35 @@ def test_y_and_z_windows_tile_the_domain():
         for o, a, b in zip(ops, tot, ref):
             scale = float(ocb.Field(o).compute().interior.abs().sum()) / (64 * 40 * 30)
             assert abs(a - b) <= 1e-12 * scale, o.name
+
+
+def test_tke_budget_about_mean_profiles_split_plan():
+    """BASELINE.json configs[1] at test size: EPV + {ShearProductionRate, DissipationRate(u - U), PressureRedistribution}
+    with U, V, W = horizontal-mean profiles.  The ccc terms run on the pipelined kernel (perturbations about z profiles
+    evaluated on the fly), EPV on the generic kernel, one plan (variant 2); values and integrals match the oracle."""
+    from cases import build_cases, check_case
+    st = State(size=(64, 44, 26), device="cuda")
+    cases = {c[0]: c for c in build_cases(st, "scalar", mean="profile")}
+    names = ["ShearProductionRate", "DissipationRate_perturbation", "KineticEnergyPressureRedistribution", "ErtelPotentialVorticity"]
+    ops = [cases[nm][1] for nm in names]
+    grp = ocb.FusedDiagnostics(*([ocb.Field(o) for o in ops] + [ocb.Integral(o) for o in ops])).compute()
+    torch.cuda.synchronize()
+    assert grp.plan.variant == 2 and grp.plan.n_launches == 3
+    vals = [m.interior_ijk() for m in grp.members if isinstance(m, ocb.ComputedField)]
+    ints = grp.integrals()
+    for nm, got, integ in zip(names, vals, ints):
+        _, _, want, loc = cases[nm]
+        check_case(st, nm, got, want)
+        assert abs(integ - K.integral(want, st.og, loc)) <= 1e-12 * integral_scale(st.og, want, loc), nm
+    # integrals only, and the z shear production alone equals the total for profile means
+    grp2 = ocb.FusedDiagnostics(*[ocb.Integral(cases[nm][1]) for nm in names[:3]] + [ocb.Integral(cases["ZShearProductionRate"][1])])
+    # SP and SPZ in one plan: one SP request per pipelined sweep, so this plan runs on the generic kernel
+    grp2.compute()
+    i2 = grp2.integrals()
+    for a, b, nm in zip(i2[:3], ints[:3], names[:3]):
+        assert abs(a - b) <= 1e-12 * integral_scale(st.og, cases[nm][2], "ccc"), nm
+    assert abs(i2[3] - i2[0]) <= 1e-12 * integral_scale(st.og, cases["ShearProductionRate"][2], "ccc")
+    only = ocb.FusedDiagnostics(*[ocb.Integral(cases[nm][1]) for nm in names[:3]])
+    assert only.plan.variant == 1
+    for a, b, nm in zip(only.compute().integrals(), ints[:3], names[:3]):
+        assert abs(a - b) <= 1e-12 * integral_scale(st.og, cases[nm][2], "ccc"), nm
