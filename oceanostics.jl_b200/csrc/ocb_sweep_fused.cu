@@ -97,7 +97,7 @@ struct Geo {
 // (A warp-specialised variant -- producer warp + per-pair mbarriers instead of the block barrier -- was measured
 //  slower on B200, 55.9 vs 66.7 Gcells/s, and removed; see profiles/r1_summary.md.)
 template <int MASK, int NW, int RY, int NS, bool OUT>
-__global__ void __launch_bounds__(NW * 32, (RY == 1 ? (NW <= 8 ? 2 : 1) : (NW <= 6 ? 2 : 1)))
+__global__ void __launch_bounds__(NW * 32, (RY == 1 ? (NW <= 8 ? 2 : 1) : (RY == 2 && NW <= 6 ? 2 : 1)))
 ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__ CUtensorMap mu, const __grid_constant__ CUtensorMap mv,
                   const __grid_constant__ CUtensorMap mw, const __grid_constant__ CUtensorMap mb, const __grid_constant__ CUtensorMap mp) {
   using G = Geo<NW, RY>;
@@ -690,16 +690,17 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
   // ---- variant: all seven terms, or the dissipation-only kernel ---------------------------------------------
   constexpr int ALL = FD_BUDGET;
   int rc;
-  // Shapes measured on B200 at 1024^3 (profiles/r1_summary.md): integrals only -> 12 warps x 2 rows (one 384-thread
-  // block per SM, 23/24 x 31/32 of the lanes produce output); with output fields -> 6 warps x 2 rows, two blocks per SM.
+  // Shapes measured on B200 at 1024^3 (profiles/r1_summary.md).  One 256-thread block per SM with the full 255
+  // registers and no spills beats every higher-occupancy shape: integrals only -> 8 warps x 3 rows (99 Gcells/s vs 90
+  // for 12 x 2), with output fields -> 8 warps x 2 rows (44 vs 29 Gcells/s for 6 x 2).
   // OCB_FUSED_CONFIG="NW,RY,NS" overrides the shape of the all-terms kernel for tuning runs.
   const char* cfg = getenv("OCB_FUSED_CONFIG");
-  int nw = any_out ? 6 : 12, ry = 2, ns = 3;
+  int nw = 8, ry = any_out ? 2 : 3, ns = 3;
   if (cfg) sscanf(cfg, "%d,%d,%d", &nw, &ry, &ns);
   constexpr int VEL = (1 << FD_K) | (1 << FD_ADV) | (1 << FD_EPS);                 // velocity-only terms
   constexpr int VELP = VEL | (1 << FD_PR);                                          // + pressure
   constexpr int VELB = VEL | (1 << FD_WB) | (1 << FD_CHI) | (1 << FD_CDF);          // + tracer
-#define OCB_PICK(M) (any_out ? setup_variant<M, 6, 2, 3>(fp, true) : setup_variant<M, 12, 2, 3>(fp, false))
+#define OCB_PICK(M) (any_out ? setup_variant<M, 8, 2, 3>(fp, true) : setup_variant<M, 8, 3, 3>(fp, false))
   constexpr int TKEM = (1 << FD_EPS) | (1 << FD_SP) | (1 << FD_PR) | (1 << FD_K);  // TKE budget about mean profiles
   if (mask & (1 << FD_SP)) {
     if (mask & ~TKEM) { delete fp; return OCB_OK; }
@@ -712,6 +713,13 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
 #undef OCB_PICK
   else if (nw == 8 && ry == 1) rc = setup_variant<ALL, 8, 1, 3>(fp, any_out);
   else if (nw == 16 && ry == 1) rc = setup_variant<ALL, 16, 1, 3>(fp, any_out);
+  else if (nw == 20 && ry == 1) rc = setup_variant<ALL, 20, 1, 3>(fp, any_out);
+  else if (nw == 8 && ry == 3) rc = setup_variant<ALL, 8, 3, 3>(fp, any_out);
+  else if (nw == 6 && ry == 4) rc = setup_variant<ALL, 6, 4, 3>(fp, any_out);
+  else if (nw == 8 && ry == 4) rc = setup_variant<ALL, 8, 4, 3>(fp, any_out);
+  else if (nw == 10 && ry == 3) rc = setup_variant<ALL, 10, 3, 3>(fp, any_out);
+  else if (nw == 6 && ry == 3) rc = setup_variant<ALL, 6, 3, 3>(fp, any_out);
+  else if (nw == 4 && ry == 6) rc = setup_variant<ALL, 4, 6, 3>(fp, any_out);
   else if (nw == 12 && ry == 2 && ns == 4) rc = setup_variant<ALL, 12, 2, 4>(fp, any_out);
   else if (nw == 12 && ry == 2 && ns == 2) rc = setup_variant<ALL, 12, 2, 2>(fp, any_out);
   else if (nw == 10 && ry == 2) rc = setup_variant<ALL, 10, 2, 3>(fp, any_out);
