@@ -237,10 +237,10 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = plan.algorithmic_bytes / (sweep_ms * 1e-3) / 1e9
     # DRAM traffic of one launch of the sweep kernel, from the committed ncu capture of this exact workload
-    # (profiles/r1_traffic_bench1024_v7.csv: dram__bytes_read.sum + dram__bytes_write.sum); null for other shapes
+    # (profiles/r1_traffic_bench1024_v13.csv: dram__bytes_read.sum + dram__bytes_write.sum); null for other shapes
     traffic = None
     if size == (1024, 1024, 1024) and not args.fields and plan.variant == 1:
-        traffic = 45682806272 + 22822144
+        traffic = 46392537344 + 32416000
     integrals = grp.integrals() if overlapped is None else [float(x) for x in overlapped.total.cpu()]
 
     out = {
