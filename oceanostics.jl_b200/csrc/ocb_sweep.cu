@@ -218,7 +218,16 @@ static int finish_plan(ocb_plan* pl, const ocb_grid* grid, const ocb_sweep_input
   for (int r = 0; r < n; ++r) {
     if (ocb_fused_handles_diag(reqs[r].diag)) fr[nf++] = reqs[r]; else gr[ng++] = reqs[r];
   }
-  if (nf > 0) {
+  for (int attempt = 0; attempt < 2 && nf > 0 && !pl->fused; ++attempt) {
+    if (attempt == 1) {
+      // the budget kernel declined the set: retry without the potential-vorticity term (its envelope is narrower)
+      int kept = 0, moved = 0;
+      for (int r = 0; r < nf; ++r) {
+        if (fr[r].diag == OCB_DIAG_EPV) { gr[ng++] = fr[r]; ++moved; } else fr[kept++] = fr[r];
+      }
+      nf = kept;
+      if (!moved || nf == 0) break;
+    }
     SweepParams<T> Pf;
     rc = ocb_build_sweep_params<T>(grid, in, fr, nf, zt, &Pf);
     if (rc != OCB_OK) return rc;
@@ -226,6 +235,7 @@ static int finish_plan(ocb_plan* pl, const ocb_grid* grid, const ocb_sweep_input
     rc = ocb_fused_try_create(grid, in, fr, nf, Pf, &pl->fused);
     if (rc != OCB_OK) return rc;
   }
+  if (!pl->fused) ng = n;                            // everything on the generic kernel (P already holds all requests)
   int fused_blocks = 0;
   if (pl->fused) {
     fused_blocks = ocb_fused_nblocks(pl->fused);

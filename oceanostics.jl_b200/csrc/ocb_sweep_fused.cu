@@ -10,6 +10,7 @@
 //   CDF c∇_dot_qᶜ                              (src/TracerVarianceEquation.jl:93-98)
 //   SP  shear_production_rate(_z)_ccc about horizontal-mean profiles U(z), V(z), W(z)
 //                                              (src/TurbulentKineticEnergyEquation.jl:224-240, 285-289)
+//   EPV ertel_potential_vorticity_fff          (src/FlowDiagnostics.jl:216-233), periodic x and y
 // as output fields and/or fused volume integrals, for Float64 array operands on a regularly spaced grid with
 // a constant-coefficient closure.  Everything else goes to the generic kernel (ocb_sweep.cu).
 //
@@ -34,8 +35,9 @@
 
 namespace {
 
-constexpr int FD_K = 0, FD_ADV = 1, FD_PR = 2, FD_WB = 3, FD_EPS = 4, FD_CHI = 5, FD_CDF = 6, FD_SP = 7, FD_N = 8;
+constexpr int FD_K = 0, FD_ADV = 1, FD_PR = 2, FD_WB = 3, FD_EPS = 4, FD_CHI = 5, FD_CDF = 6, FD_SP = 7, FD_EPV = 8, FD_N = 9;
 constexpr int FD_BUDGET = 0x7f;   // the seven KE / tracer-variance budget terms
+constexpr int NXCH = 8;            // exchanged quantities per column: P12, P23 | X12, e23, Fv (OUT only) | XS23, o13, o12 (EPV)
 constexpr int TW = 36;             // tile width: 32 lanes + west/east halo + 1 (the TMA box must start 16-byte aligned) -> 36
 
 struct FusedOut { double* out; int slot; };
@@ -55,6 +57,8 @@ struct FusedParams {
   // whether the dissipation request sees the perturbation velocities u - U (lazy `u - U`, src/Oceanostics.jl:157-173)
   const double *Uz, *Vz, *Wz;
   int eps_pert;
+  double f[3];                     // Coriolis vector of the potential-vorticity term
+  int epv_top;                     // 1: the fff window also holds the top face Nz+1 (Bounded z)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -102,12 +106,17 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
                   const __grid_constant__ CUtensorMap mw, const __grid_constant__ CUtensorMap mb, const __grid_constant__ CUtensorMap mp) {
   using G = Geo<NW, RY>;
   constexpr bool H_K = MASK & (1 << FD_K), H_ADV = MASK & (1 << FD_ADV), H_PR = MASK & (1 << FD_PR), H_WB = MASK & (1 << FD_WB),
-                 H_EPS = MASK & (1 << FD_EPS), H_CHI = MASK & (1 << FD_CHI), H_CDF = MASK & (1 << FD_CDF), H_SP = MASK & (1 << FD_SP);
+                 H_EPS = MASK & (1 << FD_EPS), H_CHI = MASK & (1 << FD_CHI), H_CDF = MASK & (1 << FD_CDF), H_SP = MASK & (1 << FD_SP),
+                 H_EPV = MASK & (1 << FD_EPV);
   constexpr bool PZ = H_SP;                            // kernels with the shear-production term carry the mean profiles
-  constexpr bool NEED_B = H_WB || H_CHI || H_CDF, NEED_P = H_PR;
+  constexpr bool NEED_B = H_WB || H_CHI || H_CDF || H_EPV, NEED_P = H_PR;
   constexpr int NF = 3 + (NEED_B ? 1 : 0) + (NEED_P ? 1 : 0);
   constexpr int F_B = 3, F_P = NEED_B ? 4 : 3;
-  constexpr int NX = 5;                                // exchanged quantities per column: P12, P23, X12, e23, Fv (last 3: OUT only)
+  constexpr int NX = H_EPV ? NXCH : 5;
+  // The fff point a thread reports is the north-east-top corner (i+1, j+1, n) of its cell, so that all sharing runs
+  // the same way as for the cell terms (east by shuffle, north by register / exchange row); to reach the points
+  // i = 1 and j = jy_lo the tiling then starts one cell earlier, in the halo.
+  constexpr int SH = H_EPV ? 1 : 0;
 
   extern __shared__ __align__(1024) double smem_d[];
   double* tiles = smem_d;                                                      // [NS][NF][TILE]
@@ -121,7 +130,7 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
   const int tx = bid % P.tiles_x; bid /= P.tiles_x;
   const int ty = bid % P.tiles_y; bid /= P.tiles_y;
   const int chunk = bid;
-  const int i0 = 1 + 31 * tx, j0 = P.jy_lo + (G::BR - 1) * ty;
+  const int i0 = 1 - SH + 31 * tx, j0 = P.jy_lo - SH + (G::BR - 1) * ty;
   const int k0 = P.kz_lo + chunk * P.kchunk;
   const int k1 = min(k0 + P.kchunk - 1, P.kz_hi);
   const int n_first = k0 - 1, n_last = k1 + 2;
@@ -171,12 +180,14 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
   double Eacc[RY], Kacc[RY], PRacc[RY], CHacc[RY], CDacc[RY], hzp[RY];   // all but CDacc: OUT only
   double ucp[RY], vcp[RY];                              // centred perturbation velocities of the previous plane (SP)
   double aS_c[RY];
+  double Dxp[RY], Dyp[RY], Sbp[RY], NE12p[RY];          // EPV: b-box sums and the corner ffc vorticity of the previous plane
 #pragma unroll
   for (int r = 0; r < RY; ++r) {
     up[r] = vp[r] = wp[r] = bp[r] = pp[r] = 0.0;
     P13p[r] = P23p[r] = dU[r] = dV[r] = dW[r] = Wwpp[r] = Apart[r] = Fvp[r] = 0.0;
     Eacc[r] = Kacc[r] = PRacc[r] = CHacc[r] = CDacc[r] = hzp[r] = 0.0;
     ucp[r] = vcp[r] = aS_c[r] = 0.0;
+    Dxp[r] = Dyp[r] = Sbp[r] = NE12p[r] = 0.0;
   }
   double acc[FD_N];
 #pragma unroll
@@ -192,17 +203,19 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
   }
 
   const unsigned FULLMASK = 0xffffffffu;
-  const bool lane_out = lane < 31 && i <= P.Nx;
+  const bool lane_out = lane < 31 && i <= P.Nx && (SH == 0 || i >= 1);
   // per-row output weight (1 for cells this thread reports, 0 for overlap cells) and output offset
   double wrow[RY];
   long long orow[RY];
   // integral-only multiplicities: how many of this block's output cells a face / edge owned by (lane, row) touches
   double mx[RY], my[RY], mxy[RY];          // x faces & fcf edges, y faces & cff edges, ffc edges
+  double wE[RY];                           // EPV: weight of the corner point (i+1, j+1)
 #pragma unroll
   for (int r = 0; r < RY; ++r) {
     const int jr = jr0 + r, j = j0 + jr;
-    const bool row_out = jr < G::BR - 1 && j <= P.jy_hi;
-    const bool south_out = jr >= 1 && (jr - 1) < G::BR - 1 && (j - 1) <= P.jy_hi;          // the cell to the south, same lane
+    const bool row_out = jr < G::BR - 1 && j <= P.jy_hi && (SH == 0 || j >= P.jy_lo);
+    const bool south_out = jr >= 1 && (jr - 1) < G::BR - 1 && (j - 1) <= P.jy_hi && (SH == 0 || (j - 1) >= P.jy_lo);   // the cell to the south, same lane
+    wE[r] = (H_EPV && lane < 31 && i + 1 <= P.Nx && jr < G::BR - 1 && j + 1 <= P.jy_hi) ? 1.0 : 0.0;
     wrow[r] = (lane_out && row_out) ? 1.0 : 0.0;
     orow[r] = OUT ? (i * P.os[0] + j * P.os[1]) : 0;
     const double wsouth = (lane_out && south_out) ? 1.0 : 0.0;
@@ -254,6 +267,7 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
     double uc[RY], vc[RY], wc[RY], bc[RY], pc[RY];
     double X12[RY], P12[RY], P12E[RY], e23[RY], P23[RY], Y13[RY], P13[RY], P13E[RY];
     double Uu[RY], UuW[RY], Vv[RY], VvS[RY], inpl[RY], Kxy[RY], PRxy[RY], CHxy[RY], CDxy[RY], ucn[RY], vcn[RY];
+    double XS23[RY], O13[RY], O12[RY], Dx[RY], Dy[RY], Sb[RY];
 #pragma unroll
     for (int r = 0; r < RY; ++r) {
       const int row = jr0 + 1 + r;                       // tile row of this cell
@@ -272,6 +286,19 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
       P13[r] = (ww + wc[r]) * (up[r] + uc[r]);
       const double s23 = (PZ ? (vc[r] - vp[r]) - dVz : (vc[r] - vp[r])) * ez + (wc[r] - ws) * ey;
       P23[r] = (ws + wc[r]) * (vp[r] + vc[r]);
+      if (H_EPV) {
+        // edge vorticities owned by this cell (always of the full velocities) and the b sums of the 2 x 2 columns
+        // (i..i+1, j..j+1) of this plane
+        O12[r] = (vc[r] - vw) * rdx - (uc[r] - us) * rdy;
+        O13[r] = (uc[r] - up[r]) * rdz - (wc[r] - ww) * rdx;
+        const double o23 = (wc[r] - ws) * rdy - (vc[r] - vp[r]) * rdz;
+        XS23[r] = o23 + __shfl_down_sync(FULLMASK, o23, 1);
+        const double* rb = Tb + row * TW + lane + xoff;
+        const double b00 = rb[1], b10 = rb[2], b01 = rb[1 + TW], b11 = rb[2 + TW];
+        Dx[r] = (b10 - b00) + (b11 - b01);
+        Dy[r] = (b01 - b00) + (b11 - b10);
+        Sb[r] = (b00 + b10) + (b01 + b11);
+      }
       if (OUT) {
         const double e12 = s12 * s12, e13 = s13 * s13;
         e23[r] = s23 * s23;
@@ -370,15 +397,19 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
     double* myx = xch + ((par * NW + warp) * NX) * 32 + lane;
     if (H_ADV) { myx[0 * 32] = P12[0]; myx[1 * 32] = P23[0]; }
     if (OUT) { myx[2 * 32] = X12[0]; myx[3 * 32] = e23[0]; myx[4 * 32] = Fvp[0]; }
+    if (H_EPV) { myx[5 * 32] = XS23[0]; myx[6 * 32] = O13[0]; myx[7 * 32] = O12[0]; }
     __syncthreads();
     // every thread is done with raw stage s: refill it (plane n + NS)
     if (tid == 0 && n + NS <= n_last) issue(n + NS);   // same ring slot as plane n
-    double X12N = 0.0, P12N = 0.0, e23N = 0.0, P23N = 0.0, FvN = 0.0;
+    double X12N = 0.0, P12N = 0.0, e23N = 0.0, P23N = 0.0, FvN = 0.0, XS23N = 0.0, O13N = 0.0, O12N = 0.0;
     if (warp + 1 < NW) {
       const double* nx_ = xch + ((par * NW + warp + 1) * NX) * 32 + lane;
       if (H_ADV) { P12N = nx_[0 * 32]; P23N = nx_[1 * 32]; }
       if (OUT) { X12N = nx_[2 * 32]; e23N = nx_[3 * 32]; FvN = nx_[4 * 32]; }
+      if (H_EPV) { XS23N = nx_[5 * 32]; O13N = nx_[6 * 32]; O12N = nx_[7 * 32]; }
     }
+    // EPV is reported at z face n itself (no lag): faces k0..k1 of this chunk, plus the top face for the last chunk
+    const double pvE = (STEADY || !H_EPV) ? 1.0 : ((n >= k0 && n <= k1 + ((k1 == P.kz_hi) ? P.epv_top : 0)) ? 1.0 : 0.0);
 
     // ---- stage 2 / finalisation, row by row (north neighbour: own row r+1, or the exchanged row) -----------------
 #pragma unroll
@@ -387,6 +418,24 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
       const double p12n = last ? P12N : P12[last ? r : r + 1];
       const double p23n = last ? P23N : P23[last ? r : r + 1];
       const double dwz = PZ ? (wc[r] - wp[r]) - dWz : (wc[r] - wp[r]);
+      if (H_EPV) {
+        // q(i+1, j+1, n) = (f + ω)·∇b, every factor a 2- or 8-point mean onto the fff corner
+        const double xs23n = last ? XS23N : XS23[last ? r : r + 1];
+        const double o13n = last ? O13N : O13[last ? r : r + 1];
+        const double o12n = last ? O12N : O12[last ? r : r + 1];
+        const double ys13e = __shfl_down_sync(FULLMASK, O13[r] + o13n, 1);
+        const double ne12 = __shfl_down_sync(FULLMASK, o12n, 1);
+        const double qx = fma(0.5, xs23n, P.f[0]) * ((Dx[r] + Dxp[r]) * (0.25 * rdx));
+        const double qy = fma(0.5, ys13e, P.f[1]) * ((Dy[r] + Dyp[r]) * (0.25 * rdy));
+        const double qz = fma(0.5, ne12 + NE12p[r], P.f[2]) * ((Sb[r] - Sbp[r]) * (0.25 * rdz));
+        const double raw = (qx + qy) + qz;
+        Dxp[r] = Dx[r]; Dyp[r] = Dy[r]; Sbp[r] = Sb[r]; NE12p[r] = ne12;
+        const double w = pvE * wE[r];
+        acc[FD_EPV] = fma(raw, w, acc[FD_EPV]);
+        if (OUT) {
+          if (w != 0.0 && P.o[FD_EPV].out) P.o[FD_EPV].out[orow[r] + P.os[0] + P.os[1] + (long long)n * P.os[2]] = raw;
+        }
+      }
       if (OUT) {
         const double x12n = last ? X12N : X12[last ? r : r + 1];
         const double e23n = last ? e23N : e23[last ? r : r + 1];
@@ -517,7 +566,7 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
       if (tid == 0) {
         double s = 0.0;
         for (int w = 0; w < NW; ++w) s += red[w];
-        const double scale[FD_N] = {SC_K, SC_ADV, SC_PR, SC_WB, SC_EPS, SC_CHI, SC_CDF, 1.0};
+        const double scale[FD_N] = {SC_K, SC_ADV, SC_PR, SC_WB, SC_EPS, SC_CHI, SC_CDF, 1.0, 1.0};
         P.partial[(size_t)blockIdx.x * P.nslots + P.o[d].slot] = s * (P.V * scale[d]);
       }
     }
@@ -553,10 +602,10 @@ struct ocb_fused_plan {
 template <int MASK, int NW, int RY, int NS>
 static int setup_variant(ocb_fused_plan* fp, bool out) {
   using G = Geo<NW, RY>;
-  constexpr bool NEED_B = MASK & ((1 << FD_WB) | (1 << FD_CHI) | (1 << FD_CDF)), NEED_P = MASK & (1 << FD_PR);
+  constexpr bool NEED_B = MASK & ((1 << FD_WB) | (1 << FD_CHI) | (1 << FD_CDF) | (1 << FD_EPV)), NEED_P = MASK & (1 << FD_PR);
   constexpr int NF = 3 + (NEED_B ? 1 : 0) + (NEED_P ? 1 : 0);
   fp->nw = NW; fp->ry = RY; fp->ns = NS; fp->mask = MASK;
-  fp->smem = sizeof(double) * ((size_t)NS * NF * G::TILE + 2 * NW * 5 * 32 + NW) + sizeof(uint64_t) * NS;
+  fp->smem = sizeof(double) * ((size_t)NS * NF * G::TILE + 2 * NW * NXCH * 32 + NW) + sizeof(uint64_t) * NS;
   // ask for the largest shared-memory carveout so that occupancy is set by registers, not by the default split
   if (out) {
     cudaFuncSetAttribute(ocb_budget_kernel<MASK, NW, RY, NS, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
@@ -591,6 +640,7 @@ static int fused_diag_index(int diag) {
     case OCB_DIAG_CHI: return FD_CHI;
     case OCB_DIAG_CDIFF: return FD_CDF;
     case OCB_DIAG_SP: case OCB_DIAG_SPZ: return FD_SP;   // equal for z-profile means (the x and y parts vanish)
+    case OCB_DIAG_EPV: return FD_EPV;
     default: return -1;
   }
 }
@@ -635,12 +685,18 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
   int which_out[FD_N], which_slot[FD_N];     // a diagnostic may appear twice: once as a Field, once as an Integral
   for (int d = 0; d < FD_N; ++d) which_out[d] = which_slot[d] = -1;
   bool eps_pert = false, any_pert = false;
-  int sp_diag = -1;
+  int sp_diag = -1, cell_req = -1, epv_top = 0;
   for (int r = 0; r < n; ++r) {
     const int d = fused_diag_index(reqs[r].diag);
     if (d < 0) return OCB_OK;
     const bool pert = reqs[r].flags & OCB_REQ_PERTURBATION;
-    if (d == FD_SP) {
+    if (d == FD_EPV) {
+      // the corner-owned fff term: periodic x and y, H >= 3, and the whole z extent (Nz + 1 faces on a Bounded axis)
+      if (pert || grid->topo[0] != OCB_PERIODIC || grid->topo[1] != OCB_PERIODIC) return OCB_OK;
+      if (grid->H[0] < 3 || grid->H[1] < 3 || grid->H[2] < 3) return OCB_OK;
+      epv_top = grid->topo[2] == OCB_BOUNDED ? 1 : 0;
+      if (SP.req[r].lo[2] != 1 || SP.req[r].hi[2] != grid->N[2] + epv_top) return OCB_OK;
+    } else if (d == FD_SP) {
       if (!pert) return OCB_OK;                       // u' handed over as fields: generic kernel
       if (sp_diag >= 0 && sp_diag != reqs[r].diag) return OCB_OK;
       sp_diag = reqs[r].diag;
@@ -653,12 +709,16 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
     any_pert = any_pert || pert;
     const DReq& R = SP.req[r];
     if (R.lo[0] != 1 || R.hi[0] != grid->N[0]) return OCB_OK;                                               // full x extent
-    if (r > 0 && (R.lo[2] != SP.req[0].lo[2] || R.hi[2] != SP.req[0].hi[2] || R.lo[1] != SP.req[0].lo[1] || R.hi[1] != SP.req[0].hi[1]))
-      return OCB_OK;                                                                                          // one y and z window
+    if (R.lo[1] != SP.req[0].lo[1] || R.hi[1] != SP.req[0].hi[1]) return OCB_OK;                            // one y window
+    if (d != FD_EPV) {                                                                                        // one z window
+      if (cell_req < 0) cell_req = r;
+      else if (R.lo[2] != SP.req[cell_req].lo[2] || R.hi[2] != SP.req[cell_req].hi[2]) return OCB_OK;
+    }
     if (R.out) { if (which_out[d] >= 0) return OCB_OK; which_out[d] = r; }
     if (R.slot >= 0) { if (which_slot[d] >= 0) return OCB_OK; which_slot[d] = r; }
     mask |= 1 << d;
   }
+  if ((mask & (1 << FD_EPV)) && cell_req >= 0 && (SP.req[cell_req].lo[2] != 1 || SP.req[cell_req].hi[2] != grid->N[2])) return OCB_OK;
   const double *Uz = nullptr, *Vz = nullptr, *Wz = nullptr;
   if (any_pert) {
     // perturbations about horizontal-mean profiles only (Average(u, dims=(1,2)) reduced fields, or ZeroField)
@@ -676,7 +736,7 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
     any_out = true;
     for (int a = 0; a < 3; ++a) os[a] = R.os[a];
   }
-  const bool need_b = mask & ((1 << FD_WB) | (1 << FD_CHI) | (1 << FD_CDF)), need_p = mask & (1 << FD_PR);
+  const bool need_b = mask & ((1 << FD_WB) | (1 << FD_CHI) | (1 << FD_CDF) | (1 << FD_EPV)), need_p = mask & (1 << FD_PR);
   if (!tma_compatible(in->u, grid) || !tma_compatible(in->v, grid) || !tma_compatible(in->w, grid)) return OCB_OK;
   if (need_b && !tma_compatible(in->b, grid)) return OCB_OK;
   if (need_p && !tma_compatible(in->p, grid)) return OCB_OK;
@@ -702,7 +762,12 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
   constexpr int VELB = VEL | (1 << FD_WB) | (1 << FD_CHI) | (1 << FD_CDF);          // + tracer
 #define OCB_PICK(M) (any_out ? setup_variant<M, 8, 2, 3>(fp, true) : setup_variant<M, 8, 3, 3>(fp, false))
   constexpr int TKEM = (1 << FD_EPS) | (1 << FD_SP) | (1 << FD_PR) | (1 << FD_K);  // TKE budget about mean profiles
-  if (mask & (1 << FD_SP)) {
+  constexpr int EPVM = 1 << FD_EPV, TKEV = TKEM | EPVM;                            // + Ertel PV (BASELINE config 2)
+  if (mask & EPVM) {
+    if (mask == EPVM) rc = OCB_PICK(EPVM);
+    else if ((mask & ~TKEV) == 0) rc = OCB_PICK(TKEV);
+    else { delete fp; return OCB_OK; }
+  } else if (mask & (1 << FD_SP)) {
     if (mask & ~TKEM) { delete fp; return OCB_OK; }
     rc = OCB_PICK(TKEM);
   } else if (mask == (1 << FD_EPS)) rc = OCB_PICK((1 << FD_EPS));
@@ -711,35 +776,28 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
   else if ((mask & ~VELB) == 0) rc = OCB_PICK(VELB);
   else if (!cfg) rc = OCB_PICK(ALL);
 #undef OCB_PICK
-  else if (nw == 8 && ry == 1) rc = setup_variant<ALL, 8, 1, 3>(fp, any_out);
   else if (nw == 16 && ry == 1) rc = setup_variant<ALL, 16, 1, 3>(fp, any_out);
-  else if (nw == 20 && ry == 1) rc = setup_variant<ALL, 20, 1, 3>(fp, any_out);
   else if (nw == 8 && ry == 3) rc = setup_variant<ALL, 8, 3, 3>(fp, any_out);
-  else if (nw == 6 && ry == 4) rc = setup_variant<ALL, 6, 4, 3>(fp, any_out);
-  else if (nw == 8 && ry == 4) rc = setup_variant<ALL, 8, 4, 3>(fp, any_out);
-  else if (nw == 10 && ry == 3) rc = setup_variant<ALL, 10, 3, 3>(fp, any_out);
-  else if (nw == 6 && ry == 3) rc = setup_variant<ALL, 6, 3, 3>(fp, any_out);
-  else if (nw == 4 && ry == 6) rc = setup_variant<ALL, 4, 6, 3>(fp, any_out);
-  else if (nw == 12 && ry == 2 && ns == 4) rc = setup_variant<ALL, 12, 2, 4>(fp, any_out);
-  else if (nw == 12 && ry == 2 && ns == 2) rc = setup_variant<ALL, 12, 2, 2>(fp, any_out);
-  else if (nw == 10 && ry == 2) rc = setup_variant<ALL, 10, 2, 3>(fp, any_out);
-  else if (nw == 12 && ry == 1) rc = setup_variant<ALL, 12, 1, 3>(fp, any_out);
   else if (nw == 6 && ry == 2) rc = setup_variant<ALL, 6, 2, 3>(fp, any_out);
   else if (nw == 8 && ry == 2) rc = setup_variant<ALL, 8, 2, 3>(fp, any_out);
   else rc = setup_variant<ALL, 12, 2, 3>(fp, any_out);
   if (rc != OCB_OK) { delete fp; return rc; }
-  const bool vneed_b = fp->mask & ((1 << FD_WB) | (1 << FD_CHI) | (1 << FD_CDF)), vneed_p = fp->mask & (1 << FD_PR);
+  const bool vneed_b = fp->mask & ((1 << FD_WB) | (1 << FD_CHI) | (1 << FD_CDF) | (1 << FD_EPV)), vneed_p = fp->mask & (1 << FD_PR);
   if ((vneed_b && !tma_compatible(in->b, grid)) || (vneed_p && !tma_compatible(in->p, grid))) { delete fp; return OCB_OK; }
 
   FusedParams& P = fp->P;
   P.Nx = grid->N[0]; P.Ny = grid->N[1]; P.Nz = grid->N[2];
   P.hx = grid->H[0]; P.hy = grid->H[1]; P.hz = grid->H[2];
   const int BR = fp->nw * fp->ry;
-  P.tiles_x = (P.Nx + 30) / 31;
+  const int sh = (fp->mask & (1 << FD_EPV)) ? 1 : 0;          // corner-owned fff points: the tiling starts one cell early
+  P.tiles_x = (P.Nx + sh + 30) / 31;
   P.jy_lo = SP.req[0].lo[1]; P.jy_hi = SP.req[0].hi[1];
-  P.tiles_y = ((P.jy_hi - P.jy_lo + 1) + BR - 2) / (BR - 1);
+  P.tiles_y = ((P.jy_hi - P.jy_lo + 1) + sh + BR - 2) / (BR - 1);
   const int tiles = P.tiles_x * P.tiles_y;
-  P.kz_lo = SP.req[0].lo[2]; P.kz_hi = SP.req[0].hi[2];
+  P.kz_lo = cell_req >= 0 ? SP.req[cell_req].lo[2] : 1;
+  P.kz_hi = cell_req >= 0 ? SP.req[cell_req].hi[2] : grid->N[2];
+  P.epv_top = epv_top;
+  for (int a = 0; a < 3; ++a) P.f[a] = in->f[a];
   const int nz_win = P.kz_hi - P.kz_lo + 1;
   int nchunks = (ocb_sm_count() * 8 + tiles - 1) / tiles;
   if (nchunks < 1) nchunks = 1;

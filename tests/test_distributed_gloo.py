@@ -37,7 +37,7 @@ def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from oceanostics_b200.distributed import SlabHaloExchanger, slab_range, allreduce_integrals
-    Nx, Ny, Nz, H = 6, 8, 4, 3
+    Nx, Ny, Nz, H = 6, 4 * world, 4, 3
     lo, hi = slab_range(Ny, rank, world)
     g = ocb.RectilinearGrid((Nx, hi - lo + 1, Nz), extent=(1, 1, 1), device="cpu")
     f = ocb.Field(("c", "c", "c"), g)
@@ -62,7 +62,8 @@ def _worker(rank, world, port, out):
             ok &= bool(torch.equal(got_hi, (kk * 1000 + above * 10 + ii).double()))
     ints = torch.tensor([float(rank + 1), 10.0 * (rank + 1)], dtype=torch.float64)
     allreduce_integrals(ints)
-    ok &= ints.tolist() == [3.0, 30.0]
+    tot = world * (world + 1) / 2
+    ok &= ints.tolist() == [tot, 10.0 * tot]
     out[rank] = ok
     dist.destroy_process_group()
 
@@ -81,3 +82,12 @@ def test_ring_halo_exchange_and_allreduce_world2():
     out = mgr.dict()
     mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
     assert out[0] and out[1]
+
+
+@pytest.mark.timeout(180)
+def test_ring_halo_exchange_and_allreduce_world4():
+    """Four slabs: every rank has two DISTINCT neighbours (at world 2 both sides are the same peer)."""
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(4, _free_port(), out), nprocs=4, join=True)
+    assert all(out[r] for r in range(4))

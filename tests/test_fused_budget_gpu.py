@@ -138,10 +138,40 @@ def test_y_and_z_windows_tile_the_domain():
             assert abs(a - b) <= 1e-12 * scale, o.name
 
 
-def test_tke_budget_about_mean_profiles_split_plan():
+@pytest.mark.parametrize("size", [(64, 44, 26), (62, 23, 3), (34, 50, 9)], ids=str)
+def test_ertel_pv_on_the_pipelined_kernel(size):
+    """ErtelPotentialVorticity (fff, Nz + 1 faces) alone on the pipelined kernel: field, integral, and both."""
+    from cases import build_cases, check_case
+    st = State(size=size, device="cuda")
+    cases = {c[0]: c for c in build_cases(st, "scalar")}
+    _, op, want, loc = cases["ErtelPotentialVorticity"]
+    assert loc == "fff"
+    for members in ([ocb.Field(op)], [ocb.Integral(op)], [ocb.Field(op), ocb.Integral(op)]):
+        grp = ocb.FusedDiagnostics(*members).compute()
+        torch.cuda.synchronize()
+        assert grp.plan.variant == 1
+        for m in grp.members:
+            if isinstance(m, ocb.ComputedField):
+                check_case(st, "ErtelPotentialVorticity", m.interior_ijk(), want)
+        for integ in grp.integrals():
+            assert abs(integ - K.integral(want, st.og, loc)) <= 1e-12 * integral_scale(st.og, want, loc)
+    os.environ["OCB_DISABLE_FUSED"] = "1"
+    try:
+        gen = ocb.FusedDiagnostics(ocb.Field(op), ocb.Integral(op))
+    finally:
+        os.environ.pop("OCB_DISABLE_FUSED", None)
+    gen.compute()
+    assert gen.plan.variant == 0
+    fused = ocb.FusedDiagnostics(ocb.Field(op), ocb.Integral(op)).compute()
+    a, b = fused.members[0].interior_ijk(), gen.members[0].interior_ijk()
+    assert a.shape == b.shape == (size[0], size[1], size[2] + 1)
+    assert_close(a, b, 1e-11, "EPV fused vs generic")
+
+
+def test_tke_budget_about_mean_profiles_one_sweep():
     """BASELINE.json configs[1] at test size: EPV + {ShearProductionRate, DissipationRate(u - U), PressureRedistribution}
-    with U, V, W = horizontal-mean profiles.  The ccc terms run on the pipelined kernel (perturbations about z profiles
-    evaluated on the fly), EPV on the generic kernel, one plan (variant 2); values and integrals match the oracle."""
+    with U, V, W = horizontal-mean profiles, all in ONE launch of the pipelined kernel (perturbations about z profiles
+    evaluated on the fly, EPV at the cell corners); values and integrals match the oracle."""
     from cases import build_cases, check_case
     st = State(size=(64, 44, 26), device="cuda")
     cases = {c[0]: c for c in build_cases(st, "scalar", mean="profile")}
@@ -149,7 +179,7 @@ def test_tke_budget_about_mean_profiles_split_plan():
     ops = [cases[nm][1] for nm in names]
     grp = ocb.FusedDiagnostics(*([ocb.Field(o) for o in ops] + [ocb.Integral(o) for o in ops])).compute()
     torch.cuda.synchronize()
-    assert grp.plan.variant == 2 and grp.plan.n_launches == 3
+    assert grp.plan.variant == 1 and grp.plan.n_launches == 2      # the sweep + the deterministic finalize of the partials
     vals = [m.interior_ijk() for m in grp.members if isinstance(m, ocb.ComputedField)]
     ints = grp.integrals()
     for nm, got, integ in zip(names, vals, ints):
@@ -168,3 +198,21 @@ def test_tke_budget_about_mean_profiles_split_plan():
     assert only.plan.variant == 1
     for a, b, nm in zip(only.compute().integrals(), ints[:3], names[:3]):
         assert abs(a - b) <= 1e-12 * integral_scale(st.og, cases[nm][2], "ccc"), nm
+
+
+def test_split_plan_budget_kernel_plus_generic_kernel():
+    """Requests outside the pipelined kernel's set (Richardson number), or outside a variant's envelope (EPV next to the
+    advection term), go to the generic kernel of the same plan (variant 2) and fill their own integral slots."""
+    from cases import build_cases
+    st = State(size=(64, 44, 26), device="cuda")
+    ops, oc = budget(st)
+    cases = {c[0]: c for c in build_cases(st, "scalar")}
+    extra = ["ErtelPotentialVorticity", "StrainRateTensorModulus"]
+    grp = ocb.FusedDiagnostics(*[ocb.Integral(o) for o in ops + [cases[nm][1] for nm in extra]]).compute()
+    assert grp.plan.variant == 2 and grp.plan.n_launches == 3
+    ints = grp.integrals()
+    for o, w_, integ in zip(ops, oracle_budget(st, oc), ints[:len(ops)]):
+        assert abs(integ - K.integral(w_, st.og, "ccc")) <= 1e-12 * integral_scale(st.og, w_, "ccc"), o.name
+    for nm, integ in zip(extra, ints[len(ops):]):
+        _, _, want, loc = cases[nm]
+        assert abs(integ - K.integral(want, st.og, loc)) <= 1e-12 * integral_scale(st.og, want, loc), nm
