@@ -188,7 +188,9 @@ int ocb_plan_create(const ocb_grid* grid, const ocb_sweep_inputs* inputs,
 /* integrals: device pointer to double[n_slots] (overwritten; may be NULL when no request integrates) */
 int ocb_plan_execute(ocb_plan* plan, double* integrals, void* stream);
 int ocb_plan_destroy(ocb_plan* plan);
-/* number of kernels one execute launches, the kernel variant chosen, and the algorithmic bytes it moves */
+/* number of kernels one execute launches, the kernel variant chosen, and the algorithmic bytes it moves.
+ * variant: 0 generic kernel, 1 budget kernel, 2 budget + generic, 3 velocity-gradient kernel,
+ *          4 velocity-gradient + generic, 5 budget + velocity-gradient, 6 all three */
 int ocb_plan_info(const ocb_plan* plan, int32_t* n_launches, int32_t* variant, double* algorithmic_bytes);
 
 /* ---- halos: Oceananigans BoundaryConditions.fill_halo_regions! (default BCs) ------------------ */

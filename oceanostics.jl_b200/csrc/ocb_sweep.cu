@@ -7,6 +7,7 @@
 // (the explicit form of that recipe is src/SpatialFilters/SpatialFilters.jl:325-330).
 #include "ocb_sweep_plan.cuh"
 #include "ocb_sweep_fused.cuh"
+#include "ocb_sweep_strain.cuh"
 #include <new>
 
 // ---- z metric tables -------------------------------------------------------------------------------------
@@ -106,16 +107,18 @@ __global__ void __launch_bounds__(256, 3) ocb_sweep_generic_kernel(const __grid_
 // ---- plan ------------------------------------------------------------------------------------------------
 struct ocb_plan {
   int dtype;
-  int variant;            // 0 = generic kernel, 1 = register-pipelined budget kernel
+  int variant;            // which kernels one execute launches: 0 generic, 1 budget, 2 budget + generic,
+                          // 3 velocity-gradient, 4 velocity-gradient + generic, 5 budget + velocity-gradient, 6 all three
   SweepParams<double> p64;
   SweepParams<float> p32;
   void* ztab;             // library-owned z metric tables
   double* partial;        // per-block partial integrals
   dim3 grid, block;
-  int nblocks, fused_blocks, generic_blocks, nslots;
+  int nblocks, fused_blocks, strain_blocks, generic_blocks, nslots;
   int n_launches;
   double algorithmic_bytes;
   ocb_fused_plan* fused;
+  ocb_strain_plan* strain;
 };
 
 template <class T>
@@ -215,8 +218,18 @@ static int finish_plan(ocb_plan* pl, const ocb_grid* grid, const ocb_sweep_input
   // ---- fused subset ---------------------------------------------------------------------------------------
   ocb_request fr[OCB_MAX_REQ], gr[OCB_MAX_REQ];
   int nf = 0, ng = 0;
+  // the dissipation rate is known to both pipelined kernels: next to other budget terms it stays with the budget
+  // kernel, next to strain / rotation moduli only it goes with them (one sweep instead of two)
+  int budget_other = 0, strain_other = 0;
   for (int r = 0; r < n; ++r) {
-    if (ocb_fused_handles_diag(reqs[r].diag)) fr[nf++] = reqs[r]; else gr[ng++] = reqs[r];
+    if (reqs[r].diag == OCB_DIAG_EPS) continue;
+    if (ocb_fused_handles_diag(reqs[r].diag)) ++budget_other;
+    if (ocb_strain_handles_diag(reqs[r].diag)) ++strain_other;
+  }
+  const bool eps_with_moduli = budget_other == 0 && strain_other > 0;
+  for (int r = 0; r < n; ++r) {
+    if (ocb_fused_handles_diag(reqs[r].diag) && !(eps_with_moduli && reqs[r].diag == OCB_DIAG_EPS)) fr[nf++] = reqs[r];
+    else gr[ng++] = reqs[r];
   }
   for (int attempt = 0; attempt < 2 && nf > 0 && !pl->fused; ++attempt) {
     if (attempt == 1) {
@@ -235,29 +248,56 @@ static int finish_plan(ocb_plan* pl, const ocb_grid* grid, const ocb_sweep_input
     rc = ocb_fused_try_create(grid, in, fr, nf, Pf, &pl->fused);
     if (rc != OCB_OK) return rc;
   }
-  if (!pl->fused) ng = n;                            // everything on the generic kernel (P already holds all requests)
-  int fused_blocks = 0;
-  if (pl->fused) {
-    fused_blocks = ocb_fused_nblocks(pl->fused);
-    pl->variant = ng > 0 ? 2 : 1;
-    if (ng > 0) {                                   // the generic kernel takes only what is left
-      rc = ocb_build_sweep_params<T>(grid, in, gr, ng, zt, P);
+  if (!pl->fused) {                                  // nothing went to the budget kernel: start over with every request
+    ng = 0;
+    for (int r = 0; r < n; ++r) gr[ng++] = reqs[r];
+  }
+  // ---- velocity-gradient subset of what is left (closure-dependent dissipation, strain / rotation moduli) -------------
+  pl->strain = nullptr;
+  {
+    ocb_request sr[OCB_MAX_REQ], rest[OCB_MAX_REQ];
+    int ns = 0, nrest = 0;
+    for (int r = 0; r < ng; ++r) {
+      if (ocb_strain_handles_diag(gr[r].diag)) sr[ns++] = gr[r]; else rest[nrest++] = gr[r];
+    }
+    if (ns > 0) {
+      SweepParams<T> Ps;
+      rc = ocb_build_sweep_params<T>(grid, in, sr, ns, zt, &Ps);
       if (rc != OCB_OK) return rc;
-      P->nslots = nslots;
+      Ps.nslots = nslots;
+      rc = ocb_strain_try_create(grid, in, sr, ns, Ps, &pl->strain);
+      if (rc != OCB_OK) return rc;
+      if (pl->strain) {
+        ng = nrest;
+        for (int r = 0; r < nrest; ++r) gr[r] = rest[r];
+      }
     }
   }
+  const int fused_blocks = pl->fused ? ocb_fused_nblocks(pl->fused) : 0;
+  const int strain_blocks = pl->strain ? ocb_strain_nblocks(pl->strain) : 0;
+  if (pl->fused && pl->strain) pl->variant = ng > 0 ? 6 : 5;
+  else if (pl->strain) pl->variant = ng > 0 ? 4 : 3;
+  else if (pl->fused) pl->variant = ng > 0 ? 2 : 1;
+  else pl->variant = 0;
+  if ((pl->fused || pl->strain) && ng > 0) {        // the generic kernel takes only what is left
+    rc = ocb_build_sweep_params<T>(grid, in, gr, ng, zt, P);
+    if (rc != OCB_OK) return rc;
+    P->nslots = nslots;
+  }
   pl->generic_blocks = 0;
-  if (pl->variant != 1) generic_geometry<T>(pl, P);
-  pl->nblocks = fused_blocks + pl->generic_blocks;
+  if (ng > 0) generic_geometry<T>(pl, P);
+  pl->nblocks = fused_blocks + strain_blocks + pl->generic_blocks;
   pl->fused_blocks = fused_blocks;
+  pl->strain_blocks = strain_blocks;
   pl->nslots = nslots;
-  pl->n_launches = (pl->fused ? 1 : 0) + (pl->variant != 1 ? 1 : 0) + (nslots > 0 ? 1 : 0);
+  pl->n_launches = (pl->fused ? 1 : 0) + (pl->strain ? 1 : 0) + (ng > 0 ? 1 : 0) + (nslots > 0 ? 1 : 0);
   if (nslots > 0) {
-    // rows [0, fused_blocks) belong to the budget kernel, the rest to the generic kernel; a slot a kernel does not own
+    // rows [0, fused_blocks) belong to the budget kernel, the next strain_blocks to the velocity-gradient kernel, the
+    // rest to the generic kernel; a slot a kernel does not own
     // stays zero in its rows (the buffer is cleared once, here)
     OCB_CUDA(cudaMalloc(&pl->partial, sizeof(double) * (size_t)pl->nblocks * nslots));
     OCB_CUDA(cudaMemset(pl->partial, 0, sizeof(double) * (size_t)pl->nblocks * nslots));
-    P->partial = pl->partial + (size_t)fused_blocks * nslots;
+    P->partial = pl->partial + (size_t)(fused_blocks + strain_blocks) * nslots;
   }
   OCB_CUDA(cudaDeviceSynchronize());   // plan creation (not execution) may block: tables are ready afterwards
   return OCB_OK;
@@ -290,7 +330,11 @@ extern "C" int ocb_plan_execute(ocb_plan* pl, double* integrals, void* stream) {
     int rc = ocb_fused_execute(pl->fused, pl->partial, st);
     if (rc != OCB_OK) return rc;
   }
-  if (pl->variant != 1) {
+  if (pl->strain) {
+    int rc = ocb_strain_execute(pl->strain, pl->partial ? pl->partial + (size_t)pl->fused_blocks * nslots : nullptr, st);
+    if (rc != OCB_OK) return rc;
+  }
+  if (pl->generic_blocks > 0) {
     if (pl->dtype == OCB_F64) ocb_sweep_generic_kernel<double><<<pl->grid, pl->block, 0, st>>>(pl->p64);
     else ocb_sweep_generic_kernel<float><<<pl->grid, pl->block, 0, st>>>(pl->p32);
   }
@@ -305,6 +349,7 @@ extern "C" int ocb_plan_execute(ocb_plan* pl, double* integrals, void* stream) {
 extern "C" int ocb_plan_destroy(ocb_plan* pl) {
   if (!pl) return OCB_OK;
   if (pl->fused) ocb_fused_destroy(pl->fused);
+  if (pl->strain) ocb_strain_destroy(pl->strain);
   if (pl->ztab) cudaFree(pl->ztab);
   if (pl->partial) cudaFree(pl->partial);
   delete pl;

@@ -52,8 +52,9 @@ def test_fused_budget_matches_oracle(size):
     st = State(size=size, device="cuda")
     ops, oc = budget(st)
     grp, vals, ints = run(ops)
-    # TMA needs 16-byte row pitches: an even Nx takes the pipelined kernel, an odd one the generic kernel
-    assert grp.plan.variant == (1 if size[0] % 2 == 0 else 0)
+    # TMA needs 16-byte row pitches: an even Nx takes the budget kernel; with an odd one the dissipation rate goes to
+    # the velocity-gradient kernel (cp.async loads) and the rest to the generic kernel
+    assert grp.plan.variant == (1 if size[0] % 2 == 0 else 4)
     want = oracle_budget(st, oc)
     for op, g, w_, integ in zip(ops, vals, want, ints):
         assert_close(g, w_, 1e-12, op.name)
@@ -107,16 +108,16 @@ def test_fused_is_deterministic_and_identities_hold():
     assert float(f.interior.min()) >= 0.0
 
 
-def test_fused_falls_back_to_generic_outside_its_envelope():
+def test_budget_kernel_envelope():
     st = State(size=(40, 24, 18), stretched=True, device="cuda")
     ops, _ = budget(st)
     grp, _, _ = run(ops, fields=False)
-    assert grp.plan.variant == 0          # stretched z: generic kernel
+    assert grp.plan.variant == 4          # stretched z: dissipation on the velocity-gradient kernel, the rest generic
     st = State(size=(40, 24, 18), device="cuda")
     oc, pc = st.closures()["smagorinsky_like"]
     m = st.model(closure=pc)
     grp = ocb.FusedDiagnostics(ocb.Integral(ocb.KineticEnergyEquation.DissipationRate(m)))
-    assert grp.plan.variant == 0          # eddy-viscosity field: generic kernel
+    assert grp.plan.variant == 3          # eddy-viscosity field: velocity-gradient kernel
 
 
 def test_y_and_z_windows_tile_the_domain():
@@ -207,7 +208,7 @@ def test_split_plan_budget_kernel_plus_generic_kernel():
     st = State(size=(64, 44, 26), device="cuda")
     ops, oc = budget(st)
     cases = {c[0]: c for c in build_cases(st, "scalar")}
-    extra = ["ErtelPotentialVorticity", "StrainRateTensorModulus"]
+    extra = ["ErtelPotentialVorticity", "RossbyNumber"]
     grp = ocb.FusedDiagnostics(*[ocb.Integral(o) for o in ops + [cases[nm][1] for nm in extra]]).compute()
     assert grp.plan.variant == 2 and grp.plan.n_launches == 3
     ints = grp.integrals()
