@@ -22,20 +22,22 @@ namespace {
 
 constexpr int SD_EPS = 0, SD_EISO = 1, SD_SMOD = 2, SD_OMOD = 3, SD_Q = 4, SD_N = 5;
 constexpr int FAM_E = 1, FAM_P = 2, FAM_M = 4;     // edge families: ν-weighted strain², (a+b)², (a-b)²
-constexpr int STW = 36, STC = 34;                  // tile row pitch / columns used (i0-1 .. i0+32)
+constexpr int STW = 36;                            // tile row pitch: i0-1 .. i0+32, plus one column either side for the pair alignment
+constexpr int ZC = 32;                             // planes per staged window of z metrics
+constexpr int STPAD = 4;                           // spare elements after each tile: the target of a thread's surplus copies
 constexpr int NFMAX = 3 + OCB_MAX_CLOSURE_FIELDS;
 
-template <class T>
-struct StrainFld { const T* p; long long sy, sz; };
 
 template <class T>
 struct StrainParams {
   int Nx, Ny, Nz, hx, hy, hz;
   int tiles_x, tiles_y, nchunks, kchunk, kz_lo, kz_hi, jy_lo, jy_hi;
   int cx, cy, cz;                        // last parent index every operand has along x / y / z (loads are clamped to it)
+  int sy;                                // parent row pitch (elements), the same for every operand
+  long long sz;                          // parent plane pitch
   T rdx, rdy, nu_c;
   const T *dzc, *dzf, *rdzc, *rdzf;      // pre-offset z tables: table[k] with the 1-based k
-  StrainFld<T> f[NFMAX];                 // u, v, w, ν_e fields (parent base pointers)
+  const T* f[NFMAX];                     // u, v, w, ν_e fields (parent base pointers)
   T* out[SD_N];
   int slot[SD_N];
   long long os[3];
@@ -46,8 +48,8 @@ struct StrainParams {
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 template <int B>
-__device__ __forceinline__ void cp_async(void* dst, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(s_u32(dst)), "l"(src), "n"(B) : "memory");
+__device__ __forceinline__ void cp_async(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst), "l"(src), "n"(B) : "memory");
 }
 __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -56,20 +58,21 @@ __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0
 __device__ __forceinline__ float t_sqrt(float x) { return sqrtf(x); }
 __device__ __forceinline__ double t_sqrt(double x) { return sqrt(x); }
 
-template <class T, int FAM, int NNU, int NW, int RY, int NS>
-__global__ void __launch_bounds__(NW * 32, (sizeof(T) == 4 ? 2 : 1))
+template <class T, int FAM, int NNU, int NW, int RY, int NS, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB)
 ocb_strain_kernel(const __grid_constant__ StrainParams<T> P) {
   constexpr bool F_E = FAM & FAM_E, F_P = FAM & FAM_P, F_M = FAM & FAM_M;
   constexpr int NFAM = (F_E ? 1 : 0) + (F_P ? 1 : 0) + (F_M ? 1 : 0);
   constexpr int IE = 0, IP = F_E ? 1 : 0, IM = IP + (F_P ? 1 : 0);       // family index -> slot in the small arrays
-  constexpr int NF = 3 + NNU, BR = NW * RY, TR = BR + 2, TILE = STW * TR, NT = NW * 32;
+  constexpr int NF = 3 + NNU, BR = NW * RY, TR = BR + 2, TILE = STW * TR + STPAD, NT = NW * 32;
   constexpr int NXS = 2 * NFAM;                                          // exchanged per column: X12 and q23 of each family
-  constexpr int NLD = (STC * TR + NT - 1) / NT;                          // copies per thread, field and plane
+  constexpr int NLD = ((STW / 2) * TR + NT - 1) / NT;                    // copies (element pairs) per thread, field and plane
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* tiles = reinterpret_cast<T*>(smem_raw);                             // [NS][NF][TILE]
   T* xch = tiles + NS * NF * TILE;                                       // [2][NW][NXS][32]
   double* red = reinterpret_cast<double*>(xch + 2 * NW * NXS * 32);      // [NW]
+  T* zts = reinterpret_cast<T*>(red + NW);                               // [4][ZC]
 
   const int lane = threadIdx.x, warp = threadIdx.y;
   const int tid = warp * 32 + lane;
@@ -84,27 +87,35 @@ ocb_strain_kernel(const __grid_constant__ StrainParams<T> P) {
   const int i = i0 + lane;
   const int jr0 = warp * RY;
 
-  // ---- loader: this thread's share of the 34 x TR tile (same positions for every field and plane) --------------
-  const int px = i0 - 1 + P.hx - 1, py = j0 - 1 + P.hy - 1;
-  int gxy_x[NLD], gxy_y[NLD], soff[NLD];
+  // ---- loader: this thread's share of the tile (same positions for every field and plane) -------------------------
+  // Rows are copied as aligned element pairs (8-byte cp.async in Float32, 16-byte in Float64): the tile starts at the
+  // even parent column at or before i0-1, and xoff = 0/1 shifts every shared-memory column index.
+  const int px_raw = i0 - 1 + P.hx - 1, py = j0 - 1 + P.hy - 1;
+  const int xoff = px_raw & 1, px = px_raw - xoff;
+  int goff[NLD];
+  uint32_t sb[NLD];
+  const uint32_t tiles_u32 = s_u32(tiles);
 #pragma unroll
   for (int t = 0; t < NLD; ++t) {
     const int e = tid + t * NT;
-    const int row = e / STC, col = e - row * STC;
-    gxy_x[t] = min(px + col, P.cx);
-    gxy_y[t] = min(py + row, P.cy);
-    soff[t] = (e < STC * TR) ? row * STW + col : -1;
+    const int row = e / (STW / 2), col = 2 * (e - row * (STW / 2));
+    const bool ok = e < (STW / 2) * TR;
+    const int gx = min(px + col, P.cx - 1), gy = min(py + row, P.cy);
+    goff[t] = ok ? gx + gy * P.sy : 0;
+    // a thread with no pair left in the last round copies something valid into the tile's spare slot instead:
+    // every copy is then unconditional (no divergent branch around LDGSTS)
+    sb[t] = (uint32_t)((ok ? row * STW + col : STW * TR) * sizeof(T));
   }
   auto issue = [&](int n) {
     const int s = (n - n_first) % NS;
     const long long pz = min(n + P.hz - 1, P.cz);
 #pragma unroll
     for (int f = 0; f < NF; ++f) {
-      T* dst = tiles + (s * NF + f) * TILE;
-      const T* src = P.f[f].p + pz * P.f[f].sz;
+      const uint32_t dst = tiles_u32 + (uint32_t)((s * NF + f) * TILE * sizeof(T));
+      const T* src = P.f[f] + pz * P.sz;
+      asm volatile("" : "+l"(src));                      // keep the plane base in a register: one address add per copy
 #pragma unroll
-      for (int t = 0; t < NLD; ++t)
-        if (soff[t] >= 0) cp_async<sizeof(T)>(dst + soff[t], src + gxy_x[t] + gxy_y[t] * P.f[f].sy);
+      for (int t = 0; t < NLD; ++t) cp_async<2 * sizeof(T)>(dst + sb[t], src + goff[t]);
     }
   };
   for (int n = n_first; n < n_first + NS; ++n) {      // one group per plane, empty past the end so the counting stays uniform
@@ -137,30 +148,47 @@ ocb_strain_kernel(const __grid_constant__ StrainParams<T> P) {
     orow[r] = i * P.os[0] + j * P.os[1];
   }
 
+  const bool do_eiso = P.out[SD_EISO] || P.slot[SD_EISO] >= 0, do_smod = P.out[SD_SMOD] || P.slot[SD_SMOD] >= 0,
+             do_omod = P.out[SD_OMOD] || P.slot[SD_OMOD] >= 0, do_q = P.out[SD_Q] || P.slot[SD_Q] >= 0;
   int s = 0, par = 0;
+  // z metrics: a window of ZC planes is staged in shared memory by the first warp (a global load consumed right
+  // after the barrier would stall every warp of the block at once, once per plane)
   for (int n = n_first; n <= n_last; ++n) {
+    const int zi = (n - n_first) % ZC;
+    if (zi == 0 && tid < ZC) {
+      const int q = min(n + tid, P.Nz + P.hz), km = max(q - 1, 1 - P.hz);       // the tables hold k = 1 - Hz .. Nz + Hz + 1
+      zts[0 * ZC + tid] = __ldg(P.rdzf + q); zts[1 * ZC + tid] = __ldg(P.dzf + q);
+      zts[2 * ZC + tid] = __ldg(P.rdzc + km); zts[3 * ZC + tid] = __ldg(P.dzc + km);
+    }
     cp_wait<NS - 1>();                                  // this thread's copies of plane n have landed ...
-    __syncthreads();                                    // ... and everybody else's
+    __syncthreads();                                    // ... and everybody else's (and the z-metric window)
     const T* Tt = tiles + s * (NF * TILE);
     const T* Tu = Tt, *Tv = Tt + TILE, *Tw = Tt + 2 * TILE;
     if (++s == NS) s = 0;
-    const T rzf = __ldg(P.rdzf + n), dzf_n = __ldg(P.dzf + n);
-    const int km = max(n - 1, 1 - P.hz);                 // the tables start at k = 1 - Hz (plane n_first carries no output)
-    const T rzc1 = __ldg(P.rdzc + km), dzc1 = __ldg(P.dzc + km);
+    const T rzf = zts[0 * ZC + zi], dzf_n = zts[1 * ZC + zi], rzc1 = zts[2 * ZC + zi], dzc1 = zts[3 * ZC + zi];
     const bool pv1 = (n - 1) >= k0 && (n - 1) <= k1;
 
     // ---- stage 1: edges owned by this thread's cells at plane n / z face n -------------------------------------------
     T uc[RY], vc[RY], wc[RY], dg[RY], nucc[RY], XN[RY], YN[RY];
     T X12[RY][NFAM > 0 ? NFAM : 1], Y13[RY][NFAM > 0 ? NFAM : 1], q23[RY][NFAM > 0 ? NFAM : 1];
+    T nuc[RY], nuw[RY];                                  // eddy viscosity (summed over the closure's fields) at the cell and to its west
+    // the thread's own column first: south / north neighbours inside the thread are then registers, not shared-memory reads
+#pragma unroll
+    for (int r = 0; r < RY; ++r) {
+      const int o = (jr0 + 1 + r) * STW + lane + xoff + 1;
+      uc[r] = Tu[o]; vc[r] = Tv[o]; wc[r] = Tw[o];
+      nuc[r] = nuw[r] = T(0);
+#pragma unroll
+      for (int q = 0; q < NNU; ++q) { nuc[r] += Tt[(3 + q) * TILE + o]; nuw[r] += Tt[(3 + q) * TILE + o - 1]; }
+    }
 #pragma unroll
     for (int r = 0; r < RY; ++r) {
       const int row = jr0 + 1 + r;
-      const T* ru = Tu + row * STW + lane;               // ru[0] west, ru[1] centre, ru[2] east
-      const T* rv = Tv + row * STW + lane;
-      const T* rw = Tw + row * STW + lane;
-      uc[r] = ru[1]; vc[r] = rv[1]; wc[r] = rw[1];
+      const T* ru = Tu + row * STW + lane + xoff;        // ru[0] west, ru[1] centre, ru[2] east
+      const T* rv = Tv + row * STW + lane + xoff;
+      const T* rw = Tw + row * STW + lane + xoff;
       const T ue = ru[2], us = (r == 0) ? ru[1 - STW] : uc[r > 0 ? r - 1 : 0];
-      const T vw = rv[0], vn = rv[1 + STW];
+      const T vw = rv[0], vn = (r == RY - 1) ? rv[1 + STW] : vc[r < RY - 1 ? r + 1 : r];
       const T ww = rw[0], ws = (r == 0) ? rw[1 - STW] : wc[r > 0 ? r - 1 : 0];
       const T a = (uc[r] - us) * rdy, b = (vc[r] - vw) * rdx;               // ∂y u, ∂x v   at ffc (i, j, n)
       const T c = (uc[r] - up[r]) * rzf, d = (wc[r] - ww) * rdx;            // ∂z u, ∂x w   at fcf (i, j, face n)
@@ -170,12 +198,15 @@ ocb_strain_kernel(const __grid_constant__ StrainParams<T> P) {
       nucc[r] = nu_c; XN[r] = YN[r] = T(0);
       T nffc = nu_c, nfcf = nu_c, ncff = nu_c;
       if (NNU > 0) {
-        T nc = T(0), nw_ = T(0), ns = T(0), nsw = T(0);
+        const T nc = nuc[r], nw_ = nuw[r];
+        T ns = T(0), nsw = T(0);
+        if (r == 0) {
 #pragma unroll
-        for (int q = 0; q < NNU; ++q) {
-          const T* rn = Tt + (3 + q) * TILE + row * STW + lane;
-          nc += rn[1]; nw_ += rn[0]; ns += rn[1 - STW]; nsw += rn[-STW];
-        }
+          for (int q = 0; q < NNU; ++q) {
+            const T* rn = Tt + (3 + q) * TILE + row * STW + lane + xoff;
+            ns += rn[1 - STW]; nsw += rn[-STW];
+          }
+        } else { ns = nuc[r > 0 ? r - 1 : 0]; nsw = nuw[r > 0 ? r - 1 : 0]; }
         nucc[r] = nu_c + nc;
         XN[r] = nw_ + nc; YN[r] = ns + nc;
         nffc = nu_c + Q4 * ((nsw + ns) + XN[r]);
@@ -232,46 +263,25 @@ ocb_strain_kernel(const __grid_constant__ StrainParams<T> P) {
       T S2 = T(0), O2 = T(0);
       if (F_P) S2 = diag + H2 * (Q4 * accp[r][IP] + Q4 * tot[IP]);
       if (F_M) O2 = H2 * (Q4 * accp[r][IM] + Q4 * tot[IM]);
-      if (F_E) {
-        // 2 ν_ccc Σ_aa² + 4 [mean_xy e12 + (mean_xz e13 + mean_yz e23) / Δz_c]   (the Δz_f weights are inside e13, e23)
-        const T val = T(2) * nucp[r] * diag + (accp[r][IE] + rzc1 * tot[IE]);
-        if (w1) {
-          acc[SD_EPS] = fma((double)val, vol, acc[SD_EPS]);
-          if (P.out[SD_EPS]) P.out[SD_EPS][o] = val;
-        }
-      }
-      if (F_P) {
-        if (P.out[SD_EISO] || P.slot[SD_EISO] >= 0) {
-          const T val = T(2) * nucp[r] * S2;
-          if (w1) {
-            acc[SD_EISO] = fma((double)val, vol, acc[SD_EISO]);
-            if (P.out[SD_EISO]) P.out[SD_EISO][o] = val;
-          }
-        }
-        if (P.out[SD_SMOD] || P.slot[SD_SMOD] >= 0) {
-          const T val = t_sqrt(S2);
-          if (w1) {
-            acc[SD_SMOD] = fma((double)val, vol, acc[SD_SMOD]);
-            if (P.out[SD_SMOD]) P.out[SD_SMOD][o] = val;
-          }
-        }
-      }
-      if (F_M) {
-        if (P.out[SD_OMOD] || P.slot[SD_OMOD] >= 0) {
-          const T val = t_sqrt(O2);
-          if (w1) {
-            acc[SD_OMOD] = fma((double)val, vol, acc[SD_OMOD]);
-            if (P.out[SD_OMOD]) P.out[SD_OMOD][o] = val;
-          }
-        }
-        if (F_P && (P.out[SD_Q] || P.slot[SD_Q] >= 0)) {
-          const T sr = t_sqrt(S2), orr = t_sqrt(O2);             // through the roots, as the reference does
-          const T val = H2 * (orr * orr - sr * sr);
-          if (w1) {
-            acc[SD_Q] = fma((double)val, vol, acc[SD_Q]);
-            if (P.out[SD_Q]) P.out[SD_Q][o] = val;
-          }
-        }
+      // 2 ν_ccc Σ_aa² + 4 [mean_xy e12 + (mean_xz e13 + mean_yz e23) / Δz_c]   (the Δz_f weights are inside e13, e23)
+      T vE = T(0), vI = T(0), vS = T(0), vO = T(0), vQ = T(0);
+      if (F_E) vE = T(2) * nucp[r] * diag + (accp[r][IE] + rzc1 * tot[IE]);
+      if (F_P && do_eiso) vI = T(2) * nucp[r] * S2;
+      if (F_P && (do_smod || do_q)) vS = t_sqrt(S2);
+      if (F_M && (do_omod || do_q)) vO = t_sqrt(O2);
+      if (F_P && F_M && do_q) vQ = H2 * (vO * vO - vS * vS);              // through the roots, as the reference does
+      // integrals: overlap cells and planes outside the chunk enter as exact zeros (a select, not a multiply by 0)
+      if (F_E) acc[SD_EPS] = fma((double)(w1 ? vE : T(0)), vol, acc[SD_EPS]);
+      if (F_P && do_eiso) acc[SD_EISO] = fma((double)(w1 ? vI : T(0)), vol, acc[SD_EISO]);
+      if (F_P && do_smod) acc[SD_SMOD] = fma((double)(w1 ? vS : T(0)), vol, acc[SD_SMOD]);
+      if (F_M && do_omod) acc[SD_OMOD] = fma((double)(w1 ? vO : T(0)), vol, acc[SD_OMOD]);
+      if (F_P && F_M && do_q) acc[SD_Q] = fma((double)(w1 ? vQ : T(0)), vol, acc[SD_Q]);
+      if (w1) {
+        if (F_E && P.out[SD_EPS]) P.out[SD_EPS][o] = vE;
+        if (F_P && P.out[SD_EISO]) P.out[SD_EISO][o] = vI;
+        if (F_P && P.out[SD_SMOD]) P.out[SD_SMOD][o] = vS;
+        if (F_M && P.out[SD_OMOD]) P.out[SD_OMOD][o] = vO;
+        if (F_P && F_M && P.out[SD_Q]) P.out[SD_Q][o] = vQ;
       }
 #pragma unroll
       for (int m = 0; m < NFAM; ++m) { accp[r][m] = inpl[m]; facep[r][m] = face[m]; }
@@ -318,7 +328,7 @@ struct ocb_strain_plan {
   int dtype;
   StrainParams<double> Pd;
   StrainParams<float> Pf;
-  int nw, nblocks;
+  int nw, ry, nblocks;
   size_t smem;
   void (*kd)(StrainParams<double>);
   void (*kf)(StrainParams<float>);
@@ -327,8 +337,8 @@ struct ocb_strain_plan {
 bool ocb_strain_handles_diag(int diag) { return strain_diag_index(diag) >= 0; }
 
 template <class T> struct StrainShape;
-template <> struct StrainShape<float> { static constexpr int NW = 8, RY = 3, NS = 3; };
-template <> struct StrainShape<double> { static constexpr int NW = 8, RY = 2, NS = 3; };
+template <> struct StrainShape<float> { static constexpr int NW = 4, RY = 3, NS = 3, MINB = 4; };
+template <> struct StrainShape<double> { static constexpr int NW = 4, RY = 3, NS = 3, MINB = 2; };
 
 template <class T> static void set_kernel(ocb_strain_plan* sp, void (*k)(StrainParams<T>));
 template <> void set_kernel<double>(ocb_strain_plan* sp, void (*k)(StrainParams<double>)) { sp->kd = k; }
@@ -337,18 +347,34 @@ template <> void set_kernel<float>(ocb_strain_plan* sp, void (*k)(StrainParams<f
 static void keep_params(ocb_strain_plan* sp, const StrainParams<double>& P) { sp->Pd = P; }
 static void keep_params(ocb_strain_plan* sp, const StrainParams<float>& P) { sp->Pf = P; }
 
-template <class T, int FAM, int NNU>
-static int strain_setup(ocb_strain_plan* sp) {
-  using S = StrainShape<T>;
+template <class T, int FAM, int NNU, int NW, int RY, int NS, int MINB>
+static int strain_setup_shape(ocb_strain_plan* sp) {
   constexpr int NFAM = ((FAM & 1) ? 1 : 0) + ((FAM & 2) ? 1 : 0) + ((FAM & 4) ? 1 : 0);
-  constexpr int NF = 3 + NNU, TR = S::NW * S::RY + 2, TILE = STW * TR;
-  sp->nw = S::NW;
-  sp->smem = sizeof(T) * ((size_t)S::NS * NF * TILE + 2 * S::NW * 2 * NFAM * 32) + sizeof(double) * S::NW;
-  auto k = ocb_strain_kernel<T, FAM, NNU, S::NW, S::RY, S::NS>;
+  constexpr int NF = 3 + NNU, TR = NW * RY + 2, TILE = STW * TR + STPAD;
+  sp->nw = NW; sp->ry = RY;
+  sp->smem = sizeof(T) * ((size_t)NS * NF * TILE + 2 * NW * 2 * NFAM * 32 + 4 * ZC) + sizeof(double) * NW;
+  auto k = ocb_strain_kernel<T, FAM, NNU, NW, RY, NS, MINB>;
   cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   OCB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp->smem));
   set_kernel<T>(sp, k);
   return OCB_OK;
+}
+
+template <class T, int FAM, int NNU>
+static int strain_setup(ocb_strain_plan* sp) {
+  using S = StrainShape<T>;
+  // Shapes measured on B200 (profiles/r1_summary.md): small blocks win -- 4 warps x 3 rows, four blocks per SM in
+  // Float32 (2.45 ms for config 4; 8 x 3 x 2: 2.7 ms, 16 x 2 x 1: 3.9 ms), two in Float64 (4.3 ms; 8 x 2 x 1: 5.5 ms).
+  if (const char* cfg = getenv("OCB_STRAIN_CONFIG")) {       // tuning runs: "NW,RY,MINB" for the config-4 kernel (eps + |S|, one nu_e field)
+    if (FAM == 3 && NNU == 1) {
+      int nw = 0, ry = 0, mb = 0, ns = 3;
+      sscanf(cfg, "%d,%d,%d,%d", &nw, &ry, &mb, &ns);
+#define OCB_SHAPE(A, B, C, D) if (nw == A && ry == B && mb == C && ns == D) return strain_setup_shape<T, 3, 1, A, B, D, C>(sp);
+      OCB_SHAPE(4, 3, 4, 3) OCB_SHAPE(4, 3, 2, 3) OCB_SHAPE(8, 3, 2, 3) OCB_SHAPE(8, 2, 1, 3)
+#undef OCB_SHAPE
+    }
+  }
+  return strain_setup_shape<T, FAM, NNU, S::NW, S::RY, S::NS, S::MINB>(sp);
 }
 
 template <class T, int FAM>
@@ -420,8 +446,7 @@ static int strain_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, c
   memset((void*)&P, 0, sizeof(P));
   P.Nx = grid->N[0]; P.Ny = grid->N[1]; P.Nz = grid->N[2];
   P.hx = grid->H[0]; P.hy = grid->H[1]; P.hz = grid->H[2];
-  using S = StrainShape<T>;
-  const int BR = S::NW * S::RY;
+  const int BR = sp->nw * sp->ry;
   P.tiles_x = (P.Nx + 30) / 31;
   P.jy_lo = SP.req[0].lo[1]; P.jy_hi = SP.req[0].hi[1];
   P.tiles_y = ((P.jy_hi - P.jy_lo + 1) + BR - 2) / (BR - 1);
@@ -441,12 +466,19 @@ static int strain_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, c
   P.nslots = SP.nslots;
   const ocb_field* f[NFMAX] = {&in->u, &in->v, &in->w, &in->closure.nu_fields[0], &in->closure.nu_fields[1]};
   P.cx = P.cy = P.cz = 1 << 30;
+  P.sy = (int)f[0]->stride[1]; P.sz = f[0]->stride[2];
+  bool pairs = P.sy % 2 == 0 && P.sz % 2 == 0;       // rows are copied as aligned element pairs
   for (int a = 0; a < 3 + nnu; ++a) {
-    P.f[a].p = (const T*)f[a]->data; P.f[a].sy = f[a]->stride[1]; P.f[a].sz = f[a]->stride[2];
+    P.f[a] = (const T*)f[a]->data;
+    // one row / plane pitch for every operand (periodic x and y: u, v, w and the ccc fields share a parent shape)
+    if (f[a]->stride[1] != P.sy || f[a]->stride[2] != P.sz || f[a]->stride[1] > (1 << 30)) { delete sp; return OCB_OK; }
+    if ((uintptr_t)f[a]->data % (2 * sizeof(T))) pairs = false;
     if (f[a]->size[0] - 1 < P.cx) P.cx = f[a]->size[0] - 1;
     if (f[a]->size[1] - 1 < P.cy) P.cy = f[a]->size[1] - 1;
     if (f[a]->size[2] - 1 < P.cz) P.cz = f[a]->size[2] - 1;
   }
+  if ((long long)P.sy * (P.cy + 1) > (1LL << 31) - 64) { delete sp; return OCB_OK; }   // in-plane offsets are 32-bit
+  if (P.cx % 2 == 0 || !pairs) { delete sp; return OCB_OK; }                            // odd row length / unaligned base: generic kernel
   for (int a = 0; a < 3; ++a) P.os[a] = os[a];
   for (int d = 0; d < SD_N; ++d) {
     P.out[d] = which_out[d] >= 0 ? (T*)SP.req[which_out[d]].out : nullptr;

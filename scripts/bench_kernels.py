@@ -54,12 +54,14 @@ def main():
                {"variant": grp.plan.variant})
         del grp, m, U, V, W
         torch.cuda.empty_cache()
-    if "config4" in which:
+    for c4, dt4 in (("config4", torch.float32), ("config4f64", torch.float64)):
+        if c4 not in which:
+            continue
         import numpy as np
         Nx, Ny, Nz = 768, 768, 384
         k = np.arange(Nz + 1)
         zf = -np.tanh(2.0 * (1 - k / Nz)) / np.tanh(2.0)          # tanh-stretched faces, fine near the top
-        grid = ocb.RectilinearGrid((Nx, Ny, Nz), x=(0, 1), y=(0, 1), z=zf, dtype=torch.float32, device=dev)
+        grid = ocb.RectilinearGrid((Nx, Ny, Nz), x=(0, 1), y=(0, 1), z=zf, dtype=dt4, device=dev)
         nu_e = ocb.CenterField(grid)
         nu_e.interior.copy_(1e-3 * (1 + 0.5 * torch.rand(nu_e.interior.shape, device=dev)))
         nu_e.fill_halo_regions()
@@ -67,12 +69,12 @@ def main():
                               ("tuple (ScalarDiffusivity, AMD-like nu_e)", ocb.Closure.tuple_of(ocb.Closure(nu=1e-6), ocb.Closure(nu_fields=(nu_e,))))):
             m = ocb.NonhydrostaticModel(grid, closure=closure)
             for f in (m.velocities.u, m.velocities.v, m.velocities.w):
-                f.interior.copy_(torch.randn(f.interior.shape, device=dev, dtype=torch.float32))
+                f.interior.copy_(torch.randn(f.interior.shape, device=dev, dtype=dt4))
             m.fill_halo_regions()
             eps, smod = ocb.Field(ocb.KineticEnergyEquation.DissipationRate(m)), ocb.Field(ocb.FlowDiagnostics.StrainRateTensorModulus(m))
             grp = ocb.FusedDiagnostics(eps, smod)
             ms = timed(grp.plan.execute)
-            report(f"config4: 768x768x384 F32 stretched z, {name}: eps + |S| fields", ms, Nx * Ny * Nz, grp.plan.algorithmic_bytes / (Nx * Ny * Nz),
+            report(f"{c4}: 768x768x384 {'F32' if dt4 == torch.float32 else 'F64'} stretched z, {name}: eps + |S| fields", ms, Nx * Ny * Nz, grp.plan.algorithmic_bytes / (Nx * Ny * Nz),
                    {"variant": grp.plan.variant})
             del grp, m, eps, smod
         torch.cuda.empty_cache()

@@ -52,9 +52,8 @@ def test_fused_budget_matches_oracle(size):
     st = State(size=size, device="cuda")
     ops, oc = budget(st)
     grp, vals, ints = run(ops)
-    # TMA needs 16-byte row pitches: an even Nx takes the budget kernel; with an odd one the dissipation rate goes to
-    # the velocity-gradient kernel (cp.async loads) and the rest to the generic kernel
-    assert grp.plan.variant == (1 if size[0] % 2 == 0 else 4)
+    # TMA needs 16-byte row pitches: an even Nx takes the pipelined kernel, an odd one the generic kernel
+    assert grp.plan.variant == (1 if size[0] % 2 == 0 else 0)
     want = oracle_budget(st, oc)
     for op, g, w_, integ in zip(ops, vals, want, ints):
         assert_close(g, w_, 1e-12, op.name)

@@ -37,7 +37,9 @@ def test_velocity_gradient_family_matches_oracle_f64(size, closure, stretched):
     cases = {c[0]: c for c in build_cases(st, closure)}
     ops = [cases[nm][1] for nm in NAMES]
     grp = _group(ops)
-    assert grp.plan.variant == 3 and grp.plan.n_launches == 2
+    # rows come in as aligned element pairs: an odd Nx (odd parent row length) takes the generic kernel
+    kv = 3 if size[0] % 2 == 0 else 0
+    assert grp.plan.variant == kv and grp.plan.n_launches == 2
     vals = [m.interior_ijk() for m in grp.members if isinstance(m, ocb.ComputedField)]
     for nm, got, integ in zip(NAMES, vals, grp.integrals()):
         _, _, want, loc = cases[nm]
@@ -47,7 +49,7 @@ def test_velocity_gradient_family_matches_oracle_f64(size, closure, stretched):
     for nm in NAMES:
         one = _group([cases[nm][1]], fields=False)
         budget_takes_it = nm == "DissipationRate" and closure == "scalar" and not stretched and size[0] % 2 == 0
-        assert one.plan.variant == (1 if budget_takes_it else 3)
+        assert one.plan.variant == (1 if budget_takes_it else kv)
         want, loc = cases[nm][2], cases[nm][3]
         assert abs(one.integrals()[0] - K.integral(want, st.og, loc)) <= 1e-12 * integral_scale(st.og, want, loc), nm
 
