@@ -75,18 +75,24 @@ __global__ void __launch_bounds__(RS_THREADS) rs_histogram(const K* __restrict__
   table[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
 }
 
-// stable scatter of one tile: warp w owns the contiguous sub-tile [w*512, (w+1)*512), walked in 16 rounds of 32
+// stable scatter of one tile: warp w owns the contiguous sub-tile [w*512, (w+1)*512), walked in 16 rounds of 32.
+// The tile is first put in digit order in shared memory (keys, then the payload through the same buffer), so that the
+// global writes are runs of consecutive addresses per digit (16 keys = 128 B on average) instead of one sector per key.
 template <class K>
 __global__ void __launch_bounds__(RS_THREADS) rs_scatter(const K* __restrict__ keys_in, const uint32_t* __restrict__ idx_in, K* __restrict__ keys_out,
                                                           uint32_t* __restrict__ idx_out, long long n, int shift,
                                                           const uint32_t* __restrict__ offsets, int nblocks) {
-  __shared__ uint32_t wcount[RS_WARPS][256];     // per-warp running digit counts -> per-warp digit bases
-  __shared__ uint32_t gbase[256];
+  __shared__ uint32_t wcount[RS_WARPS][256];     // per-warp running digit counts -> per-warp digit bases inside the tile
+  __shared__ uint32_t gbase[256];                // global position of the tile's first key of each digit, minus its tile position
+  __shared__ uint32_t tstart[256];               // tile position of the first key of each digit
+  __shared__ uint32_t wtot[RS_WARPS];
+  __shared__ K stage[RS_TILE];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int d = lane; d < 256; d += 32) wcount[warp][d] = 0;
-  gbase[threadIdx.x] = offsets[(size_t)threadIdx.x * nblocks + blockIdx.x];
   __syncwarp();
-  const long long wbase = (long long)blockIdx.x * RS_TILE + (long long)warp * (RS_ITEMS * 32);
+  const long long tbase = (long long)blockIdx.x * RS_TILE;
+  const long long wbase = tbase + (long long)warp * (RS_ITEMS * 32);
+  const int ntile = (int)((n - tbase) < (long long)RS_TILE ? (n - tbase) : (long long)RS_TILE);
   K key[RS_ITEMS];
   uint32_t rank[RS_ITEMS];
   const unsigned lt = (1u << lane) - 1u;
@@ -107,23 +113,59 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter(const K* __restrict__ k
     rank[r] = prev + __popc(peers & lt);
   }
   __syncthreads();
-  // exclusive scan across warps for each digit: thread d handles digit d
+  // thread d: exclusive scan across warps for digit d, then (block scan) the tile position where digit d starts
   {
     uint32_t run = 0;
     const int d = threadIdx.x;
 #pragma unroll
     for (int w = 0; w < RS_WARPS; ++w) { const uint32_t c = wcount[w][d]; wcount[w][d] = run; run += c; }
+    uint32_t inc = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+    if (lane == 31) wtot[warp] = inc;
+    __syncthreads();
+    uint32_t before = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) if (w < warp) before += wtot[w];
+    const uint32_t start = before + inc - run;
+    tstart[d] = start;
+    gbase[d] = offsets[(size_t)d * nblocks + blockIdx.x] - start;
   }
   __syncthreads();
+  // keys: into digit order in shared memory, then out in runs
 #pragma unroll
   for (int r = 0; r < RS_ITEMS; ++r) {
     const long long t = wbase + r * 32 + lane;
     if (t < n) {
       const uint32_t dig = (uint32_t)(key[r] >> shift) & 255u;
-      const uint32_t pos = gbase[dig] + wcount[warp][dig] + rank[r];
-      keys_out[pos] = key[r];
-      idx_out[pos] = idx_in[t];
+      rank[r] = tstart[dig] + wcount[warp][dig] + rank[r];                    // tile position
+      stage[rank[r]] = key[r];
     }
+  }
+  __syncthreads();
+  uint32_t pos[RS_ITEMS];
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; ++r) {
+    const int e = r * RS_THREADS + threadIdx.x;
+    if (e < ntile) {
+      const K k = stage[e];
+      pos[r] = gbase[(uint32_t)(k >> shift) & 255u] + (uint32_t)e;
+      keys_out[pos[r]] = k;
+    }
+  }
+  __syncthreads();
+  // payload: the same way through the same buffer
+  uint32_t* stage_i = reinterpret_cast<uint32_t*>(stage);
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; ++r) {
+    const long long t = wbase + r * 32 + lane;
+    if (t < n) stage_i[rank[r]] = idx_in[t];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; ++r) {
+    const int e = r * RS_THREADS + threadIdx.x;
+    if (e < ntile) idx_out[pos[r]] = stage_i[e];
   }
 }
 
