@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_histogram(const K* __restrict__
 // The tile is first put in digit order in shared memory (keys, then the payload through the same buffer), so that the
 // global writes are runs of consecutive addresses per digit (16 keys = 128 B on average) instead of one sector per key.
 template <class K>
-__global__ void __launch_bounds__(RS_THREADS) rs_scatter(const K* __restrict__ keys_in, const uint32_t* __restrict__ idx_in, K* __restrict__ keys_out,
+__global__ void __launch_bounds__(RS_THREADS, 3) rs_scatter(const K* __restrict__ keys_in, const uint32_t* __restrict__ idx_in, K* __restrict__ keys_out,
                                                           uint32_t* __restrict__ idx_out, long long n, int shift,
                                                           const uint32_t* __restrict__ offsets, int nblocks) {
   __shared__ uint32_t wcount[RS_WARPS][256];     // per-warp running digit counts -> per-warp digit bases inside the tile
@@ -96,11 +96,16 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter(const K* __restrict__ k
   K key[RS_ITEMS];
   uint32_t rank[RS_ITEMS];
   const unsigned lt = (1u << lane) - 1u;
+  // all of the thread's keys first (16 independent loads in flight), then the ranking rounds
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; ++r) {
+    const long long t = wbase + r * 32 + lane;
+    key[r] = t < n ? __ldg(keys_in + t) : (K)~(K)0;
+  }
 #pragma unroll
   for (int r = 0; r < RS_ITEMS; ++r) {
     const long long t = wbase + r * 32 + lane;
     const bool ok = t < n;
-    key[r] = ok ? keys_in[t] : (K)~(K)0;
     const uint32_t dig = ok ? ((uint32_t)(key[r] >> shift) & 255u) : 256u;    // 256: out of range, matches only other padding
     const unsigned peers = __match_any_sync(0xffffffffu, dig);
     uint32_t prev = 0;
@@ -159,7 +164,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter(const K* __restrict__ k
 #pragma unroll
   for (int r = 0; r < RS_ITEMS; ++r) {
     const long long t = wbase + r * 32 + lane;
-    if (t < n) stage_i[rank[r]] = idx_in[t];
+    if (t < n) stage_i[rank[r]] = __ldg(idx_in + t);
   }
   __syncthreads();
 #pragma unroll
