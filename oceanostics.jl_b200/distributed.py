@@ -131,3 +131,92 @@ class OverlappedSlabBudget:
         self.total.add_(self.high.plan.integrals[:self.n])
         allreduce_integrals(self.total, self.group)
         return self.total
+
+
+def _axis_spec(grid, d):
+    f = grid.nodes(d, "f", list(range(1, grid.N[d] + 2)))
+    return (float(f[0]), float(f[-1])) if grid.uniform[d] else f
+
+
+class SlabFilteredField:
+    """`Field(filter(ψ))` for a field that lives on a y slab.
+
+    The x and z passes of the staged filter never leave the slab; the y pass reaches `w` rows into each ring
+    neighbour (w = the filter's half width along y, 8 rows in BASELINE config 5).  Those rows of ψ are exchanged once
+    (one grouped NCCL send/recv), the slab is filtered on a grid extended by w rows on each cut side with the ordinary
+    staged kernels, and the slab's own rows are kept: every retained output sees exactly the taps, weights and
+    summation order of the single-domain filter, so the result is bit-identical to it.  With a Bounded y axis the two
+    end ranks keep their true boundary, where the filter's boundary policy applies as usual."""
+
+    def __init__(self, psi, make_filter, rank=None, world=None, group=None, periodic_y=True):
+        from .fields import Field
+        from .grids import RectilinearGrid, Bounded
+        from .SpatialFilters import FilterOperation
+        self.psi, self.group = psi, group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        g = psi.grid
+        probe = make_filter(psi)
+        if not isinstance(probe, FilterOperation):
+            raise TypeError("make_filter(ψ) must return BoxFilter(ψ; ...) or GaussianFilter(ψ; ...)")
+        self.w = probe.widths[probe.sorted_dims.index(2)] if 2 in probe.sorted_dims else 0
+        if psi.location[1] != "c":
+            raise ValueError("slab filters take fields located at cell centres in y")
+        if not g.uniform[1]:
+            raise ValueError("slab filters need a regularly spaced y axis")
+        ny = g.N[1]
+        if self.w > ny:
+            raise ValueError(f"filter half width {self.w} along y exceeds the slab's {ny} rows")
+        first, last = self.rank == 0, self.rank == self.world - 1
+        self.ext_lo = self.w if (periodic_y or not first) else 0          # rows borrowed from the low / high neighbour
+        self.ext_hi = self.w if (periodic_y or not last) else 0
+        yf = g.nodes(1, "f", [1, ny + 1])
+        dy = float(yf[1] - yf[0]) / ny
+        topo = (g.user_topology[0], Bounded, g.user_topology[2])
+        self.ext_grid = RectilinearGrid((g.N[0], ny + self.ext_lo + self.ext_hi, g.N[2]), x=_axis_spec(g, 0),
+                                        y=(float(yf[0]) - self.ext_lo * dy, float(yf[1]) + self.ext_hi * dy), z=_axis_spec(g, 2),
+                                        halo=g.H, topology=topo, dtype=g.dtype, device=g.device)
+        self.ext_psi = Field(psi.location, self.ext_grid)
+        self.ext_filtered = Field(make_filter(self.ext_psi))
+        self.result = Field(psi.location, g)
+        self.lo_rank, self.hi_rank = (self.rank - 1) % self.world, (self.rank + 1) % self.world
+        shp = lambda n: (psi.interior.shape[0], n, psi.interior.shape[2])
+        mk = lambda n: torch.empty(shp(n), dtype=psi.data.dtype, device=psi.data.device)
+        self.send_lo, self.send_hi = mk(self.w), mk(self.w)               # my first / last w rows
+        self.recv_lo, self.recv_hi = mk(self.ext_lo), mk(self.ext_hi)
+        self.bytes_per_exchange = (self.send_lo.numel() + self.send_hi.numel()) * self.send_lo.element_size()
+
+    def compute(self, time=None):
+        from .operations import compute_at
+        if getattr(self.psi, "is_computed", False):
+            compute_at(self.psi, time)
+        self.exchange()
+        ny = self.psi.grid.N[1]
+        self.ext_filtered.compute(time)
+        self.result.interior.copy_(self.ext_filtered.interior[:, self.ext_lo:self.ext_lo + ny, :])
+        return self.result
+
+    def exchange(self):
+        """Fill the extended copy of ψ: the slab's own rows plus w rows from each ring neighbour."""
+        psi, w, ny = self.psi, self.w, self.psi.grid.N[1]
+        src, ext = psi.interior, self.ext_psi.interior
+        ext[:, self.ext_lo:self.ext_lo + ny, :].copy_(src)
+        if w > 0:
+            self.send_lo.copy_(src[:, :w, :])
+            self.send_hi.copy_(src[:, ny - w:, :])
+            if self.world == 1:
+                if self.ext_hi: self.recv_hi.copy_(self.send_lo)
+                if self.ext_lo: self.recv_lo.copy_(self.send_hi)
+            else:
+                ops = []
+                # my low rows extend the low neighbour's slab upwards, my high rows the high neighbour's downwards
+                # (in a ring of two both neighbours are the same peer and messages pair up in posting order: sends low
+                # then high, receives high then low, as in SlabHaloExchanger)
+                if self.ext_lo: ops.append(dist.P2POp(dist.isend, self.send_lo, self.lo_rank, self.group))
+                if self.ext_hi: ops.append(dist.P2POp(dist.isend, self.send_hi, self.hi_rank, self.group))
+                if self.ext_hi: ops.append(dist.P2POp(dist.irecv, self.recv_hi, self.hi_rank, self.group))
+                if self.ext_lo: ops.append(dist.P2POp(dist.irecv, self.recv_lo, self.lo_rank, self.group))
+                for req in dist.batch_isend_irecv(ops):
+                    req.wait()
+            if self.ext_lo: ext[:, :self.ext_lo, :].copy_(self.recv_lo)
+            if self.ext_hi: ext[:, self.ext_lo + ny:, :].copy_(self.recv_hi)

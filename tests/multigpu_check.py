@@ -60,8 +60,20 @@ def main():
         f.data[:, :3, :] = 0.0
         f.data[:, -3:, :] = 0.0
     ov_total = ov.step().clone()
-    ok = True
+    # ---- slab filter: the y pass reaches 5 rows into each neighbour (exchanged over NCCL) -------------------------
+    from oceanostics_b200.distributed import SlabFilteredField
+    SF = ocb.SpatialFilters
+    sigma = 2.5 / Ny
+    mk = lambda f: SF.GaussianFilter(f, dims=(1, 2, 3), sigma=sigma, N=11)
+    slab_f = SlabFilteredField(m.tracers.b, mk, rank=rank, world=world).compute()
+    _, mg_all, _ = model_on(1, Ny, full=True)
+    want_f = ocb.Field(mk(mg_all.tracers.b)).compute().interior[:, lo - 1:hi, :]
+    f_err = float((slab_f.interior - want_f).abs().max()) / float(want_f.abs().max())
+    f_ok = torch.tensor([1.0 if f_err <= 1e-14 else 0.0], device=dev)
+    dist.all_reduce(f_ok, op=dist.ReduceOp.MIN)
+    ok = bool(f_ok.item() > 0)
     if rank == 0:
+        print("slab filter max rel err", f_err, flush=True)
         _, mg, _ = model_on(1, Ny, full=True)
         ref = ocb.FusedDiagnostics(*[ocb.Integral(o) for o in budget_ops(mg)]).compute()
         want = ref.plan.integrals.cpu().numpy()

@@ -91,3 +91,36 @@ def test_ring_halo_exchange_and_allreduce_world4():
     out = mgr.dict()
     mp.spawn(_worker, args=(4, _free_port(), out), nprocs=4, join=True)
     assert all(out[r] for r in range(4))
+
+
+def _filter_worker(rank, world, port, out, periodic):
+    """The slab filter's row exchange (the filter kernels themselves are CUDA-only): every rank's extended copy of ψ
+    must hold the global rows lo-w .. hi+w (wrapped when y is periodic, absent past a true boundary)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oceanostics_b200.distributed import SlabFilteredField, slab_range
+    Nx, Ny, Nz = 6, 5 * world + 1, 4
+    lo, hi = slab_range(Ny, rank, world)
+    topo = (ocb.Periodic, ocb.Periodic if periodic else ocb.Bounded, ocb.Bounded)
+    g = ocb.RectilinearGrid((Nx, hi - lo + 1, Nz), x=(0, 1), y=((lo - 1) / Ny, hi / Ny), z=(-1, 0), topology=topo, device="cpu")
+    f = ocb.Field(("c", "c", "c"), g)
+    kk, jj, ii = torch.meshgrid(torch.arange(Nz), torch.arange(lo - 1, hi), torch.arange(Nx), indexing="ij")
+    f.interior.copy_((kk * 1000 + jj * 10 + ii).double())
+    sf = SlabFilteredField(f, lambda psi: ocb.SpatialFilters.BoxFilter(psi, dims=(1, 2), N=7), rank=rank, world=world, periodic_y=periodic)
+    sf.exchange()
+    w = 3
+    assert sf.w == w
+    rows = list(range(lo - 1 - sf.ext_lo, hi + sf.ext_hi))            # 0-based global rows of the extended slab
+    assert sf.ext_lo == (w if periodic or rank > 0 else 0) and sf.ext_hi == (w if periodic or rank < world - 1 else 0)
+    kk, jj, ii = torch.meshgrid(torch.arange(Nz), torch.tensor([r % Ny for r in rows]), torch.arange(Nx), indexing="ij")
+    out[rank] = bool(torch.equal(sf.ext_psi.interior, (kk * 1000 + jj * 10 + ii).double()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(240)
+@pytest.mark.parametrize("world,periodic", [(2, True), (4, True), (3, False)])
+def test_slab_filter_row_exchange(world, periodic):
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_filter_worker, args=(world, _free_port(), out, periodic), nprocs=world, join=True)
+    assert all(out[r] for r in range(world))

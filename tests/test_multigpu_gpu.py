@@ -90,6 +90,26 @@ def test_host_streamed_budget_matches_resident_sweep():
     assert hs.h2d_bytes == sum(f.data.numel() * 8 for f in m_fields)
 
 
+@pytest.mark.parametrize("kind", ["gauss", "box"])
+def test_slab_filter_self_exchange_equals_periodic_filter(kind):
+    """One slab spanning the whole periodic y axis: the rows it borrows are its own, so the slab filter must reproduce
+    the single-domain filter (same taps, weights and order for every retained output)."""
+    from oceanostics_b200.distributed import SlabFilteredField
+    st = State(size=(40, 24, 18), device="cuda")
+    SF = ocb.SpatialFilters
+    mk = (lambda f: SF.GaussianFilter(f, dims=(1, 2, 3), sigma=2.0 / 24, N=9)) if kind == "gauss" else \
+         (lambda f: SF.BoxFilter(f, dims=(2, 3), N=7))
+    got = SlabFilteredField(st.b, mk, rank=0, world=1).compute()
+    want = ocb.Field(mk(st.b)).compute()
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(got.interior.cpu().numpy(), want.interior.cpu().numpy(), rtol=1e-13, atol=1e-15)
+    # a filter that does not touch y needs no exchange at all
+    only_x = SlabFilteredField(st.b, lambda f: SF.BoxFilter(f, dims=(1,), N=5), rank=0, world=1)
+    assert only_x.w == 0 and only_x.bytes_per_exchange == 0
+    np.testing.assert_array_equal(only_x.compute().interior.cpu().numpy(),
+                                  ocb.Field(SF.BoxFilter(st.b, dims=(1,), N=5)).compute().interior.cpu().numpy())
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
 def test_nccl_slabs_match_single_domain():
     """torchrun x2: NCCL halo exchange + all-reduced integrals equal the single-domain integrals."""
