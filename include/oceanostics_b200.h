@@ -133,6 +133,8 @@ enum {
   OCB_DIAG_PI,            /* cross_scale_ke_flux_ccc: -sum w_ij center(aux_ij - uᵢuⱼ) center(S_ij)  FilteredKineticEnergyEquation.jl:176-188 */
   OCB_DIAG_BPE,           /* minus_bz✶_ccc: -b * aux[6]              BackgroundPotentialEnergyEquation.jl:852 */
   OCB_DIAG_APE,           /* local_ape_ccc: aux[5] - b (z - aux[6])   AvailablePotentialEnergyEquation.jl:42  (next-row, §8f) */
+  OCB_DIAG_UPSILON,       /* upsilon_ccc: aux[6] - z  (aux[6] = z✶)   AvailablePotentialEnergyEquation.jl:126 (next-row, §8f) */
+  OCB_DIAG_APE_EPS,       /* ape_dissipation_rate_ccc: (1/V) sum center(-A δΥ q), Υ = aux[4], tracer b   AvailablePotentialEnergyEquation.jl:202-215 */
   OCB_DIAG_COUNT
 };
 

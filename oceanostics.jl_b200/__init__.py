@@ -13,7 +13,7 @@ from .operations import (KernelFunctionOperation, ComputedField, ReducedField, I
 from .models import (NonhydrostaticModel, HydrostaticFreeSurfaceModel, FPlane, ConstantCartesianCoriolis, BuoyancyTracer,
                      get_coriolis_frequency_components)
 from . import KineticEnergyEquation, TurbulentKineticEnergyEquation, TracerVarianceEquation, FlowDiagnostics, SpatialFilters, BackgroundPotentialEnergyEquation
-from . import FilteredKineticEnergyEquation, SubFilterKineticEnergyEquation
+from . import FilteredKineticEnergyEquation, SubFilterKineticEnergyEquation, AvailablePotentialEnergyEquation
 from .SpatialFilters import BoxFilter, GaussianFilter
 
 ScalarDiffusivity = Closure

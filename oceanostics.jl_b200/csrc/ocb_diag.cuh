@@ -523,6 +523,22 @@ OCB_EVAL(OCB_DIAG_BPE) { return -X.in.b(i, j, k) * X.in.aux[6](i, j, k); } };
 // local_ape_ccc  (src/AvailablePotentialEnergyEquation.jl:42-45): Ψδ - b (z - z✶)
 OCB_EVAL(OCB_DIAG_APE) { return X.in.aux[5](i, j, k) - X.in.b(i, j, k) * (OCB_LD(X.g.zc + k) - X.in.aux[6](i, j, k)); } };
 
+// upsilon_ccc  (src/AvailablePotentialEnergyEquation.jl:126): Υ = z✶ - z, with aux[6] = z✶
+OCB_EVAL(OCB_DIAG_UPSILON) { return X.in.aux[6](i, j, k) - OCB_LD(X.g.zc + k); } };
+// ape_dissipation_rate_ccc  (src/AvailablePotentialEnergyEquation.jl:202-215): (1/V) Σ ℑ(-A δΥ q) with q = -κ ∂c, Υ = aux[4]
+// -- the discretisation of tracer_variance_dissipation_rate_ccc with one δc replaced by δΥ, and half of it
+OCB_EVAL(OCB_DIAG_APE_EPS) {
+  const HFld<T>& Y = X.in.aux[4];       // (aux[5], aux[6] stay free for Ψδ and z✶: the whole APE family shares a sweep)
+  T cc = X.c(i, j, k), yc = Y(i, j, k);
+  T fx0 = X.ka_fcc(i, j, k) * ((cc - X.c(i - 1, j, k)) * (yc - Y(i - 1, j, k)));
+  T fx1 = X.ka_fcc(i + 1, j, k) * ((X.c(i + 1, j, k) - cc) * (Y(i + 1, j, k) - yc));
+  T fy0 = X.ka_cfc(i, j, k) * ((cc - X.c(i, j - 1, k)) * (yc - Y(i, j - 1, k)));
+  T fy1 = X.ka_cfc(i, j + 1, k) * ((X.c(i, j + 1, k) - cc) * (Y(i, j + 1, k) - yc));
+  T fz0 = X.ka_ccf(i, j, k) * ((cc - X.c(i, j, k - 1)) * (yc - Y(i, j, k - 1))) * X.rdzf(k);
+  T fz1 = X.ka_ccf(i, j, k + 1) * ((X.c(i, j, k + 1) - cc) * (Y(i, j, k + 1) - yc)) * X.rdzf(k + 1);
+  return T(0.5) * ((fx0 + fx1) * (X.g.rdx * X.g.rdx) + (fy0 + fy1) * (X.g.rdy * X.g.rdy) + (fz0 + fz1) * X.rdzc(k));
+} };
+
 // ---- dispatch -------------------------------------------------------------------------------------------------
 #define OCB_FOR_EACH_DIAG(M) \
   M(OCB_DIAG_KE) M(OCB_DIAG_ADV) M(OCB_DIAG_PR) M(OCB_DIAG_WB) M(OCB_DIAG_EPS) M(OCB_DIAG_EPS_ISO) M(OCB_DIAG_TKE) \
@@ -532,7 +548,7 @@ OCB_EVAL(OCB_DIAG_APE) { return X.in.aux[5](i, j, k) - X.in.b(i, j, k) * (OCB_LD
   M(OCB_DIAG_T11C) M(OCB_DIAG_T22C) M(OCB_DIAG_T33C) M(OCB_DIAG_T12) M(OCB_DIAG_T13) M(OCB_DIAG_T23) M(OCB_DIAG_RI) \
   M(OCB_DIAG_RO) M(OCB_DIAG_EPV) M(OCB_DIAG_TWPV) M(OCB_DIAG_DEPV) M(OCB_DIAG_VF11) M(OCB_DIAG_VF22) M(OCB_DIAG_VF33) \
   M(OCB_DIAG_VF12) M(OCB_DIAG_VF13) M(OCB_DIAG_VF23) M(OCB_DIAG_FEPS) M(OCB_DIAG_SFEPS) M(OCB_DIAG_SFKE) M(OCB_DIAG_PI) \
-  M(OCB_DIAG_BPE) M(OCB_DIAG_APE)
+  M(OCB_DIAG_BPE) M(OCB_DIAG_APE) M(OCB_DIAG_UPSILON) M(OCB_DIAG_APE_EPS)
 
 // diagnostics whose operands may be lazy perturbations (u - U, c - C); the flag is rejected for the others
 OCB_X constexpr bool ocb_diag_takes_perturbation(int d) {

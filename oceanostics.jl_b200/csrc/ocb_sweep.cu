@@ -150,6 +150,8 @@ static double count_algorithmic_bytes(const ocb_grid* g, const ocb_sweep_inputs*
       case OCB_DIAG_CHI: case OCB_DIAG_CDIFF: use[3] = true; if (pert) use[8] = true; break;
       case OCB_DIAG_RI: case OCB_DIAG_EPV: case OCB_DIAG_DEPV: case OCB_DIAG_TWPV: mark_uvw(); use[3] = true; break;
       case OCB_DIAG_BPE: use[3] = true; use[15] = true; break;
+      case OCB_DIAG_UPSILON: use[15] = true; break;
+      case OCB_DIAG_APE_EPS: use[3] = true; use[13] = true; break;
       case OCB_DIAG_APE: use[3] = true; use[14] = use[15] = true; break;
       case OCB_DIAG_FEPS: case OCB_DIAG_PI: mark_uvw(); for (int a = 0; a < 6; ++a) use[9 + a] = true; break;
       case OCB_DIAG_SFEPS: mark_uvw(); for (int a = 0; a < 7; ++a) use[9 + a] = true; break;
@@ -170,7 +172,8 @@ static double count_algorithmic_bytes(const ocb_grid* g, const ocb_sweep_inputs*
   bool eddy = false;
   for (int r = 0; r < n; ++r) {
     const int d = reqs[r].diag;
-    if (d == OCB_DIAG_EPS || d == OCB_DIAG_EPS_ISO || d == OCB_DIAG_CHI || d == OCB_DIAG_CDIFF || (d >= OCB_DIAG_VF11 && d <= OCB_DIAG_VF23)) eddy = true;
+    if (d == OCB_DIAG_EPS || d == OCB_DIAG_EPS_ISO || d == OCB_DIAG_CHI || d == OCB_DIAG_CDIFF || d == OCB_DIAG_APE_EPS ||
+        (d >= OCB_DIAG_VF11 && d <= OCB_DIAG_VF23)) eddy = true;
   }
   if (eddy) {   // count each distinct eddy field once
     const void* seen[2 * OCB_MAX_CLOSURE_FIELDS]; int ns = 0;

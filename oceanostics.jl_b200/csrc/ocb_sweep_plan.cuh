@@ -29,7 +29,7 @@ static inline const char* ocb_diag_name(int diag) {
 }
 
 // which operands a diagnostic cannot do without (bit set => must be an ARRAY operand)
-enum { OCB_NEED_B = 1, OCB_NEED_P = 2, OCB_NEED_AUX05 = 4, OCB_NEED_AUX6 = 8, OCB_NEED_AUX5 = 16 };
+enum { OCB_NEED_B = 1, OCB_NEED_P = 2, OCB_NEED_AUX05 = 4, OCB_NEED_AUX6 = 8, OCB_NEED_AUX5 = 16, OCB_NEED_AUX4 = 32 };
 static inline int ocb_diag_needs(int diag) {
   switch (diag) {
     case OCB_DIAG_PR: return OCB_NEED_P;
@@ -39,6 +39,8 @@ static inline int ocb_diag_needs(int diag) {
     case OCB_DIAG_SFEPS: return OCB_NEED_AUX05 | OCB_NEED_AUX6;
     case OCB_DIAG_SFKE: return OCB_NEED_AUX6;
     case OCB_DIAG_BPE: return OCB_NEED_B | OCB_NEED_AUX6;
+    case OCB_DIAG_UPSILON: return OCB_NEED_AUX6;
+    case OCB_DIAG_APE_EPS: return OCB_NEED_B | OCB_NEED_AUX4;
     case OCB_DIAG_APE: return OCB_NEED_B | OCB_NEED_AUX6 | OCB_NEED_AUX5;
     default: return 0;
   }
@@ -115,6 +117,7 @@ static int ocb_build_sweep_params(const ocb_grid* grid, const ocb_sweep_inputs* 
     if (needs & OCB_NEED_P) OCB_REQUIRE(I.p.p, "%s needs the pressure operand `p` as an array", ocb_diag_name(q.diag));
     if (needs & OCB_NEED_AUX6) OCB_REQUIRE(I.aux[6].p, "%s needs aux[6] as an array", ocb_diag_name(q.diag));
     if (needs & OCB_NEED_AUX5) OCB_REQUIRE(I.aux[5].p, "%s needs aux[5] as an array", ocb_diag_name(q.diag));
+    if (needs & OCB_NEED_AUX4) OCB_REQUIRE(I.aux[4].p, "%s needs aux[4] as an array", ocb_diag_name(q.diag));
     if (needs & OCB_NEED_AUX05) {
       const bool d1 = q.diag != OCB_DIAG_PI || (q.flags & OCB_REQ_TENSOR_DIM1), d2 = q.diag != OCB_DIAG_PI || (q.flags & OCB_REQ_TENSOR_DIM2),
                  d3 = q.diag != OCB_DIAG_PI || (q.flags & OCB_REQ_TENSOR_DIM3);

@@ -337,6 +337,26 @@ def tracer_variance_dissipation_rate_ccc(i, j, k, g, *args):   # :157-161
                 iz_aac(i, j, k, g, _Az_dc_q3, *args)) / V_ccc(i, j, k, g)
 
 
+# --- AvailablePotentialEnergyEquation ---------------------------------------------------------------
+def local_ape_ccc(i, j, k, g, psi_delta, b, zstar):          # src/AvailablePotentialEnergyEquation.jl:42
+    return psi_delta[i, j, k] - b[i, j, k] * (g.node(2, "c", k) - zstar[i, j, k])
+
+
+def upsilon_ccc(i, j, k, g, zstar):                          # src/AvailablePotentialEnergyEquation.jl:126
+    return zstar[i, j, k] - g.node(2, "c", k)
+
+
+def _Ax_dY_q1(i, j, k, g, Y, cl, K, idv, c, *a): return -Ax_fcc(i, j, k, g) * dx_faa(i, j, k, g, Y) * diffusive_flux_x(i, j, k, g, cl, K, idv, c, *a)   # :202-203
+def _Ay_dY_q2(i, j, k, g, Y, cl, K, idv, c, *a): return -Ay_cfc(i, j, k, g) * dy_afa(i, j, k, g, Y) * diffusive_flux_y(i, j, k, g, cl, K, idv, c, *a)   # :205-206
+def _Az_dY_q3(i, j, k, g, Y, cl, K, idv, c, *a): return -Az_ccf(i, j, k, g) * dz_aaf(i, j, k, g, Y) * diffusive_flux_z(i, j, k, g, cl, K, idv, c, *a)   # :208-209
+
+
+def ape_dissipation_rate_ccc(i, j, k, g, *args):             # src/AvailablePotentialEnergyEquation.jl:211-215
+    return (ix_caa(i, j, k, g, _Ax_dY_q1, *args) +
+            iy_aca(i, j, k, g, _Ay_dY_q2, *args) +
+            iz_aac(i, j, k, g, _Az_dY_q3, *args)) / V_ccc(i, j, k, g)
+
+
 # --- FlowDiagnostics --------------------------------------------------------------------------------
 def w2_from_u_tilted_ccc(i, j, k, g, u, v, w, vdir):          # src/FlowDiagnostics.jl:36-41
     uh = ix_caa(i, j, k, g, u)

@@ -77,6 +77,29 @@ def build_cases(st: State, closure_name="scalar", mean="profile"):
         ("QVelocityGradientTensorInvariant", FD.QVelocityGradientTensorInvariant(m),
          ev(K.Q_velocity_gradient_tensor_invariant_ccc, og, "ccc", st.ou, st.ov, st.ow), "ccc"),
     ]
+    # available-potential-energy family (scope table 8f): z✶ and Ψδ come from the oracle's sorted reference state and are
+    # handed to both sides as fields, so these cases test the pointwise / flux kernels, not the sort (tests/test_bpe_gpu.py)
+    from oracle import bpe as OB
+    from oracle.grid import OField
+    ref = OB.reference_height(st.ob, "HeavisideIntegral")
+
+    def ofield(values):
+        f = OField(og, "ccc")
+        f.interior[...] = values
+        f.fill_halo()
+        return f
+    ozs, opsi = ofield(ref["zstar"]), ofield(ref["psi_delta"])
+    oups = ofield(ev(K.upsilon_ccc, og, "ccc", ozs))
+    pzs, ppsi, pups = mirror(ozs, st.pg), mirror(opsi, st.pg), mirror(oups, st.pg)
+    KFO, SO = ocb.KernelFunctionOperation, ocb.SweepOperands
+    cases += [
+        ("AvailablePotentialEnergy", KFO("APE", st.pg, SO(b=st.b, aux={5: ppsi, 6: pzs}), name="AvailablePotentialEnergy"),
+         ev(K.local_ape_ccc, og, "ccc", opsi, st.ob, ozs), "ccc"),
+        ("BuoyancyDisplacementPotential", KFO("UPSILON", st.pg, SO(aux={6: pzs}), name="BuoyancyDisplacementPotential"),
+         ev(K.upsilon_ccc, og, "ccc", ozs), "ccc"),
+        ("AvailablePotentialEnergyDissipationRate", KFO("APE_EPS", st.pg, SO(b=st.b, aux={4: pups}, closure=pc), name="AvailablePotentialEnergyDissipationRate"),
+         ev(K.ape_dissipation_rate_ccc, og, "ccc", oups, oc, None, None, st.ob), "ccc"),
+    ]
     S, O = FD.StrainRateTensor(m), FD.VorticityTensor(m)
     T, Tc = FD.StressTensor(m), FD.StressTensor(m, collocate_diagonals=True)
     comp_args = {(1, 1): (st.ou,), (2, 2): (st.ov,), (3, 3): (st.ow,), (1, 2): (st.ou, st.ov), (1, 3): (st.ou, st.ow), (2, 3): (st.ov, st.ow)}

@@ -585,3 +585,72 @@ def test_bpe_heaviside_is_identity_on_stable_stratification_and_runs_stretched()
     assert np.all(np.isfinite(rr["zstar"])) and rr["zstar"].min() >= zb and rr["zstar"].max() <= zt
     zc = np.broadcast_to(gs.node(2, "c", gs.indices("ccc")[2]), rr["zstar"].shape)
     assert K.average(rr["zstar"], gs, "ccc") == pytest.approx(K.average(zc, gs, "ccc"), abs=1e-8)
+
+
+# ----------------------------------------------------------------------------- APE (scope table 8f, row 1)
+def _as_field(grid, values):
+    f = OField(grid, "ccc")
+    f.interior[...] = values
+    f.fill_halo()
+    return f
+
+
+def test_ape_two_cell_column_known_answers():
+    """test/test_ape_diagnostics.jl:85-107: ∫E_p = +0.25, ∫E_b = -0.25, ∫E_a = +0.50 for the unstable column; the
+    stable column holds no available potential energy."""
+    g = OGrid(2, z=(-1, 0), topology=("F", "F", "B"))
+    b = OField(g, "ccc")
+    b.interior[0, 0, :] = [1.0, -1.0]
+    r = OB.reference_height(b)
+    z = g.node(2, "c", np.arange(1, 3))
+    assert K.integral(-b.interior * z.reshape(1, 1, 2), g, "ccc") == pytest.approx(0.25)
+    psi, zs = _as_field(g, r["psi_delta"]), _as_field(g, r["zstar"])
+    Ea = K.evaluate(K.local_ape_ccc, g, "ccc", psi, b, zs)
+    assert K.integral(Ea, g, "ccc") == pytest.approx(0.50)
+    b.interior[0, 0, :] = [-1.0, 1.0]
+    r = OB.reference_height(b)
+    Ea = K.evaluate(K.local_ape_ccc, g, "ccc", _as_field(g, r["psi_delta"]), b, _as_field(g, r["zstar"]))
+    assert abs(K.integral(Ea, g, "ccc")) <= 1e-14
+
+
+@pytest.mark.parametrize("method", ["ThreeDimensionalSort", "HeavisideIntegral"])
+def test_ape_vanishes_when_sorted_and_is_nonnegative(method):
+    """test/test_ape_diagnostics.jl:108-122 (b = 3z is its own sorted state) and :61-76 (e_a >= 0, mean z✶ = mean z)."""
+    g = OGrid((4, 3, 8), x=(0, 1), y=(0, 1), z=(-1, 0), topology=("P", "P", "B"))
+    b = OField(g, "ccc")
+    b.set(lambda x, y, z: 3 * z + 0 * x)
+    b.fill_halo()
+    r = OB.reference_height(b, method)
+    Ea = K.evaluate(K.local_ape_ccc, g, "ccc", _as_field(g, r["psi_delta"]), b, _as_field(g, r["zstar"]))
+    Ep = K.integral(-b.interior * g.node(2, "c", np.arange(1, 9)).reshape(1, 1, 8), g, "ccc")
+    assert abs(K.integral(Ea, g, "ccc")) <= np.sqrt(np.finfo(float).eps) * abs(Ep)
+    b.interior[...] = np.random.default_rng(5).standard_normal(b.interior.shape)
+    b.fill_halo()
+    r = OB.reference_height(b, method)
+    zs = _as_field(g, r["zstar"])
+    Ea = K.evaluate(K.local_ape_ccc, g, "ccc", _as_field(g, r["psi_delta"]), b, zs)
+    assert Ea.min() > -np.sqrt(np.finfo(float).eps) * np.abs(b.interior).max()
+    ups = K.evaluate(K.upsilon_ccc, g, "ccc", zs)                      # :541-563: Υ = z✶ - z, zero volume mean
+    np.testing.assert_allclose(ups, r["zstar"] - g.node(2, "c", np.arange(1, 9)).reshape(1, 1, 8), rtol=0, atol=1e-15)
+    assert abs(K.average(ups, g, "ccc")) <= np.sqrt(np.finfo(float).eps)
+
+
+def test_ape_dissipation_matches_tracer_variance_discretization():
+    """test/test_ape_diagnostics.jl:565-587: handed b in place of Υ, ε_a = χ / 2 to roundoff; :592-608: it vanishes for a
+    sorted state."""
+    from oracle.kernels import Closure
+    g = OGrid((5, 4, 6), x=(0, 1), y=(0, 1), z=(-1, 0), topology=("P", "P", "B"))
+    b = OField(g, "ccc")
+    b.interior[...] = np.random.default_rng(7).standard_normal(b.interior.shape)
+    b.fill_halo()
+    cl = Closure(nu=1e-6, kappa=1e-3)
+    eps_a = K.evaluate(K.ape_dissipation_rate_ccc, g, "ccc", b, cl, None, None, b)
+    chi = K.evaluate(K.tracer_variance_dissipation_rate_ccc, g, "ccc", cl, None, None, b)
+    np.testing.assert_allclose(eps_a, chi / 2, rtol=1e-13, atol=1e-18)
+    b.set(lambda x, y, z: 3 * z + 0 * x)
+    b.fill_halo()
+    r = OB.reference_height(b, "HeavisideIntegral")
+    ups = _as_field(g, r["zstar"] - g.node(2, "c", np.arange(1, 7)).reshape(1, 1, 6))
+    chi = K.evaluate(K.tracer_variance_dissipation_rate_ccc, g, "ccc", cl, None, None, b)
+    eps_a = K.evaluate(K.ape_dissipation_rate_ccc, g, "ccc", ups, cl, None, None, b)
+    assert chi.max() > 0 and np.abs(eps_a).max() < np.sqrt(np.finfo(float).eps) * chi.max() / 2
