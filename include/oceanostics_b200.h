@@ -144,7 +144,9 @@ enum {
                                  perturbation_fields (src/Oceanostics.jl:157-173) / lazy `u-U` operands
                                  (src/TurbulentKineticEnergyEquation.jl:89-95, 327-330) evaluated on the fly */
   OCB_REQ_TENSOR_DIM1 = 1 << 4, OCB_REQ_TENSOR_DIM2 = 1 << 5, OCB_REQ_TENSOR_DIM3 = 1 << 6,  /* `dims` of PI (default all three) */
-  OCB_REQ_COLLOCATED = 1 << 7  /* PI built with collocate_diagonals=true */
+  OCB_REQ_COLLOCATED = 1 << 7, /* PI built with collocate_diagonals=true */
+  OCB_REQ_CARRIED_HEIGHT = 1 << 8  /* APE on a VerticalSort column: the parcel's own height is the field aux[3], not the grid's z
+                                      (4-argument local_ape_ccc, AvailablePotentialEnergyEquation.jl:43) */
 };
 
 typedef struct {
@@ -238,6 +240,14 @@ enum { OCB_BPE_THREE_DIMENSIONAL_SORT = 0, OCB_BPE_HEAVISIDE_INTEGRAL = 1 };
 int ocb_bpe_reference_height(const ocb_grid* grid, const ocb_field* b, int32_t method,
                              const ocb_field* zstar, const ocb_field* psi_delta,
                              int64_t* perm_out, void* b_sorted_out, void* stream);
+/* VerticalSort (BackgroundPotentialEnergyEquation.jl:584-597): a model-grid ccc field read in sorted order,
+ * dst[r] = src[perm[r]] with the 1-based `sortperm!` ranks ocb_bpe_reference_height returns (s.source_height[perm], z✶, Ψδ). */
+int ocb_gather_sorted(int32_t dtype, const ocb_field* src, const int64_t* perm, void* dst, int64_t n, void* stream);
+/* assign_reference_height!(::ProfileLookup) (BackgroundPotentialEnergyEquation.jl:550-582): match every cell to a sorted
+ * profile (b_profile, z_profile: device FT[m], both non-decreasing -- validated by the host as lookup_profile :528-547
+ * does) by binary search; slot faces are the midpoints of z_profile closed by the domain's bottom and top (:497-507). */
+int ocb_bpe_profile_lookup(const ocb_grid* grid, const ocb_field* b, const void* b_profile, const void* z_profile,
+                           int64_t m, const ocb_field* zstar, const ocb_field* psi_delta, void* stream);
 /* the radix sort alone (keys FT[n] -> sorted keys + 0-based permutation), exposed for tests/benchmarks */
 int ocb_sort_pairs(int32_t dtype, const void* keys_in, void* keys_out, uint32_t* perm_out,
                    int64_t n, void* stream);

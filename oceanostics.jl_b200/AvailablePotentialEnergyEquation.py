@@ -7,23 +7,27 @@ Same constructors as the reference: `AvailablePotentialEnergy(model; method)` / 
 `(model, z✶; upsilon)`; each returns a KernelFunctionOperation that `Field(op)` / `Integral(op)` accept."""
 from __future__ import annotations
 
+from . import _lib
 from .fields import Field
 from .operations import KernelFunctionOperation, SweepOperands
 from .models import validate_location
-from .BackgroundPotentialEnergyEquation import (BackgroundPotentialEnergy, SortedReferenceHeightField, reference_height,  # noqa: F401
+from .BackgroundPotentialEnergyEquation import (BackgroundPotentialEnergy, SortedReferenceHeightField, SortedColumnField, reference_height,  # noqa: F401
                                                 ThreeDimensionalSort, HeavisideIntegral, VerticalSort, ProfileLookup,
                                                 validate_gravity_is_z_aligned)
 from .TracerVarianceEquation import _tracer
 from .KineticEnergyEquation import PotentialEnergyConversion as PotentialToKineticEnergyConversion  # noqa: F401  (w b)
 
 
-def _zstar(name, model, zstar, method, default):
+def _zstar(name, model, zstar, method, default, column_ok=False):
     validate_gravity_is_z_aligned(name, model)
     if zstar is None:
         zstar = reference_height(model, method=method if method is not None else default)
-    if not isinstance(zstar, SortedReferenceHeightField):
+    if not isinstance(zstar, (SortedReferenceHeightField, SortedColumnField)):
         raise TypeError(f"{name}(model, z✶) takes the field returned by reference_height")
-    if zstar.grid is not model.grid:
+    if isinstance(zstar, SortedColumnField):
+        if not column_ok:                                 # validate_reference_height_grid
+            raise ValueError(f"{name} needs a reference height on the model grid; a `VerticalSort` column lives on its own 1×1×N grid")
+    elif zstar.grid is not model.grid:
         raise ValueError(f"{name}: the reference height was computed on another grid than the model's")
     return zstar
 
@@ -31,8 +35,13 @@ def _zstar(name, model, zstar, method, default):
 def AvailablePotentialEnergy(model, zstar=None, method=None, location=("c", "c", "c")):
     """e_a = Ψ(z) - Ψ(z✶) - b (z - z✶)  (local_ape_ccc, :42-45; constructors :99-111)."""
     validate_location(location, "AvailablePotentialEnergy")
-    zstar = _zstar("AvailablePotentialEnergy", model, zstar, method, ThreeDimensionalSort())
-    return KernelFunctionOperation("APE", zstar.grid, SweepOperands(b=zstar.buoyancy, aux={5: zstar.reference_potential, 6: zstar}),
+    zstar = _zstar("AvailablePotentialEnergy", model, zstar, method, ThreeDimensionalSort(), column_ok=True)
+    aux = {5: zstar.reference_potential, 6: zstar}
+    flags = 0
+    if isinstance(zstar, SortedColumnField):              # on a column the parcel's own height is a carried field (:43)
+        aux[3] = zstar.sorted_height
+        flags = _lib.OCB_REQ_CARRIED_HEIGHT
+    return KernelFunctionOperation("APE", zstar.grid, SweepOperands(b=zstar.buoyancy, aux=aux), flags=flags,
                                    name="AvailablePotentialEnergy",
                                    computes="local available potential energy density  e_a = ∫ [b✶(z̃) - b] dz̃ from z✶ to z")
 

@@ -22,6 +22,7 @@ OCB_MAX_FILTER_WIDTH = 64
 OCB_REQ_PERTURBATION = 1
 OCB_REQ_TENSOR_DIM1, OCB_REQ_TENSOR_DIM2, OCB_REQ_TENSOR_DIM3 = 1 << 4, 1 << 5, 1 << 6
 OCB_REQ_COLLOCATED = 1 << 7
+OCB_REQ_CARRIED_HEIGHT = 1 << 8
 
 _DIAG_NAMES = [
     "KE", "ADV", "PR", "WB", "EPS", "EPS_ISO", "TKE", "SPX", "SPY", "SPZ", "SP", "CHI", "CDIFF", "SMOD", "OMOD", "Q",
@@ -115,12 +116,15 @@ def lib():
     L.ocb_bpe_reference_height.argtypes = [P(ocb_grid), P(ocb_field), C.c_int32, P(ocb_field), P(ocb_field),
                                            C.c_void_p, C.c_void_p, C.c_void_p]
     L.ocb_sort_pairs.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    L.ocb_gather_sorted.argtypes = [C.c_int32, P(ocb_field), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    L.ocb_bpe_profile_lookup.argtypes = [P(ocb_grid), P(ocb_field), C.c_void_p, C.c_void_p, C.c_int64, P(ocb_field), P(ocb_field),
+                                         C.c_void_p]
     L.ocb_pointwise.argtypes = [P(ocb_grid), C.c_int32, C.c_double, P(ocb_field), P(ocb_field), P(ocb_field), C.c_void_p]
     L.ocb_halo_pack_y.argtypes = [C.c_int32, P(ocb_field), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     L.ocb_halo_unpack_y.argtypes = [C.c_int32, P(ocb_field), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     for name in ("ocb_plan_create", "ocb_plan_execute", "ocb_plan_destroy", "ocb_plan_info", "ocb_fill_halo",
                  "ocb_filter_execute", "ocb_bpe_reference_height", "ocb_sort_pairs", "ocb_pointwise",
-                 "ocb_halo_pack_y", "ocb_halo_unpack_y"):
+                 "ocb_halo_pack_y", "ocb_halo_unpack_y", "ocb_gather_sorted", "ocb_bpe_profile_lookup"):
         getattr(L, name).restype = C.c_int
     if L.ocb_abi_version() != 1:
         raise OcbError("liboceanostics_b200.so ABI version mismatch")
@@ -130,7 +134,8 @@ def lib():
 
 EXPORTED_SYMBOLS = ["ocb_abi_version", "ocb_last_error", "ocb_device_count", "ocb_plan_create", "ocb_plan_execute",
                     "ocb_plan_destroy", "ocb_plan_info", "ocb_fill_halo", "ocb_filter_execute",
-                    "ocb_bpe_reference_height", "ocb_sort_pairs", "ocb_pointwise", "ocb_halo_pack_y", "ocb_halo_unpack_y"]
+                    "ocb_bpe_reference_height", "ocb_sort_pairs", "ocb_pointwise", "ocb_halo_pack_y", "ocb_halo_unpack_y",
+                    "ocb_gather_sorted", "ocb_bpe_profile_lookup"]
 
 
 def check(status: int):

@@ -513,7 +513,143 @@ int bpe_impl(const ocb_grid* g, const ocb_field* b, int method, const ocb_field*
   return OCB_OK;
 }
 
+// ---- VerticalSort / ProfileLookup (scope table 8f) --------------------------------------------------------------------
+// gather of a model-grid field into sorted order: dst[r] = field[perm[r]]  (s.source_height[perm], BPE :584-597)
+template <class T>
+__global__ void bpe_gather_perm(const T* __restrict__ f1, long long s0, long long s1, long long s2, int Nx, int Ny, const int64_t* __restrict__ perm,
+                                long long n, T* __restrict__ dst) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;   // f1 pre-offset to index (1,1,1)
+  if (t >= n) return;
+  const long long c = perm[t] - 1;                                         // sortperm ranks are 1-based
+  const int i = (int)(c % Nx), j = (int)((c / Nx) % Ny);
+  const long long k = c / ((long long)Nx * Ny);
+  dst[t] = f1[i * s0 + j * s1 + k * s2];
+}
+
+// profile_slot_faces (:497-507): midpoints between neighbouring heights, closed by the bottom and top of the domain;
+// and the Ψ increments b✶[m] (faces[m+1] - faces[m]) of reference_potential_function (:359-368)
+template <class T>
+__global__ void bpe_profile_faces(const T* __restrict__ z, long long M, T z_bot, T z_top, T* __restrict__ faces) {
+  const long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (m > M) return;
+  faces[m] = m == 0 ? z_bot : (m == M ? z_top : (z[m - 1] + z[m]) / T(2));
+}
+template <class T>
+__global__ void bpe_profile_increments(const T* __restrict__ bs, const T* __restrict__ faces, long long M, double* __restrict__ inc) {
+  const long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (m < M) inc[m] = (double)bs[m] * ((double)faces[m + 1] - (double)faces[m]);
+}
+// 1-based searchsortedfirst / searchsortedlast over a non-decreasing array a[0..M)
+template <class T> __device__ __forceinline__ long long ss_first(const T* a, long long M, T x) {   // first idx with a[idx] >= x, M+1 if none
+  long long lo = 0, hi = M;
+  while (lo < hi) { const long long mid = (lo + hi) >> 1; if (a[mid] < x) lo = mid + 1; else hi = mid; }
+  return lo + 1;
+}
+template <class T> __device__ __forceinline__ long long ss_last(const T* a, long long M, T x) {    // last idx with a[idx] <= x, 0 if none
+  long long lo = 0, hi = M;
+  while (lo < hi) { const long long mid = (lo + hi) >> 1; if (a[mid] <= x) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+// assign_reference_height!(::ProfileLookup) (:550-582): every cell takes the mid-height of the run of slots of its
+// buoyancy class, and Ψδ = Ψ(z) - Ψ(z✶) through the profile's own piecewise-linear Ψ
+template <class T>
+__global__ void bpe_profile_lookup(const T* __restrict__ b1, long long bs0, long long bs1, long long bs2, int Nx, int Ny, long long n,
+                                   const T* __restrict__ bs, const T* __restrict__ faces, const double* __restrict__ psi_face, long long M,
+                                   const T* __restrict__ zc1, T z_bot, T dz, T* __restrict__ z1, long long zs0, long long zs1, long long zs2,
+                                   T* __restrict__ p1, long long ps0, long long ps1, long long ps2) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int i = (int)(t % Nx), j = (int)((t / Nx) % Ny);
+  const long long k = t / ((long long)Nx * Ny);
+  const T b = b1[i * bs0 + j * bs1 + k * bs2];
+  long long lo = ss_first(bs, M, b);
+  lo = lo < 1 ? 1 : (lo > M ? M : lo);
+  const long long lol = lo - 1 < 1 ? 1 : lo - 1;
+  const T dl = bs[lol - 1] - b, dh = bs[lo - 1] - b;
+  const T bclass = (dl < 0 ? -dl : dl) < (dh < 0 ? -dh : dh) ? bs[lol - 1] : bs[lo - 1];
+  const long long rf = ss_first(bs, M, bclass), rl = ss_last(bs, M, bclass);
+  const T zstar = (faces[rf - 1] + faces[rl]) / T(2);                      // faces[run_first], faces[run_last + 1] (1-based)
+  z1[i * zs0 + j * zs1 + k * zs2] = zstar;
+  if (p1) {
+    auto psi = [&](T zeta) {
+      long long kk = ss_last(faces, M + 1, zeta);
+      kk = kk < 1 ? 1 : (kk > M ? M : kk);
+      return psi_face[kk - 1] + (double)bs[kk - 1] * ((double)zeta - (double)faces[kk - 1]);
+    };
+    const T zsrc = zc1 ? zc1[k] : (T)(z_bot + (T(k) + T(0.5)) * dz);
+    p1[i * ps0 + j * ps1 + k * ps2] = (T)(psi(zsrc) - psi(zstar));
+  }
+}
+
+template <class T>
+int gather_impl(const ocb_field* src, const int64_t* perm, T* dst, long long n, cudaStream_t st) {
+  HFld<T> F;
+  int rc = make_fld<T>(*src, &F, "src", false);
+  if (rc != OCB_OK) return rc;
+  const int Nx = src->size[0] - 2 * src->halo[0], Ny = src->size[1] - 2 * src->halo[1], Nz = src->size[2] - 2 * src->halo[2];
+  OCB_REQUIRE((long long)Nx * Ny * Nz == n, "ocb_gather_sorted: the permutation has %lld entries, the field %lld cells", n, (long long)Nx * Ny * Nz);
+  const T* f1 = F.p + (F.sx + F.sy + F.sz);
+  bpe_gather_perm<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(f1, F.sx, F.sy, F.sz, Nx, Ny, perm, n, dst);
+  OCB_CUDA(cudaGetLastError());
+  return OCB_OK;
+}
+
+template <class T>
+int lookup_impl(const ocb_grid* g, const ocb_field* b, const T* bs, const T* zprof, long long M, const ocb_field* zstar, const ocb_field* psid,
+                cudaStream_t st) {
+  Scratch S(st);
+  const int Nx = g->N[0], Ny = g->N[1], Nz = g->N[2];
+  const long long n = (long long)Nx * Ny * Nz;
+  HFld<T> B, Z, P;
+  int rc = make_fld<T>(*b, &B, "b", false); if (rc != OCB_OK) return rc;
+  rc = make_fld<T>(*zstar, &Z, "zstar", false); if (rc != OCB_OK) return rc;
+  P.p = nullptr;
+  if (psid && psid->data) { rc = make_fld<T>(*psid, &P, "psi_delta", false); if (rc != OCB_OK) return rc; }
+  T* faces = S.get<T>(M + 1);
+  double* inc = S.get<double>(M + 1);
+  double* psi_face = S.get<double>(M + 1);
+  double* tot = S.get<double>((M + SC_CHUNK - 1) / SC_CHUNK + 1);
+  if (!faces || !inc || !psi_face || !tot) OCB_FAIL(OCB_ERR_ALLOC, "out of device memory for the profile-lookup scratch");
+  const unsigned gm = (unsigned)((M + 1 + 255) / 256), gn = (unsigned)((n + 255) / 256);
+  bpe_profile_faces<T><<<gm, 256, 0, st>>>(zprof, M, (T)g->z_bottom, (T)(g->z_bottom + g->L[2]), faces);
+  bpe_profile_increments<T><<<gm, 256, 0, st>>>(bs, faces, M, inc);
+  OCB_CUDA(cudaMemsetAsync(psi_face, 0, sizeof(double), st));
+  rc = device_scan<double, OP_ADD, false, false>(inc, psi_face + 1, M, tot, st);     // Ψ at the faces: inclusive sums behind a leading 0
+  if (rc != OCB_OK) return rc;
+  const T* zc1 = g->zc ? (const T*)g->zc + g->H[2] : nullptr;
+  bpe_profile_lookup<T><<<gn, 256, 0, st>>>(B.p + (B.sx + B.sy + B.sz), B.sx, B.sy, B.sz, Nx, Ny, n, bs, faces, psi_face, M, zc1, (T)g->z_bottom,
+                                            (T)g->d[2], (T*)Z.p + (Z.sx + Z.sy + Z.sz), Z.sx, Z.sy, Z.sz,
+                                            P.p ? (T*)P.p + (P.sx + P.sy + P.sz) : nullptr, P.sx, P.sy, P.sz);
+  OCB_CUDA(cudaGetLastError());
+  return OCB_OK;
+}
+
 }  // namespace
+
+extern "C" int ocb_gather_sorted(int32_t dtype, const ocb_field* src, const int64_t* perm, void* dst, int64_t n, void* stream) {
+  OCB_REQUIRE(src && perm && dst && n >= 0, "ocb_gather_sorted: bad argument");
+  OCB_REQUIRE(src->kind == OCB_FIELD_ARRAY && src->data, "ocb_gather_sorted: the source must be an array field");
+  OCB_REQUIRE(dtype == OCB_F32 || dtype == OCB_F64, "bad dtype");
+  int rc = ocb_require_device();
+  if (rc != OCB_OK) return rc;
+  if (n == 0) return OCB_OK;
+  return dtype == OCB_F64 ? gather_impl<double>(src, perm, (double*)dst, n, (cudaStream_t)stream)
+                          : gather_impl<float>(src, perm, (float*)dst, n, (cudaStream_t)stream);
+}
+
+extern "C" int ocb_bpe_profile_lookup(const ocb_grid* grid, const ocb_field* b, const void* b_profile, const void* z_profile, int64_t m,
+                                      const ocb_field* zstar, const ocb_field* psi_delta, void* stream) {
+  OCB_REQUIRE(grid && b && b_profile && z_profile && zstar, "ocb_bpe_profile_lookup: null argument");
+  OCB_REQUIRE(m >= 1, "`ProfileLookup` needs a profile with at least one slot");
+  OCB_REQUIRE(b->kind == OCB_FIELD_ARRAY && b->data && zstar->kind == OCB_FIELD_ARRAY && zstar->data, "b and zstar must be array fields");
+  for (int d = 0; d < 3; ++d) OCB_REQUIRE(b->loc[d] == OCB_CENTER && zstar->loc[d] == OCB_CENTER, "b and zstar must be (Center, Center, Center) fields");
+  int rc = ocb_require_device();
+  if (rc != OCB_OK) return rc;
+  ocb_keep_scratch_pool();
+  cudaStream_t st = (cudaStream_t)stream;
+  return grid->dtype == OCB_F64 ? lookup_impl<double>(grid, b, (const double*)b_profile, (const double*)z_profile, m, zstar, psi_delta, st)
+                                : lookup_impl<float>(grid, b, (const float*)b_profile, (const float*)z_profile, m, zstar, psi_delta, st);
+}
 
 extern "C" int ocb_sort_pairs(int32_t dtype, const void* keys_in, void* keys_out, uint32_t* perm_out, int64_t n, void* stream) {
   OCB_REQUIRE(keys_in && n >= 0 && n < (1ll << 32), "ocb_sort_pairs: bad argument");

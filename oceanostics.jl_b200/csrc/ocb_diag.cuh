@@ -521,7 +521,11 @@ OCB_EVAL(OCB_DIAG_PI) {
 // minus_bz✶_ccc  (src/BackgroundPotentialEnergyEquation.jl:852)
 OCB_EVAL(OCB_DIAG_BPE) { return -X.in.b(i, j, k) * X.in.aux[6](i, j, k); } };
 // local_ape_ccc  (src/AvailablePotentialEnergyEquation.jl:42-45): Ψδ - b (z - z✶)
-OCB_EVAL(OCB_DIAG_APE) { return X.in.aux[5](i, j, k) - X.in.b(i, j, k) * (OCB_LD(X.g.zc + k) - X.in.aux[6](i, j, k)); } };
+// (the parcel's own height is the grid's Zᶜᶜᶜ on the model grid, a carried field -- aux[3], flagged -- on a VerticalSort column, :43)
+OCB_EVAL(OCB_DIAG_APE) {
+  const T z = (flags & OCB_REQ_CARRIED_HEIGHT) ? X.in.aux[3](i, j, k) : OCB_LD(X.g.zc + k);
+  return X.in.aux[5](i, j, k) - X.in.b(i, j, k) * (z - X.in.aux[6](i, j, k));
+} };
 
 // upsilon_ccc  (src/AvailablePotentialEnergyEquation.jl:126): Υ = z✶ - z, with aux[6] = z✶
 OCB_EVAL(OCB_DIAG_UPSILON) { return X.in.aux[6](i, j, k) - OCB_LD(X.g.zc + k); } };

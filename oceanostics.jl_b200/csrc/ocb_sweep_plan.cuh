@@ -118,6 +118,7 @@ static int ocb_build_sweep_params(const ocb_grid* grid, const ocb_sweep_inputs* 
     if (needs & OCB_NEED_AUX6) OCB_REQUIRE(I.aux[6].p, "%s needs aux[6] as an array", ocb_diag_name(q.diag));
     if (needs & OCB_NEED_AUX5) OCB_REQUIRE(I.aux[5].p, "%s needs aux[5] as an array", ocb_diag_name(q.diag));
     if (needs & OCB_NEED_AUX4) OCB_REQUIRE(I.aux[4].p, "%s needs aux[4] as an array", ocb_diag_name(q.diag));
+    if (q.diag == OCB_DIAG_APE && (q.flags & OCB_REQ_CARRIED_HEIGHT)) OCB_REQUIRE(I.aux[3].p, "APE with a carried height needs aux[3] as an array");
     if (needs & OCB_NEED_AUX05) {
       const bool d1 = q.diag != OCB_DIAG_PI || (q.flags & OCB_REQ_TENSOR_DIM1), d2 = q.diag != OCB_DIAG_PI || (q.flags & OCB_REQ_TENSOR_DIM2),
                  d3 = q.diag != OCB_DIAG_PI || (q.flags & OCB_REQ_TENSOR_DIM3);

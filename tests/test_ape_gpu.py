@@ -115,3 +115,84 @@ def test_constructor_errors():
         APE.AvailablePotentialEnergyDissipationRate(m)         # no closure: no diffusive flux
     with pytest.raises(ValueError):
         APE.AvailablePotentialEnergy(m, location=("f", "c", "c"))
+
+
+def _stride_scrambled(values, shape):
+    N = values.size
+    scr = np.zeros(N)
+    for m in range(N):
+        scr[(7 * m) % N] = values[m]                     # a bijection when gcd(7, N) = 1
+    return scr.reshape(shape, order="F")
+
+
+def test_vertical_sort_column_known_profile():
+    """:280-298 and :405-441: the sorted column on its 1 x 1 x N grid recovers the tanh profile, integrates like the model
+    grid, keeps the topology, and BackgroundPotentialEnergy / AvailablePotentialEnergy accept it."""
+    Nx, Ny, Nz = 4, 3, 5
+    N, Lz = Nx * Ny * Nz, 1.0
+    zs = -Lz + (np.arange(1, N + 1) - 0.5) * Lz / N
+    bs = 0.1 * np.tanh((zs + Lz / 2) / 0.2)
+    og, pg, ob, pb = _pair((Nx, Ny, Nz), (-Lz, 0), _stride_scrambled(bs, (Nx, Ny, Nz)))
+    m = _model(pg, pb)
+    col = APE.reference_height(m, method=BPE.VerticalSort())
+    torch.cuda.synchronize()
+    assert col.interior_ijk().shape == (1, 1, N) and col.grid.user_topology == pg.user_topology
+    want = OB.vertical_sort(ob)
+    np.testing.assert_allclose(col.interior_ijk().ravel(), zs, rtol=1e-13)
+    np.testing.assert_array_equal(col.reference_buoyancy.interior_ijk().ravel(), bs)
+    np.testing.assert_allclose(col.sorted_height.interior_ijk().ravel(), want["sorted_height"], rtol=0, atol=1e-15)
+    np.testing.assert_allclose(col.reference_potential.interior_ijk().ravel(), want["psi_delta"], rtol=1e-12, atol=1e-16)
+    ranked = APE.reference_height(m)
+    eb_col, eb_rank = _integral(APE.BackgroundPotentialEnergy(m, col)), _integral(APE.BackgroundPotentialEnergy(m, ranked))
+    assert eb_col == pytest.approx(float(np.sum(-bs * zs) * (1.0 / N)), rel=1e-12) and eb_col == pytest.approx(eb_rank, rel=1e-12)
+    assert _integral(APE.AvailablePotentialEnergy(m, col)) == pytest.approx(_integral(APE.AvailablePotentialEnergy(m, ranked)), rel=1e-10)
+    with pytest.raises(ValueError):
+        APE.BuoyancyDisplacementPotential(m, col)          # Υ needs z✶ on the model grid
+
+
+def test_profile_lookup_three_ways_matches_the_ranked_sort():
+    """:226-275: ProfileLookup(), ProfileLookup(column), ProfileLookup(b✶, z✶) reproduce ThreeDimensionalSort on a tie-free
+    field; malformed profiles are rejected with the reference's messages."""
+    Nx, Ny, Nz = 3, 2, 4
+    N = Nx * Ny * Nz
+    og, pg, ob, pb = _pair((Nx, Ny, Nz), (-1, 0), _stride_scrambled(-0.5 + np.arange(N) / (N - 1), (Nx, Ny, Nz)))
+    m = _model(pg, pb)
+    ranked = APE.reference_height(m)
+    eb, ea = _integral(APE.BackgroundPotentialEnergy(m, ranked)), _integral(APE.AvailablePotentialEnergy(m, ranked))
+    col = APE.reference_height(m, method=BPE.VerticalSort())
+    bstar = col.reference_buoyancy.interior.reshape(-1).clone()
+    zprof = col.interior.reshape(-1).clone()
+    want = OB.profile_lookup(ob, bstar.cpu().numpy(), zprof.cpu().numpy())
+    for method in (BPE.ProfileLookup(), BPE.ProfileLookup(col), BPE.ProfileLookup(bstar, zprof)):
+        z = APE.reference_height(m, method=method)
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(z.interior_ijk(), ranked.interior_ijk(), rtol=1e-13)
+        np.testing.assert_allclose(z.interior_ijk(), want["zstar"], rtol=1e-13)
+        np.testing.assert_allclose(z.reference_potential.interior_ijk(), want["psi_delta"], rtol=1e-11, atol=1e-15)
+        assert _integral(APE.BackgroundPotentialEnergy(m, z)) == pytest.approx(eb, rel=1e-12)
+        assert _integral(APE.AvailablePotentialEnergy(m, z)) == pytest.approx(ea, rel=1e-10)
+        e = ocb.Field(APE.AvailablePotentialEnergy(m, z)).compute().interior_ijk()
+        assert e.min() > -np.sqrt(np.finfo(np.float64).eps) * max(np.abs(e).max(), np.finfo(np.float64).eps)
+    for msg, bad in (("buoyancy and height have different", BPE.ProfileLookup(bstar[:-1], zprof)),
+                     ("ordered from the densest fluid up", BPE.ProfileLookup(bstar.flip(0), zprof)),
+                     ("heights paired with", BPE.ProfileLookup(bstar, zprof.flip(0)))):
+        with pytest.raises(ValueError, match=msg):
+            APE.reference_height(m, method=bad)
+    with pytest.raises(TypeError):
+        APE.reference_height(m, method=BPE.ProfileLookup(3.0))
+
+
+def test_profile_lookup_with_ties_against_the_oracle():
+    """Tied buoyancy classes: every cell of a class takes the mid-height of the class's run of slots (:556-571)."""
+    rng = np.random.default_rng(23)
+    Nx, Ny, Nz = 12, 10, 8
+    vals = np.round(rng.standard_normal((Nx, Ny, Nz)) * 3) / 3          # many repeated levels
+    og, pg, ob, pb = _pair((Nx, Ny, Nz), (-1, 0), vals)
+    m = _model(pg, pb)
+    z = APE.reference_height(m, method=BPE.ProfileLookup())
+    torch.cuda.synchronize()
+    col = OB.vertical_sort(ob)
+    want = OB.profile_lookup(ob, col["b_sorted"], col["zstar"])
+    np.testing.assert_allclose(z.interior_ijk(), want["zstar"], rtol=0, atol=ztol(vals.size))
+    heav = APE.reference_height(m, method=BPE.HeavisideIntegral())       # the same band mid-heights, by construction
+    np.testing.assert_allclose(z.interior_ijk(), heav.interior_ijk(), rtol=0, atol=ztol(vals.size))

@@ -127,7 +127,7 @@ def test_random_field_methods_agree_and_stretched_grid():
     np.testing.assert_allclose(zs.interior_ijk(), want["zstar"], rtol=0, atol=tol)
 
 
-def test_recompute_on_evolution_and_unsupported_methods():
+def test_recompute_on_evolution_and_unknown_methods():
     rng = np.random.default_rng(2)
     og, pg, ob, pb = _pair((8, 8, 8), (-1, 0), rng.standard_normal((8, 8, 8)))
     z = BPE.reference_height(pb)
@@ -137,5 +137,5 @@ def test_recompute_on_evolution_and_unsupported_methods():
     torch.cuda.synchronize()
     after = z.interior_ijk()
     np.testing.assert_allclose(after, -1.0 - before, rtol=0, atol=ztol(512))       # slot centres mirror about the mid-depth
-    with pytest.raises(ocb.OcbError):
-        BPE.reference_height(pb, method=BPE.VerticalSort())
+    with pytest.raises(TypeError):
+        BPE.reference_height(pb, method="ThreeDimensionalSort")          # a method object, not a name

@@ -654,3 +654,50 @@ def test_ape_dissipation_matches_tracer_variance_discretization():
     chi = K.evaluate(K.tracer_variance_dissipation_rate_ccc, g, "ccc", cl, None, None, b)
     eps_a = K.evaluate(K.ape_dissipation_rate_ccc, g, "ccc", ups, cl, None, None, b)
     assert chi.max() > 0 and np.abs(eps_a).max() < np.sqrt(np.finfo(float).eps) * chi.max() / 2
+
+
+def _stride_scrambled(values, shape):
+    N = values.size
+    scr = np.zeros(N)
+    for m in range(N):
+        scr[(7 * m) % N] = values[m]                     # a bijection when gcd(7, N) = 1
+    return scr.reshape(shape, order="F")
+
+
+def test_vertical_sort_recovers_the_known_profile():
+    """test/test_ape_diagnostics.jl:405-441: a scrambled tanh profile: the column's heights, buoyancies and ∫E_b."""
+    Nx, Ny, Nz = 4, 3, 5
+    N, Lz = Nx * Ny * Nz, 1.0
+    g = OGrid((Nx, Ny, Nz), x=(0, 2), y=(0, 3), z=(-Lz, 0), topology=("P", "P", "B"))
+    zs = -Lz + (np.arange(1, N + 1) - 0.5) * Lz / N
+    bs = 0.1 * np.tanh((zs + Lz / 2) / 0.2)
+    b = OField(g, "ccc")
+    b.interior[...] = _stride_scrambled(bs, (Nx, Ny, Nz))
+    col = OB.vertical_sort(b)
+    np.testing.assert_allclose(col["zstar"], zs, rtol=1e-13)
+    np.testing.assert_allclose(col["b_sorted"], bs, rtol=0, atol=0)
+    assert np.sum(-col["b_sorted"] * col["zstar"] * (2 * 3 * Lz / N)) == pytest.approx(np.sum(-bs * zs * (2 * 3 * Lz / N)), rel=1e-13)
+    assert np.all(np.diff(col["b_sorted"]) >= 0) and np.all(np.diff(col["zstar"]) > 0)          # :291-293
+    # the column integrates like the model grid (:295)
+    assert np.sum(col["b_sorted"]) == pytest.approx(np.sum(b.interior), rel=1e-13)
+
+
+def test_profile_lookup_matches_the_ranked_sort_and_validates_profiles():
+    """test/test_ape_diagnostics.jl:226-275: on a tie-free field ProfileLookup -- from the field's own sort or a borrowed
+    column / bare pair -- reproduces ThreeDimensionalSort exactly; malformed profiles are rejected with the reference's
+    messages."""
+    Nx, Ny, Nz = 3, 2, 4
+    N = Nx * Ny * Nz
+    g = OGrid((Nx, Ny, Nz), x=(0, 1), y=(0, 1), z=(-1, 0), topology=("P", "P", "B"))
+    b = OField(g, "ccc")
+    b.interior[...] = _stride_scrambled(-0.5 + np.arange(N) / (N - 1), (Nx, Ny, Nz))
+    ranked = OB.reference_height(b, "ThreeDimensionalSort")
+    col = OB.vertical_sort(b)
+    got = OB.profile_lookup(b, col["b_sorted"], col["zstar"])
+    np.testing.assert_allclose(got["zstar"], ranked["zstar"], rtol=1e-13)
+    np.testing.assert_allclose(got["psi_delta"], ranked["psi_delta"], rtol=1e-12, atol=1e-15)
+    bs, zp = col["b_sorted"], col["zstar"]
+    for msg, bad in (("buoyancy and height have different", (bs[:-1], zp)), ("ordered from the densest fluid up", (bs[::-1], zp)),
+                     ("heights paired with", (bs, zp[::-1]))):
+        with pytest.raises(ValueError, match=msg):
+            OB.profile_lookup(b, *bad)
