@@ -774,6 +774,9 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
   else if ((mask & ~VEL) == 0) rc = OCB_PICK(VEL);
   else if ((mask & ~VELP) == 0) rc = OCB_PICK(VELP);
   else if ((mask & ~VELB) == 0) rc = OCB_PICK(VELB);
+  else if (!cfg && !any_out && SP.req[0].hi[1] - SP.req[0].lo[1] + 1 <= 3)
+    // a strip of up to three rows (the slab-edge sweeps of the overlapped multi-GPU step): 4-row tiles instead of 24-row ones
+    rc = setup_variant<ALL, 2, 2, 3>(fp, false);
   else if (!cfg) rc = OCB_PICK(ALL);
 #undef OCB_PICK
   else if (nw == 16 && ry == 1) rc = setup_variant<ALL, 16, 1, 3>(fp, any_out);
