@@ -139,3 +139,37 @@ def test_recompute_on_evolution_and_unknown_methods():
     np.testing.assert_allclose(after, -1.0 - before, rtol=0, atol=ztol(512))       # slot centres mirror about the mid-depth
     with pytest.raises(TypeError):
         BPE.reference_height(pb, method="ThreeDimensionalSort")          # a method object, not a name
+
+
+def test_full_size_config5_reference_height_properties():
+    """BASELINE.json configs[4] at its full size (N = 67 108 864 keys) through properties that need no oracle: the sorted
+    buoyancy is non-decreasing and a rearrangement of the input (same sum and extremes), the permutation is one (every
+    index once), z✶ conserves the volume-mean height, the two methods agree on a tie-free field, and e_a >= 0."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 20e9:
+        pytest.skip("needs ~15 GB of device memory")
+    Nx, Ny, Nz = 512, 512, 256
+    N = Nx * Ny * Nz
+    g = ocb.RectilinearGrid((Nx, Ny, Nz), extent=(1, 1, 0.5), device="cuda")
+    m = ocb.NonhydrostaticModel(g, tracers=("b",))
+    b = m.tracers.b
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    zc = -0.5 + (torch.arange(Nz, device="cuda", dtype=torch.float64) + 0.5) * 0.5 / Nz
+    b.interior.copy_((1e-5 * zc)[:, None, None] + 1e-6 * torch.randn(b.interior.shape, generator=gen, device="cuda", dtype=torch.float64))
+    b.fill_halo_regions()
+    z3 = BPE.reference_height(m)
+    bs = z3.sorted_buoyancy
+    assert bool(torch.all(bs[1:] >= bs[:-1]))
+    assert float(bs[0]) == float(b.interior.min()) and float(bs[-1]) == float(b.interior.max())
+    assert abs(float(bs.sum()) - float(b.interior.sum())) <= 1e-12 * float(b.interior.abs().sum())
+    perm = z3.permutation
+    seen = torch.zeros(N, dtype=torch.int32, device="cuda")
+    seen.index_add_(0, perm - 1, torch.ones(N, dtype=torch.int32, device="cuda"))
+    assert int(seen.min()) == 1 and int(seen.max()) == 1
+    tol = ztol(N, 0.5)
+    assert abs(float(z3.interior.mean()) - (-0.25)) <= tol                     # volume-mean z✶ = volume-mean z (uniform cells)
+    zh = BPE.reference_height(m, method=BPE.HeavisideIntegral())
+    assert float((z3.interior - zh.interior).abs().max()) <= tol
+    APE = ocb.AvailablePotentialEnergyEquation
+    ea = ocb.Field(APE.AvailablePotentialEnergy(m, z3)).compute().interior
+    assert float(ea.min()) > -np.sqrt(np.finfo(np.float64).eps) * float(b.interior.abs().max())

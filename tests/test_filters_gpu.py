@@ -151,3 +151,31 @@ def test_float32_filter():
     got = run(SF.GaussianFilter(pf, dims=(1, 2, 3), sigma=0.2, N=5))
     want = OF.gaussian_filter(of, (1, 2, 3), 0.2, 5)
     assert np.linalg.norm(got.astype(np.float64) - want) <= 1e-5 * np.linalg.norm(want)
+
+
+def test_full_size_config5_filter_properties():
+    """BASELINE.json configs[4] at its full size (512 x 512 x 256 Float64, 17-tap Gaussian, :shrink in z) through
+    properties that need no oracle: a field of ones is returned bit for bit (every pass divides the same accumulated
+    weight sum), exact power-of-two scaling, linearity to roundoff, and a horizontally periodic box filter conserves the
+    sum over x and y of every plane."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 8e9:
+        pytest.skip("needs ~6 GB of device memory")
+    Nx, Ny, Nz = 512, 512, 256
+    g = ocb.RectilinearGrid((Nx, Ny, Nz), extent=(1, 1, 0.5), device="cuda")
+    a, b = ocb.CenterField(g), ocb.CenterField(g)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    a.interior.copy_(torch.randn(a.interior.shape, generator=gen, device="cuda", dtype=torch.float64))
+    b.interior.fill_(1.0)
+    filt = SF.GaussianFilter(dims=(1, 2, 3), sigma=4.0 / 512, boundary="shrink")
+    ones = ocb.Field(filt(b)).compute()
+    assert filt(b).widths == (8, 8, 8)
+    assert torch.equal(ones.interior, torch.ones_like(ones.interior))
+    fa = ocb.Field(filt(a)).compute().interior.clone()
+    a.interior.mul_(2.0)
+    assert torch.equal(ocb.Field(filt(a)).compute().interior, 2.0 * fa)
+    a.interior.mul_(0.5).add_(b.interior)                     # a + 1
+    lin = ocb.Field(filt(a)).compute().interior
+    assert float((lin - (fa + 1.0)).abs().max()) <= 1e-13 * float(fa.abs().max() + 1.0)
+    box = ocb.Field(SF.BoxFilter(a, dims=(1, 2), N=17)).compute().interior
+    assert float((box.sum(dim=(1, 2)) - a.interior.sum(dim=(1, 2))).abs().max()) <= 1e-9 * float(a.interior.abs().sum(dim=(1, 2)).max())

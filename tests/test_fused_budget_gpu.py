@@ -216,3 +216,49 @@ def test_split_plan_budget_kernel_plus_generic_kernel():
     for nm, integ in zip(extra, ints[len(ops):]):
         _, _, want, loc = cases[nm]
         assert abs(integ - K.integral(want, st.og, loc)) <= 1e-12 * integral_scale(st.og, want, loc), nm
+
+
+def test_full_size_1024_cube_properties():
+    """BASELINE.json configs[2] at its full size (1024^3 Float64, the bench workload), through properties that need no
+    oracle: run-to-run bit equality; the pipelined kernel against the per-cell generic kernel (two independent CUDA
+    formulations) to 1e-12 of each integrand's scale; exact power-of-two scaling (u -> 2u multiplies K and eps by 4, ADV by
+    8, PR and u_i b_i by 2, bit for bit); y windows add up to the whole; <chi> = <2c div F>."""
+    import sys
+    from helpers import ROOT
+    free, _ = torch.cuda.mem_get_info()
+    if free < 70e9:
+        pytest.skip("needs ~60 GB of device memory")
+    sys.path.insert(0, ROOT)
+    import bench
+    n = 1024
+    grid, m = bench.make_state(ocb, torch, (n, n, n), torch.device("cuda", 0))
+    ops = bench.budget_ops(ocb, m)
+    fused = ocb.FusedDiagnostics(*[ocb.Integral(o) for o in ops])
+    assert fused.plan.variant == 1
+    first = fused.compute().integrals()
+    assert fused.compute().integrals() == first
+    # generic kernel: one request at a time keeps its scratch small; scale = the integral of |integrand|
+    os.environ["OCB_DISABLE_FUSED"] = "1"
+    try:
+        generic = [ocb.FusedDiagnostics(ocb.Integral(o)) for o in ops]
+    finally:
+        os.environ.pop("OCB_DISABLE_FUSED", None)
+    dV = 1.0 / n ** 3
+    for o, a, g in zip(ops, first, generic):
+        assert g.plan.variant == 0
+        b = g.compute().integrals()[0]
+        f = ocb.Field(o).compute()
+        scale = float(f.interior.abs().sum()) * dV
+        del f
+        torch.cuda.empty_cache()
+        assert abs(a - b) <= 1e-12 * scale, (o.name, a, b, scale)
+    assert abs(first[5] - first[6]) <= 1e-10 * abs(first[5])                      # <chi> = <2c div F>
+    halves = [ocb.FusedDiagnostics(*[ocb.Integral(o, indices=(None, w, None)) for o in ops]).compute().integrals()
+              for w in ((1, 511), (512, n))]
+    for o, a, h0, h1 in zip(ops, first, *halves):
+        assert abs((h0 + h1) - a) <= 1e-11 * max(abs(h0), abs(h1), abs(a)), o.name
+    for f in (m.velocities.u, m.velocities.v, m.velocities.w):
+        f.data.mul_(2.0)
+    scaled = fused.compute().integrals()
+    for a, b, factor in zip(scaled, first, (4.0, 8.0, 2.0, 2.0, 4.0, 1.0, 1.0)):
+        assert a == factor * b
