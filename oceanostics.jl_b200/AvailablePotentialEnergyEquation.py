@@ -75,3 +75,16 @@ def AvailablePotentialEnergyDissipationRate(model, zstar=None, method=None, upsi
 
 
 DissipationRate = AvailablePotentialEnergyDissipationRate
+
+KineticEnergyConversion = PotentialToKineticEnergyConversion
+
+
+def reference_buoyancy(zstar):
+    """The buoyancy paired with a reference height: the model's own b on the model grid, the sorted profile b✶ on a
+    `VerticalSort` column (BackgroundPotentialEnergyEquation.jl:270-296)."""
+    return zstar.buoyancy
+
+
+def PotentialEnergyDiffusiveVerticalBuoyancyFlux(*args, **kwargs):
+    raise _lib.OcbError("PotentialEnergyDiffusiveVerticalBuoyancyFlux (src/PotentialEnergyEquation.jl) is outside the B200 hot path "
+                        "(SURVEY.md section 8f, row 4): evaluate it with Oceanostics.jl")

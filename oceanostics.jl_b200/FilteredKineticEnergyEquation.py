@@ -49,6 +49,24 @@ def _filtered_momentum_fluxes(filter, grid, u, v, w, dims, collocate_diagonals):
     return out
 
 
+def subfilter_stress_tensor(model, filter=None, dims=(1, 2, 3), collocate_diagonals=False, **kw):
+    """τⁱʲ = filter(uⁱuʲ) - ūⁱūʲ component by component, each at its StressTensor location (:42-48, :118-160): a namespace
+    of computed Fields keyed τ₁₁ ... τ₂₃ (the kept components for `dims`)."""
+    from .operations import PointwiseField
+    FlowDiagnostics.validate_dims(dims)
+    filter = _filter_from_kwargs(filter, dict(kw, dims=kw.get("filter_dims", dims)))
+    grid = model.grid
+    u, v, w = model.velocities.u, model.velocities.v, model.velocities.w
+    ub, vb, wb = filtered_velocities(filter, dims, u, v, w)
+    full = FlowDiagnostics.StressTensor(grid, u, v, w, dims=dims, collocate_diagonals=collocate_diagonals)
+    filt = FlowDiagnostics.StressTensor(grid, ub, vb, wb, dims=dims, collocate_diagonals=collocate_diagonals)
+    out = {}
+    for key, _, _slot in _TENSOR_KEYS:
+        if hasattr(full, key):
+            out[key] = PointwiseField("-", Field(filter(Field(getattr(full, key)))), Field(getattr(filt, key)))
+    return SimpleNamespace(**out)
+
+
 def KineticEnergyCrossScaleFlux(model, filter=None, dims=(1, 2, 3), collocate_diagonals=False, **kw):
     """Πₖ = -τⁱʲ S̄ⁱʲ contracted at cell centres (:176-188, :246-261); τⁱʲ = filter(uⁱuʲ) - ūⁱūʲ."""
     FlowDiagnostics.validate_dims(dims)

@@ -135,3 +135,46 @@ def StressTensor(model_or_grid, u=None, v=None, w=None, dims=(1, 2, 3), collocat
     c = "C" if collocate_diagonals else ""
     return _tensor("T", {(1, 1): "T11" + c, (2, 2): "T22" + c, (3, 3): "T33" + c, (1, 2): "T12", (1, 3): "T13", (2, 3): "T23"},
                    g, u, v, w, dims)
+
+
+def ThermalWindPotentialVorticity(model, **kw):
+    """potential_vorticity_in_thermal_wind_fff (src/FlowDiagnostics.jl:200-214, 259): ErtelPotentialVorticity's thermal-wind form."""
+    return ErtelPotentialVorticity(model, thermal_wind=True, **kw)
+
+
+def to_center(psi):
+    """`@at (Center, Center, Center) ψ` (src/FlowDiagnostics.jl:858) as a computed Field."""
+    from .operations import PointwiseField
+    from .fields import Field as _Field
+    psi = psi if isinstance(psi, _Field) else _Field(psi)
+    return psi if psi.location == ("c", "c", "c") and not getattr(psi, "is_reduced", False) else PointwiseField("@", psi, location=("c", "c", "c"))
+
+
+def subfilter_covariance(a, b, filter, loc=("c", "c", "c"), filtered_a=None):
+    """τ(a, b) = filter(a·b) - filter(a)·filter(b), co-located at `loc` (src/FlowDiagnostics.jl:901-910).  Every filtered
+    piece is a materialised Field on the staged-filter path; the result is a computed Field that refreshes the whole
+    graph on `compute`.  `filtered_a` shares a pre-filtered first factor between several covariances."""
+    from .operations import PointwiseField
+    from .fields import Field as _Field
+    loc = normalize_location(loc)
+
+    def at_loc(x):
+        x = x if isinstance(x, _Field) else _Field(x)
+        return x if x.location == loc else PointwiseField("@", x, location=loc)
+    a_loc, b_loc = at_loc(a), at_loc(b)
+    a_bar = _Field(filter(a_loc)) if filtered_a is None else filtered_a
+    filtered_product = _Field(filter(PointwiseField("*", a_loc, b_loc, location=loc)))
+    return PointwiseField("-", filtered_product, PointwiseField("*", a_bar, _Field(filter(b_loc)), location=loc), location=loc)
+
+
+def _outside_the_hot_path(name, where):
+    def raiser(*args, **kwargs):
+        raise _lib.OcbError(f"{name} ({where}) is outside the B200 hot path (SURVEY.md section 8f / 2): evaluate it with Oceanostics.jl")
+    raiser.__name__ = name
+    return raiser
+
+
+MixedLayerDepth = _outside_the_hot_path("MixedLayerDepth", "src/FlowDiagnostics.jl")
+BuoyancyAnomalyCriterion = _outside_the_hot_path("BuoyancyAnomalyCriterion", "src/FlowDiagnostics.jl")
+DensityAnomalyCriterion = _outside_the_hot_path("DensityAnomalyCriterion", "src/FlowDiagnostics.jl")
+BottomCellValue = _outside_the_hot_path("BottomCellValue", "src/FlowDiagnostics.jl")

@@ -102,3 +102,19 @@ Advection = KineticEnergyAdvection
 PressureRedistribution = KineticEnergyPressureRedistribution
 BuoyancyProduction = PotentialEnergyConversion
 IsotropicDissipationRate = KineticEnergyIsotropicDissipationRate
+
+
+PotentialToKineticEnergyConversion = PotentialEnergyConversion
+
+
+def _deferred(name):
+    def raiser(*args, **kwargs):
+        raise _lib.OcbError(f"{name} needs Oceananigans' full momentum tendency / stress-divergence / forcing kernels and is deferred "
+                            "(SURVEY.md section 8f, row 2): evaluate it with Oceanostics.jl")
+    raiser.__name__ = name
+    return raiser
+
+
+KineticEnergyTendency = _deferred("KineticEnergyTendency")
+KineticEnergyStress = Stress = _deferred("KineticEnergyStress")
+KineticEnergyForcing = Forcing = _deferred("KineticEnergyForcing")

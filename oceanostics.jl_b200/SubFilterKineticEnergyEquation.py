@@ -31,3 +31,6 @@ def SubFilterKineticEnergyDissipationRate(model, filter=None, **kw):
 
 
 DissipationRate = SubFilterKineticEnergyDissipationRate
+
+
+from .FilteredKineticEnergyEquation import KineticEnergyCrossScaleFlux  # noqa: E402,F401  (re-exported as in the reference)

@@ -39,3 +39,12 @@ def TracerVarianceDiffusion(model, tracer_name, location=CCC):
 
 DissipationRate = TracerVarianceDissipationRate
 Diffusion = TracerVarianceDiffusion
+
+
+
+def TracerVarianceTendency(*args, **kwargs):
+    raise _lib.OcbError("TracerVarianceTendency needs Oceananigans' full tracer tendency kernel and is deferred (SURVEY.md section 8f, "
+                        "row 2): evaluate it with Oceanostics.jl")
+
+
+Tendency = TracerVarianceTendency

@@ -432,6 +432,43 @@ def materialize_binary(op: BinaryOperation, location=None) -> Field:
     return out
 
 
+class PointwiseField(Field):
+    """A computed `Field` for `@at loc a`, `a + b`, `a - b` or `a * b` of (possibly computed) Fields: recomputed by
+    `compute` / `compute_at` like any other computed field (operands first), through the library's pointwise kernel,
+    which interpolates each operand to the result's location with Oceananigans' two-point means."""
+    is_computed = True
+
+    def __new__(cls, *a, **k):
+        return object.__new__(cls)
+
+    def __init__(self, op, a, b=None, location=None):
+        for x in (a, b):
+            if isinstance(x, AbstractOperation) and not isinstance(x, Field):
+                raise TypeError("materialise operations with Field(op) before combining them pointwise")
+        grid = a.grid
+        loc = normalize_location(location) if location is not None else a.location
+        Field.__init__(self, loc, grid)
+        self.op, self.a, self.b = op, a, (as_operand(b) if op != "@" else None)
+        self.group = None
+        self.boundary["impenetrable"] = False
+
+    def compute(self, time=None):
+        grid = self.grid
+        if grid.device.type != "cuda":
+            raise _lib.OcbError("pointwise fields are evaluated by the CUDA library only (no CPU fallback)")
+        for x in (self.a, self.b):
+            if getattr(x, "is_computed", False):
+                compute_at(x, time)
+        code = {"@": _lib.OCB_OP_COPY, "+": _lib.OCB_OP_ADD, "-": _lib.OCB_OP_SUB, "*": _lib.OCB_OP_MUL}[self.op]
+        gd, da, dd = grid.descriptor(), self.a.descriptor(), self.descriptor()
+        db = self.b.descriptor() if self.b is not None else None
+        _lib.check(_lib.lib().ocb_pointwise(C.byref(gd), code, 1.0, C.byref(da), C.byref(db) if db is not None else None, C.byref(dd),
+                                            current_stream_ptr(grid.device)))
+        self.fill_halo_regions()
+        self.status_time = time
+        return self
+
+
 def perturbation_split(x, default_mean=None):
     """Pattern-match a velocity/tracer argument: `field`, or the lazy `field - mean` the reference's
     constructors build (src/TurbulentKineticEnergyEquation.jl:327-330).  Returns (field, mean or None)."""

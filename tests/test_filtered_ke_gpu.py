@@ -109,3 +109,52 @@ def test_cross_scale_flux_dims_subset_and_collocated_diagonals():
     assert not np.allclose(full, xz) and not np.allclose(full, col)
     with pytest.raises(ValueError):
         FKE.KineticEnergyCrossScaleFlux(m, filt, dims=(1, 1))
+
+
+def test_subfilter_covariance_and_stress_tensor_against_the_oracle_graph():
+    """subfilter_covariance(a, b, filter) = filter(a b) - filter(a) filter(b) with both operands co-located first
+    (src/FlowDiagnostics.jl:901-910) and subfilter_stress_tensor component by component (src/FilteredKineticEnergyEquation.jl:42-48),
+    against the same graphs assembled from the NumPy oracle; the result recomputes its whole graph on compute()."""
+    st = State(size=(24, 20, 16), device="cuda")
+    og = st.og
+    FD = ocb.FlowDiagnostics
+    filt = SF.GaussianFilter(dims=DIMS, sigma=SIGMA, boundary=BOUNDARY)
+    m = st.model(closure=st.closures()["scalar"][1])
+    # tracer flux carried by the sub-filter scales: a = u (Face in x), b = the tracer (Center)
+    cov = FD.subfilter_covariance(m.velocities.u, m.tracers.b, filt)
+    cov.compute()
+    torch.cuda.synchronize()
+    uc = materialize(og, "ccc", K.evaluate(K.ix_caa, og, "ccc", st.ou))                 # @at ccc u
+    fu, fb = ofilt(st, uc.interior, "ccc"), ofilt(st, st.ob.interior, "ccc")
+    fub = ofilt(st, uc.interior * st.ob.interior, "ccc")
+    want = fub.interior - fu.interior * fb.interior
+    assert_close(cov.interior_ijk(), want, 1e-12, "subfilter_covariance(u, b)")
+    # a shared pre-filtered first factor gives the same field
+    shared = FD.subfilter_covariance(m.velocities.u, m.tracers.b, filt, filtered_a=ocb.Field(filt(FD.to_center(m.velocities.u)))).compute()
+    np.testing.assert_array_equal(shared.interior_ijk(), cov.interior_ijk())
+    # the graph is live: change the tracer, recompute, compare again
+    m.tracers.b.data.mul_(-2.0)
+    cov.compute(time=1.0)
+    assert_close(cov.interior_ijk(), -2.0 * want, 1e-12, "subfilter_covariance after an update")
+    m.tracers.b.data.mul_(-0.5)
+    # sub-filter stress, off-diagonal component at its own (Face, Face, Center) location
+    tau = FKE.subfilter_stress_tensor(m, filt)
+    assert sorted(vars(tau)) == sorted(["τ₁₁", "τ₂₂", "τ₃₃", "τ₁₂", "τ₁₃", "τ₂₃"])
+    t12 = getattr(tau, "τ₁₂").compute()
+    ub, vb = ofilt(st, st.ou.interior, "fcc"), ofilt(st, st.ov.interior, "cfc")
+    full = ofilt(st, K.evaluate(K.stress_tensor_component(1, 2), og, "ffc", st.ou, st.ov), "ffc")
+    want12 = full.interior - K.evaluate(K.stress_tensor_component(1, 2), og, "ffc", ub, vb)
+    assert t12.location == ("f", "f", "c")
+    assert_close(t12.interior_ijk(), want12, 1e-12, "τ₁₂")
+
+
+def test_names_outside_the_hot_path_fail_loudly():
+    st = State(size=(8, 8, 8), device="cuda")
+    m = st.model(closure=st.closures()["scalar"][1])
+    for fn in (ocb.KineticEnergyEquation.KineticEnergyTendency, ocb.KineticEnergyEquation.KineticEnergyStress,
+               ocb.KineticEnergyEquation.KineticEnergyForcing, ocb.TracerVarianceEquation.TracerVarianceTendency,
+               ocb.FlowDiagnostics.MixedLayerDepth):
+        with pytest.raises(ocb.OcbError, match="Oceanostics.jl"):
+            fn(m)
+    assert ocb.KineticEnergyEquation.PotentialToKineticEnergyConversion is ocb.KineticEnergyEquation.PotentialEnergyConversion
+    assert SFKE.KineticEnergyCrossScaleFlux is FKE.KineticEnergyCrossScaleFlux
