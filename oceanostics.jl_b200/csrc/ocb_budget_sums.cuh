@@ -1,0 +1,255 @@
+// K1a-sums: the integral-only form of the budget kernel (included by ocb_sweep_fused.cu, inside its anonymous namespace).
+//
+// When a plan asks only for volume integrals of the seven budget terms
+//   K, ADV, PR, WB, EPS, CHI, CDF   (reference lines: see the table at the top of ocb_sweep_fused.cu)
+// over (all of x) x (a y window) x (a z window) of an x-periodic grid, the sum over cells of every term is re-associated
+// into sums over the staggered items the cell values are built from -- x/y/z faces, ffc corners, fcf / cff edges, cells --
+// each item weighted by the number of WINDOW cells it belongs to (class weights that depend on the row j and the plane k
+// only, never on the lane).  Every block owns a disjoint (32 x BR) set of columns: no overlap rows or lanes, no shuffles,
+// no exchange between warps, and -- away from the window edges -- one set of accumulators per thread.
+//
+// The advection term is summed by parts: with the face-located momentum fluxes
+//   Uu = (u_i + u_{i+1})^2 (ccc), P12 = (v_{i-1} + v_i)(u_{j-1} + u_j) (ffc), P13 = (w_{i-1} + w_i)(u_{k-1} + u_k) (fcf), ...
+// the reference's  sum_cells 1/8 [Fu + FuE + Fv + FvN + Fw + FwT],  Fu = u (dx Uu/Dx + dy P12/Dy + dz P13/Dz)  etc.
+// (src/KineticEnergyEquation.jl:147-152 with Oceananigans' Centered(order=2) div_Uu/div_Uv/div_Uw) equals EXACTLY (a
+// finite re-association of the same products; x periodic, window-edge faces keep their explicit boundary terms)
+//   -1/4 sum [ P12 S12 + P13 S13 + P23 S23 + Uu dxu + Vv dyv + Ww dzw ]
+// over interior items, where S12 = dyu + dxv, S13 = dzu + dxw, S23 = dzv + dyw are the strain sums the dissipation rate
+// needs anyway.  Rows and planes at a window edge take the general weighted form (GEN below); everything else the FAST
+// form.  Per cell: 68 Float64 instructions for the seven integrals (the cell-exact integral mode of ocb_budget_kernel: ~100).
+//
+// Ownership in z: a block sweeps the planes k0..k1 of its chunk (plus the two closing steps of the window for the last
+// chunk); the step at plane n handles the cell, face, corner and edge items of plane n and the z-centred items of the cell
+// below (S33, Ww, the tracer Laplacian).  Chunks other than the first pre-load two planes to warm that one-plane lag.
+
+template <int MASK, int NW, int RY, int NS, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB)
+ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_constant__ CUtensorMap mu, const __grid_constant__ CUtensorMap mv,
+                       const __grid_constant__ CUtensorMap mw, const __grid_constant__ CUtensorMap mb, const __grid_constant__ CUtensorMap mp) {
+  using G = Geo<NW, RY>;
+  constexpr bool H_K = MASK & (1 << FD_K), H_ADV = MASK & (1 << FD_ADV), H_PR = MASK & (1 << FD_PR), H_WB = MASK & (1 << FD_WB),
+                 H_EPS = MASK & (1 << FD_EPS), H_CHI = MASK & (1 << FD_CHI), H_CDF = MASK & (1 << FD_CDF);
+  constexpr bool NEED_B = H_WB || H_CHI || H_CDF, NEED_P = H_PR, NEED_S = H_EPS || H_ADV;
+  constexpr int NF = 3 + (NEED_B ? 1 : 0) + (NEED_P ? 1 : 0);
+  constexpr int F_B = 3, F_P = NEED_B ? 4 : 3;
+
+  extern __shared__ __align__(1024) double smem_d[];
+  double* tiles = smem_d;                                                      // [NS][NF][TILE]
+  double* red = tiles + NS * NF * G::TILE;                                     // [NW]
+  uint64_t* full = reinterpret_cast<uint64_t*>(red + NW);                      // [NS]
+
+  const int lane = threadIdx.x, warp = threadIdx.y;
+  const int tid = warp * 32 + lane;
+  int bid = blockIdx.x;
+  const int tx = bid % P.tiles_x; bid /= P.tiles_x;
+  const int ty = bid % P.tiles_y; bid /= P.tiles_y;
+  const int chunk = bid;
+  const int i0 = 1 + 32 * tx, j0 = P.jy_lo + G::BR * ty;
+  const int k0 = P.kz_lo + chunk * P.kchunk;
+  const int k1 = min(k0 + P.kchunk - 1, P.kz_hi);
+  const int n_first = chunk == 0 ? k0 - 1 : k0 - 2;
+  const int n_last = (k1 == P.kz_hi) ? k1 + (H_ADV ? 2 : 1) : k1;
+  const int i = i0 + lane;
+  const int jr0 = warp * RY;
+
+  // ---- TMA ring (same tiles as ocb_budget_kernel: 36 x (BR + 2), 16-byte aligned box start) -------------------------
+  constexpr uint32_t STAGE_BYTES = (uint32_t)(NF * TW * G::TR * 8);
+  const int px_raw = i0 - 1 + P.hx - 1, py = j0 - 1 + P.hy - 1;
+  const int xoff = px_raw & 1, px = px_raw - xoff;
+  auto issue = [&](int n) {
+    const int s = (n - n_first) % NS;
+    double* dst = tiles + s * (NF * G::TILE);
+    mbar_expect_tx(&full[s], STAGE_BYTES);
+    const int pz = n + P.hz - 1;
+    tma_load_3d(dst + 0 * G::TILE, &mu, &full[s], px, py, pz);
+    tma_load_3d(dst + 1 * G::TILE, &mv, &full[s], px, py, pz);
+    tma_load_3d(dst + 2 * G::TILE, &mw, &full[s], px, py, pz);
+    if (NEED_B) tma_load_3d(dst + F_B * G::TILE, &mb, &full[s], px, py, pz);
+    if (NEED_P) tma_load_3d(dst + F_P * G::TILE, &mp, &full[s], px, py, pz);
+  };
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int n = n_first; n < n_first + NS && n <= n_last; ++n) issue(n);
+  }
+
+  const double rdx = P.rdx, rdy = P.rdy, rdz = P.rdz;
+  const double rdx2 = rdx * rdx, rdy2 = rdy * rdy, rdz2 = rdz * rdz;
+
+  // ---- per-row classes (functions of j only, warp-uniform) ----------------------------------------------------------
+  // alpha = [row j in the window], beta = [row j-1 in it], alphan = [row j+1 in it]; rows jy_lo .. jy_hi+1 carry items
+  const bool xfull = i0 + 31 <= P.Nx;
+  const bool lane_ok = i <= P.Nx;
+  bool rfast[RY], rlive[RY];
+#pragma unroll
+  for (int r = 0; r < RY; ++r) {
+    const int j = j0 + jr0 + r;
+    rlive[r] = j <= P.jy_hi + 1;
+    rfast[r] = xfull && j >= P.jy_lo + 1 && j <= P.jy_hi - 1;
+  }
+
+  // pipeline state: the previous plane's centre values and the in-plane + lower-face part of the tracer Laplacian
+  double up[RY], vp[RY], wp[RY], bp[RY], pp[RY], CDacc[RY];
+#pragma unroll
+  for (int r = 0; r < RY; ++r) up[r] = vp[r] = wp[r] = bp[r] = pp[r] = CDacc[r] = 0.0;
+  // class sums, normalised to the interior weights (the closing lines of the kernel give each one its factor)
+  double aEe = 0.0, aEx = 0.0, aEy = 0.0, aEz = 0.0;       // S12^2 + S13^2 + S23^2 | (dx u)^2 | (dy v)^2 | (dz w)^2   (undivided differences)
+  double aAe = 0.0, aAx = 0.0, aAy = 0.0, aAz = 0.0;       // P12 S12 + P13 S13 + P23 S23 | Uu dxu | Vv dyv | Ww dzw
+  double aK = 0.0;                                         // u^2 + v^2 + w^2 at their faces
+  double aPx = 0.0, aPy = 0.0, aPz = 0.0;                  // u dx p | v dy p | w dz p
+  double aW = 0.0;                                         // w (b_{k-1} + b_k)
+  double aCx = 0.0, aCy = 0.0, aCz = 0.0, aD = 0.0;        // (dx b)^2 | (dy b)^2 | (dz b)^2 | b lap(b)
+
+  int s = 0;
+  uint32_t phase = 0;
+  for (int n = n_first; n <= n_last; ++n) {
+    mbar_wait(&full[s], phase);
+    const double* T = tiles + s * (NF * G::TILE);
+    const double* Tu = T, *Tv = T + G::TILE, *Tw = T + 2 * G::TILE, *Tb = T + F_B * G::TILE, *Tp = T + F_P * G::TILE;
+    if (++s == NS) { s = 0; phase ^= 1; }
+    const int col = lane + xoff + 1;                       // tile column of this lane's cell
+    const int row0 = jr0 + 1;                              // tile row of this thread's first cell
+
+    // ---- centre values of the thread's rows, the row to the south and the row to the north ----------------------------
+    double uc[RY], vc[RY], wc[RY], bc[RY], pc[RY];
+#pragma unroll
+    for (int r = 0; r < RY; ++r) {
+      const int o = (row0 + r) * TW + col;
+      uc[r] = Tu[o]; vc[r] = Tv[o]; wc[r] = Tw[o];
+      bc[r] = NEED_B ? Tb[o] : 0.0;
+      pc[r] = NEED_P ? Tp[o] : 0.0;
+    }
+    if (n > n_first) {
+      const int oS = (row0 - 1) * TW + col, oN = (row0 + RY) * TW + col;
+      const double uS = Tu[oS], wS = Tw[oS], vS = Tv[oS], vN = Tv[oN];
+      const double bS = NEED_B ? Tb[oS] : 0.0, bN = (NEED_B && H_CDF) ? Tb[oN] : 0.0, pS = NEED_P ? Tp[oS] : 0.0;
+      // plane classes (block-uniform): g0 = [this chunk owns step n and plane n is in the window], g1, g2: same for n-1, n-2
+      const bool own = n >= k0;
+      const bool in0 = n >= P.kz_lo && n <= P.kz_hi, in1 = (n - 1) >= P.kz_lo && (n - 1) <= P.kz_hi, in2 = (n - 2) >= P.kz_lo && (n - 2) <= P.kz_hi;
+      const bool pfast = own && in0 && in1 && in2;
+      const double g0 = (own && in0) ? 1.0 : 0.0, g1 = (own && in1) ? 1.0 : 0.0, g2 = (own && in2) ? 1.0 : 0.0;
+#pragma unroll
+      for (int r = 0; r < RY; ++r) {
+        if (!rlive[r]) continue;
+        const int o = (row0 + r) * TW + col;
+        const double us = r ? uc[r > 0 ? r - 1 : 0] : uS, ws = r ? wc[r > 0 ? r - 1 : 0] : wS;
+        const double vn = (r < RY - 1) ? vc[r < RY - 1 ? r + 1 : 0] : vN;
+        const double ue = Tu[o + 1], vw = Tv[o - 1], ww = Tw[o - 1];
+        // undivided differences shared by the strain sums, the diagonal strains and the by-parts advection
+        const double duy = uc[r] - us, dvx = vc[r] - vw, duz = uc[r] - up[r], dwx = wc[r] - ww, dvz = vc[r] - vp[r], dwy = wc[r] - ws;
+        const double ax = ue - uc[r], ay = vn - vc[r], dwz = wc[r] - wp[r];
+        double S12 = 0.0, S13 = 0.0, S23 = 0.0;
+        if (NEED_S) {
+          S12 = fma(dvx, rdx, duy * rdy);
+          S13 = fma(dwx, rdx, duz * rdz);
+          S23 = fma(dwy, rdy, dvz * rdz);
+        }
+        double P12 = 0.0, P13 = 0.0, P23 = 0.0, Uu = 0.0, Vv = 0.0, Ww = 0.0;
+        if (H_ADV) {
+          P12 = (vw + vc[r]) * (us + uc[r]);
+          P13 = (ww + wc[r]) * (up[r] + uc[r]);
+          P23 = (ws + wc[r]) * (vp[r] + vc[r]);
+          const double su = uc[r] + ue, sv = vc[r] + vn, sw = wp[r] + wc[r];
+          Uu = su * su; Vv = sv * sv; Ww = sw * sw;
+        }
+        const double ps = r ? pc[r > 0 ? r - 1 : 0] : pS;
+        const double dpx = NEED_P ? pc[r] - Tp[o - 1] : 0.0, dpy = pc[r] - ps, dpz = pc[r] - pp[r];
+        const double bs = r ? bc[r > 0 ? r - 1 : 0] : bS;
+        const double dbx = NEED_B ? bc[r] - Tb[o - 1] : 0.0, dby = bc[r] - bs, dbz = bc[r] - bp[r];
+        double lap = 0.0;
+        if (H_CDF) {
+          const double bn = (r < RY - 1) ? bc[r < RY - 1 ? r + 1 : 0] : bN;
+          const double de = Tb[o + 1] - bc[r], dn = bn - bc[r];
+          const double cdxy = fma(dbx - de, rdx2, (dby - dn) * rdy2);
+          lap = fma(-dbz, rdz2, CDacc[r]);                 // Laplacian (sign of div q) of the cell below, closed by this face
+          CDacc[r] = fma(dbz, rdz2, cdxy);
+        }
+        if (pfast && rfast[r]) {
+          // ---- FAST: every class weight is the interior one ----------------------------------------------------------
+          if (H_EPS) {
+            aEe = fma(S12, S12, aEe); aEe = fma(S13, S13, aEe); aEe = fma(S23, S23, aEe);
+            aEx = fma(ax, ax, aEx); aEy = fma(ay, ay, aEy); aEz = fma(dwz, dwz, aEz);
+          }
+          if (H_ADV) {
+            aAe = fma(P12, S12, aAe); aAe = fma(P13, S13, aAe); aAe = fma(P23, S23, aAe);
+            aAx = fma(Uu, ax, aAx); aAy = fma(Vv, ay, aAy); aAz = fma(Ww, dwz, aAz);
+          }
+          if (H_K) { aK = fma(uc[r], uc[r], aK); aK = fma(vc[r], vc[r], aK); aK = fma(wc[r], wc[r], aK); }
+          if (H_PR) { aPx = fma(uc[r], dpx, aPx); aPy = fma(vc[r], dpy, aPy); aPz = fma(wc[r], dpz, aPz); }
+          if (H_WB) aW = fma(wc[r], bp[r] + bc[r], aW);
+          if (H_CHI) { aCx = fma(dbx, dbx, aCx); aCy = fma(dby, dby, aCy); aCz = fma(dbz, dbz, aCz); }
+          if (H_CDF) aD = fma(bp[r], lap, aD);
+        } else if (lane_ok) {
+          // ---- GEN: a window-edge row or plane (or a partly filled x tile): explicit class weights ---------------------
+          const int j = j0 + jr0 + r;
+          const double al = (j >= P.jy_lo && j <= P.jy_hi) ? 1.0 : 0.0, be = (j - 1 >= P.jy_lo && j - 1 <= P.jy_hi) ? 1.0 : 0.0,
+                       an = (j + 1 >= P.jy_lo && j + 1 <= P.jy_hi) ? 1.0 : 0.0;
+          const double hy = 0.5 * (al + be), hyn = 0.5 * (al + an);        // y faces / corner rows j and j+1: half their cell count
+          const double hz = 0.5 * (g0 + g1), hzp = 0.5 * (g1 + g2);        // z faces n and n-1
+          if (H_EPS) {
+            aEe = fma(hy * g0 * S12, S12, aEe); aEe = fma(al * hz * S13, S13, aEe); aEe = fma(hy * hz * S23, S23, aEe);
+            aEx = fma(al * g0 * ax, ax, aEx); aEy = fma(al * g0 * ay, ay, aEy); aEz = fma(al * g1 * dwz, dwz, aEz);
+          }
+          if (H_ADV) {
+            // the by-parts weights of a window edge: the boundary face keeps the momentum on the window's side only
+            aAe = fma(g0 * P12, fma(rdx * hy, dvx, rdy * (al * uc[r] - be * us)), aAe);
+            aAe = fma(al * P13, fma(rdx * hz, dwx, rdz * (g0 * uc[r] - g1 * up[r])), aAe);
+            aAe = fma(P23, fma(rdy * hz, al * wc[r] - be * ws, rdz * hy * (g0 * vc[r] - g1 * vp[r])), aAe);
+            aAx = fma(al * g0 * Uu, ax, aAx);
+            aAy = fma(g0 * Vv, hyn * vn - hy * vc[r], aAy);
+            if (j == P.jy_lo) {                            // the flux cell south of the first window row, seen from face jy_lo only
+              const double vs = r ? vc[r > 0 ? r - 1 : 0] : vS;
+              aAy = fma(g0 * ((vs + vc[r]) * (vs + vc[r])), 0.5 * vc[r], aAy);
+            }
+            aAz = fma(al * Ww, hz * wc[r] - hzp * wp[r], aAz);
+          }
+          if (H_K) { aK = fma(al * g0 * uc[r], uc[r], aK); aK = fma(hy * g0 * vc[r], vc[r], aK); aK = fma(al * hz * wc[r], wc[r], aK); }
+          if (H_PR) { aPx = fma(al * g0 * uc[r], dpx, aPx); aPy = fma(hy * g0 * vc[r], dpy, aPy); aPz = fma(al * hz * wc[r], dpz, aPz); }
+          if (H_WB) aW = fma(al * hz * wc[r], bp[r] + bc[r], aW);
+          if (H_CHI) { aCx = fma(al * g0 * dbx, dbx, aCx); aCy = fma(hy * g0 * dby, dby, aCy); aCz = fma(al * hz * dbz, dbz, aCz); }
+          if (H_CDF) aD = fma(al * g1 * bp[r], lap, aD);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RY; ++r) {
+      up[r] = uc[r]; vp[r] = vc[r]; wp[r] = wc[r];
+      if (NEED_B) bp[r] = bc[r];
+      if (NEED_P) pp[r] = pc[r];
+    }
+    __syncthreads();
+    if (tid == 0 && n + NS <= n_last) issue(n + NS);       // every thread is done with this ring slot: refill it
+  }
+
+  // ---- class sums -> the seven integrals (per-cell scale factors of the reference formulas folded in) ---------------
+  double acc[FD_N];
+#pragma unroll
+  for (int d = 0; d < FD_N; ++d) acc[d] = 0.0;
+  acc[FD_K] = 0.5 * aK;
+  acc[FD_ADV] = -0.25 * (aAe + (rdx * aAx + rdy * aAy + rdz * aAz));
+  acc[FD_PR] = rdx * aPx + rdy * aPy + rdz * aPz;
+  acc[FD_WB] = 0.5 * P.ghat_z * aW;
+  acc[FD_EPS] = P.nu * (aEe + 2.0 * (rdx2 * aEx + rdy2 * aEy + rdz2 * aEz));
+  acc[FD_CHI] = 2.0 * P.kappa * (rdx2 * aCx + rdy2 * aCy + rdz2 * aCz);
+  acc[FD_CDF] = 2.0 * P.kappa * aD;
+  if (P.nslots > 0) {
+    const unsigned FULLMASK = 0xffffffffu;
+#pragma unroll
+    for (int d = 0; d < FD_N; ++d) {
+      if (!(MASK & (1 << d)) || P.o[d].slot < 0) continue;
+      double v = acc[d];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULLMASK, v, o);
+      __syncthreads();
+      if (lane == 0) red[warp] = v;
+      __syncthreads();
+      if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < NW; ++w) t += red[w];
+        P.partial[(size_t)blockIdx.x * P.nslots + P.o[d].slot] = t * P.V;
+      }
+    }
+  }
+}

@@ -588,12 +588,15 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+#include "ocb_budget_sums.cuh"
+
 }  // namespace
 
 struct ocb_fused_plan {
   FusedParams P;
   CUtensorMap maps[5];
   int mask, nw, ry, ns;
+  bool sums;                       // ocb_budget_sums_kernel (integral-only class sums) instead of ocb_budget_kernel
   int nblocks;
   size_t smem;
   void (*kernel)(FusedParams, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap);
@@ -616,6 +619,20 @@ static int setup_variant(ocb_fused_plan* fp, bool out) {
     fp->kernel = ocb_budget_kernel<MASK, NW, RY, NS, false>;
     OCB_CUDA(cudaFuncSetAttribute(ocb_budget_kernel<MASK, NW, RY, NS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp->smem));
   }
+  return OCB_OK;
+}
+
+template <int MASK, int NW, int RY, int NS, int MINB>
+static int setup_sums(ocb_fused_plan* fp) {
+  using G = Geo<NW, RY>;
+  constexpr bool NEED_B = MASK & ((1 << FD_WB) | (1 << FD_CHI) | (1 << FD_CDF)), NEED_P = MASK & (1 << FD_PR);
+  constexpr int NF = 3 + (NEED_B ? 1 : 0) + (NEED_P ? 1 : 0);
+  fp->nw = NW; fp->ry = RY; fp->ns = NS; fp->mask = MASK; fp->sums = true;
+  fp->smem = sizeof(double) * ((size_t)NS * NF * G::TILE + NW) + sizeof(uint64_t) * NS;
+  auto kern = ocb_budget_sums_kernel<MASK, NW, RY, NS, MINB>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  fp->kernel = kern;
+  OCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp->smem));
   return OCB_OK;
 }
 
@@ -763,7 +780,33 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
 #define OCB_PICK(M) (any_out ? setup_variant<M, 8, 2, 3>(fp, true) : setup_variant<M, 8, 3, 3>(fp, false))
   constexpr int TKEM = (1 << FD_EPS) | (1 << FD_SP) | (1 << FD_PR) | (1 << FD_K);  // TKE budget about mean profiles
   constexpr int EPVM = 1 << FD_EPV, TKEV = TKEM | EPVM;                            // + Ertel PV (BASELINE config 2)
-  if (mask & EPVM) {
+  // Integrals only, x periodic, no perturbation operands: the class-sum kernel (ocb_budget_sums.cuh).
+  // OCB_FUSED_CELL_INTEGRALS=1 keeps the cell-exact integral mode of ocb_budget_kernel (the two are compared in the tests);
+  // OCB_SUMS_CONFIG="NW,RY,NS,MINB" picks another compiled shape of the all-terms kernel for tuning runs.
+  const bool sums = !any_out && !any_pert && !(mask & ((1 << FD_SP) | (1 << FD_EPV))) && grid->topo[0] == OCB_PERIODIC &&
+                    !getenv("OCB_FUSED_CELL_INTEGRALS");
+  const int njy = SP.req[0].hi[1] - SP.req[0].lo[1] + 1;
+  if (sums) {
+    const char* sc = getenv("OCB_SUMS_CONFIG");
+    int a = 0, b = 0, c = 0, d = 0;
+    if (sc) sscanf(sc, "%d,%d,%d,%d", &a, &b, &c, &d);
+    const int key = a * 1000 + b * 100 + c * 10 + d;
+    if (!sc && njy + 1 <= 4) rc = setup_sums<ALL, 2, 2, 3, 4>(fp);          // slab-edge strips: 4-row tiles
+    else if (!sc && mask == (1 << FD_EPS)) rc = setup_sums<(1 << FD_EPS), 8, 3, 3, 1>(fp);
+    else if (!sc && (mask & ~VEL) == 0) rc = setup_sums<VEL, 8, 3, 3, 1>(fp);
+    else if (!sc && (mask & ~VELP) == 0) rc = setup_sums<VELP, 8, 3, 3, 1>(fp);
+    else if (!sc && (mask & ~VELB) == 0) rc = setup_sums<VELB, 8, 3, 3, 1>(fp);
+    else if (key == 8341) rc = setup_sums<ALL, 8, 3, 4, 1>(fp);
+    else if (key == 8431) rc = setup_sums<ALL, 8, 4, 3, 1>(fp);
+    else if (key == 8232) rc = setup_sums<ALL, 8, 2, 3, 2>(fp);
+    else if (key == 8242) rc = setup_sums<ALL, 8, 2, 4, 2>(fp);
+    else if (key == 8322) rc = setup_sums<ALL, 8, 3, 2, 2>(fp);
+    else if (key == 12231) rc = setup_sums<ALL, 12, 2, 3, 1>(fp);
+    else if (key == 16231) rc = setup_sums<ALL, 16, 2, 3, 1>(fp);
+    else if (key == 4432) rc = setup_sums<ALL, 4, 4, 3, 2>(fp);
+    else if (key == 4343) rc = setup_sums<ALL, 4, 3, 4, 3>(fp);
+    else rc = setup_sums<ALL, 8, 3, 3, 1>(fp);
+  } else if (mask & EPVM) {
     if (mask == EPVM) rc = OCB_PICK(EPVM);
     else if ((mask & ~TKEV) == 0) rc = OCB_PICK(TKEV);
     else { delete fp; return OCB_OK; }
@@ -796,6 +839,10 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
   P.tiles_x = (P.Nx + sh + 30) / 31;
   P.jy_lo = SP.req[0].lo[1]; P.jy_hi = SP.req[0].hi[1];
   P.tiles_y = ((P.jy_hi - P.jy_lo + 1) + sh + BR - 2) / (BR - 1);
+  if (fp->sums) {                                              // disjoint 32 x BR tiles over rows jy_lo .. jy_hi + 1
+    P.tiles_x = (P.Nx + 31) / 32;
+    P.tiles_y = (njy + 1 + BR - 1) / BR;
+  }
   const int tiles = P.tiles_x * P.tiles_y;
   P.kz_lo = cell_req >= 0 ? SP.req[cell_req].lo[2] : 1;
   P.kz_hi = cell_req >= 0 ? SP.req[cell_req].hi[2] : grid->N[2];
