@@ -83,13 +83,11 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
   // alpha = [row j in the window], beta = [row j-1 in it], alphan = [row j+1 in it]; rows jy_lo .. jy_hi+1 carry items
   const bool xfull = i0 + 31 <= P.Nx;
   const bool lane_ok = i <= P.Nx;
-  bool rfast[RY], rlive[RY];
+  bool rlive[RY];
 #pragma unroll
-  for (int r = 0; r < RY; ++r) {
-    const int j = j0 + jr0 + r;
-    rlive[r] = j <= P.jy_hi + 1;
-    rfast[r] = xfull && j >= P.jy_lo + 1 && j <= P.jy_hi - 1;
-  }
+  for (int r = 0; r < RY; ++r) rlive[r] = j0 + jr0 + r <= P.jy_hi + 1;
+  // the whole warp is away from the window's y edges (rows jy_lo+1 .. jy_hi-1) in a full x tile: FAST steps
+  const bool tfast = xfull && j0 + jr0 >= P.jy_lo + 1 && j0 + jr0 + RY - 1 <= P.jy_hi - 1;
 
   // pipeline state: the previous plane's centre values and the in-plane + lower-face part of the tracer Laplacian
   double up[RY], vp[RY], wp[RY], bp[RY], pp[RY], CDacc[RY];
@@ -131,9 +129,9 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
       const bool in0 = n >= P.kz_lo && n <= P.kz_hi, in1 = (n - 1) >= P.kz_lo && (n - 1) <= P.kz_hi, in2 = (n - 2) >= P.kz_lo && (n - 2) <= P.kz_hi;
       const bool pfast = own && in0 && in1 && in2;
       const double g0 = (own && in0) ? 1.0 : 0.0, g1 = (own && in1) ? 1.0 : 0.0, g2 = (own && in2) ? 1.0 : 0.0;
-#pragma unroll
-      for (int r = 0; r < RY; ++r) {
-        if (!rlive[r]) continue;
+      // one row of this thread at step n.  FAST (compile-time tag): every class weight is the interior one
+      auto do_row = [&](auto fast_tag, const int r) {
+        constexpr bool FAST = decltype(fast_tag)::value;
         const int o = (row0 + r) * TW + col;
         const double us = r ? uc[r > 0 ? r - 1 : 0] : uS, ws = r ? wc[r > 0 ? r - 1 : 0] : wS;
         const double vn = (r < RY - 1) ? vc[r < RY - 1 ? r + 1 : 0] : vN;
@@ -167,8 +165,7 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
           lap = fma(-dbz, rdz2, CDacc[r]);                 // Laplacian (sign of div q) of the cell below, closed by this face
           CDacc[r] = fma(dbz, rdz2, cdxy);
         }
-        if (pfast && rfast[r]) {
-          // ---- FAST: every class weight is the interior one ----------------------------------------------------------
+        if (FAST) {
           if (H_EPS) {
             aEe = fma(S12, S12, aEe); aEe = fma(S13, S13, aEe); aEe = fma(S23, S23, aEe);
             aEx = fma(ax, ax, aEx); aEy = fma(ay, ay, aEy); aEz = fma(dwz, dwz, aEz);
@@ -183,7 +180,7 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
           if (H_CHI) { aCx = fma(dbx, dbx, aCx); aCy = fma(dby, dby, aCy); aCz = fma(dbz, dbz, aCz); }
           if (H_CDF) aD = fma(bp[r], lap, aD);
         } else if (lane_ok) {
-          // ---- GEN: a window-edge row or plane (or a partly filled x tile): explicit class weights ---------------------
+          // ---- GEN: a window-edge row or plane (or a partly filled x tile): explicit class weights (all one elsewhere) ----
           const int j = j0 + jr0 + r;
           const double al = (j >= P.jy_lo && j <= P.jy_hi) ? 1.0 : 0.0, be = (j - 1 >= P.jy_lo && j - 1 <= P.jy_hi) ? 1.0 : 0.0,
                        an = (j + 1 >= P.jy_lo && j + 1 <= P.jy_hi) ? 1.0 : 0.0;
@@ -211,6 +208,16 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
           if (H_WB) aW = fma(al * hz * wc[r], bp[r] + bc[r], aW);
           if (H_CHI) { aCx = fma(al * g0 * dbx, dbx, aCx); aCy = fma(hy * g0 * dby, dby, aCy); aCz = fma(al * hz * dbz, dbz, aCz); }
           if (H_CDF) aD = fma(al * g1 * bp[r], lap, aD);
+        }
+      };
+      if (pfast && tfast) {
+        // straight-line code over the thread's rows: the compiler interleaves their independent chains
+#pragma unroll
+        for (int r = 0; r < RY; ++r) do_row(std::true_type{}, r);
+      } else {
+#pragma unroll
+        for (int r = 0; r < RY; ++r) {
+          if (rlive[r]) do_row(std::false_type{}, r);
         }
       }
     }

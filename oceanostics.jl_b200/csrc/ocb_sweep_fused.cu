@@ -597,6 +597,7 @@ struct ocb_fused_plan {
   CUtensorMap maps[5];
   int mask, nw, ry, ns;
   bool sums;                       // ocb_budget_sums_kernel (integral-only class sums) instead of ocb_budget_kernel
+  int minb;                        // resident blocks per SM the sums kernel was compiled for
   int nblocks;
   size_t smem;
   void (*kernel)(FusedParams, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap);
@@ -627,7 +628,7 @@ static int setup_sums(ocb_fused_plan* fp) {
   using G = Geo<NW, RY>;
   constexpr bool NEED_B = MASK & ((1 << FD_WB) | (1 << FD_CHI) | (1 << FD_CDF)), NEED_P = MASK & (1 << FD_PR);
   constexpr int NF = 3 + (NEED_B ? 1 : 0) + (NEED_P ? 1 : 0);
-  fp->nw = NW; fp->ry = RY; fp->ns = NS; fp->mask = MASK; fp->sums = true;
+  fp->nw = NW; fp->ry = RY; fp->ns = NS; fp->mask = MASK; fp->sums = true; fp->minb = MINB;
   fp->smem = sizeof(double) * ((size_t)NS * NF * G::TILE + NW) + sizeof(uint64_t) * NS;
   auto kern = ocb_budget_sums_kernel<MASK, NW, RY, NS, MINB>;
   cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
@@ -796,6 +797,7 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
     else if (!sc && (mask & ~VEL) == 0) rc = setup_sums<VEL, 8, 3, 3, 1>(fp);
     else if (!sc && (mask & ~VELP) == 0) rc = setup_sums<VELP, 8, 3, 3, 1>(fp);
     else if (!sc && (mask & ~VELB) == 0) rc = setup_sums<VELB, 8, 3, 3, 1>(fp);
+    else if (key == 8331) rc = setup_sums<ALL, 8, 3, 3, 1>(fp);
     else if (key == 8341) rc = setup_sums<ALL, 8, 3, 4, 1>(fp);
     else if (key == 8431) rc = setup_sums<ALL, 8, 4, 3, 1>(fp);
     else if (key == 8232) rc = setup_sums<ALL, 8, 2, 3, 2>(fp);
@@ -805,7 +807,15 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
     else if (key == 16231) rc = setup_sums<ALL, 16, 2, 3, 1>(fp);
     else if (key == 4432) rc = setup_sums<ALL, 4, 4, 3, 2>(fp);
     else if (key == 4343) rc = setup_sums<ALL, 4, 3, 4, 3>(fp);
-    else rc = setup_sums<ALL, 8, 3, 3, 1>(fp);
+    else if (key == 4442) rc = setup_sums<ALL, 4, 4, 4, 2>(fp);
+    else if (key == 4532) rc = setup_sums<ALL, 4, 5, 3, 2>(fp);
+    else if (key == 4631) rc = setup_sums<ALL, 4, 6, 3, 1>(fp);
+    else if (key == 4433) rc = setup_sums<ALL, 4, 4, 3, 3>(fp);
+    else if (key == 2834) rc = setup_sums<ALL, 2, 8, 3, 4>(fp);
+    else if (key == 2634) rc = setup_sums<ALL, 2, 6, 3, 4>(fp);
+    else if (key == 6431) rc = setup_sums<ALL, 6, 4, 3, 1>(fp);
+    else if (key == 3443) rc = setup_sums<ALL, 3, 4, 4, 3>(fp);
+    else rc = setup_sums<ALL, 4, 4, 3, 2>(fp);                              // measured best at 1024^3 (profiles/r1_summary.md)
   } else if (mask & EPVM) {
     if (mask == EPVM) rc = OCB_PICK(EPVM);
     else if ((mask & ~TKEV) == 0) rc = OCB_PICK(TKEV);
@@ -853,6 +863,20 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
   if (nchunks < 1) nchunks = 1;
   int kchunk = (nz_win + nchunks - 1) / nchunks;
   if (kchunk < 32) kchunk = nz_win < 32 ? nz_win : 32;
+  if (fp->sums) {
+    // z chunks of the class-sum kernel: the chunk count with the fewest block waves x planes per block (each chunk
+    // re-reads two warm-up planes; the last wave of a launch is partly empty)
+    const long long slots = (long long)ocb_sm_count() * fp->minb;
+    long long best = -1;
+    for (int nc = 1; nc <= 16; ++nc) {
+      int kc = (nz_win + nc - 1) / nc;
+      if (kc < 32) kc = nz_win < 32 ? nz_win : 32;
+      const int ncr = (nz_win + kc - 1) / kc;
+      const long long waves = ((long long)tiles * ncr + slots - 1) / slots;
+      const long long cost = waves * (kc + 3) * 16 + nc;          // ties: fewer chunks
+      if (best < 0 || cost < best) { best = cost; kchunk = kc; }
+    }
+  }
   if (const char* kc = getenv("OCB_FUSED_KCHUNK")) kchunk = atoi(kc) > 0 ? atoi(kc) : kchunk;
   P.kchunk = kchunk;
   P.nchunks = (nz_win + kchunk - 1) / kchunk;
