@@ -89,10 +89,14 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
   // the whole warp is away from the window's y edges (rows jy_lo+1 .. jy_hi-1) in a full x tile: FAST steps
   const bool tfast = xfull && j0 + jr0 >= P.jy_lo + 1 && j0 + jr0 + RY - 1 <= P.jy_hi - 1;
 
-  // pipeline state: the previous plane's centre values and the in-plane + lower-face part of the tracer Laplacian
-  double up[RY], vp[RY], wp[RY], bp[RY], pp[RY], CDacc[RY];
+  // pipeline state: the centre values of this plane and of the previous one in two register sets that swap roles from
+  // step to step (the plane loop is unrolled by two, so nothing is copied), and the in-plane + lower-face part of the
+  // tracer Laplacian
+  double cu[2][RY], cv[2][RY], cw[2][RY], cb[2][RY], cp[2][RY], CDacc[RY];
 #pragma unroll
-  for (int r = 0; r < RY; ++r) up[r] = vp[r] = wp[r] = bp[r] = pp[r] = CDacc[r] = 0.0;
+  for (int r = 0; r < RY; ++r) {
+    cu[0][r] = cv[0][r] = cw[0][r] = cb[0][r] = cp[0][r] = cu[1][r] = cv[1][r] = cw[1][r] = cb[1][r] = cp[1][r] = CDacc[r] = 0.0;
+  }
   // class sums, normalised to the interior weights (the closing lines of the kernel give each one its factor)
   double aEe = 0.0, aEx = 0.0, aEy = 0.0, aEz = 0.0;       // S12^2 + S13^2 + S23^2 | (dx u)^2 | (dy v)^2 | (dz w)^2   (undivided differences)
   double aAe = 0.0, aAx = 0.0, aAy = 0.0, aAz = 0.0;       // P12 S12 + P13 S13 + P23 S23 | Uu dxu | Vv dyv | Ww dzw
@@ -103,7 +107,10 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
 
   int s = 0;
   uint32_t phase = 0;
-  for (int n = n_first; n <= n_last; ++n) {
+  auto step = [&](auto par_tag, const int n) {
+    constexpr int C = decltype(par_tag)::value, Q = 1 - C;
+    double (&uc)[RY] = cu[C], (&vc)[RY] = cv[C], (&wc)[RY] = cw[C], (&bc)[RY] = cb[C], (&pc)[RY] = cp[C];
+    double (&up)[RY] = cu[Q], (&vp)[RY] = cv[Q], (&wp)[RY] = cw[Q], (&bp)[RY] = cb[Q], (&pp)[RY] = cp[Q];
     mbar_wait(&full[s], phase);
     const double* T = tiles + s * (NF * G::TILE);
     const double* Tu = T, *Tv = T + G::TILE, *Tw = T + 2 * G::TILE, *Tb = T + F_B * G::TILE, *Tp = T + F_P * G::TILE;
@@ -112,7 +119,6 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
     const int row0 = jr0 + 1;                              // tile row of this thread's first cell
 
     // ---- centre values of the thread's rows, the row to the south and the row to the north ----------------------------
-    double uc[RY], vc[RY], wc[RY], bc[RY], pc[RY];
 #pragma unroll
     for (int r = 0; r < RY; ++r) {
       const int o = (row0 + r) * TW + col;
@@ -221,14 +227,14 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
         }
       }
     }
-#pragma unroll
-    for (int r = 0; r < RY; ++r) {
-      up[r] = uc[r]; vp[r] = vc[r]; wp[r] = wc[r];
-      if (NEED_B) bp[r] = bc[r];
-      if (NEED_P) pp[r] = pc[r];
-    }
     __syncthreads();
     if (tid == 0 && n + NS <= n_last) issue(n + NS);       // every thread is done with this ring slot: refill it
+  };
+  for (int n = n_first;;) {
+    step(std::integral_constant<int, 0>{}, n);
+    if (++n > n_last) break;
+    step(std::integral_constant<int, 1>{}, n);
+    if (++n > n_last) break;
   }
 
   // ---- class sums -> the seven integrals (per-cell scale factors of the reference formulas folded in) ---------------
