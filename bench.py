@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="N>1: exchange halos before the sweep instead of behind its interior rows")
+    ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
+                    help="N>1 halo exchange: direct stores into the neighbours' halos over NVLink (CUDA IPC), or NCCL send/recv")
     ap.add_argument("--cpu-size", type=int, default=256, help="edge of the CPU-baseline sample cube")
     return ap.parse_args()
 
@@ -146,7 +148,10 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=device)
+        # NCCL's internal stream at high priority: its send / recv blocks are placed ahead of the sweep's pending blocks
+        # whenever an SM frees up, so the ring exchange stays hidden behind the interior rows
+        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        dist.init_process_group("nccl", device_id=device, pg_options=opts)
     size = tuple(args.size) if args.size else (1024, 1024, 1024)
     # weak scaling: every rank owns a full `size` slab stack => the job is size[0] x (size[1]*world) x size[2]
     job = (size[0], size[1] * world, size[2])
@@ -172,7 +177,11 @@ def main():
     if world > 1 and not args.fields and not args.no_overlap:
         from oceanostics_b200.distributed import OverlappedSlabBudget
         overlapped = OverlappedSlabBudget(grid, [m.velocities.u, m.velocities.v, m.velocities.w, m.tracers.b, m.pressures.pNHS],
-                                          lambda: budget_ops(ocb, m), depth=2, rank=rank, world=world)
+                                          lambda: budget_ops(ocb, m), depth=2, rank=rank, world=world, transport=args.transport)
+    elif world > 1 and args.transport == "peer":
+        from oceanostics_b200.distributed import PeerSlabExchanger
+        exchanger = PeerSlabExchanger(grid, [m.velocities.u, m.velocities.v, m.velocities.w, m.tracers.b, m.pressures.pNHS],
+                                      depth=2, rank=rank, world=world)
 
     def step():
         if overlapped is not None:
@@ -209,6 +218,13 @@ def main():
         ev1.record()
         torch.cuda.synchronize()
     total_ms = ev0.elapsed_time(ev1)
+    timeline = None
+    if overlapped is not None:       # one more (untimed) step with event marks: where the exchange ends relative to the sweep
+        tl = {}
+        overlapped.step()
+        overlapped.step(timeline=tl)
+        torch.cuda.synchronize()
+        timeline = overlapped.timeline_ms(tl)
     if overlapped is None:
         sweep_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
     else:
@@ -257,15 +273,20 @@ def main():
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                      "traffic": traffic, "kernel_ms": round(sweep_ms, 4), "algorithmic_bytes_per_cell": plan.algorithmic_bytes / cells_local,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
-        "gpu_launches": ((3 if overlapped is not None else 1) * plan.n_launches + (4 * 5 if exchanger is not None else 0)) * args.steps,
+        "gpu_launches": ((3 if overlapped is not None else 1) * plan.n_launches + ((3 if args.transport == "peer" else 2) if exchanger is not None else 0)) * args.steps,   # + push, signal, wait | pack_many, unpack_many
         "clocks": clocks.summary(),
         "integrals": integrals,
     }
     if world > 1:
-        out["comm"] = {"step_minus_sweep_ms": round(ms_per_step - sweep_ms, 4), "overlapped": overlapped is not None,
+        out["comm"] = {"step_minus_sweep_ms": round(ms_per_step - sweep_ms, 4), "overlapped": overlapped is not None, "timeline_ms": timeline,
                        "halo_bytes_per_rank_per_step": exchanger.bytes_per_exchange,
-                       "note": "exchange (pack, grouped NCCL send/recv ring, unpack) + all-reduce of the 7 integrals; when overlapped it "
-                               "runs on a side stream behind the interior rows and only the edge strips wait for it"}
+                       "transport": args.transport,
+                       "note": "exchange (peer: one kernel storing the edge rows into the neighbours' halos over NVLink + flag words; nccl: "
+                               "pack, grouped send/recv ring, unpack) + all-reduce of the 7 integrals; when overlapped it runs on a side "
+                               "stream behind the interior rows and only the edge strips wait for it"}
+        px = overlapped.exchanger if overlapped is not None else exchanger
+        if hasattr(px, "check"):
+            px.check()                                   # a halo wait that timed out invalidates the run
     # ---- end to end with HOST inputs: every rank streams its own slab from pinned host memory -----------------------
     e2e = None
     if not args.no_e2e:

@@ -263,6 +263,29 @@ int ocb_pointwise(const ocb_grid* grid, int32_t op, double alpha, const ocb_fiel
  * layer on the same stream. */
 int ocb_halo_pack_y(int32_t dtype, const ocb_field* field, int32_t side, int32_t h, void* buffer, void* stream);
 int ocb_halo_unpack_y(int32_t dtype, const ocb_field* field, int32_t side, int32_t h, const void* buffer, void* stream);
+/* the same for both edges of up to 8 fields in one launch: buffers[2*f + side]; unpack = 0 packs the interior edge
+ * planes, unpack = 1 writes the buffers into the halo planes (the overlapped slab step of the multi-GPU path) */
+int ocb_halo_pack_y_many(int32_t dtype, const ocb_field* fields, int32_t n_fields, int32_t h, void* const* buffers,
+                         int32_t unpack, void* stream);
+
+/* ---- direct peer-memory halo exchange (one process per GPU of one box, CUDA IPC over NVLink) ----
+ * ocb_ipc_export: the 64-byte cudaIpcMemHandle_t of the allocation holding `ptr` and ptr's byte offset inside it (the host
+ * layer sends both to the neighbour ranks); ocb_ipc_import maps a received handle (peer access enabled lazily) and returns
+ * the allocation base; ocb_ipc_close unmaps it.
+ * ocb_halo_push_y_many: ONE kernel stores the `h` edge rows of every field into the neighbours' halo rows --
+ * peer_arrays[2*f + side] is the neighbour's parent array of field f (side 0 = low-y neighbour, 1 = high-y neighbour),
+ * peer_ny[2*f + side] its interior length along y -- then publishes `step` in the neighbours' flag words (lo_flag = the low
+ * neighbour's flags[1], hi_flag = the high neighbour's flags[0]).
+ * ocb_halo_wait: stream-ordered wait until both of this rank's flag words (flags[0] from the low neighbour, flags[1] from
+ * the high one) reach `step`; after `timeout_seconds` it sets flags[2] = 1 and returns (the host layer checks it).
+ * Ordering contract: a push for step k+1 must be enqueued after a collective every rank enters after its step-k reads of the
+ * halo rows (e.g. the all-reduce of the integrals). */
+int ocb_ipc_export(const void* ptr, void* handle64, int64_t* offset);
+int ocb_ipc_import(const void* handle64, void** base);
+int ocb_ipc_close(void* base);
+int ocb_halo_push_y_many(int32_t dtype, const ocb_field* fields, int32_t n_fields, int32_t h, void* const* peer_arrays,
+                         const int32_t* peer_ny, void* lo_flag, void* hi_flag, int64_t step, void* stream);
+int ocb_halo_wait(void* flags, int64_t step, double timeout_seconds, void* stream);
 
 #ifdef __cplusplus
 }

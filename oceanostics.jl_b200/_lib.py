@@ -122,9 +122,17 @@ def lib():
     L.ocb_pointwise.argtypes = [P(ocb_grid), C.c_int32, C.c_double, P(ocb_field), P(ocb_field), P(ocb_field), C.c_void_p]
     L.ocb_halo_pack_y.argtypes = [C.c_int32, P(ocb_field), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     L.ocb_halo_unpack_y.argtypes = [C.c_int32, P(ocb_field), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    L.ocb_halo_pack_y_many.argtypes = [C.c_int32, P(ocb_field), C.c_int32, C.c_int32, P(C.c_void_p), C.c_int32, C.c_void_p]
+    L.ocb_ipc_export.argtypes = [C.c_void_p, C.c_void_p, P(C.c_int64)]
+    L.ocb_ipc_import.argtypes = [C.c_void_p, P(C.c_void_p)]
+    L.ocb_ipc_close.argtypes = [C.c_void_p]
+    L.ocb_halo_push_y_many.argtypes = [C.c_int32, P(ocb_field), C.c_int32, C.c_int32, P(C.c_void_p), P(C.c_int32), C.c_void_p, C.c_void_p,
+                                       C.c_int64, C.c_void_p]
+    L.ocb_halo_wait.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_void_p]
     for name in ("ocb_plan_create", "ocb_plan_execute", "ocb_plan_destroy", "ocb_plan_info", "ocb_fill_halo",
                  "ocb_filter_execute", "ocb_bpe_reference_height", "ocb_sort_pairs", "ocb_pointwise",
-                 "ocb_halo_pack_y", "ocb_halo_unpack_y", "ocb_gather_sorted", "ocb_bpe_profile_lookup"):
+                 "ocb_halo_pack_y", "ocb_halo_unpack_y", "ocb_halo_pack_y_many", "ocb_gather_sorted", "ocb_bpe_profile_lookup",
+                 "ocb_ipc_export", "ocb_ipc_import", "ocb_ipc_close", "ocb_halo_push_y_many", "ocb_halo_wait"):
         getattr(L, name).restype = C.c_int
     if L.ocb_abi_version() != 1:
         raise OcbError("liboceanostics_b200.so ABI version mismatch")
@@ -135,7 +143,8 @@ def lib():
 EXPORTED_SYMBOLS = ["ocb_abi_version", "ocb_last_error", "ocb_device_count", "ocb_plan_create", "ocb_plan_execute",
                     "ocb_plan_destroy", "ocb_plan_info", "ocb_fill_halo", "ocb_filter_execute",
                     "ocb_bpe_reference_height", "ocb_sort_pairs", "ocb_pointwise", "ocb_halo_pack_y", "ocb_halo_unpack_y",
-                    "ocb_gather_sorted", "ocb_bpe_profile_lookup"]
+                    "ocb_halo_pack_y_many", "ocb_gather_sorted", "ocb_bpe_profile_lookup", "ocb_ipc_export", "ocb_ipc_import",
+                    "ocb_ipc_close", "ocb_halo_push_y_many", "ocb_halo_wait"]
 
 
 def check(status: int):

@@ -38,6 +38,15 @@ def _unpack_cuda(field, side, h, buf):
     _lib.check(L.ocb_halo_unpack_y(dt, C.byref(d), side, h, buf.data_ptr(), current_stream_ptr(field.data.device)))
 
 
+def _pack_many_cuda(fields, h, buffers, unpack):
+    """Both edges of every field in one launch (ocb_halo_pack_y_many): buffers[2*f + side]."""
+    L = _lib.lib()
+    descs = (_lib.ocb_field * len(fields))(*[f.descriptor() for f in fields])
+    ptrs = (C.c_void_p * len(buffers))(*[b.data_ptr() for b in buffers])
+    dt = _lib.OCB_F64 if fields[0].data.dtype == torch.float64 else _lib.OCB_F32
+    _lib.check(L.ocb_halo_pack_y_many(dt, descs, len(fields), h, ptrs, 1 if unpack else 0, current_stream_ptr(fields[0].data.device)))
+
+
 class SlabHaloExchanger:
     """Exchange `depth` y-planes of each field with the ring neighbours.
 
@@ -66,9 +75,14 @@ class SlabHaloExchanger:
 
     def exchange(self):
         h = self.h
-        for f, slo, shi in zip(self.fields, self.send_lo, self.send_hi):
-            self.pack(f, 0, h, slo)       # my low-edge interior planes -> the low neighbour's high halo
-            self.pack(f, 1, h, shi)       # my high-edge interior planes -> the high neighbour's low halo
+        batched = self.pack is _pack_cuda and self.unpack is _unpack_cuda and len(self.fields) <= 8 and \
+            len({f.data.dtype for f in self.fields}) == 1
+        if batched:      # one launch for all fields and both edges
+            _pack_many_cuda(self.fields, h, [b for pair in zip(self.send_lo, self.send_hi) for b in pair], unpack=False)
+        else:
+            for f, slo, shi in zip(self.fields, self.send_lo, self.send_hi):
+                self.pack(f, 0, h, slo)       # my low-edge interior planes -> the low neighbour's high halo
+                self.pack(f, 1, h, shi)       # my high-edge interior planes -> the high neighbour's low halo
         if self.world == 1:
             for slo, shi, rlo, rhi in zip(self.send_lo, self.send_hi, self.recv_lo, self.recv_hi):
                 rhi.copy_(slo)
@@ -82,9 +96,91 @@ class SlabHaloExchanger:
                 ops.append(dist.P2POp(dist.irecv, rlo, self.lo_rank, self.group))
             for req in dist.batch_isend_irecv(ops):   # one grouped NCCL launch for all fields and both directions
                 req.wait()
-        for f, rlo, rhi in zip(self.fields, self.recv_lo, self.recv_hi):
-            self.unpack(f, 0, h, rlo)
-            self.unpack(f, 1, h, rhi)
+        if batched:
+            _pack_many_cuda(self.fields, h, [b for pair in zip(self.recv_lo, self.recv_hi) for b in pair], unpack=True)
+        else:
+            for f, rlo, rhi in zip(self.fields, self.recv_lo, self.recv_hi):
+                self.unpack(f, 0, h, rlo)
+                self.unpack(f, 1, h, rhi)
+
+
+class PeerSlabExchanger:
+    """The same ring exchange by direct stores into the neighbours' halo rows over NVLink (CUDA IPC, one process per GPU of
+    one box): ONE kernel per step instead of pack + NCCL send/recv + unpack, then a flag word per neighbour.
+
+    `push()` stores this rank's edge rows into both neighbours and publishes the step number; `wait()` is a stream-ordered
+    wait for both neighbours' pushes of the current step.  Ordering contract (include/oceanostics_b200.h): the next push must
+    follow a collective that every rank enters after it has read its halos (here: the all-reduce of the integrals)."""
+
+    def __init__(self, grid, fields, depth=2, rank=None, world=None, group=None, timeout=10.0):
+        self.grid, self.fields, self.h, self.group, self.timeout = grid, list(fields), int(depth), group, float(timeout)
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        if self.h < 1 or self.h > grid.H[1]:
+            raise ValueError(f"exchange depth {depth} must be within 1..halo ({grid.H[1]})")
+        if len(self.fields) > 8 or len({f.data.dtype for f in self.fields}) != 1:
+            raise ValueError("the peer exchange takes up to 8 fields of one dtype")
+        dev = grid.device
+        if dev.type != "cuda":
+            raise _lib.OcbError("the peer-memory exchange needs CUDA devices (no CPU fallback)")
+        self.lo_rank, self.hi_rank = (self.rank - 1) % self.world, (self.rank + 1) % self.world
+        self.flags = torch.zeros(4, dtype=torch.int64, device=dev)   # [from low, from high, timed out, unused]
+        self.step_no = 0
+        self._opened = {}
+        L = _lib.lib()
+        ny = int(grid.N[1])
+        if self.world == 1:
+            peers = {self.rank: {"fields": [(f.data.data_ptr(), ny) for f in self.fields], "flags": self.flags.data_ptr()}}
+        else:
+            torch.cuda.synchronize(dev)
+
+            def export(t):
+                handle, off = (C.c_ubyte * 64)(), C.c_int64()
+                _lib.check(L.ocb_ipc_export(t.data_ptr(), handle, C.byref(off)))
+                return bytes(handle), off.value
+            mine = {"fields": [export(f.data) + (ny,) for f in self.fields], "flags": export(self.flags)}
+            everyone = [None] * self.world
+            dist.all_gather_object(everyone, mine, group=group)
+
+            def mapped(r, handle, off):
+                if (r, handle) not in self._opened:
+                    base = C.c_void_p()
+                    _lib.check(L.ocb_ipc_import((C.c_ubyte * 64)(*handle), C.byref(base)))
+                    self._opened[(r, handle)] = base.value
+                return self._opened[(r, handle)] + off
+            peers = {r: {"fields": [(mapped(r, hd, off), n) for hd, off, n in everyone[r]["fields"]],
+                         "flags": mapped(r, *everyone[r]["flags"])} for r in {self.lo_rank, self.hi_rank}}
+            dist.barrier(group=group)
+        lo, hi = peers[self.lo_rank], peers[self.hi_rank]
+        nf = len(self.fields)
+        self._ptrs = (C.c_void_p * (2 * nf))(*[p for f in range(nf) for p in (lo["fields"][f][0], hi["fields"][f][0])])
+        self._nys = (C.c_int32 * (2 * nf))(*[n for f in range(nf) for n in (lo["fields"][f][1], hi["fields"][f][1])])
+        self._lo_flag, self._hi_flag = lo["flags"] + 8, hi["flags"]      # I am my low neighbour's high neighbour
+        self._descs = (_lib.ocb_field * nf)(*[f.descriptor() for f in self.fields])
+        self._dt = _lib.OCB_F64 if self.fields[0].data.dtype == torch.float64 else _lib.OCB_F32
+        self.bytes_per_exchange = sum(2 * f.data.shape[0] * self.h * f.data.shape[2] * f.data.element_size() for f in self.fields)
+
+    def push(self):
+        self.step_no += 1
+        _lib.check(_lib.lib().ocb_halo_push_y_many(self._dt, self._descs, len(self.fields), self.h, self._ptrs, self._nys, self._lo_flag,
+                                                   self._hi_flag, self.step_no, current_stream_ptr(self.grid.device)))
+
+    def wait(self):
+        _lib.check(_lib.lib().ocb_halo_wait(self.flags.data_ptr(), self.step_no, self.timeout, current_stream_ptr(self.grid.device)))
+
+    def exchange(self):
+        self.push()
+        self.wait()
+
+    def check(self):
+        """After a device synchronize: raise if a wait gave up (a neighbour never pushed)."""
+        if int(self.flags[2].item()) != 0:
+            raise _lib.OcbError("halo exchange: a neighbour's rows did not arrive within the timeout")
+
+    def close(self):
+        for base in self._opened.values():
+            _lib.lib().ocb_ipc_close(base)
+        self._opened = {}
 
 
 def allreduce_integrals(integrals: torch.Tensor, group=None):
@@ -101,10 +197,13 @@ class OverlappedSlabBudget:
     while the ring exchange (pack, NCCL send/recv, unpack) runs on a side stream; the two `depth`-row strips next to
     the slab edges are swept afterwards and the three partial integral vectors are added before the all-reduce."""
 
-    def __init__(self, grid, fields, make_ops, depth=2, rank=None, world=None, group=None):
+    def __init__(self, grid, fields, make_ops, depth=2, rank=None, world=None, group=None, transport="nccl"):
         from .operations import FusedDiagnostics, Integral
-        self.grid, self.group = grid, group
-        self.exchanger = SlabHaloExchanger(grid, fields, depth=depth, rank=rank, world=world, group=group)
+        self.grid, self.group, self.transport = grid, group, transport
+        if transport == "peer":        # direct stores into the neighbours' halos; the all-reduce below orders their re-use
+            self.exchanger = PeerSlabExchanger(grid, fields, depth=depth, rank=rank, world=world, group=group)
+        else:
+            self.exchanger = SlabHaloExchanger(grid, fields, depth=depth, rank=rank, world=world, group=group)
         Ny = grid.N[1]
         if Ny < 4 * depth:
             raise ValueError("slab too thin to overlap the exchange")
@@ -112,25 +211,44 @@ class OverlappedSlabBudget:
         win = lambda lo, hi: FusedDiagnostics(*[Integral(o, indices=(None, (lo, hi), None)) for o in ops])
         self.interior = win(1 + depth, Ny - depth)
         self.low, self.high = win(1, depth), win(Ny - depth + 1, Ny)
-        self.comm_stream = torch.cuda.Stream(device=grid.device)
+        self.comm_stream = torch.cuda.Stream(device=grid.device, priority=-1)   # pack / unpack ahead of the sweep's blocks
         self.done = torch.cuda.Event()
         self.total = torch.zeros(len(ops), dtype=torch.float64, device=grid.device)
         self.n = len(ops)
 
-    def step(self):
+    def step(self, timeline=None):
+        """One overlapped step.  `timeline` (a dict) receives CUDA events marking the start, the end of the exchange (side
+        stream), the end of the interior sweep, of the edge strips and of the all-reduce -- see `timeline_ms`."""
         cur = torch.cuda.current_stream(self.grid.device)
+        mark = (lambda name, stream: None) if timeline is None else (
+            lambda name, stream: timeline.setdefault(name, torch.cuda.Event(enable_timing=True)).record(stream))
+        mark("start", cur)
         self.comm_stream.wait_stream(cur)
         with torch.cuda.stream(self.comm_stream):
-            self.exchanger.exchange()
+            if self.transport == "peer":
+                self.exchanger.push()
+            else:
+                self.exchanger.exchange()
             self.done.record(self.comm_stream)
+            mark("exchange_end", self.comm_stream)
         self.interior.plan.execute()                      # overlaps the exchange
+        mark("interior_end", cur)
         cur.wait_event(self.done)
+        if self.transport == "peer":
+            self.exchanger.wait()                         # the neighbours' rows of this step have landed
         self.low.plan.execute()
         self.high.plan.execute()
+        mark("strips_end", cur)
         torch.add(self.interior.plan.integrals[:self.n], self.low.plan.integrals[:self.n], out=self.total)
         self.total.add_(self.high.plan.integrals[:self.n])
         allreduce_integrals(self.total, self.group)
+        mark("end", cur)
         return self.total
+
+    @staticmethod
+    def timeline_ms(timeline):
+        """Milliseconds from the start of a step recorded with `step(timeline=...)` (after a device synchronize)."""
+        return {k: round(timeline["start"].elapsed_time(v), 4) for k, v in timeline.items() if k != "start"}
 
 
 def _axis_spec(grid, d):

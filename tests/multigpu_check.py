@@ -60,6 +60,30 @@ def main():
         f.data[:, :3, :] = 0.0
         f.data[:, -3:, :] = 0.0
     ov_total = ov.step().clone()
+    # ---- the same step with the direct peer-memory exchange (CUDA IPC stores into the neighbours' halos) ---------------
+    from oceanostics_b200.distributed import PeerSlabExchanger
+    before = [f.data.clone() for f in flds]              # halos as NCCL left them
+    for f in flds:
+        f.data[:, :3, :] = 0.0
+        f.data[:, -3:, :] = 0.0
+    torch.cuda.synchronize(); dist.barrier()
+    px = PeerSlabExchanger(g, flds, depth=2, rank=rank, world=world)
+    px.exchange()
+    torch.cuda.synchronize(); dist.barrier()
+    px.check()
+    peer_same = all(torch.equal(f.data[:, 1:3, :], b[:, 1:3, :]) and torch.equal(f.data[:, -3:-1, :], b[:, -3:-1, :]) for f, b in zip(flds, before))
+    ovp = OverlappedSlabBudget(g, flds, lambda: budget_ops(m), depth=2, rank=rank, world=world, transport="peer")
+    for f in flds:
+        f.data[:, :3, :] = 0.0
+        f.data[:, -3:, :] = 0.0
+    torch.cuda.synchronize(); dist.barrier()
+    ovp_total = None
+    for _ in range(3):                                   # repeated steps: the flag words count up, the all-reduce orders re-use
+        ovp_total = ovp.step().clone()
+    torch.cuda.synchronize()
+    ovp.exchanger.check()
+    p_ok = torch.tensor([1.0 if peer_same else 0.0], device=dev)
+    dist.all_reduce(p_ok, op=dist.ReduceOp.MIN)
     # ---- slab filter: the y pass reaches 5 rows into each neighbour (exchanged over NCCL) -------------------------
     from oceanostics_b200.distributed import SlabFilteredField
     SF = ocb.SpatialFilters
@@ -71,7 +95,7 @@ def main():
     f_err = float((slab_f.interior - want_f).abs().max()) / float(want_f.abs().max())
     f_ok = torch.tensor([1.0 if f_err <= 1e-14 else 0.0], device=dev)
     dist.all_reduce(f_ok, op=dist.ReduceOp.MIN)
-    ok = bool(f_ok.item() > 0)
+    ok = bool(f_ok.item() > 0) and bool(p_ok.item() > 0)
     if rank == 0:
         print("slab filter max rel err", f_err, flush=True)
         _, mg, _ = model_on(1, Ny, full=True)
@@ -83,6 +107,9 @@ def main():
             ok &= abs(a - b) <= 1e-12 * s
         for a, b, s in zip(ov_total.cpu().numpy(), want, scales):
             ok &= abs(a - b) <= 1e-12 * s
+        for a, b, s in zip(ovp_total.cpu().numpy(), want, scales):
+            ok &= abs(a - b) <= 1e-12 * s
+        print("peer exchange equals NCCL exchange:", bool(p_ok.item() > 0), flush=True)
         print("MULTIGPU_CHECK", "OK" if ok else "FAIL", got.tolist(), want.tolist(), flush=True)
     dist.barrier()
     dist.destroy_process_group()

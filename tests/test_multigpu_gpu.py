@@ -71,6 +71,64 @@ def test_self_exchange_equals_periodic_fill():
     assert torch.equal(f.data[H:-H], want[H:-H])
 
 
+def test_peer_self_exchange_equals_periodic_fill():
+    """A ring of one rank through the peer-memory path (push kernel + flag words + stream-ordered wait): the slab's own
+    edge rows land in its own halos, i.e. the periodic fill; repeated steps count the flags up and never time out."""
+    from oceanostics_b200.distributed import PeerSlabExchanger
+    st = State(size=(32, 16, 8), device="cuda")
+    fields = []
+    for src in (st.u, st.w, st.b):
+        f = ocb.Field(src.location, st.pg)
+        f.data.copy_(src.data)
+        f.data[:, :3, :] = -1.0
+        f.data[:, -3:, :] = -1.0
+        fields.append(f)
+    px = PeerSlabExchanger(st.pg, fields, depth=3, rank=0, world=1, timeout=2.0)
+    for _ in range(3):
+        px.exchange()
+    torch.cuda.synchronize()
+    px.check()
+    assert px.step_no == 3 and px.flags[:3].tolist() == [3, 3, 0]
+    for f, src in zip(fields, (st.u, st.w, st.b)):
+        assert torch.equal(f.data[3:-3], src.data[3:-3])
+    # a wait for a step nobody pushed gives up after the timeout and reports it
+    px.step_no += 1
+    px.timeout = 0.05
+    px.wait()
+    torch.cuda.synchronize()
+    with pytest.raises(ocb.OcbError, match="did not arrive"):
+        px.check()
+
+
+def test_batched_pack_equals_the_per_field_kernels():
+    """ocb_halo_pack_y_many (both edges of all fields in one launch) fills the same buffers, and writes the same halo rows,
+    as ocb_halo_pack_y / ocb_halo_unpack_y called field by field (u is Face in x, w has Nz + 1 levels: different shapes)."""
+    from oceanostics_b200.distributed import _pack_cuda, _unpack_cuda, _pack_many_cuda
+    st = State(size=(32, 16, 8), device="cuda")
+    fields = [st.u, st.v, st.w, st.b, st.p]
+    h = 2
+    mk = lambda f: torch.zeros((f.data.shape[0], h, f.data.shape[2]), dtype=torch.float64, device="cuda")
+    one = [[mk(f), mk(f)] for f in fields]
+    many = [[mk(f), mk(f)] for f in fields]
+    for f, (lo, hi) in zip(fields, one):
+        _pack_cuda(f, 0, h, lo); _pack_cuda(f, 1, h, hi)
+    _pack_many_cuda(fields, h, [b for pair in many for b in pair], unpack=False)
+    torch.cuda.synchronize()
+    for a, b in zip(one, many):
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and float(a[0].abs().sum()) > 0
+    # unpack: swap the buffers (a ring of one) and compare the halo rows written by the two paths
+    ref = []
+    for f, (lo, hi) in zip(fields, one):
+        g = f.data.clone()
+        _unpack_cuda(f, 0, h, hi); _unpack_cuda(f, 1, h, lo)
+        ref.append(f.data.clone())
+        f.data.copy_(g)
+    _pack_many_cuda(fields, h, [b for lo, hi in many for b in (hi, lo)], unpack=True)
+    torch.cuda.synchronize()
+    for f, want in zip(fields, ref):
+        assert torch.equal(f.data, want)
+
+
 def test_host_streamed_budget_matches_resident_sweep():
     from oceanostics_b200.streaming import HostStreamedBudget
     st = State(size=(64, 40, 36), device="cuda")
