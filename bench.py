@@ -252,11 +252,12 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = plan.algorithmic_bytes / (sweep_ms * 1e-3) / 1e9
-    # DRAM traffic of one launch of the sweep kernel, from the committed ncu capture of this exact workload
-    # (profiles/r1_traffic_bench1024_v13.csv: dram__bytes_read.sum + dram__bytes_write.sum); null for other shapes
+    # DRAM traffic of one launch of the sweep kernel, from the committed ncu captures of this exact workload
+    # (dram__bytes_read.sum + dram__bytes_write.sum; class-sum kernel: profiles/r1_launches_bench1024_sums_v2.csv, mean of
+    # five launches; with output fields: profiles/r1_ncu_budget1024_fields_v13_metrics.csv); null for other shapes
     traffic = None
-    if size == (1024, 1024, 1024) and not args.fields and plan.variant == 1:
-        traffic = 46392537344 + 32416000
+    if size == (1024, 1024, 1024) and plan.variant == 1:
+        traffic = (47783394000 + 60439114000) if args.fields else (48463504384 + 1897165)
     integrals = grp.integrals() if overlapped is None else [float(x) for x in overlapped.total.cpu()]
 
     out = {
