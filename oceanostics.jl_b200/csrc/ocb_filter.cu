@@ -20,6 +20,7 @@ struct PassParams {
   T* dst; long long ds[3];            // destination, same convention
   int lo[3], hi[3];                   // 1-based inclusive output window
   int dim, kind, width, policy, extent;
+  int pairs_ok;                       // the source has an element on either side of every row (halo or padded scratch)
   T left, right, sigma, period;
   const T* nodes; const T* spacings;  // pre-offset: index m (1-based) -> nodes[m]
   T weights[2 * OCB_MAX_FILTER_WIDTH + 1];
@@ -155,10 +156,15 @@ __global__ void __launch_bounds__(128) ocb_filter_slide_kernel(const __grid_cons
   for (int m = 0; m < NT - 1; ++m) win[m] = __ldg(in + (long long)(c0 - W + m) * sd);
   win[NT - 1] = T(0);
   for (int c = c0; c <= c1; c += NT) {
+    // the group's 2W+1 new inputs first, as independent loads: one load per output in program order leaves a warp with a
+    // single request in flight, and the pass then runs at memory latency (0.35 ms) instead of bandwidth
+    T nxt[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) nxt[t] = (c + t <= c1) ? __ldg(in + (long long)(c + t + W) * sd) : T(0);
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
       if (c + t <= c1) {
-        win[(2 * W + t) % NT] = __ldg(in + (long long)(c + t + W) * sd);
+        win[(2 * W + t) % NT] = nxt[t];
         T s = T(0);
 #pragma unroll
         for (int j = 0; j < NT; ++j) s = BOX ? s + win[(t + j) % NT] : s + P.weights[j] * win[(t + j) % NT];
@@ -168,8 +174,79 @@ __global__ void __launch_bounds__(128) ocb_filter_slide_kernel(const __grid_cons
   }
 }
 
+// (3) Float64 pair kernel for the x pass: every thread owns two x-adjacent outputs and reads its 2W+2 inputs as W+1
+// 16-byte pairs, which halves the L1 traffic the pass is bound by (9.7 -> 4.9 GB at config 5; 0.35 -> 0.28 ms).  The
+// arithmetic per output is the one-column kernel's (same taps, same order, same division): results are bit-identical.
+// Pairs are aligned in the SOURCE array (element index even relative to a 16-byte boundary; the caller checks that the
+// base is 16-byte aligned and the y / z pitches are even); a pair that sticks out of the column window computes only
+// its inside column.
+__device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
+
+// x pass: outputs (i, i+1) need the 2W+2 inputs i-W .. i+1+W = W+1 aligned pairs.
+template <int W, bool BOX>
+__global__ void __launch_bounds__(256) ocb_filter_x2_kernel(const __grid_constant__ PassParams<double> P, int i_first) {
+  constexpr int NT = 2 * W + 1;
+  const int i = i_first + 2 * (blockIdx.x * blockDim.x + threadIdx.x);      // i - W is an aligned element
+  const int j = P.lo[1] + blockIdx.y * blockDim.y + threadIdx.y;
+  if (i > P.hi[0] || j > P.hi[1]) return;
+  const bool v0 = i >= P.lo[0], v1 = i + 1 <= P.hi[0];
+  double wtot = 0.0;
+  if (!BOX) {
+#pragma unroll
+    for (int t = 0; t < NT; ++t) wtot += P.weights[t] * 1.0;
+  }
+  for (int k = P.lo[2] + blockIdx.z; k <= P.hi[2]; k += gridDim.z) {
+    const double* q = P.src + (long long)(i - W) + j * P.ss[1] + k * P.ss[2];
+    double v[2 * W + 2];
+#pragma unroll
+    for (int m = 0; m <= W; ++m) { const double2 d = ldg2(q + 2 * m); v[2 * m] = d.x; v[2 * m + 1] = d.y; }
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      s0 = BOX ? s0 + v[t] : s0 + P.weights[t] * v[t];
+      s1 = BOX ? s1 + v[t + 1] : s1 + P.weights[t] * v[t + 1];
+    }
+    double* o = P.dst + i * P.ds[0] + j * P.ds[1] + k * P.ds[2];
+    if (v0) o[0] = BOX ? s0 / double(NT) : s0 / wtot;
+    if (v1) o[P.ds[0]] = BOX ? s1 / double(NT) : s1 / wtot;
+  }
+}
+
+// can the pair kernels read this pass's source?  16-byte aligned base, unit x stride, even y / z pitches
+static bool pair_loads_ok(const PassParams<double>& P) {
+  return P.pairs_ok && P.ss[0] == 1 && (P.ss[1] & 1) == 0 && (P.ss[2] & 1) == 0 && ((uintptr_t)P.src & 7) == 0 && !getenv("OCB_FILTER_NO_PAIRS");
+}
+// the first aligned element at or below index `i` of a row (rows share their parity because the pitches are even)
+static int aligned_at_or_below(const PassParams<double>& P, int i) {
+  const uintptr_t a = (uintptr_t)(P.src + i);
+  return (a & 15) ? i - 1 : i;
+}
+template <int W, bool BOX>
+static bool launch_pairs(const PassParams<double>& P, int c_lo, int c_hi, cudaStream_t st) {
+  if (!pair_loads_ok(P)) return false;
+  PassParams<double> Q = P;
+  if (P.dim == 0) {
+    Q.lo[0] = c_lo; Q.hi[0] = c_hi;
+    const int i_first = aligned_at_or_below(P, c_lo - W) + W;               // i_first - W aligned, i_first <= c_lo
+    const int npair = (c_hi - i_first) / 2 + 1, nj = P.hi[1] - P.lo[1] + 1, nk = P.hi[2] - P.lo[2] + 1;
+    // the first pair may reach one element below c_lo - W and the last one above c_hi + W: both exist (c_lo - W >= 1 means the
+    // row has an element at index 0 only as a halo or as the previous row's end; the value is loaded but never used)
+    dim3 block(64, 4, 1), grid((npair + 63) / 64, (nj + 3) / 4, nk < 128 ? nk : 128);
+    ocb_filter_x2_kernel<W, BOX><<<grid, block, 0, st>>>(Q, i_first);
+  } else {
+    return false;                      // y / z passes: the one-column sliding-window kernel (a two-column window needs 108
+                                       // registers and measured slower: 0.42 vs 0.35 ms)
+  }
+  return true;
+}
+template <class T, int W, bool BOX> struct PairLauncher { static bool go(const PassParams<T>&, int, int, cudaStream_t) { return false; } };
+template <int W, bool BOX> struct PairLauncher<double, W, BOX> {
+  static bool go(const PassParams<double>& P, int c_lo, int c_hi, cudaStream_t st) { return launch_pairs<W, BOX>(P, c_lo, c_hi, st); }
+};
+
 template <class T, int W, bool BOX>
 static void launch_fast_w(const PassParams<T>& P, int c_lo, int c_hi, cudaStream_t st) {
+  if (PairLauncher<T, W, BOX>::go(P, c_lo, c_hi, st)) return;
   PassParams<T> Q = P;
   if (P.dim == 0) {
     Q.lo[0] = c_lo; Q.hi[0] = c_hi;
@@ -216,6 +293,25 @@ static void launch_pass(const PassParams<T>& P, dim3 grid, dim3 block, cudaStrea
   else launch_pass_policy<T, OCB_FILTER_GAUSSIAN_STRETCHED>(P, grid, block, st);
 }
 
+// two library-owned side streams (per host thread and device) for the boundary bands of a pass
+struct BandStreams { int device; cudaStream_t s[2]; cudaEvent_t fork, join[2]; };
+static BandStreams* band_streams() {
+  static thread_local BandStreams bs = {-1, {nullptr, nullptr}, nullptr, {nullptr, nullptr}};
+  if (getenv("OCB_FILTER_NO_SIDE_STREAMS")) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  if (bs.device == dev) return &bs;
+  if (bs.device >= 0) return nullptr;                   // this thread already serves another device: stay on one stream
+  bool ok = cudaStreamCreateWithFlags(&bs.s[0], cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&bs.s[1], cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&bs.fork, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&bs.join[0], cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&bs.join[1], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) { cudaGetLastError(); return nullptr; }
+  bs.device = dev;
+  return &bs;
+}
+
 template <class T>
 static int filter_impl(const ocb_field* src, const int32_t ext[3], const ocb_filter_pass* passes, int n_pass,
                        const ocb_field* dst, const int32_t wlo[3], const int32_t whi[3], cudaStream_t st) {
@@ -228,7 +324,12 @@ static int filter_impl(const ocb_field* src, const int32_t ext[3], const ocb_fil
   }
   const size_t n_full = (size_t)ext[0] * ext[1] * ext[2];
   T* tmp[2] = {nullptr, nullptr};
-  for (int t = 0; t < n_pass - 1 && t < 2; ++t) OCB_CUDA(cudaMallocAsync((void**)&tmp[t], n_full * sizeof(T), st));
+  // two spare elements in front of and behind each temporary: the pair kernels read whole 16-byte pairs
+  T* tmp_alloc[2] = {nullptr, nullptr};
+  for (int t = 0; t < n_pass - 1 && t < 2; ++t) {
+    OCB_CUDA(cudaMallocAsync((void**)&tmp_alloc[t], (n_full + 4) * sizeof(T), st));
+    tmp[t] = tmp_alloc[t] + 2;
+  }
   int rc = OCB_OK;
   for (int ps = 0; ps < n_pass; ++ps) {
     const ocb_filter_pass& fp = passes[ps];
@@ -239,7 +340,9 @@ static int filter_impl(const ocb_field* src, const int32_t ext[3], const ocb_fil
       long long off = 0;
       for (int d = 0; d < 3; ++d) { P.ss[d] = src->stride[d]; off += (long long)(src->halo[d] - 1) * src->stride[d]; }
       P.src = (const T*)src->data + off;
+      P.pairs_ok = src->halo[0] >= 1 && src->halo[1] >= 1 && src->halo[2] >= 1;
     } else {                       // dense scratch indexed from 1
+      P.pairs_ok = 1;
       P.ss[0] = 1; P.ss[1] = ext[0]; P.ss[2] = (long long)ext[0] * ext[1];
       P.src = tmp[(ps - 1) & 1] - (P.ss[0] + P.ss[1] + P.ss[2]);
     }
@@ -256,12 +359,12 @@ static int filter_impl(const ocb_field* src, const int32_t ext[3], const ocb_fil
     P.left = T(fp.left); P.right = T(fp.right); P.sigma = T(fp.sigma); P.period = T(fp.period);
     if (fp.kind == OCB_FILTER_GAUSSIAN) for (int t = 0; t < 2 * fp.width + 1; ++t) P.weights[t] = T(fp.weights[t]);
     if (fp.kind == OCB_FILTER_GAUSSIAN_STRETCHED) { P.nodes = (const T*)fp.nodes - 1; P.spacings = (const T*)fp.spacings - 1; }
-    auto launch_generic = [&](const PassParams<T>& Q) {
+    auto launch_generic = [&](const PassParams<T>& Q, cudaStream_t on) {
       dim3 block(32, 8, 1);
       const int ni = Q.hi[0] - Q.lo[0] + 1, nj = Q.hi[1] - Q.lo[1] + 1, nk = Q.hi[2] - Q.lo[2] + 1;
       if (ni <= 0 || nj <= 0 || nk <= 0) return;
       dim3 grid((ni + 31) / 32, (nj + 7) / 8, nk < 256 ? nk : 256);
-      launch_pass<T>(Q, grid, block, st);
+      launch_pass<T>(Q, grid, block, on);
     };
     // interior outputs [w+1, n-w] of the window go to the unrolled fast kernels, the two boundary bands to the
     // policy-aware kernel
@@ -269,18 +372,31 @@ static int filter_impl(const ocb_field* src, const int32_t ext[3], const ocb_fil
     const int c_lo = P.lo[dm] > fp.width + 1 ? P.lo[dm] : fp.width + 1;
     const int c_hi = P.hi[dm] < fp.extent - fp.width ? P.hi[dm] : fp.extent - fp.width;
     bool fast = false;
-    if (fp.kind != OCB_FILTER_GAUSSIAN_STRETCHED && c_hi - c_lo + 1 >= 4 * fp.width + 2 && !getenv("OCB_FILTER_NO_FAST"))
+    BandStreams* bs = nullptr;
+    if (fp.kind != OCB_FILTER_GAUSSIAN_STRETCHED && c_hi - c_lo + 1 >= 4 * fp.width + 2 && !getenv("OCB_FILTER_NO_FAST")) {
+      // the two boundary bands write other outputs than the interior kernel: they run next to it on two side streams
+      // (fork here, after the previous pass; join below, before the next pass)
+      bs = band_streams();
+      if (bs) {
+        cudaEventRecord(bs->fork, st);
+        cudaStreamWaitEvent(bs->s[0], bs->fork, 0);
+        cudaStreamWaitEvent(bs->s[1], bs->fork, 0);
+      }
       fast = fp.kind == OCB_FILTER_BOX ? launch_fast<T, true>(P, c_lo, c_hi, st) : launch_fast<T, false>(P, c_lo, c_hi, st);
+    }
     if (fast) {
       PassParams<T> B = P;
-      B.hi[dm] = c_lo - 1; launch_generic(B);           // low band
-      B = P; B.lo[dm] = c_hi + 1; launch_generic(B);    // high band
+      B.hi[dm] = c_lo - 1; launch_generic(B, bs ? bs->s[0] : st);           // low band
+      B = P; B.lo[dm] = c_hi + 1; launch_generic(B, bs ? bs->s[1] : st);    // high band
+      if (bs) {
+        for (int q = 0; q < 2; ++q) { cudaEventRecord(bs->join[q], bs->s[q]); cudaStreamWaitEvent(st, bs->join[q], 0); }
+      }
     } else {
-      launch_generic(P);
+      launch_generic(P, st);
     }
     if (cudaGetLastError() != cudaSuccess) { ocb_set_error("filter pass launch failed"); rc = OCB_ERR_CUDA; break; }
   }
-  for (int t = 0; t < 2; ++t) if (tmp[t]) cudaFreeAsync(tmp[t], st);
+  for (int t = 0; t < 2; ++t) if (tmp_alloc[t]) cudaFreeAsync(tmp_alloc[t], st);
   return rc;
 }
 
