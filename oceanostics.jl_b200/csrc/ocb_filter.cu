@@ -262,6 +262,7 @@ static void launch_fast_w(const PassParams<T>& P, int c_lo, int c_hi, cudaStream
     ocb_filter_slide_kernel<T, W, BOX><<<grid, block, 0, st>>>(Q, c_lo, c_hi, seg);
   }
 }
+static bool fast_width_compiled(int w) { return (w >= 1 && w <= 6) || w == 8; }
 // returns false when no fast instantiation exists for this half width
 template <class T, bool BOX>
 static bool launch_fast(const PassParams<T>& P, int c_lo, int c_hi, cudaStream_t st) {
@@ -360,10 +361,12 @@ static int filter_impl(const ocb_field* src, const int32_t ext[3], const ocb_fil
     if (fp.kind == OCB_FILTER_GAUSSIAN) for (int t = 0; t < 2 * fp.width + 1; ++t) P.weights[t] = T(fp.weights[t]);
     if (fp.kind == OCB_FILTER_GAUSSIAN_STRETCHED) { P.nodes = (const T*)fp.nodes - 1; P.spacings = (const T*)fp.spacings - 1; }
     auto launch_generic = [&](const PassParams<T>& Q, cudaStream_t on) {
-      dim3 block(32, 8, 1);
       const int ni = Q.hi[0] - Q.lo[0] + 1, nj = Q.hi[1] - Q.lo[1] + 1, nk = Q.hi[2] - Q.lo[2] + 1;
       if (ni <= 0 || nj <= 0 || nk <= 0) return;
-      dim3 grid((ni + 31) / 32, (nj + 7) / 8, nk < 256 ? nk : 256);
+      int bx = 32;                                        // a band a few columns wide: narrower blocks, no idle lanes
+      while (bx > 4 && bx / 2 >= ni) bx /= 2;
+      const int by = 256 / bx;
+      dim3 block(bx, by, 1), grid((ni + bx - 1) / bx, (nj + by - 1) / by, nk < 256 ? nk : 256);
       launch_pass<T>(Q, grid, block, on);
     };
     // interior outputs [w+1, n-w] of the window go to the unrolled fast kernels, the two boundary bands to the
@@ -382,12 +385,14 @@ static int filter_impl(const ocb_field* src, const int32_t ext[3], const ocb_fil
         cudaStreamWaitEvent(bs->s[0], bs->fork, 0);
         cudaStreamWaitEvent(bs->s[1], bs->fork, 0);
       }
-      fast = fp.kind == OCB_FILTER_BOX ? launch_fast<T, true>(P, c_lo, c_hi, st) : launch_fast<T, false>(P, c_lo, c_hi, st);
+      fast = fast_width_compiled(fp.width);
     }
     if (fast) {
+      // bands first: their few blocks start at once and the interior kernel fills the rest of the machine
       PassParams<T> B = P;
       B.hi[dm] = c_lo - 1; launch_generic(B, bs ? bs->s[0] : st);           // low band
       B = P; B.lo[dm] = c_hi + 1; launch_generic(B, bs ? bs->s[1] : st);    // high band
+      if (fp.kind == OCB_FILTER_BOX) launch_fast<T, true>(P, c_lo, c_hi, st); else launch_fast<T, false>(P, c_lo, c_hi, st);
       if (bs) {
         for (int q = 0; q < 2; ++q) { cudaEventRecord(bs->join[q], bs->s[q]); cudaStreamWaitEvent(st, bs->join[q], 0); }
       }
