@@ -22,11 +22,16 @@
 // chunk); the step at plane n handles the cell, face, corner and edge items of plane n and the z-centred items of the cell
 // below (S33, Ww, the tracer Laplacian).  Chunks other than the first pre-load two planes to warm that one-plane lag.
 
-template <int MASK, int NW, int RY, int NS, int MINB>
+// TWK = tile row pitch in elements: 34 (west halo + 32 + east halo) when the tile's first column is 16-byte aligned for every
+// tile (odd x halo), else 36 (one spare column either side of the aligned box start, as in ocb_budget_kernel).
+constexpr int sums_tile_elems(int tw, int tr) { return ((tw * tr * 8 + 127) / 128) * 128 / 8; }   // 128-byte aligned field tiles
+
+template <int MASK, int NW, int RY, int NS, int MINB, int TWK>
 __global__ void __launch_bounds__(NW * 32, MINB)
 ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_constant__ CUtensorMap mu, const __grid_constant__ CUtensorMap mv,
                        const __grid_constant__ CUtensorMap mw, const __grid_constant__ CUtensorMap mb, const __grid_constant__ CUtensorMap mp) {
   using G = Geo<NW, RY>;
+  constexpr int TILE = sums_tile_elems(TWK, G::TR);
   constexpr bool H_K = MASK & (1 << FD_K), H_ADV = MASK & (1 << FD_ADV), H_PR = MASK & (1 << FD_PR), H_WB = MASK & (1 << FD_WB),
                  H_EPS = MASK & (1 << FD_EPS), H_CHI = MASK & (1 << FD_CHI), H_CDF = MASK & (1 << FD_CDF);
   constexpr bool NEED_B = H_WB || H_CHI || H_CDF, NEED_P = H_PR, NEED_S = H_EPS || H_ADV;
@@ -35,7 +40,7 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
 
   extern __shared__ __align__(1024) double smem_d[];
   double* tiles = smem_d;                                                      // [NS][NF][TILE]
-  double* red = tiles + NS * NF * G::TILE;                                     // [NW]
+  double* red = tiles + NS * NF * TILE;                                     // [NW]
   uint64_t* full = reinterpret_cast<uint64_t*>(red + NW);                      // [NS]
 
   const int lane = threadIdx.x, warp = threadIdx.y;
@@ -52,20 +57,20 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
   const int i = i0 + lane;
   const int jr0 = warp * RY;
 
-  // ---- TMA ring (same tiles as ocb_budget_kernel: 36 x (BR + 2), 16-byte aligned box start) -------------------------
-  constexpr uint32_t STAGE_BYTES = (uint32_t)(NF * TW * G::TR * 8);
+  // ---- TMA ring (tiles of TWK x (BR + 2) elements per field, 16-byte aligned box start) -------------------------
+  constexpr uint32_t STAGE_BYTES = (uint32_t)(NF * TWK * G::TR * 8);
   const int px_raw = i0 - 1 + P.hx - 1, py = j0 - 1 + P.hy - 1;
   const int xoff = px_raw & 1, px = px_raw - xoff;
   auto issue = [&](int n) {
     const int s = (n - n_first) % NS;
-    double* dst = tiles + s * (NF * G::TILE);
+    double* dst = tiles + s * (NF * TILE);
     mbar_expect_tx(&full[s], STAGE_BYTES);
     const int pz = n + P.hz - 1;
-    tma_load_3d(dst + 0 * G::TILE, &mu, &full[s], px, py, pz);
-    tma_load_3d(dst + 1 * G::TILE, &mv, &full[s], px, py, pz);
-    tma_load_3d(dst + 2 * G::TILE, &mw, &full[s], px, py, pz);
-    if (NEED_B) tma_load_3d(dst + F_B * G::TILE, &mb, &full[s], px, py, pz);
-    if (NEED_P) tma_load_3d(dst + F_P * G::TILE, &mp, &full[s], px, py, pz);
+    tma_load_3d(dst + 0 * TILE, &mu, &full[s], px, py, pz);
+    tma_load_3d(dst + 1 * TILE, &mv, &full[s], px, py, pz);
+    tma_load_3d(dst + 2 * TILE, &mw, &full[s], px, py, pz);
+    if (NEED_B) tma_load_3d(dst + F_B * TILE, &mb, &full[s], px, py, pz);
+    if (NEED_P) tma_load_3d(dst + F_P * TILE, &mp, &full[s], px, py, pz);
   };
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) mbar_init(&full[s], 1);
@@ -112,8 +117,8 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
     double (&uc)[RY] = cu[C], (&vc)[RY] = cv[C], (&wc)[RY] = cw[C], (&bc)[RY] = cb[C], (&pc)[RY] = cp[C];
     double (&up)[RY] = cu[Q], (&vp)[RY] = cv[Q], (&wp)[RY] = cw[Q], (&bp)[RY] = cb[Q], (&pp)[RY] = cp[Q];
     mbar_wait(&full[s], phase);
-    const double* T = tiles + s * (NF * G::TILE);
-    const double* Tu = T, *Tv = T + G::TILE, *Tw = T + 2 * G::TILE, *Tb = T + F_B * G::TILE, *Tp = T + F_P * G::TILE;
+    const double* T = tiles + s * (NF * TILE);
+    const double* Tu = T, *Tv = T + TILE, *Tw = T + 2 * TILE, *Tb = T + F_B * TILE, *Tp = T + F_P * TILE;
     if (++s == NS) { s = 0; phase ^= 1; }
     const int col = lane + xoff + 1;                       // tile column of this lane's cell
     const int row0 = jr0 + 1;                              // tile row of this thread's first cell
@@ -121,13 +126,13 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
     // ---- centre values of the thread's rows, the row to the south and the row to the north ----------------------------
 #pragma unroll
     for (int r = 0; r < RY; ++r) {
-      const int o = (row0 + r) * TW + col;
+      const int o = (row0 + r) * TWK + col;
       uc[r] = Tu[o]; vc[r] = Tv[o]; wc[r] = Tw[o];
       bc[r] = NEED_B ? Tb[o] : 0.0;
       pc[r] = NEED_P ? Tp[o] : 0.0;
     }
     if (n > n_first) {
-      const int oS = (row0 - 1) * TW + col, oN = (row0 + RY) * TW + col;
+      const int oS = (row0 - 1) * TWK + col, oN = (row0 + RY) * TWK + col;
       const double uS = Tu[oS], wS = Tw[oS], vS = Tv[oS], vN = Tv[oN];
       const double bS = NEED_B ? Tb[oS] : 0.0, bN = (NEED_B && H_CDF) ? Tb[oN] : 0.0, pS = NEED_P ? Tp[oS] : 0.0;
       // plane classes (block-uniform): g0 = [this chunk owns step n and plane n is in the window], g1, g2: same for n-1, n-2
@@ -138,7 +143,7 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
       // one row of this thread at step n.  FAST (compile-time tag): every class weight is the interior one
       auto do_row = [&](auto fast_tag, const int r) {
         constexpr bool FAST = decltype(fast_tag)::value;
-        const int o = (row0 + r) * TW + col;
+        const int o = (row0 + r) * TWK + col;
         const double us = r ? uc[r > 0 ? r - 1 : 0] : uS, ws = r ? wc[r > 0 ? r - 1 : 0] : wS;
         const double vn = (r < RY - 1) ? vc[r < RY - 1 ? r + 1 : 0] : vN;
         const double ue = Tu[o + 1], vw = Tv[o - 1], ww = Tw[o - 1];

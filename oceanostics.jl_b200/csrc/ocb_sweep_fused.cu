@@ -598,6 +598,7 @@ struct ocb_fused_plan {
   int mask, nw, ry, ns;
   bool sums;                       // ocb_budget_sums_kernel (integral-only class sums) instead of ocb_budget_kernel
   int minb;                        // resident blocks per SM the sums kernel was compiled for
+  int tw;                          // tile row pitch in elements (the TMA box width)
   int nblocks;
   size_t smem;
   void (*kernel)(FusedParams, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap);
@@ -623,24 +624,29 @@ static int setup_variant(ocb_fused_plan* fp, bool out) {
   return OCB_OK;
 }
 
-template <int MASK, int NW, int RY, int NS, int MINB>
+template <int MASK, int NW, int RY, int NS, int MINB, int TWK = TW>
 static int setup_sums(ocb_fused_plan* fp) {
   using G = Geo<NW, RY>;
   constexpr bool NEED_B = MASK & ((1 << FD_WB) | (1 << FD_CHI) | (1 << FD_CDF)), NEED_P = MASK & (1 << FD_PR);
   constexpr int NF = 3 + (NEED_B ? 1 : 0) + (NEED_P ? 1 : 0);
-  fp->nw = NW; fp->ry = RY; fp->ns = NS; fp->mask = MASK; fp->sums = true; fp->minb = MINB;
-  fp->smem = sizeof(double) * ((size_t)NS * NF * G::TILE + NW) + sizeof(uint64_t) * NS;
-  auto kern = ocb_budget_sums_kernel<MASK, NW, RY, NS, MINB>;
+  fp->nw = NW; fp->ry = RY; fp->ns = NS; fp->mask = MASK; fp->sums = true; fp->minb = MINB; fp->tw = TWK;
+  fp->smem = sizeof(double) * ((size_t)NS * NF * sums_tile_elems(TWK, G::TR) + NW) + sizeof(uint64_t) * NS;
+  auto kern = ocb_budget_sums_kernel<MASK, NW, RY, NS, MINB, TWK>;
   cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   fp->kernel = kern;
   OCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp->smem));
   return OCB_OK;
 }
+// the default shapes in both tile pitches: 34 columns when every tile starts on a 16-byte boundary (odd x halo)
+template <int MASK, int NW, int RY, int NS, int MINB>
+static int setup_sums_pitch(ocb_fused_plan* fp, bool narrow) {
+  return narrow ? setup_sums<MASK, NW, RY, NS, MINB, 34>(fp) : setup_sums<MASK, NW, RY, NS, MINB, 36>(fp);
+}
 
-static int make_map(EncodeTiledFn enc, const ocb_field& f, int rows, CUtensorMap* map) {
+static int make_map(EncodeTiledFn enc, const ocb_field& f, int rows, CUtensorMap* map, int tw = TW) {
   cuuint64_t dims[3] = {(cuuint64_t)f.size[0], (cuuint64_t)f.size[1], (cuuint64_t)f.size[2]};
   cuuint64_t strides[2] = {(cuuint64_t)f.stride[1] * 8, (cuuint64_t)f.stride[2] * 8};
-  cuuint32_t box[3] = {(cuuint32_t)TW, (cuuint32_t)rows, 1};
+  cuuint32_t box[3] = {(cuuint32_t)tw, (cuuint32_t)rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, f.data, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -792,30 +798,21 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
     int a = 0, b = 0, c = 0, d = 0;
     if (sc) sscanf(sc, "%d,%d,%d,%d", &a, &b, &c, &d);
     const int key = a * 1000 + b * 100 + c * 10 + d;
-    if (!sc && njy + 1 <= 4) rc = setup_sums<ALL, 2, 2, 3, 4>(fp);          // slab-edge strips: 4-row tiles
-    else if (!sc && mask == (1 << FD_EPS)) rc = setup_sums<(1 << FD_EPS), 8, 3, 3, 1>(fp);
-    else if (!sc && (mask & ~VEL) == 0) rc = setup_sums<VEL, 8, 3, 3, 1>(fp);
-    else if (!sc && (mask & ~VELP) == 0) rc = setup_sums<VELP, 8, 3, 3, 1>(fp);
-    else if (!sc && (mask & ~VELB) == 0) rc = setup_sums<VELB, 8, 3, 3, 1>(fp);
+    const bool narrow = (grid->H[0] & 1) && !getenv("OCB_SUMS_WIDE_TILES");   // every tile's first column is 16-byte aligned
+    if (!sc && njy + 1 <= 4) rc = setup_sums_pitch<ALL, 2, 2, 3, 4>(fp, narrow);          // slab-edge strips: 4-row tiles
+    else if (!sc && mask == (1 << FD_EPS)) rc = setup_sums_pitch<(1 << FD_EPS), 8, 3, 3, 1>(fp, narrow);
+    else if (!sc && (mask & ~VEL) == 0) rc = setup_sums_pitch<VEL, 8, 3, 3, 1>(fp, narrow);
+    else if (!sc && (mask & ~VELP) == 0) rc = setup_sums_pitch<VELP, 8, 3, 3, 1>(fp, narrow);
+    else if (!sc && (mask & ~VELB) == 0) rc = setup_sums_pitch<VELB, 8, 3, 3, 1>(fp, narrow);
     else if (key == 8331) rc = setup_sums<ALL, 8, 3, 3, 1>(fp);
     else if (key == 8341) rc = setup_sums<ALL, 8, 3, 4, 1>(fp);
     else if (key == 8431) rc = setup_sums<ALL, 8, 4, 3, 1>(fp);
-    else if (key == 8232) rc = setup_sums<ALL, 8, 2, 3, 2>(fp);
-    else if (key == 8242) rc = setup_sums<ALL, 8, 2, 4, 2>(fp);
-    else if (key == 8322) rc = setup_sums<ALL, 8, 3, 2, 2>(fp);
     else if (key == 12231) rc = setup_sums<ALL, 12, 2, 3, 1>(fp);
-    else if (key == 16231) rc = setup_sums<ALL, 16, 2, 3, 1>(fp);
     else if (key == 4432) rc = setup_sums<ALL, 4, 4, 3, 2>(fp);
-    else if (key == 4343) rc = setup_sums<ALL, 4, 3, 4, 3>(fp);
     else if (key == 4442) rc = setup_sums<ALL, 4, 4, 4, 2>(fp);
     else if (key == 4532) rc = setup_sums<ALL, 4, 5, 3, 2>(fp);
-    else if (key == 4631) rc = setup_sums<ALL, 4, 6, 3, 1>(fp);
-    else if (key == 4433) rc = setup_sums<ALL, 4, 4, 3, 3>(fp);
-    else if (key == 2834) rc = setup_sums<ALL, 2, 8, 3, 4>(fp);
-    else if (key == 2634) rc = setup_sums<ALL, 2, 6, 3, 4>(fp);
-    else if (key == 6431) rc = setup_sums<ALL, 6, 4, 3, 1>(fp);
-    else if (key == 3443) rc = setup_sums<ALL, 3, 4, 4, 3>(fp);
-    else rc = setup_sums<ALL, 4, 4, 3, 2>(fp);                              // measured best at 1024^3 (profiles/r1_summary.md)
+    else if (key == 4631) rc = setup_sums_pitch<ALL, 4, 6, 3, 1>(fp, narrow);
+    else rc = setup_sums_pitch<ALL, 4, 4, 3, 2>(fp, narrow);               // measured best at 1024^3 (profiles/r1_summary.md)
   } else if (mask & EPVM) {
     if (mask == EPVM) rc = OCB_PICK(EPVM);
     else if ((mask & ~TKEV) == 0) rc = OCB_PICK(TKEV);
@@ -894,7 +891,7 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
   }
   const ocb_field* f[5] = {&in->u, &in->v, &in->w, vneed_b ? &in->b : &in->u, vneed_p ? &in->p : &in->u};
   for (int a = 0; a < 5; ++a) {
-    rc = make_map(enc, *f[a], BR + 2, &fp->maps[a]);
+    rc = make_map(enc, *f[a], BR + 2, &fp->maps[a], fp->sums ? fp->tw : TW);
     if (rc != OCB_OK) { delete fp; return rc; }
   }
   *out = fp;
