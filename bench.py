@@ -238,7 +238,14 @@ def main():
         torch.cuda.synchronize()
         sweep_ms = a.elapsed_time(b) / args.steps
     t = torch.tensor([total_ms, sweep_ms], dtype=torch.float64, device=device)
+    per_rank = None
     if dist is not None:
+        # every rank's own numbers (loop time per step, stand-alone sweep, where its marked step's phases end): the boards of a
+        # box do not run at the same clock under their power caps, and the all-reduce makes every step as long as the slowest
+        mine = [total_ms / args.steps, sweep_ms] + ([timeline[k] for k in ("exchange_end", "interior_end", "strips_end", "end")] if timeline else [0.0] * 4)
+        every = [torch.zeros(6, dtype=torch.float64, device=device) for _ in range(world)]
+        dist.all_gather(every, torch.tensor(mine, dtype=torch.float64, device=device))
+        per_rank = [[round(float(x), 3) for x in e] for e in every]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.barrier()
     total_ms, sweep_ms = float(t[0]), float(t[1])
@@ -280,6 +287,7 @@ def main():
     }
     if world > 1:
         out["comm"] = {"step_minus_sweep_ms": round(ms_per_step - sweep_ms, 4), "overlapped": overlapped is not None, "timeline_ms": timeline,
+                       "per_rank_ms": {"columns": ["loop_step", "sweep_alone", "exchange_end", "interior_end", "strips_end", "end"], "rows": per_rank},
                        "halo_bytes_per_rank_per_step": exchanger.bytes_per_exchange,
                        "transport": args.transport,
                        "note": "exchange (peer: one kernel storing the edge rows into the neighbours' halos over NVLink + flag words; nccl: "
