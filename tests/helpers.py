@@ -66,8 +66,8 @@ class State:
     """u, v, w, b, p (+ eddy viscosity) on both sides, halos filled by the oracle's fill_halo."""
 
     def __init__(self, size=(16, 12, 10), stretched=False, dtype=np.float64, device="cpu", seed=SEED, topology=("P", "P", "B"),
-                 extent=(1, 1, 1), amplitude=1.0):
-        self.og, self.pg = make_grids(size, stretched, dtype, device, topology=topology, extent=extent)
+                 extent=(1, 1, 1), amplitude=1.0, halo=(3, 3, 3)):
+        self.og, self.pg = make_grids(size, stretched, dtype, device, halo=halo, topology=topology, extent=extent)
         rng = np.random.default_rng(seed)
         og = self.og
         two_pi = 2 * np.pi

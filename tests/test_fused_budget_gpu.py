@@ -138,6 +138,44 @@ def test_y_and_z_windows_tile_the_domain():
             assert abs(a - b) <= 1e-12 * scale, o.name
 
 
+@pytest.mark.parametrize("size,halo,seed", [((64, 40, 30), (3, 3, 3), 1), ((70, 21, 9), (3, 3, 3), 2), ((96, 33, 70), (3, 3, 3), 3),
+                                            ((64, 24, 12), (4, 4, 4), 4), ((38, 18, 40), (2, 2, 2), 5)], ids=str)
+def test_class_sum_kernel_on_random_windows(size, halo, seed):
+    """The class-sum kernel (integrals as weighted sums over faces / corners / edges, advection summed by parts with explicit
+    window-edge terms) against the cell-exact integral mode of the budget kernel (OCB_FUSED_CELL_INTEGRALS=1) and the oracle's
+    per-cell values summed over the window, for random y / z windows including single rows and planes, windows touching
+    either end, partly filled x tiles (Nx = 70, 38), several z chunks (Nz = 70 with 32-plane chunks) and the even-halo tile
+    pitch (36 columns, halo 2 and 4) next to the odd-halo one (34 columns)."""
+    st = State(size=size, device="cuda", halo=halo)
+    ops, oc = budget(st)
+    want = oracle_budget(st, oc)
+    Nx, Ny, Nz = size
+    rng = np.random.default_rng(seed)
+    windows = [(1, Ny, 1, Nz), (1, 1, 1, Nz), (Ny, Ny, Nz, Nz), (1, Ny, 1, 1), (2, Ny - 1, 2, Nz - 1)]
+    for _ in range(4):
+        j = sorted(rng.integers(1, Ny + 1, 2)); k = sorted(rng.integers(1, Nz + 1, 2))
+        windows.append((int(j[0]), int(j[1]), int(k[0]), int(k[1])))
+    os.environ["OCB_FUSED_KCHUNK"] = "32"
+    try:
+        for jlo, jhi, klo, khi in windows:
+            idx = (None, (jlo, jhi), (klo, khi))
+            sums = ocb.FusedDiagnostics(*[ocb.Integral(o, indices=idx) for o in ops]).compute()
+            os.environ["OCB_FUSED_CELL_INTEGRALS"] = "1"
+            try:
+                cells = ocb.FusedDiagnostics(*[ocb.Integral(o, indices=idx) for o in ops]).compute()
+            finally:
+                os.environ.pop("OCB_FUSED_CELL_INTEGRALS", None)
+            assert sums.plan.variant == 1 and cells.plan.variant == 1
+            V = 1.0 / (Nx * Ny * Nz)
+            for o, w_, a, b in zip(ops, want, sums.integrals(), cells.integrals()):
+                win = w_[:, jlo - 1:jhi, klo - 1:khi]
+                ref, scale = float(np.sum(win)) * V, float(np.sum(np.abs(win))) * V
+                assert abs(a - ref) <= 1e-12 * scale, (o.name, (jlo, jhi, klo, khi), a, ref, scale)
+                assert abs(a - b) <= 1e-12 * scale, (o.name, (jlo, jhi, klo, khi), a, b, scale)
+    finally:
+        os.environ.pop("OCB_FUSED_KCHUNK", None)
+
+
 @pytest.mark.parametrize("size", [(64, 44, 26), (62, 23, 3), (34, 50, 9)], ids=str)
 def test_ertel_pv_on_the_pipelined_kernel(size):
     """ErtelPotentialVorticity (fff, Nz + 1 faces) alone on the pipelined kernel: field, integral, and both."""
