@@ -115,6 +115,15 @@ def _deferred(name):
     return raiser
 
 
+def KineticEnergyStress(model, location=CCC):
+    """DIFF = uᵢ∂ⱼτᵢⱼ: each velocity times the divergence of its viscous fluxes, at cell centres
+    (uᵢ∂ⱼ_τᵢⱼᶜᶜᶜ, src/KineticEnergyEquation.jl:191-202, constructor :232-246).  SURVEY.md section 8f, row 2."""
+    validate_location(location, "KineticEnergyStress")
+    u, v, w = _vel(model.velocities)
+    return KernelFunctionOperation("KE_STRESS", model.grid, SweepOperands(u=u, v=v, w=w, closure=model.closure),
+                                   name="KineticEnergyStress", computes="kinetic energy stress/diffusion  uᵢ∂ⱼτᵢⱼ")
+
+
+Stress = KineticEnergyStress
 KineticEnergyTendency = _deferred("KineticEnergyTendency")
-KineticEnergyStress = Stress = _deferred("KineticEnergyStress")
 KineticEnergyForcing = Forcing = _deferred("KineticEnergyForcing")

@@ -543,6 +543,36 @@ OCB_EVAL(OCB_DIAG_APE_EPS) {
   return T(0.5) * ((fx0 + fx1) * (X.g.rdx * X.g.rdx) + (fy0 + fy1) * (X.g.rdy * X.g.rdy) + (fz0 + fz1) * X.rdzc(k));
 } };
 
+// uᵢ∂ⱼ_τᵢⱼᶜᶜᶜ  (src/KineticEnergyEquation.jl:191-202): each velocity times the divergence of its viscous fluxes at the
+// velocity point (Oceananigans ∂ⱼ_τ₁ⱼ = 1/Vᶠᶜᶜ [δxᶠ(Ax τ₁₁) + δyᶜ(Ay τ₁₂) + δzᶜ(Az τ₁₃)] and likewise for v, w; on a grid
+// with regular x and y the areas and the volume reduce to the spacings below), interpolated to the cell centre.
+template <class T> struct StressDiv {
+  const Ctx<T>& X;
+  OCB_X StressDiv(const Ctx<T>& x) : X(x) {}
+  OCB_X T t11(int i, int j, int k) const { return T(-2) * X.nu_ccc(i, j, k) * X.s11(i, j, k); }
+  OCB_X T t22(int i, int j, int k) const { return T(-2) * X.nu_ccc(i, j, k) * X.s22(i, j, k); }
+  OCB_X T t33(int i, int j, int k) const { return T(-2) * X.nu_ccc(i, j, k) * X.s33(i, j, k); }
+  OCB_X T t12(int i, int j, int k) const { return T(-2) * X.nu_ffc(i, j, k) * X.s12(i, j, k); }
+  OCB_X T t13(int i, int j, int k) const { return T(-2) * X.nu_fcf(i, j, k) * X.s13(i, j, k); }
+  OCB_X T t23(int i, int j, int k) const { return T(-2) * X.nu_cff(i, j, k) * X.s23(i, j, k); }
+  OCB_X T d1(int i, int j, int k) const {   // fcc
+    return (t11(i, j, k) - t11(i - 1, j, k)) * X.g.rdx + (t12(i, j + 1, k) - t12(i, j, k)) * X.g.rdy + (t13(i, j, k + 1) - t13(i, j, k)) * X.rdzc(k);
+  }
+  OCB_X T d2(int i, int j, int k) const {   // cfc
+    return (t12(i + 1, j, k) - t12(i, j, k)) * X.g.rdx + (t22(i, j, k) - t22(i, j - 1, k)) * X.g.rdy + (t23(i, j, k + 1) - t23(i, j, k)) * X.rdzc(k);
+  }
+  OCB_X T d3(int i, int j, int k) const {   // ccf
+    return (t13(i + 1, j, k) - t13(i, j, k)) * X.g.rdx + (t23(i, j + 1, k) - t23(i, j, k)) * X.g.rdy + (t33(i, j, k) - t33(i, j, k - 1)) * X.rdzf(k);
+  }
+};
+OCB_EVAL(OCB_DIAG_KE_STRESS) {
+  StressDiv<T> D(X);
+  T a = X.u(i, j, k) * D.d1(i, j, k) + X.u(i + 1, j, k) * D.d1(i + 1, j, k);
+  T b = X.v(i, j, k) * D.d2(i, j, k) + X.v(i, j + 1, k) * D.d2(i, j + 1, k);
+  T c = X.w(i, j, k) * D.d3(i, j, k) + X.w(i, j, k + 1) * D.d3(i, j, k + 1);
+  return T(0.5) * (a + b + c);
+} };
+
 // ---- dispatch -------------------------------------------------------------------------------------------------
 #define OCB_FOR_EACH_DIAG(M) \
   M(OCB_DIAG_KE) M(OCB_DIAG_ADV) M(OCB_DIAG_PR) M(OCB_DIAG_WB) M(OCB_DIAG_EPS) M(OCB_DIAG_EPS_ISO) M(OCB_DIAG_TKE) \
@@ -552,7 +582,7 @@ OCB_EVAL(OCB_DIAG_APE_EPS) {
   M(OCB_DIAG_T11C) M(OCB_DIAG_T22C) M(OCB_DIAG_T33C) M(OCB_DIAG_T12) M(OCB_DIAG_T13) M(OCB_DIAG_T23) M(OCB_DIAG_RI) \
   M(OCB_DIAG_RO) M(OCB_DIAG_EPV) M(OCB_DIAG_TWPV) M(OCB_DIAG_DEPV) M(OCB_DIAG_VF11) M(OCB_DIAG_VF22) M(OCB_DIAG_VF33) \
   M(OCB_DIAG_VF12) M(OCB_DIAG_VF13) M(OCB_DIAG_VF23) M(OCB_DIAG_FEPS) M(OCB_DIAG_SFEPS) M(OCB_DIAG_SFKE) M(OCB_DIAG_PI) \
-  M(OCB_DIAG_BPE) M(OCB_DIAG_APE) M(OCB_DIAG_UPSILON) M(OCB_DIAG_APE_EPS)
+  M(OCB_DIAG_BPE) M(OCB_DIAG_APE) M(OCB_DIAG_UPSILON) M(OCB_DIAG_APE_EPS) M(OCB_DIAG_KE_STRESS)
 
 // diagnostics whose operands may be lazy perturbations (u - U, c - C); the flag is rejected for the others
 OCB_X constexpr bool ocb_diag_takes_perturbation(int d) {

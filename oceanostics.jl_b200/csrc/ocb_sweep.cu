@@ -173,7 +173,7 @@ static double count_algorithmic_bytes(const ocb_grid* g, const ocb_sweep_inputs*
   for (int r = 0; r < n; ++r) {
     const int d = reqs[r].diag;
     if (d == OCB_DIAG_EPS || d == OCB_DIAG_EPS_ISO || d == OCB_DIAG_CHI || d == OCB_DIAG_CDIFF || d == OCB_DIAG_APE_EPS ||
-        (d >= OCB_DIAG_VF11 && d <= OCB_DIAG_VF23)) eddy = true;
+        d == OCB_DIAG_KE_STRESS || (d >= OCB_DIAG_VF11 && d <= OCB_DIAG_VF23)) eddy = true;
   }
   if (eddy) {   // count each distinct eddy field once
     const void* seen[2 * OCB_MAX_CLOSURE_FIELDS]; int ns = 0;

@@ -255,6 +255,40 @@ def viscous_dissipation_rate_ccc(i, j, k, g, closure_fields, fields, p):   # src
             _A_dw_t33(i, j, k, g, *a)) / V_ccc(i, j, k, g)
 
 
+# Oceananigans ∂ⱼ_τ₁ⱼ / ∂ⱼ_τ₂ⱼ / ∂ⱼ_τ₃ⱼ [OCN-mem: TurbulenceClosures, viscous flux divergences]: the finite-volume divergence
+# of the viscous fluxes at the velocity point, 1/V [δx(Ax τᵢ₁) + δy(Ay τᵢ₂) + δz(Az τᵢ₃)]
+def _Ax_t_ccc(i, j, k, g, t, *a): return Ax_ccc(i, j, k, g) * t(i, j, k, g, *a)
+def _Ay_t_ffc(i, j, k, g, t, *a): return Ay_ffc(i, j, k, g) * t(i, j, k, g, *a)
+def _Az_t_fcf(i, j, k, g, t, *a): return Az_fcf(i, j, k, g) * t(i, j, k, g, *a)
+def _Ax_t_ffc(i, j, k, g, t, *a): return Ax_ffc(i, j, k, g) * t(i, j, k, g, *a)
+def _Ay_t_ccc(i, j, k, g, t, *a): return Ay_ccc(i, j, k, g) * t(i, j, k, g, *a)
+def _Az_t_cff(i, j, k, g, t, *a): return Az_cff(i, j, k, g) * t(i, j, k, g, *a)
+def _Ax_t_fcf(i, j, k, g, t, *a): return Ax_fcf(i, j, k, g) * t(i, j, k, g, *a)
+def _Ay_t_cff(i, j, k, g, t, *a): return Ay_cff(i, j, k, g) * t(i, j, k, g, *a)
+def _Az_t_ccc(i, j, k, g, t, *a): return Az_ccc(i, j, k, g) * t(i, j, k, g, *a)
+
+
+def div_tau_1(i, j, k, g, *a):     # ∂ⱼ_τ₁ⱼ at fcc
+    return (dx_faa(i, j, k, g, _Ax_t_ccc, viscous_flux_ux, *a) + dy_aca(i, j, k, g, _Ay_t_ffc, viscous_flux_uy, *a) +
+            dz_aac(i, j, k, g, _Az_t_fcf, viscous_flux_uz, *a)) / _op.V_fcc(i, j, k, g)
+
+
+def div_tau_2(i, j, k, g, *a):     # ∂ⱼ_τ₂ⱼ at cfc
+    return (dx_caa(i, j, k, g, _Ax_t_ffc, viscous_flux_vx, *a) + dy_afa(i, j, k, g, _Ay_t_ccc, viscous_flux_vy, *a) +
+            dz_aac(i, j, k, g, _Az_t_cff, viscous_flux_vz, *a)) / _op.V_cfc(i, j, k, g)
+
+
+def div_tau_3(i, j, k, g, *a):     # ∂ⱼ_τ₃ⱼ at ccf
+    return (dx_caa(i, j, k, g, _Ax_t_fcf, viscous_flux_wx, *a) + dy_aca(i, j, k, g, _Ay_t_cff, viscous_flux_wy, *a) +
+            dz_aaf(i, j, k, g, _Az_t_ccc, viscous_flux_wz, *a)) / _op.V_ccf(i, j, k, g)
+
+
+def ke_stress_ccc(i, j, k, g, closure, closure_fields, clock, fields, buoyancy):   # uᵢ∂ⱼ_τᵢⱼᶜᶜᶜ, src/KineticEnergyEquation.jl:191-202
+    a = (closure, closure_fields, clock, fields, buoyancy)
+    return (_op.ix_caa(i, j, k, g, psif, fields["u"], div_tau_1, *a) + _op.iy_aca(i, j, k, g, psif, fields["v"], div_tau_2, *a) +
+            _op.iz_aac(i, j, k, g, psif, fields["w"], div_tau_3, *a))
+
+
 def nu_ccc_total(i, j, k, g, closure):                       # _νᶜᶜᶜ, src/Oceanostics.jl:201-208
     tot = None
     for c in _closures(closure):

@@ -49,6 +49,7 @@ def build_cases(st: State, closure_name="scalar", mean="profile"):
         ("PotentialEnergyConversion", KE.PotentialEnergyConversion(m), ev(K.ke_buoyancy_ccc, og, "ccc", of, (0, 0, 1), st.ob), "ccc"),
         ("PotentialEnergyConversion_tilted", KE.PotentialEnergyConversion(m_tilt), ev(K.ke_buoyancy_ccc, og, "ccc", of, tilt, st.ob), "ccc"),
         ("DissipationRate", KE.DissipationRate(m), ev(K.viscous_dissipation_rate_ccc, og, "ccc", None, of, par), "ccc"),
+        ("KineticEnergyStress", KE.KineticEnergyStress(m), ev(K.ke_stress_ccc, og, "ccc", oc, None, None, of, None), "ccc"),
         ("DissipationRate_perturbation", KE.DissipationRate(m, U=U, V=V, W=W) if U is not None else KE.DissipationRate(m),
          ev(K.viscous_dissipation_rate_ccc, og, "ccc", None, ofp, par), "ccc"),
         ("KineticEnergyIsotropicDissipationRate", KE.KineticEnergyIsotropicDissipationRate(m),

@@ -208,6 +208,27 @@ def test_tracer_variance_integral_identity(gname, cname):
     assert a1 == pytest.approx(a2, rel=1e-12, abs=2 * np.finfo(float).eps)
 
 
+@pytest.mark.parametrize("gname", GRIDS)
+@pytest.mark.parametrize("cname", ["scalar", "smagorinsky_like", "tuple"])
+def test_ke_stress_integral_equals_the_dissipation_integral(gname, cname):
+    """Summation by parts of DIFF = uᵢ∂ⱼτᵢⱼ (src/KineticEnergyEquation.jl:191-202) over a periodic x-y domain with impenetrable,
+    no-flux top and bottom (w = 0 on the boundary faces, mirrored u and v: every boundary flux τ₁₃, τ₂₃ vanishes) gives
+    <uᵢ∂ⱼτᵢⱼ> = -<τᵢⱼ∂ⱼuᵢ> = <ε> (src/KineticEnergyEquation.jl:441-453): the closing relation of the reference's KE budget
+    (docs/examples/two_dimensional_turbulence.jl), here between two independently restated kernels."""
+    g = GRIDS[gname]()
+    rng = np.random.default_rng(5)
+    cl = make_closures(g, rng)[cname]
+    f = {}
+    for name, loc in (("u", "fcc"), ("v", "cfc"), ("w", "ccf")):
+        fld = OField(g, loc)
+        fld.interior[...] = rng.standard_normal(fld.interior.shape)
+        f[name] = fld.fill_halo()
+    eps = K.evaluate(K.viscous_dissipation_rate_ccc, g, "ccc", None, f, {"closure": cl})
+    dif = K.evaluate(K.ke_stress_ccc, g, "ccc", cl, None, None, f, None)
+    assert K.integral(dif, g, "ccc") == pytest.approx(K.integral(eps, g, "ccc"), rel=1e-11)
+    assert not np.allclose(dif, eps)            # equal in the integral only
+
+
 def test_richardson_and_ertel_pv_known_answers():
     """test/test_active_tracer_diagnostics.jl:24-80: u = S z + S y, b = N² z  =>
     Ri[3,3,3] = N²/S², EPV[3,3,3] = N² (f_z - S)."""
