@@ -48,17 +48,28 @@ def parse():
 
 # ---- clocks sampling during the timed region ---------------------------------------------------------------
 class ClockSampler:
-    def __init__(self, index=0):
+    """SM clock and throttle reasons of one GPU, polled on a thread during the timed region.  NVML is initialised when the
+    sampler is CREATED (before the warm-up steps), not when it is entered: nvmlInit in all eight processes of a box at the
+    start of the timed region stalled kernel launches for 15 - 40 ms (a 9.2 ms step read as 11.2 ms over 20 steps)."""
+
+    def __init__(self, index=0, enabled=True):
         self.samples, self.reasons, self.max_mhz, self._stop = [], set(), None, threading.Event()
-        self.index = index
+        self.index, self.nv, self.handle = index, None, None
+        if enabled:
+            try:
+                import pynvml as nv
+                nv.nvmlInit()
+                self.nv, self.handle = nv, nv.nvmlDeviceGetHandleByIndex(index)
+                self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM)
+            except Exception as e:  # pragma: no cover
+                self.error = repr(e)
         self.thread = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
         try:
-            import pynvml as nv
-            nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            nv, h = self.nv, self.handle
+            if nv is None:
+                return
             names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
                      nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
                      nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
@@ -193,6 +204,7 @@ def main():
         if dist is not None:
             dist.all_reduce(plan.integrals)
 
+    sampler = ClockSampler(local, enabled=(rank == 0))      # NVML set up here, outside the timed region; rank 0 reports its board
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
@@ -201,7 +213,7 @@ def main():
     # ---- timed region: device-resident inputs ---------------------------------------------------------------
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    with ClockSampler(local) as clocks:
+    with sampler as clocks:
         torch.cuda.synchronize()
         ev0.record()
         for s in range(args.steps):
