@@ -136,6 +136,7 @@ enum {
   OCB_DIAG_UPSILON,       /* upsilon_ccc: aux[6] - z  (aux[6] = z✶)   AvailablePotentialEnergyEquation.jl:126 (next-row, §8f) */
   OCB_DIAG_APE_EPS,       /* ape_dissipation_rate_ccc: (1/V) sum center(-A δΥ q), Υ = aux[4], tracer b   AvailablePotentialEnergyEquation.jl:202-215 */
   OCB_DIAG_KE_STRESS,     /* uᵢ∂ⱼ_τᵢⱼᶜᶜᶜ: velocity x divergence of the viscous fluxes  KineticEnergyEquation.jl:191-202 (next-row, §8f) */
+  OCB_DIAG_KE_FORCING,    /* uᵢFᵤᵢᶜᶜᶜ: velocity x forcing, forcings materialised at the velocity points in aux[0..2]  KineticEnergyEquation.jl:251-260 (next-row, §8f) */
   OCB_DIAG_COUNT
 };
 

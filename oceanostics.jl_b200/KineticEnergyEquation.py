@@ -124,6 +124,20 @@ def KineticEnergyStress(model, location=CCC):
                                    name="KineticEnergyStress", computes="kinetic energy stress/diffusion  uᵢ∂ⱼτᵢⱼ")
 
 
+def KineticEnergyForcing(model, location=CCC):
+    """FORC = uᵢFᵤᵢ: each velocity times its forcing at the velocity point, at cell centres (uᵢFᵤᵢᶜᶜᶜ,
+    src/KineticEnergyEquation.jl:251-260, constructor :289-297; NonhydrostaticModel only, as there).  The forcing functors
+    are materialised by the host layer (`operations.ForcingField`).  SURVEY.md section 8f, row 2."""
+    from .operations import forcing_operand
+    validate_location(location, "KineticEnergyForcing")
+    if model.hydrostatic:
+        raise TypeError("KineticEnergyForcing is defined for NonhydrostaticModel only (src/KineticEnergyEquation.jl:289)")
+    u, v, w = _vel(model.velocities)
+    aux = {a: forcing_operand(getattr(model.forcing, n), f, model) for a, (n, f) in enumerate((("u", u), ("v", v), ("w", w)))}
+    return KernelFunctionOperation("KE_FORCING", model.grid, SweepOperands(u=u, v=v, w=w, aux=aux),
+                                   name="KineticEnergyForcing", computes="kinetic energy forcing  uᵢFᵤᵢ")
+
+
 Stress = KineticEnergyStress
+Forcing = KineticEnergyForcing
 KineticEnergyTendency = _deferred("KineticEnergyTendency")
-KineticEnergyForcing = Forcing = _deferred("KineticEnergyForcing")

@@ -11,7 +11,7 @@ from .fields import (Field, CenterField, XFaceField, YFaceField, ZFaceField, Zer
 from .operations import (KernelFunctionOperation, ComputedField, ReducedField, Integral, Average, FusedDiagnostics, Closure,
                          SweepOperands, SweepPlan, compute, compute_at)
 from .models import (NonhydrostaticModel, HydrostaticFreeSurfaceModel, FPlane, ConstantCartesianCoriolis, BuoyancyTracer,
-                     get_coriolis_frequency_components)
+                     Forcing, get_coriolis_frequency_components)
 from . import KineticEnergyEquation, TurbulentKineticEnergyEquation, TracerVarianceEquation, FlowDiagnostics, SpatialFilters, BackgroundPotentialEnergyEquation
 from . import FilteredKineticEnergyEquation, SubFilterKineticEnergyEquation, AvailablePotentialEnergyEquation
 from .SpatialFilters import BoxFilter, GaussianFilter

@@ -573,6 +573,17 @@ OCB_EVAL(OCB_DIAG_KE_STRESS) {
   return T(0.5) * (a + b + c);
 } };
 
+// uᵢFᵤᵢᶜᶜᶜ  (src/KineticEnergyEquation.jl:251-260): each velocity times its forcing at the velocity point, interpolated to
+// the cell centre.  The forcing functors are the host layer's business (Oceananigans evaluates them); here aux[0], aux[1],
+// aux[2] hold Fᵘ (fcc), Fᵛ (cfc), Fʷ (ccf) as arrays, numbers or ZeroField.
+OCB_EVAL(OCB_DIAG_KE_FORCING) {
+  const HFld<T>& Fu = X.in.aux[0]; const HFld<T>& Fv = X.in.aux[1]; const HFld<T>& Fw = X.in.aux[2];
+  T a = X.u(i, j, k) * Fu(i, j, k) + X.u(i + 1, j, k) * Fu(i + 1, j, k);
+  T b = X.v(i, j, k) * Fv(i, j, k) + X.v(i, j + 1, k) * Fv(i, j + 1, k);
+  T c = X.w(i, j, k) * Fw(i, j, k) + X.w(i, j, k + 1) * Fw(i, j, k + 1);
+  return T(0.5) * (a + b + c);
+} };
+
 // ---- dispatch -------------------------------------------------------------------------------------------------
 #define OCB_FOR_EACH_DIAG(M) \
   M(OCB_DIAG_KE) M(OCB_DIAG_ADV) M(OCB_DIAG_PR) M(OCB_DIAG_WB) M(OCB_DIAG_EPS) M(OCB_DIAG_EPS_ISO) M(OCB_DIAG_TKE) \
@@ -582,7 +593,7 @@ OCB_EVAL(OCB_DIAG_KE_STRESS) {
   M(OCB_DIAG_T11C) M(OCB_DIAG_T22C) M(OCB_DIAG_T33C) M(OCB_DIAG_T12) M(OCB_DIAG_T13) M(OCB_DIAG_T23) M(OCB_DIAG_RI) \
   M(OCB_DIAG_RO) M(OCB_DIAG_EPV) M(OCB_DIAG_TWPV) M(OCB_DIAG_DEPV) M(OCB_DIAG_VF11) M(OCB_DIAG_VF22) M(OCB_DIAG_VF33) \
   M(OCB_DIAG_VF12) M(OCB_DIAG_VF13) M(OCB_DIAG_VF23) M(OCB_DIAG_FEPS) M(OCB_DIAG_SFEPS) M(OCB_DIAG_SFKE) M(OCB_DIAG_PI) \
-  M(OCB_DIAG_BPE) M(OCB_DIAG_APE) M(OCB_DIAG_UPSILON) M(OCB_DIAG_APE_EPS) M(OCB_DIAG_KE_STRESS)
+  M(OCB_DIAG_BPE) M(OCB_DIAG_APE) M(OCB_DIAG_UPSILON) M(OCB_DIAG_APE_EPS) M(OCB_DIAG_KE_STRESS) M(OCB_DIAG_KE_FORCING)
 
 // diagnostics whose operands may be lazy perturbations (u - U, c - C); the flag is rejected for the others
 OCB_X constexpr bool ocb_diag_takes_perturbation(int d) {

@@ -156,6 +156,7 @@ static double count_algorithmic_bytes(const ocb_grid* g, const ocb_sweep_inputs*
       case OCB_DIAG_FEPS: case OCB_DIAG_PI: mark_uvw(); for (int a = 0; a < 6; ++a) use[9 + a] = true; break;
       case OCB_DIAG_SFEPS: mark_uvw(); for (int a = 0; a < 7; ++a) use[9 + a] = true; break;
       case OCB_DIAG_SFKE: mark_uvw(); use[15] = true; break;
+      case OCB_DIAG_KE_FORCING: mark_uvw(); use[9] = use[10] = use[11] = true; break;
       default: mark_uvw(); break;
     }
     if (pert || d == OCB_DIAG_TKE || (d >= OCB_DIAG_SPX && d <= OCB_DIAG_SP)) use[5] = use[6] = use[7] = true;

@@ -41,11 +41,23 @@ def get_coriolis_frequency_components(coriolis):
                      "`ConstantCartesianCoriolis` and `nothing`.")
 
 
+class Forcing:
+    """Oceananigans `Forcing(func; field_dependencies, parameters)` in continuous form: `func(x, y, z, t, deps..., [p])`
+    evaluated at the location of the forced field.  The host layer materialises it (`ForcingField`) the way Oceananigans
+    evaluates the functor inside its kernels: at every stored index, halos included, from the dependency's own values there.
+    `func` must be written with array operations (it receives torch tensors)."""
+
+    def __init__(self, func, field_dependencies=(), parameters=None):
+        self.func = func
+        self.field_dependencies = (field_dependencies,) if isinstance(field_dependencies, str) else tuple(field_dependencies)
+        self.parameters = parameters
+
+
 class NonhydrostaticModel:
     hydrostatic = False
 
     def __init__(self, grid, tracers=("b",), closure=None, coriolis=None, buoyancy=None, advection="Centered",
-                 closure_fields=None):
+                 closure_fields=None, forcing=None):
         self.grid = grid
         self.velocities = SimpleNamespace(u=XFaceField(grid), v=YFaceField(grid), w=ZFaceField(grid))
         self.tracers = SimpleNamespace(**{name: CenterField(grid) for name in tracers})
@@ -57,6 +69,11 @@ class NonhydrostaticModel:
         self.advection = advection
         self.clock = SimpleNamespace(time=0.0, iteration=0)
         self.velocities.w.boundary["impenetrable"] = True
+        forcing = dict(forcing or {})
+        unknown = set(forcing) - {"u", "v", "w"} - set(tracers)
+        if unknown:
+            raise ValueError(f"forcing names {sorted(unknown)} are not fields of the model")
+        self.forcing = SimpleNamespace(**{name: forcing.get(name) for name in ("u", "v", "w") + tuple(tracers)})
 
     def fields(self):
         return {**vars(self.velocities), **vars(self.tracers)}

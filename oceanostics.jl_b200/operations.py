@@ -469,6 +469,61 @@ class PointwiseField(Field):
         return self
 
 
+class ForcingField(Field):
+    """A model forcing evaluated at the points of the field it forces: a computed `Field` (recomputed by `compute` /
+    `compute_at` like any other).  `forcing` is a `models.Forcing` (continuous form `func(x, y, z, t, deps..., [p])`), a
+    number or a Field at the same location.  Dependencies must live at the forced field's location (the reference's own
+    test forces each velocity with a function of itself, test/test_kinetic_energy_equation.jl:105-129); the functor runs
+    as torch array operations on the device -- the step Oceananigans performs inside its tendency kernels."""
+    is_computed = True
+
+    def __new__(cls, *a, **k):
+        return object.__new__(cls)
+
+    def __init__(self, forcing, forced: Field, model):
+        Field.__init__(self, forced.location, forced.grid)
+        self.forcing, self.forced, self.model = forcing, forced, model
+        self.group = None
+        self.boundary["impenetrable"] = False
+
+    def compute(self, time=None):
+        import torch
+        g, F = self.grid, self.forcing
+        t = float(getattr(self.model.clock, "time", 0.0)) if time is None else float(time)
+        shape = self.data.shape                              # (z, y, x) parent, halos included
+        idx = [np.arange(1 - self.halo[d], self.stored[d] + self.halo[d] + 1) for d in range(3)]
+        node = lambda d: torch.as_tensor(np.asarray(g.nodes(d, self.location[d], idx[d]), dtype=np.float64), device=self.data.device,
+                                         dtype=self.data.dtype)
+        x, y, z = node(0)[None, None, :], node(1)[None, :, None], node(2)[:, None, None]
+        deps = []
+        for name in F.field_dependencies:
+            f = self.model.fields()[name]
+            if f.location != self.location or tuple(f.data.shape) != tuple(shape):
+                raise ValueError(f"forcing dependency `{name}` is not located where the forced field is")
+            if getattr(f, "is_computed", False):
+                compute_at(f, time)
+            deps.append(f.data)
+        args = [x, y, z, t] + deps + ([F.parameters] if F.parameters is not None else [])
+        out = F.func(*args)
+        self.data.copy_(torch.broadcast_to(torch.as_tensor(out, device=self.data.device, dtype=self.data.dtype), shape))
+        self.status_time = time
+        return self
+
+
+def forcing_operand(forcing, forced, model):
+    """`model.forcing.<name>` as an operand: nothing -> ZeroField, a number -> constant, a Field as is, a functor -> ForcingField."""
+    from .models import Forcing
+    if forcing is None:
+        return ZeroField()
+    if isinstance(forcing, Forcing):
+        return ForcingField(forcing, forced, model)
+    if isinstance(forcing, Field):
+        if forcing.location != forced.location:
+            raise ValueError("a forcing Field must be located where the field it forces is")
+        return forcing
+    return as_operand(forcing)
+
+
 def perturbation_split(x, default_mean=None):
     """Pattern-match a velocity/tracer argument: `field`, or the lazy `field - mean` the reference's
     constructors build (src/TurbulentKineticEnergyEquation.jl:327-330).  Returns (field, mean or None)."""

@@ -289,6 +289,32 @@ def ke_stress_ccc(i, j, k, g, closure, closure_fields, clock, fields, buoyancy):
             _op.iz_aac(i, j, k, g, psif, fields["w"], div_tau_3, *a))
 
 
+class ContinuousForcing:
+    """Oceananigans ContinuousForcing [OCN-mem]: F(i, j, k, grid, clock, fields) = func(x, y, z, t, deps..., [parameters]) with the
+    nodes and the dependency fields taken at the forced field's own location `loc` (dependencies located elsewhere would be
+    interpolated there by Oceananigans; the cases restated here depend on the forced field itself)."""
+
+    def __init__(self, func, loc, field_dependencies=(), parameters=None):
+        self.func, self.loc, self.deps, self.parameters = func, loc, tuple(field_dependencies), parameters
+
+    def __call__(self, i, j, k, g, clock, fields):
+        x, y, z = g.node(0, self.loc[0], i), g.node(1, self.loc[1], j), g.node(2, self.loc[2], k)
+        args = [x, y, z, getattr(clock, "time", 0.0) if clock is not None else 0.0] + [fields[n][i, j, k] for n in self.deps]
+        if self.parameters is not None:
+            args.append(self.parameters)
+        return self.func(*args)
+
+
+def _zero_forcing(i, j, k, g, clock, fields):
+    return 0.0
+
+
+def ke_forcing_ccc(i, j, k, g, forcings, clock, fields):       # uᵢFᵤᵢᶜᶜᶜ, src/KineticEnergyEquation.jl:251-260
+    Fu, Fv, Fw = (forcings.get(n) or _zero_forcing for n in ("u", "v", "w"))
+    return (_op.ix_caa(i, j, k, g, psif, fields["u"], Fu, clock, fields) + _op.iy_aca(i, j, k, g, psif, fields["v"], Fv, clock, fields) +
+            _op.iz_aac(i, j, k, g, psif, fields["w"], Fw, clock, fields))
+
+
 def nu_ccc_total(i, j, k, g, closure):                       # _νᶜᶜᶜ, src/Oceanostics.jl:201-208
     tot = None
     for c in _closures(closure):

@@ -78,6 +78,21 @@ def build_cases(st: State, closure_name="scalar", mean="profile"):
         ("QVelocityGradientTensorInvariant", FD.QVelocityGradientTensorInvariant(m),
          ev(K.Q_velocity_gradient_tensor_invariant_ccc, og, "ccc", st.ou, st.ov, st.ow), "ccc"),
     ]
+    # kinetic-energy forcing term (scope table 8f, row 2): space-dependent relaxation of each velocity, evaluated by the oracle's
+    # ContinuousForcing at every stored point and handed to the package as forcing Fields (the functor path is a GPU test)
+    relax = lambda x, y, z, t, q: -(0.5 + 0.25 * np.sin(2 * np.pi * x) * np.cos(2 * np.pi * y) + z) * q
+    oforc, pforc = {}, {}
+    for nm, loc, src in (("u", "fcc", st.ou), ("v", "cfc", st.ov), ("w", "ccf", st.ow)):
+        F = K.ContinuousForcing(relax, loc, (nm,))
+        oforc[nm] = F
+        fld = type(src)(og, loc)
+        H = og.H
+        ii, jj, kk = (np.arange(1 - H[d], fld.data.shape[d] - H[d] + 1) for d in range(3))
+        fld.data[...] = F(ii[:, None, None], jj[None, :, None], kk[None, None, :], og, None, of)
+        pforc[nm] = mirror(fld, st.pg)
+    m_forced = st.model(closure=pc)
+    m_forced.forcing.u, m_forced.forcing.v, m_forced.forcing.w = pforc["u"], pforc["v"], pforc["w"]
+    cases.append(("KineticEnergyForcing", KE.KineticEnergyForcing(m_forced), ev(K.ke_forcing_ccc, og, "ccc", oforc, None, of), "ccc"))
     # available-potential-energy family (scope table 8f): z✶ and Ψδ come from the oracle's sorted reference state and are
     # handed to both sides as fields, so these cases test the pointwise / flux kernels, not the sort (tests/test_bpe_gpu.py)
     from oracle import bpe as OB

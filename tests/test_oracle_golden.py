@@ -229,6 +229,29 @@ def test_ke_stress_integral_equals_the_dissipation_integral(gname, cname):
     assert not np.allclose(dif, eps)            # equal in the integral only
 
 
+@pytest.mark.parametrize("gname", GRIDS)
+def test_ke_forcing_known_answer(gname):
+    """test/test_kinetic_energy_equation.jl:105-129: Fᵘ = -u, Fᵛ = -v, Fʷ = -w on noise  =>
+    uᵢFᵤᵢ = @at ccc (-u² - v² - w²), rtol 1e-12."""
+    g = GRIDS[gname]()
+    rng = np.random.default_rng(9)
+    f = {}
+    for name, loc in (("u", "fcc"), ("v", "cfc"), ("w", "ccf")):
+        fld = OField(g, loc)
+        fld.interior[...] = rng.standard_normal(fld.interior.shape)
+        f[name] = fld.fill_halo()
+    damp = lambda x, y, z, t, q: -q
+    forcings = {"u": K.ContinuousForcing(damp, "fcc", ("u",)), "v": K.ContinuousForcing(damp, "cfc", ("v",)),
+                "w": K.ContinuousForcing(damp, "ccf", ("w",))}
+    got = K.evaluate(K.ke_forcing_ccc, g, "ccc", forcings, None, f)
+    sq = lambda i, j, k, gg, q: -q[i, j, k] ** 2
+    truth = (K.evaluate(K.ix_caa, g, "ccc", sq, f["u"]) + K.evaluate(K.iy_aca, g, "ccc", sq, f["v"]) +
+             K.evaluate(K.iz_aac, g, "ccc", sq, f["w"]))
+    np.testing.assert_allclose(got, truth, rtol=1e-12, atol=np.finfo(float).eps)
+    # no forcing at all: zero
+    assert not K.evaluate(K.ke_forcing_ccc, g, "ccc", {}, None, f).any()
+
+
 def test_richardson_and_ertel_pv_known_answers():
     """test/test_active_tracer_diagnostics.jl:24-80: u = S z + S y, b = N² z  =>
     Ri[3,3,3] = N²/S², EPV[3,3,3] = N² (f_z - S)."""

@@ -36,6 +36,32 @@ def test_unfused_and_operand_kinds(mean):
     _check(st, cases, vals, ints, st.og)
 
 
+def test_ke_forcing_functors_known_answer():
+    """test/test_kinetic_energy_equation.jl:105-129 through the package: Forcing(func, field_dependencies) functors are
+    materialised at the velocity points (halos included) and uᵢFᵤᵢ = @at ccc (-u² - v² - w²) to rtol 1e-12; the forcing
+    fields follow the velocities when these change (computed operands are refreshed before the sweep)."""
+    st = State(size=(40, 24, 18), device="cuda")
+    damp = lambda x, y, z, t, q: -q
+    m = st.model(closure=st.closures()["scalar"][1])
+    m.forcing.u, m.forcing.v, m.forcing.w = (ocb.Forcing(damp, field_dependencies=n) for n in ("u", "v", "w"))
+    forc = ocb.Field(ocb.KineticEnergyEquation.KineticEnergyForcing(m))
+    ke = ocb.Field(ocb.KineticEnergyEquation.KineticEnergy(m))
+    forc.compute(); ke.compute()
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(forc.interior_ijk(), -2.0 * ke.interior_ijk(), rtol=1e-12, atol=1e-300)
+    og, f = st.og, st.ofields()
+    sq = lambda i, j, k, gg, q: -q[i, j, k] ** 2
+    truth = (K.evaluate(K.ix_caa, og, "ccc", sq, st.ou) + K.evaluate(K.iy_aca, og, "ccc", sq, st.ov) + K.evaluate(K.iz_aac, og, "ccc", sq, st.ow))
+    np.testing.assert_allclose(forc.interior_ijk(), truth, rtol=1e-12, atol=1e-300)
+    m.velocities.u.data.mul_(3.0)
+    forc.compute(time=1.0); ke.compute(time=1.0)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(forc.interior_ijk(), -2.0 * ke.interior_ijk(), rtol=1e-12, atol=1e-300)
+    # a model without forcing: identically zero; hydrostatic models are refused as in the reference
+    none = ocb.Field(ocb.KineticEnergyEquation.KineticEnergyForcing(st.model(closure=st.closures()["scalar"][1]))).compute()
+    assert float(none.interior.abs().max()) == 0.0
+
+
 def test_config1_64cube_dissipation_and_richardson():
     """BASELINE.json configs[0]: 64³ Float64, ScalarDiffusivity: DissipationRate and RichardsonNumber."""
     st = State(size=(64, 64, 64), device="cuda")
