@@ -137,6 +137,7 @@ enum {
   OCB_DIAG_APE_EPS,       /* ape_dissipation_rate_ccc: (1/V) sum center(-A δΥ q), Υ = aux[4], tracer b   AvailablePotentialEnergyEquation.jl:202-215 */
   OCB_DIAG_KE_STRESS,     /* uᵢ∂ⱼ_τᵢⱼᶜᶜᶜ: velocity x divergence of the viscous fluxes  KineticEnergyEquation.jl:191-202 (next-row, §8f) */
   OCB_DIAG_KE_FORCING,    /* uᵢFᵤᵢᶜᶜᶜ: velocity x forcing, forcings materialised at the velocity points in aux[0..2]  KineticEnergyEquation.jl:251-260 (next-row, §8f) */
+  OCB_DIAG_C_TENDENCY,    /* c∂ₜcᶜᶜᶜ = 2c (-div_Uc[Centered 2nd order] - ∇·q + F), tracer in slot b, F in aux[0]  TracerVarianceEquation.jl:18-39 (next-row, §8f) */
   OCB_DIAG_COUNT
 };
 

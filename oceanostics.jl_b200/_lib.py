@@ -28,7 +28,7 @@ _DIAG_NAMES = [
     "KE", "ADV", "PR", "WB", "EPS", "EPS_ISO", "TKE", "SPX", "SPY", "SPZ", "SP", "CHI", "CDIFF", "SMOD", "OMOD", "Q",
     "S11", "S22", "S33", "S12", "S13", "S23", "O12", "O13", "O23", "T11", "T22", "T33", "T11C", "T22C", "T33C",
     "T12", "T13", "T23", "RI", "RO", "EPV", "TWPV", "DEPV", "VF11", "VF22", "VF33", "VF12", "VF13", "VF23",
-    "FEPS", "SFEPS", "SFKE", "PI", "BPE", "APE", "UPSILON", "APE_EPS", "KE_STRESS", "KE_FORCING"]
+    "FEPS", "SFEPS", "SFKE", "PI", "BPE", "APE", "UPSILON", "APE_EPS", "KE_STRESS", "KE_FORCING", "C_TENDENCY"]
 DIAG = {name: i for i, name in enumerate(_DIAG_NAMES)}
 OCB_DIAG_COUNT = len(_DIAG_NAMES)
 

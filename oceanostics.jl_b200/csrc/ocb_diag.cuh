@@ -584,6 +584,24 @@ OCB_EVAL(OCB_DIAG_KE_FORCING) {
   return T(0.5) * (a + b + c);
 } };
 
+// c∂ₜcᶜᶜᶜ  (src/TracerVarianceEquation.jl:18-39): 2c x Oceananigans' NonhydrostaticModel tracer_tendency for a model without
+// background fields, biogeochemistry or immersed boundaries:  Gc = -div_Uc - ∇·q + F, with the Centered second-order advective
+// fluxes  Ax u ℑx c, Ay v ℑy c, Az w ℑz c  (div_Uc = 1/V [δx + δy + δz] of them), the closure's diffusive fluxes as in
+// c∇_dot_qᶜ above, and the tracer forcing materialised at the cell centres in aux[0].
+OCB_EVAL(OCB_DIAG_C_TENDENCY) {
+  const HFld<T>& c = X.in.b;
+  T cc = c(i, j, k);
+  T ax = (X.u(i + 1, j, k) * (cc + c(i + 1, j, k)) - X.u(i, j, k) * (c(i - 1, j, k) + cc)) * (T(0.5) * X.g.rdx);
+  T ay = (X.v(i, j + 1, k) * (cc + c(i, j + 1, k)) - X.v(i, j, k) * (c(i, j - 1, k) + cc)) * (T(0.5) * X.g.rdy);
+  T az = (X.w(i, j, k + 1) * (cc + c(i, j, k + 1)) - X.w(i, j, k) * (c(i, j, k - 1) + cc)) * (T(0.5) * X.rdzc(k));
+  T qx0 = X.ka_fcc(i, j, k) * (cc - c(i - 1, j, k)), qx1 = X.ka_fcc(i + 1, j, k) * (c(i + 1, j, k) - cc);
+  T qy0 = X.ka_cfc(i, j, k) * (cc - c(i, j - 1, k)), qy1 = X.ka_cfc(i, j + 1, k) * (c(i, j + 1, k) - cc);
+  T qz0 = X.ka_ccf(i, j, k) * (cc - c(i, j, k - 1)) * X.rdzf(k);
+  T qz1 = X.ka_ccf(i, j, k + 1) * (c(i, j, k + 1) - cc) * X.rdzf(k + 1);
+  T divq = (qx0 - qx1) * (X.g.rdx * X.g.rdx) + (qy0 - qy1) * (X.g.rdy * X.g.rdy) + (qz0 - qz1) * X.rdzc(k);
+  return T(2) * cc * (X.in.aux[0](i, j, k) - ((ax + ay) + az) - divq);
+} };
+
 // ---- dispatch -------------------------------------------------------------------------------------------------
 #define OCB_FOR_EACH_DIAG(M) \
   M(OCB_DIAG_KE) M(OCB_DIAG_ADV) M(OCB_DIAG_PR) M(OCB_DIAG_WB) M(OCB_DIAG_EPS) M(OCB_DIAG_EPS_ISO) M(OCB_DIAG_TKE) \
@@ -593,7 +611,7 @@ OCB_EVAL(OCB_DIAG_KE_FORCING) {
   M(OCB_DIAG_T11C) M(OCB_DIAG_T22C) M(OCB_DIAG_T33C) M(OCB_DIAG_T12) M(OCB_DIAG_T13) M(OCB_DIAG_T23) M(OCB_DIAG_RI) \
   M(OCB_DIAG_RO) M(OCB_DIAG_EPV) M(OCB_DIAG_TWPV) M(OCB_DIAG_DEPV) M(OCB_DIAG_VF11) M(OCB_DIAG_VF22) M(OCB_DIAG_VF33) \
   M(OCB_DIAG_VF12) M(OCB_DIAG_VF13) M(OCB_DIAG_VF23) M(OCB_DIAG_FEPS) M(OCB_DIAG_SFEPS) M(OCB_DIAG_SFKE) M(OCB_DIAG_PI) \
-  M(OCB_DIAG_BPE) M(OCB_DIAG_APE) M(OCB_DIAG_UPSILON) M(OCB_DIAG_APE_EPS) M(OCB_DIAG_KE_STRESS) M(OCB_DIAG_KE_FORCING)
+  M(OCB_DIAG_BPE) M(OCB_DIAG_APE) M(OCB_DIAG_UPSILON) M(OCB_DIAG_APE_EPS) M(OCB_DIAG_KE_STRESS) M(OCB_DIAG_KE_FORCING) M(OCB_DIAG_C_TENDENCY)
 
 // diagnostics whose operands may be lazy perturbations (u - U, c - C); the flag is rejected for the others
 OCB_X constexpr bool ocb_diag_takes_perturbation(int d) {

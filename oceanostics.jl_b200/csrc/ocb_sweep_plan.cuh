@@ -34,7 +34,7 @@ static inline int ocb_diag_needs(int diag) {
   switch (diag) {
     case OCB_DIAG_PR: return OCB_NEED_P;
     case OCB_DIAG_WB: case OCB_DIAG_CHI: case OCB_DIAG_CDIFF: case OCB_DIAG_RI: case OCB_DIAG_EPV:
-    case OCB_DIAG_TWPV: case OCB_DIAG_DEPV: return OCB_NEED_B;
+    case OCB_DIAG_TWPV: case OCB_DIAG_DEPV: case OCB_DIAG_C_TENDENCY: return OCB_NEED_B;
     case OCB_DIAG_FEPS: case OCB_DIAG_PI: return OCB_NEED_AUX05;
     case OCB_DIAG_SFEPS: return OCB_NEED_AUX05 | OCB_NEED_AUX6;
     case OCB_DIAG_SFKE: return OCB_NEED_AUX6;

@@ -289,6 +289,35 @@ def ke_stress_ccc(i, j, k, g, closure, closure_fields, clock, fields, buoyancy):
             _op.iz_aac(i, j, k, g, psif, fields["w"], div_tau_3, *a))
 
 
+# --- Centered (2nd-order) tracer advection  [OCN-mem Advection/tracer_advection_operators.jl]: advective fluxes
+# Ax u ℑx c (fcc), Ay v ℑy c (cfc), Az w ℑz c (ccf) and their divergence at the cell centre
+def _adv_flux_x(i, j, k, g, U, c): return _op.Ax_fcc(i, j, k, g) * U[0][i, j, k] * _op.ix_faa(i, j, k, g, c)
+def _adv_flux_y(i, j, k, g, U, c): return _op.Ay_cfc(i, j, k, g) * U[1][i, j, k] * _op.iy_afa(i, j, k, g, c)
+def _adv_flux_z(i, j, k, g, U, c): return _op.Az_ccf(i, j, k, g) * U[2][i, j, k] * _op.iz_aaf(i, j, k, g, c)
+
+
+def div_Uc(i, j, k, g, advection, U, c):
+    return (_op.dx_caa(i, j, k, g, _adv_flux_x, U, c) + _op.dy_aca(i, j, k, g, _adv_flux_y, U, c) +
+            _op.dz_aac(i, j, k, g, _adv_flux_z, U, c)) / _op.V_ccc(i, j, k, g)
+
+
+def tracer_tendency(i, j, k, g, idx, name, advection, closure, c_immersed_bc, buoyancy, biogeochemistry, background_fields,
+                    velocities, tracers, auxiliary_fields, closure_fields, clock, forcing):
+    """Oceananigans NonhydrostaticModels.tracer_tendency [OCN-mem] for a model without background fields, biogeochemistry or
+    immersed boundaries (those arguments must be None here): -div_Uc - ∇_dot_qᶜ + forcing."""
+    assert c_immersed_bc is None and biogeochemistry is None and background_fields is None
+    c = tracers[name]
+    fields = {**velocities, **tracers}
+    U = (velocities["u"], velocities["v"], velocities["w"])
+    F = forcing(i, j, k, g, clock, fields) if forcing is not None else 0.0
+    return -div_Uc(i, j, k, g, advection, U, c) - div_q_c(i, j, k, g, closure, closure_fields, idx, c, clock, fields, buoyancy) + F
+
+
+def c_dt_c_ccc(i, j, k, g, idx, name, *args):                  # c∂ₜcᶜᶜᶜ, src/TracerVarianceEquation.jl:18-39
+    tracers = args[7]                                          # (advection, closure, c_immersed_bc, buoyancy, biogeochemistry, background_fields, velocities, tracers, ...)
+    return 2 * tracers[name][i, j, k] * tracer_tendency(i, j, k, g, idx, name, *args)
+
+
 class ContinuousForcing:
     """Oceananigans ContinuousForcing [OCN-mem]: F(i, j, k, grid, clock, fields) = func(x, y, z, t, deps..., [parameters]) with the
     nodes and the dependency fields taken at the forced field's own location `loc` (dependencies located elsewhere would be

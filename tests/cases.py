@@ -93,6 +93,15 @@ def build_cases(st: State, closure_name="scalar", mean="profile"):
     m_forced = st.model(closure=pc)
     m_forced.forcing.u, m_forced.forcing.v, m_forced.forcing.w = pforc["u"], pforc["v"], pforc["w"]
     cases.append(("KineticEnergyForcing", KE.KineticEnergyForcing(m_forced), ev(K.ke_forcing_ccc, og, "ccc", oforc, None, of), "ccc"))
+    # tracer-variance tendency (scope table 8f, row 2) of b with a space-dependent relaxation forcing handed over as a Field
+    Fb = K.ContinuousForcing(relax, "ccc", ("b",))
+    fb = type(st.ob)(og, "ccc")
+    ii, jj, kk = (np.arange(1 - og.H[d], fb.data.shape[d] - og.H[d] + 1) for d in range(3))
+    fb.data[...] = Fb(ii[:, None, None], jj[None, :, None], kk[None, None, :], og, None, of)
+    m_forced.forcing.b = mirror(fb, st.pg)
+    cases.append(("TracerVarianceTendency", TV.TracerVarianceTendency(m_forced, "b"),
+                  ev(K.c_dt_c_ccc, og, "ccc", 1, "b", None, oc, None, None, None, None, {"u": st.ou, "v": st.ov, "w": st.ow}, {"b": st.ob},
+                     None, None, None, Fb), "ccc"))
     # available-potential-energy family (scope table 8f): z✶ and Ψδ come from the oracle's sorted reference state and are
     # handed to both sides as fields, so these cases test the pointwise / flux kernels, not the sort (tests/test_bpe_gpu.py)
     from oracle import bpe as OB

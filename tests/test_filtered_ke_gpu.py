@@ -151,8 +151,7 @@ def test_subfilter_covariance_and_stress_tensor_against_the_oracle_graph():
 def test_names_outside_the_hot_path_fail_loudly():
     st = State(size=(8, 8, 8), device="cuda")
     m = st.model(closure=st.closures()["scalar"][1])
-    for fn in (ocb.KineticEnergyEquation.KineticEnergyTendency, ocb.TracerVarianceEquation.TracerVarianceTendency,
-               ocb.FlowDiagnostics.MixedLayerDepth):
+    for fn in (ocb.KineticEnergyEquation.KineticEnergyTendency, ocb.FlowDiagnostics.MixedLayerDepth):
         with pytest.raises(ocb.OcbError, match="Oceanostics.jl"):
             fn(m)
     assert ocb.KineticEnergyEquation.PotentialToKineticEnergyConversion is ocb.KineticEnergyEquation.PotentialEnergyConversion

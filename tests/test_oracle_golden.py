@@ -252,6 +252,44 @@ def test_ke_forcing_known_answer(gname):
     assert not K.evaluate(K.ke_forcing_ccc, g, "ccc", {}, None, f).any()
 
 
+def _tendency_args(cl, vel, b, forcing=None):
+    # (advection, closure, c_immersed_bc, buoyancy, biogeochemistry, background_fields, velocities, tracers, auxiliary_fields,
+    #  closure_fields, clock, forcing): the dependency tuple of src/TracerVarianceEquation.jl:72-85
+    return (None, cl, None, None, None, None, vel, {"b": b}, None, None, None, forcing)
+
+
+@pytest.mark.parametrize("gname", GRIDS)
+@pytest.mark.parametrize("cname", ["scalar", "smagorinsky_like", "tuple"])
+def test_tracer_variance_tendency_limits(gname, cname):
+    """c∂ₜcᶜᶜᶜ = 2c (-div_Uc - ∇·q + F) (src/TracerVarianceEquation.jl:18-39) in three limits: at rest and unforced it is
+    -c∇_dot_qᶜ (:93-98) cell by cell; a uniform horizontal flow moves variance around without creating any, so
+    <2c∂ₜc> = -<χ> (:157-161); and a pure relaxation F = -r c without flow or diffusion gives -2 r c²."""
+    g = GRIDS[gname]()
+    rng = np.random.default_rng(11)
+    cl = make_closures(g, rng)[cname]
+    b = OField(g, "ccc")
+    b.interior[...] = rng.standard_normal(b.interior.shape)
+    b.fill_halo()
+
+    def vel(u0, v0):
+        out = {}
+        for name, loc, val in (("u", "fcc", u0), ("v", "cfc", v0), ("w", "ccf", 0.0)):
+            f = OField(g, loc)
+            f.interior[...] = val
+            out[name] = f.fill_halo()
+        return out
+    rest = K.evaluate(K.c_dt_c_ccc, g, "ccc", 1, "b", *_tendency_args(cl, vel(0.0, 0.0), b))
+    dif = K.evaluate(K.c_div_q_c, g, "ccc", cl, None, 1, b)
+    np.testing.assert_allclose(rest, -dif, rtol=1e-13, atol=1e-300)
+    moving = K.evaluate(K.c_dt_c_ccc, g, "ccc", 1, "b", *_tendency_args(cl, vel(0.7, -0.4), b))
+    chi = K.evaluate(K.tracer_variance_dissipation_rate_ccc, g, "ccc", cl, None, 1, b)
+    assert not np.allclose(moving, rest)
+    assert K.integral(moving, g, "ccc") == pytest.approx(-K.integral(chi, g, "ccc"), rel=1e-10)
+    relax = K.ContinuousForcing(lambda x, y, z, t, c: -0.3 * c, "ccc", ("b",))
+    forced = K.evaluate(K.c_dt_c_ccc, g, "ccc", 1, "b", *_tendency_args(K.Closure(nu=0.0, kappa=0.0), vel(0.0, 0.0), b, relax))
+    np.testing.assert_allclose(forced, -0.6 * b.interior ** 2, rtol=1e-13, atol=1e-300)
+
+
 def test_richardson_and_ertel_pv_known_answers():
     """test/test_active_tracer_diagnostics.jl:24-80: u = S z + S y, b = N² z  =>
     Ri[3,3,3] = N²/S², EPV[3,3,3] = N² (f_z - S)."""
