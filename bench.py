@@ -273,7 +273,8 @@ def main():
     achieved = plan.algorithmic_bytes / (sweep_ms * 1e-3) / 1e9
     # DRAM traffic of one launch of the sweep kernel, from the committed ncu captures of this exact workload
     # (dram__bytes_read.sum + dram__bytes_write.sum; class-sum kernel: profiles/r1_launches_bench1024_sums_v2.csv, mean of
-    # five launches; with output fields: profiles/r1_ncu_budget1024_fields_v13_metrics.csv); null for other shapes
+    # five launches, captured with 36-column tiles -- the 34-column tiles adopted afterwards fetch 5.6 % less per tile and
+    # were not re-captured; with output fields: profiles/r1_ncu_budget1024_fields_v13_metrics.csv); null for other shapes
     traffic = None
     if size == (1024, 1024, 1024) and plan.variant == 1:
         traffic = (47783394000 + 60439114000) if args.fields else (48463504384 + 1897165)
