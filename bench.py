@@ -8,6 +8,10 @@ exchanges the y halos of u, v, w, b, p over NCCL and all-reduces the integrals.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--size NX NY NZ] [--fields] [--impl reference]
 
+N > 1 is STRONG scaling (BASELINE.json configs[2] as written): the 1024^3 grid is ONE job cut into N y slabs; the
+per-GPU-1024^3 run of round 1 is kept as the `weak` sub-object.  N = 1 adds `secondary`: the other BASELINE configs
+(2, 3B, 4, 5), each timed with CUDA events against its own roofline.
+
 Prints ONE JSON line (see the driver contract): value = whole-job Gcells/s with inputs resident in HBM;
 e2e = the same through the public API with HOST (pinned) inputs streamed in every step; roofline = the sweep
 kernel's algorithmic bytes / CUDA-event time against the measured HBM peak; cpu_baseline = the oracle's
@@ -26,7 +30,6 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "Gcells/s, fused KE + tracer-variance budget sweep (Float64)"
 
 
 def parse():
@@ -40,9 +43,12 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="N>1: exchange halos before the sweep instead of behind its interior rows")
-    ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
-                    help="N>1 halo exchange: direct stores into the neighbours' halos over NVLink (CUDA IPC), or NCCL send/recv")
-    ap.add_argument("--cpu-size", type=int, default=256, help="edge of the CPU-baseline sample cube")
+    ap.add_argument("--transport", default="ring", choices=["ring", "peer", "nccl"],
+                    help="N>1: ring = peer-memory push + gated sweep + in-kernel all-reduce (3 launches); peer = peer-memory push, "
+                         "interior/strip sweeps, ncclAllReduce; nccl = pack + ncclSend/Recv + unpack, ncclAllReduce")
+    ap.add_argument("--no-weak", action="store_true", help="N>1: skip the per-GPU-1024^3 (weak scaling) sub-run")
+    ap.add_argument("--no-secondary", action="store_true", help="N=1: skip the other BASELINE configs (secondary object)")
+    ap.add_argument("--cpu-size", type=int, default=None, help="edge of the CPU sample cube (cpu_baseline: 256, --impl reference: 512)")
     return ap.parse_args()
 
 
@@ -140,6 +146,217 @@ def budget_ops(ocb, m):
             TV.TracerVarianceDiffusion(m, "b")]
 
 
+def slab_inputs(m):
+    return [m.velocities.u, m.velocities.v, m.velocities.w, m.tracers.b, m.pressures.pNHS]
+
+
+def integrand_scales(ocb, torch, grid, m, dist, nplanes=8):
+    """sum |term| V of every budget term, estimated from `nplanes` planes in mid-depth (written as fields by the budget
+    kernel) and scaled to the whole depth: the yardstick of the N > 1 parity check (ADV and PR nearly cancel in the sum)."""
+    Nz = grid.N[2]
+    k0 = max(1, Nz // 2 - nplanes // 2)
+    k1 = min(Nz, k0 + nplanes - 1)
+    fs = [ocb.Field(o, indices=(None, None, (k0, k1))) for o in budget_ops(ocb, m)]
+    ocb.FusedDiagnostics(*fs).compute()
+    V = grid.d[0] * grid.d[1] * grid.d[2]
+    s = torch.stack([f.interior.abs().sum() for f in fs]) * (V * Nz / (k1 - k0 + 1))
+    if dist is not None:
+        dist.all_reduce(s)
+    return s
+
+
+class Runner:
+    """One workload (a job grid cut into `world` y slabs) with its step, built once and timed by `timed_run`."""
+
+    def __init__(self, ocb, torch, args, job, device, rank, world, dist):
+        self.ocb, self.torch, self.args, self.dist, self.world, self.rank, self.device = ocb, torch, args, dist, world, rank, device
+        self.grid, self.m = make_state(ocb, torch, job, device, rank, world)
+        grid, m = self.grid, self.m
+        self.fields = slab_inputs(m)
+        if world > 1:
+            from oceanostics_b200.distributed import SlabHaloExchanger
+            self.nccl_exchanger = SlabHaloExchanger(grid, self.fields, depth=2, rank=rank, world=world)
+            self.nccl_exchanger.exchange()
+            for f in self.fields:
+                f.fill_halo_regions_xz()
+        ops = budget_ops(ocb, m)
+        members = [ocb.Integral(o) for o in ops]
+        if args.fields:
+            members += [ocb.Field(o) for o in ops]
+        self.grp = ocb.FusedDiagnostics(*members)
+        self.plan = self.grp.plan
+        self.cells_local = grid.N[0] * grid.N[1] * grid.N[2]
+        self.cells_job = self.cells_local * world
+        self.transport = args.transport if world > 1 else None
+        self.ring = self.overlapped = self.exchanger = None
+        if world > 1:
+            from oceanostics_b200 import distributed as D
+            if args.fields and self.transport == "ring":
+                self.transport = "peer"          # the ring step is the integral-only class-sum sweep
+            if self.transport == "ring":
+                self.ring = D.RingSlabBudget(grid, self.fields, lambda: budget_ops(ocb, m), rank=rank, world=world)
+            elif not args.fields and not args.no_overlap:
+                self.overlapped = D.OverlappedSlabBudget(grid, self.fields, lambda: budget_ops(ocb, m), depth=2, rank=rank, world=world,
+                                                         transport=self.transport)
+            elif self.transport == "peer":
+                self.exchanger = D.PeerSlabExchanger(grid, self.fields, depth=2, rank=rank, world=world)
+            else:
+                self.exchanger = self.nccl_exchanger
+
+    def step(self):
+        if self.ring is not None:
+            return self.ring.step()
+        if self.overlapped is not None:
+            return self.overlapped.step()
+        if self.exchanger is not None:
+            self.exchanger.exchange()
+        self.plan.execute()
+        if self.dist is not None:
+            self.dist.all_reduce(self.plan.integrals)
+        return self.plan.integrals
+
+    def launches_per_step(self):
+        if self.ring is not None:
+            return 3                                                 # push (+ flag), gated sweep, partials + ring all-reduce
+        n = self.plan.n_launches
+        if self.overlapped is not None:
+            return 3 * n + (2 if self.transport == "peer" else 2)    # + push, wait | pack_many, unpack_many
+        if self.exchanger is not None:
+            return n + 2
+        return n
+
+    def halo_bytes(self):
+        x = self.ring.exchanger if self.ring is not None else (self.overlapped.exchanger if self.overlapped is not None else self.exchanger)
+        return x.bytes_per_exchange if x is not None else 0
+
+    def timed_run(self, steps, warmup, sampler=None):
+        """W untimed steps, then exactly K steps between barrier + synchronize; CUDA events, max over ranks."""
+        torch, dist = self.torch, self.dist
+        for _ in range(warmup):
+            self.step()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        single = self.world == 1
+        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)] if single else None
+
+        def region():
+            torch.cuda.synchronize()
+            ev0.record()
+            for s in range(steps):
+                if single:
+                    kev[s][0].record()
+                    self.plan.execute()
+                    kev[s][1].record()
+                else:
+                    self.step()
+            ev1.record()
+            torch.cuda.synchronize()
+        if sampler is not None:
+            with sampler:
+                region()
+        else:
+            region()
+        total_ms = ev0.elapsed_time(ev1)
+        timeline = None
+        stepper = self.ring if self.ring is not None else self.overlapped
+        if stepper is not None:          # one more (untimed) step with event marks: where the exchange ends relative to the step
+            tl = {}
+            stepper.step()
+            stepper.step(timeline=tl)
+            torch.cuda.synchronize()
+            timeline = stepper.timeline_ms(tl)
+        if single:
+            sweep_ms = sum(a.elapsed_time(b) for a, b in kev) / steps
+        else:
+            # the sweep kernel alone (ungated, no exchange), timed after the region
+            if dist is not None:
+                dist.barrier()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(steps):
+                self.plan.execute()
+            b.record()
+            torch.cuda.synchronize()
+            sweep_ms = a.elapsed_time(b) / steps
+        per_rank = None
+        t = torch.tensor([total_ms, sweep_ms], dtype=torch.float64, device=self.device)
+        if dist is not None:
+            keys = ("exchange_end", "interior_end", "strips_end", "end")
+            mine = [total_ms / steps, sweep_ms] + [float((timeline or {}).get(k, 0.0)) for k in keys]
+            every = [torch.zeros(6, dtype=torch.float64, device=self.device) for _ in range(self.world)]
+            dist.all_gather(every, torch.tensor(mine, dtype=torch.float64, device=self.device))
+            per_rank = [[round(float(x), 3) for x in e] for e in every]
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.barrier()
+        total_ms, sweep_ms = float(t[0]), float(t[1])
+        ms_per_step = total_ms / steps
+        res = {"ms_per_step": ms_per_step, "sweep_ms": sweep_ms, "value": self.cells_job / (ms_per_step * 1e-3) / 1e9,
+               "timeline": timeline, "per_rank": per_rank}
+        for x in (self.ring, self.overlapped.exchanger if self.overlapped is not None else None, self.exchanger):
+            if x is not None and hasattr(x, "check"):
+                x.check()                                    # a halo wait that timed out invalidates the run
+        return res
+
+    def integrals(self):
+        if self.ring is not None:
+            return [float(x) for x in self.ring.total.cpu()]
+        if self.overlapped is not None:
+            return [float(x) for x in self.overlapped.total.cpu()]
+        return self.grp.integrals()
+
+    def parity_check(self):
+        """N > 1: the step's integrals against the plain route -- NCCL send/recv halo exchange (2 rows), the ungated sweep of
+        the whole slab, ncclAllReduce -- to 1e-12 of each integrand's scale (sum |term| V)."""
+        torch, dist = self.torch, self.dist
+        got = torch.tensor(self.integrals(), dtype=torch.float64, device=self.device)
+        self.nccl_exchanger.exchange()
+        self.plan.execute()
+        want = self.plan.integrals[:got.numel()].clone()
+        dist.all_reduce(want)
+        scale = integrand_scales(self.ocb, torch, self.grid, self.m, dist)
+        err = ((got - want).abs() / scale).cpu()
+        spread = got.clone()
+        dist.all_reduce(spread, op=dist.ReduceOp.MAX)
+        same_bits = bool((spread == got).all())              # every rank holds the same integrals
+        ok = bool((err <= 1e-12).all()) and bool(torch.isfinite(got).all()) and same_bits
+        return {"parity_check": "ok" if ok else "FAILED", "against": "nccl halo exchange (2 rows) + ungated sweep + ncclAllReduce",
+                "max_err_over_scale": float(err.max()), "tolerance": 1e-12, "identical_on_every_rank": same_bits,
+                "reference_integrals": [float(x) for x in want.cpu()]}
+
+
+def measured_traffic(size, fields):
+    """DRAM bytes (read + write) of one launch of the dominant kernel, from the committed ncu capture of this workload
+    (profiles/r2_traffic_bench1024_*.csv, `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` over bench.py); None when
+    no capture of this shape is committed."""
+    import csv
+    if tuple(size) != (1024, 1024, 1024):
+        return None, None
+    path = os.path.join(ROOT, "profiles", "r2_traffic_bench1024_%s.csv" % ("fields" if fields else "sums"))
+    kern = "ocb_budget_kernel" if fields else "ocb_budget_sums_kernel"
+    if not os.path.exists(path):
+        return None, None
+    per_id = {}
+    with open(path, newline="") as f:
+        rows = [r for r in csv.reader(f) if r]
+    try:
+        hdr = next(i for i, r in enumerate(rows) if "Kernel Name" in r and "Metric Value" in r)
+    except StopIteration:
+        return None, None
+    h = rows[hdr]
+    ci, ck, cm, cv, cu = h.index("ID"), h.index("Kernel Name"), h.index("Metric Name"), h.index("Metric Value"), h.index("Metric Unit")
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    for r in rows[hdr + 1:]:
+        if len(r) <= cv or kern not in r[ck] or not r[cm].startswith("dram__bytes_"):
+            continue
+        per_id[r[ci]] = per_id.get(r[ci], 0.0) + float(r[cv].replace(",", "")) * mult.get(r[cu], 1.0)
+    if not per_id:
+        return None, None
+    return sum(per_id.values()) / len(per_id), os.path.relpath(path, ROOT)
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -147,6 +364,7 @@ def main():
         return run_reference(args)
     import torch
     import ocb_loader
+    from bench_config import METRIC, UNIT, DEFAULT_SIZE, workload_config
     ocb = ocb_loader.load()
 
     rank = int(os.environ.get("RANK", 0))
@@ -159,181 +377,110 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        # NCCL's internal stream at high priority: its send / recv blocks are placed ahead of the sweep's pending blocks
-        # whenever an SM frees up, so the ring exchange stays hidden behind the interior rows
         opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
         dist.init_process_group("nccl", device_id=device, pg_options=opts)
-    size = tuple(args.size) if args.size else (1024, 1024, 1024)
-    # weak scaling: every rank owns a full `size` slab stack => the job is size[0] x (size[1]*world) x size[2]
-    job = (size[0], size[1] * world, size[2])
-    grid, m = make_state(ocb, torch, job, device, rank, world)
-    exchanger = None
-    if world > 1:
-        from oceanostics_b200.distributed import SlabHaloExchanger
-        exchanger = SlabHaloExchanger(grid, [m.velocities.u, m.velocities.v, m.velocities.w, m.tracers.b, m.pressures.pNHS],
-                                      depth=2, rank=rank, world=world)
-        exchanger.exchange()
-        for f in (m.velocities.u, m.velocities.v, m.velocities.w, m.tracers.b, m.pressures.pNHS):
-            f.fill_halo_regions_xz()
+    size = tuple(args.size) if args.size else DEFAULT_SIZE
+    if size[1] % world:
+        raise SystemExit(f"Ny = {size[1]} is not divisible by {world} slabs")
+    steps, warmup = args.steps, max(args.warmup, 3)
 
-    ops = budget_ops(ocb, m)
-    members = [ocb.Integral(o) for o in ops]
-    if args.fields:
-        members += [ocb.Field(o) for o in ops]
-    grp = ocb.FusedDiagnostics(*members)
-    plan = grp.plan
-    cells_local = grid.N[0] * grid.N[1] * grid.N[2]
-    cells_job = cells_local * world
-    overlapped = None
-    if world > 1 and not args.fields and not args.no_overlap:
-        from oceanostics_b200.distributed import OverlappedSlabBudget
-        overlapped = OverlappedSlabBudget(grid, [m.velocities.u, m.velocities.v, m.velocities.w, m.tracers.b, m.pressures.pNHS],
-                                          lambda: budget_ops(ocb, m), depth=2, rank=rank, world=world, transport=args.transport)
-    elif world > 1 and args.transport == "peer":
-        from oceanostics_b200.distributed import PeerSlabExchanger
-        exchanger = PeerSlabExchanger(grid, [m.velocities.u, m.velocities.v, m.velocities.w, m.tracers.b, m.pressures.pNHS],
-                                      depth=2, rank=rank, world=world)
-
-    def step():
-        if overlapped is not None:
-            overlapped.step()
-            return
-        if exchanger is not None:
-            exchanger.exchange()
-        plan.execute()
-        if dist is not None:
-            dist.all_reduce(plan.integrals)
-
+    # ---- headline: BASELINE configs[2] as written -- the `size` grid as ONE job, y slabs over the N GPUs (strong scaling) ----
     sampler = ClockSampler(local, enabled=(rank == 0))      # NVML set up here, outside the timed region; rank 0 reports its board
-    for _ in range(max(args.warmup, 3)):
-        step()
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    # ---- timed region: device-resident inputs ---------------------------------------------------------------
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    with sampler as clocks:
-        torch.cuda.synchronize()
-        ev0.record()
-        for s in range(args.steps):
-            if overlapped is not None:
-                overlapped.step()
-                continue
-            if exchanger is not None:
-                exchanger.exchange()
-            kev[s][0].record()
-            plan.execute()
-            kev[s][1].record()
-            if dist is not None:
-                dist.all_reduce(plan.integrals)
-        ev1.record()
-        torch.cuda.synchronize()
-    total_ms = ev0.elapsed_time(ev1)
-    timeline = None
-    if overlapped is not None:       # one more (untimed) step with event marks: where the exchange ends relative to the sweep
-        tl = {}
-        overlapped.step()
-        overlapped.step(timeline=tl)
-        torch.cuda.synchronize()
-        timeline = overlapped.timeline_ms(tl)
-    if overlapped is None:
-        sweep_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
-    else:
-        # the sweep kernel alone, timed after the region (the overlapped step interleaves three sweeps with the exchange)
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(args.steps):
-            plan.execute()
-        b.record()
-        torch.cuda.synchronize()
-        sweep_ms = a.elapsed_time(b) / args.steps
-    t = torch.tensor([total_ms, sweep_ms], dtype=torch.float64, device=device)
-    per_rank = None
-    if dist is not None:
-        # every rank's own numbers (loop time per step, stand-alone sweep, where its marked step's phases end): the boards of a
-        # box do not run at the same clock under their power caps, and the all-reduce makes every step as long as the slowest
-        mine = [total_ms / args.steps, sweep_ms] + ([timeline[k] for k in ("exchange_end", "interior_end", "strips_end", "end")] if timeline else [0.0] * 4)
-        every = [torch.zeros(6, dtype=torch.float64, device=device) for _ in range(world)]
-        dist.all_gather(every, torch.tensor(mine, dtype=torch.float64, device=device))
-        per_rank = [[round(float(x), 3) for x in e] for e in every]
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.barrier()
-    total_ms, sweep_ms = float(t[0]), float(t[1])
-    ms_per_step = total_ms / args.steps
-    value = cells_job / (ms_per_step * 1e-3) / 1e9
-
+    run = Runner(ocb, torch, args, size, device, rank, world, dist)
+    res = run.timed_run(steps, warmup, sampler)
+    plan, grid = run.plan, run.grid
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = plan.algorithmic_bytes / (sweep_ms * 1e-3) / 1e9
-    # DRAM traffic of one launch of the sweep kernel, from the committed ncu captures of this exact workload
-    # (dram__bytes_read.sum + dram__bytes_write.sum; class-sum kernel: profiles/r1_launches_bench1024_sums_v2.csv, mean of
-    # five launches, captured with 36-column tiles -- the 34-column tiles adopted afterwards fetch 5.6 % less per tile and
-    # were not re-captured; with output fields: profiles/r1_ncu_budget1024_fields_v13_metrics.csv); null for other shapes
-    traffic = None
-    if size == (1024, 1024, 1024) and plan.variant == 1:
-        traffic = (47783394000 + 60439114000) if args.fields else (48463504384 + 1897165)
-    integrals = grp.integrals() if overlapped is None else [float(x) for x in overlapped.total.cpu()]
-
+    achieved = plan.algorithmic_bytes / (res["sweep_ms"] * 1e-3) / 1e9
+    traffic, traffic_src = measured_traffic(size, args.fields) if world == 1 else (None, None)
+    variant = {0: "generic", 1: "fused-budget", 2: "fused-budget + generic"}.get(plan.variant, str(plan.variant))
     out = {
-        "metric": METRIC, "value": round(value, 3), "unit": "Gcells/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
+        "metric": METRIC, "value": round(res["value"], 3), "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": round(res["ms_per_step"], 4), "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"config 3{'B' if args.fields else 'A'}: {job[0]}x{job[1]}x{job[2]} Float64, fused KE budget "
-                               "{K, ADV(Centered-2), PR, u_i b_i, eps} + tracer variance {chi, 2c div F}, 7 volume integrals"
-                               + (" + 7 output fields" if args.fields else ""),
-                   "per_gpu_grid": list(size), "halo": 3, "topology": "Periodic,Periodic,Bounded",
-                   "parallelism": f"y-slabs x{world}" if world > 1 else "single GPU",
-                   "l2": "inputs (5 x %.2f GB per GPU) exceed the 126 MB L2; no flush needed" % (cells_local * 8 / 1e9),
-                   "kernel_variant": {0: "generic", 1: "fused-budget", 2: "fused-budget + generic"}.get(plan.variant, str(plan.variant))},
+        "config": workload_config(size, world, args.fields),
+        "kernel_variant": variant + (" (class sums)" if not args.fields else ""),
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                     "traffic": traffic, "kernel_ms": round(sweep_ms, 4), "algorithmic_bytes_per_cell": plan.algorithmic_bytes / cells_local,
+                     "traffic": traffic, "traffic_source": traffic_src, "kernel_ms": round(res["sweep_ms"], 4),
+                     "kernel": "ocb_budget_kernel" if args.fields else "ocb_budget_sums_kernel",
+                     "algorithmic_bytes_per_cell": plan.algorithmic_bytes / run.cells_local, "cells_per_launch": run.cells_local,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
-        "gpu_launches": ((3 if overlapped is not None else 1) * plan.n_launches + ((3 if args.transport == "peer" else 2) if exchanger is not None else 0)) * args.steps,   # + push, signal, wait | pack_many, unpack_many
-        "clocks": clocks.summary(),
-        "integrals": integrals,
+        "gpu_launches": run.launches_per_step() * steps,
+        "clocks": sampler.summary(),
+        "integrals": run.integrals(),
     }
     if world > 1:
-        out["comm"] = {"step_minus_sweep_ms": round(ms_per_step - sweep_ms, 4), "overlapped": overlapped is not None, "timeline_ms": timeline,
-                       "per_rank_ms": {"columns": ["loop_step", "sweep_alone", "exchange_end", "interior_end", "strips_end", "end"], "rows": per_rank},
-                       "halo_bytes_per_rank_per_step": exchanger.bytes_per_exchange,
-                       "transport": args.transport,
-                       "note": "exchange (peer: one kernel storing the edge rows into the neighbours' halos over NVLink + flag words; nccl: "
-                               "pack, grouped send/recv ring, unpack) + all-reduce of the 7 integrals; when overlapped it runs on a side "
-                               "stream behind the interior rows and only the edge strips wait for it"}
-        px = overlapped.exchanger if overlapped is not None else exchanger
-        if hasattr(px, "check"):
-            px.check()                                   # a halo wait that timed out invalidates the run
+        out["comm"] = {"step_minus_sweep_ms": round(res["ms_per_step"] - res["sweep_ms"], 4), "transport": run.transport,
+                       "timeline_ms": res["timeline"],
+                       "per_rank_ms": {"columns": ["loop_step", "sweep_alone", "exchange_end", "interior_end", "strips_end", "end"], "rows": res["per_rank"]},
+                       "halo_bytes_per_rank_per_step": run.halo_bytes(),
+                       "note": {"ring": "peer-memory ring, 3 launches per step: one kernel stores ONE edge row of the 5 inputs into each y "
+                                        "neighbour's halo over NVLink and publishes the step; the class-sum sweep runs its two halo-reading "
+                                        "tile rows last, gated in the kernel on the neighbours' flags; one block sums the partials and "
+                                        "all-reduces the 7 integrals through the ranks' mapped sync blocks (no NCCL on the data path)",
+                                "peer": "peer-memory push of 2 rows + stream-ordered wait, interior / strip sweeps, ncclAllReduce",
+                                "nccl": "pack, grouped ncclSend/Recv ring, unpack, sweep, ncclAllReduce"}[run.transport]}
+        out["comm"].update(run.parity_check())
+    # ---- N > 1: the per-GPU-1024^3 (weak) run of round 1, as a sub-object -------------------------------------------
+    if world > 1 and not args.no_weak:
+        free_b, _ = torch.cuda.mem_get_info(device)
+        need = 5 * (size[0] + 6) * (size[1] + 6) * (size[2] + 7) * 8 * 1.15
+        del run, plan, grid
+        import gc
+        gc.collect()
+        ok = torch.tensor([1.0 if free_b > need else 0.0], device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok) > 0:
+            wjob = (size[0], size[1] * world, size[2])
+            wrun = Runner(ocb, torch, args, wjob, device, rank, world, dist)
+            wres = wrun.timed_run(steps, warmup)
+            out["weak"] = {"scaling": "weak", "workload": f"{wjob[0]}x{wjob[1]}x{wjob[2]} Float64: {size[0]}x{size[1]}x{size[2]} per GPU",
+                           "value": round(wres["value"], 3), "unit": UNIT, "ms_per_step": round(wres["ms_per_step"], 4),
+                           "sweep_ms": round(wres["sweep_ms"], 4), "step_minus_sweep_ms": round(wres["ms_per_step"] - wres["sweep_ms"], 4),
+                           "timeline_ms": wres["timeline"], "halo_bytes_per_rank_per_step": wrun.halo_bytes()}
+            out["weak"].update(wrun.parity_check())
+            run = wrun
+        else:
+            out["weak"] = {"skipped": "not enough free device memory for a 1024^3 slab per GPU next to the strong-scaling state"}
+            run = Runner(ocb, torch, args, size, device, rank, world, dist)
     # ---- end to end with HOST inputs: every rank streams its own slab from pinned host memory -----------------------
     e2e = None
     if not args.no_e2e:
+        if world > 1 and "weak" in out and "value" in out["weak"]:     # e2e is measured on the headline (strong) workload
+            del run
+            import gc
+            gc.collect()
+            run = Runner(ocb, torch, args, size, device, rank, world, dist)
         import psutil
-        need = 5 * cells_local * 8 * 1.05 * world            # all ranks of this node pin their slab's five inputs
+        need = 5 * run.cells_local * 8 * 1.05 * world            # all ranks of this node pin their slab's five inputs
         ok = psutil.virtual_memory().available > 1.4 * need
         flag = torch.tensor([1.0 if ok else 0.0], device=device)
         if dist is not None:
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if float(flag) > 0:
             from bench_e2e import run_e2e
-            e2e = run_e2e(ocb, torch, grid, m, args, dist=dist, exchanger=exchanger)
+            e2e = run_e2e(ocb, torch, run.grid, run.m, args, dist=dist)
             t = torch.tensor([e2e["ms_per_step"]], dtype=torch.float64, device=device)
             if dist is not None:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e["ms_per_step"] = round(float(t[0]), 3)
-            e2e["value"] = round(cells_job / (float(t[0]) * 1e-3) / 1e9, 4)
+            e2e["value"] = round(run.cells_job / (float(t[0]) * 1e-3) / 1e9, 4)
             e2e["h2d_bytes_per_step"] *= world
             e2e["d2h_bytes_per_step"] *= world
         else:
-            e2e = {"value": None, "unit": "Gcells/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
+            e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
                    "skipped": "not enough free host memory to pin every rank's inputs"}
+    if e2e is not None:
+        out["e2e"] = e2e
+    # ---- N = 1: the other BASELINE configs, driver-timed as a `secondary` object --------------------------------------
+    if world == 1 and not args.no_secondary:
+        from bench_secondary import run_secondary
+        out["secondary"] = run_secondary(ocb, torch, run, peak, steps=min(steps, 5))
     if rank == 0:
-        if e2e is not None:
-            out["e2e"] = e2e
         if not args.no_cpu and world == 1:
             from bench_reference import cpu_baseline
             out["cpu_baseline"] = cpu_baseline(args)

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define OCB_ABI_VERSION 1
+#define OCB_ABI_VERSION 2
 
 /* ---- status codes -------------------------------------------------------------------------- */
 enum {
@@ -289,6 +289,34 @@ int ocb_ipc_close(void* base);
 int ocb_halo_push_y_many(int32_t dtype, const ocb_field* fields, int32_t n_fields, int32_t h, void* const* peer_arrays,
                          const int32_t* peer_ny, void* lo_flag, void* hi_flag, int64_t step, void* stream);
 int ocb_halo_wait(void* flags, int64_t step, double timeout_seconds, void* stream);
+
+/* ---- peer-memory ring: the slab step as ONE gated sweep + ONE reduction kernel (no NCCL on the data path) -----------
+ * This is the survey's `ocb_comm_init` seam in peer-memory form: the host layer (Julia: MPI / NCCL
+ * bootstrap of Oceananigans' Distributed; Python: torch.distributed) only carries the IPC handles at set-up.
+ * Every rank owns one zero-initialised device "sync block" of OCB_RING_SYNC_WORDS 64-bit words and maps every other
+ * rank's block (ocb_ipc_export / ocb_ipc_import):
+ *   word 0, 1   halo flags: the step number of the last push from the low / high y neighbour (ocb_halo_push_y_many's
+ *               lo_flag = low neighbour's word 1, hi_flag = high neighbour's word 0)
+ *   word 2      set to 1 when a wait gave up (also: the integrals read NaN on every rank)
+ *   word 8 + 16 p + r          "rank r's partial integrals of a step with parity p have landed" (the step number)
+ *   word 64 + 16 (16 p + r) + s  rank r's partial integral of slot s (a double), parity p
+ * ocb_plan_execute_ring runs the plan's sweep with the tiles that read a neighbour's halo row placed last in launch order
+ * and made to wait (in the kernel) for that neighbour's push of `step`, so the sweep of the rows that need no neighbour
+ * data overlaps the exchange; one more kernel then sums this rank's per-block partials, stores them into every rank's sync
+ * block over NVLink, waits for all ranks' and adds them in rank order -- the same bits on every rank.  `step` must
+ * increase by one per call and match the `step` of the pushes; the reduction is also the collective that orders the next
+ * push after this step's halo reads (the ordering contract above).  Plans it accepts: integrals only, evaluated by the
+ * class-sum budget kernel over the whole y extent of a y-periodic (slab) grid; anything else is OCB_ERR_UNSUPPORTED and
+ * the host layer runs exchange + ocb_plan_execute + its own all-reduce instead. */
+#define OCB_MAX_RANKS 16
+#define OCB_RING_SYNC_WORDS 1024
+typedef struct {
+  int32_t rank, nranks;
+  void*   sync[OCB_MAX_RANKS];    /* sync[r]: rank r's sync block as mapped in this process (sync[rank] = its own) */
+  double  timeout_seconds;        /* a wait that lasts longer gives up (never a hang) */
+} ocb_ring;
+int ocb_plan_ring_capable(const ocb_plan* plan);   /* 1 if ocb_plan_execute_ring accepts this plan */
+int ocb_plan_execute_ring(ocb_plan* plan, double* integrals, const ocb_ring* ring, int64_t step, void* stream);
 
 #ifdef __cplusplus
 }

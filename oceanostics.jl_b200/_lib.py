@@ -18,6 +18,9 @@ OCB_MAX_CLOSURE_FIELDS = 2
 OCB_N_AUX = 7
 OCB_MAX_REQ = 16
 OCB_MAX_FILTER_WIDTH = 64
+OCB_MAX_RANKS = 16
+OCB_RING_SYNC_WORDS = 1024
+OCB_ABI_VERSION = 2
 
 OCB_REQ_PERTURBATION = 1
 OCB_REQ_TENSOR_DIM1, OCB_REQ_TENSOR_DIM2, OCB_REQ_TENSOR_DIM3 = 1 << 4, 1 << 5, 1 << 6
@@ -86,6 +89,10 @@ class ocb_filter_pass(C.Structure):
                 ("nodes", C.c_void_p), ("spacings", C.c_void_p)]
 
 
+class ocb_ring(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("nranks", C.c_int32), ("sync", C.c_void_p * OCB_MAX_RANKS), ("timeout_seconds", C.c_double)]
+
+
 class OcbError(RuntimeError):
     """A non-zero status from the library (OCB_ERR_CUDA / ALLOC / UNSUPPORTED)."""
 
@@ -129,12 +136,15 @@ def lib():
     L.ocb_halo_push_y_many.argtypes = [C.c_int32, P(ocb_field), C.c_int32, C.c_int32, P(C.c_void_p), P(C.c_int32), C.c_void_p, C.c_void_p,
                                        C.c_int64, C.c_void_p]
     L.ocb_halo_wait.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_void_p]
+    L.ocb_plan_ring_capable.argtypes = [C.c_void_p]
+    L.ocb_plan_execute_ring.argtypes = [C.c_void_p, C.c_void_p, P(ocb_ring), C.c_int64, C.c_void_p]
     for name in ("ocb_plan_create", "ocb_plan_execute", "ocb_plan_destroy", "ocb_plan_info", "ocb_fill_halo",
                  "ocb_filter_execute", "ocb_bpe_reference_height", "ocb_sort_pairs", "ocb_pointwise",
                  "ocb_halo_pack_y", "ocb_halo_unpack_y", "ocb_halo_pack_y_many", "ocb_gather_sorted", "ocb_bpe_profile_lookup",
-                 "ocb_ipc_export", "ocb_ipc_import", "ocb_ipc_close", "ocb_halo_push_y_many", "ocb_halo_wait"):
+                 "ocb_ipc_export", "ocb_ipc_import", "ocb_ipc_close", "ocb_halo_push_y_many", "ocb_halo_wait",
+                 "ocb_plan_ring_capable", "ocb_plan_execute_ring"):
         getattr(L, name).restype = C.c_int
-    if L.ocb_abi_version() != 1:
+    if L.ocb_abi_version() != OCB_ABI_VERSION:
         raise OcbError("liboceanostics_b200.so ABI version mismatch")
     _lib = L
     return L
@@ -144,7 +154,7 @@ EXPORTED_SYMBOLS = ["ocb_abi_version", "ocb_last_error", "ocb_device_count", "oc
                     "ocb_plan_destroy", "ocb_plan_info", "ocb_fill_halo", "ocb_filter_execute",
                     "ocb_bpe_reference_height", "ocb_sort_pairs", "ocb_pointwise", "ocb_halo_pack_y", "ocb_halo_unpack_y",
                     "ocb_halo_pack_y_many", "ocb_gather_sorted", "ocb_bpe_profile_lookup", "ocb_ipc_export", "ocb_ipc_import",
-                    "ocb_ipc_close", "ocb_halo_push_y_many", "ocb_halo_wait"]
+                    "ocb_ipc_close", "ocb_halo_push_y_many", "ocb_halo_wait", "ocb_plan_ring_capable", "ocb_plan_execute_ring"]
 
 
 def check(status: int):

@@ -37,6 +37,12 @@ int ocb_sm_count() {
   return cached > 0 ? cached : 148;
 }
 
+long long ocb_cycles(double seconds) {
+  int dev = 0, khz = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev) != cudaSuccess || khz <= 0) khz = 1965000;
+  return (long long)(seconds * 1e3 * (double)khz);
+}
+
 // Stream-ordered scratch (cudaMallocAsync) comes from the device's default pool; by default the pool hands memory
 // back to the OS at every synchronisation, which would make each filter / sort call re-allocate gigabytes.  Keep it.
 void ocb_keep_scratch_pool() {
@@ -70,4 +76,67 @@ __global__ void __launch_bounds__(256) ocb_finalize_partials_kernel(const double
 
 void ocb_launch_finalize_partials(const double* partial, int nblocks, int nslots, double* out, cudaStream_t st) {
   ocb_finalize_partials_kernel<<<nslots, 256, 0, st>>>(partial, nblocks, nslots, out);
+}
+
+// ---- the same, followed by the sum over the ranks of a peer-memory ring (ocb_plan_execute_ring) -----------------------
+// One block.  Slot sums exactly as above (same order, same bits); thread r then stores them into rank r's sync block and
+// publishes the step number behind a system-scope fence; threads r < nranks wait for rank r's contribution to this
+// rank's block and thread 0 adds them in rank order.  Two parities: a rank can be one step ahead of a slow reader, never two
+// (it needs everyone's contribution of step k+1, sent after their step-k reads, before it can send step k+2).
+struct RingPeers { long long* sync[OCB_MAX_RANKS]; };
+__global__ void __launch_bounds__(256) ocb_finalize_ring_kernel(const double* __restrict__ partial, int nblocks, int nslots,
+                                                                 double* __restrict__ out, const __grid_constant__ RingPeers peers,
+                                                                 int rank, int nranks, long long step, long long timeout_cycles) {
+  __shared__ double sh[256];
+  __shared__ double mine[16];   // OCB_MAX_REQ slots at most
+  __shared__ int timed_out;
+  const int t = threadIdx.x;
+  if (t == 0) timed_out = 0;
+  for (int s = 0; s < nslots; ++s) {
+    double acc = 0.0;
+    for (int b = t; b < nblocks; b += 256) acc += partial[(size_t)b * nslots + s];
+    sh[t] = acc;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+      if (t < w) sh[t] += sh[t + w];
+      __syncthreads();
+    }
+    if (t == 0) mine[s] = sh[0];
+    __syncthreads();
+  }
+  const int par = (int)(step & 1);
+  if (t < nranks) {
+    long long* dst = peers.sync[t];
+    double* slots = reinterpret_cast<double*>(dst + 64 + 16 * (16 * par + rank));
+    for (int s = 0; s < nslots; ++s) slots[s] = mine[s];
+    __threadfence_system();
+    asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(dst + 8 + 16 * par + rank), "l"(step) : "memory");
+  }
+  long long* own = peers.sync[rank];
+  if (t < nranks) {
+    const long long t0 = clock64();
+    for (;;) {
+      long long seen;
+      asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(seen) : "l"(own + 8 + 16 * par + t) : "memory");
+      if (seen >= step) break;
+      if (clock64() - t0 > timeout_cycles) { timed_out = 1; own[2] = 1; break; }
+      __nanosleep(50);
+    }
+  }
+  __syncthreads();
+  if (t < nslots) {
+    double total = 0.0;
+    for (int r = 0; r < nranks; ++r)
+      total += *reinterpret_cast<volatile double*>(own + 64 + 16 * (16 * par + r) + t);
+    out[t] = timed_out ? __longlong_as_double(0x7ff8000000000000LL) : total;
+  }
+}
+
+int ocb_launch_finalize_ring(const double* partial, int nblocks, int nslots, double* out, const ocb_ring* ring, long long step,
+                             long long timeout_cycles, cudaStream_t st) {
+  RingPeers P;
+  for (int r = 0; r < OCB_MAX_RANKS; ++r) P.sync[r] = r < ring->nranks ? (long long*)ring->sync[r] : nullptr;
+  ocb_finalize_ring_kernel<<<1, 256, 0, st>>>(partial, nblocks, nslots, out, P, ring->rank, ring->nranks, step, timeout_cycles);
+  OCB_CUDA(cudaGetLastError());
+  return OCB_OK;
 }

@@ -632,6 +632,7 @@ extern "C" int ocb_gather_sorted(int32_t dtype, const ocb_field* src, const int6
   OCB_REQUIRE(dtype == OCB_F32 || dtype == OCB_F64, "bad dtype");
   int rc = ocb_require_device();
   if (rc != OCB_OK) return rc;
+  OcbDeviceGuard device_guard(src->data);
   if (n == 0) return OCB_OK;
   return dtype == OCB_F64 ? gather_impl<double>(src, perm, (double*)dst, n, (cudaStream_t)stream)
                           : gather_impl<float>(src, perm, (float*)dst, n, (cudaStream_t)stream);
@@ -645,6 +646,7 @@ extern "C" int ocb_bpe_profile_lookup(const ocb_grid* grid, const ocb_field* b, 
   for (int d = 0; d < 3; ++d) OCB_REQUIRE(b->loc[d] == OCB_CENTER && zstar->loc[d] == OCB_CENTER, "b and zstar must be (Center, Center, Center) fields");
   int rc = ocb_require_device();
   if (rc != OCB_OK) return rc;
+  OcbDeviceGuard device_guard(b->data);
   ocb_keep_scratch_pool();
   cudaStream_t st = (cudaStream_t)stream;
   return grid->dtype == OCB_F64 ? lookup_impl<double>(grid, b, (const double*)b_profile, (const double*)z_profile, m, zstar, psi_delta, st)
@@ -656,6 +658,7 @@ extern "C" int ocb_sort_pairs(int32_t dtype, const void* keys_in, void* keys_out
   OCB_REQUIRE(dtype == OCB_F32 || dtype == OCB_F64, "bad dtype");
   int rc = ocb_require_device();
   if (rc != OCB_OK) return rc;
+  OcbDeviceGuard device_guard(keys_in);
   if (n == 0) return OCB_OK;
   ocb_keep_scratch_pool();
   return dtype == OCB_F64 ? sort_impl<double, uint64_t>((const double*)keys_in, (double*)keys_out, perm_out, n, (cudaStream_t)stream)
@@ -673,6 +676,7 @@ extern "C" int ocb_bpe_reference_height(const ocb_grid* grid, const ocb_field* b
                             "stretched. Only `HeavisideIntegral()` supports stretched grids.");
   int rc = ocb_require_device();
   if (rc != OCB_OK) return rc;
+  OcbDeviceGuard device_guard(b->data);
   ocb_keep_scratch_pool();
   cudaStream_t st = (cudaStream_t)stream;
   return grid->dtype == OCB_F64 ? bpe_impl<double, uint64_t>(grid, b, method, zstar, psi_delta, perm_out, b_sorted_out, st)

@@ -47,8 +47,17 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
   const int tid = warp * 32 + lane;
   int bid = blockIdx.x;
   const int tx = bid % P.tiles_x; bid /= P.tiles_x;
-  const int ty = bid % P.tiles_y; bid /= P.tiles_y;
-  const int chunk = bid;
+  int ty, chunk;
+  if (P.gate) {
+    // slab of a ring (ocb_plan_execute_ring): the two tile rows that read a neighbour's halo row come LAST in launch
+    // order, behind every tile row that needs no neighbour data, and wait for that neighbour's push of this step below
+    chunk = bid % P.nchunks;
+    const int t = bid / P.nchunks;
+    ty = P.tiles_y <= 2 ? t : (t < P.tiles_y - 2 ? t + 1 : (t == P.tiles_y - 2 ? 0 : P.tiles_y - 1));
+  } else {
+    ty = bid % P.tiles_y;
+    chunk = bid / P.tiles_y;
+  }
   const int i0 = 1 + 32 * tx, j0 = P.jy_lo + G::BR * ty;
   const int k0 = P.kz_lo + chunk * P.kchunk;
   const int k1 = min(k0 + P.kchunk - 1, P.kz_hi);
@@ -77,7 +86,22 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  bool gate_timed_out = false;
   if (tid == 0) {
+    if (P.gate && (ty == 0 || ty == P.tiles_y - 1)) {
+      // flags[0]: the low neighbour's push has landed in my south halo row, flags[1]: the high neighbour's in my north one
+      const long long t0 = clock64();
+      const bool need_lo = ty == 0, need_hi = ty == P.tiles_y - 1;
+      for (;;) {
+        long long flo = P.gate_step, fhi = P.gate_step;
+        if (need_lo) asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(flo) : "l"(P.gate) : "memory");
+        if (need_hi) asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(fhi) : "l"(P.gate + 1) : "memory");
+        if (flo >= P.gate_step && fhi >= P.gate_step) break;
+        if (clock64() - t0 > P.gate_timeout) { gate_timed_out = true; P.gate[2] = 1; break; }   // reported: flag word + NaN partials
+        __nanosleep(100);
+      }
+      asm volatile("fence.proxy.async;" ::: "memory");   // the rows were written through the generic proxy (peer stores); TMA reads them
+    }
     for (int n = n_first; n < n_first + NS && n <= n_last; ++n) issue(n);
   }
 
@@ -90,9 +114,13 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
   const bool lane_ok = i <= P.Nx;
   bool rlive[RY];
 #pragma unroll
-  for (int r = 0; r < RY; ++r) rlive[r] = j0 + jr0 + r <= P.jy_hi + 1;
+  // P.y_ring: the y window is a whole periodic extent, or one slab of a periodic ring of slabs.  Then every row's items
+  // carry the interior weights (the items of row jy_hi + 1 ARE those of the next slab's / the wrapped row jy_lo, whose
+  // boundary terms they cancel), so rows jy_lo .. jy_hi are all FAST rows and no block works on the extra row.
+  const bool ring = P.y_ring != 0;
+  for (int r = 0; r < RY; ++r) rlive[r] = j0 + jr0 + r <= P.jy_hi + (ring ? 0 : 1);
   // the whole warp is away from the window's y edges (rows jy_lo+1 .. jy_hi-1) in a full x tile: FAST steps
-  const bool tfast = xfull && j0 + jr0 >= P.jy_lo + 1 && j0 + jr0 + RY - 1 <= P.jy_hi - 1;
+  const bool tfast = xfull && (ring ? (j0 + jr0 + RY - 1 <= P.jy_hi) : (j0 + jr0 >= P.jy_lo + 1 && j0 + jr0 + RY - 1 <= P.jy_hi - 1));
 
   // pipeline state: the centre values of this plane and of the previous one in two register sets that swap roles from
   // step to step (the plane loop is unrolled by two, so nothing is copied), and the in-plane + lower-face part of the
@@ -193,8 +221,8 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
         } else if (lane_ok) {
           // ---- GEN: a window-edge row or plane (or a partly filled x tile): explicit class weights (all one elsewhere) ----
           const int j = j0 + jr0 + r;
-          const double al = (j >= P.jy_lo && j <= P.jy_hi) ? 1.0 : 0.0, be = (j - 1 >= P.jy_lo && j - 1 <= P.jy_hi) ? 1.0 : 0.0,
-                       an = (j + 1 >= P.jy_lo && j + 1 <= P.jy_hi) ? 1.0 : 0.0;
+          const double al = (ring || (j >= P.jy_lo && j <= P.jy_hi)) ? 1.0 : 0.0, be = (ring || (j - 1 >= P.jy_lo && j - 1 <= P.jy_hi)) ? 1.0 : 0.0,
+                       an = (ring || (j + 1 >= P.jy_lo && j + 1 <= P.jy_hi)) ? 1.0 : 0.0;
           const double hy = 0.5 * (al + be), hyn = 0.5 * (al + an);        // y faces / corner rows j and j+1: half their cell count
           const double hz = 0.5 * (g0 + g1), hzp = 0.5 * (g1 + g2);        // z faces n and n-1
           if (H_EPS) {
@@ -208,7 +236,7 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
             aAe = fma(P23, fma(rdy * hz, al * wc[r] - be * ws, rdz * hy * (g0 * vc[r] - g1 * vp[r])), aAe);
             aAx = fma(al * g0 * Uu, ax, aAx);
             aAy = fma(g0 * Vv, hyn * vn - hy * vc[r], aAy);
-            if (j == P.jy_lo) {                            // the flux cell south of the first window row, seen from face jy_lo only
+            if (!ring && j == P.jy_lo) {                   // the flux cell south of the first window row, seen from face jy_lo only
               const double vs = r ? vc[r > 0 ? r - 1 : 0] : vS;
               aAy = fma(g0 * ((vs + vc[r]) * (vs + vc[r])), 0.5 * vc[r], aAy);
             }
@@ -266,7 +294,8 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
       if (tid == 0) {
         double t = 0.0;
         for (int w = 0; w < NW; ++w) t += red[w];
-        P.partial[(size_t)blockIdx.x * P.nslots + P.o[d].slot] = t * P.V;
+        // a halo wait that gave up poisons this block's partials: the (all-reduced) integrals read NaN on every rank
+        P.partial[(size_t)blockIdx.x * P.nslots + P.o[d].slot] = gate_timed_out ? __longlong_as_double(0x7ff8000000000000LL) : t * P.V;
       }
     }
   }

@@ -25,6 +25,29 @@ int ocb_require_device();   // OCB_OK or OCB_ERR_CUDA ("no CUDA device": there i
 int ocb_sm_count();
 void ocb_keep_scratch_pool();   // make the stream-ordered scratch pool retain its memory between calls
 
+// Every entry point runs on the device that OWNS the caller's arrays, whatever the calling thread's current device is
+// (plan scratch, tables and launches would otherwise land on the current device next to another device's pointers and stream).
+// The guard switches to the owner of `p` (or to an explicit device index) and restores the previous device on scope exit.
+struct OcbDeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit OcbDeviceGuard(const void* p) {
+    if (!p) return;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return; }
+    if (a.type != cudaMemoryTypeDevice && a.type != cudaMemoryTypeManaged) return;
+    enter(a.device);
+  }
+  explicit OcbDeviceGuard(int device) { if (device >= 0) enter(device); }
+  void enter(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); return; }
+    if (device != prev && cudaSetDevice(device) == cudaSuccess) switched = true;
+  }
+  ~OcbDeviceGuard() { if (switched) cudaSetDevice(prev); }
+  OcbDeviceGuard(const OcbDeviceGuard&) = delete;
+  OcbDeviceGuard& operator=(const OcbDeviceGuard&) = delete;
+};
+
 // ---- device view of one operand ------------------------------------------------------------------------
 // p is pre-offset so that the 1-based (Oceananigans) index (i, j, k) lives at p[i*sx + j*sy + k*sz];
 // reduced axes have stride 0; ZeroField / Number operands have p == nullptr and value c.
@@ -86,3 +109,7 @@ static inline size_t ocb_sizeof(int dtype) { return dtype == OCB_F64 ? 8 : 4; }
 
 // deterministic two-stage reduction of per-block partial sums: partial[b * nslots + s] -> out[s]
 void ocb_launch_finalize_partials(const double* partial, int nblocks, int nslots, double* out, cudaStream_t st);
+// ... followed by the all-reduce over the ranks of a peer-memory ring (one kernel; ocb_api.cu)
+int ocb_launch_finalize_ring(const double* partial, int nblocks, int nslots, double* out, const ocb_ring* ring, long long step,
+                             long long timeout_cycles, cudaStream_t st);
+long long ocb_cycles(double seconds);   // SM clock cycles of the current device in `seconds` (spin-wait bounds)

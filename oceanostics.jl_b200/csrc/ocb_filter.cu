@@ -426,6 +426,7 @@ extern "C" int ocb_filter_execute(int32_t dtype, const ocb_field* src, const int
   }
   int rc = ocb_require_device();
   if (rc != OCB_OK) return rc;
+  OcbDeviceGuard device_guard(src->data);
   ocb_keep_scratch_pool();
   return dtype == OCB_F64 ? filter_impl<double>(src, src_extent, passes, n_pass, dst, window_lo, window_hi, (cudaStream_t)stream)
                           : filter_impl<float>(src, src_extent, passes, n_pass, dst, window_lo, window_hi, (cudaStream_t)stream);

@@ -61,6 +61,7 @@ extern "C" int ocb_fill_halo(const ocb_grid* grid, const ocb_field* field, int32
   OCB_REQUIRE(grid && field && field->data && field->kind == OCB_FIELD_ARRAY, "ocb_fill_halo: needs an array field");
   int rc = ocb_require_device();
   if (rc != OCB_OK) return rc;
+  OcbDeviceGuard device_guard(field->data);
   // gradient BCs need Δzᶠ at the two boundary faces: uniform spacing, or (stretched) the host passes the
   // already-multiplied increments by using a uniform-equivalent d[2]; here only the uniform case reads d[2].
   double dz_bot = grid->d[2], dz_top = grid->d[2];
@@ -172,6 +173,7 @@ extern "C" int ocb_pointwise(const ocb_grid* grid, int32_t op, double alpha, con
   OCB_REQUIRE(op >= OCB_OP_COPY && op <= OCB_OP_MUL, "ocb_pointwise: unknown op %d", op);
   int rc = ocb_require_device();
   if (rc != OCB_OK) return rc;
+  OcbDeviceGuard device_guard(dst->data);
   cudaStream_t st = (cudaStream_t)stream;
   return grid->dtype == OCB_F64 ? pointwise_impl<double>(grid, op, alpha, a, b, dst, st)
                                 : pointwise_impl<float>(grid, op, alpha, a, b, dst, st);
@@ -215,6 +217,7 @@ extern "C" int ocb_halo_pack_y(int32_t dtype, const ocb_field* field, int32_t si
   OCB_REQUIRE(field && field->data && buffer && (side == 0 || side == 1), "ocb_halo_pack_y: bad argument");
   int rc = ocb_require_device();
   if (rc != OCB_OK) return rc;
+  OcbDeviceGuard device_guard(field->data);
   return dtype == OCB_F64 ? pack_impl<double>(field, side, h, buffer, true, (cudaStream_t)stream)
                           : pack_impl<float>(field, side, h, buffer, true, (cudaStream_t)stream);
 }
@@ -223,6 +226,7 @@ extern "C" int ocb_halo_unpack_y(int32_t dtype, const ocb_field* field, int32_t 
   OCB_REQUIRE(field && field->data && buffer && (side == 0 || side == 1), "ocb_halo_unpack_y: bad argument");
   int rc = ocb_require_device();
   if (rc != OCB_OK) return rc;
+  OcbDeviceGuard device_guard(field->data);
   return dtype == OCB_F64 ? pack_impl<double>(field, side, h, (void*)buffer, false, (cudaStream_t)stream)
                           : pack_impl<float>(field, side, h, (void*)buffer, false, (cudaStream_t)stream);
 }
@@ -296,6 +300,7 @@ extern "C" int ocb_halo_pack_y_many(int32_t dtype, const ocb_field* fields, int3
   OCB_REQUIRE(dtype == OCB_F32 || dtype == OCB_F64, "bad dtype");
   int rc = ocb_require_device();
   if (rc != OCB_OK) return rc;
+  OcbDeviceGuard device_guard(fields[0].data);
   return dtype == OCB_F64 ? pack_many_impl<double>(fields, n_fields, h, buffers, unpack == 0, (cudaStream_t)stream)
                           : pack_many_impl<float>(fields, n_fields, h, buffers, unpack == 0, (cudaStream_t)stream);
 }
@@ -355,29 +360,47 @@ struct PushMany {
   int nx[OCB_PACK_MAX_FIELDS], nz[OCB_PACK_MAX_FIELDS], js[2 * OCB_PACK_MAX_FIELDS], jd[2 * OCB_PACK_MAX_FIELDS];
   int h;
 };
-// whole parent rows (x halos included) are contiguous: thread t copies element x of row (p, z)
-template <class T>
-__global__ void __launch_bounds__(256) ocb_push_y_many_kernel(const __grid_constant__ PushMany<T> P) {
+// The h edge rows of one z plane are h * nx CONTIGUOUS elements (whole parent rows, x halos included), in the source and in
+// the neighbour's array alike: the kernel copies them as 16-byte vectors when both runs are 16-byte aligned (VEC), one
+// (field, side) pair per blockIdx.y, planes and vectors flattened over blockIdx.x.  The last block to finish (a device
+// counter) publishes the step number in the two neighbours' flag words behind a system-scope fence, so the exchange is one
+// launch.  (The counter is one per device: pushes of one device are stream-ordered by their caller.)
+__device__ unsigned int ocb_push_done_counter = 0;
+template <class T, bool VEC>
+__global__ void __launch_bounds__(256) ocb_push_y_many_kernel(const __grid_constant__ PushMany<T> P, long long* lo_flag, long long* hi_flag,
+                                                              long long step) {
   const int q = blockIdx.y, f = q >> 1;
-  const int nx = P.nx[f], h = P.h;
-  const long long total = (long long)nx * h * P.nz[f];
-  const T* __restrict__ src = P.src[f];
-  T* __restrict__ dst = P.dst[q];
-  const long long sy = P.sy[f], sz = P.sz[f], dsz = P.dsz[q];
-  const int js = P.js[q], jd = P.jd[q];
+  constexpr int EPV = VEC ? (int)(16 / sizeof(T)) : 1;          // elements per vector
+  const int run = P.nx[f] * P.h / EPV;                          // vectors per plane
+  const long long total = (long long)run * P.nz[f];
+  const T* __restrict__ src = P.src[f] + (long long)P.js[q] * P.sy[f];
+  T* __restrict__ dst = P.dst[q] + (long long)P.jd[q] * P.sy[f];
+  const long long sz = P.sz[f], dsz = P.dsz[q];
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(t % nx);
-    const int p = (int)((t / nx) % h);
-    const int z = (int)(t / ((long long)nx * h));
-    dst[x + (long long)(jd + p) * sy + z * dsz] = src[x + (long long)(js + p) * sy + z * sz];
+    const int z = (int)(t / run);
+    const int e = (int)(t - (long long)z * run);
+    if (VEC) {
+      const int4 v = *reinterpret_cast<const int4*>(src + z * sz + (long long)e * EPV);
+      *reinterpret_cast<int4*>(dst + z * dsz + (long long)e * EPV) = v;
+    } else {
+      dst[z * dsz + e] = src[z * sz + e];
+    }
   }
-}
-
-__global__ void ocb_signal_kernel(long long* lo_flag, long long* hi_flag, long long step) {
+  // ---- publish: the last block of the grid, after every block's stores are visible system-wide ----------------------
+  __shared__ bool last;
   __threadfence_system();
-  *(volatile long long*)lo_flag = step;
-  *(volatile long long*)hi_flag = step;
-  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int nb = gridDim.x * gridDim.y;
+    last = atomicAdd(&ocb_push_done_counter, 1u) == nb - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    ocb_push_done_counter = 0;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(lo_flag), "l"(step) : "memory");
+    asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(hi_flag), "l"(step) : "memory");
+  }
 }
 
 // flags[0]: written by the low neighbour, flags[1]: by the high neighbour, flags[2]: set to 1 if the wait timed out
@@ -392,7 +415,8 @@ __global__ void ocb_wait_kernel(long long* flags, long long step, long long time
 }
 
 template <class T>
-static int push_many_impl(const ocb_field* fields, int n, int h, void* const* peer, const int32_t* peer_ny, cudaStream_t st) {
+static int push_many_impl(const ocb_field* fields, int n, int h, void* const* peer, const int32_t* peer_ny, void* lo_flag, void* hi_flag,
+                          long long step, cudaStream_t st) {
   PushMany<T> P;
   memset(&P, 0, sizeof(P));
   P.h = h;
@@ -417,10 +441,24 @@ static int push_many_impl(const ocb_field* fields, int n, int h, void* const* pe
     const long long total = (long long)F.size[0] * h * F.size[2];
     if (total > most) most = total;
   }
-  long long bx = (most + 255) / 256;
-  if (bx > 4096) bx = 4096;
+  // 16-byte vectors when every run starts on a 16-byte boundary in both arrays
+  constexpr int EPV = (int)(16 / sizeof(T));
+  bool vec = true;
+  for (int f = 0; f < n && vec; ++f) {
+    const ocb_field& F = fields[f];
+    if (((long long)F.size[0] * h) % EPV || F.stride[1] % EPV || F.stride[2] % EPV || ((uintptr_t)F.data & 15)) vec = false;
+    for (int side = 0; side < 2 && vec; ++side)
+      if (((uintptr_t)peer[2 * f + side] & 15) || P.dsz[2 * f + side] % EPV) vec = false;
+  }
+  // enough blocks to keep NVLink busy from a few SMs' worth of slots next to the sweep's blocks, few enough to retire early
+  long long bx = (most / (vec ? EPV : 1) + 255) / 256;
+  const long long cap = vec ? 96 : 1024;
+  if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
-  ocb_push_y_many_kernel<T><<<dim3((unsigned)bx, (unsigned)(2 * n), 1), 256, 0, st>>>(P);
+  if (const char* e = getenv("OCB_PUSH_BLOCKS")) { if (atoi(e) > 0) bx = atoi(e); }
+  const dim3 grid((unsigned)bx, (unsigned)(2 * n), 1);
+  if (vec) ocb_push_y_many_kernel<T, true><<<grid, 256, 0, st>>>(P, (long long*)lo_flag, (long long*)hi_flag, step);
+  else ocb_push_y_many_kernel<T, false><<<grid, 256, 0, st>>>(P, (long long*)lo_flag, (long long*)hi_flag, step);
   OCB_CUDA(cudaGetLastError());
   return OCB_OK;
 }
@@ -432,22 +470,21 @@ extern "C" int ocb_halo_push_y_many(int32_t dtype, const ocb_field* fields, int3
   OCB_REQUIRE(dtype == OCB_F32 || dtype == OCB_F64, "bad dtype");
   int rc = ocb_require_device();
   if (rc != OCB_OK) return rc;
-  rc = dtype == OCB_F64 ? push_many_impl<double>(fields, n_fields, h, peer_arrays, peer_ny, (cudaStream_t)stream)
-                        : push_many_impl<float>(fields, n_fields, h, peer_arrays, peer_ny, (cudaStream_t)stream);
-  if (rc != OCB_OK) return rc;
-  ocb_signal_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((long long*)lo_flag, (long long*)hi_flag, (long long)step);
-  OCB_CUDA(cudaGetLastError());
-  return OCB_OK;
+  OcbDeviceGuard device_guard(fields[0].data);
+  return dtype == OCB_F64 ? push_many_impl<double>(fields, n_fields, h, peer_arrays, peer_ny, lo_flag, hi_flag, (long long)step, (cudaStream_t)stream)
+                          : push_many_impl<float>(fields, n_fields, h, peer_arrays, peer_ny, lo_flag, hi_flag, (long long)step, (cudaStream_t)stream);
 }
 
 extern "C" int ocb_halo_wait(void* flags, int64_t step, double timeout_seconds, void* stream) {
   OCB_REQUIRE(flags && timeout_seconds > 0, "ocb_halo_wait: bad argument");
   int rc = ocb_require_device();
   if (rc != OCB_OK) return rc;
+  OcbDeviceGuard device_guard(flags);
   int dev = 0, khz = 0;
   OCB_CUDA(cudaGetDevice(&dev));
   OCB_CUDA(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev));
-  ocb_wait_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((long long*)flags, (long long)step, (long long)(timeout_seconds * 1e3 * (double)khz));
+  (void)khz;
+  ocb_wait_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((long long*)flags, (long long)step, ocb_cycles(timeout_seconds));
   OCB_CUDA(cudaGetLastError());
   return OCB_OK;
 }

@@ -117,6 +117,7 @@ struct ocb_plan {
   int nblocks, fused_blocks, strain_blocks, generic_blocks, nslots;
   int n_launches;
   double algorithmic_bytes;
+  int device;             // the device that owns the operands: every call of this plan runs there
   ocb_fused_plan* fused;
   ocb_strain_plan* strain;
 };
@@ -314,9 +315,17 @@ extern "C" int ocb_plan_create(const ocb_grid* grid, const ocb_sweep_inputs* inp
   OCB_REQUIRE(grid->dtype == OCB_F32 || grid->dtype == OCB_F64, "grid dtype must be OCB_F32 or OCB_F64");
   int rc = ocb_require_device();
   if (rc != OCB_OK) return rc;
+  // the device of the first array operand (or output) is the plan's device
+  const void* owner = nullptr;
+  const ocb_field* ops[] = {&inputs->u, &inputs->v, &inputs->w, &inputs->b, &inputs->p, &inputs->U, &inputs->V, &inputs->W, &inputs->B};
+  for (const ocb_field* f : ops) if (!owner && f->kind == OCB_FIELD_ARRAY && f->data) owner = f->data;
+  for (int a = 0; a < OCB_N_AUX && !owner; ++a) if (inputs->aux[a].kind == OCB_FIELD_ARRAY && inputs->aux[a].data) owner = inputs->aux[a].data;
+  for (int r = 0; r < n_requests && !owner; ++r) owner = requests[r].out;
+  OcbDeviceGuard device_guard(owner);
   ocb_plan* pl = new (std::nothrow) ocb_plan();
   if (!pl) OCB_FAIL(OCB_ERR_ALLOC, "out of host memory");
   memset((void*)pl, 0, sizeof(*pl));
+  OCB_CUDA(cudaGetDevice(&pl->device));
   pl->dtype = grid->dtype;
   pl->algorithmic_bytes = count_algorithmic_bytes(grid, inputs, requests, n_requests);
   rc = (grid->dtype == OCB_F64) ? finish_plan<double>(pl, grid, inputs, requests, n_requests, &pl->p64)
@@ -328,6 +337,7 @@ extern "C" int ocb_plan_create(const ocb_grid* grid, const ocb_sweep_inputs* inp
 
 extern "C" int ocb_plan_execute(ocb_plan* pl, double* integrals, void* stream) {
   OCB_REQUIRE(pl, "ocb_plan_execute: null plan");
+  OcbDeviceGuard device_guard(pl->device);
   cudaStream_t st = (cudaStream_t)stream;
   const int nslots = pl->nslots;
   OCB_REQUIRE(nslots == 0 || integrals, "this plan integrates %d slot(s): `integrals` must be a device double[%d]", nslots, nslots);
@@ -351,8 +361,34 @@ extern "C" int ocb_plan_execute(ocb_plan* pl, double* integrals, void* stream) {
   return OCB_OK;
 }
 
+static bool plan_ring_capable(const ocb_plan* pl) {
+  return pl && pl->fused && !pl->strain && pl->generic_blocks == 0 && pl->nslots > 0 && ocb_fused_ring_capable(pl->fused);
+}
+
+extern "C" int ocb_plan_ring_capable(const ocb_plan* pl) { return plan_ring_capable(pl) ? 1 : 0; }
+
+// One slab's step of a peer-memory ring: the class-sum sweep with its edge tile rows gated on the neighbours' pushes, then
+// the per-block partials summed and all-reduced over the ranks' sync blocks (include/oceanostics_b200.h).
+extern "C" int ocb_plan_execute_ring(ocb_plan* pl, double* integrals, const ocb_ring* ring, int64_t step, void* stream) {
+  OCB_REQUIRE(pl && integrals && ring, "ocb_plan_execute_ring: null argument");
+  OCB_REQUIRE(ring->nranks >= 1 && ring->nranks <= OCB_MAX_RANKS && ring->rank >= 0 && ring->rank < ring->nranks,
+              "ocb_plan_execute_ring: rank %d of %d (at most %d ranks)", ring->rank, ring->nranks, OCB_MAX_RANKS);
+  OCB_REQUIRE(step >= 1 && ring->timeout_seconds > 0, "ocb_plan_execute_ring: step must be >= 1 and the timeout positive");
+  for (int r = 0; r < ring->nranks; ++r) OCB_REQUIRE(ring->sync[r], "ocb_plan_execute_ring: sync block of rank %d is not mapped", r);
+  if (!plan_ring_capable(pl))
+    OCB_FAIL(OCB_ERR_UNSUPPORTED, "ocb_plan_execute_ring takes integral-only plans of the class-sum budget kernel over the whole y "
+                                  "extent of a y-periodic slab; run the exchange, ocb_plan_execute and an all-reduce instead");
+  OcbDeviceGuard device_guard(pl->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long cycles = ocb_cycles(ring->timeout_seconds);
+  int rc = ocb_fused_execute_gated(pl->fused, pl->partial, (long long*)ring->sync[ring->rank], (long long)step, cycles, st);
+  if (rc != OCB_OK) return rc;
+  return ocb_launch_finalize_ring(pl->partial, pl->nblocks, pl->nslots, integrals, ring, (long long)step, cycles, st);
+}
+
 extern "C" int ocb_plan_destroy(ocb_plan* pl) {
   if (!pl) return OCB_OK;
+  OcbDeviceGuard device_guard(pl->device);
   if (pl->fused) ocb_fused_destroy(pl->fused);
   if (pl->strain) ocb_strain_destroy(pl->strain);
   if (pl->ztab) cudaFree(pl->ztab);

@@ -59,6 +59,12 @@ struct FusedParams {
   int eps_pert;
   double f[3];                     // Coriolis vector of the potential-vorticity term
   int epv_top;                     // 1: the fff window also holds the top face Nz+1 (Bounded z)
+  // class-sum kernel only.  y_ring: the y window is a whole periodic extent / one slab of a periodic ring (interior item
+  // weights on every row).  gate: this rank's halo flag words {from low, from high, timed out} -- the first and last tile
+  // rows wait until they reach gate_step (ocb_plan_execute_ring); nullptr: no waiting.
+  int y_ring;
+  long long* gate;
+  long long gate_step, gate_timeout;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -847,8 +853,11 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
   P.jy_lo = SP.req[0].lo[1]; P.jy_hi = SP.req[0].hi[1];
   P.tiles_y = ((P.jy_hi - P.jy_lo + 1) + sh + BR - 2) / (BR - 1);
   if (fp->sums) {                                              // disjoint 32 x BR tiles over rows jy_lo .. jy_hi + 1
+    // (.. jy_hi when the window is the whole periodic y extent, or a slab whose halo rows hold the ring neighbours' rows:
+    //  the items of row jy_hi + 1 are then row jy_lo's of the wrapped domain / next slab and are counted there)
+    P.y_ring = (grid->topo[1] == OCB_PERIODIC && P.jy_lo == 1 && P.jy_hi == grid->N[1] && !getenv("OCB_SUMS_NO_RING")) ? 1 : 0;
     P.tiles_x = (P.Nx + 31) / 32;
-    P.tiles_y = (njy + 1 + BR - 1) / BR;
+    P.tiles_y = (njy + (P.y_ring ? 0 : 1) + BR - 1) / BR;
   }
   const int tiles = P.tiles_x * P.tiles_y;
   P.kz_lo = cell_req >= 0 ? SP.req[cell_req].lo[2] : 1;
@@ -899,6 +908,16 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
 }
 
 int ocb_fused_nblocks(const ocb_fused_plan* fp) { return fp->nblocks; }
+
+bool ocb_fused_ring_capable(const ocb_fused_plan* fp) { return fp->sums && fp->P.y_ring; }
+
+int ocb_fused_execute_gated(ocb_fused_plan* fp, double* partial, long long* flags, long long step, long long timeout_cycles, cudaStream_t st) {
+  OCB_REQUIRE(ocb_fused_ring_capable(fp), "gated execution needs the class-sum kernel over a whole periodic y extent");
+  fp->P.gate = flags; fp->P.gate_step = step; fp->P.gate_timeout = timeout_cycles;
+  const int rc = ocb_fused_execute(fp, partial, st);
+  fp->P.gate = nullptr;
+  return rc;
+}
 
 int ocb_fused_execute(ocb_fused_plan* fp, double* partial, cudaStream_t st) {
   fp->P.partial = partial;

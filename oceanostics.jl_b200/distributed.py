@@ -17,6 +17,26 @@ from . import _lib
 from .fields import current_stream_ptr
 
 
+_IPC_MAPPED = {}     # (device index, 64-byte handle) -> mapped base address: a handle is opened once per process
+
+
+def _ipc_export(tensor):
+    handle, off = (C.c_ubyte * 64)(), C.c_int64()
+    with torch.cuda.device(tensor.device):
+        _lib.check(_lib.lib().ocb_ipc_export(tensor.data_ptr(), handle, C.byref(off)))
+    return bytes(handle), off.value
+
+
+def _ipc_map(device, handle, offset):
+    key = (torch.device(device).index, handle)
+    if key not in _IPC_MAPPED:
+        base = C.c_void_p()
+        with torch.cuda.device(device):
+            _lib.check(_lib.lib().ocb_ipc_import((C.c_ubyte * 64)(*handle), C.byref(base)))
+        _IPC_MAPPED[key] = base.value
+    return _IPC_MAPPED[key] + offset
+
+
 def slab_range(n_global, rank, world):
     """1-based inclusive global y range owned by `rank` (even split; the remainder goes to the low ranks)."""
     base, rem = divmod(n_global, world)
@@ -112,7 +132,7 @@ class PeerSlabExchanger:
     wait for both neighbours' pushes of the current step.  Ordering contract (include/oceanostics_b200.h): the next push must
     follow a collective that every rank enters after it has read its halos (here: the all-reduce of the integrals)."""
 
-    def __init__(self, grid, fields, depth=2, rank=None, world=None, group=None, timeout=10.0):
+    def __init__(self, grid, fields, depth=2, rank=None, world=None, group=None, timeout=10.0, ring=None):
         self.grid, self.fields, self.h, self.group, self.timeout = grid, list(fields), int(depth), group, float(timeout)
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world = dist.get_world_size(group) if world is None else world
@@ -124,32 +144,20 @@ class PeerSlabExchanger:
         if dev.type != "cuda":
             raise _lib.OcbError("the peer-memory exchange needs CUDA devices (no CPU fallback)")
         self.lo_rank, self.hi_rank = (self.rank - 1) % self.world, (self.rank + 1) % self.world
-        self.flags = torch.zeros(4, dtype=torch.int64, device=dev)   # [from low, from high, timed out, unused]
+        # [from low, from high, timed out, unused]: the first words of the ring's sync block when the exchange is part of one
+        self.ring = ring
+        self.flags = ring.flags if ring is not None else torch.zeros(4, dtype=torch.int64, device=dev)
         self.step_no = 0
-        self._opened = {}
-        L = _lib.lib()
         ny = int(grid.N[1])
         if self.world == 1:
             peers = {self.rank: {"fields": [(f.data.data_ptr(), ny) for f in self.fields], "flags": self.flags.data_ptr()}}
         else:
             torch.cuda.synchronize(dev)
-
-            def export(t):
-                handle, off = (C.c_ubyte * 64)(), C.c_int64()
-                _lib.check(L.ocb_ipc_export(t.data_ptr(), handle, C.byref(off)))
-                return bytes(handle), off.value
-            mine = {"fields": [export(f.data) + (ny,) for f in self.fields], "flags": export(self.flags)}
+            mine = {"fields": [_ipc_export(f.data) + (ny,) for f in self.fields], "flags": _ipc_export(self.flags)}
             everyone = [None] * self.world
             dist.all_gather_object(everyone, mine, group=group)
-
-            def mapped(r, handle, off):
-                if (r, handle) not in self._opened:
-                    base = C.c_void_p()
-                    _lib.check(L.ocb_ipc_import((C.c_ubyte * 64)(*handle), C.byref(base)))
-                    self._opened[(r, handle)] = base.value
-                return self._opened[(r, handle)] + off
-            peers = {r: {"fields": [(mapped(r, hd, off), n) for hd, off, n in everyone[r]["fields"]],
-                         "flags": mapped(r, *everyone[r]["flags"])} for r in {self.lo_rank, self.hi_rank}}
+            peers = {r: {"fields": [(_ipc_map(dev, hd, off), n) for hd, off, n in everyone[r]["fields"]],
+                         "flags": _ipc_map(dev, *everyone[r]["flags"])} for r in {self.lo_rank, self.hi_rank}}
             dist.barrier(group=group)
         lo, hi = peers[self.lo_rank], peers[self.hi_rank]
         nf = len(self.fields)
@@ -171,16 +179,57 @@ class PeerSlabExchanger:
     def exchange(self):
         self.push()
         self.wait()
+        self._unchecked = getattr(self, "_unchecked", 0) + 1
+        if self._unchecked >= 64:          # a wait that gave up must not go unnoticed for long (one sync per 64 exchanges)
+            self.check()
 
     def check(self):
-        """After a device synchronize: raise if a wait gave up (a neighbour never pushed)."""
+        """Raise if a wait gave up (a neighbour never pushed).  Synchronises the device."""
+        self._unchecked = 0
         if int(self.flags[2].item()) != 0:
             raise _lib.OcbError("halo exchange: a neighbour's rows did not arrive within the timeout")
 
     def close(self):
-        for base in self._opened.values():
-            _lib.lib().ocb_ipc_close(base)
-        self._opened = {}
+        pass      # mappings are process-wide (_IPC_MAPPED) and live until the process exits
+
+
+class PeerRing:
+    """The sync blocks of a peer-memory ring (`ocb_ring`, include/oceanostics_b200.h): every rank owns one zeroed device
+    block of OCB_RING_SYNC_WORDS 64-bit words -- halo flags, timeout word, and the mailboxes of the integral all-reduce -- and
+    maps every other rank's over CUDA IPC.  torch.distributed only carries the 64-byte handles at set-up."""
+
+    def __init__(self, device, rank=None, world=None, group=None, timeout=10.0):
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        if self.world > _lib.OCB_MAX_RANKS:
+            raise ValueError(f"a peer ring holds at most {_lib.OCB_MAX_RANKS} ranks")
+        if torch.device(device).type != "cuda":
+            raise _lib.OcbError("the peer-memory ring needs CUDA devices (no CPU fallback)")
+        self.device, self.group, self.timeout = torch.device(device), group, float(timeout)
+        self.block = torch.zeros(_lib.OCB_RING_SYNC_WORDS, dtype=torch.int64, device=self.device)
+        ptrs = [None] * self.world
+        ptrs[self.rank] = self.block.data_ptr()
+        if self.world > 1:
+            torch.cuda.synchronize(self.device)
+            everyone = [None] * self.world
+            dist.all_gather_object(everyone, _ipc_export(self.block), group=group)
+            for r, (hd, o) in enumerate(everyone):
+                if r != self.rank:
+                    ptrs[r] = _ipc_map(self.device, hd, o)
+            dist.barrier(group=group)
+        self.ptrs = ptrs
+        self.desc = _lib.ocb_ring()
+        self.desc.rank, self.desc.nranks, self.desc.timeout_seconds = self.rank, self.world, self.timeout
+        for r in range(self.world):
+            self.desc.sync[r] = ptrs[r]
+
+    @property
+    def flags(self):
+        """words 0..3 of the own block: halo flag from the low / high neighbour, timed-out word, spare"""
+        return self.block[:4]
+
+    def timed_out(self):
+        return int(self.block[2].item()) != 0
 
 
 def allreduce_integrals(integrals: torch.Tensor, group=None):
@@ -243,12 +292,73 @@ class OverlappedSlabBudget:
         self.total.add_(self.high.plan.integrals[:self.n])
         allreduce_integrals(self.total, self.group)
         mark("end", cur)
+        if self.transport == "peer":
+            self._unchecked = getattr(self, "_unchecked", 0) + 1
+            if self._unchecked >= 64:      # a halo wait that gave up must not go unnoticed (one sync per 64 steps)
+                self._unchecked = 0
+                self.exchanger.check()
         return self.total
 
     @staticmethod
     def timeline_ms(timeline):
         """Milliseconds from the start of a step recorded with `step(timeline=...)` (after a device synchronize)."""
         return {k: round(timeline["start"].elapsed_time(v), 4) for k, v in timeline.items() if k != "start"}
+
+
+class RingSlabBudget:
+    """One slab's fused budget step over a peer-memory ring: THREE launches and no NCCL on the data path.
+
+      1. `ocb_halo_push_y_many` (side stream, high priority): ONE row of every input field stored straight into each ring
+         neighbour's halo row over NVLink, the step number published behind it.  One row is all the class-sum kernel reads
+         beyond its slab (its advection term is summed by parts), half of what the cell-exact kernels need.
+      2. the class-sum sweep over the whole slab: the tile rows that read a halo row are last in launch order and wait in the
+         kernel for the neighbour's flag, so every other row overlaps the exchange.
+      3. one block sums the per-block partials, stores them into every rank's sync block and adds all ranks' in rank order.
+
+    `step()` returns the device vector of GLOBAL integrals (bit-identical on every rank).  A wait that gives up (a neighbour
+    that never pushed) turns the integrals into NaN on every rank and sets the ring's timed-out word: never a hang, never a
+    silently stale halo."""
+
+    def __init__(self, grid, fields, make_ops, rank=None, world=None, group=None, timeout=10.0):
+        from .operations import FusedDiagnostics, Integral
+        self.grid, self.group = grid, group
+        self.ring = PeerRing(grid.device, rank=rank, world=world, group=group, timeout=timeout)
+        self.exchanger = PeerSlabExchanger(grid, fields, depth=1, rank=self.ring.rank, world=self.ring.world, group=group,
+                                           timeout=timeout, ring=self.ring)
+        self.diag = FusedDiagnostics(*[Integral(o) for o in make_ops()])
+        self.plan = self.diag.plan
+        if not self.plan.ring_capable:
+            raise _lib.OcbError("these diagnostics do not run on the class-sum kernel over a whole y-periodic slab: use "
+                                "OverlappedSlabBudget (exchange + sweep + all-reduce) instead")
+        self.n = self.plan.n_slots
+        self.total = self.plan.integrals[:self.n]
+        # slabs of one or two tile rows have no row to hide the exchange behind: push on the compute stream, then sweep
+        self.serial = grid.N[1] < 48
+        self.comm_stream = torch.cuda.Stream(device=grid.device, priority=-1)
+
+    def step(self, timeline=None):
+        cur = torch.cuda.current_stream(self.grid.device)
+        mark = (lambda name, stream: None) if timeline is None else (
+            lambda name, stream: timeline.setdefault(name, torch.cuda.Event(enable_timing=True)).record(stream))
+        mark("start", cur)
+        if self.serial:
+            self.exchanger.push()
+            mark("exchange_end", cur)
+        else:
+            # the push of this step follows the previous step's reduction (every rank has read its halo rows by then)
+            self.comm_stream.wait_stream(cur)
+            with torch.cuda.stream(self.comm_stream):
+                self.exchanger.push()
+                mark("exchange_end", self.comm_stream)
+        self.plan.execute_ring(self.ring, self.exchanger.step_no)
+        mark("end", cur)
+        return self.total
+
+    def check(self):
+        if self.ring.timed_out():
+            raise _lib.OcbError("ring step: a neighbour's rows or partial integrals did not arrive within the timeout")
+
+    timeline_ms = staticmethod(lambda timeline: {k: round(timeline["start"].elapsed_time(v), 4) for k, v in timeline.items() if k != "start"})
 
 
 def _axis_spec(grid, d):

@@ -269,6 +269,18 @@ class SweepPlan:
     def execute(self):
         _lib.check(_lib.lib().ocb_plan_execute(self.handle, self.integrals.data_ptr(), current_stream_ptr(self.grid.device)))
 
+    @property
+    def ring_capable(self):
+        """True when `execute_ring` accepts this plan (integral-only class-sum sweep over a whole y-periodic slab)."""
+        return bool(_lib.lib().ocb_plan_ring_capable(self.handle))
+
+    def execute_ring(self, ring, step):
+        """One slab's step of a peer-memory ring (`ocb_plan_execute_ring`): the sweep with its edge tile rows waiting for
+        the neighbours' pushes of `step`, then the integrals summed over the ranks -- `self.integrals` holds the GLOBAL sums."""
+        with torch.cuda.device(self.grid.device):
+            _lib.check(_lib.lib().ocb_plan_execute_ring(self.handle, self.integrals.data_ptr(), C.byref(ring.desc), int(step),
+                                                        current_stream_ptr(self.grid.device)))
+
     def __del__(self):
         try:
             if getattr(self, "handle", None):
@@ -346,9 +358,15 @@ def compute(field, time=None):
     return field
 
 
+def _up_to_date(status_time, time):
+    """Oceananigans' `compute_at!` rule: recompute when `time == zero(time) || time != status.time` -- so always at t = 0
+    (fields set after a first evaluation at t = 0 must not leave stale diagnostics) and whenever no time is given."""
+    return time is not None and time != 0 and status_time is not None and status_time == time
+
+
 def compute_at(field, time):
-    """`compute_at!`: recompute only when the status time differs."""
-    if time is not None and getattr(field, "status_time", None) == time:
+    """`compute_at!`: recompute unless the status time says the field is current (never skipped at t = 0)."""
+    if _up_to_date(getattr(field, "status_time", None), time):
         return field
     return compute(field, time)
 
@@ -386,7 +404,7 @@ class FusedDiagnostics:
         self._computed_once = False
 
     def compute(self, time=None):
-        if time is not None and self._computed_once and self.status_time == time:
+        if self._computed_once and _up_to_date(self.status_time, time):
             return self
         _refresh_arguments(self.plan.operands, time)
         self.plan.execute()

@@ -212,3 +212,5 @@ double ob_integral(const ob_state* S, int diag) {
 }
 
 int ob_num_threads(void) { return omp_get_max_threads(); }
+/* torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm of the bench asks for the host's cores explicitly */
+void ob_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }

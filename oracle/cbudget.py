@@ -36,6 +36,7 @@ def lib():
         _lib.ob_field.restype = C.c_int
         _lib.ob_field.argtypes = [C.POINTER(ob_state), C.c_int, C.c_void_p]
         _lib.ob_num_threads.restype = C.c_int
+        _lib.ob_set_num_threads.argtypes = [C.c_int]
     return _lib
 
 

@@ -187,11 +187,16 @@ def assert_close(got, want, rtol, what="", scale=None):
 
 
 def smoke_check(device="cuda:0"):
-    """__graft_entry__.smoke(): ε and Ri fields + four budget integrals on a 32x24x16 state vs the oracle."""
+    """__graft_entry__.smoke(): one small invocation of each kernel family of the hot path on `device`, each checked against
+    the oracle -- (1) field-writing budget kernel + generic kernel (eps, Ri fields and integrals), (2) the class-sum kernel
+    (integrals-only budget plan) and its ring step, (3) the velocity-gradient kernel (eddy-viscosity closure, eps + |S|),
+    (4) a 3-pass Gaussian filter, (5) the sort-based reference height."""
+    from cases import check_case, integral_scale      # conditioning-aware for the Richardson number
     st = State(size=(32, 24, 16), device=device)
     oc, pc = st.closures()["scalar"]
     m = st.model(closure=pc)
     KE, FD, TV = ocb.KineticEnergyEquation, ocb.FlowDiagnostics, ocb.TracerVarianceEquation
+    # ---- (1) fields + integrals: ocb_budget_kernel (OUT) and the generic kernel -------------------------------------
     ops = [KE.DissipationRate(m), FD.RichardsonNumber(m), KE.KineticEnergy(m), KE.KineticEnergyAdvection(m),
            KE.KineticEnergyPressureRedistribution(m), TV.TracerVarianceDissipationRate(m, "b")]
     vals, ints = run_ops(ops, st.pg, integrals=True, backend="cuda")
@@ -204,13 +209,43 @@ def smoke_check(device="cuda:0"):
             K.evaluate(K.ke_pressure_ccc, og, "ccc", f, st.op),
             K.evaluate(K.tracer_variance_dissipation_rate_ccc, og, "ccc", oc, None, None, st.ob)]
     locs = ["ccc", "ccf", "ccc", "ccc", "ccc", "ccc"]
-    from cases import check_case      # conditioning-aware for the Richardson number
     for g, w_, loc, op in zip(vals, want, locs, ops):
         check_case(st, op.name, g, w_, 1e-12)
     for g, w_, loc, op in zip(ints, want, locs, ops):
         if op.name == "RichardsonNumber":
             continue
-        ref = K.integral(w_, og, loc)
-        i_, j_, k_ = og.indices(loc)
-        scale = float(np.sum(np.abs(w_) * og.V(loc, i_, j_, k_)))
-        assert abs(g - ref) <= 1e-12 * scale, (op.name, g, ref)
+        assert abs(g - K.integral(w_, og, loc)) <= 1e-12 * integral_scale(og, w_, loc), (op.name, g)
+    # ---- (2) integrals only: ocb_budget_sums_kernel, plain and as a one-rank ring step --------------------------------
+    bops = [KE.KineticEnergy(m), KE.KineticEnergyAdvection(m), KE.KineticEnergyPressureRedistribution(m), KE.PotentialEnergyConversion(m),
+            KE.DissipationRate(m), TV.TracerVarianceDissipationRate(m, "b"), TV.TracerVarianceDiffusion(m, "b")]
+    bwant = [want[2], want[3], want[4], K.evaluate(K.ke_buoyancy_ccc, og, "ccc", f, (0, 0, 1), st.ob), want[0], want[5],
+             K.evaluate(K.c_div_q_c, og, "ccc", oc, None, None, st.ob)]
+    grp = ocb.FusedDiagnostics(*[ocb.Integral(o) for o in bops]).compute()
+    assert grp.plan.variant == 1 and grp.plan.ring_capable
+    from oceanostics_b200.distributed import RingSlabBudget
+    ring = RingSlabBudget(st.pg, [st.u, st.v, st.w, st.b, st.p], lambda: bops, rank=0, world=1, timeout=5.0)
+    ring_ints = ring.step().tolist()
+    ring.check()
+    for o, w_, a, b in zip(bops, bwant, grp.integrals(), ring_ints):
+        ref, sc = K.integral(w_, og, "ccc"), integral_scale(og, w_, "ccc")
+        assert abs(a - ref) <= 1e-12 * sc and abs(b - ref) <= 1e-12 * sc, (o.name, a, b, ref)
+    # ---- (3) velocity-gradient kernel: eddy-viscosity closure, eps + |S| fields ---------------------------------------
+    from cases import build_cases
+    cases = {c[0]: c for c in build_cases(st, "smagorinsky_like")}
+    names = ["DissipationRate", "StrainRateTensorModulus"]
+    g3 = ocb.FusedDiagnostics(*[ocb.Field(cases[n][1]) for n in names]).compute()
+    assert g3.plan.variant == 3, g3.plan.variant
+    for n, mem in zip(names, g3.members):
+        check_case(st, n, mem.interior_ijk(), cases[n][2])
+    # ---- (4) staged Gaussian filter, three passes, shrink policy in z ------------------------------------------------
+    from oracle import filters as OF
+    got = ocb.Field(ocb.SpatialFilters.GaussianFilter(st.b, dims=(1, 2, 3), sigma=2.0 / 32, N=5)).compute().interior_ijk()
+    np.testing.assert_allclose(got, OF.gaussian_filter(st.ob, (1, 2, 3), 2.0 / 32, 5), rtol=1e-13, atol=1e-18)
+    # ---- (5) sort-based reference height (radix sort + scans + scatter) -----------------------------------------------
+    from oracle import bpe as OB
+    z = ocb.BackgroundPotentialEnergyEquation.reference_height(st.b)
+    wantz = OB.reference_height(st.ob)
+    torch.cuda.synchronize()
+    n = got.size
+    np.testing.assert_array_equal(z.sorted_buoyancy.cpu().numpy(), wantz["b_sorted"])
+    np.testing.assert_allclose(z.interior_ijk(), wantz["zstar"], rtol=0, atol=max(1e-12, 4 * n * np.finfo(np.float64).eps))

@@ -82,6 +82,22 @@ def main():
         ovp_total = ovp.step().clone()
     torch.cuda.synchronize()
     ovp.exchanger.check()
+    # ---- the ring step: one-row push, gated class-sum sweep, in-kernel all-reduce over the ranks' sync blocks -------------
+    from oceanostics_b200.distributed import RingSlabBudget
+    rb = RingSlabBudget(g, flds, lambda: budget_ops(m), rank=rank, world=world, timeout=20.0)
+    for f in flds:
+        f.data[:, :3, :] = 0.0
+        f.data[:, -3:, :] = 0.0
+    torch.cuda.synchronize(); dist.barrier()
+    ring_total = None
+    for _ in range(4):
+        ring_total = rb.step().clone()
+    torch.cuda.synchronize()
+    rb.check()
+    same = ring_total.clone()
+    dist.all_reduce(same, op=dist.ReduceOp.MAX)
+    ring_same_bits = torch.tensor([1.0 if bool((same == ring_total).all()) else 0.0], device=dev)
+    dist.all_reduce(ring_same_bits, op=dist.ReduceOp.MIN)
     p_ok = torch.tensor([1.0 if peer_same else 0.0], device=dev)
     dist.all_reduce(p_ok, op=dist.ReduceOp.MIN)
     # ---- slab filter: the y pass reaches 5 rows into each neighbour (exchanged over NCCL) -------------------------
@@ -95,7 +111,7 @@ def main():
     f_err = float((slab_f.interior - want_f).abs().max()) / float(want_f.abs().max())
     f_ok = torch.tensor([1.0 if f_err <= 1e-14 else 0.0], device=dev)
     dist.all_reduce(f_ok, op=dist.ReduceOp.MIN)
-    ok = bool(f_ok.item() > 0) and bool(p_ok.item() > 0)
+    ok = bool(f_ok.item() > 0) and bool(p_ok.item() > 0) and bool(ring_same_bits.item() > 0)
     if rank == 0:
         print("slab filter max rel err", f_err, flush=True)
         _, mg, _ = model_on(1, Ny, full=True)
@@ -109,6 +125,9 @@ def main():
             ok &= abs(a - b) <= 1e-12 * s
         for a, b, s in zip(ovp_total.cpu().numpy(), want, scales):
             ok &= abs(a - b) <= 1e-12 * s
+        for a, b, s in zip(ring_total.cpu().numpy(), want, scales):
+            ok &= abs(a - b) <= 1e-12 * s
+        print("ring step integrals:", ring_total.tolist(), "identical on every rank:", bool(ring_same_bits.item() > 0), flush=True)
         print("peer exchange equals NCCL exchange:", bool(p_ok.item() > 0), flush=True)
         print("MULTIGPU_CHECK", "OK" if ok else "FAIL", got.tolist(), want.tolist(), flush=True)
     dist.barrier()

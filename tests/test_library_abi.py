@@ -25,20 +25,20 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), f"{name} is declared in the header but not exported"
     assert sorted(ocb._lib.EXPORTED_SYMBOLS) == declared
-    assert L.ocb_abi_version() == 1
+    assert L.ocb_abi_version() == ocb._lib.OCB_ABI_VERSION == 2
 
 
 def test_struct_layouts_match_header_sizes():
     # sizes the C compiler gives the descriptors (computed once with gcc from the header itself)
     import subprocess, tempfile
-    src = '#include <stdio.h>\n#include "oceanostics_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(ocb_grid), sizeof(ocb_field), sizeof(ocb_closure), sizeof(ocb_request), sizeof(ocb_sweep_inputs), sizeof(ocb_filter_pass));return 0;}\n'
+    src = '#include <stdio.h>\n#include "oceanostics_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(ocb_grid), sizeof(ocb_field), sizeof(ocb_closure), sizeof(ocb_request), sizeof(ocb_sweep_inputs), sizeof(ocb_filter_pass), sizeof(ocb_ring));return 0;}\n'
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "s.c"), "w").write(src)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "s.c"), "-o", os.path.join(d, "s")])
         sizes = [int(x) for x in subprocess.check_output([os.path.join(d, "s")]).split()]
     L = ocb._lib
     assert sizes == [C.sizeof(L.ocb_grid), C.sizeof(L.ocb_field), C.sizeof(L.ocb_closure), C.sizeof(L.ocb_request),
-                     C.sizeof(L.ocb_sweep_inputs), C.sizeof(L.ocb_filter_pass)]
+                     C.sizeof(L.ocb_sweep_inputs), C.sizeof(L.ocb_filter_pass), C.sizeof(L.ocb_ring)]
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")

@@ -100,6 +100,84 @@ def test_peer_self_exchange_equals_periodic_fill():
         px.check()
 
 
+@pytest.mark.parametrize("size", [(64, 48, 24), (70, 21, 9), (64, 33, 40), (32, 16, 5)], ids=str)
+def test_ring_mode_of_the_class_sum_kernel(size):
+    """Whole periodic y extent: the class-sum kernel gives every row the interior item weights and drops the extra row
+    jy_hi + 1 (its items are the wrapped row 1's).  Same integrals as the window form (OCB_SUMS_NO_RING=1) and the oracle."""
+    import os
+    from test_fused_budget_gpu import oracle_budget
+    st = State(size=size, device="cuda")
+    ops, oc = budget(st)
+    want = oracle_budget(st, oc)
+    ring = ocb.FusedDiagnostics(*[ocb.Integral(o) for o in ops]).compute()
+    os.environ["OCB_SUMS_NO_RING"] = "1"
+    try:
+        plain = ocb.FusedDiagnostics(*[ocb.Integral(o) for o in ops]).compute()
+    finally:
+        os.environ.pop("OCB_SUMS_NO_RING", None)
+    assert ring.plan.variant == 1 and ring.plan.ring_capable and not plain.plan.ring_capable
+    V = 1.0 / (size[0] * size[1] * size[2])
+    for o, w_, a, b in zip(ops, want, ring.integrals(), plain.integrals()):
+        ref, scale = float(np.sum(w_)) * V, float(np.sum(np.abs(w_))) * V
+        assert abs(a - ref) <= 1e-12 * scale, (o.name, a, ref)
+        assert abs(a - b) <= 1e-12 * scale, (o.name, a, b)
+
+
+def test_ring_step_on_a_ring_of_one():
+    """RingSlabBudget with one rank: the push lands the slab's own edge rows in its own halos, the sweep's edge tile rows
+    wait for the flag words in the kernel, the reduction kernel passes through the (one-rank) mailboxes.  Wiped y halos must
+    be refilled by the step itself; repeated steps count the flags up; the integrals are those of the periodic domain."""
+    from oceanostics_b200.distributed import RingSlabBudget
+    st = State(size=(64, 80, 24), device="cuda")
+    ops, _ = budget(st)
+    ref = ocb.FusedDiagnostics(*[ocb.Integral(o) for o in ops]).compute().integrals()
+    scales = [float(ocb.Field(o).compute().interior.abs().sum()) / (64 * 80 * 24) for o in ops]
+    fields = [st.u, st.v, st.w, st.b, st.p]
+    rb = RingSlabBudget(st.pg, fields, lambda: budget(st)[0], rank=0, world=1, timeout=5.0)
+    assert not rb.serial
+    for f in fields:
+        f.data[:, :3, :] = 0.0
+        f.data[:, -3:, :] = 0.0
+    for _ in range(3):
+        got = rb.step().clone()
+    torch.cuda.synchronize()
+    rb.check()
+    assert rb.ring.block[:3].tolist() == [3, 3, 0]
+    for o, a, b, sc in zip(ops, got.tolist(), ref, scales):
+        assert abs(a - b) <= 1e-12 * sc, (o.name, a, b)
+    # a thin slab (fewer than three tile rows) runs the push on the compute stream first; same numbers
+    st2 = State(size=(64, 24, 12), device="cuda")
+    ops2, _ = budget(st2)
+    ref2 = ocb.FusedDiagnostics(*[ocb.Integral(o) for o in ops2]).compute().integrals()
+    rb2 = RingSlabBudget(st2.pg, [st2.u, st2.v, st2.w, st2.b, st2.p], lambda: budget(st2)[0], rank=0, world=1, timeout=5.0)
+    assert rb2.serial
+    got2 = rb2.step().tolist()
+    scales2 = [float(ocb.Field(o).compute().interior.abs().sum()) / (64 * 24 * 12) for o in ops2]
+    for o, a, b, sc in zip(ops2, got2, ref2, scales2):
+        assert abs(a - b) <= 1e-12 * sc, (o.name, a, b)
+    # a step whose push never happened: the gated tiles give up after the timeout, the integrals read NaN, the word is set
+    rb.ring.desc.timeout_seconds = 0.05
+    rb.exchanger.step_no += 1
+    rb.plan.execute_ring(rb.ring, rb.exchanger.step_no)
+    torch.cuda.synchronize()
+    assert bool(torch.isnan(rb.total).all())
+    with pytest.raises(ocb.OcbError, match="did not arrive"):
+        rb.check()
+
+
+def test_operands_on_a_non_current_device_are_guarded():
+    """Every entry point runs on the device that owns its operands (OcbDeviceGuard), whatever the current device is."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    st = State(size=(32, 16, 8), device="cuda:1")
+    ops, _ = budget(st)
+    with torch.cuda.device(0):
+        got = ocb.FusedDiagnostics(*[ocb.Integral(o) for o in ops]).compute().integrals()
+    with torch.cuda.device(1):
+        want = ocb.FusedDiagnostics(*[ocb.Integral(o) for o in ops]).compute().integrals()
+    assert got == want
+
+
 def test_batched_pack_equals_the_per_field_kernels():
     """ocb_halo_pack_y_many (both edges of all fields in one launch) fills the same buffers, and writes the same halo rows,
     as ocb_halo_pack_y / ocb_halo_unpack_y called field by field (u is Face in x, w has Nz + 1 levels: different shapes)."""

@@ -154,6 +154,13 @@ def test_status_gated_recompute():
     np.testing.assert_array_equal(f.interior_ijk(), before)
     grp.compute(time=2.0)                      # new time: recomputed from the evolved state
     assert not np.array_equal(f.interior_ijk(), before)
+    # Oceananigans recomputes whenever time == 0 (compute_at!: `time == zero(time) || time != status.time`)
+    grp.compute(time=0.0)
+    at_zero = f.interior_ijk().copy()
+    st.u.data.mul_(2.0)
+    grp.compute(time=0.0)
+    assert not np.array_equal(f.interior_ijk(), at_zero)
+    ocb.compute_at(f, 0.0)
 
 
 def test_error_behaviour():
