@@ -158,7 +158,7 @@ def integrand_scales(ocb, torch, grid, m, dist, nplanes=8):
     k1 = min(Nz, k0 + nplanes - 1)
     fs = [ocb.Field(o, indices=(None, None, (k0, k1))) for o in budget_ops(ocb, m)]
     ocb.FusedDiagnostics(*fs).compute()
-    V = grid.d[0] * grid.d[1] * grid.d[2]
+    V = float(grid.spacing0[0]) * float(grid.spacing0[1]) * float(grid.spacing0[2])
     s = torch.stack([f.interior.abs().sum() for f in fs]) * (V * Nz / (k1 - k0 + 1))
     if dist is not None:
         dist.all_reduce(s)

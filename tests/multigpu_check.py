@@ -29,7 +29,7 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     from oceanostics_b200.distributed import SlabHaloExchanger, slab_range, allreduce_integrals
-    Nx, Ny, Nz = 128, 96, 64
+    Nx, Ny, Nz = 128, 192, 32          # slabs of 96 / 48 rows at 2 / 4 ranks (gated ring step), 24 rows at 8 (serial ring step)
     gen = torch.Generator(device=dev).manual_seed(1234)
     glob = {n: torch.randn((Nz + (1 if n == "w" else 0), Ny, Nx), generator=gen, device=dev, dtype=torch.float64) for n in "uvwbp"}
     glob["w"][0].zero_(); glob["w"][-1].zero_()
