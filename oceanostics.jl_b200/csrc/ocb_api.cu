@@ -38,9 +38,17 @@ int ocb_sm_count() {
 }
 
 long long ocb_cycles(double seconds) {
-  int dev = 0, khz = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev) != cudaSuccess || khz <= 0) khz = 1965000;
-  return (long long)(seconds * 1e3 * (double)khz);
+  // cudaDevAttrClockRate is one of the attributes the runtime fetches from the device on every query (slow, and serialised
+  // between the processes of a box): asked once per device, never on a per-step path
+  static int khz_of[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  if (khz_of[dev] <= 0) {
+    int khz = 0;
+    if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev) != cudaSuccess || khz <= 0) khz = 1965000;
+    khz_of[dev] = khz;
+  }
+  return (long long)(seconds * 1e3 * (double)khz_of[dev]);
 }
 
 // Stream-ordered scratch (cudaMallocAsync) comes from the device's default pool; by default the pool hands memory

@@ -480,10 +480,6 @@ extern "C" int ocb_halo_wait(void* flags, int64_t step, double timeout_seconds, 
   int rc = ocb_require_device();
   if (rc != OCB_OK) return rc;
   OcbDeviceGuard device_guard(flags);
-  int dev = 0, khz = 0;
-  OCB_CUDA(cudaGetDevice(&dev));
-  OCB_CUDA(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev));
-  (void)khz;
   ocb_wait_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((long long*)flags, (long long)step, ocb_cycles(timeout_seconds));
   OCB_CUDA(cudaGetLastError());
   return OCB_OK;
