@@ -138,6 +138,12 @@ enum {
   OCB_DIAG_KE_STRESS,     /* uᵢ∂ⱼ_τᵢⱼᶜᶜᶜ: velocity x divergence of the viscous fluxes  KineticEnergyEquation.jl:191-202 (next-row, §8f) */
   OCB_DIAG_KE_FORCING,    /* uᵢFᵤᵢᶜᶜᶜ: velocity x forcing, forcings materialised at the velocity points in aux[0..2]  KineticEnergyEquation.jl:251-260 (next-row, §8f) */
   OCB_DIAG_C_TENDENCY,    /* c∂ₜcᶜᶜᶜ = 2c (-div_Uc[Centered 2nd order] - ∇·q + F), tracer in slot b, F in aux[0]  TracerVarianceEquation.jl:18-39 (next-row, §8f) */
+  OCB_DIAG_KE_TENDENCY,   /* uᵢGᵢᶜᶜᶜ: velocity x NonhydrostaticModel momentum tendency (Centered 2nd-order advection, Coriolis f[3], buoyancy b x ghat,
+                             hydrostatic pressure anomaly in slot p, viscous flux divergence, forcings in aux[0..2]); no background fields,
+                             immersed boundaries or Stokes drift  KineticEnergyEquation.jl:74-95 (next-row, §8f) */
+  OCB_DIAG_NU_SMAG,       /* the step before the path (§8f row 3): Smagorinsky-Lilly eddy viscosity νₑ = ς (C Δᶠ)² √(2 ΣᵢⱼΣᵢⱼ) at ccc, Δᶠ = ∛(ΔxΔyΔz),
+                             ς² = max(0, 1 - Cb N²/(Pr ΣᵢⱼΣᵢⱼ)), N² = max(0, ℑz ∂z b); C, Cb, Pr in les[0..2] (Cb = 0: no stratification
+                             correction, b unused) -- Oceananigans' calc_nonlinear_νᶜᶜᶜ for SmagorinskyLilly; ΣᵢⱼΣᵢⱼ as in FlowDiagnostics.jl:431-441 */
   OCB_DIAG_COUNT
 };
 
@@ -148,8 +154,10 @@ enum {
                                  (src/TurbulentKineticEnergyEquation.jl:89-95, 327-330) evaluated on the fly */
   OCB_REQ_TENSOR_DIM1 = 1 << 4, OCB_REQ_TENSOR_DIM2 = 1 << 5, OCB_REQ_TENSOR_DIM3 = 1 << 6,  /* `dims` of PI (default all three) */
   OCB_REQ_COLLOCATED = 1 << 7, /* PI built with collocate_diagonals=true */
-  OCB_REQ_CARRIED_HEIGHT = 1 << 8  /* APE on a VerticalSort column: the parcel's own height is the field aux[3], not the grid's z
+  OCB_REQ_CARRIED_HEIGHT = 1 << 8, /* APE on a VerticalSort column: the parcel's own height is the field aux[3], not the grid's z
                                       (4-argument local_ape_ccc, AvailablePotentialEnergyEquation.jl:43) */
+  OCB_REQ_HYDROSTATIC_SPLIT = 1 << 9 /* KE_TENDENCY: the model carries a hydrostatic pressure anomaly pHY′ (slot p), so the vertical momentum
+                                      tendency has no buoyancy term (Oceananigans' w_velocity_tendency) */
 };
 
 typedef struct {
@@ -178,6 +186,7 @@ typedef struct {
   double      f_dir;        /* DEPV: sum(f .* direction) */
   double      ghat[3];      /* -gravity_unit_vector (uᵢbᵢ); (0,0,1) by default */
   double      ro_bg[6];     /* Rossby background shears: dWdy, dVdz, dUdz, dWdx, dUdy, dVdx */
+  double      les[4];       /* NU_SMAG: Smagorinsky coefficient C, buoyancy coefficient Cb (0 = none), turbulent Prandtl number Pr, reserved */
 } ocb_sweep_inputs;
 
 typedef struct ocb_plan ocb_plan;

@@ -138,6 +138,38 @@ def KineticEnergyForcing(model, location=CCC):
                                    name="KineticEnergyForcing", computes="kinetic energy forcing  uᵢFᵤᵢ")
 
 
+def KineticEnergyTendency(model, location=CCC):
+    """KET = uᵢGᵢ, the kinetic-energy tendency excluding the nonhydrostatic pressure contribution (uᵢGᵢᶜᶜᶜ,
+    src/KineticEnergyEquation.jl:74-95, constructor :120-142): each velocity times Oceananigans' NonhydrostaticModel velocity
+    tendency -- advection (Centered second order), Coriolis (FPlane / ConstantCartesianCoriolis), buoyancy, hydrostatic
+    pressure anomaly, viscous-flux divergence, forcing -- for a model without background fields, immersed boundaries or
+    Stokes drift (anything else is refused).  SURVEY.md section 8f, row 2."""
+    from .models import get_coriolis_frequency_components
+    from .operations import forcing_operand
+    validate_location(location, "KineticEnergyTendency")
+    if model.hydrostatic:
+        raise TypeError("KineticEnergyTendency is defined for NonhydrostaticModel only (src/KineticEnergyEquation.jl:120)")
+    if str(model.advection) not in ("Centered", "Centered(order=2)"):
+        raise _lib.OcbError(f"advection scheme {model.advection!r}: only Centered second-order momentum advection is "
+                            "evaluated by the CUDA library")
+    for name in ("stokes_drift", "background_fields", "immersed_boundary"):
+        if getattr(model, name, None) is not None:
+            raise _lib.OcbError(f"KineticEnergyTendency with model.{name} is not evaluated by the CUDA library")
+    u, v, w = _vel(model.velocities)
+    kw = dict(u=u, v=v, w=w, closure=model.closure, f=tuple(get_coriolis_frequency_components(model.coriolis)))
+    if model.buoyancy is not None:
+        kw["b"] = model.tracers.b
+        kw["ghat"] = tuple(-g for g in model.buoyancy.gravity_unit_vector)
+    flags = 0
+    pHY = getattr(model.pressures, "pHY", None)
+    if pHY is not None:
+        kw["p"] = pHY
+        flags |= _lib.OCB_REQ_HYDROSTATIC_SPLIT
+    kw["aux"] = {a: forcing_operand(getattr(model.forcing, n), f_, model) for a, (n, f_) in enumerate((("u", u), ("v", v), ("w", w)))}
+    return KernelFunctionOperation("KE_TENDENCY", model.grid, SweepOperands(**kw), flags=flags, name="KineticEnergyTendency",
+                                   computes="kinetic energy tendency  uᵢGᵢ (excl. nonhydrostatic pressure)")
+
+
 Stress = KineticEnergyStress
 Forcing = KineticEnergyForcing
-KineticEnergyTendency = _deferred("KineticEnergyTendency")
+Tendency = KineticEnergyTendency

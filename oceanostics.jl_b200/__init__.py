@@ -8,7 +8,7 @@ from ._lib import OcbError
 from .grids import RectilinearGrid, Periodic, Bounded, Flat, Center, Face
 from .fields import (Field, CenterField, XFaceField, YFaceField, ZFaceField, ZeroField, ConstantField, BinaryOperation,
                      average_xy)
-from .operations import (KernelFunctionOperation, ComputedField, ReducedField, Integral, Average, FusedDiagnostics, Closure,
+from .operations import (KernelFunctionOperation, ComputedField, ReducedField, Integral, Average, FusedDiagnostics, Closure, SmagorinskyLilly,
                          SweepOperands, SweepPlan, compute, compute_at)
 from .models import (NonhydrostaticModel, HydrostaticFreeSurfaceModel, FPlane, ConstantCartesianCoriolis, BuoyancyTracer,
                      Forcing, get_coriolis_frequency_components)

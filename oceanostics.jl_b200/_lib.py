@@ -26,12 +26,13 @@ OCB_REQ_PERTURBATION = 1
 OCB_REQ_TENSOR_DIM1, OCB_REQ_TENSOR_DIM2, OCB_REQ_TENSOR_DIM3 = 1 << 4, 1 << 5, 1 << 6
 OCB_REQ_COLLOCATED = 1 << 7
 OCB_REQ_CARRIED_HEIGHT = 1 << 8
+OCB_REQ_HYDROSTATIC_SPLIT = 1 << 9
 
 _DIAG_NAMES = [
     "KE", "ADV", "PR", "WB", "EPS", "EPS_ISO", "TKE", "SPX", "SPY", "SPZ", "SP", "CHI", "CDIFF", "SMOD", "OMOD", "Q",
     "S11", "S22", "S33", "S12", "S13", "S23", "O12", "O13", "O23", "T11", "T22", "T33", "T11C", "T22C", "T33C",
     "T12", "T13", "T23", "RI", "RO", "EPV", "TWPV", "DEPV", "VF11", "VF22", "VF33", "VF12", "VF13", "VF23",
-    "FEPS", "SFEPS", "SFKE", "PI", "BPE", "APE", "UPSILON", "APE_EPS", "KE_STRESS", "KE_FORCING", "C_TENDENCY"]
+    "FEPS", "SFEPS", "SFKE", "PI", "BPE", "APE", "UPSILON", "APE_EPS", "KE_STRESS", "KE_FORCING", "C_TENDENCY", "KE_TENDENCY", "NU_SMAG"]
 DIAG = {name: i for i, name in enumerate(_DIAG_NAMES)}
 OCB_DIAG_COUNT = len(_DIAG_NAMES)
 
@@ -79,7 +80,7 @@ class ocb_sweep_inputs(C.Structure):
                 ("U", ocb_field), ("V", ocb_field), ("W", ocb_field), ("B", ocb_field),
                 ("aux", ocb_field * OCB_N_AUX), ("closure", ocb_closure),
                 ("f", C.c_double * 3), ("dir", C.c_double * 3), ("f_dir", C.c_double), ("ghat", C.c_double * 3),
-                ("ro_bg", C.c_double * 6)]
+                ("ro_bg", C.c_double * 6), ("les", C.c_double * 4)]
 
 
 class ocb_filter_pass(C.Structure):

@@ -19,7 +19,7 @@ struct SweepIn {
   HFld<T> aux[OCB_N_AUX];
   T nu_c; int n_nu; HFld<T> nu_f[OCB_MAX_CLOSURE_FIELDS];
   T ka_c; int n_ka; HFld<T> ka_f[OCB_MAX_CLOSURE_FIELDS]; T ka_s[OCB_MAX_CLOSURE_FIELDS];
-  T f[3], dir[3], f_dir, ghat[3], ro_bg[6];
+  T f[3], dir[3], f_dir, ghat[3], ro_bg[6], les[4];
 };
 
 struct DReq {
@@ -602,6 +602,77 @@ OCB_EVAL(OCB_DIAG_C_TENDENCY) {
   return T(2) * cc * (X.in.aux[0](i, j, k) - ((ax + ay) + az) - divq);
 } };
 
+// uᵢGᵢᶜᶜᶜ  (src/KineticEnergyEquation.jl:74-95): each velocity times Oceananigans' NonhydrostaticModel velocity tendency at the
+// velocity point, interpolated to the cell centre.  For a model without background fields, immersed boundaries or Stokes drift
+//   Gu = -div_𝐯u + x_dot_g_b - x_f_cross_U - ∂x pHY′ - ∂ⱼ_τ₁ⱼ + Fu      (v alike)
+//   Gw = -div_𝐯w + [no pHY′: z_dot_g_b] - z_f_cross_U - ∂ⱼ_τ₃ⱼ + Fw
+// [OCN-mem: Models/NonhydrostaticModels/velocity_and_tracer_tendencies.jl; Coriolis/constant_cartesian_coriolis.jl -- FPlane is
+//  f = (0, 0, f)], Centered second-order advection.  The nonhydrostatic pressure gradient is not part of G (:100-103).
+template <class T> struct Tendency {
+  const Ctx<T>& X;
+  AdvFlux<T> A;
+  StressDiv<T> D;
+  bool w_buoyancy;
+  OCB_X Tendency(const Ctx<T>& x, int flags) : X(x), A(x), D(x), w_buoyancy(!(flags & OCB_REQ_HYDROSTATIC_SPLIT)) {}
+  OCB_X T gu(int i, int j, int k) const {   // fcc
+    const SweepIn<T>& I = X.in;
+    T r = I.aux[0](i, j, k) - A.divu(i, j, k) - D.d1(i, j, k) - (I.p(i, j, k) - I.p(i - 1, j, k)) * X.g.rdx;
+    if (I.ghat[0] != T(0)) r += I.ghat[0] * (T(0.5) * (I.b(i - 1, j, k) + I.b(i, j, k)));
+    T cor = T(0);
+    if (I.f[1] != T(0)) cor += I.f[1] * (T(0.25) * ((X.w(i - 1, j, k) + X.w(i, j, k)) + (X.w(i - 1, j, k + 1) + X.w(i, j, k + 1))));
+    if (I.f[2] != T(0)) cor -= I.f[2] * (T(0.25) * ((X.v(i - 1, j, k) + X.v(i, j, k)) + (X.v(i - 1, j + 1, k) + X.v(i, j + 1, k))));
+    return r - cor;
+  }
+  OCB_X T gv(int i, int j, int k) const {   // cfc
+    const SweepIn<T>& I = X.in;
+    T r = I.aux[1](i, j, k) - A.divv(i, j, k) - D.d2(i, j, k) - (I.p(i, j, k) - I.p(i, j - 1, k)) * X.g.rdy;
+    if (I.ghat[1] != T(0)) r += I.ghat[1] * (T(0.5) * (I.b(i, j - 1, k) + I.b(i, j, k)));
+    T cor = T(0);
+    if (I.f[2] != T(0)) cor += I.f[2] * (T(0.25) * ((X.u(i, j - 1, k) + X.u(i + 1, j - 1, k)) + (X.u(i, j, k) + X.u(i + 1, j, k))));
+    if (I.f[0] != T(0)) cor -= I.f[0] * (T(0.25) * ((X.w(i, j - 1, k) + X.w(i, j, k)) + (X.w(i, j - 1, k + 1) + X.w(i, j, k + 1))));
+    return r - cor;
+  }
+  OCB_X T gw(int i, int j, int k) const {   // ccf
+    const SweepIn<T>& I = X.in;
+    T r = I.aux[2](i, j, k) - A.divw(i, j, k) - D.d3(i, j, k);
+    if (w_buoyancy && I.ghat[2] != T(0)) r += I.ghat[2] * (T(0.5) * (I.b(i, j, k - 1) + I.b(i, j, k)));
+    T cor = T(0);
+    if (I.f[0] != T(0)) cor += I.f[0] * (T(0.25) * ((X.v(i, j, k - 1) + X.v(i, j + 1, k - 1)) + (X.v(i, j, k) + X.v(i, j + 1, k))));
+    if (I.f[1] != T(0)) cor -= I.f[1] * (T(0.25) * ((X.u(i, j, k - 1) + X.u(i + 1, j, k - 1)) + (X.u(i, j, k) + X.u(i + 1, j, k))));
+    return r - cor;
+  }
+};
+OCB_EVAL(OCB_DIAG_KE_TENDENCY) {
+  Tendency<T> G(X, flags);
+  T a = X.u(i, j, k) * G.gu(i, j, k) + X.u(i + 1, j, k) * G.gu(i + 1, j, k);
+  T b = X.v(i, j, k) * G.gv(i, j, k) + X.v(i, j + 1, k) * G.gv(i, j + 1, k);
+  T c = X.w(i, j, k) * G.gw(i, j, k) + X.w(i, j, k + 1) * G.gw(i, j, k + 1);
+  return T(0.5) * (a + b + c);
+} };
+
+// Smagorinsky-Lilly eddy viscosity at ccc (Oceananigans' compute_diffusivities! for SmagorinskyLilly,
+// the step before the path) [OCN-mem: TurbulenceClosures/turbulence_closure_implementations/smagorinsky_lilly.jl]:
+//   νₑ = ς (C Δᶠ)² √(2 Σ²),  Σ² = ΣᵢⱼΣᵢⱼᶜᶜᶜ (the square of strain_rate_tensor_modulus_ccc, src/FlowDiagnostics.jl:431-441),
+//   Δᶠ = ∛(Δx Δy Δz),  ς = Σ² == 0 ? 0 : √(max(0, 1 - Cb N²⁺/(Pr Σ²))),  N²⁺ = max(0, ℑzᵃᵃᶜ ∂zᶜᶜᶠ b)
+template <class T> OCB_X T ocb_cbrt(T x);
+template <> OCB_X double ocb_cbrt<double>(double x) { return cbrt(x); }
+template <> OCB_X float ocb_cbrt<float>(float x) { return cbrtf(x); }
+OCB_EVAL(OCB_DIAG_NU_SMAG) {
+  const SweepIn<T>& I = X.in;
+  const T S2 = ocb_strain_sq(X, i, j, k);
+  const T C = I.les[0], Cb = I.les[1], Pr = I.les[2];
+  const T delta = ocb_cbrt(X.g.dx * X.g.dy * X.dzc(k));
+  T sig = T(1);
+  if (Cb != T(0)) {
+    const T bc = I.b(i, j, k);
+    T N2 = T(0.5) * ((bc - I.b(i, j, k - 1)) * X.rdzf(k) + (I.b(i, j, k + 1) - bc) * X.rdzf(k + 1));
+    N2 = N2 > T(0) ? N2 : T(0);
+    const T s2 = T(1) - Cb * N2 / (Pr * S2);
+    sig = S2 == T(0) ? T(0) : ocb_sqrt(s2 > T(0) ? s2 : T(0));
+  }
+  return sig * ocb_sq(C * delta) * ocb_sqrt(T(2) * S2);
+} };
+
 // ---- dispatch -------------------------------------------------------------------------------------------------
 #define OCB_FOR_EACH_DIAG(M) \
   M(OCB_DIAG_KE) M(OCB_DIAG_ADV) M(OCB_DIAG_PR) M(OCB_DIAG_WB) M(OCB_DIAG_EPS) M(OCB_DIAG_EPS_ISO) M(OCB_DIAG_TKE) \
@@ -611,7 +682,8 @@ OCB_EVAL(OCB_DIAG_C_TENDENCY) {
   M(OCB_DIAG_T11C) M(OCB_DIAG_T22C) M(OCB_DIAG_T33C) M(OCB_DIAG_T12) M(OCB_DIAG_T13) M(OCB_DIAG_T23) M(OCB_DIAG_RI) \
   M(OCB_DIAG_RO) M(OCB_DIAG_EPV) M(OCB_DIAG_TWPV) M(OCB_DIAG_DEPV) M(OCB_DIAG_VF11) M(OCB_DIAG_VF22) M(OCB_DIAG_VF33) \
   M(OCB_DIAG_VF12) M(OCB_DIAG_VF13) M(OCB_DIAG_VF23) M(OCB_DIAG_FEPS) M(OCB_DIAG_SFEPS) M(OCB_DIAG_SFKE) M(OCB_DIAG_PI) \
-  M(OCB_DIAG_BPE) M(OCB_DIAG_APE) M(OCB_DIAG_UPSILON) M(OCB_DIAG_APE_EPS) M(OCB_DIAG_KE_STRESS) M(OCB_DIAG_KE_FORCING) M(OCB_DIAG_C_TENDENCY)
+  M(OCB_DIAG_BPE) M(OCB_DIAG_APE) M(OCB_DIAG_UPSILON) M(OCB_DIAG_APE_EPS) M(OCB_DIAG_KE_STRESS) M(OCB_DIAG_KE_FORCING) M(OCB_DIAG_C_TENDENCY) \
+  M(OCB_DIAG_KE_TENDENCY) M(OCB_DIAG_NU_SMAG)
 
 // diagnostics whose operands may be lazy perturbations (u - U, c - C); the flag is rejected for the others
 OCB_X constexpr bool ocb_diag_takes_perturbation(int d) {

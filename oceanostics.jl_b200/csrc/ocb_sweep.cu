@@ -159,6 +159,8 @@ static double count_algorithmic_bytes(const ocb_grid* g, const ocb_sweep_inputs*
       case OCB_DIAG_SFKE: mark_uvw(); use[15] = true; break;
       case OCB_DIAG_KE_FORCING: mark_uvw(); use[9] = use[10] = use[11] = true; break;
       case OCB_DIAG_C_TENDENCY: mark_uvw(); use[3] = true; use[9] = true; break;
+      case OCB_DIAG_KE_TENDENCY: mark_uvw(); use[3] = use[4] = true; use[9] = use[10] = use[11] = true; break;
+      case OCB_DIAG_NU_SMAG: mark_uvw(); if (in->les[1] != 0) use[3] = true; break;
       default: mark_uvw(); break;
     }
     if (pert || d == OCB_DIAG_TKE || (d >= OCB_DIAG_SPX && d <= OCB_DIAG_SP)) use[5] = use[6] = use[7] = true;
@@ -176,7 +178,7 @@ static double count_algorithmic_bytes(const ocb_grid* g, const ocb_sweep_inputs*
   for (int r = 0; r < n; ++r) {
     const int d = reqs[r].diag;
     if (d == OCB_DIAG_EPS || d == OCB_DIAG_EPS_ISO || d == OCB_DIAG_CHI || d == OCB_DIAG_CDIFF || d == OCB_DIAG_APE_EPS ||
-        d == OCB_DIAG_KE_STRESS || d == OCB_DIAG_C_TENDENCY || (d >= OCB_DIAG_VF11 && d <= OCB_DIAG_VF23)) eddy = true;
+        d == OCB_DIAG_KE_STRESS || d == OCB_DIAG_C_TENDENCY || d == OCB_DIAG_KE_TENDENCY || (d >= OCB_DIAG_VF11 && d <= OCB_DIAG_VF23)) eddy = true;
   }
   if (eddy) {   // count each distinct eddy field once
     const void* seen[2 * OCB_MAX_CLOSURE_FIELDS]; int ns = 0;

@@ -94,6 +94,7 @@ static int ocb_build_sweep_params(const ocb_grid* grid, const ocb_sweep_inputs* 
   for (int d = 0; d < 3; ++d) { I.f[d] = T(in->f[d]); I.dir[d] = T(in->dir[d]); I.ghat[d] = T(in->ghat[d]); }
   I.f_dir = T(in->f_dir);
   for (int d = 0; d < 6; ++d) I.ro_bg[d] = T(in->ro_bg[d]);
+  for (int d = 0; d < 4; ++d) I.les[d] = T(in->les[d]);
 
   P.nreq = n;
   int nslots = 0;
@@ -118,6 +119,10 @@ static int ocb_build_sweep_params(const ocb_grid* grid, const ocb_sweep_inputs* 
     if (needs & OCB_NEED_AUX6) OCB_REQUIRE(I.aux[6].p, "%s needs aux[6] as an array", ocb_diag_name(q.diag));
     if (needs & OCB_NEED_AUX5) OCB_REQUIRE(I.aux[5].p, "%s needs aux[5] as an array", ocb_diag_name(q.diag));
     if (needs & OCB_NEED_AUX4) OCB_REQUIRE(I.aux[4].p, "%s needs aux[4] as an array", ocb_diag_name(q.diag));
+    if (q.diag == OCB_DIAG_NU_SMAG) {
+      OCB_REQUIRE(in->les[0] > 0, "NU_SMAG needs the Smagorinsky coefficient C > 0 in les[0]");
+      if (in->les[1] != 0) OCB_REQUIRE(I.b.p && in->les[2] > 0, "NU_SMAG with a buoyancy coefficient Cb needs the buoyancy operand `b` as an array and Pr > 0");
+    }
     if (q.diag == OCB_DIAG_APE && (q.flags & OCB_REQ_CARRIED_HEIGHT)) OCB_REQUIRE(I.aux[3].p, "APE with a carried height needs aux[3] as an array");
     if (needs & OCB_NEED_AUX05) {
       const bool d1 = q.diag != OCB_DIAG_PI || (q.flags & OCB_REQ_TENSOR_DIM1), d2 = q.diag != OCB_DIAG_PI || (q.flags & OCB_REQ_TENSOR_DIM2),

@@ -74,6 +74,17 @@ class NonhydrostaticModel:
         if unknown:
             raise ValueError(f"forcing names {sorted(unknown)} are not fields of the model")
         self.forcing = SimpleNamespace(**{name: forcing.get(name) for name in ("u", "v", "w") + tuple(tracers)})
+        self.stokes_drift = self.background_fields = self.immersed_boundary = None
+        if hasattr(self.closure, "bind"):          # closures whose eddy fields the library computes (SmagorinskyLilly)
+            self.closure.bind(self)
+
+    def compute_diffusivities(self, time=None):
+        """Oceananigans' `compute_diffusivities!` for the closures the library evaluates: refresh model.closure_fields."""
+        from .operations import compute
+        for f in self.closure.field_arguments():
+            if getattr(f, "is_computed", False):
+                compute(f, time)
+        return self.closure_fields
 
     def fields(self):
         return {**vars(self.velocities), **vars(self.tracers)}

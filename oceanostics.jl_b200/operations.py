@@ -34,7 +34,7 @@ class SweepOperands:
         self.fields = {}     # slot name -> operand (Field / ZeroField / ConstantField)
         self.aux = {}        # aux index -> Field
         self.closure = None  # Closure or None
-        self.scalars = {}    # "f", "dir", "f_dir", "ghat", "ro_bg"
+        self.scalars = {}    # "f", "dir", "f_dir", "ghat", "ro_bg", "les"
         for k, v in kw.items():
             if k in _SLOTS:
                 self.fields[k] = as_operand(v)
@@ -85,6 +85,8 @@ class SweepOperands:
         s.f_dir = float(self.scalars.get("f_dir", 0.0))
         for d in range(6):
             s.ro_bg[d] = float(self.scalars.get("ro_bg", (0.0,) * 6)[d])
+        for d in range(4):
+            s.les[d] = float(self.scalars.get("les", (0.0,) * 4)[d])
         return s
 
     def field_arguments(self):
@@ -150,6 +152,32 @@ class Closure:
             c.kappa_fields[i] = f.descriptor()
             c.kappa_scale[i] = self.kappa_scale[i]
         return c
+
+
+class SmagorinskyLilly(Closure):
+    """Oceananigans' `SmagorinskyLilly(C, Cb, Pr)` with its eddy viscosity computed ON THE DEVICE (SURVEY.md section 8f row 3:
+    the `compute_diffusivities!` step before the path).  `bind(model)` -- called by the model constructor -- makes
+    `model.closure_fields.νₑ` a computed Field of the library's OCB_DIAG_NU_SMAG kernel over the model's velocities and
+    buoyancy; every diagnostic built with this closure refreshes it first (`compute_at!`), so no νₑ array is handed in.
+    κₑ = νₑ / Pr.  `Cb = None` (Oceananigans' default): no stratification correction."""
+
+    def __init__(self, C=0.16, Cb=None, Pr=1.0):
+        Closure.__init__(self, name="SmagorinskyLilly")
+        self.C, self.Cb, self.Pr = float(C), (None if Cb is None else float(Cb)), float(Pr)
+        self.nu_e = None
+
+    def bind(self, model):
+        from types import SimpleNamespace
+        v = model.velocities
+        kw = dict(u=v.u, v=v.v, w=v.w, les=(self.C, self.Cb or 0.0, self.Pr, 0.0))
+        if self.Cb:
+            kw["b"] = model.tracers.b
+        op = KernelFunctionOperation("NU_SMAG", model.grid, SweepOperands(**kw), name="SmagorinskyLillyViscosity",
+                                     computes="eddy viscosity  νₑ = ς (C Δᶠ)² √(2 ΣᵢⱼΣᵢⱼ)")
+        self.nu_e = ComputedField(op)
+        self.nu_fields, self.kappa_fields, self.kappa_scale = (self.nu_e,), (self.nu_e,), (1.0 / self.Pr,)
+        model.closure_fields = SimpleNamespace(nu_e=self.nu_e, **{"νₑ": self.nu_e})
+        return self
 
 
 class AbstractOperation(AbstractField):

@@ -289,6 +289,95 @@ def ke_stress_ccc(i, j, k, g, closure, closure_fields, clock, fields, buoyancy):
             _op.iz_aac(i, j, k, g, psif, fields["w"], div_tau_3, *a))
 
 
+# --- Coriolis force [OCN-mem Coriolis/constant_cartesian_coriolis.jl; FPlane(f) is f = (0, 0, f): Coriolis/f_plane.jl]
+def x_f_cross_U(i, j, k, g, f, U): return f[1] * _op.ixz_fac(i, j, k, g, U["w"]) - f[2] * _op.ixy_fca(i, j, k, g, U["v"])
+def y_f_cross_U(i, j, k, g, f, U): return f[2] * _op.ixy_cfa(i, j, k, g, U["u"]) - f[0] * _op.iyz_afc(i, j, k, g, U["w"])
+def z_f_cross_U(i, j, k, g, f, U): return f[0] * _op.iyz_acf(i, j, k, g, U["v"]) - f[1] * _op.ixz_caf(i, j, k, g, U["u"])
+
+
+def _tendency_common(stokes_drift, immersed_bc, background_fields):
+    assert stokes_drift is None and immersed_bc is None and background_fields is None, \
+        "restated for a model without Stokes drift, immersed boundaries or background fields"
+
+
+def _hydrostatic_gradient(deriv, i, j, k, g, pHY):
+    return 0.0 if pHY is None else deriv(i, j, k, g, pHY)
+
+
+def u_velocity_tendency(i, j, k, g, advection, coriolis, stokes_drift, closure, u_immersed_bc, buoyancy, background_fields, velocities,
+                        tracers, auxiliary_fields, closure_fields, pHY, clock, forcing):
+    """Oceananigans NonhydrostaticModels.u_velocity_tendency [OCN-mem velocity_and_tracer_tendencies.jl]:
+    -div_𝐯u + x_dot_g_b - x_f_cross_U - ∂x pHY′ - ∂ⱼ_τ₁ⱼ + Fu.  `buoyancy` = (ĝ, name of the buoyancy tracer) or None,
+    `coriolis` = (fx, fy, fz) or None."""
+    _tendency_common(stokes_drift, u_immersed_bc, background_fields)
+    fields = {**velocities, **tracers}
+    r = -div_Uu(i, j, k, g, advection, velocities, velocities["u"])
+    if buoyancy is not None:
+        r = r + x_dot_g_b_fcc(i, j, k, g, buoyancy[0], tracers[buoyancy[1]])
+    if coriolis is not None:
+        r = r - x_f_cross_U(i, j, k, g, coriolis, velocities)
+    r = r - _hydrostatic_gradient(_op.ddx_fcc, i, j, k, g, pHY)
+    r = r - div_tau_1(i, j, k, g, closure, closure_fields, clock, fields, buoyancy)
+    return r + (forcing(i, j, k, g, clock, fields) if forcing is not None else 0.0)
+
+
+def v_velocity_tendency(i, j, k, g, advection, coriolis, stokes_drift, closure, v_immersed_bc, buoyancy, background_fields, velocities,
+                        tracers, auxiliary_fields, closure_fields, pHY, clock, forcing):
+    _tendency_common(stokes_drift, v_immersed_bc, background_fields)
+    fields = {**velocities, **tracers}
+    r = -div_Uv(i, j, k, g, advection, velocities, velocities["v"])
+    if buoyancy is not None:
+        r = r + y_dot_g_b_cfc(i, j, k, g, buoyancy[0], tracers[buoyancy[1]])
+    if coriolis is not None:
+        r = r - y_f_cross_U(i, j, k, g, coriolis, velocities)
+    r = r - _hydrostatic_gradient(_op.ddy_cfc, i, j, k, g, pHY)
+    r = r - div_tau_2(i, j, k, g, closure, closure_fields, clock, fields, buoyancy)
+    return r + (forcing(i, j, k, g, clock, fields) if forcing is not None else 0.0)
+
+
+def w_velocity_tendency(i, j, k, g, advection, coriolis, stokes_drift, closure, w_immersed_bc, buoyancy, background_fields, velocities,
+                        tracers, auxiliary_fields, closure_fields, pHY, clock, forcing):
+    """... the vertical buoyancy term only when the model does not separate a hydrostatic pressure anomaly
+    (maybe_z_dot_g_bᶜᶜᶠ: zero when pHY′ is a field, since buoyancy then acts through ∇ₕ pHY′)."""
+    _tendency_common(stokes_drift, w_immersed_bc, background_fields)
+    fields = {**velocities, **tracers}
+    r = -div_Uw(i, j, k, g, advection, velocities, velocities["w"])
+    if buoyancy is not None and pHY is None:
+        r = r + z_dot_g_b_ccf(i, j, k, g, buoyancy[0], tracers[buoyancy[1]])
+    if coriolis is not None:
+        r = r - z_f_cross_U(i, j, k, g, coriolis, velocities)
+    r = r - div_tau_3(i, j, k, g, closure, closure_fields, clock, fields, buoyancy)
+    return r + (forcing(i, j, k, g, clock, fields) if forcing is not None else 0.0)
+
+
+def ke_tendency_ccc(i, j, k, g, advection, coriolis, stokes_drift, closure, u_ibc, v_ibc, w_ibc, buoyancy, background_fields,
+                    velocities, tracers, auxiliary_fields, closure_fields, pHY, clock, forcings):   # uᵢGᵢᶜᶜᶜ, src/KineticEnergyEquation.jl:74-95
+    common = (buoyancy, background_fields, velocities, tracers, auxiliary_fields, closure_fields, pHY, clock)
+    F = forcings or {}
+    a = _op.ix_caa(i, j, k, g, psif, velocities["u"], u_velocity_tendency, advection, coriolis, stokes_drift, closure, u_ibc, *common, F.get("u"))
+    b = _op.iy_aca(i, j, k, g, psif, velocities["v"], v_velocity_tendency, advection, coriolis, stokes_drift, closure, v_ibc, *common, F.get("v"))
+    c = _op.iz_aac(i, j, k, g, psif, velocities["w"], w_velocity_tendency, advection, coriolis, stokes_drift, closure, w_ibc, *common, F.get("w"))
+    return a + b + c
+
+
+# --- Smagorinsky-Lilly eddy viscosity [OCN-mem TurbulenceClosures/.../smagorinsky_lilly.jl: calc_nonlinear_νᶜᶜᶜ, stability]
+def _dzb_ccf(i, j, k, g, b): return _op.ddz_ccf(i, j, k, g, b)
+
+
+def smagorinsky_nu_ccc(i, j, k, g, u, v, w, b, C, Cb=0.0, Pr=1.0):
+    """νₑ = ς (C Δᶠ)² √(2 ΣᵢⱼΣᵢⱼ), Δᶠ = ∛(ΔxΔyΔz) at ccc, ς = Σ² == 0 ? 0 : √max(0, 1 - Cb N²⁺ / (Pr Σ²)),
+    N²⁺ = max(0, ℑzᵃᵃᶜ ∂zᶜᶜᶠ b).  ΣᵢⱼΣᵢⱼ is the square of strain_rate_tensor_modulus_ccc (src/FlowDiagnostics.jl:431-441).
+    Cb = 0 (Oceananigans' `Cb = nothing`): no stratification correction."""
+    S2 = strain_rate_tensor_modulus_ccc(i, j, k, g, u, v, w) ** 2
+    delta = np.cbrt(_op.Dx_ccc(i, j, k, g) * _op.Dy_ccc(i, j, k, g) * _op.Dz_ccc(i, j, k, g))
+    sig = 1.0
+    if Cb:
+        N2 = np.maximum(0.0, _op.iz_aac(i, j, k, g, _dzb_ccf, b))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            sig = np.where(S2 == 0, 0.0, np.sqrt(np.maximum(0.0, 1.0 - Cb * N2 / (Pr * S2))))
+    return sig * (C * delta) ** 2 * np.sqrt(2.0 * S2)
+
+
 # --- Centered (2nd-order) tracer advection  [OCN-mem Advection/tracer_advection_operators.jl]: advective fluxes
 # Ax u ℑx c (fcc), Ay v ℑy c (cfc), Az w ℑz c (ccf) and their divergence at the cell centre
 def _adv_flux_x(i, j, k, g, U, c): return _op.Ax_fcc(i, j, k, g) * U[0][i, j, k] * _op.ix_faa(i, j, k, g, c)

@@ -102,6 +102,23 @@ def build_cases(st: State, closure_name="scalar", mean="profile"):
     cases.append(("TracerVarianceTendency", TV.TracerVarianceTendency(m_forced, "b"),
                   ev(K.c_dt_c_ccc, og, "ccc", 1, "b", None, oc, None, None, None, None, {"u": st.ou, "v": st.ov, "w": st.ow}, {"b": st.ob},
                      None, None, None, Fb), "ccc"))
+    # kinetic-energy tendency uᵢGᵢ (scope table 8f, row 2): Coriolis, buoyancy, viscous stress and the forcings above; once for a
+    # model without a hydrostatic pressure anomaly (w feels buoyancy) and once with one (st.p stands in for pHY′)
+    buoy = ((0.0, 0.0, 1.0), "b")
+    vel = {"u": st.ou, "v": st.ov, "w": st.ow}
+    for tag, opHY in (("", None), ("_pHY", st.op)):
+        m_t = st.model(closure=pc, coriolis=ocb.ConstantCartesianCoriolis(*f_cor))
+        m_t.forcing.u, m_t.forcing.v, m_t.forcing.w = pforc["u"], pforc["v"], pforc["w"]
+        m_t.pressures.pHY = st.p if opHY is not None else None
+        cases.append(("KineticEnergyTendency" + tag, KE.KineticEnergyTendency(m_t),
+                      ev(K.ke_tendency_ccc, og, "ccc", None, f_cor, None, oc, None, None, None, buoy, None, vel, {"b": st.ob}, None, None, opHY, None,
+                         oforc), "ccc"))
+    # Smagorinsky-Lilly eddy viscosity computed by the library (scope table 8f, row 3), without and with the stratification factor
+    for tag, Cb in (("", None), ("_Cb", 1.0)):
+        sm = ocb.SmagorinskyLilly(C=0.16, Cb=Cb, Pr=1.0)
+        m_s = st.model(closure=sm)
+        cases.append(("SmagorinskyViscosity" + tag, sm.nu_e.operand,
+                      ev(K.smagorinsky_nu_ccc, og, "ccc", st.ou, st.ov, st.ow, st.ob, 0.16, Cb or 0.0, 1.0), "ccc"))
     # available-potential-energy family (scope table 8f): z✶ and Ψδ come from the oracle's sorted reference state and are
     # handed to both sides as fields, so these cases test the pointwise / flux kernels, not the sort (tests/test_bpe_gpu.py)
     from oracle import bpe as OB
@@ -216,4 +233,5 @@ def check_case(st, name, got, want, rtol=1e-12):
 # positive-definite diagnostics checked elementwise
 ELEMENTWISE = {"KineticEnergy", "TurbulentKineticEnergy", "DissipationRate", "DissipationRate_perturbation",
                "KineticEnergyIsotropicDissipationRate", "TKEIsotropicDissipationRate", "TracerVarianceDissipationRate",
-               "StrainRateTensorModulus", "VorticityTensorModulus", "T11", "T22", "T33", "T11c", "T22c", "T33c"}
+               "StrainRateTensorModulus", "VorticityTensorModulus", "T11", "T22", "T33", "T11c", "T22c", "T33c",
+               "SmagorinskyViscosity"}

@@ -110,6 +110,8 @@ class State:
         m.velocities.u, m.velocities.v, m.velocities.w = self.u, self.v, self.w
         m.tracers.b = self.b
         m.pressures.pNHS = self.p
+        if hasattr(m.closure, "bind"):
+            m.closure.bind(m)            # eddy fields computed by the library read the fields just swapped in
         return m
 
     def ofields(self):

@@ -151,8 +151,15 @@ def test_subfilter_covariance_and_stress_tensor_against_the_oracle_graph():
 def test_names_outside_the_hot_path_fail_loudly():
     st = State(size=(8, 8, 8), device="cuda")
     m = st.model(closure=st.closures()["scalar"][1])
-    for fn in (ocb.KineticEnergyEquation.KineticEnergyTendency, ocb.FlowDiagnostics.MixedLayerDepth):
+    for fn in (ocb.FlowDiagnostics.MixedLayerDepth,):
         with pytest.raises(ocb.OcbError, match="Oceanostics.jl"):
             fn(m)
+    # the kinetic-energy tendency is evaluated for the plain NonhydrostaticModel; what the library does not restate is refused
+    m.advection = "WENO(order=5)"
+    with pytest.raises(ocb.OcbError, match="Centered"):
+        ocb.KineticEnergyEquation.KineticEnergyTendency(m)
+    m.advection, m.stokes_drift = "Centered", object()
+    with pytest.raises(ocb.OcbError, match="stokes_drift"):
+        ocb.KineticEnergyEquation.KineticEnergyTendency(m)
     assert ocb.KineticEnergyEquation.PotentialToKineticEnergyConversion is ocb.KineticEnergyEquation.PotentialEnergyConversion
     assert SFKE.KineticEnergyCrossScaleFlux is FKE.KineticEnergyCrossScaleFlux

@@ -290,6 +290,95 @@ def test_tracer_variance_tendency_limits(gname, cname):
     np.testing.assert_allclose(forced, -0.6 * b.interior ** 2, rtol=1e-13, atol=1e-300)
 
 
+def _random_state(g, seed):
+    rng = np.random.default_rng(seed)
+    f = {}
+    for name, loc in (("u", "fcc"), ("v", "cfc"), ("w", "ccf"), ("b", "ccc"), ("p", "ccc")):
+        fld = OField(g, loc)
+        fld.interior[...] = rng.standard_normal(fld.interior.shape)
+        f[name] = fld.fill_halo()
+    return f
+
+
+def _ke_tendency(g, cl, f, coriolis=None, buoyancy=None, pHY=None, forcings=None):
+    vel = {"u": f["u"], "v": f["v"], "w": f["w"]}
+    return K.evaluate(K.ke_tendency_ccc, g, "ccc", None, coriolis, None, cl, None, None, None, buoyancy, None, vel, {"b": f["b"]}, None,
+                      None, pHY, None, forcings)
+
+
+@pytest.mark.parametrize("gname", GRIDS)
+@pytest.mark.parametrize("cname", ["scalar", "smagorinsky_like", "tuple"])
+def test_ke_tendency_is_the_sum_of_the_pinned_budget_terms(gname, cname):
+    """uᵢGᵢ (src/KineticEnergyEquation.jl:74-95) is linear in the velocity tendency, and every piece of Oceananigans'
+    NonhydrostaticModel tendency has its own Oceanostics diagnostic that is pinned above (ADV = C₁²C₂y, wb = w₀b₀, <DIFF> = <ε>,
+    uᵢFᵢ = -Σuᵢ²): cell by cell  uᵢGᵢ = -ADV + uᵢbᵢ - uᵢ(f x u)ᵢ - uₕ·∇ₕpHY′ - uᵢ∂ⱼτᵢⱼ + uᵢFᵢ  (KET + PR closes the budget:
+    :100-103).  With a hydrostatic pressure anomaly the vertical buoyancy term leaves the tendency."""
+    g = GRIDS[gname]()
+    cl = make_closures(g, np.random.default_rng(3))[cname]
+    f = _random_state(g, 21)
+    vel = {"u": f["u"], "v": f["v"], "w": f["w"]}
+    damp = lambda x, y, z, t, q: -0.3 * q
+    forcings = {"u": K.ContinuousForcing(damp, "fcc", ("u",)), "v": K.ContinuousForcing(damp, "cfc", ("v",)),
+                "w": K.ContinuousForcing(damp, "ccf", ("w",))}
+    fcor, ghat = (1e-2, -2e-2, 0.7), (0.0, 0.0, 1.0)
+    ev = K.evaluate
+    adv = ev(K.ke_advection_ccc, g, "ccc", vel)
+    wb = ev(K.ke_buoyancy_ccc, g, "ccc", vel, ghat, f["b"])
+    dif = ev(K.ke_stress_ccc, g, "ccc", cl, None, None, {**vel, "b": f["b"]}, None)
+    frc = ev(K.ke_forcing_ccc, g, "ccc", forcings, None, {**vel, "b": f["b"]})
+    cor = (ev(K.ix_caa, g, "ccc", K.psif, f["u"], K.x_f_cross_U, fcor, vel) + ev(K.iy_aca, g, "ccc", K.psif, f["v"], K.y_f_cross_U, fcor, vel) +
+           ev(K.iz_aac, g, "ccc", K.psif, f["w"], K.z_f_cross_U, fcor, vel))
+    got = _ke_tendency(g, cl, f, coriolis=fcor, buoyancy=(ghat, "b"), forcings=forcings)
+    want = -adv + wb - cor - dif + frc
+    scale = np.abs(adv).max() + np.abs(dif).max() + np.abs(wb).max()
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-12 * scale)
+    assert np.abs(cor).max() > 1e-3 and np.abs(got).max() > 1e-2
+    # hydrostatic split: w loses its buoyancy term, u and v feel -∇ₕ pHY′
+    zero = OField(g, "ccf").set(0.0).fill_halo()
+    wb_h = ev(K.ke_buoyancy_ccc, g, "ccc", {"u": f["u"], "v": f["v"], "w": zero}, ghat, f["b"])     # horizontal part (zero here)
+    pr_h = ev(K.ke_pressure_ccc, g, "ccc", {"u": f["u"], "v": f["v"], "w": zero}, f["p"])
+    got_h = _ke_tendency(g, cl, f, coriolis=fcor, buoyancy=(ghat, "b"), pHY=f["p"], forcings=forcings)
+    np.testing.assert_allclose(got_h, -adv + wb_h - cor - pr_h - dif + frc, rtol=0, atol=1e-12 * (scale + np.abs(pr_h).max()))
+
+
+def test_ke_tendency_of_uniform_flow_on_an_f_plane_vanishes():
+    """A uniform horizontal flow has no advection, stress or pressure tendency, and the Coriolis force does no work:
+    x_f_cross_U = -f v₀, y_f_cross_U = f u₀  =>  uᵢGᵢ = u₀ f v₀ - v₀ f u₀ = 0, while each part is f u₀ v₀."""
+    g = regular_grid()
+    u, v, w = velocities(g, 2.0, 3.0, 0.0)
+    b = OField(g, "ccc").set(0.0).fill_halo()
+    f = {"u": u, "v": v, "w": w, "b": b}
+    got = _ke_tendency(g, K.Closure(nu=1e-3, kappa=1e-3), f, coriolis=(0.0, 0.0, 0.5))
+    assert np.abs(got).max() <= 1e-15
+    vel = {"u": u, "v": v, "w": w}
+    part = K.evaluate(K.ix_caa, g, "ccc", K.psif, u, K.x_f_cross_U, (0.0, 0.0, 0.5), vel)
+    np.testing.assert_allclose(part, -0.5 * 2.0 * 3.0, rtol=1e-14)
+
+
+@pytest.mark.parametrize("gname", GRIDS)
+def test_smagorinsky_viscosity_of_a_linear_shear(gname):
+    """u = S z: ΣᵢⱼΣᵢⱼ = S²/2 (test/test_canonical_flows.jl:130-146 pins |S|), so νₑ = (C Δᶠ)² S with Δᶠ = ∛(ΔxΔyΔz); on a
+    linear stratification b = N² z the Lilly factor is ς = √(1 - Cb N²/(Pr S²/2)), zero once Cb N² ≥ Pr S²/2."""
+    g = GRIDS[gname]()
+    S, N2, C = 2.0, 0.5, 0.16
+    u, v, w = velocities(g, lambda x, y, z: S * z)
+    b = OField(g, "ccc").set(lambda x, y, z: N2 * z).fill_halo()
+    i, j, k = IDX
+    delta = np.cbrt(g.Dx("ccc", i + 1, j + 1, k + 1) * g.Dy("ccc", i + 1, j + 1, k + 1) * g.Dz("ccc", i + 1, j + 1, k + 1))
+    rtol = 1e-12 if gname == "regular" else 0.06          # the stretched grid's tolerance for shear diagnostics (as for ε above)
+    nu = K.evaluate(K.smagorinsky_nu_ccc, g, "ccc", u, v, w, b, C)
+    assert nu[IDX] == pytest.approx((C * delta) ** 2 * S, rel=rtol)
+    nu_b = K.evaluate(K.smagorinsky_nu_ccc, g, "ccc", u, v, w, b, C, 1.0, 1.0)
+    if gname == "regular":
+        assert nu_b[IDX] == pytest.approx((C * delta) ** 2 * S * np.sqrt(1 - N2 / (S ** 2 / 2)), rel=1e-12)
+    assert np.all(nu_b <= nu + 1e-18)
+    nu_stable = K.evaluate(K.smagorinsky_nu_ccc, g, "ccc", u, v, w, b, C, 100.0, 1.0)
+    assert nu_stable[IDX] == 0.0
+    # unstable stratification is clipped (N²⁺ = max(0, N²)): no enhancement
+    b_un = OField(g, "ccc").set(lambda x, y, z: -N2 * z).fill_halo()
+    np.testing.assert_array_equal(K.evaluate(K.smagorinsky_nu_ccc, g, "ccc", u, v, w, b_un, C, 1.0, 1.0), nu)
+
+
 def test_richardson_and_ertel_pv_known_answers():
     """test/test_active_tracer_diagnostics.jl:24-80: u = S z + S y, b = N² z  =>
     Ri[3,3,3] = N²/S², EPV[3,3,3] = N² (f_z - S)."""

@@ -108,3 +108,34 @@ def test_windows_and_split_plans():
     for nm, integ in zip(names, grp.integrals()):
         _, _, want, loc = c2[nm]
         assert abs(integ - K.integral(want, st2.og, loc)) <= 1e-12 * integral_scale(st2.og, want, loc), nm
+
+
+@pytest.mark.parametrize("stretched", [False, True], ids=["regular", "stretched"])
+def test_smagorinsky_viscosity_computed_on_the_device_feeds_the_dissipation(stretched):
+    """with closure = SmagorinskyLilly the eddy viscosity is a computed Field of the library
+    (OCB_DIAG_NU_SMAG) that every diagnostic refreshes first -- no nu_e array is handed in.  eps and |S| then run on the
+    velocity-gradient kernel and must equal the oracle's eps with the oracle's own Smagorinsky viscosity."""
+    from oracle.grid import OField
+    st = State(size=(40, 24, 18), stretched=stretched, device="cuda")
+    sm = ocb.SmagorinskyLilly(C=0.16, Cb=1.0, Pr=0.8)
+    m = st.model(closure=sm)
+    assert m.closure_fields.nu_e is sm.nu_e and sm.kappa_scale == (1.25,)
+    eps = ocb.Field(ocb.KineticEnergyEquation.DissipationRate(m))
+    smod = ocb.Field(ocb.FlowDiagnostics.StrainRateTensorModulus(m))
+    grp = ocb.FusedDiagnostics(eps, smod)
+    grp.compute(time=1.0)
+    torch.cuda.synchronize()
+    assert grp.plan.variant == 3
+    og = st.og
+    onu = OField(og, "ccc")
+    onu.interior[...] = K.evaluate(K.smagorinsky_nu_ccc, og, "ccc", st.ou, st.ov, st.ow, st.ob, 0.16, 1.0, 0.8)
+    onu.fill_halo()
+    np.testing.assert_allclose(sm.nu_e.interior_ijk(), onu.interior, rtol=1e-12, atol=1e-22)
+    want = K.evaluate(K.viscous_dissipation_rate_ccc, og, "ccc", None, st.ofields(), {"closure": K.Closure(nu=onu, Pr=0.8)})
+    check_case(st, "DissipationRate", eps.interior_ijk(), want)
+    # the state evolves: the next compute refreshes the viscosity before the sweep
+    st.u.data.mul_(1.5)
+    grp.compute(time=2.0)
+    torch.cuda.synchronize()
+    assert float(sm.nu_e.interior.max()) > 0 and not np.allclose(sm.nu_e.interior_ijk(), onu.interior)
+    assert m.compute_diffusivities(time=3.0).nu_e is sm.nu_e
