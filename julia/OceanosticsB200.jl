@@ -44,6 +44,7 @@ const OCB_REQ_PERTURBATION = Int32(1)
 const OCB_REQ_TENSOR_DIM1, OCB_REQ_TENSOR_DIM2, OCB_REQ_TENSOR_DIM3 = Int32(1 << 4), Int32(1 << 5), Int32(1 << 6)
 const OCB_REQ_COLLOCATED = Int32(1 << 7)
 const OCB_REQ_CARRIED_HEIGHT = Int32(1 << 8)
+const OCB_REQ_HYDROSTATIC_SPLIT = Int32(1 << 9)
 const OCB_FILTER_BOX, OCB_FILTER_GAUSSIAN, OCB_FILTER_GAUSSIAN_STRETCHED = Int32(0), Int32(1), Int32(2)
 const OCB_POLICY_PERIODIC, OCB_POLICY_SHRINK, OCB_POLICY_EDGE, OCB_POLICY_CONSTANT = Int32(0), Int32(1), Int32(2), Int32(3)
 const OCB_BPE_THREE_DIMENSIONAL_SORT, OCB_BPE_HEAVISIDE_INTEGRAL = Int32(0), Int32(1)
@@ -121,6 +122,7 @@ struct OcbSweepInputs
     f_dir::Float64
     ghat::NTuple{3,Float64}
     ro_bg::NTuple{6,Float64}
+    les::NTuple{4,Float64}
 end
 
 struct OcbFilterPass
@@ -250,11 +252,11 @@ mutable struct Slots
     u; v; w; b; p; U; V; W; B
     aux::Vector{Any}
     closure::OcbClosure
-    f::NTuple{3,Float64}; dir::NTuple{3,Float64}; f_dir::Float64; ghat::NTuple{3,Float64}; ro_bg::NTuple{6,Float64}
+    f::NTuple{3,Float64}; dir::NTuple{3,Float64}; f_dir::Float64; ghat::NTuple{3,Float64}; ro_bg::NTuple{6,Float64}; les::NTuple{4,Float64}
     flags::Int32
 end
 Slots() = Slots(nothing, nothing, nothing, nothing, nothing, nothing, nothing, nothing, nothing, Any[nothing for _ in 1:OCB_N_AUX],
-                NO_CLOSURE, (0.0, 0.0, 0.0), (0.0, 0.0, 1.0), 0.0, (0.0, 0.0, 1.0), ntuple(_ -> 0.0, 6), Int32(0))
+                NO_CLOSURE, (0.0, 0.0, 0.0), (0.0, 0.0, 1.0), 0.0, (0.0, 0.0, 1.0), ntuple(_ -> 0.0, 6), (0.0, 0.0, 0.0, 0.0), Int32(0))
 function velocities!(s::Slots, u, v, w)
     (s.u, U), (s.v, V), (s.w, W) = perturbation_split(u), perturbation_split(v), perturbation_split(w)
     if U !== nothing || V !== nothing || W !== nothing
@@ -272,7 +274,7 @@ function tracer!(s::Slots, c)
 end
 descriptor(s::Slots) = OcbSweepInputs(ocb_field(s.u), ocb_field(s.v), ocb_field(s.w), ocb_field(s.b), ocb_field(s.p), ocb_field(s.U),
                                       ocb_field(s.V), ocb_field(s.W), ocb_field(s.B), ntuple(a -> ocb_field(s.aux[a]), OCB_N_AUX), s.closure,
-                                      s.f, s.dir, s.f_dir, s.ghat, s.ro_bg)
+                                      s.f, s.dir, s.f_dir, s.ghat, s.ro_bg, s.les)
 field_arguments(s::Slots) = filter(x -> x isa Field, Any[s.u, s.v, s.w, s.b, s.p, s.U, s.V, s.W, s.B, s.aux...])
 ghat(buoyancy) = buoyancy === nothing ? (0.0, 0.0, 1.0) : map(x -> -Float64(x), Tuple(buoyancy.gravity_unit_vector))   # ĝ = -gravity unit vector
 tracer_index(::Val{id}) where id = id
@@ -378,10 +380,9 @@ const DIAG = Dict{Any,Tuple{Symbol,Function}}(
 DIAG[SFKEq.subfilter_ke_dissipation_rate_ccc] = (:SFEPS, a -> subfilter_dissipation_slots(a[1]))
 DIAG[FKEq.cross_scale_ke_flux_ccc] = (:PI, a -> cross_scale_flux_slots(a[1]))
 
-"Centered second order is evaluated by the budget kernel and WENO(order = 5) by the generic kernel; anything else stays with Oceananigans."
-advection_supported(adv) = adv isa Oceananigans.Advection.Centered || adv isa Oceananigans.Advection.WENO ||
-    throw(UnsupportedByLibrary("advection scheme $(nameof(typeof(adv)))"))
-advection_code(adv) = adv isa Oceananigans.Advection.WENO ? Int32(1) : Int32(0)
+"Centered second order is what the library restates; any other scheme keeps Oceananigans' own `compute!` (UnsupportedByLibrary)."
+advection_supported(adv) = (adv isa Oceananigans.Advection.Centered && Oceananigans.Advection.required_halo_size_x(adv) == 1) ||
+    throw(UnsupportedByLibrary("advection scheme $(summary(adv)): only Centered(order = 2) is evaluated by the library"))
 
 "A lazy argument (`sum(model.pressures)`, `u - U` handed to a diagnostic that takes no perturbation flag) is materialised once and refreshed with the other arguments."
 materialized(x::Field) = x
@@ -397,7 +398,7 @@ function forcing_field(F, forced::Field, clock, model_fields)
 end
 
 # c∂ₜcᶜᶜᶜ (TracerVarianceEquation.jl:70-88) and uᵢGᵢᶜᶜᶜ (KineticEnergyEquation.jl:120-142): NonhydrostaticModel without
-# background fields, immersed boundaries, Stokes drift or biogeochemistry; Centered(order = 2) or WENO(order = 5) advection
+# background fields, immersed boundaries, Stokes drift or biogeochemistry; Centered(order = 2) advection
 function tendency_slots_tracer(a)
     id, name, advection, closure, immersed, buoyancy, bgc, background, velocities, tracers, aux, K, clock, forcing = a
     (immersed === nothing && bgc === nothing && all(isnothing, values(background.tracers))) ||
@@ -406,7 +407,6 @@ function tendency_slots_tracer(a)
     c = tracers[tracer_index(name isa Val ? id : id)]
     s = with_closure(tracer!(velnt(velocities), c), closure, K, tracer_index(id))
     s.aux[1] = forcing_field(forcing, c, clock, merge(velocities, tracers))
-    s.ro_bg = (Float64(advection_code(advection)), 0.0, 0.0, 0.0, 0.0, 0.0)      # ro_bg[0] carries the advection scheme for the tendency terms
     return s
 end
 function tendency_slots_momentum(a)
@@ -419,11 +419,12 @@ function tendency_slots_momentum(a)
     if buoyancy !== nothing
         s.b = tracers.b; s.ghat = ghat(buoyancy)
     end
-    s.p = pHY                                                                    # hydrostatic pressure anomaly (nothing -> ZeroField)
+    if pHY !== nothing                                                           # hydrostatic pressure anomaly: ∇ₕ pHY′ in u, v; no buoyancy in w
+        s.p = pHY; s.flags |= OCB_REQ_HYDROSTATIC_SPLIT
+    end
     mf = merge(velocities, tracers)
     s.aux[1:3] = [forcing_field(forcing.u, velocities.u, clock, mf), forcing_field(forcing.v, velocities.v, clock, mf),
                   forcing_field(forcing.w, velocities.w, clock, mf)]
-    s.ro_bg = (Float64(advection_code(advection)), 0.0, 0.0, 0.0, 0.0, 0.0)
     return s
 end
 
@@ -754,8 +755,7 @@ end
 "νₑ = (C Δᶠ)² √(2 |S|² ς(N²/|S|²)) written into `νₑ` by the library (OCB_DIAG_NU_SMAG); `closure` carries C, Cb and Pr."
 function compute_smagorinsky_viscosity!(νₑ::Field, closure, velocities, b)
     s = velnt(velocities); s.b = b
-    s.ro_bg = (Float64(closure.coefficient isa Number ? closure.coefficient : closure.C), Float64(something(closure.Cb, 0.0)),
-               Float64(closure.Pr isa NamedTuple ? first(closure.Pr) : closure.Pr), 0.0, 0.0, 0.0)
+    s.les = (Float64(closure.C), Float64(something(closure.Cb, 0.0)), Float64(closure.Pr isa NamedTuple ? first(closure.Pr) : closure.Pr), 0.0)
     req = OcbRequest(diag_id(:NU_SMAG), Int32(0), devptr(parent(νₑ)), i32(halo_size(νₑ.grid)), i64(strides(parent(νₑ))), (0, 0, 0), (0, 0, 0), (1, 1, 1), Int32(-1))
     handle = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:ocb_plan_create, lib), Cint, (Ref{OcbGrid}, Ref{OcbSweepInputs}, Ref{OcbRequest}, Int32, Ref{Ptr{Cvoid}}), ocb_grid(νₑ.grid), descriptor(s), req, Int32(1), handle))
