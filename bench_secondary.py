@@ -37,6 +37,23 @@ def run_secondary(ocb, torch, run, peak, steps=5):
     from bench import budget_ops, make_state
     dev = run.device
     out = {"peak_GBps": peak, "timing": f"CUDA events, 3 warm-up + {steps} timed executions each"}
+    # ---- the headline workload plus the TKE budget about U(z), V(z), W(z): north_star's "TKE + KE + tracer-variance" plan -------
+    try:
+        m = run.m
+        U, V, W = (ocb.average_xy(f) for f in (m.velocities.u, m.velocities.v, m.velocities.w))
+        TKE, KE = ocb.TurbulentKineticEnergyEquation, ocb.KineticEnergyEquation
+        ops = budget_ops(ocb, m) + [TKE.ShearProductionRate(m, U=U, V=V, W=W), KE.DissipationRate(m, U=U, V=V, W=W),
+                                    TKE.TurbulentKineticEnergy(m, U=U, V=V, W=W)]
+        grp = ocb.FusedDiagnostics(*[ocb.Integral(o) for o in ops])
+        cells = run.cells_local
+        ms = _timed(torch, grp.plan.execute, reps=steps)
+        out["config3A_tke_ke_tracer_variance"] = _entry(
+            ms, cells, grp.plan.algorithmic_bytes / cells, peak, variant=VARIANTS.get(grp.plan.variant), launches=grp.plan.n_launches,
+            workload="1024^3 F64: KE budget {K, ADV, PR, u_i b_i, eps} + tracer variance {chi, 2c div F} + TKE budget about "
+                     "U(z), V(z), W(z) {shear production, eps(u - U), TKE}: 10 volume integrals, one sweep", integrals=grp.integrals())
+        del grp, ops, U, V, W
+    except Exception as e:  # pragma: no cover
+        out["config3A_tke_ke_tracer_variance"] = {"error": repr(e)[:300]}
     # ---- config 3B: the headline workload with the 7 terms also written as fields (96 B/cell) ---------------------------
     try:
         ops = budget_ops(ocb, run.m)

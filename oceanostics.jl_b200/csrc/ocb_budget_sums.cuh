@@ -33,8 +33,13 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
   using G = Geo<NW, RY>;
   constexpr int TILE = sums_tile_elems(TWK, G::TR);
   constexpr bool H_K = MASK & (1 << FD_K), H_ADV = MASK & (1 << FD_ADV), H_PR = MASK & (1 << FD_PR), H_WB = MASK & (1 << FD_WB),
-                 H_EPS = MASK & (1 << FD_EPS), H_CHI = MASK & (1 << FD_CHI), H_CDF = MASK & (1 << FD_CDF);
-  constexpr bool NEED_B = H_WB || H_CHI || H_CDF, NEED_P = H_PR, NEED_S = H_EPS || H_ADV;
+                 H_EPS = MASK & (1 << FD_EPS), H_CHI = MASK & (1 << FD_CHI), H_CDF = MASK & (1 << FD_CDF),
+                 H_SP = MASK & (1 << FD_SP), H_EPSP = MASK & (1 << FD_EPSP), H_TKE = MASK & (1 << FD_TKE);
+  // PZ: terms about horizontal-mean profiles U(z), V(z), W(z) (the TKE budget): shear production (its z part -- the x and y
+  // parts vanish for profiles), the dissipation rate of u - U (only the z differences of the strains change, by per-plane
+  // constants) and the turbulent kinetic energy
+  constexpr bool PZ = H_SP || H_EPSP || H_TKE;
+  constexpr bool NEED_B = H_WB || H_CHI || H_CDF, NEED_P = H_PR, NEED_S = H_EPS || H_ADV || H_EPSP;
   constexpr int NF = 3 + (NEED_B ? 1 : 0) + (NEED_P ? 1 : 0);
   constexpr int F_B = 3, F_P = NEED_B ? 4 : 3;
 
@@ -137,6 +142,12 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
   double aPx = 0.0, aPy = 0.0, aPz = 0.0;                  // u dx p | v dy p | w dz p
   double aW = 0.0;                                         // w (b_{k-1} + b_k)
   double aCx = 0.0, aCy = 0.0, aCz = 0.0, aD = 0.0;        // (dx b)^2 | (dy b)^2 | (dz b)^2 | b lap(b)
+  double aEeP = 0.0, aEzP = 0.0;                           // the same as aEe, aEz for the strains of u - U
+  double aKP = 0.0;                                        // (u-U)^2 + (v-V)^2 + (w-W)^2 at their faces
+  // shear production, summed by faces: sum_cells ubar' wbar' GU_k = 1/4 sum_{x faces, z faces n} (w'_{i-1} + w'_i)_n (GU_n u'_n + GU_{n-1} u'_{n-1})
+  // (x periodic; ubar', wbar' the two-point means to the cell centre, GU_k = (U_{k+1} - U_{k-1})/2 the undivided mean shear at cell k),
+  // likewise for v with the y faces, and sum_cells (w'^2)bar GW_k = 1/2 sum_{z faces n} w'_n^2 (GW_n + GW_{n-1}), GW_k = W_{k+1} - W_k
+  double aSuv = 0.0, aSw = 0.0;
 
   int s = 0;
   uint32_t phase = 0;
@@ -168,6 +179,16 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
       const bool in0 = n >= P.kz_lo && n <= P.kz_hi, in1 = (n - 1) >= P.kz_lo && (n - 1) <= P.kz_hi, in2 = (n - 2) >= P.kz_lo && (n - 2) <= P.kz_hi;
       const bool pfast = own && in0 && in1 && in2;
       const double g0 = (own && in0) ? 1.0 : 0.0, g1 = (own && in1) ? 1.0 : 0.0, g2 = (own && in2) ? 1.0 : 0.0;
+      // mean-flow profiles around this plane (uniform loads; a missing profile is a ZeroField)
+      double Un = 0.0, Un1 = 0.0, Vn = 0.0, Vn1 = 0.0, Wn = 0.0, dUz = 0.0, dVz = 0.0, dWz = 0.0;
+      double GUc = 0.0, GUp = 0.0, GVc = 0.0, GVp = 0.0, GWc = 0.0, GWp = 0.0;
+      if (PZ) {
+        if (P.Uz) { const double a = __ldg(P.Uz + n + 1), d = __ldg(P.Uz + n - 2); Un = __ldg(P.Uz + n); Un1 = __ldg(P.Uz + n - 1);
+                    GUc = 0.5 * (a - Un1); GUp = 0.5 * (Un - d); dUz = Un - Un1; }
+        if (P.Vz) { const double a = __ldg(P.Vz + n + 1), d = __ldg(P.Vz + n - 2); Vn = __ldg(P.Vz + n); Vn1 = __ldg(P.Vz + n - 1);
+                    GVc = 0.5 * (a - Vn1); GVp = 0.5 * (Vn - d); dVz = Vn - Vn1; }
+        if (P.Wz) { const double a = __ldg(P.Wz + n + 1), d = __ldg(P.Wz + n - 1); Wn = __ldg(P.Wz + n); GWc = a - Wn; GWp = Wn - d; dWz = GWp; }
+      }
       // one row of this thread at step n.  FAST (compile-time tag): every class weight is the interior one
       auto do_row = [&](auto fast_tag, const int r) {
         constexpr bool FAST = decltype(fast_tag)::value;
@@ -204,7 +225,21 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
           lap = fma(-dbz, rdz2, CDacc[r]);                 // Laplacian (sign of div q) of the cell below, closed by this face
           CDacc[r] = fma(dbz, rdz2, cdxy);
         }
+        // perturbations about the profiles: this plane's (u', v' at level n, w' at face n) and the previous plane's u', v'
+        const double ucq = uc[r] - Un, vcq = vc[r] - Vn, wcq = wc[r] - Wn, upq = up[r] - Un1, vpq = vp[r] - Vn1;
+        const double S13q = H_EPSP ? fma(-rdz, dUz, S13) : 0.0, S23q = H_EPSP ? fma(-rdz, dVz, S23) : 0.0, dwzq = dwz - dWz;
         if (FAST) {
+          if (H_EPSP) {
+            aEeP = fma(S12, S12, aEeP); aEeP = fma(S13q, S13q, aEeP); aEeP = fma(S23q, S23q, aEeP);
+            aEzP = fma(dwzq, dwzq, aEzP);
+          }
+          if (H_EPSP && !H_EPS) { aEx = fma(ax, ax, aEx); aEy = fma(ay, ay, aEy); }
+          if (H_TKE) { aKP = fma(ucq, ucq, aKP); aKP = fma(vcq, vcq, aKP); aKP = fma(wcq, wcq, aKP); }
+          if (H_SP) {
+            aSuv = fma((ww - Wn) + wcq, fma(GUc, ucq, GUp * upq), aSuv);
+            aSuv = fma((ws - Wn) + wcq, fma(GVc, vcq, GVp * vpq), aSuv);
+            aSw = fma(wcq * wcq, GWc + GWp, aSw);
+          }
           if (H_EPS) {
             aEe = fma(S12, S12, aEe); aEe = fma(S13, S13, aEe); aEe = fma(S23, S23, aEe);
             aEx = fma(ax, ax, aEx); aEy = fma(ay, ay, aEy); aEz = fma(dwz, dwz, aEz);
@@ -227,7 +262,20 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
           const double hz = 0.5 * (g0 + g1), hzp = 0.5 * (g1 + g2);        // z faces n and n-1
           if (H_EPS) {
             aEe = fma(hy * g0 * S12, S12, aEe); aEe = fma(al * hz * S13, S13, aEe); aEe = fma(hy * hz * S23, S23, aEe);
-            aEx = fma(al * g0 * ax, ax, aEx); aEy = fma(al * g0 * ay, ay, aEy); aEz = fma(al * g1 * dwz, dwz, aEz);
+            aEz = fma(al * g1 * dwz, dwz, aEz);
+          }
+          if (H_EPS || H_EPSP) { aEx = fma(al * g0 * ax, ax, aEx); aEy = fma(al * g0 * ay, ay, aEy); }
+          if (H_EPSP) {
+            aEeP = fma(hy * g0 * S12, S12, aEeP); aEeP = fma(al * hz * S13q, S13q, aEeP); aEeP = fma(hy * hz * S23q, S23q, aEeP);
+            aEzP = fma(al * g1 * dwzq, dwzq, aEzP);
+          }
+          if (H_TKE) { aKP = fma(al * g0 * ucq, ucq, aKP); aKP = fma(hy * g0 * vcq, vcq, aKP); aKP = fma(al * hz * wcq, wcq, aKP); }
+          if (H_SP) {
+            // x faces belong to one row; a y face j to the cells j-1 (weight be) and j (weight al); the part with GU_n to the
+            // cells of plane n (g0), the part with GU_{n-1} to those of plane n-1 (g1)
+            aSuv = fma(al * ((ww - Wn) + wcq), fma(g0 * GUc, ucq, g1 * GUp * upq), aSuv);
+            aSuv = fma(fma(be, ws - Wn, al * wcq), fma(g0 * GVc, vcq, g1 * GVp * vpq), aSuv);
+            aSw = fma(al * wcq * wcq, fma(g0, GWc, g1 * GWp), aSw);
           }
           if (H_ADV) {
             // the by-parts weights of a window edge: the boundary face keeps the momentum on the window's side only
@@ -281,6 +329,9 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
   acc[FD_EPS] = P.nu * (aEe + 2.0 * (rdx2 * aEx + rdy2 * aEy + rdz2 * aEz));
   acc[FD_CHI] = 2.0 * P.kappa * (rdx2 * aCx + rdy2 * aCy + rdz2 * aCz);
   acc[FD_CDF] = 2.0 * P.kappa * aD;
+  acc[FD_EPSP] = P.nu * (aEeP + 2.0 * (rdx2 * aEx + rdy2 * aEy + rdz2 * aEzP));
+  acc[FD_TKE] = 0.5 * aKP;
+  acc[FD_SP] = -rdz * (0.25 * aSuv + 0.5 * aSw);
   if (P.nslots > 0) {
     const unsigned FULLMASK = 0xffffffffu;
 #pragma unroll

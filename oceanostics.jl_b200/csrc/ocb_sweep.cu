@@ -239,15 +239,18 @@ static int finish_plan(ocb_plan* pl, const ocb_grid* grid, const ocb_sweep_input
     if (ocb_fused_handles_diag(reqs[r].diag) && !(eps_with_moduli && reqs[r].diag == OCB_DIAG_EPS)) fr[nf++] = reqs[r];
     else gr[ng++] = reqs[r];
   }
-  for (int attempt = 0; attempt < 2 && nf > 0 && !pl->fused; ++attempt) {
-    if (attempt == 1) {
-      // the budget kernel declined the set: retry without the potential-vorticity term (its envelope is narrower)
+  for (int attempt = 0; attempt < 3 && nf > 0 && !pl->fused; ++attempt) {
+    if (attempt >= 1) {
+      // the budget kernels declined the set: retry without the term with the narrowest envelope -- first the potential
+      // vorticity, then the turbulent kinetic energy (class-sum kernel only)
+      const int drop = attempt == 1 ? OCB_DIAG_EPV : OCB_DIAG_TKE;
       int kept = 0, moved = 0;
       for (int r = 0; r < nf; ++r) {
-        if (fr[r].diag == OCB_DIAG_EPV) { gr[ng++] = fr[r]; ++moved; } else fr[kept++] = fr[r];
+        if (fr[r].diag == drop) { gr[ng++] = fr[r]; ++moved; } else fr[kept++] = fr[r];
       }
       nf = kept;
-      if (!moved || nf == 0) break;
+      if (!moved) continue;
+      if (nf == 0) break;
     }
     SweepParams<T> Pf;
     rc = ocb_build_sweep_params<T>(grid, in, fr, nf, zt, &Pf);

@@ -35,7 +35,8 @@
 
 namespace {
 
-constexpr int FD_K = 0, FD_ADV = 1, FD_PR = 2, FD_WB = 3, FD_EPS = 4, FD_CHI = 5, FD_CDF = 6, FD_SP = 7, FD_EPV = 8, FD_N = 9;
+constexpr int FD_K = 0, FD_ADV = 1, FD_PR = 2, FD_WB = 3, FD_EPS = 4, FD_CHI = 5, FD_CDF = 6, FD_SP = 7, FD_EPV = 8,
+              FD_EPSP = 9, FD_TKE = 10, FD_N = 11;   // EPSP / TKE: class-sum kernel only (the dissipation of u - U next to that of u; TKE)
 constexpr int FD_BUDGET = 0x7f;   // the seven KE / tracer-variance budget terms
 constexpr int NXCH = 8;            // exchanged quantities per column: P12, P23 | X12, e23, Fv (OUT only) | XS23, o13, o12 (EPV)
 constexpr int TW = 36;             // tile width: 32 lanes + west/east halo + 1 (the TMA box must start 16-byte aligned) -> 36
@@ -572,7 +573,7 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
       if (tid == 0) {
         double s = 0.0;
         for (int w = 0; w < NW; ++w) s += red[w];
-        const double scale[FD_N] = {SC_K, SC_ADV, SC_PR, SC_WB, SC_EPS, SC_CHI, SC_CDF, 1.0, 1.0};
+        const double scale[FD_N] = {SC_K, SC_ADV, SC_PR, SC_WB, SC_EPS, SC_CHI, SC_CDF, 1.0, 1.0, 1.0, 1.0};
         P.partial[(size_t)blockIdx.x * P.nslots + P.o[d].slot] = s * (P.V * scale[d]);
       }
     }
@@ -671,6 +672,7 @@ static int fused_diag_index(int diag) {
     case OCB_DIAG_CDIFF: return FD_CDF;
     case OCB_DIAG_SP: case OCB_DIAG_SPZ: return FD_SP;   // equal for z-profile means (the x and y parts vanish)
     case OCB_DIAG_EPV: return FD_EPV;
+    case OCB_DIAG_TKE: return FD_TKE;                    // class-sum kernel only (integrals about mean profiles)
     default: return -1;
   }
 }
@@ -714,13 +716,21 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
   int mask = 0;
   int which_out[FD_N], which_slot[FD_N];     // a diagnostic may appear twice: once as a Field, once as an Integral
   for (int d = 0; d < FD_N; ++d) which_out[d] = which_slot[d] = -1;
-  bool eps_pert = false, any_pert = false;
+  bool eps_pert = false, any_pert = false, any_outq = false;
   int sp_diag = -1, cell_req = -1, epv_top = 0;
+  // The class-sum kernel (integrals only, x periodic, no potential vorticity) takes the dissipation of u and of u - U side by
+  // side (FD_EPS / FD_EPSP) and the turbulent kinetic energy; the cell-exact kernel one dissipation request and no TKE.
+  for (int r = 0; r < n; ++r) any_outq = any_outq || SP.req[r].out;
+  bool sums_convention = !any_outq && grid->topo[0] == OCB_PERIODIC && !getenv("OCB_FUSED_CELL_INTEGRALS");
+  for (int r = 0; r < n; ++r) if (reqs[r].diag == OCB_DIAG_EPV) sums_convention = false;
   for (int r = 0; r < n; ++r) {
-    const int d = fused_diag_index(reqs[r].diag);
+    int d = fused_diag_index(reqs[r].diag);
     if (d < 0) return OCB_OK;
     const bool pert = reqs[r].flags & OCB_REQ_PERTURBATION;
-    if (d == FD_EPV) {
+    if (d == FD_TKE) {
+      if (!sums_convention) return OCB_OK;              // (always about U, V, W: src/TurbulentKineticEnergyEquation.jl:24-30)
+      any_pert = true;
+    } else if (d == FD_EPV) {
       // the corner-owned fff term: periodic x and y, H >= 3, and the whole z extent (Nz + 1 faces on a Bounded axis)
       if (pert || grid->topo[0] != OCB_PERIODIC || grid->topo[1] != OCB_PERIODIC) return OCB_OK;
       if (grid->H[0] < 3 || grid->H[1] < 3 || grid->H[2] < 3) return OCB_OK;
@@ -731,8 +741,12 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
       if (sp_diag >= 0 && sp_diag != reqs[r].diag) return OCB_OK;
       sp_diag = reqs[r].diag;
     } else if (d == FD_EPS) {
-      if (which_out[d] >= 0 || which_slot[d] >= 0) { if (pert != eps_pert) return OCB_OK; }
-      eps_pert = pert;
+      if (sums_convention) {
+        if (pert) d = FD_EPSP;
+      } else {
+        if (which_out[d] >= 0 || which_slot[d] >= 0) { if (pert != eps_pert) return OCB_OK; }
+        eps_pert = pert;
+      }
     } else if (pert) {
       return OCB_OK;
     }
@@ -754,7 +768,7 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
     // perturbations about horizontal-mean profiles only (Average(u, dims=(1,2)) reduced fields, or ZeroField)
     if (grid->H[2] < 3) return OCB_OK;
     if (!profile_pointer(in->U, OCB_CENTER, &Uz) || !profile_pointer(in->V, OCB_CENTER, &Vz) || !profile_pointer(in->W, OCB_FACE, &Wz)) return OCB_OK;
-    mask |= 1 << FD_SP;                               // the profile-carrying kernels are the ones with the SP term
+    if (!sums_convention) mask |= 1 << FD_SP;         // cell-exact kernel: the profile-carrying variants are the ones with the SP term
   }
   if ((mask & (1 << FD_WB)) && (in->ghat[0] != 0.0 || in->ghat[1] != 0.0)) return OCB_OK;   // vertical gravity only
   bool any_out = false;
@@ -796,8 +810,7 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
   // Integrals only, x periodic, no perturbation operands: the class-sum kernel (ocb_budget_sums.cuh).
   // OCB_FUSED_CELL_INTEGRALS=1 keeps the cell-exact integral mode of ocb_budget_kernel (the two are compared in the tests);
   // OCB_SUMS_CONFIG="NW,RY,NS,MINB" picks another compiled shape of the all-terms kernel for tuning runs.
-  const bool sums = !any_out && !any_pert && !(mask & ((1 << FD_SP) | (1 << FD_EPV))) && grid->topo[0] == OCB_PERIODIC &&
-                    !getenv("OCB_FUSED_CELL_INTEGRALS");
+  const bool sums = sums_convention;
   const int njy = SP.req[0].hi[1] - SP.req[0].lo[1] + 1;
   if (sums) {
     const char* sc = getenv("OCB_SUMS_CONFIG");
@@ -805,7 +818,14 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
     if (sc) sscanf(sc, "%d,%d,%d,%d", &a, &b, &c, &d);
     const int key = a * 1000 + b * 100 + c * 10 + d;
     const bool narrow = (grid->H[0] & 1) && !getenv("OCB_SUMS_WIDE_TILES");   // every tile's first column is 16-byte aligned
-    if (!sc && njy + 1 <= 4) rc = setup_sums_pitch<ALL, 2, 2, 3, 4>(fp, narrow);          // slab-edge strips: 4-row tiles
+    constexpr int TKEB = (1 << FD_SP) | (1 << FD_EPSP) | (1 << FD_TKE);              // the TKE-budget terms about mean profiles
+    constexpr int ALLT = ALL | TKEB;                                                  // TKE + KE + tracer-variance budget: 10 integrals
+    constexpr int TKEP = TKEB | (1 << FD_PR) | (1 << FD_K);                           // TKE budget with pressure redistribution (config 2 without EPV)
+    if (mask & TKEB) {
+      if ((mask & ~TKEP) == 0) rc = setup_sums_pitch<TKEP, 4, 4, 3, 2>(fp, narrow);
+      else rc = setup_sums_pitch<ALLT, 4, 4, 3, 2>(fp, narrow);
+    }
+    else if (!sc && njy + 1 <= 4) rc = setup_sums_pitch<ALL, 2, 2, 3, 4>(fp, narrow);          // slab-edge strips: 4-row tiles
     else if (!sc && mask == (1 << FD_EPS)) rc = setup_sums_pitch<(1 << FD_EPS), 8, 3, 3, 1>(fp, narrow);
     else if (!sc && (mask & ~VEL) == 0) rc = setup_sums_pitch<VEL, 8, 3, 3, 1>(fp, narrow);
     else if (!sc && (mask & ~VELP) == 0) rc = setup_sums_pitch<VELP, 8, 3, 3, 1>(fp, narrow);

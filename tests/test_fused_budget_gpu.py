@@ -238,6 +238,60 @@ def test_tke_budget_about_mean_profiles_one_sweep():
         assert abs(a - b) <= 1e-12 * integral_scale(st.og, cases[nm][2], "ccc"), nm
 
 
+@pytest.mark.parametrize("size,seed", [((64, 44, 26), 1), ((70, 21, 40), 2), ((96, 48, 70), 3)], ids=str)
+def test_class_sum_kernel_tke_ke_and_tracer_variance_budget(size, seed):
+    """north_star's target plan -- the TKE + KE + tracer-variance budget as volume integrals -- in ONE launch of the class-sum
+    kernel: the seven KE / tracer-variance terms plus, about the horizontal-mean profiles U(z), V(z), W(z), the shear production
+    (summed over x / y / z faces), the dissipation of u - U and the turbulent kinetic energy.  Against the oracle's per-cell
+    values summed over the window, and against the generic kernel, on the whole domain and on random y / z windows."""
+    from cases import build_cases
+    st = State(size=size, device="cuda")
+    cases = {c[0]: c for c in build_cases(st, "scalar", mean="profile")}
+    names = ["KineticEnergy", "KineticEnergyAdvection", "KineticEnergyPressureRedistribution", "PotentialEnergyConversion", "DissipationRate",
+             "TracerVarianceDissipationRate", "TracerVarianceDiffusion", "ShearProductionRate", "DissipationRate_perturbation",
+             "TurbulentKineticEnergy"]
+    ops = [cases[nm][1] for nm in names]
+    Nx, Ny, Nz = size
+    V = 1.0 / (Nx * Ny * Nz)
+    rng = np.random.default_rng(seed)
+    windows = [None, (1, Ny, 1, 1), (1, 1, 1, Nz), (2, Ny - 1, 2, Nz - 1), (Ny, Ny, Nz, Nz)]
+    for _ in range(3):
+        j = sorted(rng.integers(1, Ny + 1, 2)); k = sorted(rng.integers(1, Nz + 1, 2))
+        windows.append((int(j[0]), int(j[1]), int(k[0]), int(k[1])))
+    os.environ["OCB_FUSED_KCHUNK"] = "32"
+    try:
+        for win in windows:
+            idx = None if win is None else (None, (win[0], win[1]), (win[2], win[3]))
+            jlo, jhi, klo, khi = win or (1, Ny, 1, Nz)
+            sums = ocb.FusedDiagnostics(*[ocb.Integral(o, indices=idx) for o in ops]).compute()
+            assert sums.plan.variant == 1 and sums.plan.n_launches == 2, (win, sums.plan.variant)
+            os.environ["OCB_DISABLE_FUSED"] = "1"
+            try:
+                gen = ocb.FusedDiagnostics(*[ocb.Integral(o, indices=idx) for o in ops]).compute()
+            finally:
+                os.environ.pop("OCB_DISABLE_FUSED", None)
+            assert gen.plan.variant == 0
+            for nm, a, b in zip(names, sums.integrals(), gen.integrals()):
+                w_ = cases[nm][2][:, jlo - 1:jhi, klo - 1:khi]
+                ref, scale = float(np.sum(w_)) * V, float(np.sum(np.abs(w_))) * V
+                assert abs(a - ref) <= 1e-12 * scale, (nm, win, a, ref, scale)
+                assert abs(a - b) <= 1e-12 * scale, (nm, win, a, b, scale)
+    finally:
+        os.environ.pop("OCB_FUSED_KCHUNK", None)
+    # the TKE-budget subset alone (config 2 without the potential vorticity) has its own compiled variant
+    sub = ["ShearProductionRate", "DissipationRate_perturbation", "KineticEnergyPressureRedistribution", "TurbulentKineticEnergy"]
+    g = ocb.FusedDiagnostics(*[ocb.Integral(cases[nm][1]) for nm in sub]).compute()
+    assert g.plan.variant == 1
+    for nm, a in zip(sub, g.integrals()):
+        w_ = cases[nm][2]
+        assert abs(a - float(np.sum(w_)) * V) <= 1e-12 * float(np.sum(np.abs(w_))) * V, nm
+    # no mean flow at all (ZeroField means): TKE is K
+    cz = {c[0]: c for c in build_cases(st, "scalar", mean="none")}
+    gz = ocb.FusedDiagnostics(*[ocb.Integral(cz[nm][1]) for nm in ("TurbulentKineticEnergy", "KineticEnergy")]).compute()
+    a, b = gz.integrals()
+    assert abs(a - b) <= 1e-13 * abs(b)
+
+
 def test_split_plan_budget_kernel_plus_generic_kernel():
     """Requests outside the pipelined kernel's set (Richardson number), or outside a variant's envelope (EPV next to the
     advection term), go to the generic kernel of the same plan (variant 2) and fill their own integral slots."""
