@@ -66,6 +66,8 @@ def DissipationRate(model, U=None, V=None, W=None, location=CCC):
     validate_location(location, "DissipationRate")
     ops = perturbation_velocities(model, U, V, W)
     pert = any(x is not None for x in (U, V, W))
+    if not pert:        # no mean flow: the request does not read U, V, W, so it can share a sweep with siblings that carry means
+        ops = {k: v for k, v in ops.items() if k in ("u", "v", "w")}
     return KernelFunctionOperation("EPS", model.grid, SweepOperands(closure=model.closure, **ops),
                                    flags=_lib.OCB_REQ_PERTURBATION if pert else 0, name="KineticEnergyDissipationRate",
                                    computes="kinetic energy dissipation rate  ε = ∂ⱼuᵢ·τᵢⱼ")
