@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(RS_THREADS, 3) rs_scatter(const K* __restrict_
   __shared__ uint32_t wtot[RS_WARPS];
   __shared__ K stage[RS_TILE];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int d = lane; d < 256; d += 32) wcount[warp][d] = 0;
+  for (int d = lane; d < 256; d += 32) { wcount[warp][d] = 0; reinterpret_cast<uint32_t*>(stage)[warp * 256 + d] = 0; }
   __syncwarp();
   const long long tbase = (long long)blockIdx.x * RS_TILE;
   const long long wbase = tbase + (long long)warp * (RS_ITEMS * 32);
@@ -102,18 +102,25 @@ __global__ void __launch_bounds__(RS_THREADS, 3) rs_scatter(const K* __restrict_
     const long long t = wbase + r * 32 + lane;
     key[r] = t < n ? __ldg(keys_in + t) : (K)~(K)0;
   }
+  // Ranking: lanes of a round that hold the same digit must learn of each other (their ranks follow the lane order: the sort
+  // is stable).  MATCH.ANY does that in hardware by looping over the distinct values of the warp -- ~30 of them with 8-bit
+  // digits, which made these 16 rounds the whole cost of a pass (issue slots 12 % busy, profiles/r1_summary.md).  Instead every
+  // lane ORs its bit into a per-warp, per-digit mask word in shared memory (the staging buffer, idle until the ranks are known)
+  // and reads the word back: one shared atomic and two loads per round.
+  uint32_t (*wmask)[256] = reinterpret_cast<uint32_t (*)[256]>(stage);
 #pragma unroll
   for (int r = 0; r < RS_ITEMS; ++r) {
     const long long t = wbase + r * 32 + lane;
     const bool ok = t < n;
-    const uint32_t dig = ok ? ((uint32_t)(key[r] >> shift) & 255u) : 256u;    // 256: out of range, matches only other padding
-    const unsigned peers = __match_any_sync(0xffffffffu, dig);
-    uint32_t prev = 0;
-    if (ok) {
-      prev = wcount[warp][dig];
-      __syncwarp(peers);
-      if ((peers & lt) == 0) wcount[warp][dig] = prev + __popc(peers);       // the lowest lane of each digit group updates
-    }
+    const uint32_t dig = ok ? ((uint32_t)(key[r] >> shift) & 255u) : 0u;
+    volatile uint32_t* mp = &wmask[warp][dig];
+    volatile uint32_t* cp = &wcount[warp][dig];
+    if (ok) atomicOr(&wmask[warp][dig], 1u << lane);
+    __syncwarp();
+    const unsigned peers = ok ? *mp : 0u;
+    const uint32_t prev = ok ? *cp : 0u;
+    __syncwarp();
+    if (ok && (peers & lt) == 0) { *cp = prev + __popc(peers); *mp = 0u; }   // the lowest lane of each digit group updates and clears
     __syncwarp();
     rank[r] = prev + __popc(peers & lt);
   }
