@@ -223,14 +223,20 @@ __device__ __forceinline__ T block_scan_chunk(T (&x)[SC_ITEMS], T* sh) {
   return total;
 }
 
+// scan inputs: an array, or values formed on the fly from other arrays (in(t))
+template <class T> struct PtrInput {
+  const T* p;
+  __device__ __forceinline__ T operator()(long long t) const { return p[t]; }
+};
+
 // phase 1: chunk totals.  REV: the scan runs from the end of the array (element n-1 first).
-template <class T, int OP, bool REV>
-__global__ void __launch_bounds__(SC_THREADS) sc_chunk_totals(const T* __restrict__ in, long long n, T* __restrict__ totals) {
+template <class T, int OP, bool REV, class In>
+__global__ void __launch_bounds__(SC_THREADS) sc_chunk_totals(const In in, long long n, T* __restrict__ totals) {
   __shared__ T sh[SC_THREADS / 32];
   T x[SC_ITEMS];
   const long long base = (long long)blockIdx.x * SC_CHUNK + (long long)threadIdx.x * SC_ITEMS;
 #pragma unroll
-  for (int q = 0; q < SC_ITEMS; ++q) { const long long t = base + q; x[q] = t < n ? in[REV ? n - 1 - t : t] : sc_identity<T, OP>(); }
+  for (int q = 0; q < SC_ITEMS; ++q) { const long long t = base + q; x[q] = t < n ? in(REV ? n - 1 - t : t) : sc_identity<T, OP>(); }
   const T total = block_scan_chunk<T, OP>(x, sh);
   if (threadIdx.x == 0) totals[blockIdx.x] = total;
 }
@@ -261,14 +267,14 @@ __global__ void __launch_bounds__(SC_THREADS) sc_scan_totals(T* __restrict__ tot
   }
 }
 // phase 3: scan each chunk and combine with its prefix.  EXCL: write the exclusive scan.
-template <class T, int OP, bool REV, bool EXCL>
-__global__ void __launch_bounds__(SC_THREADS) sc_apply(const T* __restrict__ in, long long n, const T* __restrict__ totals, T* __restrict__ out) {
+template <class T, int OP, bool REV, bool EXCL, class In>
+__global__ void __launch_bounds__(SC_THREADS) sc_apply(const In in, long long n, const T* __restrict__ totals, T* __restrict__ out) {
   __shared__ T sh[SC_THREADS / 32];
   __shared__ T last[SC_THREADS];
   T x[SC_ITEMS];
   const long long base = (long long)blockIdx.x * SC_CHUNK + (long long)threadIdx.x * SC_ITEMS;
 #pragma unroll
-  for (int q = 0; q < SC_ITEMS; ++q) { const long long t = base + q; x[q] = t < n ? in[REV ? n - 1 - t : t] : sc_identity<T, OP>(); }
+  for (int q = 0; q < SC_ITEMS; ++q) { const long long t = base + q; x[q] = t < n ? in(REV ? n - 1 - t : t) : sc_identity<T, OP>(); }
   block_scan_chunk<T, OP>(x, sh);
   const T prefix = totals[blockIdx.x];
   if (EXCL) { last[threadIdx.x] = x[SC_ITEMS - 1]; __syncthreads(); }
@@ -288,14 +294,18 @@ __global__ void __launch_bounds__(SC_THREADS) sc_apply(const T* __restrict__ in,
   }
 }
 
-template <class T, int OP, bool REV, bool EXCL>
-int device_scan(const T* in, T* out, long long n, T* totals_scratch, cudaStream_t st) {
+template <class T, int OP, bool REV, bool EXCL, class In>
+int device_scan_of(const In in, T* out, long long n, T* totals_scratch, cudaStream_t st) {
   const int nchunks = (int)((n + SC_CHUNK - 1) / SC_CHUNK);
-  sc_chunk_totals<T, OP, REV><<<nchunks, SC_THREADS, 0, st>>>(in, n, totals_scratch);
+  sc_chunk_totals<T, OP, REV, In><<<nchunks, SC_THREADS, 0, st>>>(in, n, totals_scratch);
   sc_scan_totals<T, OP><<<1, SC_THREADS, 0, st>>>(totals_scratch, nchunks);
-  sc_apply<T, OP, REV, EXCL><<<nchunks, SC_THREADS, 0, st>>>(in, n, totals_scratch, out);
+  sc_apply<T, OP, REV, EXCL, In><<<nchunks, SC_THREADS, 0, st>>>(in, n, totals_scratch, out);
   OCB_CUDA(cudaGetLastError());
   return OCB_OK;
+}
+template <class T, int OP, bool REV, bool EXCL>
+int device_scan(const T* in, T* out, long long n, T* totals_scratch, cudaStream_t st) {
+  return device_scan_of<T, OP, REV, EXCL, PtrInput<T>>(PtrInput<T>{in}, out, n, totals_scratch, st);
 }
 
 template <class K>
@@ -417,6 +427,62 @@ __global__ void bpe_perm_to_int64(const uint32_t* __restrict__ perm, long long n
   if (t < n) out[t] = (int64_t)perm[t] + 1;
 }
 
+// ---- ThreeDimensionalSort on its (always uniform-volume) grid: the epilogue without the N-length temporaries -----------
+// With equal cell volumes the cumulative volume of the first m sorted cells is m dV, so the volume array, its scan, the
+// sorted-height array and the b* dz array need not exist: slot faces, slot centres and the Psi increments are formed where they
+// are used, from the slot number and the sorted keys (same expressions as slot_centers! / slot_faces / fill_reference_potential!,
+// BackgroundPotentialEnergyEquation.jl:326-348, 383-397).  Bytes per cell: 20 (keys from the field) + 24 (Psi scan) +
+// 36 + the two scattered stores, instead of 232.
+template <class T, class K>
+__global__ void bpe_keys_from_field(const T* __restrict__ b1, long long s0, long long s1, long long s2, int Nx, int Ny, long long n,
+                                    K* __restrict__ keys, uint32_t* __restrict__ idx) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;   // b1 pre-offset to index (1,1,1) -> element 0
+  if (t >= n) return;
+  const int i = (int)(t % Nx), j = (int)((t / Nx) % Ny), k = (int)(t / ((long long)Nx * Ny));
+  keys[t] = to_key(b1[i * s0 + j * s1 + k * s2]);
+  idx[t] = (uint32_t)t;
+}
+struct UniformSlots {          // faces[m] = z_bot + cum[m-1]/A with cum[m-1] = m dV  (0-based face m below slot m)
+  double z_bot, A, dV;
+  __host__ __device__ __forceinline__ double face(long long m) const { return z_bot + ((double)m * dV) / A; }
+  __host__ __device__ __forceinline__ double centre(long long t) const { return z_bot + ((double)(t + 1) * dV - dV / 2) / A; }
+};
+template <class T, class K> struct BdzOfKeys {       // b*[t] (faces[t+1] - faces[t])
+  const K* ks; UniformSlots U;
+  __device__ __forceinline__ double operator()(long long t) const { return (double)from_key(ks[t]) * (U.face(t + 1) - U.face(t)); }
+};
+template <class T, class K>
+__global__ void bpe_psi_levels_uniform(const double* __restrict__ psi_incl, const K* __restrict__ ks, long long n, int Nz, UniformSlots U,
+                                       T z0, T dz_uniform, double* __restrict__ psi_level) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= Nz) return;
+  const double zeta = (double)z0 + (double)dz_uniform * (k + 0.5);
+  long long lo = -1, hi = n + 1;      // searchsortedlast(faces, zeta), clamped to 1..n (reference_potential_function :359-368)
+  while (hi - lo > 1) { const long long mid = (lo + hi) >> 1; if (U.face(mid) <= zeta) lo = mid; else hi = mid; }
+  long long m = lo + 1;
+  m = m < 1 ? 1 : (m > n ? n : m);
+  psi_level[k] = (m - 1 ? psi_incl[m - 2] : 0.0) + (double)from_key(ks[m - 1]) * (zeta - U.face(m - 1));
+}
+template <class T, class K>
+__global__ void bpe_scatter_uniform(const uint32_t* __restrict__ perm, const K* __restrict__ ks, const double* __restrict__ psi_incl, long long n,
+                                    int Nx, int Ny, UniformSlots U, const double* __restrict__ psi_level, T* __restrict__ zstar, long long zs0,
+                                    long long zs1, long long zs2, T* __restrict__ psid, long long ps0, long long ps1, long long ps2,
+                                    int64_t* __restrict__ perm_out, T* __restrict__ bs_out) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const uint32_t cell = perm[t];
+  const int i = (int)(cell % Nx), j = (int)((cell / Nx) % Ny), k = (int)(cell / ((long long)Nx * Ny));
+  const T bs = from_key(ks[t]);
+  const T zs = (T)U.centre(t);
+  zstar[i * zs0 + j * zs1 + k * zs2] = zs;
+  if (psid) {
+    const double ps = (t ? psi_incl[t - 1] : 0.0) + (double)bs * ((double)zs - U.face(t));
+    psid[i * ps0 + j * ps1 + k * ps2] = (T)(psi_level[k] - ps);
+  }
+  if (perm_out) perm_out[t] = (int64_t)cell + 1;
+  if (bs_out) bs_out[t] = bs;
+}
+
 struct Scratch {
   cudaStream_t st;
   void* ptrs[24];
@@ -452,14 +518,58 @@ int sort_impl(const T* keys_in, T* keys_out, uint32_t* perm_out, long long n, cu
 }
 
 template <class T, class K>
+int bpe_sort3d_uniform(const ocb_grid* g, const ocb_field* b, const ocb_field* zstar, const ocb_field* psid, int64_t* perm_out, void* bs_out,
+                       cudaStream_t st) {
+  const int Nx = g->N[0], Ny = g->N[1], Nz = g->N[2];
+  const long long n = (long long)Nx * Ny * Nz;
+  Scratch S(st);
+  const int nblocks = (int)((n + RS_TILE - 1) / RS_TILE);
+  K* ka = S.get<K>(n); K* kb = S.get<K>(n);
+  uint32_t* ia = S.get<uint32_t>(n); uint32_t* ib = S.get<uint32_t>(n);
+  uint32_t* table = S.get<uint32_t>(256ull * nblocks);
+  uint32_t* tot = S.get<uint32_t>((256ull * nblocks + SC_CHUNK - 1) / SC_CHUNK + 1);
+  double* psi = S.get<double>(n);
+  double* dtot = S.get<double>((n + SC_CHUNK - 1) / SC_CHUNK + 1);
+  double* psi_level = S.get<double>(Nz);
+  if (!ka || !kb || !ia || !ib || !table || !tot || !psi || !dtot || !psi_level)
+    OCB_FAIL(OCB_ERR_ALLOC, "out of device memory for the reference-height scratch");
+  HFld<T> B, Z, P;
+  int rc = make_fld<T>(*b, &B, "b", false); if (rc != OCB_OK) return rc;
+  rc = make_fld<T>(*zstar, &Z, "zstar", false); if (rc != OCB_OK) return rc;
+  OCB_REQUIRE(B.p && Z.p, "b and zstar must be array fields");
+  P.p = nullptr; P.sx = P.sy = P.sz = 0;
+  if (psid && psid->data) { rc = make_fld<T>(*psid, &P, "psi_delta", false); if (rc != OCB_OK) return rc; }
+  const unsigned gr = (unsigned)((n + 255) / 256);
+  bpe_keys_from_field<T, K><<<gr, 256, 0, st>>>(B.p + (B.sx + B.sy + B.sz), B.sx, B.sy, B.sz, Nx, Ny, n, ka, ia);
+  K* ks; uint32_t* perm;
+  rc = radix_sort_pairs<K>(ka, ia, kb, ib, n, table, tot, nblocks, st, &ks, &perm);
+  if (rc != OCB_OK) return rc;
+  UniformSlots U;
+  U.z_bot = g->z_bottom; U.A = (g->L[0] * g->L[1] * g->L[2]) / g->L[2];
+  U.dV = (double)((T)(g->d[0] * g->d[1]) * (T)g->d[2]);               // the cell volume in the grid's precision, as the general path forms it
+  T* p1 = P.p ? (T*)P.p + (P.sx + P.sy + P.sz) : nullptr;
+  if (p1) {
+    rc = device_scan_of<double, OP_ADD, false, false, BdzOfKeys<T, K>>(BdzOfKeys<T, K>{ks, U}, psi, n, dtot, st);
+    if (rc != OCB_OK) return rc;
+    bpe_psi_levels_uniform<T, K><<<(Nz + 127) / 128, 128, 0, st>>>(psi, ks, n, Nz, U, (T)g->z_bottom, (T)g->d[2], psi_level);
+  }
+  bpe_scatter_uniform<T, K><<<gr, 256, 0, st>>>(perm, ks, psi, n, Nx, Ny, U, psi_level, (T*)Z.p + (Z.sx + Z.sy + Z.sz), Z.sx, Z.sy, Z.sz,
+                                                p1, P.sx, P.sy, P.sz, perm_out, (T*)bs_out);
+  OCB_CUDA(cudaGetLastError());
+  return OCB_OK;
+}
+
+template <class T, class K>
 int bpe_impl(const ocb_grid* g, const ocb_field* b, int method, const ocb_field* zstar, const ocb_field* psid, int64_t* perm_out, void* bs_out,
              cudaStream_t st) {
   const int Nx = g->N[0], Ny = g->N[1], Nz = g->N[2];
   const long long n = (long long)Nx * Ny * Nz;
   OCB_REQUIRE(n < (1ll << 32), "the sort payload is a 32-bit index: at most 2^32 - 1 cells");
+  if (method == OCB_BPE_THREE_DIMENSIONAL_SORT && !g->dzc && !getenv("OCB_BPE_GENERAL_EPILOGUE"))
+    return bpe_sort3d_uniform<T, K>(g, b, zstar, psid, perm_out, bs_out, st);
   Scratch S(st);
   const int nblocks = (int)((n + RS_TILE - 1) / RS_TILE);
-  T* work = S.get<T>(n); T* bs = S.get<T>(n); T* zs_sorted = S.get<T>(n);
+  T* bs = S.get<T>(n); T* zs_sorted = S.get<T>(n);
   K* ka = S.get<K>(n); K* kb = S.get<K>(n);
   uint32_t* ia = S.get<uint32_t>(n); uint32_t* ib = S.get<uint32_t>(n);
   uint32_t* table = S.get<uint32_t>(256ull * nblocks);
@@ -468,7 +578,7 @@ int bpe_impl(const ocb_grid* g, const ocb_field* b, int method, const ocb_field*
   double* dtot = S.get<double>((n + SC_CHUNK - 1) / SC_CHUNK + 1);
   double *den = nullptr, *nol = nullptr;
   if (method == OCB_BPE_HEAVISIDE_INTEGRAL) { den = S.get<double>(n); nol = S.get<double>(n); }
-  if (!work || !bs || !zs_sorted || !ka || !kb || !ia || !ib || !table || !tot || !dV || !cum || !bdz || !psi || !dtot ||
+  if (!bs || !zs_sorted || !ka || !kb || !ia || !ib || !table || !tot || !dV || !cum || !bdz || !psi || !dtot ||
       (method == OCB_BPE_HEAVISIDE_INTEGRAL && (!den || !nol)))
     OCB_FAIL(OCB_ERR_ALLOC, "out of device memory for the reference-height scratch");
   const unsigned gr = (unsigned)((n + 255) / 256);
@@ -480,8 +590,7 @@ int bpe_impl(const ocb_grid* g, const ocb_field* b, int method, const ocb_field*
   P.p = nullptr; P.sx = P.sy = P.sz = 0;
   if (psid && psid->data) { rc = make_fld<T>(*psid, &P, "psi_delta", false); if (rc != OCB_OK) return rc; }
   const T* b1 = B.p + (B.sx + B.sy + B.sz);        // element at index (1,1,1)
-  bpe_gather_interior<T><<<gr, 256, 0, st>>>(b1, B.sx, B.sy, B.sz, Nx, Ny, n, work);
-  rs_make_keys<K><<<gr, 256, 0, st>>>(work, ka, ia, n);
+  bpe_keys_from_field<T, K><<<gr, 256, 0, st>>>(b1, B.sx, B.sy, B.sz, Nx, Ny, n, ka, ia);
   K* ks; uint32_t* perm;
   rc = radix_sort_pairs<K>(ka, ia, kb, ib, n, table, tot, nblocks, st, &ks, &perm);
   if (rc != OCB_OK) return rc;

@@ -174,6 +174,87 @@ __global__ void __launch_bounds__(128) ocb_filter_slide_kernel(const __grid_cons
   }
 }
 
+// (2b) x and y passes FUSED for periodic x and y (the common horizontal case, BASELINE config 5): a thread owns one x column and
+// slides along y; for every new row it forms the x-filtered value of its column (2W+1 cached loads of consecutive addresses,
+// the division included) and pushes it into the register window of the y pass.  The intermediate field of the staged form
+// (16 B/cell of traffic and one launch) never exists.  Every output goes through exactly the staged arithmetic -- x sum in tap
+// order, division, y sum in tap order, division -- so the results are bit-identical to the two staged passes.  Periodic wrap is
+// native: rows wrap by index, columns whose stencil crosses the x boundary take per-tap wrapped loads (the edge warps only).
+template <class T, int W, bool BOX>
+__global__ void __launch_bounds__(128) ocb_filter_xy_kernel(const __grid_constant__ PassParams<T> P, int nx, int ny, int seg) {
+  constexpr int NT = 2 * W + 1;
+  const int i = P.lo[0] + blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = P.lo[2] + blockIdx.y;
+  if (i > P.hi[0]) return;
+  const int c0 = P.lo[1] + blockIdx.z * seg;
+  const int c1 = min(c0 + seg - 1, P.hi[1]);
+  if (c0 > c1) return;
+  T wtot = T(0);
+  if (!BOX) {
+#pragma unroll
+    for (int t = 0; t < NT; ++t) wtot += P.weights[t] * T(1);
+  }
+  const T* plane = P.src + (long long)k * P.ss[2];
+  T* out = P.dst + i * P.ds[0] + (long long)k * P.ds[2];
+  const bool xin = i - W >= 1 && i + W <= nx;
+  // the x-filtered value of column i in row r (1-based, already wrapped into 1..ny)
+  auto xrow = [&](int r) -> T {
+    const T* row = plane + (long long)r * P.ss[1];
+    T s = T(0);
+    if (xin) {
+      const T* q = row + (i - W);
+#pragma unroll
+      for (int t = 0; t < NT; ++t) s = BOX ? s + __ldg(q + t) : s + P.weights[t] * __ldg(q + t);
+    } else {
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        int ii = i + t - W;
+        ii += ii < 1 ? nx : (ii > nx ? -nx : 0);
+        s = BOX ? s + __ldg(row + ii) : s + P.weights[t] * __ldg(row + ii);
+      }
+    }
+    return BOX ? s / T(NT) : s / wtot;
+  };
+  auto wrap = [&](int r) { return r < 1 ? r + ny : (r > ny ? r - ny : r); };
+  T win[NT];
+#pragma unroll
+  for (int m = 0; m < NT - 1; ++m) win[m] = xrow(wrap(c0 - W + m));
+  win[NT - 1] = T(0);
+  for (int c = c0; c <= c1; c += NT) {
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      if (c + t <= c1) {
+        win[(2 * W + t) % NT] = xrow(wrap(c + t + W));
+        T s = T(0);
+#pragma unroll
+        for (int j = 0; j < NT; ++j) s = BOX ? s + win[(t + j) % NT] : s + P.weights[j] * win[(t + j) % NT];
+        out[(long long)(c + t) * P.ds[1]] = BOX ? s / T(NT) : s / wtot;
+      }
+    }
+  }
+}
+template <class T, int W, bool BOX>
+static void launch_xy_w(const PassParams<T>& P, int nx, int ny, cudaStream_t st) {
+  const int ni = P.hi[0] - P.lo[0] + 1, nj = P.hi[1] - P.lo[1] + 1, nk = P.hi[2] - P.lo[2] + 1;
+  int seg = 256;
+  if (nj < seg) seg = nj;
+  dim3 block(128, 1, 1), grid((ni + 127) / 128, nk, (nj + seg - 1) / seg);
+  ocb_filter_xy_kernel<T, W, BOX><<<grid, block, 0, st>>>(P, nx, ny, seg);
+}
+template <class T, bool BOX>
+static bool launch_xy(const PassParams<T>& P, int nx, int ny, cudaStream_t st) {
+  switch (P.width) {
+    case 1: launch_xy_w<T, 1, BOX>(P, nx, ny, st); return true;
+    case 2: launch_xy_w<T, 2, BOX>(P, nx, ny, st); return true;
+    case 3: launch_xy_w<T, 3, BOX>(P, nx, ny, st); return true;
+    case 4: launch_xy_w<T, 4, BOX>(P, nx, ny, st); return true;
+    case 5: launch_xy_w<T, 5, BOX>(P, nx, ny, st); return true;
+    case 6: launch_xy_w<T, 6, BOX>(P, nx, ny, st); return true;
+    case 8: launch_xy_w<T, 8, BOX>(P, nx, ny, st); return true;
+    default: return false;
+  }
+}
+
 // (3) Float64 pair kernel for the x pass: every thread owns two x-adjacent outputs and reads its 2W+2 inputs as W+1
 // 16-byte pairs, which halves the L1 traffic the pass is bound by (9.7 -> 4.9 GB at config 5; 0.35 -> 0.28 ms).  The
 // arithmetic per output is the one-column kernel's (same taps, same order, same division): results are bit-identical.
@@ -332,11 +413,21 @@ static int filter_impl(const ocb_field* src, const int32_t ext[3], const ocb_fil
     tmp[t] = tmp_alloc[t] + 2;
   }
   int rc = OCB_OK;
+  // x and y passes of the same periodic box / uniform Gaussian filter run as ONE kernel (ocb_filter_xy_kernel)
+  bool fuse_xy = n_pass >= 2 && passes[0].dim == 1 && passes[1].dim == 2 && passes[0].kind == passes[1].kind &&
+                 passes[0].kind != OCB_FILTER_GAUSSIAN_STRETCHED && passes[0].policy == OCB_POLICY_PERIODIC &&
+                 passes[1].policy == OCB_POLICY_PERIODIC && passes[0].width == passes[1].width && fast_width_compiled(passes[0].width) &&
+                 ext[0] >= 2 * passes[0].width + 1 && ext[1] >= 2 * passes[0].width + 1 && src->stride[0] == 1 && !getenv("OCB_FILTER_NO_XY");
+  if (fuse_xy && passes[0].kind == OCB_FILTER_GAUSSIAN)
+    for (int t = 0; t < 2 * passes[0].width + 1; ++t) if (T(passes[0].weights[t]) != T(passes[1].weights[t])) fuse_xy = false;
   for (int ps = 0; ps < n_pass; ++ps) {
     const ocb_filter_pass& fp = passes[ps];
     PassParams<T> P;
     memset(&P, 0, sizeof(P));
-    const bool first = ps == 0, last = ps == n_pass - 1;
+    const bool fused_now = fuse_xy && ps == 0;
+    const bool first = ps == 0;
+    if (fused_now) ps = 1;                                 // this iteration does the work of passes 0 and 1
+    const bool last = ps == n_pass - 1;
     if (first) {
       long long off = 0;
       for (int d = 0; d < 3; ++d) { P.ss[d] = src->stride[d]; off += (long long)(src->halo[d] - 1) * src->stride[d]; }
@@ -359,6 +450,11 @@ static int filter_impl(const ocb_field* src, const int32_t ext[3], const ocb_fil
     P.dim = fp.dim - 1; P.kind = fp.kind; P.width = fp.width; P.policy = fp.policy; P.extent = fp.extent;
     P.left = T(fp.left); P.right = T(fp.right); P.sigma = T(fp.sigma); P.period = T(fp.period);
     if (fp.kind == OCB_FILTER_GAUSSIAN) for (int t = 0; t < 2 * fp.width + 1; ++t) P.weights[t] = T(fp.weights[t]);
+    if (fused_now) {
+      const bool done = fp.kind == OCB_FILTER_BOX ? launch_xy<T, true>(P, ext[0], ext[1], st) : launch_xy<T, false>(P, ext[0], ext[1], st);
+      if (!done || cudaGetLastError() != cudaSuccess) { ocb_set_error("fused x-y filter launch failed"); rc = OCB_ERR_CUDA; break; }
+      continue;
+    }
     if (fp.kind == OCB_FILTER_GAUSSIAN_STRETCHED) { P.nodes = (const T*)fp.nodes - 1; P.spacings = (const T*)fp.spacings - 1; }
     auto launch_generic = [&](const PassParams<T>& Q, cudaStream_t on) {
       const int ni = Q.hi[0] - Q.lo[0] + 1, nj = Q.hi[1] - Q.lo[1] + 1, nk = Q.hi[2] - Q.lo[2] + 1;

@@ -1,5 +1,5 @@
 #!/bin/bash
-# quick GPU pass: the tests named on the command line, then the sort / BPE timings
+# quick GPU pass: the tests named on the command line, then the kernel timings named in $KB (bench_kernels.py arguments)
 O=gpurun_out
 python -m pytest $@ -x -q 2>&1 | tail -12 > $O/r2_quick_tests.log; tail -4 $O/r2_quick_tests.log
-python scripts/bench_kernels.py bpe > $O/r2_quick_bpe.log 2>&1; cat $O/r2_quick_bpe.log | cut -c1-220
+python scripts/bench_kernels.py ${KB:-bpe} > $O/r2_quick_kernels.log 2>&1; cat $O/r2_quick_kernels.log | cut -c1-250
