@@ -313,7 +313,7 @@ def test_split_plan_budget_kernel_plus_generic_kernel():
 def test_full_size_1024_cube_properties():
     """BASELINE.json configs[2] at its full size (1024^3 Float64, the bench workload), through properties that need no
     oracle: run-to-run bit equality; the pipelined kernel against the per-cell generic kernel (two independent CUDA
-    formulations) to 1e-12 of each integrand's scale; exact power-of-two scaling (u -> 2u multiplies K and eps by 4, ADV by
+    formulations) to 1e-12 of each integrand's scale; windows of the domain against the oracle's C twin; exact power-of-two scaling (u -> 2u multiplies K and eps by 4, ADV by
     8, PR and u_i b_i by 2, bit for bit); y windows add up to the whole; <chi> = <2c div F>."""
     import sys
     from helpers import ROOT
@@ -349,6 +349,24 @@ def test_full_size_1024_cube_properties():
               for w in ((1, 511), (512, n))]
     for o, a, h0, h1 in zip(ops, first, *halves):
         assert abs((h0 + h1) - a) <= 1e-11 * max(abs(h0), abs(h1), abs(a)), o.name
+    # against the ORACLE at full size: the class-sum integrals over a 1024 x 64 x 64 window (whole x rows, as the kernel
+    # requires), against the oracle's C twin evaluated per cell on the same block of the parent arrays (its halo cells are
+    # the window's real neighbours), to 1e-12 of each integrand's scale
+    import __graft_entry__ as ge
+    from oracle import cbudget
+    ge.build_oracle()
+    H, nw = 3, 64
+    for j0, k0 in ((481, 1), (1, 961), (700, 333)):
+        win = ocb.FusedDiagnostics(*[ocb.Integral(o, indices=(None, (j0, j0 + nw - 1), (k0, k0 + nw - 1))) for o in ops])
+        assert win.plan.variant == 1
+        got = win.compute().integrals()
+        blk = lambda f, nz: f.data[k0 - 1:k0 - 1 + nz + 2 * H, j0 - 1:j0 - 1 + nw + 2 * H, :].cpu().numpy()
+        stt = cbudget.BudgetState((n, nw, nw), H, (1.0 / n,) * 3, 1e-6, 1e-7, blk(m.velocities.u, nw), blk(m.velocities.v, nw),
+                                  blk(m.velocities.w, nw + 1), blk(m.tracers.b, nw), blk(m.pressures.pNHS, nw))
+        for o, d, a in zip(ops, cbudget.DIAGS, got):
+            ref = stt.integral(d)
+            scale = float(np.abs(stt.field(d)).sum()) * dV
+            assert abs(a - ref) <= 1e-12 * scale, (o.name, (j0, k0), a, ref, scale)
     for f in (m.velocities.u, m.velocities.v, m.velocities.w):
         f.data.mul_(2.0)
     scaled = fused.compute().integrals()
