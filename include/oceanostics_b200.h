@@ -144,10 +144,26 @@ enum {
   OCB_DIAG_NU_SMAG,       /* the step before the path (§8f row 3): Smagorinsky-Lilly eddy viscosity νₑ = ς (C Δᶠ)² √(2 ΣᵢⱼΣᵢⱼ) at ccc, Δᶠ = ∛(ΔxΔyΔz),
                              ς² = max(0, 1 - Cb N²/(Pr ΣᵢⱼΣᵢⱼ)), N² = max(0, ℑz ∂z b); C, Cb, Pr in les[0..2] (Cb = 0: no stratification
                              correction, b unused) -- Oceananigans' calc_nonlinear_νᶜᶜᶜ for SmagorinskyLilly; ΣᵢⱼΣᵢⱼ as in FlowDiagnostics.jl:431-441 */
+  /* ---- pass-through modules (§8f row 4): the Oceananigans tendency terms UMomentumEquation / VMomentumEquation /
+   * WMomentumEquation / TracerEquation hand out one by one, at the velocity points (fcc / cfc / ccf) or the cell centre.  The
+   * term is picked by OCB_REQ_TERM(code) in the request flags: OCB_TERM_TENDENCY the whole tendency (u_velocity_tendency /
+   * tracer_tendency, the model without background fields, immersed boundaries, Stokes drift: as KE_TENDENCY / C_TENDENCY),
+   * ADVECTION div_𝐯u / div_Uc (Centered 2nd order), BUOYANCY x_dot_g_b, CORIOLIS x_f_cross_U, PRESSURE ∂x of slot p
+   * (hydrostatic_pressure_gradient_x), DIFFUSION ∂ⱼ_τ₁ⱼ / ∇_dot_qᶜ, FORCING the materialised functor (aux[0..2]; tracer: aux[0]).
+   * UMomentumEquation.jl:99-504, VMomentumEquation.jl, WMomentumEquation.jl, TracerEquation.jl:70-327 */
+  OCB_DIAG_U_TERM,        /* fcc */
+  OCB_DIAG_V_TERM,        /* cfc */
+  OCB_DIAG_W_TERM,        /* ccf */
+  OCB_DIAG_C_TERM,        /* ccc: tracer in slot b */
+  OCB_DIAG_QX, OCB_DIAG_QY, OCB_DIAG_QZ,   /* diffusive_flux_x / y / z of the tracer in slot b   TracerEquation.jl:221-294   fcc cfc ccf */
   OCB_DIAG_COUNT
 };
 
 /* request flags */
+enum { OCB_TERM_TENDENCY = 0, OCB_TERM_ADVECTION = 1, OCB_TERM_BUOYANCY = 2, OCB_TERM_CORIOLIS = 3, OCB_TERM_PRESSURE = 4,
+       OCB_TERM_DIFFUSION = 5, OCB_TERM_FORCING = 6 };
+#define OCB_REQ_TERM_SHIFT 12
+#define OCB_REQ_TERM(code) ((code) << OCB_REQ_TERM_SHIFT)     /* U_TERM / V_TERM / W_TERM / C_TERM: which term (bits 12..15) */
 enum {
   OCB_REQ_PERTURBATION = 1,   /* velocities seen by this diagnostic are (u-U, v-V, w-W) and the tracer is c-C:
                                  perturbation_fields (src/Oceanostics.jl:157-173) / lazy `u-U` operands

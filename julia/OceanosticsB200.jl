@@ -45,6 +45,9 @@ const OCB_REQ_TENSOR_DIM1, OCB_REQ_TENSOR_DIM2, OCB_REQ_TENSOR_DIM3 = Int32(1 <<
 const OCB_REQ_COLLOCATED = Int32(1 << 7)
 const OCB_REQ_CARRIED_HEIGHT = Int32(1 << 8)
 const OCB_REQ_HYDROSTATIC_SPLIT = Int32(1 << 9)
+const OCB_REQ_TERM_SHIFT = 12
+const OCB_TERM_TENDENCY, OCB_TERM_ADVECTION, OCB_TERM_BUOYANCY, OCB_TERM_CORIOLIS, OCB_TERM_PRESSURE, OCB_TERM_DIFFUSION, OCB_TERM_FORCING = Int32(0), Int32(1), Int32(2), Int32(3), Int32(4), Int32(5), Int32(6)
+term_flag(code) = Int32(code) << OCB_REQ_TERM_SHIFT
 const OCB_FILTER_BOX, OCB_FILTER_GAUSSIAN, OCB_FILTER_GAUSSIAN_STRETCHED = Int32(0), Int32(1), Int32(2)
 const OCB_POLICY_PERIODIC, OCB_POLICY_SHRINK, OCB_POLICY_EDGE, OCB_POLICY_CONSTANT = Int32(0), Int32(1), Int32(2), Int32(3)
 const OCB_BPE_THREE_DIMENSIONAL_SORT, OCB_BPE_HEAVISIDE_INTEGRAL = Int32(0), Int32(1)
@@ -55,7 +58,7 @@ const DIAG_NAMES = (:KE, :ADV, :PR, :WB, :EPS, :EPS_ISO, :TKE, :SPX, :SPY, :SPZ,
                     :S11, :S22, :S33, :S12, :S13, :S23, :O12, :O13, :O23, :T11, :T22, :T33, :T11C, :T22C, :T33C,
                     :T12, :T13, :T23, :RI, :RO, :EPV, :TWPV, :DEPV, :VF11, :VF22, :VF33, :VF12, :VF13, :VF23,
                     :FEPS, :SFEPS, :SFKE, :PI, :BPE, :APE, :UPSILON, :APE_EPS, :KE_STRESS, :KE_FORCING, :C_TENDENCY,
-                    :KE_TENDENCY, :NU_SMAG)
+                    :KE_TENDENCY, :NU_SMAG, :U_TERM, :V_TERM, :W_TERM, :C_TERM, :QX, :QY, :QZ)
 diag_id(name::Symbol) = Int32(findfirst(==(name), DIAG_NAMES) - 1)
 
 # ---- mirrors of the C structs (same field order and types; isbits, so `Ref{T}` passes them by pointer) -----------------
@@ -375,6 +378,48 @@ const DIAG = Dict{Any,Tuple{Symbol,Function}}(
     TVEq.c∂ₜcᶜᶜᶜ                                => (:C_TENDENCY, tendency_slots_tracer),                 # TracerVarianceEquation.jl:88
     KEq.uᵢGᵢᶜᶜᶜ                                 => (:KE_TENDENCY, tendency_slots_momentum),              # KineticEnergyEquation.jl:142
 )
+# ---- pass-through modules (UMomentumEquation.jl, VMomentumEquation.jl, WMomentumEquation.jl, TracerEquation.jl): one term each --
+const UEq, VEq, WEq, TrEq = Oceanostics.UMomentumEquation, Oceanostics.VMomentumEquation, Oceanostics.WMomentumEquation, Oceanostics.TracerEquation
+const NHM, ADVM, BF, COR = Oceananigans.Models.NonhydrostaticModels, Oceananigans.Advection, Oceananigans.BuoyancyFormulations, Oceananigans.Coriolis
+term!(s::Slots, code) = (s.flags |= term_flag(code); s)
+adv_slots(a) = (advection_supported(a[1]); term!(velnt(a[2]), OCB_TERM_ADVECTION))                       # (advection, velocities, uᵢ)
+buoy_slots(a) = (s = Slots(); s.b = a[2].b; s.ghat = ghat(a[1]); term!(s, OCB_TERM_BUOYANCY))             # (buoyancy, tracers)
+cor_slots(a) = (s = velnt(a[2]); s.f = a[1] === nothing ? (0.0, 0.0, 0.0) : map(Float64, get_coriolis_frequency_components(a[1])); term!(s, OCB_TERM_CORIOLIS))
+pgrad_slots(a) = (s = Slots(); s.p = a[1]; term!(s, OCB_TERM_PRESSURE))                                   # (hydrostatic_pressure,)
+visc_slots(a) = term!(flux_slots(a), OCB_TERM_DIFFUSION)                                                  # (closure, diffusivities, clock, model_fields, buoyancy)
+force_slots(axis) = a -> (s = Slots(); s.aux[axis] = forcing_field(a[1], getproperty(a[3], (:u, :v, :w)[axis]), a[2], a[3]); term!(s, OCB_TERM_FORCING))
+function velocity_tendency_slots(axis)      # (advection, coriolis, stokes_drift, closure, immersed_bc, buoyancy, background_fields, velocities, tracers, aux, K, pHY′, clock, forcing)
+    return a -> begin
+        advection, coriolis, stokes, closure, ibc, buoyancy, background, velocities, tracers, aux, K, pHY, clock, forcing = a
+        (ibc === nothing && stokes === nothing && all(isnothing, values(background.velocities))) ||
+            throw(UnsupportedByLibrary("velocity tendency with immersed boundaries / Stokes drift / background fields"))
+        advection_supported(advection)
+        s = with_closure(velnt(velocities), closure, K)
+        s.f = coriolis === nothing ? (0.0, 0.0, 0.0) : map(Float64, get_coriolis_frequency_components(coriolis))
+        buoyancy === nothing || (s.b = tracers.b; s.ghat = ghat(buoyancy))
+        pHY === nothing || (s.p = pHY; s.flags |= OCB_REQ_HYDROSTATIC_SPLIT)
+        s.aux[axis] = forcing_field(forcing, getproperty(velocities, (:u, :v, :w)[axis]), clock, merge(velocities, tracers))
+        term!(s, OCB_TERM_TENDENCY)
+    end
+end
+for (row, key) in ((:U_TERM, 1), (:V_TERM, 2), (:W_TERM, 3))
+    Eq = (UEq, VEq, WEq)[key]
+    DIAG[(ADVM.div_𝐯u, ADVM.div_𝐯v, ADVM.div_𝐯w)[key]] = (row, adv_slots)                                    # UMomentumEquation.jl:99-101
+    DIAG[(BF.x_dot_g_bᶠᶜᶜ, BF.y_dot_g_bᶜᶠᶜ, BF.z_dot_g_bᶜᶜᶠ)[key]] = (row, buoy_slots)                      # :138
+    DIAG[(COR.x_f_cross_U, COR.y_f_cross_U, COR.z_f_cross_U)[key]] = (row, cor_slots)                          # :171
+    key < 3 && (DIAG[(UEq.hydrostatic_pressure_gradient_x, VEq.hydrostatic_pressure_gradient_y)[key]] = (row, pgrad_slots))   # :204
+    DIAG[(TC.∂ⱼ_τ₁ⱼ, TC.∂ⱼ_τ₂ⱼ, TC.∂ⱼ_τ₃ⱼ)[key]] = (row, visc_slots)                                         # :285
+    DIAG[(UEq.forcing_fcc, VEq.forcing_cfc, WEq.forcing_ccf)[key]] = (row, force_slots(key))                   # :453
+    DIAG[(NHM.u_velocity_tendency, NHM.v_velocity_tendency, NHM.w_velocity_tendency)[key]] = (row, velocity_tendency_slots(key))   # :499
+end
+DIAG[ADVM.div_Uc] = (:C_TERM, a -> (advection_supported(a[1]); term!(tracer!(velnt(a[2]), a[3]), OCB_TERM_ADVECTION)))              # TracerEquation.jl:72
+DIAG[TC.∇_dot_qᶜ] = (:C_TERM, a -> term!(with_closure(tracer!(velnt(a[6]), a[4]), a[1], a[2], tracer_index(a[3])), OCB_TERM_DIFFUSION))  # :114
+DIAG[TrEq.forcing_ccc] = (:C_TERM, a -> (s = Slots(); s.aux[1] = forcing_field(a[1], a[3].b, a[2], a[3]); term!(s, OCB_TERM_FORCING)))   # :324
+tracer_flux_row(a) = with_closure(tracer!(Slots(), a[4]), a[1], a[2], tracer_index(a[3]))                 # (closure, closure_fields, Val(id), c, clock, fields, buoyancy)
+DIAG[TC.diffusive_flux_x] = (:QX, tracer_flux_row)                                                        # :223
+DIAG[TC.diffusive_flux_y] = (:QY, tracer_flux_row)                                                        # :257
+DIAG[TC.diffusive_flux_z] = (:QZ, tracer_flux_row)                                                        # :291
+
 # SFEPS, PI: the reference wraps an operation TREE in a one-argument kernel (`εˢ[i,j,k]`, `Πᵏ[i,j,k]`:
 # SubFilterKineticEnergyEquation.jl:143-147, FilteredKineticEnergyEquation.jl:246-257); `tree_slots` walks that tree's leaves.
 DIAG[SFKEq.subfilter_ke_dissipation_rate_ccc] = (:SFEPS, a -> subfilter_dissipation_slots(a[1]))

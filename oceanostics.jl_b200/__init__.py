@@ -14,6 +14,7 @@ from .models import (NonhydrostaticModel, HydrostaticFreeSurfaceModel, FPlane, C
                      Forcing, get_coriolis_frequency_components)
 from . import KineticEnergyEquation, TurbulentKineticEnergyEquation, TracerVarianceEquation, FlowDiagnostics, SpatialFilters, BackgroundPotentialEnergyEquation
 from . import FilteredKineticEnergyEquation, SubFilterKineticEnergyEquation, AvailablePotentialEnergyEquation
+from . import UMomentumEquation, VMomentumEquation, WMomentumEquation, TracerEquation
 from .SpatialFilters import BoxFilter, GaussianFilter
 
 ScalarDiffusivity = Closure

@@ -27,12 +27,15 @@ OCB_REQ_TENSOR_DIM1, OCB_REQ_TENSOR_DIM2, OCB_REQ_TENSOR_DIM3 = 1 << 4, 1 << 5, 
 OCB_REQ_COLLOCATED = 1 << 7
 OCB_REQ_CARRIED_HEIGHT = 1 << 8
 OCB_REQ_HYDROSTATIC_SPLIT = 1 << 9
+OCB_REQ_TERM_SHIFT = 12
+OCB_TERM_TENDENCY, OCB_TERM_ADVECTION, OCB_TERM_BUOYANCY, OCB_TERM_CORIOLIS, OCB_TERM_PRESSURE, OCB_TERM_DIFFUSION, OCB_TERM_FORCING = range(7)
 
 _DIAG_NAMES = [
     "KE", "ADV", "PR", "WB", "EPS", "EPS_ISO", "TKE", "SPX", "SPY", "SPZ", "SP", "CHI", "CDIFF", "SMOD", "OMOD", "Q",
     "S11", "S22", "S33", "S12", "S13", "S23", "O12", "O13", "O23", "T11", "T22", "T33", "T11C", "T22C", "T33C",
     "T12", "T13", "T23", "RI", "RO", "EPV", "TWPV", "DEPV", "VF11", "VF22", "VF33", "VF12", "VF13", "VF23",
-    "FEPS", "SFEPS", "SFKE", "PI", "BPE", "APE", "UPSILON", "APE_EPS", "KE_STRESS", "KE_FORCING", "C_TENDENCY", "KE_TENDENCY", "NU_SMAG"]
+    "FEPS", "SFEPS", "SFKE", "PI", "BPE", "APE", "UPSILON", "APE_EPS", "KE_STRESS", "KE_FORCING", "C_TENDENCY", "KE_TENDENCY", "NU_SMAG",
+    "U_TERM", "V_TERM", "W_TERM", "C_TERM", "QX", "QY", "QZ"]
 DIAG = {name: i for i, name in enumerate(_DIAG_NAMES)}
 OCB_DIAG_COUNT = len(_DIAG_NAMES)
 
@@ -44,7 +47,8 @@ for _n in ("S13", "O13", "T13", "VF13"):
     DIAG_LOC[_n] = "fcf"
 for _n in ("S23", "O23", "T23", "VF23"):
     DIAG_LOC[_n] = "cff"
-DIAG_LOC.update(T11="fcc", T22="cfc", T33="ccf", RI="ccf", RO="fff", EPV="fff", TWPV="fff", DEPV="fff")
+DIAG_LOC.update(T11="fcc", T22="cfc", T33="ccf", RI="ccf", RO="fff", EPV="fff", TWPV="fff", DEPV="fff",
+                U_TERM="fcc", V_TERM="cfc", W_TERM="ccf", QX="fcc", QY="cfc", QZ="ccf")
 
 OCB_FILTER_BOX, OCB_FILTER_GAUSSIAN, OCB_FILTER_GAUSSIAN_STRETCHED = 0, 1, 2
 OCB_POLICY_PERIODIC, OCB_POLICY_SHRINK, OCB_POLICY_EDGE, OCB_POLICY_CONSTANT = 0, 1, 2, 3

@@ -614,32 +614,41 @@ template <class T> struct Tendency {
   StressDiv<T> D;
   bool w_buoyancy;
   OCB_X Tendency(const Ctx<T>& x, int flags) : X(x), A(x), D(x), w_buoyancy(!(flags & OCB_REQ_HYDROSTATIC_SPLIT)) {}
-  OCB_X T gu(int i, int j, int k) const {   // fcc
+  // x_dot_g_b, y_dot_g_b, z_dot_g_b  [OCN-mem BuoyancyFormulations/buoyancy_force.jl]
+  OCB_X T bx(int i, int j, int k) const { const SweepIn<T>& I = X.in; return I.ghat[0] != T(0) ? I.ghat[0] * (T(0.5) * (I.b(i - 1, j, k) + I.b(i, j, k))) : T(0); }
+  OCB_X T by(int i, int j, int k) const { const SweepIn<T>& I = X.in; return I.ghat[1] != T(0) ? I.ghat[1] * (T(0.5) * (I.b(i, j - 1, k) + I.b(i, j, k))) : T(0); }
+  OCB_X T bz(int i, int j, int k) const { const SweepIn<T>& I = X.in; return I.ghat[2] != T(0) ? I.ghat[2] * (T(0.5) * (I.b(i, j, k - 1) + I.b(i, j, k))) : T(0); }
+  // x_f_cross_U, y_f_cross_U, z_f_cross_U
+  OCB_X T cx(int i, int j, int k) const {
     const SweepIn<T>& I = X.in;
-    T r = I.aux[0](i, j, k) - A.divu(i, j, k) - D.d1(i, j, k) - (I.p(i, j, k) - I.p(i - 1, j, k)) * X.g.rdx;
-    if (I.ghat[0] != T(0)) r += I.ghat[0] * (T(0.5) * (I.b(i - 1, j, k) + I.b(i, j, k)));
     T cor = T(0);
     if (I.f[1] != T(0)) cor += I.f[1] * (T(0.25) * ((X.w(i - 1, j, k) + X.w(i, j, k)) + (X.w(i - 1, j, k + 1) + X.w(i, j, k + 1))));
     if (I.f[2] != T(0)) cor -= I.f[2] * (T(0.25) * ((X.v(i - 1, j, k) + X.v(i, j, k)) + (X.v(i - 1, j + 1, k) + X.v(i, j + 1, k))));
-    return r - cor;
+    return cor;
   }
-  OCB_X T gv(int i, int j, int k) const {   // cfc
+  OCB_X T cy(int i, int j, int k) const {
     const SweepIn<T>& I = X.in;
-    T r = I.aux[1](i, j, k) - A.divv(i, j, k) - D.d2(i, j, k) - (I.p(i, j, k) - I.p(i, j - 1, k)) * X.g.rdy;
-    if (I.ghat[1] != T(0)) r += I.ghat[1] * (T(0.5) * (I.b(i, j - 1, k) + I.b(i, j, k)));
     T cor = T(0);
     if (I.f[2] != T(0)) cor += I.f[2] * (T(0.25) * ((X.u(i, j - 1, k) + X.u(i + 1, j - 1, k)) + (X.u(i, j, k) + X.u(i + 1, j, k))));
     if (I.f[0] != T(0)) cor -= I.f[0] * (T(0.25) * ((X.w(i, j - 1, k) + X.w(i, j, k)) + (X.w(i, j - 1, k + 1) + X.w(i, j, k + 1))));
-    return r - cor;
+    return cor;
   }
-  OCB_X T gw(int i, int j, int k) const {   // ccf
+  OCB_X T cz(int i, int j, int k) const {
     const SweepIn<T>& I = X.in;
-    T r = I.aux[2](i, j, k) - A.divw(i, j, k) - D.d3(i, j, k);
-    if (w_buoyancy && I.ghat[2] != T(0)) r += I.ghat[2] * (T(0.5) * (I.b(i, j, k - 1) + I.b(i, j, k)));
     T cor = T(0);
     if (I.f[0] != T(0)) cor += I.f[0] * (T(0.25) * ((X.v(i, j, k - 1) + X.v(i, j + 1, k - 1)) + (X.v(i, j, k) + X.v(i, j + 1, k))));
     if (I.f[1] != T(0)) cor -= I.f[1] * (T(0.25) * ((X.u(i, j, k - 1) + X.u(i + 1, j, k - 1)) + (X.u(i, j, k) + X.u(i + 1, j, k))));
-    return r - cor;
+    return cor;
+  }
+  // hydrostatic_pressure_gradient_x / _y of the pressure in slot p
+  OCB_X T px(int i, int j, int k) const { return (X.in.p(i, j, k) - X.in.p(i - 1, j, k)) * X.g.rdx; }
+  OCB_X T py(int i, int j, int k) const { return (X.in.p(i, j, k) - X.in.p(i, j - 1, k)) * X.g.rdy; }
+  OCB_X T gu(int i, int j, int k) const { return ((X.in.aux[0](i, j, k) - A.divu(i, j, k) - D.d1(i, j, k) - px(i, j, k)) + bx(i, j, k)) - cx(i, j, k); }   // fcc
+  OCB_X T gv(int i, int j, int k) const { return ((X.in.aux[1](i, j, k) - A.divv(i, j, k) - D.d2(i, j, k) - py(i, j, k)) + by(i, j, k)) - cy(i, j, k); }   // cfc
+  OCB_X T gw(int i, int j, int k) const {                                                                                                                      // ccf
+    T r = X.in.aux[2](i, j, k) - A.divw(i, j, k) - D.d3(i, j, k);
+    if (w_buoyancy) r += bz(i, j, k);
+    return r - cz(i, j, k);
   }
 };
 OCB_EVAL(OCB_DIAG_KE_TENDENCY) {
@@ -649,6 +658,75 @@ OCB_EVAL(OCB_DIAG_KE_TENDENCY) {
   T c = X.w(i, j, k) * G.gw(i, j, k) + X.w(i, j, k + 1) * G.gw(i, j, k + 1);
   return T(0.5) * (a + b + c);
 } };
+
+// The tendency terms one by one (UMomentumEquation.jl:99-504 and its v / w twins): the raw Oceananigans kernels, unsigned
+OCB_EVAL(OCB_DIAG_U_TERM) {
+  Tendency<T> G(X, flags);
+  switch ((flags >> OCB_REQ_TERM_SHIFT) & 15) {
+    case OCB_TERM_ADVECTION: return G.A.divu(i, j, k);
+    case OCB_TERM_BUOYANCY: return G.bx(i, j, k);
+    case OCB_TERM_CORIOLIS: return G.cx(i, j, k);
+    case OCB_TERM_PRESSURE: return G.px(i, j, k);
+    case OCB_TERM_DIFFUSION: return G.D.d1(i, j, k);
+    case OCB_TERM_FORCING: return X.in.aux[0](i, j, k);
+    default: return G.gu(i, j, k);
+  }
+} };
+OCB_EVAL(OCB_DIAG_V_TERM) {
+  Tendency<T> G(X, flags);
+  switch ((flags >> OCB_REQ_TERM_SHIFT) & 15) {
+    case OCB_TERM_ADVECTION: return G.A.divv(i, j, k);
+    case OCB_TERM_BUOYANCY: return G.by(i, j, k);
+    case OCB_TERM_CORIOLIS: return G.cy(i, j, k);
+    case OCB_TERM_PRESSURE: return G.py(i, j, k);
+    case OCB_TERM_DIFFUSION: return G.D.d2(i, j, k);
+    case OCB_TERM_FORCING: return X.in.aux[1](i, j, k);
+    default: return G.gv(i, j, k);
+  }
+} };
+OCB_EVAL(OCB_DIAG_W_TERM) {
+  Tendency<T> G(X, flags);
+  switch ((flags >> OCB_REQ_TERM_SHIFT) & 15) {
+    case OCB_TERM_ADVECTION: return G.A.divw(i, j, k);
+    case OCB_TERM_BUOYANCY: return G.bz(i, j, k);
+    case OCB_TERM_CORIOLIS: return G.cz(i, j, k);
+    case OCB_TERM_PRESSURE: return T(0);                 // the vertical momentum equation carries no hydrostatic pressure gradient
+    case OCB_TERM_DIFFUSION: return G.D.d3(i, j, k);
+    case OCB_TERM_FORCING: return X.in.aux[2](i, j, k);
+    default: return G.gw(i, j, k);
+  }
+} };
+// TracerEquation.jl:70-327: div_Uc, ∇_dot_qᶜ, the forcing, the whole tracer tendency; and the three diffusive fluxes
+template <class T> struct TracerTerms {
+  const Ctx<T>& X;
+  OCB_X TracerTerms(const Ctx<T>& x) : X(x) {}
+  OCB_X T qx(int i, int j, int k) const { return -X.ka_fcc(i, j, k) * ((X.in.b(i, j, k) - X.in.b(i - 1, j, k)) * X.g.rdx); }
+  OCB_X T qy(int i, int j, int k) const { return -X.ka_cfc(i, j, k) * ((X.in.b(i, j, k) - X.in.b(i, j - 1, k)) * X.g.rdy); }
+  OCB_X T qz(int i, int j, int k) const { return -X.ka_ccf(i, j, k) * ((X.in.b(i, j, k) - X.in.b(i, j, k - 1)) * X.rdzf(k)); }
+  OCB_X T adv(int i, int j, int k) const {
+    const HFld<T>& c = X.in.b;
+    const T cc = c(i, j, k);
+    const T ax = (X.u(i + 1, j, k) * (cc + c(i + 1, j, k)) - X.u(i, j, k) * (c(i - 1, j, k) + cc)) * (T(0.5) * X.g.rdx);
+    const T ay = (X.v(i, j + 1, k) * (cc + c(i, j + 1, k)) - X.v(i, j, k) * (c(i, j - 1, k) + cc)) * (T(0.5) * X.g.rdy);
+    const T az = (X.w(i, j, k + 1) * (cc + c(i, j, k + 1)) - X.w(i, j, k) * (c(i, j, k - 1) + cc)) * (T(0.5) * X.rdzc(k));
+    return (ax + ay) + az;
+  }
+  OCB_X T divq(int i, int j, int k) const {
+    return (qx(i + 1, j, k) - qx(i, j, k)) * X.g.rdx + (qy(i, j + 1, k) - qy(i, j, k)) * X.g.rdy + (qz(i, j, k + 1) - qz(i, j, k)) * X.rdzc(k);
+  }
+};
+OCB_EVAL(OCB_DIAG_C_TERM) {
+  TracerTerms<T> C(X);
+  switch ((flags >> OCB_REQ_TERM_SHIFT) & 15) {
+    case OCB_TERM_ADVECTION: return C.adv(i, j, k);
+    case OCB_TERM_DIFFUSION: return C.divq(i, j, k);
+    case OCB_TERM_FORCING: return X.in.aux[0](i, j, k);
+    default: return (X.in.aux[0](i, j, k) - C.adv(i, j, k)) - C.divq(i, j, k);
+  }
+} };
+OCB_EVAL(OCB_DIAG_QX) { return TracerTerms<T>(X).qx(i, j, k); } };
+OCB_EVAL(OCB_DIAG_QY) { return TracerTerms<T>(X).qy(i, j, k); } };
+OCB_EVAL(OCB_DIAG_QZ) { return TracerTerms<T>(X).qz(i, j, k); } };
 
 // Smagorinsky-Lilly eddy viscosity at ccc (Oceananigans' compute_diffusivities! for SmagorinskyLilly,
 // the step before the path) [OCN-mem: TurbulenceClosures/turbulence_closure_implementations/smagorinsky_lilly.jl]:
@@ -683,7 +761,8 @@ OCB_EVAL(OCB_DIAG_NU_SMAG) {
   M(OCB_DIAG_RO) M(OCB_DIAG_EPV) M(OCB_DIAG_TWPV) M(OCB_DIAG_DEPV) M(OCB_DIAG_VF11) M(OCB_DIAG_VF22) M(OCB_DIAG_VF33) \
   M(OCB_DIAG_VF12) M(OCB_DIAG_VF13) M(OCB_DIAG_VF23) M(OCB_DIAG_FEPS) M(OCB_DIAG_SFEPS) M(OCB_DIAG_SFKE) M(OCB_DIAG_PI) \
   M(OCB_DIAG_BPE) M(OCB_DIAG_APE) M(OCB_DIAG_UPSILON) M(OCB_DIAG_APE_EPS) M(OCB_DIAG_KE_STRESS) M(OCB_DIAG_KE_FORCING) M(OCB_DIAG_C_TENDENCY) \
-  M(OCB_DIAG_KE_TENDENCY) M(OCB_DIAG_NU_SMAG)
+  M(OCB_DIAG_KE_TENDENCY) M(OCB_DIAG_NU_SMAG) M(OCB_DIAG_U_TERM) M(OCB_DIAG_V_TERM) M(OCB_DIAG_W_TERM) M(OCB_DIAG_C_TERM) \
+  M(OCB_DIAG_QX) M(OCB_DIAG_QY) M(OCB_DIAG_QZ)
 
 // diagnostics whose operands may be lazy perturbations (u - U, c - C); the flag is rejected for the others
 OCB_X constexpr bool ocb_diag_takes_perturbation(int d) {

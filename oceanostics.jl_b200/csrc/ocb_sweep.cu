@@ -161,6 +161,9 @@ static double count_algorithmic_bytes(const ocb_grid* g, const ocb_sweep_inputs*
       case OCB_DIAG_C_TENDENCY: mark_uvw(); use[3] = true; use[9] = true; break;
       case OCB_DIAG_KE_TENDENCY: mark_uvw(); use[3] = use[4] = true; use[9] = use[10] = use[11] = true; break;
       case OCB_DIAG_NU_SMAG: mark_uvw(); if (in->les[1] != 0) use[3] = true; break;
+      case OCB_DIAG_U_TERM: case OCB_DIAG_V_TERM: case OCB_DIAG_W_TERM: mark_uvw(); use[3] = use[4] = true; use[9] = use[10] = use[11] = true; break;
+      case OCB_DIAG_C_TERM: mark_uvw(); use[3] = true; use[9] = true; break;
+      case OCB_DIAG_QX: case OCB_DIAG_QY: case OCB_DIAG_QZ: use[3] = true; break;
       default: mark_uvw(); break;
     }
     if (pert || d == OCB_DIAG_TKE || (d >= OCB_DIAG_SPX && d <= OCB_DIAG_SP)) use[5] = use[6] = use[7] = true;
@@ -178,7 +181,7 @@ static double count_algorithmic_bytes(const ocb_grid* g, const ocb_sweep_inputs*
   for (int r = 0; r < n; ++r) {
     const int d = reqs[r].diag;
     if (d == OCB_DIAG_EPS || d == OCB_DIAG_EPS_ISO || d == OCB_DIAG_CHI || d == OCB_DIAG_CDIFF || d == OCB_DIAG_APE_EPS ||
-        d == OCB_DIAG_KE_STRESS || d == OCB_DIAG_C_TENDENCY || d == OCB_DIAG_KE_TENDENCY || (d >= OCB_DIAG_VF11 && d <= OCB_DIAG_VF23)) eddy = true;
+        d == OCB_DIAG_KE_STRESS || d == OCB_DIAG_C_TENDENCY || d == OCB_DIAG_KE_TENDENCY || (d >= OCB_DIAG_U_TERM && d <= OCB_DIAG_QZ) || (d >= OCB_DIAG_VF11 && d <= OCB_DIAG_VF23)) eddy = true;
   }
   if (eddy) {   // count each distinct eddy field once
     const void* seen[2 * OCB_MAX_CLOSURE_FIELDS]; int ns = 0;

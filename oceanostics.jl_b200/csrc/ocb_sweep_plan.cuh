@@ -12,9 +12,9 @@ static inline void ocb_diag_location(int diag, int loc[3]) {
     case OCB_DIAG_S12: case OCB_DIAG_O12: case OCB_DIAG_T12: case OCB_DIAG_VF12: l[0] = F; l[1] = F; break;
     case OCB_DIAG_S13: case OCB_DIAG_O13: case OCB_DIAG_T13: case OCB_DIAG_VF13: l[0] = F; l[2] = F; break;
     case OCB_DIAG_S23: case OCB_DIAG_O23: case OCB_DIAG_T23: case OCB_DIAG_VF23: l[1] = F; l[2] = F; break;
-    case OCB_DIAG_T11: l[0] = F; break;
-    case OCB_DIAG_T22: l[1] = F; break;
-    case OCB_DIAG_T33: l[2] = F; break;
+    case OCB_DIAG_T11: case OCB_DIAG_U_TERM: case OCB_DIAG_QX: l[0] = F; break;
+    case OCB_DIAG_T22: case OCB_DIAG_V_TERM: case OCB_DIAG_QY: l[1] = F; break;
+    case OCB_DIAG_T33: case OCB_DIAG_W_TERM: case OCB_DIAG_QZ: l[2] = F; break;
     case OCB_DIAG_RI: l[2] = F; break;
     case OCB_DIAG_RO: case OCB_DIAG_EPV: case OCB_DIAG_TWPV: case OCB_DIAG_DEPV: l[0] = l[1] = l[2] = F; break;
     default: break;
@@ -34,7 +34,8 @@ static inline int ocb_diag_needs(int diag) {
   switch (diag) {
     case OCB_DIAG_PR: return OCB_NEED_P;
     case OCB_DIAG_WB: case OCB_DIAG_CHI: case OCB_DIAG_CDIFF: case OCB_DIAG_RI: case OCB_DIAG_EPV:
-    case OCB_DIAG_TWPV: case OCB_DIAG_DEPV: case OCB_DIAG_C_TENDENCY: return OCB_NEED_B;
+    case OCB_DIAG_TWPV: case OCB_DIAG_DEPV: case OCB_DIAG_C_TENDENCY: case OCB_DIAG_C_TERM: case OCB_DIAG_QX: case OCB_DIAG_QY:
+    case OCB_DIAG_QZ: return OCB_NEED_B;
     case OCB_DIAG_FEPS: case OCB_DIAG_PI: return OCB_NEED_AUX05;
     case OCB_DIAG_SFEPS: return OCB_NEED_AUX05 | OCB_NEED_AUX6;
     case OCB_DIAG_SFKE: return OCB_NEED_AUX6;

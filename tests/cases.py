@@ -113,6 +113,38 @@ def build_cases(st: State, closure_name="scalar", mean="profile"):
         cases.append(("KineticEnergyTendency" + tag, KE.KineticEnergyTendency(m_t),
                       ev(K.ke_tendency_ccc, og, "ccc", None, f_cor, None, oc, None, None, None, buoy, None, vel, {"b": st.ob}, None, None, opHY, None,
                          oforc), "ccc"))
+    # pass-through modules (scope table 8f, row 4): the terms of the momentum and tracer equations one by one, on the forced,
+    # rotating, stratified model above with st.p standing in for the hydrostatic pressure anomaly
+    m_p = st.model(closure=pc, coriolis=ocb.ConstantCartesianCoriolis(*f_cor), buoyancy=ocb.BuoyancyTracer(gravity_unit_vector=tuple(-t for t in tilt)))
+    m_p.forcing.u, m_p.forcing.v, m_p.forcing.w, m_p.forcing.b = pforc["u"], pforc["v"], pforc["w"], m_forced.forcing.b
+    m_p.pressures.pHY = st.p
+    flds = {**vel, "b": st.ob}
+    tbuoy = (tilt, "b")
+    tend_args = (None, f_cor, None, oc, None, tbuoy, None, vel, {"b": st.ob}, None, None, st.op, None)
+    mom = {"u": (ocb.UMomentumEquation, "fcc", K.div_Uu, K.x_dot_g_b_fcc, K.x_f_cross_U, K.ddx_fcc, K.div_tau_1, K.u_velocity_tendency),
+           "v": (ocb.VMomentumEquation, "cfc", K.div_Uv, K.y_dot_g_b_cfc, K.y_f_cross_U, K.ddy_cfc, K.div_tau_2, K.v_velocity_tendency),
+           "w": (ocb.WMomentumEquation, "ccf", K.div_Uw, K.z_dot_g_b_ccf, K.z_f_cross_U, None, K.div_tau_3, K.w_velocity_tendency)}
+    for cn, (mod, loc, f_adv, f_buoy, f_cor_, f_pg, f_tau, f_tend) in mom.items():
+        C = cn.upper()
+        cases += [
+            (f"{C}Advection", mod.Advection(m_p), ev(f_adv, og, loc, None, vel, vel[cn]), loc),
+            (f"{C}BuoyancyAcceleration", mod.BuoyancyAcceleration(m_p), ev(f_buoy, og, loc, tilt, st.ob), loc),
+            (f"{C}CoriolisAcceleration", mod.CoriolisAcceleration(m_p), ev(f_cor_, og, loc, f_cor, vel), loc),
+            (f"{C}PressureGradient", mod.PressureGradient(m_p), ev(f_pg, og, loc, st.op) if f_pg else np.zeros(og.extent_of(loc)), loc),
+            (f"{C}ViscousDissipation", mod.ViscousDissipation(m_p), ev(f_tau, og, loc, oc, None, None, flds, None), loc),
+            (f"{C}Forcing", mod.Forcing(m_p), ev(oforc[cn], og, loc, None, flds), loc),
+            (f"{C}Tendency", mod.Tendency(m_p), ev(f_tend, og, loc, *tend_args, oforc[cn]), loc),
+        ]
+    TE = ocb.TracerEquation
+    Uo = (st.ou, st.ov, st.ow)
+    cases += [
+        ("TracerAdvection", TE.Advection(m_p, "b"), ev(K.div_Uc, og, "ccc", None, Uo, st.ob), "ccc"),
+        ("TracerDiffusion", TE.Diffusion(m_p, "b"), ev(K.div_q_c, og, "ccc", oc, None, 1, st.ob, None, flds, None), "ccc"),
+        ("TracerForcing", TE.Forcing(m_p, "b"), ev(Fb, og, "ccc", None, flds), "ccc"),
+        ("TracerXDiffusiveFlux", TE.XDiffusiveFlux(m_p, "b"), ev(K.diffusive_flux_x, og, "fcc", oc, None, 1, st.ob), "fcc"),
+        ("TracerYDiffusiveFlux", TE.YDiffusiveFlux(m_p, "b"), ev(K.diffusive_flux_y, og, "cfc", oc, None, 1, st.ob), "cfc"),
+        ("TracerZDiffusiveFlux", TE.ZDiffusiveFlux(m_p, "b"), ev(K.diffusive_flux_z, og, "ccf", oc, None, 1, st.ob), "ccf"),
+    ]
     # Smagorinsky-Lilly eddy viscosity computed by the library (scope table 8f, row 3), without and with the stratification factor
     for tag, Cb in (("", None), ("_Cb", 1.0)):
         sm = ocb.SmagorinskyLilly(C=0.16, Cb=Cb, Pr=1.0)

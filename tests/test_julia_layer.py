@@ -73,6 +73,7 @@ def test_diagnostic_table_is_the_header_enum():
     # every row of the kernel-function table names a diagnostic of the enum, and every diagnostic a Julia caller can reach
     # through an Oceanostics constructor has a row
     rows = set(re.findall(r"=>\s*\(:([A-Z_0-9]+),", JL)) | set(re.findall(r"\] = \(:([A-Z_0-9]+),", JL))
+    rows |= set(re.findall(r"\(:([A-Z_0-9]+), \d\)", JL))          # rows filled in a loop: for (row, key) in ((:U_TERM, 1), ...)
     assert rows <= set(enum)
     reached_otherwise = {"NU_SMAG"}        # compute_smagorinsky_viscosity! (no Oceanostics kernel function: Oceananigans' closure step)
     assert set(enum) - rows == reached_otherwise, sorted(set(enum) - rows)
