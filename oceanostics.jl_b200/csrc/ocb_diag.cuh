@@ -643,8 +643,10 @@ template <class T> struct Tendency {
   // hydrostatic_pressure_gradient_x / _y of the pressure in slot p
   OCB_X T px(int i, int j, int k) const { return (X.in.p(i, j, k) - X.in.p(i - 1, j, k)) * X.g.rdx; }
   OCB_X T py(int i, int j, int k) const { return (X.in.p(i, j, k) - X.in.p(i, j - 1, k)) * X.g.rdy; }
-  OCB_X T gu(int i, int j, int k) const { return ((X.in.aux[0](i, j, k) - A.divu(i, j, k) - D.d1(i, j, k) - px(i, j, k)) + bx(i, j, k)) - cx(i, j, k); }   // fcc
-  OCB_X T gv(int i, int j, int k) const { return ((X.in.aux[1](i, j, k) - A.divv(i, j, k) - D.d2(i, j, k) - py(i, j, k)) + by(i, j, k)) - cy(i, j, k); }   // cfc
+  // the whole tendency reads slot p only when the request says the model carries a hydrostatic pressure anomaly there (siblings
+  // of the same sweep may keep the nonhydrostatic pressure in that slot: uᵢ∂ᵢp)
+  OCB_X T gu(int i, int j, int k) const { return ((X.in.aux[0](i, j, k) - A.divu(i, j, k) - D.d1(i, j, k) - (w_buoyancy ? T(0) : px(i, j, k))) + bx(i, j, k)) - cx(i, j, k); }   // fcc
+  OCB_X T gv(int i, int j, int k) const { return ((X.in.aux[1](i, j, k) - A.divv(i, j, k) - D.d2(i, j, k) - (w_buoyancy ? T(0) : py(i, j, k))) + by(i, j, k)) - cy(i, j, k); }   // cfc
   OCB_X T gw(int i, int j, int k) const {                                                                                                                      // ccf
     T r = X.in.aux[2](i, j, k) - A.divw(i, j, k) - D.d3(i, j, k);
     if (w_buoyancy) r += bz(i, j, k);

@@ -180,12 +180,21 @@ __global__ void __launch_bounds__(128) ocb_filter_slide_kernel(const __grid_cons
 // (16 B/cell of traffic and one launch) never exists.  Every output goes through exactly the staged arithmetic -- x sum in tap
 // order, division, y sum in tap order, division -- so the results are bit-identical to the two staged passes.  Periodic wrap is
 // native: rows wrap by index, columns whose stencil crosses the x boundary take per-tap wrapped loads (the edge warps only).
-template <class T, int W, bool BOX>
+// EDGE = false: the columns whose x stencil lies inside the row (straight loads; the other threads leave at once);
+// EDGE = true: the 2W columns next to the x boundary, per-tap wrapped loads (launched over those columns only).
+template <class T, int W, bool BOX, bool EDGE>
 __global__ void __launch_bounds__(128) ocb_filter_xy_kernel(const __grid_constant__ PassParams<T> P, int nx, int ny, int seg) {
   constexpr int NT = 2 * W + 1;
-  const int i = P.lo[0] + blockIdx.x * blockDim.x + threadIdx.x;
+  int i = P.lo[0] + blockIdx.x * blockDim.x + threadIdx.x;
+  if (EDGE) {                                               // thread e of the edge launch: columns 1..W, then nx-W+1..nx
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= 2 * W) return;
+    i = e < W ? e + 1 : nx - 2 * W + e + 1;
+    if (i < P.lo[0] || i > P.hi[0]) return;
+  } else {
+    if (i > P.hi[0] || i - W < 1 || i + W > nx) return;
+  }
   const int k = P.lo[2] + blockIdx.y;
-  if (i > P.hi[0]) return;
   const int c0 = P.lo[1] + blockIdx.z * seg;
   const int c1 = min(c0 + seg - 1, P.hi[1]);
   if (c0 > c1) return;
@@ -196,22 +205,15 @@ __global__ void __launch_bounds__(128) ocb_filter_xy_kernel(const __grid_constan
   }
   const T* plane = P.src + (long long)k * P.ss[2];
   T* out = P.dst + i * P.ds[0] + (long long)k * P.ds[2];
-  const bool xin = i - W >= 1 && i + W <= nx;
   // the x-filtered value of column i in row r (1-based, already wrapped into 1..ny)
   auto xrow = [&](int r) -> T {
     const T* row = plane + (long long)r * P.ss[1];
     T s = T(0);
-    if (xin) {
-      const T* q = row + (i - W);
 #pragma unroll
-      for (int t = 0; t < NT; ++t) s = BOX ? s + __ldg(q + t) : s + P.weights[t] * __ldg(q + t);
-    } else {
-#pragma unroll
-      for (int t = 0; t < NT; ++t) {
-        int ii = i + t - W;
-        ii += ii < 1 ? nx : (ii > nx ? -nx : 0);
-        s = BOX ? s + __ldg(row + ii) : s + P.weights[t] * __ldg(row + ii);
-      }
+    for (int t = 0; t < NT; ++t) {
+      int ii = i + t - W;
+      if (EDGE) ii += ii < 1 ? nx : (ii > nx ? -nx : 0);
+      s = BOX ? s + __ldg(row + ii) : s + P.weights[t] * __ldg(row + ii);
     }
     return BOX ? s / T(NT) : s / wtot;
   };
@@ -221,10 +223,15 @@ __global__ void __launch_bounds__(128) ocb_filter_xy_kernel(const __grid_constan
   for (int m = 0; m < NT - 1; ++m) win[m] = xrow(wrap(c0 - W + m));
   win[NT - 1] = T(0);
   for (int c = c0; c <= c1; c += NT) {
+    // the group's 2W+1 new x-filtered rows first: their loads are independent and overlap (one row at a time leaves a warp
+    // with a single DRAM request in flight)
+    T nxt[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) nxt[t] = (c + t <= c1) ? xrow(wrap(c + t + W)) : T(0);
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
       if (c + t <= c1) {
-        win[(2 * W + t) % NT] = xrow(wrap(c + t + W));
+        win[(2 * W + t) % NT] = nxt[t];
         T s = T(0);
 #pragma unroll
         for (int j = 0; j < NT; ++j) s = BOX ? s + win[(t + j) % NT] : s + P.weights[j] * win[(t + j) % NT];
@@ -238,8 +245,9 @@ static void launch_xy_w(const PassParams<T>& P, int nx, int ny, cudaStream_t st)
   const int ni = P.hi[0] - P.lo[0] + 1, nj = P.hi[1] - P.lo[1] + 1, nk = P.hi[2] - P.lo[2] + 1;
   int seg = 256;
   if (nj < seg) seg = nj;
-  dim3 block(128, 1, 1), grid((ni + 127) / 128, nk, (nj + seg - 1) / seg);
-  ocb_filter_xy_kernel<T, W, BOX><<<grid, block, 0, st>>>(P, nx, ny, seg);
+  const int nseg = (nj + seg - 1) / seg;
+  ocb_filter_xy_kernel<T, W, BOX, true><<<dim3(1, nk, nseg), dim3(32, 1, 1), 0, st>>>(P, nx, ny, seg);        // 2W <= 16 edge columns
+  ocb_filter_xy_kernel<T, W, BOX, false><<<dim3((ni + 127) / 128, nk, nseg), dim3(128, 1, 1), 0, st>>>(P, nx, ny, seg);
 }
 template <class T, bool BOX>
 static bool launch_xy(const PassParams<T>& P, int nx, int ny, cudaStream_t st) {
