@@ -425,7 +425,10 @@ static int filter_impl(const ocb_field* src, const int32_t ext[3], const ocb_fil
   bool fuse_xy = n_pass >= 2 && passes[0].dim == 1 && passes[1].dim == 2 && passes[0].kind == passes[1].kind &&
                  passes[0].kind != OCB_FILTER_GAUSSIAN_STRETCHED && passes[0].policy == OCB_POLICY_PERIODIC &&
                  passes[1].policy == OCB_POLICY_PERIODIC && passes[0].width == passes[1].width && fast_width_compiled(passes[0].width) &&
-                 ext[0] >= 2 * passes[0].width + 1 && ext[1] >= 2 * passes[0].width + 1 && src->stride[0] == 1 && !getenv("OCB_FILTER_NO_XY");
+                 ext[0] >= 2 * passes[0].width + 1 && ext[1] >= 2 * passes[0].width + 1 && src->stride[0] == 1 && getenv("OCB_FILTER_XY");
+  // (measured at 512 x 512 x 256, 17 taps: the fused kernel 0.93 + 0.28 ms against 0.28 + 0.24 ms for the two staged passes --
+  //  2W+1 cached loads AND a 2W+1-deep register window per output leave too few loads in flight; kept behind OCB_FILTER_XY=1,
+  //  bit-identical, for tuning runs: profiles/r2_summary.md)
   if (fuse_xy && passes[0].kind == OCB_FILTER_GAUSSIAN)
     for (int t = 0; t < 2 * passes[0].width + 1; ++t) if (T(passes[0].weights[t]) != T(passes[1].weights[t])) fuse_xy = false;
   for (int ps = 0; ps < n_pass; ++ps) {
