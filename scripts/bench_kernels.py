@@ -82,8 +82,11 @@ def main():
         Nx, Ny, Nz = 512, 512, 256
         grid = ocb.RectilinearGrid((Nx, Ny, Nz), extent=(1, 1, 0.5), device=dev)
         m = ocb.NonhydrostaticModel(grid, closure=ocb.Closure(nu=1e-6, kappa=1e-7))
-        for f in (m.velocities.u, m.velocities.v, m.velocities.w, m.tracers.b):
+        for f in (m.velocities.u, m.velocities.v, m.velocities.w):
             f.interior.copy_(torch.randn(f.interior.shape, device=dev, dtype=torch.float64))
+        # buoyancy as SURVEY.md section 8d prescribes: b = N^2 z + 0.1 N^2 Lz xi
+        zc = -0.5 + (torch.arange(Nz, device=dev, dtype=torch.float64) + 0.5) * (0.5 / Nz)
+        m.tracers.b.interior.copy_(1e-5 * zc[:, None, None] + (0.1 * 1e-5 * 0.5) * torch.randn(m.tracers.b.interior.shape, device=dev, dtype=torch.float64))
         m.fill_halo_regions()
         cells = Nx * Ny * Nz
         if "filter_only" in which:        # the single staged filter alone (profiling runs)
