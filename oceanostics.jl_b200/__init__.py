@@ -18,3 +18,5 @@ from . import UMomentumEquation, VMomentumEquation, WMomentumEquation, TracerEqu
 from .SpatialFilters import BoxFilter, GaussianFilter
 
 ScalarDiffusivity = Closure
+from . import output_writers
+from .output_writers import NetCDFWriter, JLD2Writer, TimeInterval, IterationInterval, AveragedTimeInterval
