@@ -10,13 +10,16 @@ import pytest
 from helpers import State, K
 
 
-def class_sums(st, nu, kappa, jlo, jhi, klo, khi):
+def class_sums(st, nu, kappa, jlo, jhi, klo, khi, ring=False, profiles=None):
+    """ring: the kernel's ring mode -- rows jlo .. jhi only, every row weight one (the y window is a whole periodic extent or
+    one slab of a ring).  profiles = (U, V, W) oracle reduced fields: also returns the TKE-budget class sums (shear production
+    summed by faces, dissipation of u - U, turbulent kinetic energy)."""
     og = st.og
     Nx, Ny, Nz = og.N
     H = og.H[0]
     rdx, rdy, rdz = Nx / 1.0, Ny / 1.0, Nz / 1.0
     I = np.arange(1, Nx + 1)[:, None, None]
-    J = np.arange(jlo, jhi + 2)[None, :, None]                  # rows jlo .. jhi + 1 carry items
+    J = np.arange(jlo, jhi + (1 if ring else 2))[None, :, None]  # rows jlo .. jhi + 1 carry items (ring mode: the next slab's / wrapped row counts them)
     N = np.arange(klo, khi + 3)[None, None, :]                  # steps klo .. khi + 2
 
     def at(f, di=0, dj=0, dk=0):
@@ -25,6 +28,8 @@ def class_sums(st, nu, kappa, jlo, jhi, klo, khi):
     u, v, w, b, p = st.ou, st.ov, st.ow, st.ob, st.op
     inw = lambda a, lo, hi: ((a >= lo) & (a <= hi)).astype(np.float64)
     al, be, an = inw(J, jlo, jhi), inw(J - 1, jlo, jhi), inw(J + 1, jlo, jhi)
+    if ring:
+        al, be, an = np.ones_like(al), np.ones_like(al), np.ones_like(al)
     g0, g1, g2 = inw(N, klo, khi), inw(N - 1, klo, khi), inw(N - 2, klo, khi)
     hy, hyn, hz, hzp = 0.5 * (al + be), 0.5 * (al + an), 0.5 * (g0 + g1), 0.5 * (g1 + g2)
     uc, us, up_, ue = at(u), at(u, dj=-1), at(u, dk=-1), at(u, di=1)
@@ -43,7 +48,7 @@ def class_sums(st, nu, kappa, jlo, jhi, klo, khi):
     aAe = S(g0 * P12 * (rdx * hy * dvx + rdy * (al * uc - be * us)) + al * P13 * (rdx * hz * dwx + rdz * (g0 * uc - g1 * up_)) +
             P23 * (rdy * hz * (al * wc - be * ws) + rdz * hy * (g0 * vc - g1 * vp)))
     aAx = S(al * g0 * Uu * ax)
-    aAy = S(g0 * Vv * (hyn * vn - hy * vc)) + S((J == jlo) * g0 * VvS * 0.5 * vc)
+    aAy = S(g0 * Vv * (hyn * vn - hy * vc)) + (0.0 if ring else S((J == jlo) * g0 * VvS * 0.5 * vc))
     aAz = S(al * Ww * (hz * wc - hzp * wp))
     aK = S(al * g0 * uc ** 2 + hy * g0 * vc ** 2 + al * hz * wc ** 2)
     aPx, aPy, aPz = S(al * g0 * uc * (pc - pw)), S(hy * g0 * vc * (pc - ps)), S(al * hz * wc * (pc - pp))
@@ -55,7 +60,23 @@ def class_sums(st, nu, kappa, jlo, jhi, klo, khi):
     lap = rdx ** 2 * ((bp - bpw) - (bpe - bp)) + rdy ** 2 * ((bp - bps) - (bpn - bp)) + rdz ** 2 * ((bp - bpp) - dbz)
     aD = S(al * g1 * bp * lap)
     V = 1.0 / (rdx * rdy * rdz)
-    return [V * 0.5 * aK, V * -0.25 * (aAe + rdx * aAx + rdy * aAy + rdz * aAz), V * (rdx * aPx + rdy * aPy + rdz * aPz), V * 0.5 * aW,
+    extra = []
+    if profiles is not None:
+        U, Vp, W = profiles
+        prof = lambda f, dk=0: f.data[0, 0, N[0, 0, :] + dk + H - 1][None, None, :]
+        Un, Un1, Vn, Vn1, Wn = prof(U), prof(U, -1), prof(Vp), prof(Vp, -1), prof(W)
+        GUc, GUp = 0.5 * (prof(U, 1) - Un1), 0.5 * (Un - prof(U, -2))
+        GVc, GVp = 0.5 * (prof(Vp, 1) - Vn1), 0.5 * (Vn - prof(Vp, -2))
+        GWc, GWp = prof(W, 1) - Wn, Wn - prof(W, -1)
+        ucq, vcq, wcq, upq, vpq = uc - Un, vc - Vn, wc - Wn, up_ - Un1, vp - Vn1
+        S13q, S23q, dwzq = S13 - rdz * (Un - Un1), S23 - rdz * (Vn - Vn1), dwz - GWp
+        aEeP = S(hy * g0 * S12 ** 2 + al * hz * S13q ** 2 + hy * hz * S23q ** 2)
+        aEzP = S(al * g1 * dwzq ** 2)
+        aKP = S(al * g0 * ucq ** 2 + hy * g0 * vcq ** 2 + al * hz * wcq ** 2)
+        aSuv = S(al * ((ww - Wn) + wcq) * (g0 * GUc * ucq + g1 * GUp * upq)) + S((be * (ws - Wn) + al * wcq) * (g0 * GVc * vcq + g1 * GVp * vpq))
+        aSw = S(al * wcq ** 2 * (g0 * GWc + g1 * GWp))
+        extra = [V * -rdz * (0.25 * aSuv + 0.5 * aSw), V * nu * (aEeP + 2.0 * (rdx ** 2 * aEx + rdy ** 2 * aEy + rdz ** 2 * aEzP)), V * 0.5 * aKP]
+    return extra + [V * 0.5 * aK, V * -0.25 * (aAe + rdx * aAx + rdy * aAy + rdz * aAz), V * (rdx * aPx + rdy * aPy + rdz * aPz), V * 0.5 * aW,
             V * nu * (aEe + 2.0 * (rdx ** 2 * aEx + rdy ** 2 * aEy + rdz ** 2 * aEz)),
             V * 2.0 * kappa * (rdx ** 2 * aCx + rdy ** 2 * aCy + rdz ** 2 * aCz), V * 2.0 * kappa * aD]
 
@@ -78,3 +99,56 @@ def test_class_sums_reproduce_the_windowed_cell_integrals(window):
         win = c[:, jlo - 1:jhi, klo - 1:khi]
         want, scale = float(np.sum(win)) * V, float(np.sum(np.abs(win))) * V
         assert abs(g - want) <= 1e-12 * scale, (name, g, want, scale)
+
+
+def _budget_cells(st, oc):
+    og, f = st.og, st.ofields()
+    ev = K.evaluate
+    return [ev(K.kinetic_energy_ccc, og, "ccc", st.ou, st.ov, st.ow), ev(K.ke_advection_ccc, og, "ccc", f),
+            ev(K.ke_pressure_ccc, og, "ccc", f, st.op), ev(K.ke_buoyancy_ccc, og, "ccc", f, (0, 0, 1), st.ob),
+            ev(K.viscous_dissipation_rate_ccc, og, "ccc", None, f, {"closure": oc}),
+            ev(K.tracer_variance_dissipation_rate_ccc, og, "ccc", oc, None, None, st.ob), ev(K.c_div_q_c, og, "ccc", oc, None, None, st.ob)]
+
+
+def test_ring_mode_shares_add_up_to_the_global_integrals():
+    """Ring mode of the kernel (csrc/ocb_budget_sums.cuh, `y_ring`): with every row weight one and no extra row, the whole
+    periodic y extent gives the global integrals, and the shares of y slabs -- each reading ONE row beyond its slab -- add up to
+    them, although a share is not the integral over its slab's cells (the advection term moves momentum across the cut)."""
+    st = State(size=(16, 12, 10))
+    nu, kappa = 1e-6, 1e-7
+    cells = _budget_cells(st, K.Closure(nu=nu, kappa=kappa))
+    V = 1.0 / (16 * 12 * 10)
+    whole = class_sums(st, nu, kappa, 1, 12, 1, 10, ring=True)
+    slabs = [class_sums(st, nu, kappa, lo, hi, 1, 10, ring=True) for lo, hi in ((1, 4), (5, 8), (9, 12))]
+    for n, (name, c) in enumerate(zip("K ADV PR WB EPS CHI CDF".split(), cells)):
+        want, scale = float(np.sum(c)) * V, float(np.sum(np.abs(c))) * V
+        assert abs(whole[n] - want) <= 1e-12 * scale, (name, whole[n], want)
+        assert abs(sum(s[n] for s in slabs) - want) <= 1e-12 * scale, name
+    adv_cells_of_slab = float(np.sum(cells[1][:, 0:4, :])) * V
+    assert abs(slabs[0][1] - adv_cells_of_slab) > 1e-9 * float(np.sum(np.abs(cells[1][:, 0:4, :]))) * V
+
+
+@pytest.mark.parametrize("window", [None, (3, 9, 1, 10), (1, 1, 2, 2), (12, 12, 10, 10), (2, 11, 3, 8)], ids=str)
+def test_tke_budget_class_sums_reproduce_the_cell_integrals(window):
+    """The TKE-budget terms of the class-sum kernel about U(z), V(z), W(z): shear production summed over x / y / z faces, the
+    dissipation of u - U, the turbulent kinetic energy -- against the oracle's per-cell kernels
+    (src/TurbulentKineticEnergyEquation.jl:24-30, 224-240, 285-289; src/KineticEnergyEquation.jl:441-453) summed over the window."""
+    from oracle.grid import average_dims, DiffField
+    st = State(size=(16, 12, 10))
+    og = st.og
+    nu, kappa = 1e-6, 1e-7
+    oc = K.Closure(nu=nu, kappa=kappa)
+    U, Vp, W = average_dims(st.ou, (1, 2)), average_dims(st.ov, (1, 2)), average_dims(st.ow, (1, 2))
+    up, vp, wp = DiffField(st.ou, U), DiffField(st.ov, Vp), DiffField(st.ow, W)
+    ev = K.evaluate
+    cells = [ev(K.shear_production_rate_ccc, og, "ccc", up, vp, wp, U, Vp, W),
+             ev(K.viscous_dissipation_rate_ccc, og, "ccc", None, {"u": up, "v": vp, "w": wp, "b": st.ob}, {"closure": oc}),
+             ev(K.turbulent_kinetic_energy_ccc, og, "ccc", st.ou, st.ov, st.ow, U, Vp, W)]
+    jlo, jhi, klo, khi = window or (1, 12, 1, 10)
+    Vol = 1.0 / (16 * 12 * 10)
+    for ring in ([False, True] if window is None else [False]):
+        got = class_sums(st, nu, kappa, jlo, jhi, klo, khi, ring=ring, profiles=(U, Vp, W))[:3]
+        for name, c, g in zip(("SP", "EPS'", "TKE"), cells, got):
+            win = c[:, jlo - 1:jhi, klo - 1:khi]
+            want, scale = float(np.sum(win)) * Vol, float(np.sum(np.abs(win))) * Vol
+            assert abs(g - want) <= 1e-12 * scale, (name, ring, g, want, scale)
