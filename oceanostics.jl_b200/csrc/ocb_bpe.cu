@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(RS_THREADS, 3) rs_scatter(const K* __restrict_
 #pragma unroll
   for (int r = 0; r < RS_ITEMS; ++r) {
     const long long t = wbase + r * 32 + lane;
-    if (t < n) stage_i[rank[r]] = __ldg(idx_in + t);
+    if (t < n) stage_i[rank[r]] = idx_in ? __ldg(idx_in + t) : (uint32_t)t;      // no payload array: the key's position
   }
   __syncthreads();
 #pragma unroll
@@ -483,6 +483,37 @@ __global__ void bpe_scatter_uniform(const uint32_t* __restrict__ perm, const K* 
   if (bs_out) bs_out[t] = bs;
 }
 
+// The same scatter, fed in DESTINATION order: (cell, rank) pairs grouped by the region of the cell (one stable radix pass on
+// the upper bits of the cell index).  The two 8-byte stores of a block then land in a few megabytes of the destination fields,
+// which stay in L2 until their sectors are complete, instead of 2 N read-modify-written sectors all over the arrays; the
+// price is two gathers (sorted key and Psi prefix at the rank), which are reads.
+template <class T, class K>
+__global__ void bpe_scatter_bucketed(const uint32_t* __restrict__ cells, const uint32_t* __restrict__ ranks, const K* __restrict__ ks,
+                                     const double* __restrict__ psi_incl, long long n, int Nx, int Ny, UniformSlots U,
+                                     const double* __restrict__ psi_level, T* __restrict__ zstar, long long zs0, long long zs1, long long zs2,
+                                     T* __restrict__ psid, long long ps0, long long ps1, long long ps2) {
+  const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const uint32_t cell = cells[e];
+  const long long t = ranks[e];
+  const int i = (int)(cell % Nx), j = (int)((cell / Nx) % Ny), k = (int)(cell / ((long long)Nx * Ny));
+  const T zs = (T)U.centre(t);
+  zstar[i * zs0 + j * zs1 + k * zs2] = zs;
+  if (psid) {
+    const T bs = from_key(__ldg(ks + t));
+    const double ps = (t ? __ldg(psi_incl + t - 1) : 0.0) + (double)bs * ((double)zs - U.face(t));
+    psid[i * ps0 + j * ps1 + k * ps2] = (T)(psi_level[k] - ps);
+  }
+}
+template <class T, class K>
+__global__ void bpe_sorted_outputs(const uint32_t* __restrict__ perm, const K* __restrict__ ks, long long n, int64_t* __restrict__ perm_out,
+                                   T* __restrict__ bs_out) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  if (perm_out) perm_out[t] = (int64_t)perm[t] + 1;
+  if (bs_out) bs_out[t] = from_key(ks[t]);
+}
+
 struct Scratch {
   cudaStream_t st;
   void* ptrs[24];
@@ -553,8 +584,25 @@ int bpe_sort3d_uniform(const ocb_grid* g, const ocb_field* b, const ocb_field* z
     if (rc != OCB_OK) return rc;
     bpe_psi_levels_uniform<T, K><<<(Nz + 127) / 128, 128, 0, st>>>(psi, ks, n, Nz, U, (T)g->z_bottom, (T)g->d[2], psi_level);
   }
-  bpe_scatter_uniform<T, K><<<gr, 256, 0, st>>>(perm, ks, psi, n, Nx, Ny, U, psi_level, (T*)Z.p + (Z.sx + Z.sy + Z.sz), Z.sx, Z.sy, Z.sz,
-                                                p1, P.sx, P.sy, P.sz, perm_out, (T*)bs_out);
+  T* z1 = (T*)Z.p + (Z.sx + Z.sy + Z.sz);
+  if ((n >= (1ll << 20) || getenv("OCB_BPE_BUCKETED")) && !getenv("OCB_BPE_DIRECT_SCATTER")) {
+    // one stable radix pass on bits [shift, shift + 8) of the cell index: 256 destination regions (2 MB of each field at 67 M cells).
+    // The sort's idle ping-pong buffer holds the bucketed pairs.
+    int bits = 0;
+    while ((1ll << bits) < n) ++bits;
+    const int shift = bits > 8 ? bits - 8 : 0;
+    uint32_t* cells2 = reinterpret_cast<uint32_t*>(ks == ka ? kb : ka);
+    uint32_t* ranks2 = (perm == ia) ? ib : ia;
+    rs_histogram<uint32_t><<<nblocks, RS_THREADS, 0, st>>>(perm, n, shift, table, nblocks);
+    rc = device_scan<uint32_t, OP_ADD, false, true>(table, table, 256ll * nblocks, tot, st);
+    if (rc != OCB_OK) return rc;
+    rs_scatter<uint32_t><<<nblocks, RS_THREADS, 0, st>>>(perm, nullptr, cells2, ranks2, n, shift, table, nblocks);
+    bpe_scatter_bucketed<T, K><<<gr, 256, 0, st>>>(cells2, ranks2, ks, psi, n, Nx, Ny, U, psi_level, z1, Z.sx, Z.sy, Z.sz, p1, P.sx, P.sy, P.sz);
+    if (perm_out || bs_out) bpe_sorted_outputs<T, K><<<gr, 256, 0, st>>>(perm, ks, n, perm_out, (T*)bs_out);
+  } else {
+    bpe_scatter_uniform<T, K><<<gr, 256, 0, st>>>(perm, ks, psi, n, Nx, Ny, U, psi_level, z1, Z.sx, Z.sy, Z.sz, p1, P.sx, P.sy, P.sz, perm_out,
+                                                  (T*)bs_out);
+  }
   OCB_CUDA(cudaGetLastError());
   return OCB_OK;
 }

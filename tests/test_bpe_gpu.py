@@ -127,6 +127,28 @@ def test_random_field_methods_agree_and_stretched_grid():
     np.testing.assert_allclose(zs.interior_ijk(), want["zstar"], rtol=0, atol=tol)
 
 
+def test_bucketed_scatter_equals_the_direct_one(monkeypatch):
+    """Above 2^20 cells the ThreeDimensionalSort epilogue buckets the (cell, rank) pairs by destination region before the final
+    scatter; forced here at a size the oracle reaches: the same z*, Psi_delta, permutation and sorted buoyancy bit for bit."""
+    rng = np.random.default_rng(21)
+    Nx, Ny, Nz = 40, 33, 29
+    vals = rng.standard_normal((Nx, Ny, Nz)) * 1e-6 + 1e-5 * (-1 + (np.arange(Nz) + 0.5) / Nz)
+    vals[3:9, :, 7] = vals[3, 0, 7]
+    og, pg, ob, pb = _pair((Nx, Ny, Nz), (-1, 0), vals)
+    direct = BPE.reference_height(pb)
+    torch.cuda.synchronize()
+    monkeypatch.setenv("OCB_BPE_BUCKETED", "1")
+    pb2 = mirror(ob, pg)
+    buck = BPE.reference_height(pb2)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(buck.interior_ijk(), direct.interior_ijk())
+    np.testing.assert_array_equal(buck.reference_potential.interior_ijk(), direct.reference_potential.interior_ijk())
+    np.testing.assert_array_equal(buck.permutation.cpu().numpy(), direct.permutation.cpu().numpy())
+    np.testing.assert_array_equal(buck.sorted_buoyancy.cpu().numpy(), direct.sorted_buoyancy.cpu().numpy())
+    want = OB.reference_height(ob)
+    np.testing.assert_allclose(buck.interior_ijk(), want["zstar"], rtol=0, atol=ztol(Nx * Ny * Nz))
+
+
 def test_recompute_on_evolution_and_unknown_methods():
     rng = np.random.default_rng(2)
     og, pg, ob, pb = _pair((8, 8, 8), (-1, 0), rng.standard_normal((8, 8, 8)))
