@@ -78,10 +78,18 @@ __global__ void __launch_bounds__(RS_THREADS) rs_histogram(const K* __restrict__
 // stable scatter of one tile: warp w owns the contiguous sub-tile [w*512, (w+1)*512), walked in 16 rounds of 32.
 // The tile is first put in digit order in shared memory (keys, then the payload through the same buffer), so that the
 // global writes are runs of consecutive addresses per digit (16 keys = 128 B on average) instead of one sector per key.
-template <class K>
+// CHAINED = false: the tile's global digit offsets come from the scanned per-tile histogram table (`offsets`, digit-major).
+// CHAINED = true ("onesweep"): no histogram pass and no table scan -- `offsets` holds the 256 global digit bases of this pass
+// (from ONE up-front histogram of all digits), tiles take their number from a ticket counter, publish their digit counts in
+// `desc[tile][digit]` (count | flag in one word: AGGREGATE = the tile's own count, INCLUSIVE = everything up to and including the
+// tile) and thread d looks back over the preceding tiles' words of digit d until it meets an INCLUSIVE one (decoupled look-back;
+// a tile only ever waits for tiles with smaller tickets, which are running).  A wait is bounded: a stuck look-back sets desc's
+// error word and moves on instead of hanging the device.
+constexpr uint32_t RS_AGG = 1u << 30, RS_INCL = 1u << 31, RS_CNT = (1u << 30) - 1u;
+template <class K, bool CHAINED = false>
 __global__ void __launch_bounds__(RS_THREADS, 3) rs_scatter(const K* __restrict__ keys_in, const uint32_t* __restrict__ idx_in, K* __restrict__ keys_out,
                                                           uint32_t* __restrict__ idx_out, long long n, int shift,
-                                                          const uint32_t* __restrict__ offsets, int nblocks) {
+                                                          const uint32_t* __restrict__ offsets, int nblocks, uint32_t* desc = nullptr) {
   __shared__ uint32_t wcount[RS_WARPS][256];     // per-warp running digit counts -> per-warp digit bases inside the tile
   __shared__ uint32_t gbase[256];                // global position of the tile's first key of each digit, minus its tile position
   __shared__ uint32_t tstart[256];               // tile position of the first key of each digit
@@ -89,8 +97,15 @@ __global__ void __launch_bounds__(RS_THREADS, 3) rs_scatter(const K* __restrict_
   __shared__ K stage[RS_TILE];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int d = lane; d < 256; d += 32) { wcount[warp][d] = 0; reinterpret_cast<uint32_t*>(stage)[warp * 256 + d] = 0; }
+  int tile = blockIdx.x;
+  if (CHAINED) {                                          // desc: [nblocks][256] words, then the ticket counter, then the error word
+    if (threadIdx.x == 0) wtot[0] = atomicAdd(desc + (size_t)nblocks * 256, 1u);
+    __syncthreads();
+    tile = (int)wtot[0];
+    __syncthreads();
+  }
   __syncwarp();
-  const long long tbase = (long long)blockIdx.x * RS_TILE;
+  const long long tbase = (long long)tile * RS_TILE;
   const long long wbase = tbase + (long long)warp * (RS_ITEMS * 32);
   const int ntile = (int)((n - tbase) < (long long)RS_TILE ? (n - tbase) : (long long)RS_TILE);
   K key[RS_ITEMS];
@@ -141,7 +156,28 @@ __global__ void __launch_bounds__(RS_THREADS, 3) rs_scatter(const K* __restrict_
     for (int w = 0; w < RS_WARPS; ++w) if (w < warp) before += wtot[w];
     const uint32_t start = before + inc - run;
     tstart[d] = start;
-    gbase[d] = offsets[(size_t)d * nblocks + blockIdx.x] - start;
+    if (!CHAINED) {
+      gbase[d] = offsets[(size_t)d * nblocks + tile] - start;
+    } else {
+      volatile uint32_t* D = desc;
+      uint32_t excl = 0;
+      if (tile == 0) {
+        D[d] = run | RS_INCL;
+      } else {
+        D[(size_t)tile * 256 + d] = run | RS_AGG;
+        int j = tile - 1;
+        unsigned spins = 0;
+        for (;;) {
+          const uint32_t v = D[(size_t)j * 256 + d];
+          if (v & RS_INCL) { excl += v & RS_CNT; break; }
+          if (v & RS_AGG) { excl += v & RS_CNT; --j; spins = 0; continue; }
+          if (++spins > (1u << 22)) { D[(size_t)nblocks * 256 + 1] = 1u; break; }
+          __nanosleep(20);
+        }
+        D[(size_t)tile * 256 + d] = (excl + run) | RS_INCL;
+      }
+      gbase[d] = offsets[d] + excl - start;
+    }
   }
   __syncthreads();
   // keys: into digit order in shared memory, then out in runs
@@ -179,6 +215,50 @@ __global__ void __launch_bounds__(RS_THREADS, 3) rs_scatter(const K* __restrict_
     const int e = r * RS_THREADS + threadIdx.x;
     if (e < ntile) idx_out[pos[r]] = stage_i[e];
   }
+}
+
+// all digit histograms of the keys in one read: hist[pass][256] (global digit counts do not depend on the order of the keys)
+template <class K>
+__global__ void __launch_bounds__(RS_THREADS) rs_histogram_all(const K* __restrict__ keys, long long n, uint32_t* __restrict__ hist) {
+  constexpr int NP = KeyTraits<K>::BITS / 8;
+  __shared__ uint32_t h[NP][256];
+  for (int p = 0; p < NP; ++p) h[p][threadIdx.x] = 0;
+  __syncthreads();
+  for (long long base = (long long)blockIdx.x * RS_TILE; base < n; base += (long long)gridDim.x * RS_TILE) {
+#pragma unroll 4
+    for (int r = 0; r < RS_ITEMS; ++r) {
+      const long long t = base + r * RS_THREADS + threadIdx.x;
+      const bool ok = t < n;
+      const K key = ok ? __ldg(keys + t) : (K)0;
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        const uint32_t dig = (uint32_t)(key >> (8 * p)) & 255u;
+        // the upper digits of real data are nearly constant: one add per warp when all its lanes agree
+        int same = 0;
+        const unsigned act = __ballot_sync(0xffffffffu, ok);
+        if (act == 0xffffffffu) __match_all_sync(0xffffffffu, dig, &same);
+        if (same) { if ((threadIdx.x & 31) == 0) atomicAdd(&h[p][dig], 32u); }
+        else if (ok) atomicAdd(&h[p][dig], 1u);
+      }
+    }
+  }
+  __syncthreads();
+  for (int p = 0; p < NP; ++p) { const uint32_t c = h[p][threadIdx.x]; if (c) atomicAdd(hist + p * 256 + threadIdx.x, c); }
+}
+// exclusive scan of each pass's 256 counts, in place (one block per pass)
+__global__ void __launch_bounds__(256) rs_digit_bases(uint32_t* __restrict__ hist) {
+  __shared__ uint32_t sh[256];
+  uint32_t* h = hist + blockIdx.x * 256;
+  const uint32_t c = h[threadIdx.x];
+  sh[threadIdx.x] = c;
+  __syncthreads();
+  for (int o = 1; o < 256; o <<= 1) {
+    const uint32_t v = threadIdx.x >= o ? sh[threadIdx.x - o] : 0u;
+    __syncthreads();
+    sh[threadIdx.x] += v;
+    __syncthreads();
+  }
+  h[threadIdx.x] = sh[threadIdx.x] - c;
 }
 
 // ---- block scans ----------------------------------------------------------------------------------------------
@@ -314,6 +394,29 @@ int radix_sort_pairs(K* keys_a, uint32_t* idx_a, K* keys_b, uint32_t* idx_b, lon
   K* kin = keys_a; K* kout = keys_b;
   uint32_t* iin = idx_a; uint32_t* iout = idx_b;
   const long long ntab = 256ll * nblocks;
+  if (n < (1ll << 30) && !getenv("OCB_SORT_TABLE_SCAN")) {
+    // onesweep: one histogram of all digits up front, then ONE kernel per digit.  `table` (256 nblocks words + the allocation's
+    // spare 64) holds the tile descriptors of the current pass, then the ticket counter and the error word; `table_tot` (sized
+    // for it by the callers) the digit histograms / bases.
+    constexpr int NP = KeyTraits<K>::BITS / 8;
+    {
+      uint32_t* hist = table_tot;
+      OCB_CUDA(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * NP * 256, st));
+      int hb = ocb_sm_count() * 4;
+      if (hb > nblocks) hb = nblocks;
+      rs_histogram_all<K><<<hb, RS_THREADS, 0, st>>>(kin, n, hist);
+      rs_digit_bases<<<NP, 256, 0, st>>>(hist);
+      for (int p = 0; p < NP; ++p) {
+        OCB_CUDA(cudaMemsetAsync(table, 0, sizeof(uint32_t) * ((size_t)ntab + 2), st));      // descriptors, ticket, error word
+        rs_scatter<K, true><<<nblocks, RS_THREADS, 0, st>>>(kin, iin, kout, iout, n, 8 * p, hist + p * 256, nblocks, table);
+        K* tk = kin; kin = kout; kout = tk;
+        uint32_t* ti = iin; iin = iout; iout = ti;
+      }
+      OCB_CUDA(cudaGetLastError());
+      *keys_sorted = kin; *idx_sorted = iin;
+      return OCB_OK;
+    }
+  }
   for (int shift = 0; shift < KeyTraits<K>::BITS; shift += 8) {
     rs_histogram<K><<<nblocks, RS_THREADS, 0, st>>>(kin, n, shift, table, nblocks);
     int rc = device_scan<uint32_t, OP_ADD, false, true>(table, table, ntab, table_tot, st);
@@ -535,7 +638,7 @@ int sort_impl(const T* keys_in, T* keys_out, uint32_t* perm_out, long long n, cu
   K* ka = S.get<K>(n); K* kb = S.get<K>(n);
   uint32_t* ia = S.get<uint32_t>(n); uint32_t* ib = S.get<uint32_t>(n);
   uint32_t* table = S.get<uint32_t>(256ull * nblocks);
-  uint32_t* tot = S.get<uint32_t>((256ull * nblocks + SC_CHUNK - 1) / SC_CHUNK + 1);
+  uint32_t* tot = S.get<uint32_t>((256ull * nblocks + SC_CHUNK - 1) / SC_CHUNK + 1 + 8 * 256);   // + the digit histograms of the onesweep path
   if (!ka || !kb || !ia || !ib || !table || !tot) OCB_FAIL(OCB_ERR_ALLOC, "out of device memory for the sort scratch");
   const unsigned g = (unsigned)((n + 255) / 256);
   rs_make_keys<K><<<g, 256, 0, st>>>(keys_in, ka, ia, n);
@@ -558,7 +661,7 @@ int bpe_sort3d_uniform(const ocb_grid* g, const ocb_field* b, const ocb_field* z
   K* ka = S.get<K>(n); K* kb = S.get<K>(n);
   uint32_t* ia = S.get<uint32_t>(n); uint32_t* ib = S.get<uint32_t>(n);
   uint32_t* table = S.get<uint32_t>(256ull * nblocks);
-  uint32_t* tot = S.get<uint32_t>((256ull * nblocks + SC_CHUNK - 1) / SC_CHUNK + 1);
+  uint32_t* tot = S.get<uint32_t>((256ull * nblocks + SC_CHUNK - 1) / SC_CHUNK + 1 + 8 * 256);   // + the digit histograms of the onesweep path
   double* psi = S.get<double>(n);
   double* dtot = S.get<double>((n + SC_CHUNK - 1) / SC_CHUNK + 1);
   double* psi_level = S.get<double>(Nz);
@@ -621,7 +724,7 @@ int bpe_impl(const ocb_grid* g, const ocb_field* b, int method, const ocb_field*
   K* ka = S.get<K>(n); K* kb = S.get<K>(n);
   uint32_t* ia = S.get<uint32_t>(n); uint32_t* ib = S.get<uint32_t>(n);
   uint32_t* table = S.get<uint32_t>(256ull * nblocks);
-  uint32_t* tot = S.get<uint32_t>((256ull * nblocks + SC_CHUNK - 1) / SC_CHUNK + 1);
+  uint32_t* tot = S.get<uint32_t>((256ull * nblocks + SC_CHUNK - 1) / SC_CHUNK + 1 + 8 * 256);   // + the digit histograms of the onesweep path
   double* dV = S.get<double>(n); double* cum = S.get<double>(n); double* bdz = S.get<double>(n); double* psi = S.get<double>(n);
   double* dtot = S.get<double>((n + SC_CHUNK - 1) / SC_CHUNK + 1);
   double *den = nullptr, *nol = nullptr;

@@ -168,6 +168,8 @@ class _Writer:
         time = float(clock.time)
         s = self.schedule
         if isinstance(s, AveragedTimeInterval):
+            if self._last_time is None:            # first call: the next output is the first multiple of the interval after now
+                s.next = (np.floor(time / s.interval + 1e-9) + 1) * s.interval
             dt = 0.0 if self._last_time is None else time - self._last_time
             self._last_time = time
             if s.collecting(time) and dt > 0:
