@@ -165,31 +165,14 @@ __global__ void __launch_bounds__(RS_THREADS, 3) rs_scatter(const K* __restrict_
         D[d] = run | RS_INCL;
       } else {
         D[(size_t)tile * 256 + d] = run | RS_AGG;
-        // look back LB tiles at a time: the loads of a batch are independent (one L2 round trip for LB predecessors; the first
-        // wave of tiles starts together, so the last of them walks over hundreds of aggregates)
-        constexpr int LB = 8;
         int j = tile - 1;
         unsigned spins = 0;
-        bool done = false;
-        while (!done) {
-          uint32_t v[LB];
-#pragma unroll
-          for (int q = 0; q < LB; ++q) v[q] = (j - q >= 0) ? (uint32_t)D[(size_t)(j - q) * 256 + d] : (uint32_t)(1u << 31);
-          int used = 0;
-#pragma unroll
-          for (int q = 0; q < LB; ++q) {
-            if (done || used < q) continue;                       // stop at the first word that is not published yet
-            if (v[q] & RS_INCL) { excl += v[q] & RS_CNT; done = true; }
-            else if (v[q] & RS_AGG) { excl += v[q] & RS_CNT; used = q + 1; }
-          }
-          if (done) break;
-          j -= used;
-          if (used == 0) {
-            if (++spins > (1u << 22)) { D[(size_t)nblocks * 256 + 1] = 1u; break; }
-            __nanosleep(20);
-          } else {
-            spins = 0;
-          }
+        for (;;) {
+          const uint32_t v = D[(size_t)j * 256 + d];
+          if (v & RS_INCL) { excl += v & RS_CNT; break; }
+          if (v & RS_AGG) { excl += v & RS_CNT; --j; spins = 0; continue; }
+          if (++spins > (1u << 22)) { D[(size_t)nblocks * 256 + 1] = 1u; break; }
+          __nanosleep(20);
         }
         D[(size_t)tile * 256 + d] = (excl + run) | RS_INCL;
       }
