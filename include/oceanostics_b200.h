@@ -172,8 +172,9 @@ enum {
   OCB_REQ_COLLOCATED = 1 << 7, /* PI built with collocate_diagonals=true */
   OCB_REQ_CARRIED_HEIGHT = 1 << 8, /* APE on a VerticalSort column: the parcel's own height is the field aux[3], not the grid's z
                                       (4-argument local_ape_ccc, AvailablePotentialEnergyEquation.jl:43) */
-  OCB_REQ_HYDROSTATIC_SPLIT = 1 << 9 /* KE_TENDENCY: the model carries a hydrostatic pressure anomaly pHY′ (slot p), so the vertical momentum
-                                      tendency has no buoyancy term (Oceananigans' w_velocity_tendency) */
+  OCB_REQ_HYDROSTATIC_SPLIT = 1 << 9 /* KE_TENDENCY / U,V,W_TERM tendency: the model carries a hydrostatic pressure anomaly pHY′ in slot p -- its
+                                      horizontal gradient enters the u, v tendencies and the vertical momentum tendency has no buoyancy term
+                                      (Oceananigans' w_velocity_tendency).  Without the flag the tendency does not read slot p at all. */
 };
 
 typedef struct {

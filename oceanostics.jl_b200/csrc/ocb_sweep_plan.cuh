@@ -47,6 +47,17 @@ static inline int ocb_diag_needs(int diag) {
   }
 }
 
+// how many halo cells a diagnostic reads beyond the interior along each axis: 2 for the terms that
+// difference a flux which itself reaches one cell out (Centered second-order momentum advection, the viscous-flux divergence,
+// the tendencies built from them) and for the tilted Richardson number, 1 for everything else
+static inline int ocb_diag_reach(int diag) {
+  switch (diag) {
+    case OCB_DIAG_ADV: case OCB_DIAG_KE_STRESS: case OCB_DIAG_KE_TENDENCY: case OCB_DIAG_U_TERM: case OCB_DIAG_V_TERM:
+    case OCB_DIAG_W_TERM: case OCB_DIAG_RI: return 2;
+    default: return 1;
+  }
+}
+
 template <class T>
 struct ZTables {     // pointers pre-offset so that table[k] is valid for k = 1-Hz .. Nz+Hz+1
   const T *dzc, *dzf, *rdzc, *rdzf, *zc, *zf;
@@ -155,5 +166,25 @@ static int ocb_build_sweep_params(const ocb_grid* grid, const ocb_sweep_inputs* 
     }
   }
   P.nslots = nslots;
+  // every array operand must carry the halo the requested stencils reach into (a thin halo would be read out of bounds)
+  int reach = 1;
+  for (int r = 0; r < n; ++r) if (ocb_diag_reach(reqs[r].diag) > reach) reach = ocb_diag_reach(reqs[r].diag);
+  const ocb_field* arr[] = {&in->u, &in->v, &in->w, &in->b, &in->p, &in->U, &in->V, &in->W, &in->B, &in->aux[0], &in->aux[1], &in->aux[2],
+                            &in->aux[3], &in->aux[4], &in->aux[5], &in->aux[6], &in->closure.nu_fields[0], &in->closure.nu_fields[1],
+                            &in->closure.kappa_fields[0], &in->closure.kappa_fields[1]};
+  const char* names[] = {"u", "v", "w", "b", "p", "U", "V", "W", "B", "aux[0]", "aux[1]", "aux[2]", "aux[3]", "aux[4]", "aux[5]", "aux[6]",
+                         "closure.nu_fields[0]", "closure.nu_fields[1]", "closure.kappa_fields[0]", "closure.kappa_fields[1]"};
+  for (int a = 0; a < 20; ++a) {
+    const ocb_field& f = *arr[a];
+    if (f.kind != OCB_FIELD_ARRAY || !f.data) continue;
+    if (a >= 16 && a < 18 && a - 16 >= c.n_nu_fields) continue;
+    if (a >= 18 && a - 18 >= c.n_kappa_fields) continue;
+    const int need = a < 5 ? reach : 1;                 // means, aux and closure fields are read one cell out at most
+    for (int d = 0; d < 3; ++d) {
+      if (f.loc[d] == OCB_NOTHING) continue;
+      OCB_REQUIRE(f.halo[d] >= need, "operand `%s` has a halo of %d along axis %d, but the requested diagnostics read %d cell(s) beyond the interior",
+                  names[a], f.halo[d], d + 1, need);
+    }
+  }
   return OCB_OK;
 }

@@ -175,3 +175,9 @@ def test_error_behaviour():
     bad = ocb.Field(ocb.KineticEnergyEquation.KineticEnergy(m), indices=((1, 9), None, None))   # window past Nx
     with pytest.raises(ValueError):
         bad.compute()
+    # operands must carry the halo the stencils reach into: a one-cell halo serves the kinetic energy, not the advection term
+    thin = State(size=(8, 8, 4), device="cuda", halo=(1, 1, 1))
+    mt = thin.model(closure=thin.closures()["scalar"][1])
+    ocb.Field(ocb.KineticEnergyEquation.KineticEnergy(mt)).compute()
+    with pytest.raises(ValueError, match="halo of 1"):
+        ocb.Field(ocb.KineticEnergyEquation.KineticEnergyAdvection(mt)).compute()
