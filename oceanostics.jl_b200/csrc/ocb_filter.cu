@@ -13,6 +13,7 @@
 #include "ocb_common.cuh"
 #include <math.h>
 #include <stdlib.h>
+#include <type_traits>
 
 template <class T>
 struct PassParams {
@@ -133,9 +134,13 @@ __global__ void __launch_bounds__(256) ocb_filter_x_kernel(const __grid_constant
 // (2) y / z pass: a thread slides a register window of 2W+1 inputs along the filtered axis -- one load, 2W+1 FMAs and
 // one store per output.  Threads run along x (coalesced); blockIdx.y walks the third axis, blockIdx.z the segments of
 // the filtered axis.  The window rotates through compile-time slot indices (the loop is unrolled 2W+1 times).
-template <class T, int W, bool BOX>
+// WRAP: the axis is periodic -- the kernel covers every output of the window and rows / planes beyond the ends are read at
+// their wrapped index (no boundary-band launches for a periodic pass).
+template <class T, int W, bool BOX, bool WRAP = false>
 __global__ void __launch_bounds__(128) ocb_filter_slide_kernel(const __grid_constant__ PassParams<T> P, int c_lo, int c_hi, int seg) {
   constexpr int NT = 2 * W + 1;
+  const int next = P.extent;
+  auto wr = [&](int r) { return WRAP ? (r < 1 ? r + next : (r > next ? r - next : r)) : r; };
   const int dim = P.dim, oth = dim == 1 ? 2 : 1;                 // filtered axis, and the remaining (non-x) axis
   const int i = P.lo[0] + blockIdx.x * blockDim.x + threadIdx.x;
   const int o = P.lo[oth] + blockIdx.y;
@@ -153,14 +158,14 @@ __global__ void __launch_bounds__(128) ocb_filter_slide_kernel(const __grid_cons
   }
   T win[NT];
 #pragma unroll
-  for (int m = 0; m < NT - 1; ++m) win[m] = __ldg(in + (long long)(c0 - W + m) * sd);
+  for (int m = 0; m < NT - 1; ++m) win[m] = __ldg(in + (long long)wr(c0 - W + m) * sd);
   win[NT - 1] = T(0);
   for (int c = c0; c <= c1; c += NT) {
     // the group's 2W+1 new inputs first, as independent loads: one load per output in program order leaves a warp with a
     // single request in flight, and the pass then runs at memory latency (0.35 ms) instead of bandwidth
     T nxt[NT];
 #pragma unroll
-    for (int t = 0; t < NT; ++t) nxt[t] = (c + t <= c1) ? __ldg(in + (long long)(c + t + W) * sd) : T(0);
+    for (int t = 0; t < NT; ++t) nxt[t] = (c + t <= c1) ? __ldg(in + (long long)wr(c + t + W) * sd) : T(0);
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
       if (c + t <= c1) {
@@ -272,13 +277,16 @@ static bool launch_xy(const PassParams<T>& P, int nx, int ny, cudaStream_t st) {
 __device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
 
 // x pass: outputs (i, i+1) need the 2W+2 inputs i-W .. i+1+W = W+1 aligned pairs.
-template <int W, bool BOX>
+// WRAP: x is periodic -- pairs whose window crosses an end of the row read their taps one by one at the wrapped column.
+template <int W, bool BOX, bool WRAP = false>
 __global__ void __launch_bounds__(256) ocb_filter_x2_kernel(const __grid_constant__ PassParams<double> P, int i_first) {
   constexpr int NT = 2 * W + 1;
   const int i = i_first + 2 * (blockIdx.x * blockDim.x + threadIdx.x);      // i - W is an aligned element
   const int j = P.lo[1] + blockIdx.y * blockDim.y + threadIdx.y;
   if (i > P.hi[0] || j > P.hi[1]) return;
   const bool v0 = i >= P.lo[0], v1 = i + 1 <= P.hi[0];
+  const int nx = P.extent;
+  const bool crossing = WRAP && (i - W < 1 || i + 1 + W > nx);
   double wtot = 0.0;
   if (!BOX) {
 #pragma unroll
@@ -287,8 +295,14 @@ __global__ void __launch_bounds__(256) ocb_filter_x2_kernel(const __grid_constan
   for (int k = P.lo[2] + blockIdx.z; k <= P.hi[2]; k += gridDim.z) {
     const double* q = P.src + (long long)(i - W) + j * P.ss[1] + k * P.ss[2];
     double v[2 * W + 2];
+    if (crossing) {
+      const double* row = P.src + j * P.ss[1] + k * P.ss[2];
 #pragma unroll
-    for (int m = 0; m <= W; ++m) { const double2 d = ldg2(q + 2 * m); v[2 * m] = d.x; v[2 * m + 1] = d.y; }
+      for (int m = 0; m < 2 * W + 2; ++m) { int ii = i - W + m; ii += ii < 1 ? nx : (ii > nx ? -nx : 0); v[m] = __ldg(row + ii); }
+    } else {
+#pragma unroll
+      for (int m = 0; m <= W; ++m) { const double2 d = ldg2(q + 2 * m); v[2 * m] = d.x; v[2 * m + 1] = d.y; }
+    }
     double s0 = 0.0, s1 = 0.0;
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
@@ -305,13 +319,15 @@ __global__ void __launch_bounds__(256) ocb_filter_x2_kernel(const __grid_constan
 static bool pair_loads_ok(const PassParams<double>& P) {
   return P.pairs_ok && P.ss[0] == 1 && (P.ss[1] & 1) == 0 && (P.ss[2] & 1) == 0 && ((uintptr_t)P.src & 7) == 0 && !getenv("OCB_FILTER_NO_PAIRS");
 }
+template <class T> static bool pair_loads_ok_any(const PassParams<T>&) { return false; }
+template <> bool pair_loads_ok_any<double>(const PassParams<double>& P) { return pair_loads_ok(P); }
 // the first aligned element at or below index `i` of a row (rows share their parity because the pitches are even)
 static int aligned_at_or_below(const PassParams<double>& P, int i) {
   const uintptr_t a = (uintptr_t)(P.src + i);
   return (a & 15) ? i - 1 : i;
 }
 template <int W, bool BOX>
-static bool launch_pairs(const PassParams<double>& P, int c_lo, int c_hi, cudaStream_t st) {
+static bool launch_pairs(const PassParams<double>& P, int c_lo, int c_hi, cudaStream_t st, bool wrap) {
   if (!pair_loads_ok(P)) return false;
   PassParams<double> Q = P;
   if (P.dim == 0) {
@@ -321,21 +337,30 @@ static bool launch_pairs(const PassParams<double>& P, int c_lo, int c_hi, cudaSt
     // the first pair may reach one element below c_lo - W and the last one above c_hi + W: both exist (c_lo - W >= 1 means the
     // row has an element at index 0 only as a halo or as the previous row's end; the value is loaded but never used)
     dim3 block(64, 4, 1), grid((npair + 63) / 64, (nj + 3) / 4, nk < 128 ? nk : 128);
-    ocb_filter_x2_kernel<W, BOX><<<grid, block, 0, st>>>(Q, i_first);
+    if (wrap) ocb_filter_x2_kernel<W, BOX, true><<<grid, block, 0, st>>>(Q, i_first);
+    else ocb_filter_x2_kernel<W, BOX><<<grid, block, 0, st>>>(Q, i_first);
   } else {
     return false;                      // y / z passes: the one-column sliding-window kernel (a two-column window needs 108
                                        // registers and measured slower: 0.42 vs 0.35 ms)
   }
   return true;
 }
-template <class T, int W, bool BOX> struct PairLauncher { static bool go(const PassParams<T>&, int, int, cudaStream_t) { return false; } };
+template <class T, int W, bool BOX> struct PairLauncher { static bool go(const PassParams<T>&, int, int, cudaStream_t, bool) { return false; } };
 template <int W, bool BOX> struct PairLauncher<double, W, BOX> {
-  static bool go(const PassParams<double>& P, int c_lo, int c_hi, cudaStream_t st) { return launch_pairs<W, BOX>(P, c_lo, c_hi, st); }
+  static bool go(const PassParams<double>& P, int c_lo, int c_hi, cudaStream_t st, bool wrap) { return launch_pairs<W, BOX>(P, c_lo, c_hi, st, wrap); }
 };
 
+// can the fast kernels of this pass cover a periodic axis end to end (wrapped reads instead of boundary bands)?
+template <class T>
+static bool wrap_capable(const PassParams<T>& P) {
+  if (P.policy != OCB_POLICY_PERIODIC || getenv("OCB_FILTER_NO_WRAP")) return false;
+  if (P.dim == 0) return std::is_same<T, double>::value && pair_loads_ok_any(P);
+  return true;
+}
+
 template <class T, int W, bool BOX>
-static void launch_fast_w(const PassParams<T>& P, int c_lo, int c_hi, cudaStream_t st) {
-  if (PairLauncher<T, W, BOX>::go(P, c_lo, c_hi, st)) return;
+static void launch_fast_w(const PassParams<T>& P, int c_lo, int c_hi, cudaStream_t st, bool wrap) {
+  if (PairLauncher<T, W, BOX>::go(P, c_lo, c_hi, st, wrap)) return;
   PassParams<T> Q = P;
   if (P.dim == 0) {
     Q.lo[0] = c_lo; Q.hi[0] = c_hi;
@@ -348,21 +373,22 @@ static void launch_fast_w(const PassParams<T>& P, int c_lo, int c_hi, cudaStream
     int seg = 128;
     if (nc < seg) seg = nc;
     dim3 block(128, 1, 1), grid((ni + 127) / 128, no, (nc + seg - 1) / seg);
-    ocb_filter_slide_kernel<T, W, BOX><<<grid, block, 0, st>>>(Q, c_lo, c_hi, seg);
+    if (wrap) ocb_filter_slide_kernel<T, W, BOX, true><<<grid, block, 0, st>>>(Q, c_lo, c_hi, seg);
+    else ocb_filter_slide_kernel<T, W, BOX><<<grid, block, 0, st>>>(Q, c_lo, c_hi, seg);
   }
 }
 static bool fast_width_compiled(int w) { return (w >= 1 && w <= 6) || w == 8; }
 // returns false when no fast instantiation exists for this half width
 template <class T, bool BOX>
-static bool launch_fast(const PassParams<T>& P, int c_lo, int c_hi, cudaStream_t st) {
+static bool launch_fast(const PassParams<T>& P, int c_lo, int c_hi, cudaStream_t st, bool wrap = false) {
   switch (P.width) {
-    case 1: launch_fast_w<T, 1, BOX>(P, c_lo, c_hi, st); return true;
-    case 2: launch_fast_w<T, 2, BOX>(P, c_lo, c_hi, st); return true;
-    case 3: launch_fast_w<T, 3, BOX>(P, c_lo, c_hi, st); return true;
-    case 4: launch_fast_w<T, 4, BOX>(P, c_lo, c_hi, st); return true;
-    case 5: launch_fast_w<T, 5, BOX>(P, c_lo, c_hi, st); return true;
-    case 6: launch_fast_w<T, 6, BOX>(P, c_lo, c_hi, st); return true;
-    case 8: launch_fast_w<T, 8, BOX>(P, c_lo, c_hi, st); return true;
+    case 1: launch_fast_w<T, 1, BOX>(P, c_lo, c_hi, st, wrap); return true;
+    case 2: launch_fast_w<T, 2, BOX>(P, c_lo, c_hi, st, wrap); return true;
+    case 3: launch_fast_w<T, 3, BOX>(P, c_lo, c_hi, st, wrap); return true;
+    case 4: launch_fast_w<T, 4, BOX>(P, c_lo, c_hi, st, wrap); return true;
+    case 5: launch_fast_w<T, 5, BOX>(P, c_lo, c_hi, st, wrap); return true;
+    case 6: launch_fast_w<T, 6, BOX>(P, c_lo, c_hi, st, wrap); return true;
+    case 8: launch_fast_w<T, 8, BOX>(P, c_lo, c_hi, st, wrap); return true;
     default: return false;
   }
 }
@@ -494,7 +520,10 @@ static int filter_impl(const ocb_field* src, const int32_t ext[3], const ocb_fil
       }
       fast = fast_width_compiled(fp.width);
     }
-    if (fast) {
+    if (fast && wrap_capable<T>(P) && P.lo[dm] == 1 && P.hi[dm] == fp.extent && fp.extent >= 2 * fp.width + 1) {
+      // a periodic axis covered end to end: the fast kernel reads beyond the ends at the wrapped index, no boundary bands
+      if (fp.kind == OCB_FILTER_BOX) launch_fast<T, true>(P, P.lo[dm], P.hi[dm], st, true); else launch_fast<T, false>(P, P.lo[dm], P.hi[dm], st, true);
+    } else if (fast) {
       // bands first: their few blocks start at once and the interior kernel fills the rest of the machine
       PassParams<T> B = P;
       B.hi[dm] = c_lo - 1; launch_generic(B, bs ? bs->s[0] : st);           // low band
