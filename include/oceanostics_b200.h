@@ -172,6 +172,8 @@ enum {
   OCB_REQ_COLLOCATED = 1 << 7, /* PI built with collocate_diagonals=true */
   OCB_REQ_CARRIED_HEIGHT = 1 << 8, /* APE on a VerticalSort column: the parcel's own height is the field aux[3], not the grid's z
                                       (4-argument local_ape_ccc, AvailablePotentialEnergyEquation.jl:43) */
+  OCB_REQ_CENTERED4 = 1 << 10,     /* ADV / KE_TENDENCY / C_TENDENCY / U,V,W,C_TERM: Centered(order = 4) advection -- (-1, 7, 7, -1)/12 symmetric interpolation of
+                                      the advecting and the advected quantity, order 2 next to the walls of a Bounded axis; default: Centered(order = 2) */
   OCB_REQ_HYDROSTATIC_SPLIT = 1 << 9 /* KE_TENDENCY / U,V,W_TERM tendency: the model carries a hydrostatic pressure anomaly pHY′ in slot p -- its
                                       horizontal gradient enters the u, v tendencies and the vertical momentum tendency has no buoyancy term
                                       (Oceananigans' w_velocity_tendency).  Without the flag the tendency does not read slot p at all. */

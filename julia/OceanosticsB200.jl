@@ -45,6 +45,7 @@ const OCB_REQ_TENSOR_DIM1, OCB_REQ_TENSOR_DIM2, OCB_REQ_TENSOR_DIM3 = Int32(1 <<
 const OCB_REQ_COLLOCATED = Int32(1 << 7)
 const OCB_REQ_CARRIED_HEIGHT = Int32(1 << 8)
 const OCB_REQ_HYDROSTATIC_SPLIT = Int32(1 << 9)
+const OCB_REQ_CENTERED4 = Int32(1 << 10)
 const OCB_REQ_TERM_SHIFT = 12
 const OCB_TERM_TENDENCY, OCB_TERM_ADVECTION, OCB_TERM_BUOYANCY, OCB_TERM_CORIOLIS, OCB_TERM_PRESSURE, OCB_TERM_DIFFUSION, OCB_TERM_FORCING = Int32(0), Int32(1), Int32(2), Int32(3), Int32(4), Int32(5), Int32(6)
 term_flag(code) = Int32(code) << OCB_REQ_TERM_SHIFT
@@ -314,7 +315,7 @@ end
 
 const DIAG = Dict{Any,Tuple{Symbol,Function}}(
     KEq.kinetic_energy_ccc                       => (:KE,      vel3),                                     # KineticEnergyEquation.jl:45
-    KEq.uᵢ∂ⱼuⱼuᵢᶜᶜᶜ                             => (:ADV,     a -> (advection_supported(a[2]); velnt(a[1]))),  # :186 (velocities, advection)
+    KEq.uᵢ∂ⱼuⱼuᵢᶜᶜᶜ                             => (:ADV,     a -> advected!(velnt(a[1]), a[2])),            # :186 (velocities, advection)
     KEq.uᵢ∂ᵢpᶜᶜᶜ                                => (:PR,      a -> (s = velnt(a[1]); s.p = materialized(a[2]); s)),  # :357 (velocities, pressure)
     KEq.uᵢbᵢᶜᶜᶜ                                 => (:WB,      a -> (s = velnt(a[1]); s.b = a[3].b; s.ghat = ghat(a[2]); s)),  # :421
     KEq.viscous_dissipation_rate_ccc             => (:EPS,     a -> with_closure(velnt(a[2]), a[3].closure, a[1])),  # :491 (closure_fields, fields, parameters)
@@ -382,7 +383,7 @@ const DIAG = Dict{Any,Tuple{Symbol,Function}}(
 const UEq, VEq, WEq, TrEq = Oceanostics.UMomentumEquation, Oceanostics.VMomentumEquation, Oceanostics.WMomentumEquation, Oceanostics.TracerEquation
 const NHM, ADVM, BF, COR = Oceananigans.Models.NonhydrostaticModels, Oceananigans.Advection, Oceananigans.BuoyancyFormulations, Oceananigans.Coriolis
 term!(s::Slots, code) = (s.flags |= term_flag(code); s)
-adv_slots(a) = (advection_supported(a[1]); term!(velnt(a[2]), OCB_TERM_ADVECTION))                       # (advection, velocities, uᵢ)
+adv_slots(a) = term!(advected!(velnt(a[2]), a[1]), OCB_TERM_ADVECTION)                                    # (advection, velocities, uᵢ)
 buoy_slots(a) = (s = Slots(); s.b = a[2].b; s.ghat = ghat(a[1]); term!(s, OCB_TERM_BUOYANCY))             # (buoyancy, tracers)
 cor_slots(a) = (s = velnt(a[2]); s.f = a[1] === nothing ? (0.0, 0.0, 0.0) : map(Float64, get_coriolis_frequency_components(a[1])); term!(s, OCB_TERM_CORIOLIS))
 pgrad_slots(a) = (s = Slots(); s.p = a[1]; term!(s, OCB_TERM_PRESSURE))                                   # (hydrostatic_pressure,)
@@ -393,8 +394,7 @@ function velocity_tendency_slots(axis)      # (advection, coriolis, stokes_drift
         advection, coriolis, stokes, closure, ibc, buoyancy, background, velocities, tracers, aux, K, pHY, clock, forcing = a
         (ibc === nothing && stokes === nothing && all(isnothing, values(background.velocities))) ||
             throw(UnsupportedByLibrary("velocity tendency with immersed boundaries / Stokes drift / background fields"))
-        advection_supported(advection)
-        s = with_closure(velnt(velocities), closure, K)
+        s = advected!(with_closure(velnt(velocities), closure, K), advection)
         s.f = coriolis === nothing ? (0.0, 0.0, 0.0) : map(Float64, get_coriolis_frequency_components(coriolis))
         buoyancy === nothing || (s.b = tracers.b; s.ghat = ghat(buoyancy))
         pHY === nothing || (s.p = pHY; s.flags |= OCB_REQ_HYDROSTATIC_SPLIT)
@@ -412,7 +412,7 @@ for (row, key) in ((:U_TERM, 1), (:V_TERM, 2), (:W_TERM, 3))
     DIAG[(UEq.forcing_fcc, VEq.forcing_cfc, WEq.forcing_ccf)[key]] = (row, force_slots(key))                   # :453
     DIAG[(NHM.u_velocity_tendency, NHM.v_velocity_tendency, NHM.w_velocity_tendency)[key]] = (row, velocity_tendency_slots(key))   # :499
 end
-DIAG[ADVM.div_Uc] = (:C_TERM, a -> (advection_supported(a[1]); term!(tracer!(velnt(a[2]), a[3]), OCB_TERM_ADVECTION)))              # TracerEquation.jl:72
+DIAG[ADVM.div_Uc] = (:C_TERM, a -> term!(advected!(tracer!(velnt(a[2]), a[3]), a[1]), OCB_TERM_ADVECTION))                          # TracerEquation.jl:72
 DIAG[TC.∇_dot_qᶜ] = (:C_TERM, a -> term!(with_closure(tracer!(velnt(a[6]), a[4]), a[1], a[2], tracer_index(a[3])), OCB_TERM_DIFFUSION))  # :114
 DIAG[TrEq.forcing_ccc] = (:C_TERM, a -> (s = Slots(); s.aux[1] = forcing_field(a[1], a[3].b, a[2], a[3]); term!(s, OCB_TERM_FORCING)))   # :324
 tracer_flux_row(a) = with_closure(tracer!(Slots(), a[4]), a[1], a[2], tracer_index(a[3]))                 # (closure, closure_fields, Val(id), c, clock, fields, buoyancy)
@@ -425,9 +425,13 @@ DIAG[TC.diffusive_flux_z] = (:QZ, tracer_flux_row)                              
 DIAG[SFKEq.subfilter_ke_dissipation_rate_ccc] = (:SFEPS, a -> subfilter_dissipation_slots(a[1]))
 DIAG[FKEq.cross_scale_ke_flux_ccc] = (:PI, a -> cross_scale_flux_slots(a[1]))
 
-"Centered second order is what the library restates; any other scheme keeps Oceananigans' own `compute!` (UnsupportedByLibrary)."
-advection_supported(adv) = (adv isa Oceananigans.Advection.Centered && Oceananigans.Advection.required_halo_size_x(adv) == 1) ||
-    throw(UnsupportedByLibrary("advection scheme $(summary(adv)): only Centered(order = 2) is evaluated by the library"))
+"Centered(order = 2 | 4) is what the library restates (the reference's examples all run Centered(order = 4)); any other scheme keeps Oceananigans' own `compute!` (UnsupportedByLibrary)."
+function advection_supported(adv)
+    (adv isa Oceananigans.Advection.Centered && Oceananigans.Advection.required_halo_size_x(adv) <= 2) ||
+        throw(UnsupportedByLibrary("advection scheme $(summary(adv)): only Centered(order = 2 | 4) is evaluated by the library"))
+    return Oceananigans.Advection.required_halo_size_x(adv) == 2 ? OCB_REQ_CENTERED4 : Int32(0)      # the request flag
+end
+advected!(s::Slots, adv) = (s.flags |= advection_supported(adv); s)
 
 "A lazy argument (`sum(model.pressures)`, `u - U` handed to a diagnostic that takes no perturbation flag) is materialised once and refreshed with the other arguments."
 materialized(x::Field) = x
@@ -448,9 +452,8 @@ function tendency_slots_tracer(a)
     id, name, advection, closure, immersed, buoyancy, bgc, background, velocities, tracers, aux, K, clock, forcing = a
     (immersed === nothing && bgc === nothing && all(isnothing, values(background.tracers))) ||
         throw(UnsupportedByLibrary("tracer tendency with immersed boundaries / biogeochemistry / background fields"))
-    advection_supported(advection)
     c = tracers[tracer_index(name isa Val ? id : id)]
-    s = with_closure(tracer!(velnt(velocities), c), closure, K, tracer_index(id))
+    s = advected!(with_closure(tracer!(velnt(velocities), c), closure, K, tracer_index(id)), advection)
     s.aux[1] = forcing_field(forcing, c, clock, merge(velocities, tracers))
     return s
 end
@@ -458,8 +461,7 @@ function tendency_slots_momentum(a)
     advection, coriolis, stokes, closure, ibu, ibv, ibw, buoyancy, background, velocities, tracers, aux, K, pHY, clock, forcing = a
     (ibu === nothing && ibv === nothing && ibw === nothing && stokes === nothing && all(isnothing, values(background.velocities))) ||
         throw(UnsupportedByLibrary("momentum tendency with immersed boundaries / Stokes drift / background fields"))
-    advection_supported(advection)
-    s = with_closure(velnt(velocities), closure, K)
+    s = advected!(with_closure(velnt(velocities), closure, K), advection)
     s.f = coriolis === nothing ? (0.0, 0.0, 0.0) : map(Float64, get_coriolis_frequency_components(coriolis))
     if buoyancy !== nothing
         s.b = tracers.b; s.ghat = ghat(buoyancy)

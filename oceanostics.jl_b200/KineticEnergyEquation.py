@@ -29,11 +29,10 @@ def KineticEnergyAdvection(model, velocities=None, location=CCC):
     validate_location(location, "KineticEnergyAdvection")
     if getattr(model, "hydrostatic", False):
         raise TypeError("KineticEnergyAdvection is defined for a NonhydrostaticModel")
-    if str(model.advection) not in ("Centered", "Centered(order=2)"):
-        raise _lib.OcbError(f"advection scheme {model.advection!r}: only Centered second-order momentum advection is "
-                            "evaluated by the CUDA library")
+    from .models import advection_flags
     u, v, w = _vel(velocities if velocities is not None else model.velocities)
-    return KernelFunctionOperation("ADV", model.grid, SweepOperands(u=u, v=v, w=w), name="KineticEnergyAdvection",
+    return KernelFunctionOperation("ADV", model.grid, SweepOperands(u=u, v=v, w=w), flags=advection_flags(model, "KineticEnergyAdvection"),
+                                   name="KineticEnergyAdvection",
                                    computes="kinetic energy advection  uᵢ∂ⱼ(uᵢuⱼ)")
 
 
@@ -151,9 +150,8 @@ def KineticEnergyTendency(model, location=CCC):
     validate_location(location, "KineticEnergyTendency")
     if model.hydrostatic:
         raise TypeError("KineticEnergyTendency is defined for NonhydrostaticModel only (src/KineticEnergyEquation.jl:120)")
-    if str(model.advection) not in ("Centered", "Centered(order=2)"):
-        raise _lib.OcbError(f"advection scheme {model.advection!r}: only Centered second-order momentum advection is "
-                            "evaluated by the CUDA library")
+    from .models import advection_flags
+    flags0 = advection_flags(model, "KineticEnergyTendency")
     for name in ("stokes_drift", "background_fields", "immersed_boundary"):
         if getattr(model, name, None) is not None:
             raise _lib.OcbError(f"KineticEnergyTendency with model.{name} is not evaluated by the CUDA library")
@@ -162,7 +160,7 @@ def KineticEnergyTendency(model, location=CCC):
     if model.buoyancy is not None:
         kw["b"] = model.tracers.b
         kw["ghat"] = tuple(-g for g in model.buoyancy.gravity_unit_vector)
-    flags = 0
+    flags = flags0
     pHY = getattr(model.pressures, "pHY", None)
     if pHY is not None:
         kw["p"] = pHY

@@ -22,11 +22,11 @@ def _vel(model):
 
 
 def Advection(model, tracer_name, location=CCC):
-    """∂ⱼ(uⱼ c) = div_Uc, Centered second order (src/TracerEquation.jl:70-78)."""
+    """∂ⱼ(uⱼ c) = div_Uc, Centered(order = 2 | 4) (src/TracerEquation.jl:70-78)."""
     validate_location(location, "Advection")
-    _check_model(model, "TracerEquation.Advection"); _check_advection(model)
+    _check_model(model, "TracerEquation.Advection")
     return KernelFunctionOperation("C_TERM", model.grid, SweepOperands(b=_tracer(model, tracer_name), **_vel(model)),
-                                   flags=_flags(_lib.OCB_TERM_ADVECTION), name="TracerAdvection", computes="tracer advection  ∂ⱼ(uⱼ c)")
+                                   flags=_flags(_lib.OCB_TERM_ADVECTION) | _check_advection(model), name="TracerAdvection", computes="tracer advection  ∂ⱼ(uⱼ c)")
 
 
 def Diffusion(model, tracer_name, location=CCC):

@@ -44,22 +44,21 @@ Diffusion = TracerVarianceDiffusion
 
 def TracerVarianceTendency(model, tracer_name, location=CCC):
     """TEND = 2c ∂ₜc with Oceananigans' NonhydrostaticModel tracer tendency (c∂ₜcᶜᶜᶜ, src/TracerVarianceEquation.jl:18-39,
-    constructor :66-88):  ∂ₜc = -div_Uc - ∇·q + F  for a model with Centered second-order advection and without background
+    constructor :66-88):  ∂ₜc = -div_Uc - ∇·q + F  for a model with Centered(order = 2 | 4) advection and without background
     fields, biogeochemistry or immersed boundaries (this model container has none); the tracer forcing is materialised by
     the host layer (`operations.ForcingField`).  SURVEY.md section 8f, row 2."""
     from .operations import forcing_operand
     validate_location(location, "TracerVarianceTendency")
     if model.hydrostatic:
         raise TypeError("TracerVarianceTendency is defined for NonhydrostaticModel only (src/TracerVarianceEquation.jl:66)")
-    if str(getattr(model, "advection", "Centered")) not in ("Centered", "Centered(order=2)"):
-        raise _lib.OcbError(f"TracerVarianceTendency: advection scheme {model.advection!r} is outside the B200 hot path "
-                            "(Centered second order only, SURVEY.md section 8f row 2): evaluate it with Oceanostics.jl")
+    from .models import advection_flags
+    flags = advection_flags(model, "TracerVarianceTendency")
     c = _tracer(model, tracer_name)
     name = str(tracer_name).lstrip(":")
     u, v, w = model.velocities.u, model.velocities.v, model.velocities.w
     forcing = forcing_operand(getattr(model.forcing, name, None), c, model)
     return KernelFunctionOperation("C_TENDENCY", model.grid, SweepOperands(u=u, v=v, w=w, b=c, closure=model.closure, aux={0: forcing}),
-                                   name="TracerVarianceTendency", computes="tracer variance tendency  2c ∂ₜc")
+                                   flags=flags, name="TracerVarianceTendency", computes="tracer variance tendency  2c ∂ₜc")
 
 
 Tendency = TracerVarianceTendency

@@ -27,6 +27,7 @@ OCB_REQ_TENSOR_DIM1, OCB_REQ_TENSOR_DIM2, OCB_REQ_TENSOR_DIM3 = 1 << 4, 1 << 5, 
 OCB_REQ_COLLOCATED = 1 << 7
 OCB_REQ_CARRIED_HEIGHT = 1 << 8
 OCB_REQ_HYDROSTATIC_SPLIT = 1 << 9
+OCB_REQ_CENTERED4 = 1 << 10
 OCB_REQ_TERM_SHIFT = 12
 OCB_TERM_TENDENCY, OCB_TERM_ADVECTION, OCB_TERM_BUOYANCY, OCB_TERM_CORIOLIS, OCB_TERM_PRESSURE, OCB_TERM_DIFFUSION, OCB_TERM_FORCING = range(7)
 

@@ -25,8 +25,9 @@ def _check_model(model, what):
 
 
 def _check_advection(model):
-    if str(model.advection) not in ("Centered", "Centered(order=2)"):
-        raise _lib.OcbError(f"advection scheme {model.advection!r}: only Centered second-order advection is evaluated by the CUDA library")
+    """-> the request flag of the model's advection scheme (Centered(order = 2 | 4)); refuses anything else."""
+    from .models import advection_flags
+    return advection_flags(model, "advection term")
 
 
 def make_module(comp):
@@ -45,8 +46,10 @@ def make_module(comp):
     def Advection(model, location=loc):
         f"""ADV = ∂ⱼ(uⱼ{comp}): Oceananigans' div_𝐯{comp} (src/{C}MomentumEquation.jl `Advection`)."""
         validate_location(location, "Advection", loc)
-        _check_model(model, "Advection"); _check_advection(model)
-        return op(model, _lib.OCB_TERM_ADVECTION, "Advection", f"advection of {comp}-momentum  ∂ⱼ(uⱼ{comp})")
+        _check_model(model, "Advection")
+        o = op(model, _lib.OCB_TERM_ADVECTION, "Advection", f"advection of {comp}-momentum  ∂ⱼ(uⱼ{comp})")
+        o.flags |= _check_advection(model)
+        return o
 
     def BuoyancyAcceleration(model, location=loc):
         validate_location(location, "BuoyancyAcceleration", loc)
@@ -81,13 +84,14 @@ def make_module(comp):
 
     def Tendency(model, location=loc):
         validate_location(location, "Tendency", loc)
-        _check_model(model, "Tendency"); _check_advection(model)
+        _check_model(model, "Tendency")
+        adv_flag = _check_advection(model)
         v = model.velocities
         kw = dict(closure=model.closure, f=tuple(get_coriolis_frequency_components(model.coriolis)))
         if model.buoyancy is not None:
             kw["b"] = model.tracers.b
             kw["ghat"] = tuple(-g for g in model.buoyancy.gravity_unit_vector)
-        flags = _flags(_lib.OCB_TERM_TENDENCY)
+        flags = _flags(_lib.OCB_TERM_TENDENCY) | adv_flag
         pHY = getattr(model.pressures, "pHY", None)
         if pHY is not None:
             kw["p"] = pHY

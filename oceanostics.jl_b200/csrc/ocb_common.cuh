@@ -103,6 +103,7 @@ struct DGrid {
   const T* dzc;  const T* dzf;   // Δzᵃᵃᶜ[k], Δzᵃᵃᶠ[k]
   const T* rdzc; const T* rdzf;  // their reciprocals
   const T* zc;   const T* zf;    // nodes
+  int oi, oj, ok;                // absolute index of the origin the z tables / operand pointers are currently shifted to (0 when unshifted)
 };
 
 static inline size_t ocb_sizeof(int dtype) { return dtype == OCB_F64 ? 8 : 4; }

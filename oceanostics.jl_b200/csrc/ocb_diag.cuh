@@ -159,24 +159,102 @@ OCB_EVAL(OCB_DIAG_TKE) {
 
 // ---- uᵢ∂ⱼuⱼuᵢᶜᶜᶜ, Centered second order  (src/KineticEnergyEquation.jl:147-152) -----------------------
 // momentum fluxes: (area-weighted advecting velocity averaged to the flux point) x (advected velocity there)
+// Centered(order = N) symmetric interpolation [OCN-mem Advection/centered_reconstruction.jl]: the two-point mean (order 2) or
+// (-1, 7, 7, -1)/12 over the four nearest points (order 4; uniform-grid coefficients on every axis, as `Centered(order = 4)` built
+// without a grid has them); along a Bounded axis order 4 falls back to order 2 where the stencil would reach across a wall
+// (outside_symmetric_halo: face index m keeps it for 3 <= m <= N-1, centre index for 2 <= m <= N-1).
 template <class T> struct AdvFlux {
   const Ctx<T>& X;
-  OCB_X AdvFlux(const Ctx<T>& x) : X(x) {}
+  bool o4;
+  OCB_X AdvFlux(const Ctx<T>& x, int flags = 0) : X(x), o4(flags & OCB_REQ_CENTERED4) {}
   OCB_X T axu(int i, int j, int k) const { return X.g.dy * X.dzc(k) * X.u(i, j, k); }   // Ax_fcc u
   OCB_X T ayv(int i, int j, int k) const { return X.g.dx * X.dzc(k) * X.v(i, j, k); }   // Ay_cfc v
   OCB_X T azw(int i, int j, int k) const { return X.g.dx * X.g.dy * X.w(i, j, k); }     // Az_ccf w
-  // u-momentum
-  OCB_X T Uu(int i, int j, int k) const { return T(0.25) * (axu(i, j, k) + axu(i + 1, j, k)) * (X.u(i, j, k) + X.u(i + 1, j, k)); }   // ccc
-  OCB_X T Vu(int i, int j, int k) const { return T(0.25) * (ayv(i - 1, j, k) + ayv(i, j, k)) * (X.u(i, j - 1, k) + X.u(i, j, k)); }   // ffc
-  OCB_X T Wu(int i, int j, int k) const { return T(0.25) * (azw(i - 1, j, k) + azw(i, j, k)) * (X.u(i, j, k - 1) + X.u(i, j, k)); }   // fcf
+  // does the order-4 stencil along axis d fit at index m (absolute = origin + m)?  to_face: interpolation to a face index
+  OCB_X bool wide(int d, int m, bool to_face) const {
+    if (!o4) return false;
+    const int topo = d == 0 ? X.g.tx : (d == 1 ? X.g.ty : X.g.tz);
+    if (topo != OCB_BOUNDED) return true;
+    const int N = d == 0 ? X.g.Nx : (d == 1 ? X.g.Ny : X.g.Nz);
+    const int a = m + (d == 0 ? X.g.oi : (d == 1 ? X.g.oj : X.g.ok));
+    return a >= (to_face ? 3 : 2) && a <= N - 1;
+  }
+  // interpolation of four samples (s_-1, s_0, s_1, s_2 around the target) -- the middle two for order 2
+  OCB_X T mix(bool w4, T sm, T s0, T s1, T s2) const { return w4 ? (T(7) * (s0 + s1) - (sm + s2)) * T(1.0 / 12.0) : T(0.5) * (s0 + s1); }
+#define OCB_I4(FN, AXIS, TOFACE, IDX, LO, ARG)                                                             \
+  OCB_X T FN(int i, int j, int k) const {                                                                   \
+    const bool w4 = wide(AXIS, IDX, TOFACE);                                                                \
+    return mix(w4, w4 ? ARG(LO - 1) : T(0), ARG(LO), ARG(LO + 1), w4 ? ARG(LO + 2) : T(0));                \
+  }
+  // advecting (area-weighted) velocities and advected velocities at the nine flux points; to a centre: samples m, m+1 (LO = 0),
+  // to a face: samples m-1, m (LO = -1)
+#define A_(s) axu(i + (s), j, k)
+  OCB_I4(Ucx, 0, false, i, 0, A_)     // Ax u -> ccc along x
+#undef A_
+#define A_(s) axu(i, j + (s), k)
+  OCB_I4(Ufy, 1, true, j, -1, A_)     // Ax u -> ffc along y
+#undef A_
+#define A_(s) axu(i, j, k + (s))
+  OCB_I4(Ufz, 2, true, k, -1, A_)     // Ax u -> fcf along z
+#undef A_
+#define A_(s) ayv(i + (s), j, k)
+  OCB_I4(Vfx, 0, true, i, -1, A_)     // Ay v -> ffc along x
+#undef A_
+#define A_(s) ayv(i, j + (s), k)
+  OCB_I4(Vcy, 1, false, j, 0, A_)     // Ay v -> ccc along y
+#undef A_
+#define A_(s) ayv(i, j, k + (s))
+  OCB_I4(Vfz, 2, true, k, -1, A_)     // Ay v -> cff along z
+#undef A_
+#define A_(s) azw(i + (s), j, k)
+  OCB_I4(Wfx, 0, true, i, -1, A_)     // Az w -> fcf along x
+#undef A_
+#define A_(s) azw(i, j + (s), k)
+  OCB_I4(Wfy, 1, true, j, -1, A_)     // Az w -> cff along y
+#undef A_
+#define A_(s) azw(i, j, k + (s))
+  OCB_I4(Wcz, 2, false, k, 0, A_)     // Az w -> ccc along z
+#undef A_
+#define A_(s) X.u(i + (s), j, k)
+  OCB_I4(ucx, 0, false, i, 0, A_)
+#undef A_
+#define A_(s) X.u(i, j + (s), k)
+  OCB_I4(ufy, 1, true, j, -1, A_)
+#undef A_
+#define A_(s) X.u(i, j, k + (s))
+  OCB_I4(ufz, 2, true, k, -1, A_)
+#undef A_
+#define A_(s) X.v(i + (s), j, k)
+  OCB_I4(vfx, 0, true, i, -1, A_)
+#undef A_
+#define A_(s) X.v(i, j + (s), k)
+  OCB_I4(vcy, 1, false, j, 0, A_)
+#undef A_
+#define A_(s) X.v(i, j, k + (s))
+  OCB_I4(vfz, 2, true, k, -1, A_)
+#undef A_
+#define A_(s) X.w(i + (s), j, k)
+  OCB_I4(wfx, 0, true, i, -1, A_)
+#undef A_
+#define A_(s) X.w(i, j + (s), k)
+  OCB_I4(wfy, 1, true, j, -1, A_)
+#undef A_
+#define A_(s) X.w(i, j, k + (s))
+  OCB_I4(wcz, 2, false, k, 0, A_)
+#undef A_
+#undef OCB_I4
+  // u-momentum fluxes
+  OCB_X T Uu(int i, int j, int k) const { return Ucx(i, j, k) * ucx(i, j, k); }   // ccc
+  OCB_X T Vu(int i, int j, int k) const { return Vfx(i, j, k) * ufy(i, j, k); }   // ffc
+  OCB_X T Wu(int i, int j, int k) const { return Wfx(i, j, k) * ufz(i, j, k); }   // fcf
   // v-momentum
-  OCB_X T Uv(int i, int j, int k) const { return T(0.25) * (axu(i, j - 1, k) + axu(i, j, k)) * (X.v(i - 1, j, k) + X.v(i, j, k)); }   // ffc
-  OCB_X T Vv(int i, int j, int k) const { return T(0.25) * (ayv(i, j, k) + ayv(i, j + 1, k)) * (X.v(i, j, k) + X.v(i, j + 1, k)); }   // ccc
-  OCB_X T Wv(int i, int j, int k) const { return T(0.25) * (azw(i, j - 1, k) + azw(i, j, k)) * (X.v(i, j, k - 1) + X.v(i, j, k)); }   // cff
+  OCB_X T Uv(int i, int j, int k) const { return Ufy(i, j, k) * vfx(i, j, k); }   // ffc
+  OCB_X T Vv(int i, int j, int k) const { return Vcy(i, j, k) * vcy(i, j, k); }   // ccc
+  OCB_X T Wv(int i, int j, int k) const { return Wfy(i, j, k) * vfz(i, j, k); }   // cff
   // w-momentum
-  OCB_X T Uw(int i, int j, int k) const { return T(0.25) * (axu(i, j, k - 1) + axu(i, j, k)) * (X.w(i - 1, j, k) + X.w(i, j, k)); }   // fcf
-  OCB_X T Vw(int i, int j, int k) const { return T(0.25) * (ayv(i, j, k - 1) + ayv(i, j, k)) * (X.w(i, j - 1, k) + X.w(i, j, k)); }   // cff
-  OCB_X T Ww(int i, int j, int k) const { return T(0.25) * (azw(i, j, k) + azw(i, j, k + 1)) * (X.w(i, j, k) + X.w(i, j, k + 1)); }   // ccc
+  OCB_X T Uw(int i, int j, int k) const { return Ufz(i, j, k) * wfx(i, j, k); }   // fcf
+  OCB_X T Vw(int i, int j, int k) const { return Vfz(i, j, k) * wfy(i, j, k); }   // cff
+  OCB_X T Ww(int i, int j, int k) const { return Wcz(i, j, k) * wcz(i, j, k); }   // ccc
   // flux divergences at the velocity points
   OCB_X T divu(int i, int j, int k) const {   // fcc
     T s = (Uu(i, j, k) - Uu(i - 1, j, k)) + (Vu(i, j + 1, k) - Vu(i, j, k)) + (Wu(i, j, k + 1) - Wu(i, j, k));
@@ -192,7 +270,7 @@ template <class T> struct AdvFlux {
   }
 };
 OCB_EVAL(OCB_DIAG_ADV) {
-  AdvFlux<T> A(X);
+  AdvFlux<T> A(X, flags);
   T a = X.u(i, j, k) * A.divu(i, j, k) + X.u(i + 1, j, k) * A.divu(i + 1, j, k);
   T b = X.v(i, j, k) * A.divv(i, j, k) + X.v(i, j + 1, k) * A.divv(i, j + 1, k);
   T c = X.w(i, j, k) * A.divw(i, j, k) + X.w(i, j, k + 1) * A.divw(i, j, k + 1);
@@ -584,22 +662,46 @@ OCB_EVAL(OCB_DIAG_KE_FORCING) {
   return T(0.5) * (a + b + c);
 } };
 
+// TracerEquation.jl:70-327: div_Uc, ∇_dot_qᶜ, the forcing, the whole tracer tendency; and the three diffusive fluxes.
+// Advective fluxes Ax u ℑx c, Ay v ℑy c, Az w ℑz c with the Centered(order = 2 | 4) symmetric interpolation of the tracer.
+template <class T> struct TracerTerms {
+  const Ctx<T>& X;
+  AdvFlux<T> A;
+  OCB_X TracerTerms(const Ctx<T>& x, int flags = 0) : X(x), A(x, flags) {}
+  OCB_X T qx(int i, int j, int k) const { return -X.ka_fcc(i, j, k) * ((X.in.b(i, j, k) - X.in.b(i - 1, j, k)) * X.g.rdx); }
+  OCB_X T qy(int i, int j, int k) const { return -X.ka_cfc(i, j, k) * ((X.in.b(i, j, k) - X.in.b(i, j - 1, k)) * X.g.rdy); }
+  OCB_X T qz(int i, int j, int k) const { return -X.ka_ccf(i, j, k) * ((X.in.b(i, j, k) - X.in.b(i, j, k - 1)) * X.rdzf(k)); }
+  // twice the tracer interpolated to the x / y / z face m (the factor 1/2 of the two-point mean is applied by `adv`)
+  OCB_X T cx2(int i, int j, int k) const { const HFld<T>& c = X.in.b; const bool w4 = A.wide(0, i, true);
+    return T(2) * A.mix(w4, w4 ? c(i - 2, j, k) : T(0), c(i - 1, j, k), c(i, j, k), w4 ? c(i + 1, j, k) : T(0)); }
+  OCB_X T cy2(int i, int j, int k) const { const HFld<T>& c = X.in.b; const bool w4 = A.wide(1, j, true);
+    return T(2) * A.mix(w4, w4 ? c(i, j - 2, k) : T(0), c(i, j - 1, k), c(i, j, k), w4 ? c(i, j + 1, k) : T(0)); }
+  OCB_X T cz2(int i, int j, int k) const { const HFld<T>& c = X.in.b; const bool w4 = A.wide(2, k, true);
+    return T(2) * A.mix(w4, w4 ? c(i, j, k - 2) : T(0), c(i, j, k - 1), c(i, j, k), w4 ? c(i, j, k + 1) : T(0)); }
+  OCB_X T adv(int i, int j, int k) const {
+    const T ax = (X.u(i + 1, j, k) * cx2(i + 1, j, k) - X.u(i, j, k) * cx2(i, j, k)) * (T(0.5) * X.g.rdx);
+    const T ay = (X.v(i, j + 1, k) * cy2(i, j + 1, k) - X.v(i, j, k) * cy2(i, j, k)) * (T(0.5) * X.g.rdy);
+    const T az = (X.w(i, j, k + 1) * cz2(i, j, k + 1) - X.w(i, j, k) * cz2(i, j, k)) * (T(0.5) * X.rdzc(k));
+    return (ax + ay) + az;
+  }
+  OCB_X T divq(int i, int j, int k) const {
+    return (qx(i + 1, j, k) - qx(i, j, k)) * X.g.rdx + (qy(i, j + 1, k) - qy(i, j, k)) * X.g.rdy + (qz(i, j, k + 1) - qz(i, j, k)) * X.rdzc(k);
+  }
+};
 // c∂ₜcᶜᶜᶜ  (src/TracerVarianceEquation.jl:18-39): 2c x Oceananigans' NonhydrostaticModel tracer_tendency for a model without
-// background fields, biogeochemistry or immersed boundaries:  Gc = -div_Uc - ∇·q + F, with the Centered second-order advective
-// fluxes  Ax u ℑx c, Ay v ℑy c, Az w ℑz c  (div_Uc = 1/V [δx + δy + δz] of them), the closure's diffusive fluxes as in
-// c∇_dot_qᶜ above, and the tracer forcing materialised at the cell centres in aux[0].
+// background fields, biogeochemistry or immersed boundaries:  Gc = -div_Uc - ∇·q + F, with the Centered advective fluxes
+// Ax u ℑx c, Ay v ℑy c, Az w ℑz c  (div_Uc = 1/V [δx + δy + δz] of them), the closure's diffusive fluxes as in c∇_dot_qᶜ above, and
+// the tracer forcing materialised at the cell centres in aux[0].
 OCB_EVAL(OCB_DIAG_C_TENDENCY) {
+  TracerTerms<T> C(X, flags);
   const HFld<T>& c = X.in.b;
   T cc = c(i, j, k);
-  T ax = (X.u(i + 1, j, k) * (cc + c(i + 1, j, k)) - X.u(i, j, k) * (c(i - 1, j, k) + cc)) * (T(0.5) * X.g.rdx);
-  T ay = (X.v(i, j + 1, k) * (cc + c(i, j + 1, k)) - X.v(i, j, k) * (c(i, j - 1, k) + cc)) * (T(0.5) * X.g.rdy);
-  T az = (X.w(i, j, k + 1) * (cc + c(i, j, k + 1)) - X.w(i, j, k) * (c(i, j, k - 1) + cc)) * (T(0.5) * X.rdzc(k));
   T qx0 = X.ka_fcc(i, j, k) * (cc - c(i - 1, j, k)), qx1 = X.ka_fcc(i + 1, j, k) * (c(i + 1, j, k) - cc);
   T qy0 = X.ka_cfc(i, j, k) * (cc - c(i, j - 1, k)), qy1 = X.ka_cfc(i, j + 1, k) * (c(i, j + 1, k) - cc);
   T qz0 = X.ka_ccf(i, j, k) * (cc - c(i, j, k - 1)) * X.rdzf(k);
   T qz1 = X.ka_ccf(i, j, k + 1) * (c(i, j, k + 1) - cc) * X.rdzf(k + 1);
   T divq = (qx0 - qx1) * (X.g.rdx * X.g.rdx) + (qy0 - qy1) * (X.g.rdy * X.g.rdy) + (qz0 - qz1) * X.rdzc(k);
-  return T(2) * cc * (X.in.aux[0](i, j, k) - ((ax + ay) + az) - divq);
+  return T(2) * cc * (X.in.aux[0](i, j, k) - C.adv(i, j, k) - divq);
 } };
 
 // uᵢGᵢᶜᶜᶜ  (src/KineticEnergyEquation.jl:74-95): each velocity times Oceananigans' NonhydrostaticModel velocity tendency at the
@@ -613,7 +715,7 @@ template <class T> struct Tendency {
   AdvFlux<T> A;
   StressDiv<T> D;
   bool w_buoyancy;
-  OCB_X Tendency(const Ctx<T>& x, int flags) : X(x), A(x), D(x), w_buoyancy(!(flags & OCB_REQ_HYDROSTATIC_SPLIT)) {}
+  OCB_X Tendency(const Ctx<T>& x, int flags) : X(x), A(x, flags), D(x), w_buoyancy(!(flags & OCB_REQ_HYDROSTATIC_SPLIT)) {}
   // x_dot_g_b, y_dot_g_b, z_dot_g_b  [OCN-mem BuoyancyFormulations/buoyancy_force.jl]
   OCB_X T bx(int i, int j, int k) const { const SweepIn<T>& I = X.in; return I.ghat[0] != T(0) ? I.ghat[0] * (T(0.5) * (I.b(i - 1, j, k) + I.b(i, j, k))) : T(0); }
   OCB_X T by(int i, int j, int k) const { const SweepIn<T>& I = X.in; return I.ghat[1] != T(0) ? I.ghat[1] * (T(0.5) * (I.b(i, j - 1, k) + I.b(i, j, k))) : T(0); }
@@ -698,27 +800,9 @@ OCB_EVAL(OCB_DIAG_W_TERM) {
     default: return G.gw(i, j, k);
   }
 } };
-// TracerEquation.jl:70-327: div_Uc, ∇_dot_qᶜ, the forcing, the whole tracer tendency; and the three diffusive fluxes
-template <class T> struct TracerTerms {
-  const Ctx<T>& X;
-  OCB_X TracerTerms(const Ctx<T>& x) : X(x) {}
-  OCB_X T qx(int i, int j, int k) const { return -X.ka_fcc(i, j, k) * ((X.in.b(i, j, k) - X.in.b(i - 1, j, k)) * X.g.rdx); }
-  OCB_X T qy(int i, int j, int k) const { return -X.ka_cfc(i, j, k) * ((X.in.b(i, j, k) - X.in.b(i, j - 1, k)) * X.g.rdy); }
-  OCB_X T qz(int i, int j, int k) const { return -X.ka_ccf(i, j, k) * ((X.in.b(i, j, k) - X.in.b(i, j, k - 1)) * X.rdzf(k)); }
-  OCB_X T adv(int i, int j, int k) const {
-    const HFld<T>& c = X.in.b;
-    const T cc = c(i, j, k);
-    const T ax = (X.u(i + 1, j, k) * (cc + c(i + 1, j, k)) - X.u(i, j, k) * (c(i - 1, j, k) + cc)) * (T(0.5) * X.g.rdx);
-    const T ay = (X.v(i, j + 1, k) * (cc + c(i, j + 1, k)) - X.v(i, j, k) * (c(i, j - 1, k) + cc)) * (T(0.5) * X.g.rdy);
-    const T az = (X.w(i, j, k + 1) * (cc + c(i, j, k + 1)) - X.w(i, j, k) * (c(i, j, k - 1) + cc)) * (T(0.5) * X.rdzc(k));
-    return (ax + ay) + az;
-  }
-  OCB_X T divq(int i, int j, int k) const {
-    return (qx(i + 1, j, k) - qx(i, j, k)) * X.g.rdx + (qy(i, j + 1, k) - qy(i, j, k)) * X.g.rdy + (qz(i, j, k + 1) - qz(i, j, k)) * X.rdzc(k);
-  }
-};
+// (TracerTerms: defined above, next to c∂ₜcᶜᶜᶜ)
 OCB_EVAL(OCB_DIAG_C_TERM) {
-  TracerTerms<T> C(X);
+  TracerTerms<T> C(X, flags);
   switch ((flags >> OCB_REQ_TERM_SHIFT) & 15) {
     case OCB_TERM_ADVECTION: return C.adv(i, j, k);
     case OCB_TERM_DIFFUSION: return C.divq(i, j, k);
@@ -789,6 +873,7 @@ OCB_X void ocb_shift_inputs(SweepIn<T>& L, DGrid<T>& G, int i, int j, int k) {
   for (int a = 0; a < OCB_N_AUX; ++a) ocb_shift_field(L.aux[a], i, j, k);
   for (int a = 0; a < OCB_MAX_CLOSURE_FIELDS; ++a) { ocb_shift_field(L.nu_f[a], i, j, k); ocb_shift_field(L.ka_f[a], i, j, k); }
   G.dzc += k; G.dzf += k; G.rdzc += k; G.rdzf += k; G.zc += k; G.zf += k;
+  G.oi += i; G.oj += j; G.ok += k;
 }
 
 // volume element at a request's location (Integral(op) = Σ op·V, Oceananigans Reduction(sum!, op * V))

@@ -234,12 +234,13 @@ static int finish_plan(ocb_plan* pl, const ocb_grid* grid, const ocb_sweep_input
   int budget_other = 0, strain_other = 0;
   for (int r = 0; r < n; ++r) {
     if (reqs[r].diag == OCB_DIAG_EPS) continue;
-    if (ocb_fused_handles_diag(reqs[r].diag)) ++budget_other;
+    if (ocb_fused_handles_diag(reqs[r].diag) && !(reqs[r].flags & OCB_REQ_CENTERED4)) ++budget_other;
     if (ocb_strain_handles_diag(reqs[r].diag)) ++strain_other;
   }
   const bool eps_with_moduli = budget_other == 0 && strain_other > 0;
   for (int r = 0; r < n; ++r) {
-    if (ocb_fused_handles_diag(reqs[r].diag) && !(eps_with_moduli && reqs[r].diag == OCB_DIAG_EPS)) fr[nf++] = reqs[r];
+    // (the pipelined kernels evaluate Centered second-order advection; a fourth-order request stays with the generic kernel)
+    if (ocb_fused_handles_diag(reqs[r].diag) && !(reqs[r].flags & OCB_REQ_CENTERED4) && !(eps_with_moduli && reqs[r].diag == OCB_DIAG_EPS)) fr[nf++] = reqs[r];
     else gr[ng++] = reqs[r];
   }
   for (int attempt = 0; attempt < 3 && nf > 0 && !pl->fused; ++attempt) {

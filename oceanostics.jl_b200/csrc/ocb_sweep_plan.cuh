@@ -50,7 +50,8 @@ static inline int ocb_diag_needs(int diag) {
 // how many halo cells a diagnostic reads beyond the interior along each axis: 2 for the terms that
 // difference a flux which itself reaches one cell out (Centered second-order momentum advection, the viscous-flux divergence,
 // the tendencies built from them) and for the tilted Richardson number, 1 for everything else
-static inline int ocb_diag_reach(int diag) {
+static inline int ocb_diag_reach(int diag, int flags = 0) {
+  if (flags & OCB_REQ_CENTERED4) return 3;             // fourth-order fluxes reach one cell further than second-order ones
   switch (diag) {
     case OCB_DIAG_ADV: case OCB_DIAG_KE_STRESS: case OCB_DIAG_KE_TENDENCY: case OCB_DIAG_U_TERM: case OCB_DIAG_V_TERM:
     case OCB_DIAG_W_TERM: case OCB_DIAG_RI: return 2;
@@ -168,7 +169,7 @@ static int ocb_build_sweep_params(const ocb_grid* grid, const ocb_sweep_inputs* 
   P.nslots = nslots;
   // every array operand must carry the halo the requested stencils reach into (a thin halo would be read out of bounds)
   int reach = 1;
-  for (int r = 0; r < n; ++r) if (ocb_diag_reach(reqs[r].diag) > reach) reach = ocb_diag_reach(reqs[r].diag);
+  for (int r = 0; r < n; ++r) if (ocb_diag_reach(reqs[r].diag, reqs[r].flags) > reach) reach = ocb_diag_reach(reqs[r].diag, reqs[r].flags);
   const ocb_field* arr[] = {&in->u, &in->v, &in->w, &in->b, &in->p, &in->U, &in->V, &in->W, &in->B, &in->aux[0], &in->aux[1], &in->aux[2],
                             &in->aux[3], &in->aux[4], &in->aux[5], &in->aux[6], &in->closure.nu_fields[0], &in->closure.nu_fields[1],
                             &in->closure.kappa_fields[0], &in->closure.kappa_fields[1]};

@@ -119,3 +119,16 @@ def perturbation_velocities(model, U=None, V=None, W=None):
     if model.hydrostatic:
         w = ZeroField()
     return dict(u=u, v=v, w=w, U=as_operand(U), V=as_operand(V), W=as_operand(W))
+
+
+def advection_flags(model, what):
+    """Request flags for the model's advection scheme: Centered second order (0) or Centered(order = 4) (OCB_REQ_CENTERED4) -- the
+    schemes every example of the reference uses (docs/examples/*.jl: `advection = Centered(order=4)`); anything else (upwind-biased,
+    WENO) is refused: its reconstruction is not restated."""
+    from . import _lib
+    adv = str(getattr(model, "advection", "Centered")).replace(" ", "")
+    if adv in ("Centered", "Centered(order=2)", "Centered()"):
+        return 0
+    if adv == "Centered(order=4)":
+        return _lib.OCB_REQ_CENTERED4
+    raise _lib.OcbError(f"{what}: advection scheme {model.advection!r} -- only Centered(order = 2 | 4) advection is evaluated by the CUDA library")

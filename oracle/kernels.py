@@ -146,36 +146,69 @@ def _Ayv(i, j, k, g, v): return _op.Ay_cfc(i, j, k, g) * v[i, j, k]
 def _Azw(i, j, k, g, w): return _op.Az_ccf(i, j, k, g) * w[i, j, k]
 
 
-def _flux_Uu(i, j, k, g, U, u): return _op.ix_caa(i, j, k, g, _Axu, U[0]) * _op.ix_caa(i, j, k, g, u)
-def _flux_Vu(i, j, k, g, U, u): return _op.ix_faa(i, j, k, g, _Ayv, U[1]) * _op.iy_afa(i, j, k, g, u)
-def _flux_Wu(i, j, k, g, U, u): return _op.ix_faa(i, j, k, g, _Azw, U[2]) * _op.iz_aaf(i, j, k, g, u)
-def _flux_Uv(i, j, k, g, U, v): return _op.iy_afa(i, j, k, g, _Axu, U[0]) * _op.ix_faa(i, j, k, g, v)
-def _flux_Vv(i, j, k, g, U, v): return _op.iy_aca(i, j, k, g, _Ayv, U[1]) * _op.iy_aca(i, j, k, g, v)
-def _flux_Wv(i, j, k, g, U, v): return _op.iy_afa(i, j, k, g, _Azw, U[2]) * _op.iz_aaf(i, j, k, g, v)
-def _flux_Uw(i, j, k, g, U, w): return _op.iz_aaf(i, j, k, g, _Axu, U[0]) * _op.ix_faa(i, j, k, g, w)
-def _flux_Vw(i, j, k, g, U, w): return _op.iz_aaf(i, j, k, g, _Ayv, U[1]) * _op.iy_afa(i, j, k, g, w)
-def _flux_Ww(i, j, k, g, U, w): return _op.iz_aac(i, j, k, g, _Azw, U[2]) * _op.iz_aac(i, j, k, g, w)
+# Centered(order = N) symmetric interpolation [OCN-mem Advection/centered_reconstruction.jl, topologically_conditional_interpolation.jl].
+# order 2: the two-point mean.  order 4: (-1, 7, 7, -1)/12 over the four nearest points (the uniform-grid coefficients, which
+# `Centered(order = 4)` built without a grid uses on stretched axes too); along a Bounded axis the stencil falls back to order 2
+# where it would reach across the wall: a face index m keeps order 4 for H+1 <= m <= N+1-H, a centre index for H <= m <= N+1-H,
+# with H = required_halo_size = 2 (outside_symmetric_haloᶠ / ᶜ).
+def advection_order(advection):
+    if advection is None or advection in ("Centered", "Centered(order=2)", 2):
+        return 2
+    if advection in ("Centered(order=4)", 4):
+        return 4
+    raise ValueError(f"advection scheme {advection!r} is not restated")
+
+
+def sym_interp(i, j, k, g, order, d, target, f, *args):
+    """Symmetric interpolation of `f` along axis d (0, 1, 2) to the location `target` ('c': from faces, index m between faces m
+    and m+1; 'f': from centres, index m between centres m-1 and m)."""
+    idx = (i, j, k)[d]
+    sh = lambda s: f(*_op._sh(d, i, j, k, s), g, *args) if callable(f) else f[_op._sh(d, i, j, k, s)]
+    lo = 0 if target == "c" else -1                     # the two nearest points: lo, lo + 1
+    two = (sh(lo) + sh(lo + 1)) / 2
+    if order == 2:
+        return two
+    four = (7 * (sh(lo) + sh(lo + 1)) - (sh(lo - 1) + sh(lo + 2))) / 12
+    if g.topology[d] != "B":
+        return four
+    N, Hs = g.N[d], 2
+    inside = (idx >= (Hs if target == "c" else Hs + 1)) & (idx <= N + 1 - Hs)
+    return np.where(inside, four, two)
+
+
+def _flux_Uu(i, j, k, g, o, U, u): return sym_interp(i, j, k, g, o, 0, "c", _Axu, U[0]) * sym_interp(i, j, k, g, o, 0, "c", u)
+def _flux_Vu(i, j, k, g, o, U, u): return sym_interp(i, j, k, g, o, 0, "f", _Ayv, U[1]) * sym_interp(i, j, k, g, o, 1, "f", u)
+def _flux_Wu(i, j, k, g, o, U, u): return sym_interp(i, j, k, g, o, 0, "f", _Azw, U[2]) * sym_interp(i, j, k, g, o, 2, "f", u)
+def _flux_Uv(i, j, k, g, o, U, v): return sym_interp(i, j, k, g, o, 1, "f", _Axu, U[0]) * sym_interp(i, j, k, g, o, 0, "f", v)
+def _flux_Vv(i, j, k, g, o, U, v): return sym_interp(i, j, k, g, o, 1, "c", _Ayv, U[1]) * sym_interp(i, j, k, g, o, 1, "c", v)
+def _flux_Wv(i, j, k, g, o, U, v): return sym_interp(i, j, k, g, o, 1, "f", _Azw, U[2]) * sym_interp(i, j, k, g, o, 2, "f", v)
+def _flux_Uw(i, j, k, g, o, U, w): return sym_interp(i, j, k, g, o, 2, "f", _Axu, U[0]) * sym_interp(i, j, k, g, o, 0, "f", w)
+def _flux_Vw(i, j, k, g, o, U, w): return sym_interp(i, j, k, g, o, 2, "f", _Ayv, U[1]) * sym_interp(i, j, k, g, o, 1, "f", w)
+def _flux_Ww(i, j, k, g, o, U, w): return sym_interp(i, j, k, g, o, 2, "c", _Azw, U[2]) * sym_interp(i, j, k, g, o, 2, "c", w)
 
 
 def div_Uu(i, j, k, g, advection, U, u):
     U = (U["u"], U["v"], U["w"]) if isinstance(U, dict) else U
-    return 1 / _op.V_fcc(i, j, k, g) * (_op.dx_faa(i, j, k, g, _flux_Uu, U, u) +
-                                       _op.dy_aca(i, j, k, g, _flux_Vu, U, u) +
-                                       _op.dz_aac(i, j, k, g, _flux_Wu, U, u))
+    o = advection_order(advection)
+    return 1 / _op.V_fcc(i, j, k, g) * (_op.dx_faa(i, j, k, g, _flux_Uu, o, U, u) +
+                                       _op.dy_aca(i, j, k, g, _flux_Vu, o, U, u) +
+                                       _op.dz_aac(i, j, k, g, _flux_Wu, o, U, u))
 
 
 def div_Uv(i, j, k, g, advection, U, v):
     U = (U["u"], U["v"], U["w"]) if isinstance(U, dict) else U
-    return 1 / _op.V_cfc(i, j, k, g) * (_op.dx_caa(i, j, k, g, _flux_Uv, U, v) +
-                                       _op.dy_afa(i, j, k, g, _flux_Vv, U, v) +
-                                       _op.dz_aac(i, j, k, g, _flux_Wv, U, v))
+    o = advection_order(advection)
+    return 1 / _op.V_cfc(i, j, k, g) * (_op.dx_caa(i, j, k, g, _flux_Uv, o, U, v) +
+                                       _op.dy_afa(i, j, k, g, _flux_Vv, o, U, v) +
+                                       _op.dz_aac(i, j, k, g, _flux_Wv, o, U, v))
 
 
 def div_Uw(i, j, k, g, advection, U, w):
     U = (U["u"], U["v"], U["w"]) if isinstance(U, dict) else U
-    return 1 / _op.V_ccf(i, j, k, g) * (_op.dx_caa(i, j, k, g, _flux_Uw, U, w) +
-                                       _op.dy_aca(i, j, k, g, _flux_Vw, U, w) +
-                                       _op.dz_aaf(i, j, k, g, _flux_Ww, U, w))
+    o = advection_order(advection)
+    return 1 / _op.V_ccf(i, j, k, g) * (_op.dx_caa(i, j, k, g, _flux_Uw, o, U, w) +
+                                       _op.dy_aca(i, j, k, g, _flux_Vw, o, U, w) +
+                                       _op.dz_aaf(i, j, k, g, _flux_Ww, o, U, w))
 
 
 # --- buoyancy projections for BuoyancyTracer [OCN-mem BuoyancyFormulations/buoyancy_force.jl]
@@ -208,7 +241,7 @@ def kinetic_energy_ccc(i, j, k, g, u, v, w):                 # src/KineticEnergy
     return (ix_caa(i, j, k, g, psi2, u) + iy_aca(i, j, k, g, psi2, v) + iz_aac(i, j, k, g, psi2, w)) / 2
 
 
-def ke_advection_ccc(i, j, k, g, velocities, advection=None):   # uᵢ∂ⱼuⱼuᵢᶜᶜᶜ, src/KineticEnergyEquation.jl:147-152
+def ke_advection_ccc(i, j, k, g, velocities, advection=None):   # uᵢ∂ⱼuⱼuᵢᶜᶜᶜ, src/KineticEnergyEquation.jl:147-152 (any Centered order)
     U = velocities
     a = ix_caa(i, j, k, g, psif, U["u"], div_Uu, advection, U, U["u"])
     b = iy_aca(i, j, k, g, psif, U["v"], div_Uv, advection, U, U["v"])
@@ -380,14 +413,15 @@ def smagorinsky_nu_ccc(i, j, k, g, u, v, w, b, C, Cb=0.0, Pr=1.0):
 
 # --- Centered (2nd-order) tracer advection  [OCN-mem Advection/tracer_advection_operators.jl]: advective fluxes
 # Ax u ℑx c (fcc), Ay v ℑy c (cfc), Az w ℑz c (ccf) and their divergence at the cell centre
-def _adv_flux_x(i, j, k, g, U, c): return _op.Ax_fcc(i, j, k, g) * U[0][i, j, k] * _op.ix_faa(i, j, k, g, c)
-def _adv_flux_y(i, j, k, g, U, c): return _op.Ay_cfc(i, j, k, g) * U[1][i, j, k] * _op.iy_afa(i, j, k, g, c)
-def _adv_flux_z(i, j, k, g, U, c): return _op.Az_ccf(i, j, k, g) * U[2][i, j, k] * _op.iz_aaf(i, j, k, g, c)
+def _adv_flux_x(i, j, k, g, o, U, c): return _op.Ax_fcc(i, j, k, g) * U[0][i, j, k] * sym_interp(i, j, k, g, o, 0, "f", c)
+def _adv_flux_y(i, j, k, g, o, U, c): return _op.Ay_cfc(i, j, k, g) * U[1][i, j, k] * sym_interp(i, j, k, g, o, 1, "f", c)
+def _adv_flux_z(i, j, k, g, o, U, c): return _op.Az_ccf(i, j, k, g) * U[2][i, j, k] * sym_interp(i, j, k, g, o, 2, "f", c)
 
 
 def div_Uc(i, j, k, g, advection, U, c):
-    return (_op.dx_caa(i, j, k, g, _adv_flux_x, U, c) + _op.dy_aca(i, j, k, g, _adv_flux_y, U, c) +
-            _op.dz_aac(i, j, k, g, _adv_flux_z, U, c)) / _op.V_ccc(i, j, k, g)
+    o = advection_order(advection)
+    return (_op.dx_caa(i, j, k, g, _adv_flux_x, o, U, c) + _op.dy_aca(i, j, k, g, _adv_flux_y, o, U, c) +
+            _op.dz_aac(i, j, k, g, _adv_flux_z, o, U, c)) / _op.V_ccc(i, j, k, g)
 
 
 def tracer_tendency(i, j, k, g, idx, name, advection, closure, c_immersed_bc, buoyancy, biogeochemistry, background_fields,

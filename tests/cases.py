@@ -145,6 +145,23 @@ def build_cases(st: State, closure_name="scalar", mean="profile"):
         ("TracerYDiffusiveFlux", TE.YDiffusiveFlux(m_p, "b"), ev(K.diffusive_flux_y, og, "cfc", oc, None, 1, st.ob), "cfc"),
         ("TracerZDiffusiveFlux", TE.ZDiffusiveFlux(m_p, "b"), ev(K.diffusive_flux_z, og, "ccf", oc, None, 1, st.ob), "ccf"),
     ]
+    # Centered(order = 4) advection (the scheme of every example of the reference, docs/examples/*.jl): the KE advection term, the
+    # KE and tracer-variance tendencies, and the momentum / tracer advection terms
+    m4 = st.model(closure=pc, coriolis=ocb.ConstantCartesianCoriolis(*f_cor), buoyancy=ocb.BuoyancyTracer(gravity_unit_vector=tuple(-t for t in tilt)))
+    m4.advection = "Centered(order=4)"
+    m4.forcing.u, m4.forcing.v, m4.forcing.w, m4.forcing.b = pforc["u"], pforc["v"], pforc["w"], m_forced.forcing.b
+    o4 = "Centered(order=4)"
+    cases += [
+        ("KineticEnergyAdvection_o4", KE.KineticEnergyAdvection(m4), ev(K.ke_advection_ccc, og, "ccc", of, o4), "ccc"),
+        ("KineticEnergyTendency_o4", KE.KineticEnergyTendency(m4),
+         ev(K.ke_tendency_ccc, og, "ccc", o4, f_cor, None, oc, None, None, None, tbuoy, None, vel, {"b": st.ob}, None, None, None, None, oforc), "ccc"),
+        ("TracerVarianceTendency_o4", TV.TracerVarianceTendency(m4, "b"),
+         ev(K.c_dt_c_ccc, og, "ccc", 1, "b", o4, oc, None, None, None, None, {"u": st.ou, "v": st.ov, "w": st.ow}, {"b": st.ob}, None, None, None, Fb), "ccc"),
+        ("UAdvection_o4", ocb.UMomentumEquation.Advection(m4), ev(K.div_Uu, og, "fcc", o4, vel, st.ou), "fcc"),
+        ("VAdvection_o4", ocb.VMomentumEquation.Advection(m4), ev(K.div_Uv, og, "cfc", o4, vel, st.ov), "cfc"),
+        ("WAdvection_o4", ocb.WMomentumEquation.Advection(m4), ev(K.div_Uw, og, "ccf", o4, vel, st.ow), "ccf"),
+        ("TracerAdvection_o4", TE.Advection(m4, "b"), ev(K.div_Uc, og, "ccc", o4, Uo, st.ob), "ccc"),
+    ]
     # Smagorinsky-Lilly eddy viscosity computed by the library (scope table 8f, row 3), without and with the stratification factor
     for tag, Cb in (("", None), ("_Cb", 1.0)):
         sm = ocb.SmagorinskyLilly(C=0.16, Cb=Cb, Pr=1.0)

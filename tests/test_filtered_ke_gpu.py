@@ -156,7 +156,7 @@ def test_names_outside_the_hot_path_fail_loudly():
             fn(m)
     # the kinetic-energy tendency is evaluated for the plain NonhydrostaticModel; what the library does not restate is refused
     m.advection = "WENO(order=5)"
-    with pytest.raises(ocb.OcbError, match="Centered"):
+    with pytest.raises(ocb.OcbError, match="Centered"):           # (Centered(order = 4) IS evaluated: cases "_o4")
         ocb.KineticEnergyEquation.KineticEnergyTendency(m)
     m.advection, m.stokes_drift = "Centered", object()
     with pytest.raises(ocb.OcbError, match="stokes_drift"):

@@ -163,6 +163,46 @@ def test_ke_advection_known_answer():
     np.testing.assert_allclose(adv[0, 1:N - 1, 0], C1 ** 2 * C2 * yc, rtol=1e-12)
 
 
+def test_centered_fourth_order_advection():
+    """Centered(order = 4) -- the scheme of every example of the reference (docs/examples/*.jl: `advection = Centered(order=4)`).
+    (a) the reference's own advection known answer u = C1 y, v = C2 => ADV = C1² C2 y (test/test_kinetic_energy_equation.jl:41-55)
+    holds for any consistent centred scheme on these linear fields; (b) with a constant advecting velocity the flux divergence of
+    the (-1, 7, 7, -1)/12 interpolation IS the classic fourth-order central difference: the error of div_Uc on c = sin 2πx drops 16 x
+    per halving of the spacing (4 x with order 2) -- this pins the coefficients and the flux positions; (c) along the Bounded z axis
+    the stencil falls back to order 2 next to the walls [OCN-mem: outside_symmetric_halo], and only there."""
+    g = regular_grid()
+    C1, C2 = 2.0, 3.0
+    u, v, w = velocities(g, lambda x, y, z: C1 * y, C2)
+    adv = K.evaluate(K.ke_advection_ccc, g, "ccc", dict(u=u, v=v, w=w), "Centered(order=4)")
+    yc = g.centers[1][np.arange(3, N - 1)]
+    np.testing.assert_allclose(adv[0, 2:N - 2, 0], C1 ** 2 * C2 * yc, rtol=1e-12)      # rows whose stencil stays clear of the periodic seam
+    errs = {}
+    for order in ("Centered", "Centered(order=4)"):
+        for n in (16, 32):
+            gg = OGrid((n, 4, 4), extent=(1, 1, 1))
+            uu = OField(gg, "fcc").set(1.5).fill_halo()
+            vv = OField(gg, "cfc").set(0.0).fill_halo()
+            ww = OField(gg, "ccf").set(0.0).fill_halo()
+            c = OField(gg, "ccc").set(lambda x, y, z: np.sin(2 * np.pi * x)).fill_halo()
+            got = K.evaluate(K.div_Uc, gg, "ccc", order, (uu, vv, ww), c)[:, 0, 1]
+            xc = (np.arange(n) + 0.5) / n
+            errs[(order, n)] = np.abs(got - 1.5 * 2 * np.pi * np.cos(2 * np.pi * xc)).max()
+    assert 3.8 < errs[("Centered", 16)] / errs[("Centered", 32)] < 4.2
+    assert 15.0 < errs[("Centered(order=4)", 16)] / errs[("Centered(order=4)", 32)] < 17.0
+    assert errs[("Centered(order=4)", 32)] < 1e-2 * errs[("Centered", 32)]
+    # (c) vertical advection of a tracer by w = const: faces 2 and Nz (and the wall faces) are second order, faces 3 .. Nz-1 fourth
+    gz = OGrid((4, 4, 8), extent=(1, 1, 1))
+    zero_u, zero_v = OField(gz, "fcc").set(0.0).fill_halo(), OField(gz, "cfc").set(0.0).fill_halo()
+    wz = OField(gz, "ccf").set(1.0).fill_halo(impenetrable=False)
+    cz = OField(gz, "ccc").set(lambda x, y, z: z ** 3).fill_halo()
+    kk = np.arange(1, 10)[None, None, :]
+    one = np.array([[[1]]])
+    f2 = K._adv_flux_z(one, one, kk, gz, 2, (zero_u, zero_v, wz), cz)[0, 0]
+    f4 = K._adv_flux_z(one, one, kk, gz, 4, (zero_u, zero_v, wz), cz)[0, 0]
+    same = np.isclose(f2, f4, rtol=1e-14, atol=0)
+    assert same.tolist() == [True, True, False, False, False, False, False, True, True]
+
+
 @pytest.mark.parametrize("gname", GRIDS)
 def test_buoyancy_production_known_answer(gname):
     """test/test_kinetic_energy_equation.jl:131-140: w = w0, b = b0  =>  wb == w0 b0 exactly."""
