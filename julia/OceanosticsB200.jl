@@ -447,7 +447,7 @@ function forcing_field(F, forced::Field, clock, model_fields)
 end
 
 # c∂ₜcᶜᶜᶜ (TracerVarianceEquation.jl:70-88) and uᵢGᵢᶜᶜᶜ (KineticEnergyEquation.jl:120-142): NonhydrostaticModel without
-# background fields, immersed boundaries, Stokes drift or biogeochemistry; Centered(order = 2) advection
+# background fields, immersed boundaries, Stokes drift or biogeochemistry; Centered(order = 2 | 4) advection
 function tendency_slots_tracer(a)
     id, name, advection, closure, immersed, buoyancy, bgc, background, velocities, tracers, aux, K, clock, forcing = a
     (immersed === nothing && bgc === nothing && all(isnothing, values(background.tracers))) ||

@@ -25,6 +25,7 @@ constexpr int RS_THREADS = 256;
 constexpr int RS_ITEMS = 16;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;   // keys per block
 constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_MAX_DEVICES = 64;
 
 template <class K> struct KeyTraits;
 template <> struct KeyTraits<uint64_t> { using F = double; static constexpr int BITS = 64; };
@@ -75,77 +76,159 @@ __global__ void __launch_bounds__(RS_THREADS) rs_histogram(const K* __restrict__
   table[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
 }
 
-// stable scatter of one tile: warp w owns the contiguous sub-tile [w*512, (w+1)*512), walked in 16 rounds of 32.
-// The tile is first put in digit order in shared memory (keys, then the payload through the same buffer), so that the
-// global writes are runs of consecutive addresses per digit (16 keys = 128 B on average) instead of one sector per key.
-// CHAINED = false: the tile's global digit offsets come from the scanned per-tile histogram table (`offsets`, digit-major).
+// stable scatter of a tile: warp w owns the contiguous sub-tile [w*512, (w+1)*512), walked in 16 rounds of 32.
+// The tile is first put in digit order in shared memory (keys in `stage`, the payload in `ibuf`), so that the global writes are
+// runs of consecutive addresses per digit (16 keys = 128 B on average) instead of one sector per key.
+// CHAINED = false: the tile is blockIdx.x and its global digit offsets come from the scanned per-tile histogram table (`offsets`,
+// digit-major).
 // CHAINED = true ("onesweep"): no histogram pass and no table scan -- `offsets` holds the 256 global digit bases of this pass
-// (from ONE up-front histogram of all digits), tiles take their number from a ticket counter, publish their digit counts in
-// `desc[tile][digit]` (count | flag in one word: AGGREGATE = the tile's own count, INCLUSIVE = everything up to and including the
-// tile) and thread d looks back over the preceding tiles' words of digit d until it meets an INCLUSIVE one (decoupled look-back;
-// a tile only ever waits for tiles with smaller tickets, which are running).  A wait is bounded: a stuck look-back sets desc's
-// error word and moves on instead of hanging the device.
-constexpr uint32_t RS_AGG = 1u << 30, RS_INCL = 1u << 31, RS_CNT = (1u << 30) - 1u;
+// (from ONE up-front histogram of all digits); the blocks are persistent and take tile numbers from a ticket counter (the next
+// ticket is requested while the current tile is processed), publish their digit counts in `desc[tile][digit]` (count | flag in one
+// word: AGGREGATE = the tile's own count, INCLUSIVE = everything up to and including the tile) and thread d looks back over the
+// preceding tiles' words of digit d until it meets an INCLUSIVE one (decoupled look-back; a tile only ever waits for tiles with
+// smaller tickets, which are running).  A wait is bounded: a stuck look-back sets desc's error word and moves on instead of
+// hanging the device.
+// Latency (profiles/r2_summary.md, K3): the payload of the tile is fetched with cp.async into `ibuf` BEFORE the ranking rounds (it
+// used to be loaded where it was needed: 44 % of the kernel's stall samples), and the look-back runs after the keys have been
+// staged, i.e. as late as its result is needed, when the predecessors have had time to publish their inclusive words.
+// Two-level chained scan.  Tiles form groups of RS_G consecutive tickets.  Every tile publishes its digit counts agg[tile][256];
+// the exclusive prefix of tile t = (g, i) is GX[g] + the counts of the i tiles before it in its group, where GX[g] = the counts of
+// all tiles of groups < g.  The last tile of a group publishes the group total GT[g], the first one GX[g]; a tile that needs
+// GX[g] takes the nearest published GX[g-k] plus GT[g-1] .. GT[g-k].  One poll of the flags (lanes 0..15: the group's tiles, lanes
+// 16..31: the groups g, g-1, ..) and one batch of independent loads when everything is there: ~25 words per thread and two round
+// trips to L2, where a plain look-back (one level, 32 tiles per poll) read ~64 words per thread in 5 polls -- at 28 tiles per
+// microsecond the inclusive frontier of a one-level chain trails 64 tiles behind (measured; profiles/r2_summary.md, K3).
+// desc layout (32-bit words): aggf[nblocks] flags, the ticket counter, the error word, gtf[ngroups], gxf[ngroups], padding to
+// rs_desc_header(nblocks); then agg[nblocks][256], gt[ngroups][256], gx[ngroups][256], all write-once per pass, so only the header
+// is cleared between passes.
+constexpr int RS_G = 16;    // tiles per group
+constexpr int RS_GK = 8;    // groups looked back over per poll
+__host__ __device__ constexpr size_t rs_groups(int nblocks) { return ((size_t)nblocks + RS_G - 1) / RS_G; }
+__host__ __device__ constexpr size_t rs_desc_header(int nblocks) { return (((size_t)nblocks + 2 + 2 * rs_groups(nblocks) + 63) / 64) * 64; }
+constexpr size_t rs_table_words(int nblocks) {                         // also >= the 256 nblocks table of the scan path
+  return rs_desc_header(nblocks) + 256ull * ((size_t)nblocks + 2 * rs_groups(nblocks));
+}
+__device__ __forceinline__ void rs_st_release(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// flag poll: a relaxed gpu-scope load (L2).  ld.acquire.gpu compiles to the same load plus CCTL.IVALL -- an invalidation of the
+// whole L1 per poll and warp, measured at +0.5 ms per pass.  The words read after a flag are read with __ldcg (L2, never L1) at
+// addresses / under predicates that depend on the flag's value, so they are issued after the flag has arrived, and the writer
+// orders its words before its flag with a gpu-scope release.
+__device__ __forceinline__ uint32_t rs_ld_flag(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+template <class K> constexpr size_t rs_scatter_smem() {
+  return sizeof(K) * RS_TILE + sizeof(uint32_t) * (RS_TILE + RS_WARPS * 256 + 256 + 256 + RS_WARPS + 8);
+}
+__device__ __forceinline__ void rs_cp_async16(void* smem, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void rs_cp_async4(void* smem, const void* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
+}
 template <class K, bool CHAINED = false>
 __global__ void __launch_bounds__(RS_THREADS, 3) rs_scatter(const K* __restrict__ keys_in, const uint32_t* __restrict__ idx_in, K* __restrict__ keys_out,
                                                           uint32_t* __restrict__ idx_out, long long n, int shift,
-                                                          const uint32_t* __restrict__ offsets, int nblocks, uint32_t* desc = nullptr) {
-  __shared__ uint32_t wcount[RS_WARPS][256];     // per-warp running digit counts -> per-warp digit bases inside the tile
-  __shared__ uint32_t gbase[256];                // global position of the tile's first key of each digit, minus its tile position
-  __shared__ uint32_t tstart[256];               // tile position of the first key of each digit
-  __shared__ uint32_t wtot[RS_WARPS];
-  __shared__ K stage[RS_TILE];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int d = lane; d < 256; d += 32) { wcount[warp][d] = 0; reinterpret_cast<uint32_t*>(stage)[warp * 256 + d] = 0; }
-  int tile = blockIdx.x;
-  if (CHAINED) {                                          // desc: [nblocks][256] words, then the ticket counter, then the error word
-    if (threadIdx.x == 0) wtot[0] = atomicAdd(desc + (size_t)nblocks * 256, 1u);
-    __syncthreads();
-    tile = (int)wtot[0];
-    __syncthreads();
-  }
-  __syncwarp();
-  const long long tbase = (long long)tile * RS_TILE;
-  const long long wbase = tbase + (long long)warp * (RS_ITEMS * 32);
-  const int ntile = (int)((n - tbase) < (long long)RS_TILE ? (n - tbase) : (long long)RS_TILE);
-  K key[RS_ITEMS];
-  uint32_t rank[RS_ITEMS];
-  const unsigned lt = (1u << lane) - 1u;
-  // all of the thread's keys first (16 independent loads in flight), then the ranking rounds
-#pragma unroll
-  for (int r = 0; r < RS_ITEMS; ++r) {
-    const long long t = wbase + r * 32 + lane;
-    key[r] = t < n ? __ldg(keys_in + t) : (K)~(K)0;
-  }
-  // Ranking: lanes of a round that hold the same digit must learn of each other (their ranks follow the lane order: the sort
-  // is stable).  MATCH.ANY does that in hardware by looping over the distinct values of the warp -- ~30 of them with 8-bit
-  // digits, which made these 16 rounds the whole cost of a pass (issue slots 12 % busy, profiles/r1_summary.md).  Instead every
-  // lane ORs its bit into a per-warp, per-digit mask word in shared memory (the staging buffer, idle until the ranks are known)
-  // and reads the word back: one shared atomic and two loads per round.
+                                                          const uint32_t* __restrict__ offsets, int nblocks, uint32_t* desc = nullptr, int dbg = 0) {
+  extern __shared__ __align__(16) unsigned char rs_smem[];
+  K* stage = reinterpret_cast<K*>(rs_smem);                                     // the tile's keys in digit order
+  uint32_t* ibuf = reinterpret_cast<uint32_t*>(stage + RS_TILE);                // the tile's payload: tile order, then digit order
+  uint32_t (*wcount)[256] = reinterpret_cast<uint32_t (*)[256]>(ibuf + RS_TILE);  // per-warp running digit counts -> per-warp digit bases
+  uint32_t* gbase = ibuf + RS_TILE + RS_WARPS * 256;   // global position of the tile's first key of each digit, minus its tile position
+  uint32_t* tstart = gbase + 256;                      // tile position of the first key of each digit
+  uint32_t* wtot = tstart + 256;                       // [RS_WARPS] block-scan totals, [RS_WARPS] the tile number
+  // the ranking masks live in the staging buffer, idle until the ranks are known
   uint32_t (*wmask)[256] = reinterpret_cast<uint32_t (*)[256]>(stage);
-#pragma unroll
-  for (int r = 0; r < RS_ITEMS; ++r) {
-    const long long t = wbase + r * 32 + lane;
-    const bool ok = t < n;
-    const uint32_t dig = ok ? ((uint32_t)(key[r] >> shift) & 255u) : 0u;
-    volatile uint32_t* mp = &wmask[warp][dig];
-    volatile uint32_t* cp = &wcount[warp][dig];
-    if (ok) atomicOr(&wmask[warp][dig], 1u << lane);
-    __syncwarp();
-    const unsigned peers = ok ? *mp : 0u;
-    const uint32_t prev = ok ? *cp : 0u;
-    __syncwarp();
-    if (ok && (peers & lt) == 0) { *cp = prev + __popc(peers); *mp = 0u; }   // the lowest lane of each digit group updates and clears
-    __syncwarp();
-    rank[r] = prev + __popc(peers & lt);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  int tile = blockIdx.x;
+  const int ngroups = (int)rs_groups(nblocks);
+  uint32_t* const gtf = desc + nblocks + 2;
+  uint32_t* const gxf = gtf + ngroups;
+  uint32_t* const agg = desc + rs_desc_header(nblocks);
+  uint32_t* const gt = agg + (size_t)nblocks * 256;
+  uint32_t* const gx = gt + (size_t)ngroups * 256;
+  if (CHAINED) {
+    if (threadIdx.x == 0) wtot[RS_WARPS] = atomicAdd(desc + nblocks, 1u);
+    __syncthreads();
+    tile = (int)wtot[RS_WARPS];
   }
-  __syncthreads();
-  // thread d: exclusive scan across warps for digit d, then (block scan) the tile position where digit d starts
-  {
-    uint32_t run = 0;
+  while (tile < nblocks) {
+    uint32_t next_ticket = 0;
+    const long long tbase = (long long)tile * RS_TILE;
+    const int ntile = (int)((n - tbase) < (long long)RS_TILE ? (n - tbase) : (long long)RS_TILE);
+    const int wl = warp * (RS_ITEMS * 32) + lane;         // tile position of the thread's key of round r: wl + 32 r
+    for (int d = lane; d < 256; d += 32) { wcount[warp][d] = 0; wmask[warp][d] = 0; }
+    if (idx_in) {                                         // payload -> ibuf, tile order, asynchronously
+      const uint32_t* src = idx_in + tbase;
+      if (ntile == RS_TILE && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+#pragma unroll
+        for (int q = 0; q < RS_ITEMS / 4; ++q) rs_cp_async16(ibuf + 4 * (threadIdx.x + RS_THREADS * q), src + 4 * (threadIdx.x + RS_THREADS * q));
+      } else {
+#pragma unroll
+        for (int r = 0; r < RS_ITEMS; ++r) { const int e = r * RS_THREADS + threadIdx.x; if (e < ntile) rs_cp_async4(ibuf + e, src + e); }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    K key[RS_ITEMS];
+    uint32_t rank[RS_ITEMS];
+    // all of the thread's keys first (16 independent loads in flight), then the ranking rounds
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) key[r] = (wl + 32 * r) < ntile ? __ldg(keys_in + tbase + wl + 32 * r) : (K)~(K)0;
+    __syncwarp();
+    // Ranking: lanes of a round that hold the same digit must learn of each other (their ranks follow the lane order: the sort
+    // is stable).  MATCH.ANY does that in hardware by looping over the distinct values of the warp -- ~30 of them with 8-bit
+    // digits, which made these 16 rounds the whole cost of a pass (issue slots 12 % busy, profiles/r1_summary.md).  Instead every
+    // lane ORs its bit into a per-warp, per-digit mask word in shared memory and reads the word back: one shared atomic and two
+    // loads per round.
+    if (dbg & 4) {
+#pragma unroll
+      for (int r = 0; r < RS_ITEMS; ++r) {
+        const bool ok = (wl + 32 * r) < ntile;
+        const uint32_t dig = ok ? ((uint32_t)(key[r] >> shift) & 255u) : 0u;
+        unsigned peers = __ballot_sync(0xffffffffu, ok);
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          const bool bit = (dig >> b) & 1u;
+          const unsigned m = __ballot_sync(0xffffffffu, bit);
+          peers &= bit ? m : ~m;
+        }
+        if (!ok) peers = 0u;
+        volatile uint32_t* cp = &wcount[warp][dig];
+        const uint32_t prev = ok ? *cp : 0u;
+        __syncwarp();
+        if (ok && (peers & lt) == 0) *cp = prev + __popc(peers);
+        __syncwarp();
+        rank[r] = prev + __popc(peers & lt);
+      }
+    } else {
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+      const bool ok = (wl + 32 * r) < ntile;
+      const uint32_t dig = ok ? ((uint32_t)(key[r] >> shift) & 255u) : 0u;
+      volatile uint32_t* mp = &wmask[warp][dig];
+      volatile uint32_t* cp = &wcount[warp][dig];
+      if (ok) atomicOr(&wmask[warp][dig], 1u << lane);
+      __syncwarp();
+      const unsigned peers = ok ? *mp : 0u;
+      const uint32_t prev = ok ? *cp : 0u;
+      __syncwarp();
+      if (ok && (peers & lt) == 0) { *cp = prev + __popc(peers); *mp = 0u; }   // the lowest lane of each digit group updates and clears
+      __syncwarp();
+      rank[r] = prev + __popc(peers & lt);
+    }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    // thread d: exclusive scan across warps for digit d, then (block scan) the tile position where digit d starts
     const int d = threadIdx.x;
+    uint32_t run = 0;
 #pragma unroll
     for (int w = 0; w < RS_WARPS; ++w) { const uint32_t c = wcount[w][d]; wcount[w][d] = run; run += c; }
+    if (CHAINED) agg[(size_t)tile * 256 + d] = run;
     uint32_t inc = run;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
@@ -156,65 +239,117 @@ __global__ void __launch_bounds__(RS_THREADS, 3) rs_scatter(const K* __restrict_
     for (int w = 0; w < RS_WARPS; ++w) if (w < warp) before += wtot[w];
     const uint32_t start = before + inc - run;
     tstart[d] = start;
-    if (!CHAINED) {
-      gbase[d] = offsets[(size_t)d * nblocks + tile] - start;
-    } else {
-      volatile uint32_t* D = desc;
-      uint32_t excl = 0;
-      if (tile == 0) {
-        D[d] = run | RS_INCL;
-      } else {
-        D[(size_t)tile * 256 + d] = run | RS_AGG;
-        int j = tile - 1;
-        unsigned spins = 0;
-        for (;;) {
-          const uint32_t v = D[(size_t)j * 256 + d];
-          if (v & RS_INCL) { excl += v & RS_CNT; break; }
-          if (v & RS_AGG) { excl += v & RS_CNT; --j; spins = 0; continue; }
-          if (++spins > (1u << 22)) { D[(size_t)nblocks * 256 + 1] = 1u; break; }
-          __nanosleep(20);
-        }
-        D[(size_t)tile * 256 + d] = (excl + run) | RS_INCL;
+    if (CHAINED && threadIdx.x == 0) rs_st_release(desc + tile, 1u);   // after the scan's barrier: all 256 words are written
+    if (!CHAINED) gbase[d] = offsets[(size_t)d * nblocks + tile] - start;
+    __syncthreads();
+    // keys: into digit order in shared memory; the thread's payload: out of the tile-order buffer into registers
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+      if ((wl + 32 * r) < ntile) {
+        const uint32_t dig = (uint32_t)(key[r] >> shift) & 255u;
+        rank[r] = tstart[dig] + wcount[warp][dig] + rank[r];                    // tile position
+        stage[rank[r]] = key[r];
       }
-      gbase[d] = offsets[d] + excl - start;
     }
-  }
-  __syncthreads();
-  // keys: into digit order in shared memory, then out in runs
+    const int grp = tile / RS_G, gi = tile % RS_G;
+    if (CHAINED) {
+      uint32_t pin = 0, gxs = 0;                           // counts of the group's earlier tiles; of all earlier groups
+      if (!(dbg & 2)) {
+        bool need_in = gi > 0, need_g = grp > 0;
+        unsigned spins = 0;
+        while (need_in || need_g) {
+          uint32_t fa = 0, fx = 0, ft = 0;
+          if (lane < 16) {
+            if (need_in && lane < gi) fa = rs_ld_flag(desc + tile - 1 - lane);
+          } else if (need_g) {
+            const int k = lane - 16;
+            if (k < RS_GK && grp - k >= 0) fx = rs_ld_flag(gxf + grp - k);
+            if (k < RS_GK && grp - 1 - k >= 0) ft = rs_ld_flag(gtf + grp - 1 - k);
+          }
+          __syncwarp();
+          const unsigned am = __ballot_sync(0xffffffffu, fa != 0u) & 0xffffu;
+          const unsigned xm = __ballot_sync(0xffffffffu, fx != 0u) >> 16, tm = __ballot_sync(0xffffffffu, ft != 0u) >> 16;
+          const bool go_in = need_in && am == ((1u << gi) - 1u);
+          const int kx = xm ? __ffs(xm) - 1 : 99;              // nearest group whose exclusive prefix is published
+          const bool go_g = need_g && xm && (tm & ((1u << kx) - 1u)) == ((1u << kx) - 1u);
+          uint32_t va[RS_G - 1], vg[RS_GK];
+          if (go_in) {
 #pragma unroll
-  for (int r = 0; r < RS_ITEMS; ++r) {
-    const long long t = wbase + r * 32 + lane;
-    if (t < n) {
-      const uint32_t dig = (uint32_t)(key[r] >> shift) & 255u;
-      rank[r] = tstart[dig] + wcount[warp][dig] + rank[r];                    // tile position
-      stage[rank[r]] = key[r];
+            for (int q = 0; q < RS_G - 1; ++q) va[q] = q < gi ? __ldcg(agg + (size_t)(tile - 1 - q) * 256 + d) : 0u;
+          }
+          if (go_g) {
+            vg[0] = __ldcg(gx + (size_t)(grp - kx) * 256 + d);
+#pragma unroll
+            for (int q = 1; q < RS_GK; ++q) vg[q] = q <= kx ? __ldcg(gt + (size_t)(grp - q) * 256 + d) : 0u;
+          }
+          if (go_in) {
+#pragma unroll
+            for (int q = 0; q < RS_G - 1; ++q) pin += va[q];
+            need_in = false;
+          }
+          if (go_g) {
+#pragma unroll
+            for (int q = 0; q < RS_GK; ++q) gxs += vg[q];
+            need_g = false;
+          }
+          if (!go_in && !go_g) {
+            if (++spins > (1u << 20)) { if (lane == 0) atomicExch(desc + nblocks + 1, 1u); break; }
+            __nanosleep(40);
+          } else spins = 0;
+        }
+        if (gi == 0) gx[(size_t)grp * 256 + d] = gxs;
+        if (gi == RS_G - 1) gt[(size_t)grp * 256 + d] = pin + run;
+      }
+      gbase[d] = offsets[d] + gxs + pin - start;
     }
-  }
-  __syncthreads();
-  uint32_t pos[RS_ITEMS];
+    uint32_t pay[RS_ITEMS];
 #pragma unroll
-  for (int r = 0; r < RS_ITEMS; ++r) {
-    const int e = r * RS_THREADS + threadIdx.x;
-    if (e < ntile) {
-      const K k = stage[e];
-      pos[r] = gbase[(uint32_t)(k >> shift) & 255u] + (uint32_t)e;
-      keys_out[pos[r]] = k;
+    for (int r = 0; r < RS_ITEMS; ++r) pay[r] = idx_in ? ibuf[wl + 32 * r] : (uint32_t)(tbase + wl + 32 * r);   // no payload array: the key's position
+    __syncthreads();
+    if (CHAINED && threadIdx.x == 0) {                     // after the barrier: all 256 words of the rows are written
+      if (gi == 0) rs_st_release(gxf + grp, 1u);
+      if (gi == RS_G - 1) rs_st_release(gtf + grp, 1u);
     }
-  }
-  __syncthreads();
-  // payload: the same way through the same buffer
-  uint32_t* stage_i = reinterpret_cast<uint32_t*>(stage);
 #pragma unroll
-  for (int r = 0; r < RS_ITEMS; ++r) {
-    const long long t = wbase + r * 32 + lane;
-    if (t < n) stage_i[rank[r]] = idx_in ? __ldg(idx_in + t) : (uint32_t)t;      // no payload array: the key's position
-  }
-  __syncthreads();
+    for (int r = 0; r < RS_ITEMS; ++r) if ((wl + 32 * r) < ntile) ibuf[rank[r]] = pay[r];
+    __syncthreads();
+    // the next tile's number: asked for as late as the write-out can still hide the round trip -- tickets are the look-back
+    // order, and a ticket held long before its tile starts makes every successor wait for it
+    if (CHAINED && threadIdx.x == 0) next_ticket = atomicAdd(desc + nblocks, 1u);
+    // out in runs: key and payload of tile position e
 #pragma unroll
-  for (int r = 0; r < RS_ITEMS; ++r) {
-    const int e = r * RS_THREADS + threadIdx.x;
-    if (e < ntile) idx_out[pos[r]] = stage_i[e];
+    for (int r = 0; r < RS_ITEMS; ++r) {
+      const int e = r * RS_THREADS + threadIdx.x;
+      if (e < ntile) {
+        const K k = stage[e];
+        uint32_t pos = gbase[(uint32_t)(k >> shift) & 255u] + (uint32_t)e;
+        if (dbg & 1) pos = (uint32_t)tbase + (uint32_t)e;
+        keys_out[pos] = k;
+        idx_out[pos] = ibuf[e];
+      }
+    }
+    if (!CHAINED) break;
+    if (threadIdx.x == 0) wtot[RS_WARPS] = next_ticket;
+    __syncthreads();                                       // also: the staging buffers are free again
+    tile = (int)wtot[RS_WARPS];
   }
+}
+template <class K, bool CHAINED>
+int rs_launch_scatter(const K* kin, const uint32_t* iin, K* kout, uint32_t* iout, long long n, int shift, const uint32_t* offsets, int nblocks,
+                      uint32_t* desc, cudaStream_t st) {
+  static bool configured[RS_MAX_DEVICES] = {};
+  int dev = 0;
+  OCB_CUDA(cudaGetDevice(&dev));
+  constexpr size_t smem = rs_scatter_smem<K>();
+  if (dev < 0 || dev >= RS_MAX_DEVICES || !configured[dev]) {
+    OCB_CUDA(cudaFuncSetAttribute(rs_scatter<K, CHAINED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (dev >= 0 && dev < RS_MAX_DEVICES) configured[dev] = true;
+  }
+  int grid = nblocks;
+  if (CHAINED) { const int resident = 3 * ocb_sm_count(); if (grid > resident) grid = resident; }
+  static const int dbg = getenv("OCB_SORT_DBG") ? atoi(getenv("OCB_SORT_DBG")) : 0;
+  rs_scatter<K, CHAINED><<<grid, RS_THREADS, smem, st>>>(kin, iin, kout, iout, n, shift, offsets, nblocks, desc, dbg);
+  return OCB_OK;
 }
 
 // all digit histograms of the keys in one read: hist[pass][256] (global digit counts do not depend on the order of the keys)
@@ -407,8 +542,8 @@ int radix_sort_pairs(K* keys_a, uint32_t* idx_a, K* keys_b, uint32_t* idx_b, lon
       rs_histogram_all<K><<<hb, RS_THREADS, 0, st>>>(kin, n, hist);
       rs_digit_bases<<<NP, 256, 0, st>>>(hist);
       for (int p = 0; p < NP; ++p) {
-        OCB_CUDA(cudaMemsetAsync(table, 0, sizeof(uint32_t) * ((size_t)ntab + 2), st));      // descriptors, ticket, error word
-        rs_scatter<K, true><<<nblocks, RS_THREADS, 0, st>>>(kin, iin, kout, iout, n, 8 * p, hist + p * 256, nblocks, table);
+        OCB_CUDA(cudaMemsetAsync(table, 0, sizeof(uint32_t) * rs_desc_header(nblocks), st));      // flags, ticket, error word
+        { const int rc = rs_launch_scatter<K, true>(kin, iin, kout, iout, n, 8 * p, hist + p * 256, nblocks, table, st); if (rc != OCB_OK) return rc; }
         K* tk = kin; kin = kout; kout = tk;
         uint32_t* ti = iin; iin = iout; iout = ti;
       }
@@ -421,7 +556,8 @@ int radix_sort_pairs(K* keys_a, uint32_t* idx_a, K* keys_b, uint32_t* idx_b, lon
     rs_histogram<K><<<nblocks, RS_THREADS, 0, st>>>(kin, n, shift, table, nblocks);
     int rc = device_scan<uint32_t, OP_ADD, false, true>(table, table, ntab, table_tot, st);
     if (rc != OCB_OK) return rc;
-    rs_scatter<K><<<nblocks, RS_THREADS, 0, st>>>(kin, iin, kout, iout, n, shift, table, nblocks);
+    rc = rs_launch_scatter<K, false>(kin, iin, kout, iout, n, shift, table, nblocks, nullptr, st);
+    if (rc != OCB_OK) return rc;
     K* tk = kin; kin = kout; kout = tk;
     uint32_t* ti = iin; iin = iout; iout = ti;
   }
@@ -637,7 +773,7 @@ int sort_impl(const T* keys_in, T* keys_out, uint32_t* perm_out, long long n, cu
   const int nblocks = (int)((n + RS_TILE - 1) / RS_TILE);
   K* ka = S.get<K>(n); K* kb = S.get<K>(n);
   uint32_t* ia = S.get<uint32_t>(n); uint32_t* ib = S.get<uint32_t>(n);
-  uint32_t* table = S.get<uint32_t>(256ull * nblocks);
+  uint32_t* table = S.get<uint32_t>(rs_table_words(nblocks));
   uint32_t* tot = S.get<uint32_t>((256ull * nblocks + SC_CHUNK - 1) / SC_CHUNK + 1 + 8 * 256);   // + the digit histograms of the onesweep path
   if (!ka || !kb || !ia || !ib || !table || !tot) OCB_FAIL(OCB_ERR_ALLOC, "out of device memory for the sort scratch");
   const unsigned g = (unsigned)((n + 255) / 256);
@@ -660,7 +796,7 @@ int bpe_sort3d_uniform(const ocb_grid* g, const ocb_field* b, const ocb_field* z
   const int nblocks = (int)((n + RS_TILE - 1) / RS_TILE);
   K* ka = S.get<K>(n); K* kb = S.get<K>(n);
   uint32_t* ia = S.get<uint32_t>(n); uint32_t* ib = S.get<uint32_t>(n);
-  uint32_t* table = S.get<uint32_t>(256ull * nblocks);
+  uint32_t* table = S.get<uint32_t>(rs_table_words(nblocks));
   uint32_t* tot = S.get<uint32_t>((256ull * nblocks + SC_CHUNK - 1) / SC_CHUNK + 1 + 8 * 256);   // + the digit histograms of the onesweep path
   double* psi = S.get<double>(n);
   double* dtot = S.get<double>((n + SC_CHUNK - 1) / SC_CHUNK + 1);
@@ -699,7 +835,7 @@ int bpe_sort3d_uniform(const ocb_grid* g, const ocb_field* b, const ocb_field* z
     rs_histogram<uint32_t><<<nblocks, RS_THREADS, 0, st>>>(perm, n, shift, table, nblocks);
     rc = device_scan<uint32_t, OP_ADD, false, true>(table, table, 256ll * nblocks, tot, st);
     if (rc != OCB_OK) return rc;
-    rs_scatter<uint32_t><<<nblocks, RS_THREADS, 0, st>>>(perm, nullptr, cells2, ranks2, n, shift, table, nblocks);
+    { const int rc2 = rs_launch_scatter<uint32_t, false>(perm, nullptr, cells2, ranks2, n, shift, table, nblocks, nullptr, st); if (rc2 != OCB_OK) return rc2; }
     bpe_scatter_bucketed<T, K><<<gr, 256, 0, st>>>(cells2, ranks2, ks, psi, n, Nx, Ny, U, psi_level, z1, Z.sx, Z.sy, Z.sz, p1, P.sx, P.sy, P.sz);
     if (perm_out || bs_out) bpe_sorted_outputs<T, K><<<gr, 256, 0, st>>>(perm, ks, n, perm_out, (T*)bs_out);
   } else {
@@ -723,7 +859,7 @@ int bpe_impl(const ocb_grid* g, const ocb_field* b, int method, const ocb_field*
   T* bs = S.get<T>(n); T* zs_sorted = S.get<T>(n);
   K* ka = S.get<K>(n); K* kb = S.get<K>(n);
   uint32_t* ia = S.get<uint32_t>(n); uint32_t* ib = S.get<uint32_t>(n);
-  uint32_t* table = S.get<uint32_t>(256ull * nblocks);
+  uint32_t* table = S.get<uint32_t>(rs_table_words(nblocks));
   uint32_t* tot = S.get<uint32_t>((256ull * nblocks + SC_CHUNK - 1) / SC_CHUNK + 1 + 8 * 256);   // + the digit histograms of the onesweep path
   double* dV = S.get<double>(n); double* cum = S.get<double>(n); double* bdz = S.get<double>(n); double* psi = S.get<double>(n);
   double* dtot = S.get<double>((n + SC_CHUNK - 1) / SC_CHUNK + 1);
