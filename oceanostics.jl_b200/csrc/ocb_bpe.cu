@@ -82,29 +82,34 @@ __global__ void __launch_bounds__(RS_THREADS) rs_histogram(const K* __restrict__
 // CHAINED = false: the tile is blockIdx.x and its global digit offsets come from the scanned per-tile histogram table (`offsets`,
 // digit-major).
 // CHAINED = true ("onesweep"): no histogram pass and no table scan -- `offsets` holds the 256 global digit bases of this pass
-// (from ONE up-front histogram of all digits); the blocks are persistent and take tile numbers from a ticket counter (the next
-// ticket is requested while the current tile is processed), publish their digit counts in `desc[tile][digit]` (count | flag in one
-// word: AGGREGATE = the tile's own count, INCLUSIVE = everything up to and including the tile) and thread d looks back over the
-// preceding tiles' words of digit d until it meets an INCLUSIVE one (decoupled look-back; a tile only ever waits for tiles with
-// smaller tickets, which are running).  A wait is bounded: a stuck look-back sets desc's error word and moves on instead of
-// hanging the device.
-// Latency (profiles/r2_summary.md, K3): the payload of the tile is fetched with cp.async into `ibuf` BEFORE the ranking rounds (it
-// used to be loaded where it was needed: 44 % of the kernel's stall samples), and the look-back runs after the keys have been
-// staged, i.e. as late as its result is needed, when the predecessors have had time to publish their inclusive words.
-// Two-level chained scan.  Tiles form groups of RS_G consecutive tickets.  Every tile publishes its digit counts agg[tile][256];
-// the exclusive prefix of tile t = (g, i) is GX[g] + the counts of the i tiles before it in its group, where GX[g] = the counts of
-// all tiles of groups < g.  The last tile of a group publishes the group total GT[g], the first one GX[g]; a tile that needs
-// GX[g] takes the nearest published GX[g-k] plus GT[g-1] .. GT[g-k].  One poll of the flags (lanes 0..15: the group's tiles, lanes
-// 16..31: the groups g, g-1, ..) and one batch of independent loads when everything is there: ~25 words per thread and two round
-// trips to L2, where a plain look-back (one level, 32 tiles per poll) read ~64 words per thread in 5 polls -- at 28 tiles per
-// microsecond the inclusive frontier of a one-level chain trails 64 tiles behind (measured; profiles/r2_summary.md, K3).
-// desc layout (32-bit words): aggf[nblocks] flags, the ticket counter, the error word, gtf[ngroups], gxf[ngroups], padding to
-// rs_desc_header(nblocks); then agg[nblocks][256], gt[ngroups][256], gx[ngroups][256], all write-once per pass, so only the header
-// is cleared between passes.
+// (from ONE up-front histogram of all digits); the blocks are persistent, take tile numbers from a ticket counter, publish their
+// digit counts and find their exclusive prefix from the counts of the tiles with smaller tickets (a tile only ever waits for
+// those, and they are running).  A wait is bounded: a stuck look-back sets desc's error word and moves on instead of hanging the
+// device.
+//
+// Two-level chained scan.  Tiles form groups of RS_G consecutive tickets.  Every tile publishes its digit counts agg[tile][256]
+// and adds them to its group's total gt[g][256] (RED.ADD), then bumps the group's counter; the block whose bump completes group g
+// computes GX[g+1] = the counts of all tiles of groups <= g from the nearest published GX[g+1-k] and the totals of the complete
+// groups in between (a decoupled look-back over GROUPS: 1.8 of them per microsecond instead of 28 tiles) and publishes it.  The
+// exclusive prefix of tile t = (g, i) is GX[g] + the counts of the i tiles before it in its group: one poll of 16 flags and one
+// batch of <= 16 independent loads.  A one-level look-back cannot keep up here: at 28 tiles per microsecond its inclusive
+// frontier trails ~64 tiles behind (measured: 64 words per thread and 5 polls per tile).
+//
+// Software pipeline.  What a look-back costs is mostly WAITING: the tiles in flight progress at different speeds, and a tile that
+// asks for its predecessors' counts right after publishing its own waits for the slowest of them (measured: 5 us of a 20 us tile,
+// whatever the look-back's shape).  So the block publishes tile t's counts, keeps the staged tile in shared memory, loads and
+// ranks tile t+1 (~7 us), and only then asks for tile t's prefix and writes it out: everything the prefix needs was published
+// by the other blocks one tile earlier in THEIR loops.  Between the two the registers hold of tile t+1 only the digits (8 bits)
+// and the in-warp ranks (16 bits) of the thread's 16 keys -- 12 registers; the keys are read again (from L2) when they are
+// staged, together with the payload (prefetched into L2 at the start of the tile).
+// desc layout (32-bit words): aggf[nblocks] flags, the ticket counter, the error word, gcount[ngroups], gxf[ngroups], padding to
+// rs_desc_header(nblocks), gt[ngroups][256] -- all of that cleared before every pass (rs_desc_clear words) -- then
+// agg[nblocks][256] and gx[ngroups][256], write-once per pass.
 constexpr int RS_G = 16;    // tiles per group
 constexpr int RS_GK = 8;    // groups looked back over per poll
 __host__ __device__ constexpr size_t rs_groups(int nblocks) { return ((size_t)nblocks + RS_G - 1) / RS_G; }
 __host__ __device__ constexpr size_t rs_desc_header(int nblocks) { return (((size_t)nblocks + 2 + 2 * rs_groups(nblocks) + 63) / 64) * 64; }
+__host__ __device__ constexpr size_t rs_desc_clear(int nblocks) { return rs_desc_header(nblocks) + 256ull * rs_groups(nblocks); }
 constexpr size_t rs_table_words(int nblocks) {                         // also >= the 256 nblocks table of the scan path
   return rs_desc_header(nblocks) + 256ull * ((size_t)nblocks + 2 * rs_groups(nblocks));
 }
@@ -112,225 +117,234 @@ __device__ __forceinline__ void rs_st_release(uint32_t* p, uint32_t v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 // flag poll: a relaxed gpu-scope load (L2).  ld.acquire.gpu compiles to the same load plus CCTL.IVALL -- an invalidation of the
-// whole L1 per poll and warp, measured at +0.5 ms per pass.  The words read after a flag are read with __ldcg (L2, never L1) at
-// addresses / under predicates that depend on the flag's value, so they are issued after the flag has arrived, and the writer
-// orders its words before its flag with a gpu-scope release.
+// whole L1 per poll and warp.  The words read after a flag are read with __ldcg (L2, never L1) at addresses / under predicates
+// that depend on the flag's value, so they are issued after the flag has arrived, and the writer orders its words before its
+// flag with a gpu-scope release.
 __device__ __forceinline__ uint32_t rs_ld_flag(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 template <class K> constexpr size_t rs_scatter_smem() {
-  return sizeof(K) * RS_TILE + sizeof(uint32_t) * (RS_TILE + RS_WARPS * 256 + 256 + 256 + RS_WARPS + 8);
-}
-__device__ __forceinline__ void rs_cp_async16(void* smem, const void* g) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
-}
-__device__ __forceinline__ void rs_cp_async4(void* smem, const void* g) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
+  return sizeof(K) * RS_TILE + sizeof(uint32_t) * (RS_TILE + 2 * RS_WARPS * 256 + 256 + 256 + RS_WARPS + 8);
 }
 template <class K, bool CHAINED = false>
 __global__ void __launch_bounds__(RS_THREADS, 3) rs_scatter(const K* __restrict__ keys_in, const uint32_t* __restrict__ idx_in, K* __restrict__ keys_out,
                                                           uint32_t* __restrict__ idx_out, long long n, int shift,
                                                           const uint32_t* __restrict__ offsets, int nblocks, uint32_t* desc = nullptr, int dbg = 0) {
   extern __shared__ __align__(16) unsigned char rs_smem[];
-  K* stage = reinterpret_cast<K*>(rs_smem);                                     // the tile's keys in digit order
-  uint32_t* ibuf = reinterpret_cast<uint32_t*>(stage + RS_TILE);                // the tile's payload: tile order, then digit order
+  K* stage = reinterpret_cast<K*>(rs_smem);                                     // the staged tile's keys in digit order
+  uint32_t* ibuf = reinterpret_cast<uint32_t*>(stage + RS_TILE);                // the staged tile's payload in digit order
   uint32_t (*wcount)[256] = reinterpret_cast<uint32_t (*)[256]>(ibuf + RS_TILE);  // per-warp running digit counts -> per-warp digit bases
-  uint32_t* gbase = ibuf + RS_TILE + RS_WARPS * 256;   // global position of the tile's first key of each digit, minus its tile position
-  uint32_t* tstart = gbase + 256;                      // tile position of the first key of each digit
-  uint32_t* wtot = tstart + 256;                       // [RS_WARPS] block-scan totals, [RS_WARPS] the tile number
-  // the ranking masks live in the staging buffer, idle until the ranks are known
-  uint32_t (*wmask)[256] = reinterpret_cast<uint32_t (*)[256]>(stage);
+  uint32_t (*wmask)[256] = wcount + RS_WARPS;                                   // the ranking masks
+  uint32_t* gbase = &wmask[RS_WARPS][0];   // global position of the staged tile's first key of each digit, minus its tile position
+  uint32_t* tstart = gbase + 256;          // tile position of the first key of each digit
+  uint32_t* wtot = tstart + 256;           // [RS_WARPS] block-scan totals, [RS_WARPS] the next tile number
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
-  int tile = blockIdx.x;
+  const int d = threadIdx.x;
   const int ngroups = (int)rs_groups(nblocks);
-  uint32_t* const gtf = desc + nblocks + 2;
-  uint32_t* const gxf = gtf + ngroups;
-  uint32_t* const agg = desc + rs_desc_header(nblocks);
-  uint32_t* const gt = agg + (size_t)nblocks * 256;
-  uint32_t* const gx = gt + (size_t)ngroups * 256;
+  uint32_t* const gcount = desc + nblocks + 2;
+  uint32_t* const gxf = gcount + ngroups;
+  uint32_t* const gt = desc + rs_desc_header(nblocks);
+  uint32_t* const agg = gt + (size_t)ngroups * 256;
+  uint32_t* const gx = agg + (size_t)nblocks * 256;
+  const int wl = warp * (RS_ITEMS * 32) + lane;         // tile position of the thread's key of round r: wl + 32 r
+  int tile = blockIdx.x;
   if (CHAINED) {
     if (threadIdx.x == 0) wtot[RS_WARPS] = atomicAdd(desc + nblocks, 1u);
     __syncthreads();
     tile = (int)wtot[RS_WARPS];
   }
-  while (tile < nblocks) {
-    uint32_t next_ticket = 0;
+  int ptile = -1;                   // the staged tile, waiting for its prefix
+  uint32_t prun = 0, pstart = 0;    // its count and tile position of digit d
+  for (;;) {
+    const bool have = tile < nblocks;
     const long long tbase = (long long)tile * RS_TILE;
-    const int ntile = (int)((n - tbase) < (long long)RS_TILE ? (n - tbase) : (long long)RS_TILE);
-    const int wl = warp * (RS_ITEMS * 32) + lane;         // tile position of the thread's key of round r: wl + 32 r
-    for (int d = lane; d < 256; d += 32) { wcount[warp][d] = 0; wmask[warp][d] = 0; }
-    if (idx_in) {                                         // payload -> ibuf, tile order, asynchronously
-      const uint32_t* src = idx_in + tbase;
-      if (ntile == RS_TILE && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    const int ntile = have ? (int)((n - tbase) < (long long)RS_TILE ? (n - tbase) : (long long)RS_TILE) : 0;
+    uint32_t dg[RS_ITEMS / 4], rk[RS_ITEMS / 2];        // the thread's 16 digits (8 bits each) and in-warp ranks (16 bits each)
+    uint32_t run = 0, start = 0, closes = 0;
+    if (have) {
+      for (int q = lane; q < 256; q += 32) { wcount[warp][q] = 0; wmask[warp][q] = 0; }
+      if (idx_in && threadIdx.x * 32 < ntile) asm volatile("prefetch.global.L2 [%0];" ::"l"(idx_in + tbase + threadIdx.x * 32));
+      {
+        K key[RS_ITEMS];
 #pragma unroll
-        for (int q = 0; q < RS_ITEMS / 4; ++q) rs_cp_async16(ibuf + 4 * (threadIdx.x + RS_THREADS * q), src + 4 * (threadIdx.x + RS_THREADS * q));
-      } else {
+        for (int r = 0; r < RS_ITEMS; ++r) key[r] = (wl + 32 * r) < ntile ? __ldg(keys_in + tbase + wl + 32 * r) : (K)~(K)0;
 #pragma unroll
-        for (int r = 0; r < RS_ITEMS; ++r) { const int e = r * RS_THREADS + threadIdx.x; if (e < ntile) rs_cp_async4(ibuf + e, src + e); }
+        for (int q = 0; q < RS_ITEMS / 4; ++q) {
+          dg[q] = 0;
+#pragma unroll
+          for (int b = 0; b < 4; ++b) dg[q] |= ((uint32_t)(key[4 * q + b] >> shift) & 255u) << (8 * b);
+        }
       }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    }
-    K key[RS_ITEMS];
-    uint32_t rank[RS_ITEMS];
-    // all of the thread's keys first (16 independent loads in flight), then the ranking rounds
-#pragma unroll
-    for (int r = 0; r < RS_ITEMS; ++r) key[r] = (wl + 32 * r) < ntile ? __ldg(keys_in + tbase + wl + 32 * r) : (K)~(K)0;
-    __syncwarp();
-    // Ranking: lanes of a round that hold the same digit must learn of each other (their ranks follow the lane order: the sort
-    // is stable).  MATCH.ANY does that in hardware by looping over the distinct values of the warp -- ~30 of them with 8-bit
-    // digits, which made these 16 rounds the whole cost of a pass (issue slots 12 % busy, profiles/r1_summary.md).  Instead every
-    // lane ORs its bit into a per-warp, per-digit mask word in shared memory and reads the word back: one shared atomic and two
-    // loads per round.
-    if (dbg & 4) {
+      __syncwarp();
+      // Ranking: lanes of a round that hold the same digit must learn of each other (their ranks follow the lane order: the
+      // sort is stable).  MATCH.ANY does that in hardware by looping over the distinct values of the warp -- ~30 of them with
+      // 8-bit digits (issue slots 12 % busy, profiles/r1_summary.md).  Instead every lane ORs its bit into a per-warp, per-digit
+      // mask word in shared memory and reads the word back: one shared atomic and two loads per round.
 #pragma unroll
       for (int r = 0; r < RS_ITEMS; ++r) {
         const bool ok = (wl + 32 * r) < ntile;
-        const uint32_t dig = ok ? ((uint32_t)(key[r] >> shift) & 255u) : 0u;
-        unsigned peers = __ballot_sync(0xffffffffu, ok);
+        const uint32_t dig = (dg[r >> 2] >> (8 * (r & 3))) & 255u;
+        uint32_t rank;
+        if (dbg & 4) {
+          unsigned peers = __ballot_sync(0xffffffffu, ok);
 #pragma unroll
-        for (int b = 0; b < 8; ++b) {
-          const bool bit = (dig >> b) & 1u;
-          const unsigned m = __ballot_sync(0xffffffffu, bit);
-          peers &= bit ? m : ~m;
-        }
-        if (!ok) peers = 0u;
-        volatile uint32_t* cp = &wcount[warp][dig];
-        const uint32_t prev = ok ? *cp : 0u;
-        __syncwarp();
-        if (ok && (peers & lt) == 0) *cp = prev + __popc(peers);
-        __syncwarp();
-        rank[r] = prev + __popc(peers & lt);
-      }
-    } else {
-#pragma unroll
-    for (int r = 0; r < RS_ITEMS; ++r) {
-      const bool ok = (wl + 32 * r) < ntile;
-      const uint32_t dig = ok ? ((uint32_t)(key[r] >> shift) & 255u) : 0u;
-      volatile uint32_t* mp = &wmask[warp][dig];
-      volatile uint32_t* cp = &wcount[warp][dig];
-      if (ok) atomicOr(&wmask[warp][dig], 1u << lane);
-      __syncwarp();
-      const unsigned peers = ok ? *mp : 0u;
-      const uint32_t prev = ok ? *cp : 0u;
-      __syncwarp();
-      if (ok && (peers & lt) == 0) { *cp = prev + __popc(peers); *mp = 0u; }   // the lowest lane of each digit group updates and clears
-      __syncwarp();
-      rank[r] = prev + __popc(peers & lt);
-    }
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-    // thread d: exclusive scan across warps for digit d, then (block scan) the tile position where digit d starts
-    const int d = threadIdx.x;
-    uint32_t run = 0;
-#pragma unroll
-    for (int w = 0; w < RS_WARPS; ++w) { const uint32_t c = wcount[w][d]; wcount[w][d] = run; run += c; }
-    if (CHAINED) agg[(size_t)tile * 256 + d] = run;
-    uint32_t inc = run;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
-    if (lane == 31) wtot[warp] = inc;
-    __syncthreads();
-    uint32_t before = 0;
-#pragma unroll
-    for (int w = 0; w < RS_WARPS; ++w) if (w < warp) before += wtot[w];
-    const uint32_t start = before + inc - run;
-    tstart[d] = start;
-    if (CHAINED && threadIdx.x == 0) rs_st_release(desc + tile, 1u);   // after the scan's barrier: all 256 words are written
-    if (!CHAINED) gbase[d] = offsets[(size_t)d * nblocks + tile] - start;
-    __syncthreads();
-    // keys: into digit order in shared memory; the thread's payload: out of the tile-order buffer into registers
-#pragma unroll
-    for (int r = 0; r < RS_ITEMS; ++r) {
-      if ((wl + 32 * r) < ntile) {
-        const uint32_t dig = (uint32_t)(key[r] >> shift) & 255u;
-        rank[r] = tstart[dig] + wcount[warp][dig] + rank[r];                    // tile position
-        stage[rank[r]] = key[r];
-      }
-    }
-    const int grp = tile / RS_G, gi = tile % RS_G;
-    if (CHAINED) {
-      uint32_t pin = 0, gxs = 0;                           // counts of the group's earlier tiles; of all earlier groups
-      if (!(dbg & 2)) {
-        bool need_in = gi > 0, need_g = grp > 0;
-        unsigned spins = 0;
-        while (need_in || need_g) {
-          uint32_t fa = 0, fx = 0, ft = 0;
-          if (lane < 16) {
-            if (need_in && lane < gi) fa = rs_ld_flag(desc + tile - 1 - lane);
-          } else if (need_g) {
-            const int k = lane - 16;
-            if (k < RS_GK && grp - k >= 0) fx = rs_ld_flag(gxf + grp - k);
-            if (k < RS_GK && grp - 1 - k >= 0) ft = rs_ld_flag(gtf + grp - 1 - k);
+          for (int b = 0; b < 8; ++b) {
+            const bool bit = (dig >> b) & 1u;
+            const unsigned m = __ballot_sync(0xffffffffu, bit);
+            peers &= bit ? m : ~m;
           }
+          if (!ok) peers = 0u;
+          volatile uint32_t* cp = &wcount[warp][dig];
+          const uint32_t prev = ok ? *cp : 0u;
           __syncwarp();
-          const unsigned am = __ballot_sync(0xffffffffu, fa != 0u) & 0xffffu;
-          const unsigned xm = __ballot_sync(0xffffffffu, fx != 0u) >> 16, tm = __ballot_sync(0xffffffffu, ft != 0u) >> 16;
-          const bool go_in = need_in && am == ((1u << gi) - 1u);
-          const int kx = xm ? __ffs(xm) - 1 : 99;              // nearest group whose exclusive prefix is published
-          const bool go_g = need_g && xm && (tm & ((1u << kx) - 1u)) == ((1u << kx) - 1u);
-          uint32_t va[RS_G - 1], vg[RS_GK];
-          if (go_in) {
+          if (ok && (peers & lt) == 0) *cp = prev + __popc(peers);
+          __syncwarp();
+          rank = prev + __popc(peers & lt);
+        } else {
+          volatile uint32_t* mp = &wmask[warp][dig];
+          volatile uint32_t* cp = &wcount[warp][dig];
+          if (ok) atomicOr(&wmask[warp][dig], 1u << lane);
+          __syncwarp();
+          const unsigned peers = ok ? *mp : 0u;
+          const uint32_t prev = ok ? *cp : 0u;
+          __syncwarp();
+          if (ok && (peers & lt) == 0) { *cp = prev + __popc(peers); *mp = 0u; }   // the lowest lane of each digit group updates and clears
+          __syncwarp();
+          rank = prev + __popc(peers & lt);
+        }
+        if (r & 1) rk[r >> 1] |= rank << 16; else rk[r >> 1] = rank;
+      }
+    }
+    __syncthreads();
+    if (have) {
+      // thread d: exclusive scan across warps for digit d, then (block scan) the tile position where digit d starts
 #pragma unroll
-            for (int q = 0; q < RS_G - 1; ++q) va[q] = q < gi ? __ldcg(agg + (size_t)(tile - 1 - q) * 256 + d) : 0u;
-          }
-          if (go_g) {
-            vg[0] = __ldcg(gx + (size_t)(grp - kx) * 256 + d);
+      for (int w = 0; w < RS_WARPS; ++w) { const uint32_t c = wcount[w][d]; wcount[w][d] = run; run += c; }
+      if (CHAINED) {
+        agg[(size_t)tile * 256 + d] = run;
+        if (run) atomicAdd(gt + (size_t)(tile / RS_G) * 256 + d, run);
+      }
+      uint32_t inc = run;
 #pragma unroll
-            for (int q = 1; q < RS_GK; ++q) vg[q] = q <= kx ? __ldcg(gt + (size_t)(grp - q) * 256 + d) : 0u;
-          }
-          if (go_in) {
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+      if (lane == 31) wtot[warp] = inc;
+      __syncthreads();
+      uint32_t before = 0;
 #pragma unroll
-            for (int q = 0; q < RS_G - 1; ++q) pin += va[q];
-            need_in = false;
-          }
-          if (go_g) {
-#pragma unroll
-            for (int q = 0; q < RS_GK; ++q) gxs += vg[q];
-            need_g = false;
-          }
-          if (!go_in && !go_g) {
+      for (int w = 0; w < RS_WARPS; ++w) if (w < warp) before += wtot[w];
+      start = before + inc - run;
+      tstart[d] = start;
+      if (CHAINED && threadIdx.x == 0) {                 // after the scan's barrier: all 256 words are written / added
+        rs_st_release(desc + tile, 1u);
+        closes = atomicAdd(gcount + tile / RS_G, 1u);    // (the release above ordered the block's RED.ADDs before this one)
+      }
+    }
+    // ---- the staged tile: its prefix, then out in runs
+    if (ptile >= 0) {
+      const int pgrp = ptile / RS_G, gi = ptile % RS_G;
+      const long long pbase = (long long)ptile * RS_TILE;
+      const int pn = (int)((n - pbase) < (long long)RS_TILE ? (n - pbase) : (long long)RS_TILE);
+      if (!CHAINED) {
+        gbase[d] = offsets[(size_t)d * nblocks + ptile] - pstart;
+      } else {
+        uint32_t pin = 0, gxs = 0;                           // counts of the group's earlier tiles; of all earlier groups
+        if (!(dbg & 2) && (gi > 0 || pgrp > 0)) {
+          const unsigned want = ((1u << gi) - 1u) | (pgrp > 0 ? 1u << 16 : 0u);
+          unsigned spins = 0;
+          for (;;) {
+            uint32_t f = 0;
+            if (lane < gi) f = rs_ld_flag(desc + ptile - 1 - lane);
+            else if (lane == 16 && pgrp > 0) f = rs_ld_flag(gxf + pgrp);
+            __syncwarp();
+            if ((__ballot_sync(0xffffffffu, f != 0u) & want) == want) break;
             if (++spins > (1u << 20)) { if (lane == 0) atomicExch(desc + nblocks + 1, 1u); break; }
             __nanosleep(40);
-          } else spins = 0;
+          }
+          uint32_t va[RS_G - 1];
+#pragma unroll
+          for (int q = 0; q < RS_G - 1; ++q) va[q] = q < gi ? __ldcg(agg + (size_t)(ptile - 1 - q) * 256 + d) : 0u;
+          if (pgrp > 0) gxs = __ldcg(gx + (size_t)pgrp * 256 + d);
+#pragma unroll
+          for (int q = 0; q < RS_G - 1; ++q) pin += va[q];
         }
-        if (gi == 0) gx[(size_t)grp * 256 + d] = gxs;
-        if (gi == RS_G - 1) gt[(size_t)grp * 256 + d] = pin + run;
+        gbase[d] = offsets[d] + gxs + pin - pstart;
       }
-      gbase[d] = offsets[d] + gxs + pin - start;
-    }
-    uint32_t pay[RS_ITEMS];
+      __syncthreads();
 #pragma unroll
-    for (int r = 0; r < RS_ITEMS; ++r) pay[r] = idx_in ? ibuf[wl + 32 * r] : (uint32_t)(tbase + wl + 32 * r);   // no payload array: the key's position
-    __syncthreads();
-    if (CHAINED && threadIdx.x == 0) {                     // after the barrier: all 256 words of the rows are written
-      if (gi == 0) rs_st_release(gxf + grp, 1u);
-      if (gi == RS_G - 1) rs_st_release(gtf + grp, 1u);
+      for (int r = 0; r < RS_ITEMS; ++r) {
+        const int e = r * RS_THREADS + threadIdx.x;
+        if (e < pn) {
+          const K k = stage[e];
+          const uint32_t pos = gbase[(uint32_t)(k >> shift) & 255u] + (uint32_t)e;
+          keys_out[pos] = k;
+          idx_out[pos] = ibuf[e];
+        }
+      }
     }
+    if (!have) break;
+    if (CHAINED && threadIdx.x == 0) wtot[RS_WARPS + 1] = closes;
+    __syncthreads();                                      // the staging buffers are free; tstart is complete
+    if (CHAINED && wtot[RS_WARPS + 1] == RS_G - 1 && tile / RS_G + 1 < ngroups && !(dbg & 2)) {
+      // this block's tile completed its group: GX[G1] of the next group = GX[G1-k] + GT[G1-1] + .. + GT[G1-k], k >= 1 the
+      // nearest group whose GX is published (GX[0] = 0 is not stored) with every group in between complete
+      const int G1 = tile / RS_G + 1;
+      uint32_t sum = 0;
+      unsigned spins = 0;
+      for (;;) {
+        const int k = lane + 1, gk = G1 - k;
+        uint32_t fx = 0, fc = 0;
+        if (k <= RS_GK && gk >= 0) {
+          fx = gk == 0 ? 1u : rs_ld_flag(gxf + gk);
+          fc = rs_ld_flag(gcount + gk) == (uint32_t)RS_G;
+        }
+        __syncwarp();
+        const unsigned xm = __ballot_sync(0xffffffffu, fx != 0u), cm = __ballot_sync(0xffffffffu, fc != 0u);
+        const int kx = xm ? __ffs(xm) : 0;                 // k of the nearest published prefix
+        if (kx && (cm & ((1u << kx) - 1u)) == ((1u << kx) - 1u)) {
+          uint32_t vg[RS_GK + 1];
+          vg[0] = G1 - kx > 0 ? __ldcg(gx + (size_t)(G1 - kx) * 256 + d) : 0u;
 #pragma unroll
-    for (int r = 0; r < RS_ITEMS; ++r) if ((wl + 32 * r) < ntile) ibuf[rank[r]] = pay[r];
-    __syncthreads();
-    // the next tile's number: asked for as late as the write-out can still hide the round trip -- tickets are the look-back
-    // order, and a ticket held long before its tile starts makes every successor wait for it
+          for (int q = 1; q <= RS_GK; ++q) vg[q] = q <= kx ? __ldcg(gt + (size_t)(G1 - q) * 256 + d) : 0u;
+#pragma unroll
+          for (int q = 0; q <= RS_GK; ++q) sum += vg[q];
+          break;
+        }
+        if (++spins > (1u << 20)) { if (lane == 0) atomicExch(desc + nblocks + 1, 1u); break; }
+        __nanosleep(40);
+      }
+      gx[(size_t)G1 * 256 + d] = sum;
+      __syncthreads();
+      if (threadIdx.x == 0) rs_st_release(gxf + G1, 1u);
+    }
+    // the next tile's number: tickets are the look-back order, so it is asked for just before the tile starts (the staging
+    // below hides the round trip)
+    uint32_t next_ticket = (uint32_t)nblocks;
     if (CHAINED && threadIdx.x == 0) next_ticket = atomicAdd(desc + nblocks, 1u);
-    // out in runs: key and payload of tile position e
+    // keys (again, from L2) and payload into digit order in shared memory
+    {
+      K key[RS_ITEMS];
+      uint32_t pay[RS_ITEMS];
 #pragma unroll
-    for (int r = 0; r < RS_ITEMS; ++r) {
-      const int e = r * RS_THREADS + threadIdx.x;
-      if (e < ntile) {
-        const K k = stage[e];
-        uint32_t pos = gbase[(uint32_t)(k >> shift) & 255u] + (uint32_t)e;
-        if (dbg & 1) pos = (uint32_t)tbase + (uint32_t)e;
-        keys_out[pos] = k;
-        idx_out[pos] = ibuf[e];
+      for (int r = 0; r < RS_ITEMS; ++r) key[r] = (wl + 32 * r) < ntile ? __ldcg(keys_in + tbase + wl + 32 * r) : (K)0;
+#pragma unroll
+      for (int r = 0; r < RS_ITEMS; ++r)
+        pay[r] = idx_in ? ((wl + 32 * r) < ntile ? __ldcg(idx_in + tbase + wl + 32 * r) : 0u) : (uint32_t)(tbase + wl + 32 * r);   // no payload array: the key's position
+#pragma unroll
+      for (int r = 0; r < RS_ITEMS; ++r) {
+        if ((wl + 32 * r) < ntile) {
+          const uint32_t dig = (dg[r >> 2] >> (8 * (r & 3))) & 255u;
+          const uint32_t pos = tstart[dig] + wcount[warp][dig] + ((rk[r >> 1] >> (16 * (r & 1))) & 0xffffu);   // tile position
+          stage[pos] = key[r];
+          ibuf[pos] = pay[r];
+        }
       }
     }
-    if (!CHAINED) break;
+    ptile = tile; prun = run; pstart = start;
     if (threadIdx.x == 0) wtot[RS_WARPS] = next_ticket;
-    __syncthreads();                                       // also: the staging buffers are free again
+    __syncthreads();
     tile = (int)wtot[RS_WARPS];
   }
 }
@@ -542,7 +556,7 @@ int radix_sort_pairs(K* keys_a, uint32_t* idx_a, K* keys_b, uint32_t* idx_b, lon
       rs_histogram_all<K><<<hb, RS_THREADS, 0, st>>>(kin, n, hist);
       rs_digit_bases<<<NP, 256, 0, st>>>(hist);
       for (int p = 0; p < NP; ++p) {
-        OCB_CUDA(cudaMemsetAsync(table, 0, sizeof(uint32_t) * rs_desc_header(nblocks), st));      // flags, ticket, error word
+        OCB_CUDA(cudaMemsetAsync(table, 0, sizeof(uint32_t) * rs_desc_clear(nblocks), st));      // flags, ticket, error word, group totals
         { const int rc = rs_launch_scatter<K, true>(kin, iin, kout, iout, n, 8 * p, hist + p * 256, nblocks, table, st); if (rc != OCB_OK) return rc; }
         K* tk = kin; kin = kout; kout = tk;
         uint32_t* ti = iin; iin = iout; iout = ti;
