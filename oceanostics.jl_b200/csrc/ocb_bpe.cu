@@ -48,16 +48,74 @@ __device__ __forceinline__ float from_key(uint32_t k) {
   return __uint_as_float(u);
 }
 
-// keys from a flat float array, payload = 0-based index
-template <class K>
-__global__ void rs_make_keys(const typename KeyTraits<K>::F* __restrict__ v, K* __restrict__ keys, uint32_t* __restrict__ idx, long long n) {
-  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (t < n) { keys[t] = to_key(v[t]); idx[t] = (uint32_t)t; }
-}
 template <class K>
 __global__ void rs_unmake_keys(const K* __restrict__ keys, typename KeyTraits<K>::F* __restrict__ v, long long n) {
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t < n) v[t] = from_key(keys[t]);
+}
+
+// Where a pass reads its keys from.  The first pass of a sort reads the caller's data and makes the keys on the fly (and its
+// payload is the key's position), so no make-keys pass writes and re-reads 12 B/key.  A thread walks its keys with a cursor
+// (`at(t)`, then `advance(step)` between reads); `first` is the read for the digits, `again` the second read of the same key
+// when the tile is staged (from L2).
+template <class K> struct PtrKeys {
+  const K* p;
+  struct Cursor {
+    const K* q;
+    __device__ __forceinline__ K first() const { return __ldg(q); }
+    __device__ __forceinline__ K again() const { return __ldcg(q); }
+    __device__ __forceinline__ void advance(uint32_t step) { q += step; }
+  };
+  __device__ __forceinline__ Cursor at(long long t) const { return Cursor{p + t}; }
+};
+template <class K> struct FloatKeys {           // a flat floating-point array
+  const typename KeyTraits<K>::F* p;
+  struct Cursor {
+    const typename KeyTraits<K>::F* q;
+    __device__ __forceinline__ K first() const { return to_key(__ldg(q)); }
+    __device__ __forceinline__ K again() const { return to_key(__ldcg(q)); }
+    __device__ __forceinline__ void advance(uint32_t step) { q += step; }
+  };
+  __device__ __forceinline__ Cursor at(long long t) const { return Cursor{p + t}; }
+};
+// unsigned division by a run-time invariant (Granlund & Montgomery): q = (t1 + ((n - t1) >> sh1)) >> sh2 with t1 = mulhi(m, n)
+struct FastDiv {
+  uint32_t d, m, sh1, sh2;
+  FastDiv() : d(1), m(1), sh1(0), sh2(0) {}
+  explicit FastDiv(uint32_t div) : d(div) {
+    uint32_t s = 0;
+    while ((1ull << s) < div) ++s;
+    m = (uint32_t)(((1ull << 32) * ((1ull << s) - div)) / div + 1);
+    sh1 = s < 1 ? s : 1; sh2 = s - sh1;
+  }
+  __device__ __forceinline__ uint32_t div(uint32_t n) const { const uint32_t t1 = __umulhi(m, n); return (t1 + ((n - t1) >> sh1)) >> sh2; }
+};
+template <class T, class K> struct FieldKeys {  // the interior of a field (< 2^32 cells): b1 pre-offset to index (1,1,1) -> element 0
+  const T* b1; long long s0, s1, s2; FastDiv dx, dy;
+  struct Cursor {                               // (i, j) of the cell and its address; a step carries into j and k
+    const T* q; uint32_t i, j, Nx, Ny; long long s0, back_x, back_y;
+    __device__ __forceinline__ K first() const { return to_key(__ldg(q)); }
+    __device__ __forceinline__ K again() const { return to_key(__ldcg(q)); }
+    __device__ __forceinline__ void advance(uint32_t step) {
+      i += step; q += step * s0;
+      while (i >= Nx) {
+        i -= Nx; q += back_x; ++j;              // back_x = s1 - Nx s0: to the start of the next row
+        if (j == Ny) { j = 0; q += back_y; }    // back_y = s2 - Ny s1: to the start of the next plane
+      }
+    }
+  };
+  __device__ __forceinline__ Cursor at(long long t) const {
+    const uint32_t tt = (uint32_t)t, q = dx.div(tt), i = tt - q * dx.d, k = dy.div(q), j = q - k * dy.d;
+    return Cursor{b1 + (i * s0 + j * s1 + k * s2), i, j, dx.d, dy.d, s0, s1 - (long long)dx.d * s0, s2 - (long long)dy.d * s1};
+  }
+};
+// the bit pattern of from_key(k): what the last pass of a sort stores when the caller wants values, not keys
+__device__ __forceinline__ uint64_t unkey_bits(uint64_t k) { return (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k; }
+__device__ __forceinline__ uint32_t unkey_bits(uint32_t k) { return (k >> 31) ? (k & 0x7fffffffu) : ~k; }
+template <class K, class In>
+__global__ void rs_materialize_keys(const In in, K* __restrict__ keys, uint32_t* __restrict__ idx, long long n) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t < n) { keys[t] = in.at(t).first(); idx[t] = (uint32_t)t; }
 }
 
 // per-tile digit histogram, written digit-major: table[digit * nblocks + block]
@@ -126,20 +184,19 @@ __device__ __forceinline__ uint32_t rs_ld_flag(const uint32_t* p) {
   return v;
 }
 template <class K> constexpr size_t rs_scatter_smem() {
-  return sizeof(K) * RS_TILE + sizeof(uint32_t) * (RS_TILE + 2 * RS_WARPS * 256 + 256 + 256 + RS_WARPS + 8);
+  return sizeof(K) * RS_TILE + sizeof(uint32_t) * (RS_TILE + 2 * RS_WARPS * 256 + 256 + RS_WARPS + 8);
 }
-template <class K, bool CHAINED = false>
-__global__ void __launch_bounds__(RS_THREADS, 3) rs_scatter(const K* __restrict__ keys_in, const uint32_t* __restrict__ idx_in, K* __restrict__ keys_out,
+template <class K, bool CHAINED = false, class In = PtrKeys<K>, bool UNMAKE = false>
+__global__ void __launch_bounds__(RS_THREADS, 3) rs_scatter(const In keys_in, const uint32_t* __restrict__ idx_in, K* __restrict__ keys_out,
                                                           uint32_t* __restrict__ idx_out, long long n, int shift,
-                                                          const uint32_t* __restrict__ offsets, int nblocks, uint32_t* desc = nullptr, int dbg = 0) {
+                                                          const uint32_t* __restrict__ offsets, int nblocks, uint32_t* desc = nullptr) {
   extern __shared__ __align__(16) unsigned char rs_smem[];
   K* stage = reinterpret_cast<K*>(rs_smem);                                     // the staged tile's keys in digit order
   uint32_t* ibuf = reinterpret_cast<uint32_t*>(stage + RS_TILE);                // the staged tile's payload in digit order
-  uint32_t (*wcount)[256] = reinterpret_cast<uint32_t (*)[256]>(ibuf + RS_TILE);  // per-warp running digit counts -> per-warp digit bases
-  uint32_t (*wmask)[256] = wcount + RS_WARPS;                                   // the ranking masks
-  uint32_t* gbase = &wmask[RS_WARPS][0];   // global position of the staged tile's first key of each digit, minus its tile position
-  uint32_t* tstart = gbase + 256;          // tile position of the first key of each digit
-  uint32_t* wtot = tstart + 256;           // [RS_WARPS] block-scan totals, [RS_WARPS] the next tile number
+  // per warp and digit: ranking mask | running count << 32, then (count half) the tile position of the warp's first key of the digit
+  unsigned long long (*wmc)[256] = reinterpret_cast<unsigned long long (*)[256]>(ibuf + RS_TILE);
+  uint32_t* gbase = reinterpret_cast<uint32_t*>(&wmc[RS_WARPS][0]);   // global position of the staged tile's first key of each digit, minus its tile position
+  uint32_t* wtot = gbase + 256;            // [RS_WARPS] block-scan totals, [RS_WARPS] the next tile number
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
   const int d = threadIdx.x;
@@ -165,12 +222,13 @@ __global__ void __launch_bounds__(RS_THREADS, 3) rs_scatter(const K* __restrict_
     uint32_t dg[RS_ITEMS / 4], rk[RS_ITEMS / 2];        // the thread's 16 digits (8 bits each) and in-warp ranks (16 bits each)
     uint32_t run = 0, start = 0, closes = 0;
     if (have) {
-      for (int q = lane; q < 256; q += 32) { wcount[warp][q] = 0; wmask[warp][q] = 0; }
+      for (int q = lane; q < 256; q += 32) wmc[warp][q] = 0ull;
       if (idx_in && threadIdx.x * 32 < ntile) asm volatile("prefetch.global.L2 [%0];" ::"l"(idx_in + tbase + threadIdx.x * 32));
       {
         K key[RS_ITEMS];
+        auto cur = keys_in.at(tbase + wl);
 #pragma unroll
-        for (int r = 0; r < RS_ITEMS; ++r) key[r] = (wl + 32 * r) < ntile ? __ldg(keys_in + tbase + wl + 32 * r) : (K)~(K)0;
+        for (int r = 0; r < RS_ITEMS; ++r) { key[r] = (wl + 32 * r) < ntile ? cur.first() : (K)~(K)0; cur.advance(32); }
 #pragma unroll
         for (int q = 0; q < RS_ITEMS / 4; ++q) {
           dg[q] = 0;
@@ -187,42 +245,27 @@ __global__ void __launch_bounds__(RS_THREADS, 3) rs_scatter(const K* __restrict_
       for (int r = 0; r < RS_ITEMS; ++r) {
         const bool ok = (wl + 32 * r) < ntile;
         const uint32_t dig = (dg[r >> 2] >> (8 * (r & 3))) & 255u;
-        uint32_t rank;
-        if (dbg & 4) {
-          unsigned peers = __ballot_sync(0xffffffffu, ok);
-#pragma unroll
-          for (int b = 0; b < 8; ++b) {
-            const bool bit = (dig >> b) & 1u;
-            const unsigned m = __ballot_sync(0xffffffffu, bit);
-            peers &= bit ? m : ~m;
-          }
-          if (!ok) peers = 0u;
-          volatile uint32_t* cp = &wcount[warp][dig];
-          const uint32_t prev = ok ? *cp : 0u;
-          __syncwarp();
-          if (ok && (peers & lt) == 0) *cp = prev + __popc(peers);
-          __syncwarp();
-          rank = prev + __popc(peers & lt);
-        } else {
-          volatile uint32_t* mp = &wmask[warp][dig];
-          volatile uint32_t* cp = &wcount[warp][dig];
-          if (ok) atomicOr(&wmask[warp][dig], 1u << lane);
-          __syncwarp();
-          const unsigned peers = ok ? *mp : 0u;
-          const uint32_t prev = ok ? *cp : 0u;
-          __syncwarp();
-          if (ok && (peers & lt) == 0) { *cp = prev + __popc(peers); *mp = 0u; }   // the lowest lane of each digit group updates and clears
-          __syncwarp();
-          rank = prev + __popc(peers & lt);
-        }
+        // mask (low word) and running count (high word) of the warp's digit share one 64-bit word: one load, one store
+        volatile unsigned long long* mc = &wmc[warp][dig];
+        if (ok) atomicOr(reinterpret_cast<uint32_t*>(&wmc[warp][dig]), 1u << lane);
+        __syncwarp();
+        const unsigned long long v = ok ? *mc : 0ull;
+        const unsigned peers = (unsigned)v;
+        const uint32_t prev = (uint32_t)(v >> 32);
+        __syncwarp();
+        if (ok && (peers & lt) == 0) *mc = (unsigned long long)(prev + __popc(peers)) << 32;   // the lowest lane of each digit group updates and clears
+        __syncwarp();
+        const uint32_t rank = prev + __popc(peers & lt);
         if (r & 1) rk[r >> 1] |= rank << 16; else rk[r >> 1] = rank;
       }
     }
     __syncthreads();
     if (have) {
-      // thread d: exclusive scan across warps for digit d, then (block scan) the tile position where digit d starts
+      // thread d: the warps' counts of digit d, (block scan) the tile position where digit d starts, and back into wmc's count halves the
+      // tile position where warp w's keys of digit d start
+      uint32_t wc[RS_WARPS];
 #pragma unroll
-      for (int w = 0; w < RS_WARPS; ++w) { const uint32_t c = wcount[w][d]; wcount[w][d] = run; run += c; }
+      for (int w = 0; w < RS_WARPS; ++w) { wc[w] = (uint32_t)(wmc[w][d] >> 32); run += wc[w]; }
       if (CHAINED) {
         agg[(size_t)tile * 256 + d] = run;
         if (run) atomicAdd(gt + (size_t)(tile / RS_G) * 256 + d, run);
@@ -236,7 +279,11 @@ __global__ void __launch_bounds__(RS_THREADS, 3) rs_scatter(const K* __restrict_
 #pragma unroll
       for (int w = 0; w < RS_WARPS; ++w) if (w < warp) before += wtot[w];
       start = before + inc - run;
-      tstart[d] = start;
+      {
+        uint32_t at = start;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) { reinterpret_cast<uint32_t*>(&wmc[w][d])[1] = at; at += wc[w]; }
+      }
       if (CHAINED && threadIdx.x == 0) {                 // after the scan's barrier: all 256 words are written / added
         rs_st_release(desc + tile, 1u);
         closes = atomicAdd(gcount + tile / RS_G, 1u);    // (the release above ordered the block's RED.ADDs before this one)
@@ -251,7 +298,7 @@ __global__ void __launch_bounds__(RS_THREADS, 3) rs_scatter(const K* __restrict_
         gbase[d] = offsets[(size_t)d * nblocks + ptile] - pstart;
       } else {
         uint32_t pin = 0, gxs = 0;                           // counts of the group's earlier tiles; of all earlier groups
-        if (!(dbg & 2) && (gi > 0 || pgrp > 0)) {
+        if (gi > 0 || pgrp > 0) {
           const unsigned want = ((1u << gi) - 1u) | (pgrp > 0 ? 1u << 16 : 0u);
           unsigned spins = 0;
           for (;;) {
@@ -279,15 +326,15 @@ __global__ void __launch_bounds__(RS_THREADS, 3) rs_scatter(const K* __restrict_
         if (e < pn) {
           const K k = stage[e];
           const uint32_t pos = gbase[(uint32_t)(k >> shift) & 255u] + (uint32_t)e;
-          keys_out[pos] = k;
+          keys_out[pos] = UNMAKE ? unkey_bits(k) : k;
           idx_out[pos] = ibuf[e];
         }
       }
     }
     if (!have) break;
     if (CHAINED && threadIdx.x == 0) wtot[RS_WARPS + 1] = closes;
-    __syncthreads();                                      // the staging buffers are free; tstart is complete
-    if (CHAINED && wtot[RS_WARPS + 1] == RS_G - 1 && tile / RS_G + 1 < ngroups && !(dbg & 2)) {
+    __syncthreads();                                      // the staging buffers are free; the warps' digit bases are complete
+    if (CHAINED && wtot[RS_WARPS + 1] == RS_G - 1 && tile / RS_G + 1 < ngroups) {
       // this block's tile completed its group: GX[G1] of the next group = GX[G1-k] + GT[G1-1] + .. + GT[G1-k], k >= 1 the
       // nearest group whose GX is published (GX[0] = 0 is not stored) with every group in between complete
       const int G1 = tile / RS_G + 1;
@@ -327,8 +374,9 @@ __global__ void __launch_bounds__(RS_THREADS, 3) rs_scatter(const K* __restrict_
     {
       K key[RS_ITEMS];
       uint32_t pay[RS_ITEMS];
+      auto cur = keys_in.at(tbase + wl);
 #pragma unroll
-      for (int r = 0; r < RS_ITEMS; ++r) key[r] = (wl + 32 * r) < ntile ? __ldcg(keys_in + tbase + wl + 32 * r) : (K)0;
+      for (int r = 0; r < RS_ITEMS; ++r) { key[r] = (wl + 32 * r) < ntile ? cur.again() : (K)0; cur.advance(32); }
 #pragma unroll
       for (int r = 0; r < RS_ITEMS; ++r)
         pay[r] = idx_in ? ((wl + 32 * r) < ntile ? __ldcg(idx_in + tbase + wl + 32 * r) : 0u) : (uint32_t)(tbase + wl + 32 * r);   // no payload array: the key's position
@@ -336,7 +384,7 @@ __global__ void __launch_bounds__(RS_THREADS, 3) rs_scatter(const K* __restrict_
       for (int r = 0; r < RS_ITEMS; ++r) {
         if ((wl + 32 * r) < ntile) {
           const uint32_t dig = (dg[r >> 2] >> (8 * (r & 3))) & 255u;
-          const uint32_t pos = tstart[dig] + wcount[warp][dig] + ((rk[r >> 1] >> (16 * (r & 1))) & 0xffffu);   // tile position
+          const uint32_t pos = reinterpret_cast<const uint32_t*>(&wmc[warp][dig])[1] + ((rk[r >> 1] >> (16 * (r & 1))) & 0xffffu);   // tile position
           stage[pos] = key[r];
           ibuf[pos] = pay[r];
         }
@@ -348,44 +396,53 @@ __global__ void __launch_bounds__(RS_THREADS, 3) rs_scatter(const K* __restrict_
     tile = (int)wtot[RS_WARPS];
   }
 }
-template <class K, bool CHAINED>
-int rs_launch_scatter(const K* kin, const uint32_t* iin, K* kout, uint32_t* iout, long long n, int shift, const uint32_t* offsets, int nblocks,
+template <class K, bool CHAINED, class In = PtrKeys<K>, bool UNMAKE = false>
+int rs_launch_scatter(const In kin, const uint32_t* iin, K* kout, uint32_t* iout, long long n, int shift, const uint32_t* offsets, int nblocks,
                       uint32_t* desc, cudaStream_t st) {
   static bool configured[RS_MAX_DEVICES] = {};
   int dev = 0;
   OCB_CUDA(cudaGetDevice(&dev));
   constexpr size_t smem = rs_scatter_smem<K>();
   if (dev < 0 || dev >= RS_MAX_DEVICES || !configured[dev]) {
-    OCB_CUDA(cudaFuncSetAttribute(rs_scatter<K, CHAINED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OCB_CUDA(cudaFuncSetAttribute(rs_scatter<K, CHAINED, In, UNMAKE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (dev >= 0 && dev < RS_MAX_DEVICES) configured[dev] = true;
   }
   int grid = nblocks;
   if (CHAINED) { const int resident = 3 * ocb_sm_count(); if (grid > resident) grid = resident; }
-  static const int dbg = getenv("OCB_SORT_DBG") ? atoi(getenv("OCB_SORT_DBG")) : 0;
-  rs_scatter<K, CHAINED><<<grid, RS_THREADS, smem, st>>>(kin, iin, kout, iout, n, shift, offsets, nblocks, desc, dbg);
+  rs_scatter<K, CHAINED, In, UNMAKE><<<grid, RS_THREADS, smem, st>>>(kin, iin, kout, iout, n, shift, offsets, nblocks, desc);
   return OCB_OK;
 }
 
 // all digit histograms of the keys in one read: hist[pass][256] (global digit counts do not depend on the order of the keys)
-template <class K>
-__global__ void __launch_bounds__(RS_THREADS) rs_histogram_all(const K* __restrict__ keys, long long n, uint32_t* __restrict__ hist) {
+template <class K, class In>
+__global__ void __launch_bounds__(RS_THREADS, 4) rs_histogram_all(const In keys, long long n, uint32_t* __restrict__ hist) {
   constexpr int NP = KeyTraits<K>::BITS / 8;
+  constexpr int HB = 8;                               // loads in flight per thread
   __shared__ uint32_t h[NP][256];
   for (int p = 0; p < NP; ++p) h[p][threadIdx.x] = 0;
   __syncthreads();
-  for (long long base = (long long)blockIdx.x * RS_TILE; base < n; base += (long long)gridDim.x * RS_TILE) {
-#pragma unroll 4
-    for (int r = 0; r < RS_ITEMS; ++r) {
+  for (long long base = (long long)blockIdx.x * (HB * RS_THREADS); base < n; base += (long long)gridDim.x * (HB * RS_THREADS)) {
+    K keyr[HB];
+    auto cur = keys.at(base + threadIdx.x < n ? base + threadIdx.x : 0);
+#pragma unroll
+    for (int r = 0; r < HB; ++r) {
+      const long long t = base + r * RS_THREADS + threadIdx.x;
+      keyr[r] = t < n ? cur.first() : (K)0;
+      cur.advance(RS_THREADS);
+    }
+#pragma unroll
+    for (int r = 0; r < HB; ++r) {
       const long long t = base + r * RS_THREADS + threadIdx.x;
       const bool ok = t < n;
-      const K key = ok ? __ldg(keys + t) : (K)0;
+      const K key = keyr[r];
+      // the upper digits of real data are nearly constant: one add per warp when all its lanes agree on a digit (the bits in which
+      // a lane differs from lane 0, one vote per digit)
+      const unsigned act = __ballot_sync(0xffffffffu, ok);
+      const K diff = key ^ __shfl_sync(0xffffffffu, key, 0);
 #pragma unroll
       for (int p = 0; p < NP; ++p) {
         const uint32_t dig = (uint32_t)(key >> (8 * p)) & 255u;
-        // the upper digits of real data are nearly constant: one add per warp when all its lanes agree
-        int same = 0;
-        const unsigned act = __ballot_sync(0xffffffffu, ok);
-        if (act == 0xffffffffu) __match_all_sync(0xffffffffu, dig, &same);
+        const bool same = __all_sync(0xffffffffu, ((uint32_t)(diff >> (8 * p)) & 255u) == 0u) && act == 0xffffffffu;
         if (same) { if ((threadIdx.x & 31) == 0) atomicAdd(&h[p][dig], 32u); }
         else if (ok) atomicAdd(&h[p][dig], 1u);
       }
@@ -537,43 +594,68 @@ int device_scan(const T* in, T* out, long long n, T* totals_scratch, cudaStream_
   return device_scan_of<T, OP, REV, EXCL, PtrInput<T>>(PtrInput<T>{in}, out, n, totals_scratch, st);
 }
 
-template <class K>
-int radix_sort_pairs(K* keys_a, uint32_t* idx_a, K* keys_b, uint32_t* idx_b, long long n, uint32_t* table, uint32_t* table_tot,
-                     int nblocks, cudaStream_t st, K** keys_sorted, uint32_t** idx_sorted) {
-  K* kin = keys_a; K* kout = keys_b;
-  uint32_t* iin = idx_a; uint32_t* iout = idx_b;
+// Sort of n (key, position) pairs.  `first` is where the keys come from (the first pass makes them on the fly and its payload is
+// the position).  Passes alternate between the (a) and (b) scratch pairs; the LAST pass writes to (final_keys, final_idx) when
+// they are given -- the caller's own arrays -- and stores values instead of keys with `unmake`.  *keys_sorted / *idx_sorted are
+// where the result is.
+template <class K, class In>
+int radix_sort_pairs(const In first, K* keys_a, uint32_t* idx_a, K* keys_b, uint32_t* idx_b, long long n, uint32_t* table, uint32_t* table_tot,
+                     int nblocks, cudaStream_t st, K** keys_sorted, uint32_t** idx_sorted, bool unmake = false, K* final_keys = nullptr,
+                     uint32_t* final_idx = nullptr) {
+  constexpr int NP = KeyTraits<K>::BITS / 8;
   const long long ntab = 256ll * nblocks;
   if (n < (1ll << 30) && !getenv("OCB_SORT_TABLE_SCAN")) {
-    // onesweep: one histogram of all digits up front, then ONE kernel per digit.  `table` (256 nblocks words + the allocation's
-    // spare 64) holds the tile descriptors of the current pass, then the ticket counter and the error word; `table_tot` (sized
-    // for it by the callers) the digit histograms / bases.
-    constexpr int NP = KeyTraits<K>::BITS / 8;
-    {
-      uint32_t* hist = table_tot;
-      OCB_CUDA(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * NP * 256, st));
-      int hb = ocb_sm_count() * 4;
-      if (hb > nblocks) hb = nblocks;
-      rs_histogram_all<K><<<hb, RS_THREADS, 0, st>>>(kin, n, hist);
-      rs_digit_bases<<<NP, 256, 0, st>>>(hist);
-      for (int p = 0; p < NP; ++p) {
-        OCB_CUDA(cudaMemsetAsync(table, 0, sizeof(uint32_t) * rs_desc_clear(nblocks), st));      // flags, ticket, error word, group totals
-        { const int rc = rs_launch_scatter<K, true>(kin, iin, kout, iout, n, 8 * p, hist + p * 256, nblocks, table, st); if (rc != OCB_OK) return rc; }
-        K* tk = kin; kin = kout; kout = tk;
-        uint32_t* ti = iin; iin = iout; iout = ti;
-      }
-      OCB_CUDA(cudaGetLastError());
-      *keys_sorted = kin; *idx_sorted = iin;
-      return OCB_OK;
+    // onesweep: one histogram of all digits up front, then ONE kernel per digit.  `table` (rs_table_words) holds the tile / group
+    // descriptors of the current pass; `table_tot` (sized for it by the callers) the digit histograms / bases.
+    uint32_t* hist = table_tot;
+    OCB_CUDA(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * NP * 256, st));
+    int per_sm = 0;                                     // exactly the resident blocks: a partial second wave would cost a whole one
+    OCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rs_histogram_all<K, In>, RS_THREADS, 0));
+    int hb = ocb_sm_count() * (per_sm > 0 ? per_sm : 1);
+    if (hb > 2 * nblocks) hb = 2 * nblocks;
+    rs_histogram_all<K, In><<<hb, RS_THREADS, 0, st>>>(first, n, hist);
+    rs_digit_bases<<<NP, 256, 0, st>>>(hist);
+    K* kin = nullptr; uint32_t* iin = nullptr;
+    for (int p = 0; p < NP; ++p) {
+      const bool last = p == NP - 1;
+      K* kout = last && final_keys ? final_keys : ((p & 1) ? keys_b : keys_a);
+      uint32_t* iout = last && final_idx ? final_idx : ((p & 1) ? idx_b : idx_a);
+      OCB_CUDA(cudaMemsetAsync(table, 0, sizeof(uint32_t) * rs_desc_clear(nblocks), st));      // flags, ticket, error word, group totals
+      int rc;
+      if (p == 0) rc = rs_launch_scatter<K, true, In, false>(first, nullptr, kout, iout, n, 0, hist, nblocks, table, st);
+      else if (last && unmake) rc = rs_launch_scatter<K, true, PtrKeys<K>, true>(PtrKeys<K>{kin}, iin, kout, iout, n, 8 * p, hist + p * 256, nblocks, table, st);
+      else rc = rs_launch_scatter<K, true, PtrKeys<K>, false>(PtrKeys<K>{kin}, iin, kout, iout, n, 8 * p, hist + p * 256, nblocks, table, st);
+      if (rc != OCB_OK) return rc;
+      kin = kout; iin = iout;
     }
+    OCB_CUDA(cudaGetLastError());
+    *keys_sorted = kin; *idx_sorted = iin;
+    return OCB_OK;
   }
+  // per-pass histogram table + scan (n >= 2^30, or OCB_SORT_TABLE_SCAN): keys made by a pass of their own, values by another
+  K* kin = keys_a; K* kout = keys_b;
+  uint32_t* iin = idx_a; uint32_t* iout = idx_b;
+  rs_materialize_keys<K, In><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(first, kin, iin, n);
   for (int shift = 0; shift < KeyTraits<K>::BITS; shift += 8) {
     rs_histogram<K><<<nblocks, RS_THREADS, 0, st>>>(kin, n, shift, table, nblocks);
     int rc = device_scan<uint32_t, OP_ADD, false, true>(table, table, ntab, table_tot, st);
     if (rc != OCB_OK) return rc;
-    rc = rs_launch_scatter<K, false>(kin, iin, kout, iout, n, shift, table, nblocks, nullptr, st);
+    rc = rs_launch_scatter<K, false>(PtrKeys<K>{kin}, iin, kout, iout, n, shift, table, nblocks, nullptr, st);
     if (rc != OCB_OK) return rc;
     K* tk = kin; kin = kout; kout = tk;
     uint32_t* ti = iin; iin = iout; iout = ti;
+  }
+  if (unmake) {
+    typename KeyTraits<K>::F* dst = reinterpret_cast<typename KeyTraits<K>::F*>(final_keys ? final_keys : kout);
+    rs_unmake_keys<K><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(kin, dst, n);
+    kin = reinterpret_cast<K*>(dst);
+  } else if (final_keys) {
+    OCB_CUDA(cudaMemcpyAsync(final_keys, kin, n * sizeof(K), cudaMemcpyDeviceToDevice, st));
+    kin = final_keys;
+  }
+  if (final_idx) {
+    OCB_CUDA(cudaMemcpyAsync(final_idx, iin, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    iin = final_idx;
   }
   OCB_CUDA(cudaGetLastError());
   *keys_sorted = kin; *idx_sorted = iin;
@@ -686,15 +768,6 @@ __global__ void bpe_perm_to_int64(const uint32_t* __restrict__ perm, long long n
 // are used, from the slot number and the sorted keys (same expressions as slot_centers! / slot_faces / fill_reference_potential!,
 // BackgroundPotentialEnergyEquation.jl:326-348, 383-397).  Bytes per cell: 20 (keys from the field) + 24 (Psi scan) +
 // 36 + the two scattered stores, instead of 232.
-template <class T, class K>
-__global__ void bpe_keys_from_field(const T* __restrict__ b1, long long s0, long long s1, long long s2, int Nx, int Ny, long long n,
-                                    K* __restrict__ keys, uint32_t* __restrict__ idx) {
-  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;   // b1 pre-offset to index (1,1,1) -> element 0
-  if (t >= n) return;
-  const int i = (int)(t % Nx), j = (int)((t / Nx) % Ny), k = (int)(t / ((long long)Nx * Ny));
-  keys[t] = to_key(b1[i * s0 + j * s1 + k * s2]);
-  idx[t] = (uint32_t)t;
-}
 struct UniformSlots {          // faces[m] = z_bot + cum[m-1]/A with cum[m-1] = m dV  (0-based face m below slot m)
   double z_bot, A, dV;
   __host__ __device__ __forceinline__ double face(long long m) const { return z_bot + ((double)m * dV) / A; }
@@ -790,13 +863,11 @@ int sort_impl(const T* keys_in, T* keys_out, uint32_t* perm_out, long long n, cu
   uint32_t* table = S.get<uint32_t>(rs_table_words(nblocks));
   uint32_t* tot = S.get<uint32_t>((256ull * nblocks + SC_CHUNK - 1) / SC_CHUNK + 1 + 8 * 256);   // + the digit histograms of the onesweep path
   if (!ka || !kb || !ia || !ib || !table || !tot) OCB_FAIL(OCB_ERR_ALLOC, "out of device memory for the sort scratch");
-  const unsigned g = (unsigned)((n + 255) / 256);
-  rs_make_keys<K><<<g, 256, 0, st>>>(keys_in, ka, ia, n);
+  // the first pass reads the caller's values, the last one writes the sorted values and the permutation into the caller's arrays
   K* ks; uint32_t* is;
-  int rc = radix_sort_pairs<K>(ka, ia, kb, ib, n, table, tot, nblocks, st, &ks, &is);
+  int rc = radix_sort_pairs<K, FloatKeys<K>>(FloatKeys<K>{keys_in}, ka, ia, kb, ib, n, table, tot, nblocks, st, &ks, &is, true,
+                                             reinterpret_cast<K*>(keys_out), perm_out);
   if (rc != OCB_OK) return rc;
-  if (keys_out) rs_unmake_keys<K><<<g, 256, 0, st>>>(ks, keys_out, n);
-  if (perm_out) OCB_CUDA(cudaMemcpyAsync(perm_out, is, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
   OCB_CUDA(cudaGetLastError());
   return OCB_OK;
 }
@@ -824,9 +895,9 @@ int bpe_sort3d_uniform(const ocb_grid* g, const ocb_field* b, const ocb_field* z
   P.p = nullptr; P.sx = P.sy = P.sz = 0;
   if (psid && psid->data) { rc = make_fld<T>(*psid, &P, "psi_delta", false); if (rc != OCB_OK) return rc; }
   const unsigned gr = (unsigned)((n + 255) / 256);
-  bpe_keys_from_field<T, K><<<gr, 256, 0, st>>>(B.p + (B.sx + B.sy + B.sz), B.sx, B.sy, B.sz, Nx, Ny, n, ka, ia);
-  K* ks; uint32_t* perm;
-  rc = radix_sort_pairs<K>(ka, ia, kb, ib, n, table, tot, nblocks, st, &ks, &perm);
+  K* ks; uint32_t* perm;       // keys straight from the field: the first pass of the sort makes them
+  rc = radix_sort_pairs<K, FieldKeys<T, K>>(FieldKeys<T, K>{B.p + (B.sx + B.sy + B.sz), B.sx, B.sy, B.sz, FastDiv((uint32_t)Nx), FastDiv((uint32_t)Ny)}, ka, ia, kb, ib, n, table, tot,
+                                            nblocks, st, &ks, &perm);
   if (rc != OCB_OK) return rc;
   UniformSlots U;
   U.z_bot = g->z_bottom; U.A = (g->L[0] * g->L[1] * g->L[2]) / g->L[2];
@@ -849,7 +920,7 @@ int bpe_sort3d_uniform(const ocb_grid* g, const ocb_field* b, const ocb_field* z
     rs_histogram<uint32_t><<<nblocks, RS_THREADS, 0, st>>>(perm, n, shift, table, nblocks);
     rc = device_scan<uint32_t, OP_ADD, false, true>(table, table, 256ll * nblocks, tot, st);
     if (rc != OCB_OK) return rc;
-    { const int rc2 = rs_launch_scatter<uint32_t, false>(perm, nullptr, cells2, ranks2, n, shift, table, nblocks, nullptr, st); if (rc2 != OCB_OK) return rc2; }
+    { const int rc2 = rs_launch_scatter<uint32_t, false>(PtrKeys<uint32_t>{perm}, nullptr, cells2, ranks2, n, shift, table, nblocks, nullptr, st); if (rc2 != OCB_OK) return rc2; }
     bpe_scatter_bucketed<T, K><<<gr, 256, 0, st>>>(cells2, ranks2, ks, psi, n, Nx, Ny, U, psi_level, z1, Z.sx, Z.sy, Z.sz, p1, P.sx, P.sy, P.sz);
     if (perm_out || bs_out) bpe_sorted_outputs<T, K><<<gr, 256, 0, st>>>(perm, ks, n, perm_out, (T*)bs_out);
   } else {
@@ -891,11 +962,10 @@ int bpe_impl(const ocb_grid* g, const ocb_field* b, int method, const ocb_field*
   P.p = nullptr; P.sx = P.sy = P.sz = 0;
   if (psid && psid->data) { rc = make_fld<T>(*psid, &P, "psi_delta", false); if (rc != OCB_OK) return rc; }
   const T* b1 = B.p + (B.sx + B.sy + B.sz);        // element at index (1,1,1)
-  bpe_keys_from_field<T, K><<<gr, 256, 0, st>>>(b1, B.sx, B.sy, B.sz, Nx, Ny, n, ka, ia);
-  K* ks; uint32_t* perm;
-  rc = radix_sort_pairs<K>(ka, ia, kb, ib, n, table, tot, nblocks, st, &ks, &perm);
+  K* ks; uint32_t* perm;       // the first pass makes the keys from the field, the last one writes the sorted values b*
+  rc = radix_sort_pairs<K, FieldKeys<T, K>>(FieldKeys<T, K>{b1, B.sx, B.sy, B.sz, FastDiv((uint32_t)Nx), FastDiv((uint32_t)Ny)}, ka, ia, kb, ib, n, table, tot, nblocks, st, &ks, &perm,
+                                            true, reinterpret_cast<K*>(bs));
   if (rc != OCB_OK) return rc;
-  rs_unmake_keys<K><<<gr, 256, 0, st>>>(ks, bs, n);
   // volumes in sorted order and their cumulative sum (slot_centers!)
   const T* dzc1 = g->dzc ? (const T*)g->dzc + g->H[2] : nullptr;       // Δzᶜ at k = 1
   const T* zc1 = g->zc ? (const T*)g->zc + g->H[2] : nullptr;
