@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "liboceanostics_b200.so")
+LIB_PATH = os.environ.get("OCB_LIB_PATH") or os.path.join(HERE, "lib", "liboceanostics_b200.so")   # OCB_LIB_PATH: another build of the same ABI (A/B runs)
 
 OCB_F32, OCB_F64 = 0, 1
 OCB_PERIODIC, OCB_BOUNDED = 0, 1

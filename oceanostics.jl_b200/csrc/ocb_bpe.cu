@@ -183,20 +183,28 @@ __device__ __forceinline__ uint32_t rs_ld_flag(const uint32_t* p) {
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-template <class K> constexpr size_t rs_scatter_smem() {
-  return sizeof(K) * RS_TILE + sizeof(uint32_t) * (RS_TILE + 2 * RS_WARPS * 256 + 256 + RS_WARPS + 8);
+// An optional second payload: one double per element, formed from the element's position when its tile is staged and moved with
+// the pair (the bucketing pass of the reference-height epilogue carries the cell's Psi this way instead of gathering it later).
+struct NoPay2 {
+  static constexpr bool ON = false;
+  __device__ __forceinline__ double at(long long) const { return 0.0; }
+};
+template <class K, class Pay2 = NoPay2> constexpr size_t rs_scatter_smem() {
+  return sizeof(K) * RS_TILE + sizeof(uint32_t) * (RS_TILE + 2 * RS_WARPS * 256 + 256 + RS_WARPS + 8) + (Pay2::ON ? sizeof(double) * RS_TILE : 0);
 }
-template <class K, bool CHAINED = false, class In = PtrKeys<K>, bool UNMAKE = false>
-__global__ void __launch_bounds__(RS_THREADS, 3) rs_scatter(const In keys_in, const uint32_t* __restrict__ idx_in, K* __restrict__ keys_out,
+template <class K, bool CHAINED = false, class In = PtrKeys<K>, bool UNMAKE = false, class Pay2 = NoPay2>
+__global__ void __launch_bounds__(RS_THREADS, Pay2::ON ? 2 : 3) rs_scatter(const In keys_in, const uint32_t* __restrict__ idx_in, K* __restrict__ keys_out,
                                                           uint32_t* __restrict__ idx_out, long long n, int shift,
-                                                          const uint32_t* __restrict__ offsets, int nblocks, uint32_t* desc = nullptr) {
+                                                          const uint32_t* __restrict__ offsets, int nblocks, uint32_t* desc = nullptr,
+                                                          const Pay2 pay2 = Pay2(), double* __restrict__ pay2_out = nullptr) {
   extern __shared__ __align__(16) unsigned char rs_smem[];
   K* stage = reinterpret_cast<K*>(rs_smem);                                     // the staged tile's keys in digit order
   uint32_t* ibuf = reinterpret_cast<uint32_t*>(stage + RS_TILE);                // the staged tile's payload in digit order
   // per warp and digit: ranking mask | running count << 32, then (count half) the tile position of the warp's first key of the digit
   unsigned long long (*wmc)[256] = reinterpret_cast<unsigned long long (*)[256]>(ibuf + RS_TILE);
   uint32_t* gbase = reinterpret_cast<uint32_t*>(&wmc[RS_WARPS][0]);   // global position of the staged tile's first key of each digit, minus its tile position
-  uint32_t* wtot = gbase + 256;            // [RS_WARPS] block-scan totals, [RS_WARPS] the next tile number
+  uint32_t* wtot = gbase + 256;           // [RS_WARPS] block-scan totals, [RS_WARPS] the next tile number
+  double* ibuf2 = reinterpret_cast<double*>(wtot + RS_WARPS + 8);             // the staged tile's second payload (Pay2::ON)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
   const int d = threadIdx.x;
@@ -328,6 +336,7 @@ __global__ void __launch_bounds__(RS_THREADS, 3) rs_scatter(const In keys_in, co
           const uint32_t pos = gbase[(uint32_t)(k >> shift) & 255u] + (uint32_t)e;
           keys_out[pos] = UNMAKE ? unkey_bits(k) : k;
           idx_out[pos] = ibuf[e];
+          if (Pay2::ON) pay2_out[pos] = ibuf2[e];
         }
       }
     }
@@ -370,23 +379,31 @@ __global__ void __launch_bounds__(RS_THREADS, 3) rs_scatter(const In keys_in, co
     // below hides the round trip)
     uint32_t next_ticket = (uint32_t)nblocks;
     if (CHAINED && threadIdx.x == 0) next_ticket = atomicAdd(desc + nblocks, 1u);
-    // keys (again, from L2) and payload into digit order in shared memory
-    {
-      K key[RS_ITEMS];
-      uint32_t pay[RS_ITEMS];
-      auto cur = keys_in.at(tbase + wl);
+    // keys (again, from L2) and payload into digit order in shared memory (with a second payload: in two halves, for the registers)
+    constexpr int EB = Pay2::ON ? RS_ITEMS / 2 : RS_ITEMS;
+    auto cur = keys_in.at(tbase + wl);
 #pragma unroll
-      for (int r = 0; r < RS_ITEMS; ++r) { key[r] = (wl + 32 * r) < ntile ? cur.again() : (K)0; cur.advance(32); }
+    for (int r0 = 0; r0 < RS_ITEMS; r0 += EB) {
+      K key[EB];
+      uint32_t pay[EB];
+      double p2[EB];
 #pragma unroll
-      for (int r = 0; r < RS_ITEMS; ++r)
-        pay[r] = idx_in ? ((wl + 32 * r) < ntile ? __ldcg(idx_in + tbase + wl + 32 * r) : 0u) : (uint32_t)(tbase + wl + 32 * r);   // no payload array: the key's position
+      for (int q = 0; q < EB; ++q) { key[q] = (wl + 32 * (r0 + q)) < ntile ? cur.again() : (K)0; cur.advance(32); }
 #pragma unroll
-      for (int r = 0; r < RS_ITEMS; ++r) {
+      for (int q = 0; q < EB; ++q) {
+        const int r = r0 + q;
+        pay[q] = idx_in ? ((wl + 32 * r) < ntile ? __ldcg(idx_in + tbase + wl + 32 * r) : 0u) : (uint32_t)(tbase + wl + 32 * r);   // no payload array: the key's position
+        p2[q] = (Pay2::ON && (wl + 32 * r) < ntile) ? pay2.at(tbase + wl + 32 * r) : 0.0;
+      }
+#pragma unroll
+      for (int q = 0; q < EB; ++q) {
+        const int r = r0 + q;
         if ((wl + 32 * r) < ntile) {
           const uint32_t dig = (dg[r >> 2] >> (8 * (r & 3))) & 255u;
           const uint32_t pos = reinterpret_cast<const uint32_t*>(&wmc[warp][dig])[1] + ((rk[r >> 1] >> (16 * (r & 1))) & 0xffffu);   // tile position
-          stage[pos] = key[r];
-          ibuf[pos] = pay[r];
+          stage[pos] = key[q];
+          ibuf[pos] = pay[q];
+          if (Pay2::ON) ibuf2[pos] = p2[q];
         }
       }
     }
@@ -396,20 +413,30 @@ __global__ void __launch_bounds__(RS_THREADS, 3) rs_scatter(const In keys_in, co
     tile = (int)wtot[RS_WARPS];
   }
 }
-template <class K, bool CHAINED, class In = PtrKeys<K>, bool UNMAKE = false>
+template <class K, bool CHAINED, class In = PtrKeys<K>, bool UNMAKE = false, class Pay2 = NoPay2>
 int rs_launch_scatter(const In kin, const uint32_t* iin, K* kout, uint32_t* iout, long long n, int shift, const uint32_t* offsets, int nblocks,
-                      uint32_t* desc, cudaStream_t st) {
+                      uint32_t* desc, cudaStream_t st, const Pay2 pay2 = Pay2(), double* pay2_out = nullptr) {
   static bool configured[RS_MAX_DEVICES] = {};
   int dev = 0;
   OCB_CUDA(cudaGetDevice(&dev));
-  constexpr size_t smem = rs_scatter_smem<K>();
+  constexpr size_t smem = rs_scatter_smem<K, Pay2>();
   if (dev < 0 || dev >= RS_MAX_DEVICES || !configured[dev]) {
-    OCB_CUDA(cudaFuncSetAttribute(rs_scatter<K, CHAINED, In, UNMAKE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OCB_CUDA(cudaFuncSetAttribute(rs_scatter<K, CHAINED, In, UNMAKE, Pay2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (dev >= 0 && dev < RS_MAX_DEVICES) configured[dev] = true;
   }
   int grid = nblocks;
-  if (CHAINED) { const int resident = 3 * ocb_sm_count(); if (grid > resident) grid = resident; }
-  rs_scatter<K, CHAINED, In, UNMAKE><<<grid, RS_THREADS, smem, st>>>(kin, iin, kout, iout, n, shift, offsets, nblocks, desc);
+  if (CHAINED) {                                         // persistent: exactly the resident blocks
+    static int per_sm[RS_MAX_DEVICES] = {};
+    const int di = dev >= 0 && dev < RS_MAX_DEVICES ? dev : 0;
+    if (per_sm[di] <= 0) {
+      int v = 0;
+      OCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, rs_scatter<K, CHAINED, In, UNMAKE, Pay2>, RS_THREADS, smem));
+      per_sm[di] = v > 0 ? v : 1;
+    }
+    const int resident = per_sm[di] * ocb_sm_count();
+    if (grid > resident) grid = resident;
+  }
+  rs_scatter<K, CHAINED, In, UNMAKE, Pay2><<<grid, RS_THREADS, smem, st>>>(kin, iin, kout, iout, n, shift, offsets, nblocks, desc, pay2, pay2_out);
   return OCB_OK;
 }
 
@@ -465,6 +492,13 @@ __global__ void __launch_bounds__(256) rs_digit_bases(uint32_t* __restrict__ his
     __syncthreads();
   }
   h[threadIdx.x] = sh[threadIdx.x] - c;
+}
+
+// digit bases of the integers 0 .. n-1 (a permutation's values) for the digit at bits [shift, shift + 8), n <= 2^(shift + 8):
+// digit d holds min(max(n - d 2^shift, 0), 2^shift) of them -- no histogram pass
+__global__ void __launch_bounds__(256) rs_iota_digit_bases(long long n, int shift, uint32_t* __restrict__ bases) {
+  const long long lo = (long long)threadIdx.x << shift;
+  bases[threadIdx.x] = (uint32_t)(lo < n ? lo : n);
 }
 
 // ---- block scans ----------------------------------------------------------------------------------------------
@@ -831,6 +865,31 @@ __global__ void bpe_scatter_bucketed(const uint32_t* __restrict__ cells, const u
     psid[i * ps0 + j * ps1 + k * ps2] = (T)(psi_level[k] - ps);
   }
 }
+// The reference potential of the cell of rank t, Psi(z*) (fill_reference_potential!), formed where the sorted keys and the
+// running sum are read in order: the bucketing pass carries it with the (cell, rank) pair.
+template <class T, class K> struct PsiOfRank {
+  static constexpr bool ON = true;
+  const K* ks; const double* psi_incl; UniformSlots U;
+  __device__ __forceinline__ double at(long long t) const {
+    const T bs = from_key(__ldg(ks + t));
+    const T zs = (T)U.centre(t);
+    return (t ? __ldg(psi_incl + t - 1) : 0.0) + (double)bs * ((double)zs - U.face(t));
+  }
+};
+// final scatter of (z*, Psi delta) from the bucketed (cell, rank, Psi) triples: every read in order, the stores within one region
+template <class T>
+__global__ void bpe_scatter_triples(const uint32_t* __restrict__ cells, const uint32_t* __restrict__ ranks, const double* __restrict__ psis,
+                                    long long n, FastDiv dx, FastDiv dy, UniformSlots U, const double* __restrict__ psi_level,
+                                    T* __restrict__ zstar, long long zs0, long long zs1, long long zs2,
+                                    T* __restrict__ psid, long long ps0, long long ps1, long long ps2) {
+  const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const uint32_t cell = __ldg(cells + e);
+  const long long t = __ldg(ranks + e);
+  const uint32_t q = dx.div(cell), i = cell - q * dx.d, k = dy.div(q), j = q - k * dy.d;
+  zstar[i * zs0 + j * zs1 + k * zs2] = (T)U.centre(t);
+  psid[i * ps0 + j * ps1 + k * ps2] = (T)(psi_level[k] - __ldg(psis + e));
+}
 template <class T, class K>
 __global__ void bpe_sorted_outputs(const uint32_t* __restrict__ perm, const K* __restrict__ ks, long long n, int64_t* __restrict__ perm_out,
                                    T* __restrict__ bs_out) {
@@ -917,11 +976,24 @@ int bpe_sort3d_uniform(const ocb_grid* g, const ocb_field* b, const ocb_field* z
     const int shift = bits > 8 ? bits - 8 : 0;
     uint32_t* cells2 = reinterpret_cast<uint32_t*>(ks == ka ? kb : ka);
     uint32_t* ranks2 = (perm == ia) ? ib : ia;
-    rs_histogram<uint32_t><<<nblocks, RS_THREADS, 0, st>>>(perm, n, shift, table, nblocks);
-    rc = device_scan<uint32_t, OP_ADD, false, true>(table, table, 256ll * nblocks, tot, st);
-    if (rc != OCB_OK) return rc;
-    { const int rc2 = rs_launch_scatter<uint32_t, false>(PtrKeys<uint32_t>{perm}, nullptr, cells2, ranks2, n, shift, table, nblocks, nullptr, st); if (rc2 != OCB_OK) return rc2; }
-    bpe_scatter_bucketed<T, K><<<gr, 256, 0, st>>>(cells2, ranks2, ks, psi, n, Nx, Ny, U, psi_level, z1, Z.sx, Z.sy, Z.sz, p1, P.sx, P.sy, P.sz);
+    double* psis2 = (p1 && !getenv("OCB_BPE_GATHER_PSI")) ? S.get<double>(n) : nullptr;     // no room: the gathering scatter
+    // the values of a permutation: the digit bases are known without a histogram, so the pass is one chained scatter
+    uint32_t* bases = tot;
+    rs_iota_digit_bases<<<1, 256, 0, st>>>(n, shift, bases);
+    OCB_CUDA(cudaMemsetAsync(table, 0, sizeof(uint32_t) * rs_desc_clear(nblocks), st));
+    if (p1 && psis2) {
+      // with Psi: the pass carries Psi(rank) as a second payload, so the final scatter reads everything in order (the gathers of the
+      // sorted key and the running sum at the rank, a 32-byte sector each, were 2.3 ms of the 8.7 at 67 M cells)
+      const int rc2 = rs_launch_scatter<uint32_t, true, PtrKeys<uint32_t>, false, PsiOfRank<T, K>>(
+          PtrKeys<uint32_t>{perm}, nullptr, cells2, ranks2, n, shift, bases, nblocks, table, st, PsiOfRank<T, K>{ks, psi, U}, psis2);
+      if (rc2 != OCB_OK) return rc2;
+      bpe_scatter_triples<T><<<gr, 256, 0, st>>>(cells2, ranks2, psis2, n, FastDiv((uint32_t)Nx), FastDiv((uint32_t)Ny), U, psi_level, z1, Z.sx, Z.sy,
+                                                 Z.sz, p1, P.sx, P.sy, P.sz);
+    } else {
+      const int rc2 = rs_launch_scatter<uint32_t, true>(PtrKeys<uint32_t>{perm}, nullptr, cells2, ranks2, n, shift, bases, nblocks, table, st);
+      if (rc2 != OCB_OK) return rc2;
+      bpe_scatter_bucketed<T, K><<<gr, 256, 0, st>>>(cells2, ranks2, ks, psi, n, Nx, Ny, U, psi_level, z1, Z.sx, Z.sy, Z.sz, p1, P.sx, P.sy, P.sz);
+    }
     if (perm_out || bs_out) bpe_sorted_outputs<T, K><<<gr, 256, 0, st>>>(perm, ks, n, perm_out, (T*)bs_out);
   } else {
     bpe_scatter_uniform<T, K><<<gr, 256, 0, st>>>(perm, ks, psi, n, Nx, Ny, U, psi_level, z1, Z.sx, Z.sy, Z.sz, p1, P.sx, P.sy, P.sz, perm_out,

@@ -150,6 +150,7 @@ ocb_strain_kernel(const __grid_constant__ StrainParams<T> P) {
 
   const bool do_eiso = P.out[SD_EISO] || P.slot[SD_EISO] >= 0, do_smod = P.out[SD_SMOD] || P.slot[SD_SMOD] >= 0,
              do_omod = P.out[SD_OMOD] || P.slot[SD_OMOD] >= 0, do_q = P.out[SD_Q] || P.slot[SD_Q] >= 0;
+  const bool integ = P.nslots > 0;
   int s = 0, par = 0;
   // z metrics: a window of ZC planes is staged in shared memory by the first warp (a global load consumed right
   // after the barrier would stall every warp of the block at once, once per plane)
@@ -271,11 +272,13 @@ ocb_strain_kernel(const __grid_constant__ StrainParams<T> P) {
       if (F_M && (do_omod || do_q)) vO = t_sqrt(O2);
       if (F_P && F_M && do_q) vQ = H2 * (vO * vO - vS * vS);              // through the roots, as the reference does
       // integrals: overlap cells and planes outside the chunk enter as exact zeros (a select, not a multiply by 0)
-      if (F_E) acc[SD_EPS] = fma((double)(w1 ? vE : T(0)), vol, acc[SD_EPS]);
-      if (F_P && do_eiso) acc[SD_EISO] = fma((double)(w1 ? vI : T(0)), vol, acc[SD_EISO]);
-      if (F_P && do_smod) acc[SD_SMOD] = fma((double)(w1 ? vS : T(0)), vol, acc[SD_SMOD]);
-      if (F_M && do_omod) acc[SD_OMOD] = fma((double)(w1 ? vO : T(0)), vol, acc[SD_OMOD]);
-      if (F_P && F_M && do_q) acc[SD_Q] = fma((double)(w1 ? vQ : T(0)), vol, acc[SD_Q]);
+      if (integ) {                                        // (uniform) plans that only write fields skip the Float64 accumulation
+        if (F_E) acc[SD_EPS] = fma((double)(w1 ? vE : T(0)), vol, acc[SD_EPS]);
+        if (F_P && do_eiso) acc[SD_EISO] = fma((double)(w1 ? vI : T(0)), vol, acc[SD_EISO]);
+        if (F_P && do_smod) acc[SD_SMOD] = fma((double)(w1 ? vS : T(0)), vol, acc[SD_SMOD]);
+        if (F_M && do_omod) acc[SD_OMOD] = fma((double)(w1 ? vO : T(0)), vol, acc[SD_OMOD]);
+        if (F_P && F_M && do_q) acc[SD_Q] = fma((double)(w1 ? vQ : T(0)), vol, acc[SD_Q]);
+      }
       if (w1) {
         if (F_E && P.out[SD_EPS]) P.out[SD_EPS][o] = vE;
         if (F_P && P.out[SD_EISO]) P.out[SD_EISO][o] = vI;
