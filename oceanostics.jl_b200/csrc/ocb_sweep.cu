@@ -243,14 +243,19 @@ static int finish_plan(ocb_plan* pl, const ocb_grid* grid, const ocb_sweep_input
     if (ocb_fused_handles_diag(reqs[r].diag) && !(reqs[r].flags & OCB_REQ_CENTERED4) && !(eps_with_moduli && reqs[r].diag == OCB_DIAG_EPS)) fr[nf++] = reqs[r];
     else gr[ng++] = reqs[r];
   }
-  for (int attempt = 0; attempt < 3 && nf > 0 && !pl->fused; ++attempt) {
+  const bool stretched_z = grid->dzc || grid->dzf;
+  for (int attempt = 0; attempt < 4 && nf > 0 && !pl->fused; ++attempt) {
     if (attempt >= 1) {
       // the budget kernels declined the set: retry without the term with the narrowest envelope -- first the potential
-      // vorticity, then the turbulent kinetic energy (class-sum kernel only)
+      // vorticity, then the turbulent kinetic energy (class-sum kernel only), then (stretched z: the per-plane-metric variant
+      // evaluates the seven plain budget terms) everything about mean-flow operands
+      if (attempt == 3 && !stretched_z) break;
       const int drop = attempt == 1 ? OCB_DIAG_EPV : OCB_DIAG_TKE;
       int kept = 0, moved = 0;
       for (int r = 0; r < nf; ++r) {
-        if (fr[r].diag == drop) { gr[ng++] = fr[r]; ++moved; } else fr[kept++] = fr[r];
+        const bool go = attempt < 3 ? fr[r].diag == drop
+                                    : ((fr[r].flags & OCB_REQ_PERTURBATION) || fr[r].diag == OCB_DIAG_SP || fr[r].diag == OCB_DIAG_SPZ);
+        if (go) { gr[ng++] = fr[r]; ++moved; } else fr[kept++] = fr[r];
       }
       nf = kept;
       if (!moved) continue;

@@ -63,6 +63,8 @@ struct FusedParams {
   // class-sum kernel only.  y_ring: the y window is a whole periodic extent / one slab of a periodic ring (interior item
   // weights on every row).  gate: this rank's halo flag words {from low, from high, timed out} -- the first and last tile
   // rows wait until they reach gate_step (ocb_plan_execute_ring); nullptr: no waiting.
+  // stretched z (ocb_budget_kernel<.., STR = true>): pre-offset metric tables, table[k] with the 1-based k, k = 1 - Hz .. Nz + Hz
+  const double *dzc, *dzf, *rdzc, *rdzf;
   int y_ring;
   long long* gate;
   long long gate_step, gate_timeout;
@@ -107,7 +109,11 @@ struct Geo {
 //              the five exchanged rows and seven pipeline registers per row disappear.
 // (A warp-specialised variant -- producer warp + per-pair mbarriers instead of the block barrier -- was measured
 //  slower on B200, 55.9 vs 66.7 Gcells/s, and removed; see profiles/r1_summary.md.)
-template <int MASK, int NW, int RY, int NS, bool OUT>
+// STR = true (with OUT): z is a stretched axis.  What changes is where a z metric sits (Oceananigans' area / volume weighted
+// forms, restated in oracle/kernels.py): face gradients take 1/dzf of their face, cell differences 1/dzc of their cell, the fcf / cff
+// strain edges and the z-face tracer gradients enter a cell with weight dzf(face) / dzc(cell), the advecting transports of the w
+// equation are dzc-weighted means (Ax = dy dzc), and integrals weigh a cell by dzc.  The metrics are uniform loads per plane.
+template <int MASK, int NW, int RY, int NS, bool OUT, bool STR = false>
 __global__ void __launch_bounds__(NW * 32, (RY == 1 ? (NW <= 8 ? 2 : 1) : (RY == 2 && NW <= 6 ? 2 : 1)))
 ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__ CUtensorMap mu, const __grid_constant__ CUtensorMap mv,
                   const __grid_constant__ CUtensorMap mw, const __grid_constant__ CUtensorMap mb, const __grid_constant__ CUtensorMap mp) {
@@ -188,8 +194,10 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
   double ucp[RY], vcp[RY];                              // centred perturbation velocities of the previous plane (SP)
   double aS_c[RY];
   double Dxp[RY], Dyp[RY], Sbp[RY], NE12p[RY];          // EPV: b-box sums and the corner ffc vorticity of the previous plane
+  double Efp[RY], Gzp[RY], Gcp[RY];                     // STR: dzf-weighted edge sums / tracer z gradients of the previous face
 #pragma unroll
   for (int r = 0; r < RY; ++r) {
+    Efp[r] = Gzp[r] = Gcp[r] = 0.0;
     up[r] = vp[r] = wp[r] = bp[r] = pp[r] = 0.0;
     P13p[r] = P23p[r] = dU[r] = dV[r] = dW[r] = Wwpp[r] = Apart[r] = Fvp[r] = 0.0;
     Eacc[r] = Kacc[r] = PRacc[r] = CHacc[r] = CDacc[r] = hzp[r] = 0.0;
@@ -267,6 +275,15 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
       if (P.Vz) { Vn = __ldg(P.Vz + n); Vn1 = __ldg(P.Vz + n - 1); Vn2 = __ldg(P.Vz + n - 2); }
       if (P.Wz) { Wn = __ldg(P.Wz + n); Wn1 = __ldg(P.Wz + n - 1); }
     }
+    // z metrics of this step (STR; otherwise the constants): face n, face n-1, cells n, n-1, n-2
+    double rzf = rdz, rzf1 = rdz, rzc1 = rdz, dzc0 = 1.0, dzc1 = 1.0, dzc2 = 1.0, dzf0 = 1.0;
+    if (STR) {
+      const int lo = 1 - P.hz, hi = P.Nz + P.hz;
+      const int q0 = min(max(n, lo), hi), q1 = min(max(n - 1, lo), hi), q2 = min(max(n - 2, lo), hi);
+      rzf = __ldg(P.rdzf + q0); rzf1 = __ldg(P.rdzf + q1); rzc1 = __ldg(P.rdzc + q1);
+      dzc0 = __ldg(P.dzc + q0); dzc1 = __ldg(P.dzc + q1); dzc2 = __ldg(P.dzc + q2); dzf0 = __ldg(P.dzf + q0);
+    }
+    const double ez_n = STR ? rzf * hsn : ez, dz2_1 = STR ? 2.0 * P.nu * (rzc1 * rzc1) : dz2;
     const bool ep = PZ && P.eps_pert;                   // dissipation of u - U: only the z differences change
     const double dUz = ep ? Un - Un1 : 0.0, dVz = ep ? Vn - Vn1 : 0.0, dWz = ep ? Wn - Wn1 : 0.0;
     auto accum = [&](double& a, double x, double y, double f) {     // a += f * x * y  (f folds away when STEADY)
@@ -275,7 +292,7 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
 
     // ---- stage 1: quantities owned by this thread's cells at plane n --------------------------------------
     double uc[RY], vc[RY], wc[RY], bc[RY], pc[RY];
-    double X12[RY], P12[RY], P12E[RY], e23[RY], P23[RY], Y13[RY], P13[RY], P13E[RY];
+    double X12[RY], P12[RY], P12E[RY], e23[RY], P23[RY], Y13[RY], P13[RY], P13E[RY], P13w[RY], P23w[RY];
     double Uu[RY], UuW[RY], Vv[RY], VvS[RY], inpl[RY], Kxy[RY], PRxy[RY], CHxy[RY], CDxy[RY], ucn[RY], vcn[RY];
     double XS23[RY], O13[RY], O12[RY], Dx[RY], Dy[RY], Sb[RY];
 #pragma unroll
@@ -292,10 +309,13 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
       const double s12 = (uc[r] - us) * ey + (vc[r] - vw) * ex;
       P12[r] = (vw + vc[r]) * (us + uc[r]);
       // fcf edge (i, j, n) and cff edge
-      const double s13 = (PZ ? (uc[r] - up[r]) - dUz : (uc[r] - up[r])) * ez + (wc[r] - ww) * ex;
+      const double s13 = (PZ ? (uc[r] - up[r]) - dUz : (uc[r] - up[r])) * ez_n + (wc[r] - ww) * ex;
       P13[r] = (ww + wc[r]) * (up[r] + uc[r]);
-      const double s23 = (PZ ? (vc[r] - vp[r]) - dVz : (vc[r] - vp[r])) * ez + (wc[r] - ws) * ey;
+      const double s23 = (PZ ? (vc[r] - vp[r]) - dVz : (vc[r] - vp[r])) * ez_n + (wc[r] - ws) * ey;
       P23[r] = (ws + wc[r]) * (vp[r] + vc[r]);
+      // w equation: the advecting transports are means of Ax u = dy dzc u (Ay v) over the two cell planes of the face
+      P13w[r] = STR ? (ww + wc[r]) * fma(dzc1, up[r], dzc0 * uc[r]) : P13[r];
+      P23w[r] = STR ? (ws + wc[r]) * fma(dzc1, vp[r], dzc0 * vc[r]) : P23[r];
       if (H_EPV) {
         // edge vorticities owned by this cell (always of the full velocities) and the b sums of the 2 x 2 columns
         // (i..i+1, j..j+1) of this plane
@@ -322,7 +342,7 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
       }
       if (H_ADV) {
         P12E[r] = __shfl_down_sync(FULLMASK, P12[r], 1);
-        P13E[r] = __shfl_down_sync(FULLMASK, P13[r], 1);
+        P13E[r] = __shfl_down_sync(FULLMASK, P13w[r], 1);
         Uu[r] = (uc[r] + ue) * (uc[r] + ue);
         const double uw = ru[0];
         UuW[r] = (uw + uc[r]) * (uw + uc[r]);
@@ -405,7 +425,7 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
 
     // ---- y exchange between warps: row 0 of the warp to the north ---------------------------------------------
     double* myx = xch + ((par * NW + warp) * NX) * 32 + lane;
-    if (H_ADV) { myx[0 * 32] = P12[0]; myx[1 * 32] = P23[0]; }
+    if (H_ADV) { myx[0 * 32] = P12[0]; myx[1 * 32] = P23w[0]; }
     if (OUT) { myx[2 * 32] = X12[0]; myx[3 * 32] = e23[0]; myx[4 * 32] = Fvp[0]; }
     if (H_EPV) { myx[5 * 32] = XS23[0]; myx[6 * 32] = O13[0]; myx[7 * 32] = O12[0]; }
     __syncthreads();
@@ -426,7 +446,7 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
     for (int r = 0; r < RY; ++r) {
       const bool last = (r == RY - 1);
       const double p12n = last ? P12N : P12[last ? r : r + 1];
-      const double p23n = last ? P23N : P23[last ? r : r + 1];
+      const double p23n = last ? P23N : P23w[last ? r : r + 1];
       const double dwz = PZ ? (wc[r] - wp[r]) - dWz : (wc[r] - wp[r]);
       if (H_EPV) {
         // q(i+1, j+1, n) = (f + ω)·∇b, every factor a 2- or 8-point mean onto the fff corner
@@ -450,13 +470,21 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
         const double x12n = last ? X12N : X12[last ? r : r + 1];
         const double e23n = last ? e23N : e23[last ? r : r + 1];
         const double fvn = last ? FvN : Fvp[last ? r : r + 1];          // Fv(j+1) at plane n-2
-        const double w1 = pv1 * wrow[r];                                 // plane n-1 terms
-        const double w2 = pv2 * wrow[r];                                 // ADV lags one more plane
+        const double w1 = STR ? (pv1 * wrow[r]) * dzc1 : pv1 * wrow[r];   // plane n-1 terms (STR: the cell's dz_c is its volume weight)
+        const double w2 = STR ? (pv2 * wrow[r]) * dzc2 : pv2 * wrow[r];   // ADV lags one more plane
         // eps(n-1) = [in-plane + xy edges](n-1) + z strain + the fcf/cff edge sums at faces n-1 and n
         if (H_EPS) {
           const double edge_n = Y13[r] + (e23[r] + e23n);
-          const double raw = fma(dwz * dwz, dz2, Eacc[r] + edge_n);
-          Eacc[r] = (inpl[r] + edge_n) + (X12[r] + x12n);
+          double raw;
+          if (!STR) {
+            raw = fma(dwz * dwz, dz2, Eacc[r] + edge_n);
+            Eacc[r] = (inpl[r] + edge_n) + (X12[r] + x12n);
+          } else {
+            const double ew = dzf0 * edge_n;                 // Az dz_f: the weight of an fcf / cff edge in its two cells
+            raw = fma(dwz * dwz, dz2_1, fma(rzc1, Efp[r] + ew, Eacc[r]));
+            Eacc[r] = inpl[r] + (X12[r] + x12n);
+            Efp[r] = ew;
+          }
           emit(FD_EPS, raw, SC_EPS, w1, n - 1, r);
         }
         if (H_K) {
@@ -467,8 +495,8 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
         }
         if (H_PR) {
           const double fz = wc[r] * (pc[r] - pp[r]);
-          const double raw = fma(fz, rdz, PRacc[r]);
-          PRacc[r] = fma(fz, rdz, PRxy[r]);
+          const double raw = fma(fz, rzf, PRacc[r]);
+          PRacc[r] = fma(fz, rzf, PRxy[r]);
           emit(FD_PR, raw, SC_PR, w1, n - 1, r);
         }
         if (NEED_B) {
@@ -481,13 +509,29 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
           }
           if (H_CHI) {
             const double gz = dbz * dbz;
-            const double raw = fma(gz, rdz2, CHacc[r]);
-            CHacc[r] = fma(gz, rdz2, CHxy[r]);
+            double raw;
+            if (!STR) {
+              raw = fma(gz, rdz2, CHacc[r]);
+              CHacc[r] = fma(gz, rdz2, CHxy[r]);
+            } else {
+              const double gw = gz * rzf;                    // Az dz_f (db/dz)^2 / (dx dy)
+              raw = fma(rzc1, Gzp[r] + gw, CHacc[r]);
+              CHacc[r] = CHxy[r];
+              Gzp[r] = gw;
+            }
             emit(FD_CHI, raw, SC_CHI, w1, n - 1, r);
           }
           if (H_CDF) {
-            const double raw = bp[r] * fma(-dbz, rdz2, CDacc[r]);
-            CDacc[r] = fma(dbz, rdz2, CDxy[r]);
+            double raw;
+            if (!STR) {
+              raw = bp[r] * fma(-dbz, rdz2, CDacc[r]);
+              CDacc[r] = fma(dbz, rdz2, CDxy[r]);
+            } else {
+              const double gl = dbz * rzf;                   // db/dz at face n
+              raw = bp[r] * fma(rzc1, Gcp[r] - gl, CDacc[r]);
+              CDacc[r] = CDxy[r];
+              Gcp[r] = gl;
+            }
             emit(FD_CDF, raw, SC_CDF, w1, n - 1, r);
           }
         }
@@ -501,11 +545,11 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
         }
         if (H_ADV) {
           // faces of plane n-1: F = velocity x flux divergence (the common 1/8 is the diagnostic's scale factor)
-          const double Fu = up[r] * fma(P13[r] - P13p[r], rdz, dU[r]);
-          const double Fv = vp[r] * fma(P23[r] - P23p[r], rdz, dV[r]);
+          const double Fu = up[r] * fma(P13[r] - P13p[r], rzc1, dU[r]);
+          const double Fv = vp[r] * fma(P23[r] - P23p[r], rzc1, dV[r]);
           const double wsum = wp[r] + wc[r];
           const double Wwp = wsum * wsum;                                 // Ww at cell plane n-1
-          const double Fw = wp[r] * fma(Wwp - Wwpp[r], rdz, dW[r]);      // face n-1
+          const double Fw = wp[r] * fma(Wwp - Wwpp[r], rzf1, dW[r]);     // face n-1
           // ADV(n-2) = 1/8 [Fu + FuE + Fv + FvN + Fw(n-2) + Fw(n-1)]
           const double raw = (Apart[r] + fvn) + Fw;
           const double FuE = __shfl_down_sync(FULLMASK, Fu, 1);
@@ -514,7 +558,8 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
           Wwpp[r] = Wwp;
           dU[r] = fma(Uu[r] - UuW[r], rdx, (p12n - P12[r]) * rdy);
           dV[r] = fma(P12E[r] - P12[r], rdx, (Vv[r] - VvS[r]) * rdy);
-          dW[r] = fma(P13E[r] - P13[r], rdx, (p23n - P23[r]) * rdy);
+          dW[r] = fma(P13E[r] - P13w[r], rdx, (p23n - P23w[r]) * rdy);
+          if (STR) dW[r] *= rzf;                                          // / dz_f of face n (V_ccf)
           P13p[r] = P13[r]; P23p[r] = P23[r];
           emit(FD_ADV, raw, SC_ADV, w2, n - 2, r);
         }
@@ -529,7 +574,7 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
           Wwpp[r] = Wwp;
           dU[r] = fma(Uu[r] - UuW[r], rdx, (p12n - P12[r]) * rdy);
           dV[r] = fma(P12E[r] - P12[r], rdx, (Vv[r] - VvS[r]) * rdy);
-          dW[r] = fma(P13E[r] - P13[r], rdx, (p23n - P23[r]) * rdy);
+          dW[r] = fma(P13E[r] - P13w[r], rdx, (p23n - P23w[r]) * rdy);
           P13p[r] = P13[r]; P23p[r] = P23[r];
         }
       }
@@ -641,6 +686,19 @@ static int setup_variant(ocb_fused_plan* fp, bool out) {
   return OCB_OK;
 }
 
+// stretched z: the all-terms field / cell-integral kernel with per-plane metrics (always the OUT = true form; a plan without
+// output fields simply has no destinations)
+template <int MASK, int NW, int RY, int NS>
+static int setup_variant_stretched(ocb_fused_plan* fp) {
+  const int rc = setup_variant<MASK, NW, RY, NS>(fp, true);       // shape bookkeeping and shared-memory size are the same
+  if (rc != OCB_OK) return rc;
+  auto kern = ocb_budget_kernel<MASK, NW, RY, NS, true, true>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  fp->kernel = kern;
+  OCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp->smem));
+  return OCB_OK;
+}
+
 template <int MASK, int NW, int RY, int NS, int MINB, int TWK = TW>
 static int setup_sums(ocb_fused_plan* fp) {
   using G = Geo<NW, RY>;
@@ -720,7 +778,9 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
   *out = nullptr;
   if (getenv("OCB_DISABLE_FUSED")) return OCB_OK;
   // ---- envelope ------------------------------------------------------------------------------------------
-  if (grid->dzc || grid->dzf) return OCB_OK;                                   // regular z only
+  // stretched z: the seven budget terms (no mean-flow operands, no potential vorticity) on the per-plane-metric variant
+  const bool stretched = grid->dzc || grid->dzf;
+  if (stretched && (!SP.g.dzc || !SP.g.dzf || !SP.g.rdzc || !SP.g.rdzf || getenv("OCB_DISABLE_FUSED_STRETCHED"))) return OCB_OK;
   if (grid->H[0] < 2 || grid->H[1] < 2 || grid->H[2] < 2) return OCB_OK;
   if (in->closure.n_nu_fields || in->closure.n_kappa_fields) return OCB_OK;    // constant coefficients only
   int mask = 0;
@@ -731,7 +791,7 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
   // The class-sum kernel (integrals only, x periodic, no potential vorticity) takes the dissipation of u and of u - U side by
   // side (FD_EPS / FD_EPSP) and the turbulent kinetic energy; the cell-exact kernel one dissipation request and no TKE.
   for (int r = 0; r < n; ++r) any_outq = any_outq || SP.req[r].out;
-  bool sums_convention = !any_outq && grid->topo[0] == OCB_PERIODIC && !getenv("OCB_FUSED_CELL_INTEGRALS");
+  bool sums_convention = !any_outq && !stretched && grid->topo[0] == OCB_PERIODIC && !getenv("OCB_FUSED_CELL_INTEGRALS");
   for (int r = 0; r < n; ++r) if (reqs[r].diag == OCB_DIAG_EPV) sums_convention = false;
   for (int r = 0; r < n; ++r) {
     int d = fused_diag_index(reqs[r].diag);
@@ -772,6 +832,7 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
     if (R.slot >= 0) { if (which_slot[d] >= 0) return OCB_OK; which_slot[d] = r; }
     mask |= 1 << d;
   }
+  if (stretched && ((mask & ~FD_BUDGET) || any_pert)) return OCB_OK;
   if ((mask & (1 << FD_EPV)) && cell_req >= 0 && (SP.req[cell_req].lo[2] != 1 || SP.req[cell_req].hi[2] != grid->N[2])) return OCB_OK;
   const double *Uz = nullptr, *Vz = nullptr, *Wz = nullptr;
   if (any_pert) {
@@ -822,7 +883,12 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
   // OCB_SUMS_CONFIG="NW,RY,NS,MINB" picks another compiled shape of the all-terms kernel for tuning runs.
   const bool sums = sums_convention;
   const int njy = SP.req[0].hi[1] - SP.req[0].lo[1] + 1;
-  if (sums) {
+  if (stretched) {
+    if ((mask & ~VEL) == 0) rc = setup_variant_stretched<VEL, 8, 2, 3>(fp);
+    else if ((mask & ~VELP) == 0) rc = setup_variant_stretched<VELP, 8, 2, 3>(fp);
+    else if ((mask & ~VELB) == 0) rc = setup_variant_stretched<VELB, 8, 2, 3>(fp);
+    else rc = setup_variant_stretched<ALL, 8, 2, 3>(fp);
+  } else if (sums) {
     const char* sc = getenv("OCB_SUMS_CONFIG");
     int a = 0, b = 0, c = 0, d = 0;
     if (sc) sscanf(sc, "%d,%d,%d,%d", &a, &b, &c, &d);
@@ -917,9 +983,10 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
   P.kchunk = kchunk;
   P.nchunks = (nz_win + kchunk - 1) / kchunk;
   fp->nblocks = tiles * P.nchunks;
-  P.rdx = 1.0 / grid->d[0]; P.rdy = 1.0 / grid->d[1]; P.rdz = 1.0 / grid->d[2];
+  P.rdx = 1.0 / grid->d[0]; P.rdy = 1.0 / grid->d[1]; P.rdz = stretched ? 1.0 : 1.0 / grid->d[2];
   P.nu = in->closure.nu_const; P.kappa = in->closure.kappa_const; P.ghat_z = in->ghat[2];
-  P.V = grid->d[0] * grid->d[1] * grid->d[2];
+  P.V = stretched ? grid->d[0] * grid->d[1] : grid->d[0] * grid->d[1] * grid->d[2];      // stretched: dz_c is the cell's integral weight
+  P.dzc = SP.g.dzc; P.dzf = SP.g.dzf; P.rdzc = SP.g.rdzc; P.rdzf = SP.g.rdzf;
   P.nslots = SP.nslots;
   P.Uz = Uz; P.Vz = Vz; P.Wz = Wz; P.eps_pert = eps_pert ? 1 : 0;
   for (int a = 0; a < 3; ++a) P.os[a] = os[a];

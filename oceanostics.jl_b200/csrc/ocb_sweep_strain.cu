@@ -154,6 +154,7 @@ ocb_strain_kernel(const __grid_constant__ StrainParams<T> P) {
   int s = 0, par = 0;
   // z metrics: a window of ZC planes is staged in shared memory by the first warp (a global load consumed right
   // after the barrier would stall every warp of the block at once, once per plane)
+#pragma unroll 2
   for (int n = n_first; n <= n_last; ++n) {
     const int zi = (n - n_first) % ZC;
     if (zi == 0 && tid < ZC) {

@@ -60,6 +60,45 @@ def test_fused_budget_matches_oracle(size):
         assert abs(integ - K.integral(w_, st.og, "ccc")) <= 1e-12 * integral_scale(st.og, w_, "ccc"), op.name
 
 
+@pytest.mark.parametrize("size", [(64, 48, 40), (34, 22, 9), (32, 11, 4)], ids=str)
+@pytest.mark.parametrize("topology", [("P", "P", "B"), ("P", "B", "B")], ids=lambda t: "".join(t))
+def test_fused_budget_stretched_z_matches_oracle(size, topology):
+    """The per-plane-metric variant of the budget kernel (stretched z, the reference's tanh-like test grid of
+    test/test_utils.jl:17-24): all seven terms as fields and as integrals against the oracle's area / volume weighted forms,
+    rtol 1e-12 -- dz_f of the face in the strain edges and tracer gradients, dz_c of the cell in the divergences and the integral
+    weights, dz_c-weighted advecting transports in the w equation."""
+    st = State(size=size, stretched=True, device="cuda", topology=topology)
+    ops, oc = budget(st)
+    grp, vals, ints = run(ops)
+    assert grp.plan.variant == 1
+    want = oracle_budget(st, oc)
+    for op, g, w_, integ in zip(ops, vals, want, ints):
+        assert_close(g, w_, 1e-12, op.name)
+        assert abs(integ - K.integral(w_, st.og, "ccc")) <= 1e-12 * integral_scale(st.og, w_, "ccc"), op.name
+    # integrals only (no destinations), and a subset
+    grp, _, ints2 = run(ops, fields=False)
+    assert grp.plan.variant == 1
+    for a, b_, w_ in zip(ints, ints2, want):
+        assert abs(a - b_) <= 1e-13 * integral_scale(st.og, w_, "ccc")
+    for subset in ([1, 4], [0, 1, 2, 4], [1, 3, 5, 6]):          # velocity-only, + pressure, + tracer variants
+        grp, vals, _ = run([ops[q] for q in subset], integrals=False)
+        assert grp.plan.variant == 1
+        for q, g in zip(subset, vals):
+            assert_close(g, want[q], 1e-12, ops[q].name)
+
+
+def test_fused_budget_stretched_z_matches_generic_kernel_at_size():
+    st = State(size=(128, 96, 64), stretched=True, device="cuda")
+    ops, _ = budget(st)
+    grp, vals, ints = run(ops)
+    assert grp.plan.variant == 1
+    grp0, vals0, ints0 = run(ops, disable_fused=True)
+    assert grp0.plan.variant in (0, 4)
+    for op, a, b_, ia, ib in zip(ops, vals, vals0, ints, ints0):
+        assert_close(a, b_, 1e-12, op.name)
+        assert abs(ia - ib) <= 1e-12 * max(abs(ia), abs(ib), float(np.abs(b_).sum()) * 1e-6), op.name
+
+
 def test_fused_integrals_only_and_subsets():
     st = State(size=(48, 40, 20), device="cuda")
     ops, oc = budget(st)
@@ -111,7 +150,7 @@ def test_budget_kernel_envelope():
     st = State(size=(40, 24, 18), stretched=True, device="cuda")
     ops, _ = budget(st)
     grp, _, _ = run(ops, fields=False)
-    assert grp.plan.variant == 4          # stretched z: dissipation on the velocity-gradient kernel, the rest generic
+    assert grp.plan.variant == 1          # stretched z, constant coefficients: the per-plane-metric variant of the budget kernel
     st = State(size=(40, 24, 18), device="cuda")
     oc, pc = st.closures()["smagorinsky_like"]
     m = st.model(closure=pc)
