@@ -87,6 +87,30 @@ def run_secondary(ocb, torch, run, peak, steps=5):
         out["config2"] = {"error": repr(e)[:300]}
     gc.collect()
     torch.cuda.empty_cache()
+    # ---- the KE + tracer-variance budget on a stretched z axis (the grid of config 4 in Float64, constant coefficients) ----
+    try:
+        n = 512
+        k = np.arange(n + 1)
+        zf = -np.tanh(2.0 * (1 - k / n)) / np.tanh(2.0)
+        grid = ocb.RectilinearGrid((n, n, n), x=(0, 1), y=(0, 1), z=zf, device=dev)
+        m = ocb.NonhydrostaticModel(grid, closure=ocb.Closure(nu=1e-6, kappa=1e-7))
+        for f in (m.velocities.u, m.velocities.v, m.velocities.w, m.tracers.b, m.pressures.pNHS):
+            f.interior.copy_(torch.randn(f.interior.shape, device=dev, dtype=torch.float64))
+        m.fill_halo_regions()
+        ops = budget_ops(ocb, m)
+        for key, members, what in (("stretched_budget_integrals", [ocb.Integral(o) for o in ops], "7 integrals"),
+                                   ("stretched_budget_fields", [ocb.Integral(o) for o in ops] + [ocb.Field(o) for o in ops], "7 integrals + 7 fields")):
+            grp = ocb.FusedDiagnostics(*members)
+            ms = _timed(torch, grp.plan.execute, reps=steps)
+            out[key] = _entry(ms, n ** 3, grp.plan.algorithmic_bytes / n ** 3, peak, variant=VARIANTS.get(grp.plan.variant),
+                              workload=f"512^3 F64, stretched z (tanh faces), constant nu / kappa: KE + tracer-variance budget, {what}, one sweep "
+                                       "(per-plane-metric variant of the budget kernel)")
+            del grp
+        del ops, m, grid
+    except Exception as e:  # pragma: no cover
+        out["stretched_budget"] = {"error": repr(e)[:300]}
+    gc.collect()
+    torch.cuda.empty_cache()
     # ---- config 4: 768x768x384 Float32, stretched z, eddy-viscosity closures: eps + |S| fields ---------------------------
     try:
         Nx, Ny, Nz = 768, 768, 384

@@ -244,6 +244,16 @@ static int finish_plan(ocb_plan* pl, const ocb_grid* grid, const ocb_sweep_input
     else gr[ng++] = reqs[r];
   }
   const bool stretched_z = grid->dzc || grid->dzf;
+  if (in->closure.n_nu_fields || in->closure.n_kappa_fields) {
+    // eddy-viscosity / diffusivity fields: the budget kernels keep the closure-independent terms (K, ADV, PR, w b); the
+    // dissipation goes to the velocity-gradient kernel, the tracer-variance terms to the generic one
+    int kept = 0;
+    for (int r = 0; r < nf; ++r) {
+      const int dg = fr[r].diag;
+      if (dg == OCB_DIAG_EPS || dg == OCB_DIAG_CHI || dg == OCB_DIAG_CDIFF) gr[ng++] = fr[r]; else fr[kept++] = fr[r];
+    }
+    nf = kept;
+  }
   for (int attempt = 0; attempt < 4 && nf > 0 && !pl->fused; ++attempt) {
     if (attempt >= 1) {
       // the budget kernels declined the set: retry without the term with the narrowest envelope -- first the potential

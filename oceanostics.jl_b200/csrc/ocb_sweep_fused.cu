@@ -782,7 +782,8 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
   const bool stretched = grid->dzc || grid->dzf;
   if (stretched && (!SP.g.dzc || !SP.g.dzf || !SP.g.rdzc || !SP.g.rdzf || getenv("OCB_DISABLE_FUSED_STRETCHED"))) return OCB_OK;
   if (grid->H[0] < 2 || grid->H[1] < 2 || grid->H[2] < 2) return OCB_OK;
-  if (in->closure.n_nu_fields || in->closure.n_kappa_fields) return OCB_OK;    // constant coefficients only
+  // eddy-viscosity / diffusivity fields: only the closure-independent terms (K, ADV, PR, w b) -- checked below, once the mask is known
+  const bool closure_fields = in->closure.n_nu_fields || in->closure.n_kappa_fields;
   int mask = 0;
   int which_out[FD_N], which_slot[FD_N];     // a diagnostic may appear twice: once as a Field, once as an Integral
   for (int d = 0; d < FD_N; ++d) which_out[d] = which_slot[d] = -1;
@@ -833,6 +834,8 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
     mask |= 1 << d;
   }
   if (stretched && ((mask & ~FD_BUDGET) || any_pert)) return OCB_OK;
+  constexpr int CLOSURE_TERMS = (1 << FD_EPS) | (1 << FD_EPSP) | (1 << FD_CHI) | (1 << FD_CDF);
+  if (closure_fields && (mask & CLOSURE_TERMS)) return OCB_OK;                  // those go to the velocity-gradient / generic kernels
   if ((mask & (1 << FD_EPV)) && cell_req >= 0 && (SP.req[cell_req].lo[2] != 1 || SP.req[cell_req].hi[2] != grid->N[2])) return OCB_OK;
   const double *Uz = nullptr, *Vz = nullptr, *Wz = nullptr;
   if (any_pert) {

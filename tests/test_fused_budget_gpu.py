@@ -158,6 +158,25 @@ def test_budget_kernel_envelope():
     assert grp.plan.variant == 3          # eddy-viscosity field: velocity-gradient kernel
 
 
+@pytest.mark.parametrize("stretched", [False, True], ids=["regular", "stretched"])
+def test_les_closure_budget_splits_over_the_pipelined_kernels(stretched):
+    """Eddy-viscosity closures (a nu_e / kappa_e field): the closure-independent terms (K, ADV, PR, w b) stay on the budget kernel, the
+    dissipation goes to the velocity-gradient kernel, the tracer-variance terms to the generic one -- one plan, three launches,
+    every term against the oracle."""
+    st = State(size=(48, 40, 20), stretched=stretched, device="cuda")
+    ops, oc = budget(st, closure="smagorinsky_like")
+    grp, vals, ints = run(ops)
+    assert grp.plan.variant == 6
+    want = oracle_budget(st, oc)
+    for op, g, w_, integ in zip(ops, vals, want, ints):
+        assert_close(g, w_, 1e-12, op.name)
+        assert abs(integ - K.integral(w_, st.og, "ccc")) <= 1e-12 * integral_scale(st.og, w_, "ccc"), op.name
+    grp, vals, _ = run(ops[:5], integrals=False)                 # the KE budget alone: no generic launch
+    assert grp.plan.variant == 5
+    for op, g, w_ in zip(ops[:5], vals, want[:5]):
+        assert_close(g, w_, 1e-12, op.name)
+
+
 def test_y_and_z_windows_tile_the_domain():
     """Integral(op, indices=...) over y strips / z slabs (the pieces the overlapped multi-GPU step and the host-streamed
     path sweep separately) add up to the whole-domain integrals, all on the pipelined kernel."""

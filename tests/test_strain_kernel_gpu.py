@@ -48,7 +48,7 @@ def test_velocity_gradient_family_matches_oracle_f64(size, closure, stretched):
     # subsets compile to their own edge families: each alone, integrals only
     for nm in NAMES:
         one = _group([cases[nm][1]], fields=False)
-        budget_takes_it = nm == "DissipationRate" and closure == "scalar" and not stretched and size[0] % 2 == 0
+        budget_takes_it = nm == "DissipationRate" and closure == "scalar" and size[0] % 2 == 0     # regular or stretched z
         assert one.plan.variant == (1 if budget_takes_it else kv)
         want, loc = cases[nm][2], cases[nm][3]
         assert abs(one.integrals()[0] - K.integral(want, st.og, loc)) <= 1e-12 * integral_scale(st.og, want, loc), nm
@@ -92,10 +92,11 @@ def test_windows_and_split_plans():
             tot += np.array(grp.integrals())
         for nm, a, b in zip(NAMES, tot, ref):
             assert abs(a - b) <= 1e-12 * integral_scale(st.og, cases[nm][2], "ccc"), nm
-    # stretched z keeps the budget kernel out: |S| and Q on the velocity-gradient kernel, KE and Ri on the generic one
+    # stretched z with an eddy-viscosity closure: |S| and Q on the velocity-gradient kernel, the closure-independent KE on the
+    # budget kernel's per-plane-metric variant, Ro on the generic one
     mixed = ["StrainRateTensorModulus", "KineticEnergy", "QVelocityGradientTensorInvariant", "RossbyNumber"]
     grp = ocb.FusedDiagnostics(*[ocb.Integral(cases[nm][1]) for nm in mixed]).compute()
-    assert grp.plan.variant == 4 and grp.plan.n_launches == 3
+    assert grp.plan.variant == 6 and grp.plan.n_launches == 4
     for nm, integ in zip(mixed, grp.integrals()):
         _, _, want, loc = cases[nm]
         assert abs(integ - K.integral(want, st.og, loc)) <= 1e-12 * integral_scale(st.og, want, loc), nm
