@@ -109,6 +109,9 @@ template <class T, class K> struct FieldKeys {  // the interior of a field (< 2^
     return Cursor{b1 + (i * s0 + j * s1 + k * s2), i, j, dx.d, dy.d, s0, s1 - (long long)dx.d * s0, s2 - (long long)dy.d * s1};
   }
 };
+// ... and the value such a pattern stands for (the epilogues of the uniform-volume reference height read the sorted VALUES)
+__device__ __forceinline__ double value_of_bits(uint64_t u) { return __longlong_as_double((long long)u); }
+__device__ __forceinline__ float value_of_bits(uint32_t u) { return __uint_as_float(u); }
 // the bit pattern of from_key(k): what the last pass of a sort stores when the caller wants values, not keys
 __device__ __forceinline__ uint64_t unkey_bits(uint64_t k) { return (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k; }
 __device__ __forceinline__ uint32_t unkey_bits(uint32_t k) { return (k >> 31) ? (k & 0x7fffffffu) : ~k; }
@@ -187,7 +190,7 @@ __device__ __forceinline__ uint32_t rs_ld_flag(const uint32_t* p) {
 // the pair (the bucketing pass of the reference-height epilogue carries the cell's Psi this way instead of gathering it later).
 struct NoPay2 {
   static constexpr bool ON = false;
-  __device__ __forceinline__ double at(long long) const { return 0.0; }
+  __device__ __forceinline__ double at(long long, uint32_t) const { return 0.0; }
 };
 template <class K, class Pay2 = NoPay2> constexpr size_t rs_scatter_smem() {
   return sizeof(K) * RS_TILE + sizeof(uint32_t) * (RS_TILE + 2 * RS_WARPS * 256 + 256 + RS_WARPS + 8) + (Pay2::ON ? sizeof(double) * RS_TILE : 0);
@@ -393,7 +396,7 @@ __global__ void __launch_bounds__(RS_THREADS, Pay2::ON ? 2 : 3) rs_scatter(const
       for (int q = 0; q < EB; ++q) {
         const int r = r0 + q;
         pay[q] = idx_in ? ((wl + 32 * r) < ntile ? __ldcg(idx_in + tbase + wl + 32 * r) : 0u) : (uint32_t)(tbase + wl + 32 * r);   // no payload array: the key's position
-        p2[q] = (Pay2::ON && (wl + 32 * r) < ntile) ? pay2.at(tbase + wl + 32 * r) : 0.0;
+        p2[q] = (Pay2::ON && (wl + 32 * r) < ntile) ? pay2.at(tbase + wl + 32 * r, (uint32_t)key[q]) : 0.0;
       }
 #pragma unroll
       for (int q = 0; q < EB; ++q) {
@@ -809,7 +812,7 @@ struct UniformSlots {          // faces[m] = z_bot + cum[m-1]/A with cum[m-1] = 
 };
 template <class T, class K> struct BdzOfKeys {       // b*[t] (faces[t+1] - faces[t])
   const K* ks; UniformSlots U;
-  __device__ __forceinline__ double operator()(long long t) const { return (double)from_key(ks[t]) * (U.face(t + 1) - U.face(t)); }
+  __device__ __forceinline__ double operator()(long long t) const { return (double)value_of_bits(ks[t]) * (U.face(t + 1) - U.face(t)); }
 };
 template <class T, class K>
 __global__ void bpe_psi_levels_uniform(const double* __restrict__ psi_incl, const K* __restrict__ ks, long long n, int Nz, UniformSlots U,
@@ -821,7 +824,7 @@ __global__ void bpe_psi_levels_uniform(const double* __restrict__ psi_incl, cons
   while (hi - lo > 1) { const long long mid = (lo + hi) >> 1; if (U.face(mid) <= zeta) lo = mid; else hi = mid; }
   long long m = lo + 1;
   m = m < 1 ? 1 : (m > n ? n : m);
-  psi_level[k] = (m - 1 ? psi_incl[m - 2] : 0.0) + (double)from_key(ks[m - 1]) * (zeta - U.face(m - 1));
+  psi_level[k] = (m - 1 ? psi_incl[m - 2] : 0.0) + (double)value_of_bits(ks[m - 1]) * (zeta - U.face(m - 1));
 }
 template <class T, class K>
 __global__ void bpe_scatter_uniform(const uint32_t* __restrict__ perm, const K* __restrict__ ks, const double* __restrict__ psi_incl, long long n,
@@ -832,7 +835,7 @@ __global__ void bpe_scatter_uniform(const uint32_t* __restrict__ perm, const K* 
   if (t >= n) return;
   const uint32_t cell = perm[t];
   const int i = (int)(cell % Nx), j = (int)((cell / Nx) % Ny), k = (int)(cell / ((long long)Nx * Ny));
-  const T bs = from_key(ks[t]);
+  const T bs = value_of_bits(ks[t]);
   const T zs = (T)U.centre(t);
   zstar[i * zs0 + j * zs1 + k * zs2] = zs;
   if (psid) {
@@ -860,7 +863,7 @@ __global__ void bpe_scatter_bucketed(const uint32_t* __restrict__ cells, const u
   const T zs = (T)U.centre(t);
   zstar[i * zs0 + j * zs1 + k * zs2] = zs;
   if (psid) {
-    const T bs = from_key(__ldg(ks + t));
+    const T bs = value_of_bits(__ldg(ks + t));
     const double ps = (t ? __ldg(psi_incl + t - 1) : 0.0) + (double)bs * ((double)zs - U.face(t));
     psid[i * ps0 + j * ps1 + k * ps2] = (T)(psi_level[k] - ps);
   }
@@ -869,9 +872,10 @@ __global__ void bpe_scatter_bucketed(const uint32_t* __restrict__ cells, const u
 // running sum are read in order: the bucketing pass carries it with the (cell, rank) pair.
 template <class T, class K> struct PsiOfRank {
   static constexpr bool ON = true;
-  const K* ks; const double* psi_incl; UniformSlots U;
-  __device__ __forceinline__ double at(long long t) const {
-    const T bs = from_key(__ldg(ks + t));
+  const K* ks; const double* psi_incl; UniformSlots U; int64_t* perm_out;      // ks: the sorted values (bit patterns)
+  __device__ __forceinline__ double at(long long t, uint32_t cell) const {
+    if (perm_out) perm_out[t] = (int64_t)cell + 1;                             // the 1-based sortperm, written where it is read in order
+    const T bs = value_of_bits(__ldg(ks + t));
     const T zs = (T)U.centre(t);
     return (t ? __ldg(psi_incl + t - 1) : 0.0) + (double)bs * ((double)zs - U.face(t));
   }
@@ -896,7 +900,7 @@ __global__ void bpe_sorted_outputs(const uint32_t* __restrict__ perm, const K* _
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= n) return;
   if (perm_out) perm_out[t] = (int64_t)perm[t] + 1;
-  if (bs_out) bs_out[t] = from_key(ks[t]);
+  if (bs_out) bs_out[t] = value_of_bits(ks[t]);
 }
 
 struct Scratch {
@@ -954,9 +958,12 @@ int bpe_sort3d_uniform(const ocb_grid* g, const ocb_field* b, const ocb_field* z
   P.p = nullptr; P.sx = P.sy = P.sz = 0;
   if (psid && psid->data) { rc = make_fld<T>(*psid, &P, "psi_delta", false); if (rc != OCB_OK) return rc; }
   const unsigned gr = (unsigned)((n + 255) / 256);
-  K* ks; uint32_t* perm;       // keys straight from the field: the first pass of the sort makes them
+  // keys straight from the field (the first pass of the sort makes them); the last pass stores the sorted VALUES -- into the
+  // caller's sorted-buoyancy array when there is one -- and the epilogue reads those
+  K* ks; uint32_t* perm;
   rc = radix_sort_pairs<K, FieldKeys<T, K>>(FieldKeys<T, K>{B.p + (B.sx + B.sy + B.sz), B.sx, B.sy, B.sz, FastDiv((uint32_t)Nx), FastDiv((uint32_t)Ny)}, ka, ia, kb, ib, n, table, tot,
-                                            nblocks, st, &ks, &perm);
+                                            nblocks, st, &ks, &perm, true, reinterpret_cast<K*>(bs_out));
+  const bool bs_done = bs_out && (void*)ks == bs_out;
   if (rc != OCB_OK) return rc;
   UniformSlots U;
   U.z_bot = g->z_bottom; U.A = (g->L[0] * g->L[1] * g->L[2]) / g->L[2];
@@ -974,7 +981,7 @@ int bpe_sort3d_uniform(const ocb_grid* g, const ocb_field* b, const ocb_field* z
     int bits = 0;
     while ((1ll << bits) < n) ++bits;
     const int shift = bits > 8 ? bits - 8 : 0;
-    uint32_t* cells2 = reinterpret_cast<uint32_t*>(ks == ka ? kb : ka);
+    uint32_t* cells2 = reinterpret_cast<uint32_t*>(ks == ka ? kb : ka);        // (the last pass read ka and wrote ks: both scratch pairs are idle)
     uint32_t* ranks2 = (perm == ia) ? ib : ia;
     double* psis2 = (p1 && !getenv("OCB_BPE_GATHER_PSI")) ? S.get<double>(n) : nullptr;     // no room: the gathering scatter
     // the values of a permutation: the digit bases are known without a histogram, so the pass is one chained scatter
@@ -985,7 +992,7 @@ int bpe_sort3d_uniform(const ocb_grid* g, const ocb_field* b, const ocb_field* z
       // with Psi: the pass carries Psi(rank) as a second payload, so the final scatter reads everything in order (the gathers of the
       // sorted key and the running sum at the rank, a 32-byte sector each, were 2.3 ms of the 8.7 at 67 M cells)
       const int rc2 = rs_launch_scatter<uint32_t, true, PtrKeys<uint32_t>, false, PsiOfRank<T, K>>(
-          PtrKeys<uint32_t>{perm}, nullptr, cells2, ranks2, n, shift, bases, nblocks, table, st, PsiOfRank<T, K>{ks, psi, U}, psis2);
+          PtrKeys<uint32_t>{perm}, nullptr, cells2, ranks2, n, shift, bases, nblocks, table, st, PsiOfRank<T, K>{ks, psi, U, perm_out}, psis2);
       if (rc2 != OCB_OK) return rc2;
       bpe_scatter_triples<T><<<gr, 256, 0, st>>>(cells2, ranks2, psis2, n, FastDiv((uint32_t)Nx), FastDiv((uint32_t)Ny), U, psi_level, z1, Z.sx, Z.sy,
                                                  Z.sz, p1, P.sx, P.sy, P.sz);
@@ -994,10 +1001,14 @@ int bpe_sort3d_uniform(const ocb_grid* g, const ocb_field* b, const ocb_field* z
       if (rc2 != OCB_OK) return rc2;
       bpe_scatter_bucketed<T, K><<<gr, 256, 0, st>>>(cells2, ranks2, ks, psi, n, Nx, Ny, U, psi_level, z1, Z.sx, Z.sy, Z.sz, p1, P.sx, P.sy, P.sz);
     }
-    if (perm_out || bs_out) bpe_sorted_outputs<T, K><<<gr, 256, 0, st>>>(perm, ks, n, perm_out, (T*)bs_out);
+    {
+      int64_t* perm_left = (p1 && psis2) ? nullptr : perm_out;                  // (written by the bucketing pass above)
+      T* bs_left = bs_done ? nullptr : (T*)bs_out;
+      if (perm_left || bs_left) bpe_sorted_outputs<T, K><<<gr, 256, 0, st>>>(perm, ks, n, perm_left, bs_left);
+    }
   } else {
     bpe_scatter_uniform<T, K><<<gr, 256, 0, st>>>(perm, ks, psi, n, Nx, Ny, U, psi_level, z1, Z.sx, Z.sy, Z.sz, p1, P.sx, P.sy, P.sz, perm_out,
-                                                  (T*)bs_out);
+                                                  bs_done ? nullptr : (T*)bs_out);
   }
   OCB_CUDA(cudaGetLastError());
   return OCB_OK;
