@@ -42,6 +42,35 @@ def test_radix_sort_is_sorted_stable_and_a_permutation(n, dtype):
     np.testing.assert_array_equal(out.cpu().numpy(), kn[want])
 
 
+def test_chained_scatter_stress():
+    """The chained scatter waits on other tiles' flags and reads their counts behind relaxed loads: many sorts of awkward
+    sizes and digit distributions (all keys equal, two values, few distinct digits, sorted and reversed input, group-boundary
+    tile counts 15/16/17 and 255/256/257 tiles), each checked for order, stability (through the permutation) and content."""
+    g = torch.Generator(device="cuda").manual_seed(20261020)
+    tile = 4096
+    sizes = [tile * t + d for t in (15, 16, 17, 255, 256, 257) for d in (-1, 0, 1)] + [7, 300_001, 1_234_567, 2_500_000]
+    for trial, n in enumerate(sizes * 2):
+        kind = trial % 6
+        if kind == 0:
+            keys = torch.randn(n, generator=g, device="cuda", dtype=torch.float64)
+        elif kind == 1:
+            keys = torch.full((n,), 1.25, device="cuda", dtype=torch.float64)
+        elif kind == 2:
+            keys = (torch.rand(n, generator=g, device="cuda") < 0.5).double() - 0.5
+        elif kind == 3:
+            keys = torch.randint(0, 7, (n,), generator=g, device="cuda").double() * 2.0 ** -20
+        elif kind == 4:
+            keys = torch.arange(n, device="cuda", dtype=torch.float64)
+        else:
+            keys = -torch.arange(n, device="cuda", dtype=torch.float64) * 1e-3
+        out, perm = sort_pairs(keys)
+        assert bool((out[1:] >= out[:-1]).all()), (n, kind)
+        assert bool((keys[perm] == out).all()), (n, kind)
+        same = out[1:] == out[:-1]
+        assert bool((perm[1:][same] > perm[:-1][same]).all()), (n, kind)          # stable: ties keep their input order
+        assert int(perm.sum()) == n * (n - 1) // 2, (n, kind)                      # a permutation
+
+
 def ztol(n, Lz=1.0):
     """z✶ = z_bot + (cumulative volume)/A: the reference accumulates the N sorted volumes sequentially (cumsum!), the
     library with a tree scan; both carry up to ~N eps/2 of rounding relative to the column depth, so heights are
