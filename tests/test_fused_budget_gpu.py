@@ -177,10 +177,28 @@ def test_les_closure_budget_splits_over_the_pipelined_kernels(stretched):
         assert_close(g, w_, 1e-12, op.name)
 
 
-def test_y_and_z_windows_tile_the_domain():
+@pytest.mark.parametrize("stretched", [False, True], ids=["regular", "stretched"])
+def test_windowed_budget_fields_match_the_full_fields(stretched):
+    """Field(op, indices=(:, j-window, k-window)) of all seven terms in one sweep of the pipelined kernel: the window holds
+    exactly the full field's values (the z window of a stretched grid starts at a plane with other metrics than plane 1)."""
+    st = State(size=(64, 40, 30), stretched=stretched, device="cuda")
+    ops, _ = budget(st)
+    _, full, _ = run(ops, integrals=False)
+    win = ocb.FusedDiagnostics(*[ocb.Field(o, indices=(None, (5, 33), (4, 27))) for o in ops]).compute()
+    torch.cuda.synchronize()
+    assert win.plan.variant == 1
+    for o, f, w in zip(ops, full, win.members):
+        a, b = f[:, 4:33, 3:27], w.interior_ijk()
+        assert b.shape == a.shape, o.name
+        assert np.abs(a - b).max() <= 1e-13 * np.abs(a).max(), o.name
+
+
+@pytest.mark.parametrize("stretched", [False, True], ids=["regular", "stretched"])
+def test_y_and_z_windows_tile_the_domain(stretched):
     """Integral(op, indices=...) over y strips / z slabs (the pieces the overlapped multi-GPU step and the host-streamed
-    path sweep separately) add up to the whole-domain integrals, all on the pipelined kernel."""
-    st = State(size=(64, 40, 30), device="cuda")
+    path sweep separately) add up to the whole-domain integrals, all on the pipelined kernel (stretched z: its per-plane-metric
+    variant, whose z slabs start and end at planes with different metrics)."""
+    st = State(size=(64, 40, 30), stretched=stretched, device="cuda")
     ops, _ = budget(st)
     ref = ocb.FusedDiagnostics(*[ocb.Integral(o) for o in ops]).compute().integrals()
     for windows in ([(None, (1, 2), None), (None, (3, 38), None), (None, (39, 40), None)],
