@@ -26,7 +26,13 @@
 // tile (odd x halo), else 36 (one spare column either side of the aligned box start, as in ocb_budget_kernel).
 constexpr int sums_tile_elems(int tw, int tr) { return ((tw * tr * 8 + 127) / 128) * 128 / 8; }   // 128-byte aligned field tiles
 
-template <int MASK, int NW, int RY, int NS, int MINB, int TWK>
+// STR = true: z is a stretched axis (the seven budget terms only).  The class sums then carry per-plane weights -- the cell's dz_c
+// for the items of a cell plane, dz_f of the face for the fcf / cff strain edges, (dz_c(n-1) + dz_c(n)) / 2 for the z-face
+// items of K and w b, 1 / dz_f and 1 / dz_c where a squared z difference stays divided once after the volume weight cancels one
+// factor -- and the by-parts advection splits its fcf / cff products in two: the u (v) equation's z part, whose cell weight
+// cancels the 1 / dz_c of the divergence, and the w equation's x (y) part with the dz_c-weighted advecting transport (the same
+// forms as ocb_budget_kernel<.., STR>, re-associated; oracle/kernels.py has the reference's area / volume weighted formulas).
+template <int MASK, int NW, int RY, int NS, int MINB, int TWK, bool STR = false>
 __global__ void __launch_bounds__(NW * 32, MINB)
 ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_constant__ CUtensorMap mu, const __grid_constant__ CUtensorMap mv,
                        const __grid_constant__ CUtensorMap mw, const __grid_constant__ CUtensorMap mb, const __grid_constant__ CUtensorMap mp) {
@@ -189,6 +195,18 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
                     GVc = 0.5 * (a - Vn1); GVp = 0.5 * (Vn - d); dVz = Vn - Vn1; }
         if (P.Wz) { const double a = __ldg(P.Wz + n + 1), d = __ldg(P.Wz + n - 1); Wn = __ldg(P.Wz + n); GWc = a - Wn; GWp = Wn - d; dWz = GWp; }
       }
+      // z metrics of this step (STR): cell planes n, n-1, n-2 and faces n, n-1; G* = the window / chunk classes times dz_c
+      double c0 = 1.0, c1 = 1.0, c2 = 1.0, dzf0 = 1.0, rzf0 = rdz, rzf1 = rdz, rzc1 = rdz;
+      if (STR) {
+        const int lo = 1 - P.hz, hi = P.Nz + P.hz;
+        const int q0 = min(max(n, lo), hi), q1 = min(max(n - 1, lo), hi), q2 = min(max(n - 2, lo), hi);
+        c0 = __ldg(P.dzc + q0); c1 = __ldg(P.dzc + q1); c2 = __ldg(P.dzc + q2);
+        dzf0 = __ldg(P.dzf + q0); rzf0 = __ldg(P.rdzf + q0); rzf1 = __ldg(P.rdzf + q1); rzc1 = __ldg(P.rdzc + q1);
+      }
+      const double G0 = g0 * c0, G1 = g1 * c1, G2 = g2 * c2;
+      const double hzw = 0.5 * (c0 + c1);                               // FAST: volume weight of a z-face item
+      const double rho0 = hzw * rzf0, rho1 = (0.5 * (c1 + c2)) * rzf1;  // (dz_c(n-1) + dz_c(n)) / (2 dz_f(n)): one for midpoint centres
+      const double hzK = 0.5 * (G0 + G1), rho0g = hzK * rzf0, rho1g = (0.5 * (G1 + G2)) * rzf1;   // GEN: the same with the classes
       // one row of this thread at step n.  FAST (compile-time tag): every class weight is the interior one
       auto do_row = [&](auto fast_tag, const int r) {
         constexpr bool FAST = decltype(fast_tag)::value;
@@ -202,14 +220,15 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
         double S12 = 0.0, S13 = 0.0, S23 = 0.0;
         if (NEED_S) {
           S12 = fma(dvx, rdx, duy * rdy);
-          S13 = fma(dwx, rdx, duz * rdz);
-          S23 = fma(dwy, rdy, dvz * rdz);
+          S13 = fma(dwx, rdx, duz * (STR ? rzf0 : rdz));
+          S23 = fma(dwy, rdy, dvz * (STR ? rzf0 : rdz));
         }
-        double P12 = 0.0, P13 = 0.0, P23 = 0.0, Uu = 0.0, Vv = 0.0, Ww = 0.0;
+        double P12 = 0.0, P13 = 0.0, P23 = 0.0, Uu = 0.0, Vv = 0.0, Ww = 0.0, P13w = 0.0, P23w = 0.0;
         if (H_ADV) {
           P12 = (vw + vc[r]) * (us + uc[r]);
           P13 = (ww + wc[r]) * (up[r] + uc[r]);
           P23 = (ws + wc[r]) * (vp[r] + vc[r]);
+          if (STR) { P13w = (ww + wc[r]) * fma(c1, up[r], c0 * uc[r]); P23w = (ws + wc[r]) * fma(c1, vp[r], c0 * vc[r]); }
           const double su = uc[r] + ue, sv = vc[r] + vn, sw = wp[r] + wc[r];
           Uu = su * su; Vv = sv * sv; Ww = sw * sw;
         }
@@ -222,13 +241,35 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
           const double bn = (r < RY - 1) ? bc[r < RY - 1 ? r + 1 : 0] : bN;
           const double de = Tb[o + 1] - bc[r], dn = bn - bc[r];
           const double cdxy = fma(dbx - de, rdx2, (dby - dn) * rdy2);
-          lap = fma(-dbz, rdz2, CDacc[r]);                 // Laplacian (sign of div q) of the cell below, closed by this face
-          CDacc[r] = fma(dbz, rdz2, cdxy);
+          if (!STR) {
+            lap = fma(-dbz, rdz2, CDacc[r]);               // Laplacian (sign of div q) of the cell below, closed by this face
+            CDacc[r] = fma(dbz, rdz2, cdxy);
+          } else {                                         // dz_c x the Laplacian: dz_c (in-plane part) + the two face gradients
+            const double gl = dbz * rzf0;
+            lap = CDacc[r] - gl;
+            CDacc[r] = fma(c0, cdxy, gl);
+          }
         }
         // perturbations about the profiles: this plane's (u', v' at level n, w' at face n) and the previous plane's u', v'
         const double ucq = uc[r] - Un, vcq = vc[r] - Vn, wcq = wc[r] - Wn, upq = up[r] - Un1, vpq = vp[r] - Vn1;
         const double S13q = H_EPSP ? fma(-rdz, dUz, S13) : 0.0, S23q = H_EPSP ? fma(-rdz, dVz, S23) : 0.0, dwzq = dwz - dWz;
-        if (FAST) {
+        if (FAST && STR) {
+          if (H_EPS) {
+            aEe = fma(c0 * S12, S12, aEe); aEe = fma(dzf0 * S13, S13, aEe); aEe = fma(dzf0 * S23, S23, aEe);
+            aEx = fma(c0 * ax, ax, aEx); aEy = fma(c0 * ay, ay, aEy); aEz = fma(rzc1 * dwz, dwz, aEz);
+          }
+          if (H_ADV) {
+            aAe = fma(c0 * P12, S12, aAe);
+            aAe = fma(P13w, (rho0 * rdx) * dwx, aAe); aAe = fma(P13, duz, aAe);
+            aAe = fma(P23w, (rho0 * rdy) * dwy, aAe); aAe = fma(P23, dvz, aAe);
+            aAx = fma(c0 * Uu, ax, aAx); aAy = fma(c0 * Vv, ay, aAy); aAz = fma(Ww, fma(rho0, wc[r], -(rho1 * wp[r])), aAz);
+          }
+          if (H_K) { aK = fma(c0 * uc[r], uc[r], aK); aK = fma(c0 * vc[r], vc[r], aK); aK = fma(hzw * wc[r], wc[r], aK); }
+          if (H_PR) { aPx = fma(c0 * uc[r], dpx, aPx); aPy = fma(c0 * vc[r], dpy, aPy); aPz = fma(rho0 * wc[r], dpz, aPz); }
+          if (H_WB) aW = fma(hzw * wc[r], bp[r] + bc[r], aW);
+          if (H_CHI) { aCx = fma(c0 * dbx, dbx, aCx); aCy = fma(c0 * dby, dby, aCy); aCz = fma(rzf0 * dbz, dbz, aCz); }
+          if (H_CDF) aD = fma(bp[r], lap, aD);
+        } else if (FAST) {
           if (H_EPSP) {
             aEeP = fma(S12, S12, aEeP); aEeP = fma(S13q, S13q, aEeP); aEeP = fma(S23q, S23q, aEeP);
             aEzP = fma(dwzq, dwzq, aEzP);
@@ -253,6 +294,35 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
           if (H_WB) aW = fma(wc[r], bp[r] + bc[r], aW);
           if (H_CHI) { aCx = fma(dbx, dbx, aCx); aCy = fma(dby, dby, aCy); aCz = fma(dbz, dbz, aCz); }
           if (H_CDF) aD = fma(bp[r], lap, aD);
+        } else if (lane_ok && STR) {
+          // ---- GEN on a stretched axis: the class weights of the regular form below, times the metrics of their items ----
+          const int j = j0 + jr0 + r;
+          const double al = (ring || (j >= P.jy_lo && j <= P.jy_hi)) ? 1.0 : 0.0, be = (ring || (j - 1 >= P.jy_lo && j - 1 <= P.jy_hi)) ? 1.0 : 0.0,
+                       an = (ring || (j + 1 >= P.jy_lo && j + 1 <= P.jy_hi)) ? 1.0 : 0.0;
+          const double hy = 0.5 * (al + be), hyn = 0.5 * (al + an);
+          const double hz = 0.5 * (g0 + g1);                               // cells sharing face n, halved
+          if (H_EPS) {
+            aEe = fma(hy * G0 * S12, S12, aEe); aEe = fma(al * (hz * dzf0) * S13, S13, aEe); aEe = fma(hy * (hz * dzf0) * S23, S23, aEe);
+            aEz = fma(al * g1 * rzc1 * dwz, dwz, aEz);
+            aEx = fma(al * G0 * ax, ax, aEx); aEy = fma(al * G0 * ay, ay, aEy);
+          }
+          if (H_ADV) {
+            aAe = fma(G0 * P12, fma(rdx * hy, dvx, rdy * (al * uc[r] - be * us)), aAe);
+            aAe = fma(al * P13w, (rdx * rho0g) * dwx, aAe); aAe = fma(al * P13, g0 * uc[r] - g1 * up[r], aAe);
+            aAe = fma(P23w, (rdy * rho0g) * (al * wc[r] - be * ws), aAe); aAe = fma(hy * P23, g0 * vc[r] - g1 * vp[r], aAe);
+            aAx = fma(al * G0 * Uu, ax, aAx);
+            aAy = fma(G0 * Vv, hyn * vn - hy * vc[r], aAy);
+            if (!ring && j == P.jy_lo) {
+              const double vs = r ? vc[r > 0 ? r - 1 : 0] : vS;
+              aAy = fma(G0 * ((vs + vc[r]) * (vs + vc[r])), 0.5 * vc[r], aAy);
+            }
+            aAz = fma(al * Ww, rho0g * wc[r] - rho1g * wp[r], aAz);
+          }
+          if (H_K) { aK = fma(al * G0 * uc[r], uc[r], aK); aK = fma(hy * G0 * vc[r], vc[r], aK); aK = fma(al * hzK * wc[r], wc[r], aK); }
+          if (H_PR) { aPx = fma(al * G0 * uc[r], dpx, aPx); aPy = fma(hy * G0 * vc[r], dpy, aPy); aPz = fma(al * rho0g * wc[r], dpz, aPz); }
+          if (H_WB) aW = fma(al * hzK * wc[r], bp[r] + bc[r], aW);
+          if (H_CHI) { aCx = fma(al * G0 * dbx, dbx, aCx); aCy = fma(hy * G0 * dby, dby, aCy); aCz = fma(al * (hz * rzf0) * dbz, dbz, aCz); }
+          if (H_CDF) aD = fma(al * g1 * bp[r], lap, aD);
         } else if (lane_ok) {
           // ---- GEN: a window-edge row or plane (or a partly filled x tile): explicit class weights (all one elsewhere) ----
           const int j = j0 + jr0 + r;
@@ -322,12 +392,13 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
   double acc[FD_N];
 #pragma unroll
   for (int d = 0; d < FD_N; ++d) acc[d] = 0.0;
+  const double fz = STR ? 1.0 : rdz, fz2 = STR ? 1.0 : rdz2;          // STR: the z metrics are inside the sums
   acc[FD_K] = 0.5 * aK;
-  acc[FD_ADV] = -0.25 * (aAe + (rdx * aAx + rdy * aAy + rdz * aAz));
-  acc[FD_PR] = rdx * aPx + rdy * aPy + rdz * aPz;
+  acc[FD_ADV] = -0.25 * (aAe + (rdx * aAx + rdy * aAy + fz * aAz));
+  acc[FD_PR] = rdx * aPx + rdy * aPy + fz * aPz;
   acc[FD_WB] = 0.5 * P.ghat_z * aW;
-  acc[FD_EPS] = P.nu * (aEe + 2.0 * (rdx2 * aEx + rdy2 * aEy + rdz2 * aEz));
-  acc[FD_CHI] = 2.0 * P.kappa * (rdx2 * aCx + rdy2 * aCy + rdz2 * aCz);
+  acc[FD_EPS] = P.nu * (aEe + 2.0 * (rdx2 * aEx + rdy2 * aEy + fz2 * aEz));
+  acc[FD_CHI] = 2.0 * P.kappa * (rdx2 * aCx + rdy2 * aCy + fz2 * aCz);
   acc[FD_CDF] = 2.0 * P.kappa * aD;
   acc[FD_EPSP] = P.nu * (aEeP + 2.0 * (rdx2 * aEx + rdy2 * aEy + rdz2 * aEzP));
   acc[FD_TKE] = 0.5 * aKP;

@@ -699,23 +699,23 @@ static int setup_variant_stretched(ocb_fused_plan* fp) {
   return OCB_OK;
 }
 
-template <int MASK, int NW, int RY, int NS, int MINB, int TWK = TW>
+template <int MASK, int NW, int RY, int NS, int MINB, int TWK = TW, bool STR = false>
 static int setup_sums(ocb_fused_plan* fp) {
   using G = Geo<NW, RY>;
   constexpr bool NEED_B = MASK & ((1 << FD_WB) | (1 << FD_CHI) | (1 << FD_CDF)), NEED_P = MASK & (1 << FD_PR);
   constexpr int NF = 3 + (NEED_B ? 1 : 0) + (NEED_P ? 1 : 0);
   fp->nw = NW; fp->ry = RY; fp->ns = NS; fp->mask = MASK; fp->sums = true; fp->minb = MINB; fp->tw = TWK;
   fp->smem = sizeof(double) * ((size_t)NS * NF * sums_tile_elems(TWK, G::TR) + NW) + sizeof(uint64_t) * NS;
-  auto kern = ocb_budget_sums_kernel<MASK, NW, RY, NS, MINB, TWK>;
+  auto kern = ocb_budget_sums_kernel<MASK, NW, RY, NS, MINB, TWK, STR>;
   cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   fp->kernel = kern;
   OCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp->smem));
   return OCB_OK;
 }
 // the default shapes in both tile pitches: 34 columns when every tile starts on a 16-byte boundary (odd x halo)
-template <int MASK, int NW, int RY, int NS, int MINB>
+template <int MASK, int NW, int RY, int NS, int MINB, bool STR = false>
 static int setup_sums_pitch(ocb_fused_plan* fp, bool narrow) {
-  return narrow ? setup_sums<MASK, NW, RY, NS, MINB, 34>(fp) : setup_sums<MASK, NW, RY, NS, MINB, 36>(fp);
+  return narrow ? setup_sums<MASK, NW, RY, NS, MINB, 34, STR>(fp) : setup_sums<MASK, NW, RY, NS, MINB, 36, STR>(fp);
 }
 
 static int make_map(EncodeTiledFn enc, const ocb_field& f, int rows, CUtensorMap* map, int tw = TW) {
@@ -792,7 +792,9 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
   // The class-sum kernel (integrals only, x periodic, no potential vorticity) takes the dissipation of u and of u - U side by
   // side (FD_EPS / FD_EPSP) and the turbulent kinetic energy; the cell-exact kernel one dissipation request and no TKE.
   for (int r = 0; r < n; ++r) any_outq = any_outq || SP.req[r].out;
-  bool sums_convention = !any_outq && !stretched && grid->topo[0] == OCB_PERIODIC && !getenv("OCB_FUSED_CELL_INTEGRALS");
+  // (stretched z: the class-sum form needs all five inputs -- its one compiled variant is the all-terms one)
+  bool sums_convention = !any_outq && grid->topo[0] == OCB_PERIODIC && !getenv("OCB_FUSED_CELL_INTEGRALS") &&
+                         (!stretched || (tma_compatible(in->b, grid) && tma_compatible(in->p, grid) && !getenv("OCB_DISABLE_SUMS_STRETCHED")));
   for (int r = 0; r < n; ++r) if (reqs[r].diag == OCB_DIAG_EPV) sums_convention = false;
   for (int r = 0; r < n; ++r) {
     int d = fused_diag_index(reqs[r].diag);
@@ -886,7 +888,11 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
   // OCB_SUMS_CONFIG="NW,RY,NS,MINB" picks another compiled shape of the all-terms kernel for tuning runs.
   const bool sums = sums_convention;
   const int njy = SP.req[0].hi[1] - SP.req[0].lo[1] + 1;
-  if (stretched) {
+  if (stretched && sums) {
+    const bool narrow = (grid->H[0] & 1) && !getenv("OCB_SUMS_WIDE_TILES");
+    if (njy + 1 <= 4) rc = setup_sums_pitch<ALL, 2, 2, 3, 4, true>(fp, narrow);
+    else rc = setup_sums_pitch<ALL, 4, 4, 3, 2, true>(fp, narrow);
+  } else if (stretched) {
     if ((mask & ~VEL) == 0) rc = setup_variant_stretched<VEL, 8, 2, 3>(fp);
     else if ((mask & ~VELP) == 0) rc = setup_variant_stretched<VELP, 8, 2, 3>(fp);
     else if ((mask & ~VELB) == 0) rc = setup_variant_stretched<VELB, 8, 2, 3>(fp);
