@@ -104,7 +104,7 @@ def run_secondary(ocb, torch, run, peak, steps=5):
             ms = _timed(torch, grp.plan.execute, reps=steps)
             out[key] = _entry(ms, n ** 3, grp.plan.algorithmic_bytes / n ** 3, peak, variant=VARIANTS.get(grp.plan.variant),
                               workload=f"512^3 F64, stretched z (tanh faces), constant nu / kappa: KE + tracer-variance budget, {what}, one sweep "
-                                       "(per-plane-metric variant of the budget kernel)")
+                                       "(per-plane-metric variants of the class-sum / budget kernels)")
             del grp
         del ops, m, grid
     except Exception as e:  # pragma: no cover

@@ -34,8 +34,14 @@ def main():
     glob = {n: torch.randn((Nz + (1 if n == "w" else 0), Ny, Nx), generator=gen, device=dev, dtype=torch.float64) for n in "uvwbp"}
     glob["w"][0].zero_(); glob["w"][-1].zero_()
 
+    # MG_STRETCHED=1: a tanh-stretched z axis -- the same steps then run on the per-plane-metric variants of the kernels
+    zspec = (-1, 0)
+    if os.environ.get("MG_STRETCHED"):
+        kf = np.arange(Nz + 1)
+        zspec = -np.tanh(2.0 * (1 - kf / Nz)) / np.tanh(2.0)
+
     def model_on(lo, hi, full):
-        g = ocb.RectilinearGrid((Nx, hi - lo + 1, Nz), x=(0, 1), y=((lo - 1) / Ny, hi / Ny), z=(-1, 0), device=dev)
+        g = ocb.RectilinearGrid((Nx, hi - lo + 1, Nz), x=(0, 1), y=((lo - 1) / Ny, hi / Ny), z=zspec, device=dev)
         m = ocb.NonhydrostaticModel(g, tracers=("b",), closure=ocb.Closure(nu=1e-3, kappa=1e-4))
         flds = {"u": m.velocities.u, "v": m.velocities.v, "w": m.velocities.w, "b": m.tracers.b, "p": m.pressures.pNHS}
         for n, f in flds.items():

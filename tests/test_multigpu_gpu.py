@@ -247,13 +247,18 @@ def test_slab_filter_self_exchange_equals_periodic_filter(kind):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
-def test_nccl_slabs_match_single_domain():
-    """torchrun x2: NCCL halo exchange + all-reduced integrals equal the single-domain integrals."""
+@pytest.mark.parametrize("stretched", [False, True], ids=["regular", "stretched"])
+def test_nccl_slabs_match_single_domain(stretched):
+    """torchrun x2: NCCL halo exchange + all-reduced integrals equal the single-domain integrals; so do the overlapped, the
+    peer-memory and the ring steps (on a stretched z axis: through the per-plane-metric kernel variants)."""
     import os
     import subprocess
     import sys
     here = os.path.dirname(os.path.abspath(__file__))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29533", os.path.join(here, "multigpu_check.py")]
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    env = dict(os.environ)
+    if stretched:
+        env["MG_STRETCHED"] = "1"
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, env=env)
     assert r.returncode == 0 and "MULTIGPU_CHECK OK" in r.stdout, r.stdout[-3000:]
