@@ -880,6 +880,7 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
   constexpr int VEL = (1 << FD_K) | (1 << FD_ADV) | (1 << FD_EPS);                 // velocity-only terms
   constexpr int VELP = VEL | (1 << FD_PR);                                          // + pressure
   constexpr int VELB = VEL | (1 << FD_WB) | (1 << FD_CHI) | (1 << FD_CDF);          // + tracer
+  constexpr int KAPW = (1 << FD_K) | (1 << FD_ADV) | (1 << FD_PR) | (1 << FD_WB);   // K, ADV, PR, w b
 #define OCB_PICK(M) (any_out ? setup_variant<M, 8, 2, 3>(fp, true) : setup_variant<M, 8, 3, 3>(fp, false))
   constexpr int TKEM = (1 << FD_EPS) | (1 << FD_SP) | (1 << FD_PR) | (1 << FD_K);  // TKE budget about mean profiles
   constexpr int EPVM = 1 << FD_EPV, TKEV = TKEM | EPVM;                            // + Ertel PV (BASELINE config 2)
@@ -915,6 +916,8 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
     else if (!sc && (mask & ~VEL) == 0) rc = setup_sums_pitch<VEL, 8, 3, 3, 1>(fp, narrow);
     else if (!sc && (mask & ~VELP) == 0) rc = setup_sums_pitch<VELP, 8, 3, 3, 1>(fp, narrow);
     else if (!sc && (mask & ~VELB) == 0) rc = setup_sums_pitch<VELB, 8, 3, 3, 1>(fp, narrow);
+    // the closure-independent terms (what the budget kernels keep of a plan with eddy-viscosity / diffusivity fields)
+    else if (!sc && (mask & ~KAPW) == 0) rc = setup_sums_pitch<KAPW, 4, 4, 3, 2>(fp, narrow);
     else if (key == 8331) rc = setup_sums<ALL, 8, 3, 3, 1>(fp);
     else if (key == 8341) rc = setup_sums<ALL, 8, 3, 4, 1>(fp);
     else if (key == 8431) rc = setup_sums<ALL, 8, 4, 3, 1>(fp);

@@ -171,6 +171,10 @@ def test_les_closure_budget_splits_over_the_pipelined_kernels(stretched):
     for op, g, w_, integ in zip(ops, vals, want, ints):
         assert_close(g, w_, 1e-12, op.name)
         assert abs(integ - K.integral(w_, st.og, "ccc")) <= 1e-12 * integral_scale(st.og, w_, "ccc"), op.name
+    grp, _, ints2 = run(ops, fields=False)                       # integrals only: the closure-independent class sums
+    assert grp.plan.variant == 6
+    for op, w_, integ in zip(ops, want, ints2):
+        assert abs(integ - K.integral(w_, st.og, "ccc")) <= 1e-12 * integral_scale(st.og, w_, "ccc"), op.name
     grp, vals, _ = run(ops[:5], integrals=False)                 # the KE budget alone: no generic launch
     assert grp.plan.variant == 5
     for op, g, w_ in zip(ops[:5], vals, want[:5]):
