@@ -185,28 +185,34 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
       const bool in0 = n >= P.kz_lo && n <= P.kz_hi, in1 = (n - 1) >= P.kz_lo && (n - 1) <= P.kz_hi, in2 = (n - 2) >= P.kz_lo && (n - 2) <= P.kz_hi;
       const bool pfast = own && in0 && in1 && in2;
       const double g0 = (own && in0) ? 1.0 : 0.0, g1 = (own && in1) ? 1.0 : 0.0, g2 = (own && in2) ? 1.0 : 0.0;
-      // mean-flow profiles around this plane (uniform loads; a missing profile is a ZeroField)
-      double Un = 0.0, Un1 = 0.0, Vn = 0.0, Vn1 = 0.0, Wn = 0.0, dUz = 0.0, dVz = 0.0, dWz = 0.0;
-      double GUc = 0.0, GUp = 0.0, GVc = 0.0, GVp = 0.0, GWc = 0.0, GWp = 0.0;
-      if (PZ) {
-        if (P.Uz) { const double a = __ldg(P.Uz + n + 1), d = __ldg(P.Uz + n - 2); Un = __ldg(P.Uz + n); Un1 = __ldg(P.Uz + n - 1);
-                    GUc = 0.5 * (a - Un1); GUp = 0.5 * (Un - d); dUz = Un - Un1; }
-        if (P.Vz) { const double a = __ldg(P.Vz + n + 1), d = __ldg(P.Vz + n - 2); Vn = __ldg(P.Vz + n); Vn1 = __ldg(P.Vz + n - 1);
-                    GVc = 0.5 * (a - Vn1); GVp = 0.5 * (Vn - d); dVz = Vn - Vn1; }
-        if (P.Wz) { const double a = __ldg(P.Wz + n + 1), d = __ldg(P.Wz + n - 1); Wn = __ldg(P.Wz + n); GWc = a - Wn; GWp = Wn - d; dWz = GWp; }
-      }
       // z metrics of this step (STR): cell planes n, n-1, n-2 and faces n, n-1; G* = the window / chunk classes times dz_c
-      double c0 = 1.0, c1 = 1.0, c2 = 1.0, dzf0 = 1.0, rzf0 = rdz, rzf1 = rdz, rzc1 = rdz;
+      double c0 = 1.0, c1 = 1.0, c2 = 1.0, dzf0 = 1.0, rzf0 = rdz, rzf1 = rdz, rzfn = rdz, rzc1 = rdz;
       if (STR) {
         const int lo = 1 - P.hz, hi = P.Nz + P.hz;
         const int q0 = min(max(n, lo), hi), q1 = min(max(n - 1, lo), hi), q2 = min(max(n - 2, lo), hi);
         c0 = __ldg(P.dzc + q0); c1 = __ldg(P.dzc + q1); c2 = __ldg(P.dzc + q2);
         dzf0 = __ldg(P.dzf + q0); rzf0 = __ldg(P.rdzf + q0); rzf1 = __ldg(P.rdzf + q1); rzc1 = __ldg(P.rdzc + q1);
+        if (PZ) rzfn = __ldg(P.rdzf + min(max(n + 1, lo), hi));
       }
       const double G0 = g0 * c0, G1 = g1 * c1, G2 = g2 * c2;
       const double hzw = 0.5 * (c0 + c1);                               // FAST: volume weight of a z-face item
       const double rho0 = hzw * rzf0, rho1 = (0.5 * (c1 + c2)) * rzf1;  // (dz_c(n-1) + dz_c(n)) / (2 dz_f(n)): one for midpoint centres
       const double hzK = 0.5 * (G0 + G1), rho0g = hzK * rzf0, rho1g = (0.5 * (G1 + G2)) * rzf1;   // GEN: the same with the classes
+      // mean-flow profiles around this plane (uniform loads; a missing profile is a ZeroField)
+      double Un = 0.0, Un1 = 0.0, Vn = 0.0, Vn1 = 0.0, Wn = 0.0, dUz = 0.0, dVz = 0.0, dWz = 0.0;
+      double GUc = 0.0, GUp = 0.0, GVc = 0.0, GVp = 0.0, GWc = 0.0, GWp = 0.0;
+      if (PZ) {
+        // (STR: the mean shear of a cell is the mean of its two face gradients, and it carries the cell's dz_c as volume weight)
+        if (P.Uz) { const double a = __ldg(P.Uz + n + 1), d = __ldg(P.Uz + n - 2); Un = __ldg(P.Uz + n); Un1 = __ldg(P.Uz + n - 1);
+                    dUz = Un - Un1;
+                    if (!STR) { GUc = 0.5 * (a - Un1); GUp = 0.5 * (Un - d); }
+                    else { GUc = (0.5 * c0) * fma(a - Un, rzfn, dUz * rzf0); GUp = (0.5 * c1) * fma(dUz, rzf0, (Un1 - d) * rzf1); } }
+        if (P.Vz) { const double a = __ldg(P.Vz + n + 1), d = __ldg(P.Vz + n - 2); Vn = __ldg(P.Vz + n); Vn1 = __ldg(P.Vz + n - 1);
+                    dVz = Vn - Vn1;
+                    if (!STR) { GVc = 0.5 * (a - Vn1); GVp = 0.5 * (Vn - d); }
+                    else { GVc = (0.5 * c0) * fma(a - Vn, rzfn, dVz * rzf0); GVp = (0.5 * c1) * fma(dVz, rzf0, (Vn1 - d) * rzf1); } }
+        if (P.Wz) { const double a = __ldg(P.Wz + n + 1), d = __ldg(P.Wz + n - 1); Wn = __ldg(P.Wz + n); GWc = a - Wn; GWp = Wn - d; dWz = GWp; }
+      }
       // one row of this thread at step n.  FAST (compile-time tag): every class weight is the interior one
       auto do_row = [&](auto fast_tag, const int r) {
         constexpr bool FAST = decltype(fast_tag)::value;
@@ -252,8 +258,19 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
         }
         // perturbations about the profiles: this plane's (u', v' at level n, w' at face n) and the previous plane's u', v'
         const double ucq = uc[r] - Un, vcq = vc[r] - Vn, wcq = wc[r] - Wn, upq = up[r] - Un1, vpq = vp[r] - Vn1;
-        const double S13q = H_EPSP ? fma(-rdz, dUz, S13) : 0.0, S23q = H_EPSP ? fma(-rdz, dVz, S23) : 0.0, dwzq = dwz - dWz;
+        const double S13q = H_EPSP ? fma(-(STR ? rzf0 : rdz), dUz, S13) : 0.0, S23q = H_EPSP ? fma(-(STR ? rzf0 : rdz), dVz, S23) : 0.0, dwzq = dwz - dWz;
         if (FAST && STR) {
+          if (H_EPSP) {
+            aEeP = fma(c0 * S12, S12, aEeP); aEeP = fma(dzf0 * S13q, S13q, aEeP); aEeP = fma(dzf0 * S23q, S23q, aEeP);
+            aEzP = fma(rzc1 * dwzq, dwzq, aEzP);
+          }
+          if (H_EPSP && !H_EPS) { aEx = fma(c0 * ax, ax, aEx); aEy = fma(c0 * ay, ay, aEy); }
+          if (H_TKE) { aKP = fma(c0 * ucq, ucq, aKP); aKP = fma(c0 * vcq, vcq, aKP); aKP = fma(hzw * wcq, wcq, aKP); }
+          if (H_SP) {                                        // (the weights are in GU*, GV*; dz_c cancels in the W part)
+            aSuv = fma((ww - Wn) + wcq, fma(GUc, ucq, GUp * upq), aSuv);
+            aSuv = fma((ws - Wn) + wcq, fma(GVc, vcq, GVp * vpq), aSuv);
+            aSw = fma(wcq * wcq, GWc + GWp, aSw);
+          }
           if (H_EPS) {
             aEe = fma(c0 * S12, S12, aEe); aEe = fma(dzf0 * S13, S13, aEe); aEe = fma(dzf0 * S23, S23, aEe);
             aEx = fma(c0 * ax, ax, aEx); aEy = fma(c0 * ay, ay, aEy); aEz = fma(rzc1 * dwz, dwz, aEz);
@@ -304,7 +321,17 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
           if (H_EPS) {
             aEe = fma(hy * G0 * S12, S12, aEe); aEe = fma(al * (hz * dzf0) * S13, S13, aEe); aEe = fma(hy * (hz * dzf0) * S23, S23, aEe);
             aEz = fma(al * g1 * rzc1 * dwz, dwz, aEz);
-            aEx = fma(al * G0 * ax, ax, aEx); aEy = fma(al * G0 * ay, ay, aEy);
+          }
+          if (H_EPS || H_EPSP) { aEx = fma(al * G0 * ax, ax, aEx); aEy = fma(al * G0 * ay, ay, aEy); }
+          if (H_EPSP) {
+            aEeP = fma(hy * G0 * S12, S12, aEeP); aEeP = fma(al * (hz * dzf0) * S13q, S13q, aEeP); aEeP = fma(hy * (hz * dzf0) * S23q, S23q, aEeP);
+            aEzP = fma(al * g1 * rzc1 * dwzq, dwzq, aEzP);
+          }
+          if (H_TKE) { aKP = fma(al * G0 * ucq, ucq, aKP); aKP = fma(hy * G0 * vcq, vcq, aKP); aKP = fma(al * hzK * wcq, wcq, aKP); }
+          if (H_SP) {
+            aSuv = fma(al * ((ww - Wn) + wcq), fma(g0 * GUc, ucq, g1 * GUp * upq), aSuv);
+            aSuv = fma(fma(be, ws - Wn, al * wcq), fma(g0 * GVc, vcq, g1 * GVp * vpq), aSuv);
+            aSw = fma(al * wcq * wcq, fma(g0, GWc, g1 * GWp), aSw);
           }
           if (H_ADV) {
             aAe = fma(G0 * P12, fma(rdx * hy, dvx, rdy * (al * uc[r] - be * us)), aAe);
@@ -400,9 +427,9 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
   acc[FD_EPS] = P.nu * (aEe + 2.0 * (rdx2 * aEx + rdy2 * aEy + fz2 * aEz));
   acc[FD_CHI] = 2.0 * P.kappa * (rdx2 * aCx + rdy2 * aCy + fz2 * aCz);
   acc[FD_CDF] = 2.0 * P.kappa * aD;
-  acc[FD_EPSP] = P.nu * (aEeP + 2.0 * (rdx2 * aEx + rdy2 * aEy + rdz2 * aEzP));
+  acc[FD_EPSP] = P.nu * (aEeP + 2.0 * (rdx2 * aEx + rdy2 * aEy + fz2 * aEzP));
   acc[FD_TKE] = 0.5 * aKP;
-  acc[FD_SP] = -rdz * (0.25 * aSuv + 0.5 * aSw);
+  acc[FD_SP] = -fz * (0.25 * aSuv + 0.5 * aSw);
   if (P.nslots > 0) {
     const unsigned FULLMASK = 0xffffffffu;
 #pragma unroll

@@ -792,9 +792,20 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
   // The class-sum kernel (integrals only, x periodic, no potential vorticity) takes the dissipation of u and of u - U side by
   // side (FD_EPS / FD_EPSP) and the turbulent kinetic energy; the cell-exact kernel one dissipation request and no TKE.
   for (int r = 0; r < n; ++r) any_outq = any_outq || SP.req[r].out;
-  // (stretched z: the class-sum form needs all five inputs -- its one compiled variant is the all-terms one)
-  bool sums_convention = !any_outq && grid->topo[0] == OCB_PERIODIC && !getenv("OCB_FUSED_CELL_INTEGRALS") &&
-                         (!stretched || (tma_compatible(in->b, grid) && tma_compatible(in->p, grid) && !getenv("OCB_DISABLE_SUMS_STRETCHED")));
+  // (stretched z: the class-sum form is compiled for all terms -- five inputs -- and for the TKE budget with pressure
+  //  redistribution -- u, v, w, p; plans whose operands do not cover the variant they would need stay cell-exact)
+  bool str_sums_ok = false;
+  if (stretched && !getenv("OCB_DISABLE_SUMS_STRETCHED")) {
+    bool only_tkep = true;
+    for (int r = 0; r < n; ++r) {
+      const int dg = reqs[r].diag;
+      const bool pert = reqs[r].flags & OCB_REQ_PERTURBATION;
+      if (!(dg == OCB_DIAG_SP || dg == OCB_DIAG_SPZ || dg == OCB_DIAG_TKE || dg == OCB_DIAG_PR || dg == OCB_DIAG_KE || (dg == OCB_DIAG_EPS && pert)))
+        only_tkep = false;
+    }
+    str_sums_ok = tma_compatible(in->p, grid) && (only_tkep || tma_compatible(in->b, grid));
+  }
+  bool sums_convention = !any_outq && grid->topo[0] == OCB_PERIODIC && !getenv("OCB_FUSED_CELL_INTEGRALS") && (!stretched || str_sums_ok);
   for (int r = 0; r < n; ++r) if (reqs[r].diag == OCB_DIAG_EPV) sums_convention = false;
   for (int r = 0; r < n; ++r) {
     int d = fused_diag_index(reqs[r].diag);
@@ -835,7 +846,10 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
     if (R.slot >= 0) { if (which_slot[d] >= 0) return OCB_OK; which_slot[d] = r; }
     mask |= 1 << d;
   }
-  if (stretched && ((mask & ~FD_BUDGET) || any_pert)) return OCB_OK;
+  // stretched z: the cell-exact variant evaluates the seven plain budget terms; the class-sum form also the TKE-budget terms
+  constexpr int TKE_TERMS = (1 << FD_SP) | (1 << FD_EPSP) | (1 << FD_TKE);
+  if (stretched && !sums_convention && ((mask & ~FD_BUDGET) || any_pert)) return OCB_OK;
+  if (stretched && sums_convention && (mask & ~(FD_BUDGET | TKE_TERMS))) return OCB_OK;
   constexpr int CLOSURE_TERMS = (1 << FD_EPS) | (1 << FD_EPSP) | (1 << FD_CHI) | (1 << FD_CDF);
   if (closure_fields && (mask & CLOSURE_TERMS)) return OCB_OK;                  // those go to the velocity-gradient / generic kernels
   if ((mask & (1 << FD_EPV)) && cell_req >= 0 && (SP.req[cell_req].lo[2] != 1 || SP.req[cell_req].hi[2] != grid->N[2])) return OCB_OK;
@@ -891,7 +905,13 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
   const int njy = SP.req[0].hi[1] - SP.req[0].lo[1] + 1;
   if (stretched && sums) {
     const bool narrow = (grid->H[0] & 1) && !getenv("OCB_SUMS_WIDE_TILES");
-    if (njy + 1 <= 4) rc = setup_sums_pitch<ALL, 2, 2, 3, 4, true>(fp, narrow);
+    constexpr int TKEB_S = (1 << FD_SP) | (1 << FD_EPSP) | (1 << FD_TKE);
+    constexpr int TKEP_S = TKEB_S | (1 << FD_PR) | (1 << FD_K);
+    if (mask & TKEB_S) {
+      if ((mask & ~TKEP_S) == 0) rc = setup_sums_pitch<TKEP_S, 4, 4, 3, 2, true>(fp, narrow);
+      else rc = setup_sums_pitch<ALL | TKEB_S, 4, 4, 3, 2, true>(fp, narrow);
+    }
+    else if (njy + 1 <= 4) rc = setup_sums_pitch<ALL, 2, 2, 3, 4, true>(fp, narrow);
     else rc = setup_sums_pitch<ALL, 4, 4, 3, 2, true>(fp, narrow);
   } else if (stretched) {
     if ((mask & ~VEL) == 0) rc = setup_variant_stretched<VEL, 8, 2, 3>(fp);

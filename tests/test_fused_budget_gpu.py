@@ -356,21 +356,23 @@ def test_tke_budget_about_mean_profiles_one_sweep():
         assert abs(a - b) <= 1e-12 * integral_scale(st.og, cases[nm][2], "ccc"), nm
 
 
+@pytest.mark.parametrize("stretched", [False, True], ids=["regular", "stretched"])
 @pytest.mark.parametrize("size,seed", [((64, 44, 26), 1), ((70, 21, 40), 2), ((96, 48, 70), 3)], ids=str)
-def test_class_sum_kernel_tke_ke_and_tracer_variance_budget(size, seed):
+def test_class_sum_kernel_tke_ke_and_tracer_variance_budget(size, seed, stretched):
     """north_star's target plan -- the TKE + KE + tracer-variance budget as volume integrals -- in ONE launch of the class-sum
     kernel: the seven KE / tracer-variance terms plus, about the horizontal-mean profiles U(z), V(z), W(z), the shear production
     (summed over x / y / z faces), the dissipation of u - U and the turbulent kinetic energy.  Against the oracle's per-cell
     values summed over the window, and against the generic kernel, on the whole domain and on random y / z windows."""
     from cases import build_cases
-    st = State(size=size, device="cuda")
+    st = State(size=size, stretched=stretched, device="cuda")      # (stretched z: the per-plane-weight form of the kernel)
     cases = {c[0]: c for c in build_cases(st, "scalar", mean="profile")}
     names = ["KineticEnergy", "KineticEnergyAdvection", "KineticEnergyPressureRedistribution", "PotentialEnergyConversion", "DissipationRate",
              "TracerVarianceDissipationRate", "TracerVarianceDiffusion", "ShearProductionRate", "DissipationRate_perturbation",
              "TurbulentKineticEnergy"]
     ops = [cases[nm][1] for nm in names]
     Nx, Ny, Nz = size
-    V = 1.0 / (Nx * Ny * Nz)
+    ii, jj, kk = st.og.indices("ccc")
+    V = np.broadcast_to(st.og.V("ccc", ii, jj, kk), cases[names[0]][2].shape)      # cell volumes
     rng = np.random.default_rng(seed)
     windows = [None, (1, Ny, 1, 1), (1, 1, 1, Nz), (2, Ny - 1, 2, Nz - 1), (Ny, Ny, Nz, Nz)]
     for _ in range(3):
@@ -390,8 +392,8 @@ def test_class_sum_kernel_tke_ke_and_tracer_variance_budget(size, seed):
                 os.environ.pop("OCB_DISABLE_FUSED", None)
             assert gen.plan.variant == 0
             for nm, a, b in zip(names, sums.integrals(), gen.integrals()):
-                w_ = cases[nm][2][:, jlo - 1:jhi, klo - 1:khi]
-                ref, scale = float(np.sum(w_)) * V, float(np.sum(np.abs(w_))) * V
+                w_, v_ = cases[nm][2][:, jlo - 1:jhi, klo - 1:khi], V[:, jlo - 1:jhi, klo - 1:khi]
+                ref, scale = float(np.sum(w_ * v_)), float(np.sum(np.abs(w_) * v_))
                 assert abs(a - ref) <= 1e-12 * scale, (nm, win, a, ref, scale)
                 assert abs(a - b) <= 1e-12 * scale, (nm, win, a, b, scale)
     finally:
@@ -402,7 +404,7 @@ def test_class_sum_kernel_tke_ke_and_tracer_variance_budget(size, seed):
     assert g.plan.variant == 1
     for nm, a in zip(sub, g.integrals()):
         w_ = cases[nm][2]
-        assert abs(a - float(np.sum(w_)) * V) <= 1e-12 * float(np.sum(np.abs(w_))) * V, nm
+        assert abs(a - float(np.sum(w_ * V))) <= 1e-12 * float(np.sum(np.abs(w_) * V)), nm
     # no mean flow at all (ZeroField means): TKE is K
     cz = {c[0]: c for c in build_cases(st, "scalar", mean="none")}
     gz = ocb.FusedDiagnostics(*[ocb.Integral(cz[nm][1]) for nm in ("TurbulentKineticEnergy", "KineticEnergy")]).compute()
