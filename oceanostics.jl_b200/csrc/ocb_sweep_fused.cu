@@ -538,7 +538,11 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
         if (H_SP) {
           const double wq1 = wc[r] - Wn, wq0 = wp[r] - Wn1;
           const double wcen = 0.5 * (wq0 + wq1), ww2 = 0.5 * fma(wq0, wq0, wq1 * wq1);
-          const double raw = -(fma(ucp[r] * wcen, 0.5 * (Un - Un2) * rdz, fma(vcp[r] * wcen, 0.5 * (Vn - Vn2) * rdz, ww2 * ((Wn - Wn1) * rdz))));
+          // mean shear of cell n-1 (STR: the mean of its two face gradients; dW/dz over the cell's dz_c)
+          const double gU = STR ? 0.5 * fma(Un - Un1, rzf, (Un1 - Un2) * rzf1) : 0.5 * (Un - Un2) * rdz;
+          const double gV = STR ? 0.5 * fma(Vn - Vn1, rzf, (Vn1 - Vn2) * rzf1) : 0.5 * (Vn - Vn2) * rdz;
+          const double gW = (Wn - Wn1) * (STR ? rzc1 : rdz);
+          const double raw = -(fma(ucp[r] * wcen, gU, fma(vcp[r] * wcen, gV, ww2 * gW)));
           ucp[r] = ucn[r];
           vcp[r] = vcn[r];
           emit(FD_SP, raw, 1.0, w1, n - 1, r);
@@ -848,7 +852,9 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
   }
   // stretched z: the cell-exact variant evaluates the seven plain budget terms; the class-sum form also the TKE-budget terms
   constexpr int TKE_TERMS = (1 << FD_SP) | (1 << FD_EPSP) | (1 << FD_TKE);
-  if (stretched && !sums_convention && ((mask & ~FD_BUDGET) || any_pert)) return OCB_OK;
+  // (cell-exact: the seven plain terms, or the TKE budget about mean profiles {eps(u - U), SP, PR, K} -- no potential vorticity)
+  constexpr int TKEM_S = (1 << FD_EPS) | (1 << FD_SP) | (1 << FD_PR) | (1 << FD_K);
+  if (stretched && !sums_convention && ((mask & (1 << FD_EPV)) || (any_pert ? (mask & ~TKEM_S) != 0 : (mask & ~FD_BUDGET) != 0))) return OCB_OK;
   if (stretched && sums_convention && (mask & ~(FD_BUDGET | TKE_TERMS))) return OCB_OK;
   constexpr int CLOSURE_TERMS = (1 << FD_EPS) | (1 << FD_EPSP) | (1 << FD_CHI) | (1 << FD_CDF);
   if (closure_fields && (mask & CLOSURE_TERMS)) return OCB_OK;                  // those go to the velocity-gradient / generic kernels
@@ -914,7 +920,8 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
     else if (njy + 1 <= 4) rc = setup_sums_pitch<ALL, 2, 2, 3, 4, true>(fp, narrow);
     else rc = setup_sums_pitch<ALL, 4, 4, 3, 2, true>(fp, narrow);
   } else if (stretched) {
-    if ((mask & ~VEL) == 0) rc = setup_variant_stretched<VEL, 8, 2, 3>(fp);
+    if (mask & (1 << FD_SP)) rc = setup_variant_stretched<TKEM, 8, 2, 3>(fp);
+    else if ((mask & ~VEL) == 0) rc = setup_variant_stretched<VEL, 8, 2, 3>(fp);
     else if ((mask & ~VELP) == 0) rc = setup_variant_stretched<VELP, 8, 2, 3>(fp);
     else if ((mask & ~VELB) == 0) rc = setup_variant_stretched<VELB, 8, 2, 3>(fp);
     else rc = setup_variant_stretched<ALL, 8, 2, 3>(fp);

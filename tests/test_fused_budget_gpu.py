@@ -324,6 +324,25 @@ def test_ertel_pv_on_the_pipelined_kernel(size):
     assert_close(a, b, 1e-11, "EPV fused vs generic")
 
 
+def test_tke_budget_fields_on_a_stretched_axis():
+    """The TKE budget about horizontal-mean profiles {SP, eps(u - U), PR, K} as FIELDS and integrals on a stretched z axis (the
+    boundary-layer LES case): one launch of the budget kernel's per-plane-metric variant -- the mean shear of a cell is the mean
+    of its two face gradients -- against the oracle."""
+    from cases import build_cases, check_case
+    st = State(size=(64, 44, 26), stretched=True, device="cuda")
+    cases = {c[0]: c for c in build_cases(st, "scalar", mean="profile")}
+    names = ["ShearProductionRate", "DissipationRate_perturbation", "KineticEnergyPressureRedistribution", "KineticEnergy"]
+    ops = [cases[nm][1] for nm in names]
+    grp = ocb.FusedDiagnostics(*([ocb.Field(o) for o in ops] + [ocb.Integral(o) for o in ops])).compute()
+    torch.cuda.synchronize()
+    assert grp.plan.variant == 1 and grp.plan.n_launches == 2
+    vals = [m.interior_ijk() for m in grp.members if isinstance(m, ocb.ComputedField)]
+    for nm, got, integ in zip(names, vals, grp.integrals()):
+        _, _, want, loc = cases[nm]
+        check_case(st, nm, got, want)
+        assert abs(integ - K.integral(want, st.og, loc)) <= 1e-12 * integral_scale(st.og, want, loc), nm
+
+
 def test_tke_budget_about_mean_profiles_one_sweep():
     """BASELINE.json configs[1] at test size: EPV + {ShearProductionRate, DissipationRate(u - U), PressureRedistribution}
     with U, V, W = horizontal-mean profiles, all in ONE launch of the pipelined kernel (perturbations about z profiles
