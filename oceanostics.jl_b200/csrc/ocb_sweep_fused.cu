@@ -320,8 +320,8 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
         // edge vorticities owned by this cell (always of the full velocities) and the b sums of the 2 x 2 columns
         // (i..i+1, j..j+1) of this plane
         O12[r] = (vc[r] - vw) * rdx - (uc[r] - us) * rdy;
-        O13[r] = (uc[r] - up[r]) * rdz - (wc[r] - ww) * rdx;
-        const double o23 = (wc[r] - ws) * rdy - (vc[r] - vp[r]) * rdz;
+        O13[r] = (uc[r] - up[r]) * rzf - (wc[r] - ww) * rdx;               // (rzf: 1 / dz_f of face n; rdz on a regular axis)
+        const double o23 = (wc[r] - ws) * rdy - (vc[r] - vp[r]) * rzf;
         XS23[r] = o23 + __shfl_down_sync(FULLMASK, o23, 1);
         const double* rb = Tb + row * TW + lane + xoff;
         const double b00 = rb[1], b10 = rb[2], b01 = rb[1 + TW], b11 = rb[2 + TW];
@@ -457,10 +457,10 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
         const double ne12 = __shfl_down_sync(FULLMASK, o12n, 1);
         const double qx = fma(0.5, xs23n, P.f[0]) * ((Dx[r] + Dxp[r]) * (0.25 * rdx));
         const double qy = fma(0.5, ys13e, P.f[1]) * ((Dy[r] + Dyp[r]) * (0.25 * rdy));
-        const double qz = fma(0.5, ne12 + NE12p[r], P.f[2]) * ((Sb[r] - Sbp[r]) * (0.25 * rdz));
+        const double qz = fma(0.5, ne12 + NE12p[r], P.f[2]) * ((Sb[r] - Sbp[r]) * (0.25 * rzf));
         const double raw = (qx + qy) + qz;
         Dxp[r] = Dx[r]; Dyp[r] = Dy[r]; Sbp[r] = Sb[r]; NE12p[r] = ne12;
-        const double w = pvE * wE[r];
+        const double w = STR ? (pvE * wE[r]) * dzf0 : pvE * wE[r];          // (STR: the fff point's volume is dx dy dz_f)
         acc[FD_EPV] = fma(raw, w, acc[FD_EPV]);
         if (OUT) {
           if (w != 0.0 && P.o[FD_EPV].out) P.o[FD_EPV].out[orow[r] + P.os[0] + P.os[1] + (long long)n * P.os[2]] = raw;
@@ -854,7 +854,11 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
   constexpr int TKE_TERMS = (1 << FD_SP) | (1 << FD_EPSP) | (1 << FD_TKE);
   // (cell-exact: the seven plain terms, or the TKE budget about mean profiles {eps(u - U), SP, PR, K} -- no potential vorticity)
   constexpr int TKEM_S = (1 << FD_EPS) | (1 << FD_SP) | (1 << FD_PR) | (1 << FD_K);
-  if (stretched && !sums_convention && ((mask & (1 << FD_EPV)) || (any_pert ? (mask & ~TKEM_S) != 0 : (mask & ~FD_BUDGET) != 0))) return OCB_OK;
+  if (stretched && !sums_convention) {
+    const int rest = mask & ~(1 << FD_EPV);
+    if (mask & (1 << FD_EPV)) { if (rest & ~TKEM_S) return OCB_OK; }              // the potential vorticity alone or with the TKE budget
+    else if (any_pert ? (rest & ~TKEM_S) != 0 : (rest & ~FD_BUDGET) != 0) return OCB_OK;
+  }
   if (stretched && sums_convention && (mask & ~(FD_BUDGET | TKE_TERMS))) return OCB_OK;
   constexpr int CLOSURE_TERMS = (1 << FD_EPS) | (1 << FD_EPSP) | (1 << FD_CHI) | (1 << FD_CDF);
   if (closure_fields && (mask & CLOSURE_TERMS)) return OCB_OK;                  // those go to the velocity-gradient / generic kernels
@@ -920,7 +924,8 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
     else if (njy + 1 <= 4) rc = setup_sums_pitch<ALL, 2, 2, 3, 4, true>(fp, narrow);
     else rc = setup_sums_pitch<ALL, 4, 4, 3, 2, true>(fp, narrow);
   } else if (stretched) {
-    if (mask & (1 << FD_SP)) rc = setup_variant_stretched<TKEM, 8, 2, 3>(fp);
+    if (mask & EPVM) rc = mask == EPVM ? setup_variant_stretched<EPVM, 8, 2, 3>(fp) : setup_variant_stretched<TKEV, 8, 2, 3>(fp);
+    else if (mask & (1 << FD_SP)) rc = setup_variant_stretched<TKEM, 8, 2, 3>(fp);
     else if ((mask & ~VEL) == 0) rc = setup_variant_stretched<VEL, 8, 2, 3>(fp);
     else if ((mask & ~VELP) == 0) rc = setup_variant_stretched<VELP, 8, 2, 3>(fp);
     else if ((mask & ~VELB) == 0) rc = setup_variant_stretched<VELB, 8, 2, 3>(fp);

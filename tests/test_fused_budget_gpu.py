@@ -294,11 +294,13 @@ def test_class_sum_kernel_on_a_stretched_axis(size, halo, seed):
         os.environ.pop("OCB_FUSED_KCHUNK", None)
 
 
+@pytest.mark.parametrize("stretched", [False, True], ids=["regular", "stretched"])
 @pytest.mark.parametrize("size", [(64, 44, 26), (62, 23, 3), (34, 50, 9)], ids=str)
-def test_ertel_pv_on_the_pipelined_kernel(size):
-    """ErtelPotentialVorticity (fff, Nz + 1 faces) alone on the pipelined kernel: field, integral, and both."""
+def test_ertel_pv_on_the_pipelined_kernel(size, stretched):
+    """ErtelPotentialVorticity (fff, Nz + 1 faces) alone on the pipelined kernel: field, integral, and both (stretched z: the
+    z differences over dz_f of their face, the fff point's volume dx dy dz_f)."""
     from cases import build_cases, check_case
-    st = State(size=size, device="cuda")
+    st = State(size=size, stretched=stretched, device="cuda")
     cases = {c[0]: c for c in build_cases(st, "scalar")}
     _, op, want, loc = cases["ErtelPotentialVorticity"]
     assert loc == "fff"
@@ -343,12 +345,13 @@ def test_tke_budget_fields_on_a_stretched_axis():
         assert abs(integ - K.integral(want, st.og, loc)) <= 1e-12 * integral_scale(st.og, want, loc), nm
 
 
-def test_tke_budget_about_mean_profiles_one_sweep():
+@pytest.mark.parametrize("stretched", [False, True], ids=["regular", "stretched"])
+def test_tke_budget_about_mean_profiles_one_sweep(stretched):
     """BASELINE.json configs[1] at test size: EPV + {ShearProductionRate, DissipationRate(u - U), PressureRedistribution}
     with U, V, W = horizontal-mean profiles, all in ONE launch of the pipelined kernel (perturbations about z profiles
-    evaluated on the fly, EPV at the cell corners); values and integrals match the oracle."""
+    evaluated on the fly, EPV at the cell corners); values and integrals match the oracle.  Also on a stretched z axis."""
     from cases import build_cases, check_case
-    st = State(size=(64, 44, 26), device="cuda")
+    st = State(size=(64, 44, 26), stretched=stretched, device="cuda")
     cases = {c[0]: c for c in build_cases(st, "scalar", mean="profile")}
     names = ["ShearProductionRate", "DissipationRate_perturbation", "KineticEnergyPressureRedistribution", "ErtelPotentialVorticity"]
     ops = [cases[nm][1] for nm in names]
