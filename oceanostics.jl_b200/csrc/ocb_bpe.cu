@@ -145,8 +145,8 @@ __global__ void __launch_bounds__(RS_THREADS) rs_histogram(const K* __restrict__
 // CHAINED = true ("onesweep"): no histogram pass and no table scan -- `offsets` holds the 256 global digit bases of this pass
 // (from ONE up-front histogram of all digits); the blocks are persistent, take tile numbers from a ticket counter, publish their
 // digit counts and find their exclusive prefix from the counts of the tiles with smaller tickets (a tile only ever waits for
-// those, and they are running).  A wait is bounded: a stuck look-back sets desc's error word and moves on instead of hanging the
-// device.
+// those, and they are running).  A wait is bounded: a stuck wait sets desc's error word and traps (RS_SPIN_LIMIT) instead of
+// hanging the device or returning a wrong order.
 //
 // Two-level chained scan.  Tiles form groups of RS_G consecutive tickets.  Every tile publishes its digit counts agg[tile][256]
 // and adds them to its group's total gt[g][256] (RED.ADD), then bumps the group's counter; the block whose bump completes group g
@@ -166,6 +166,9 @@ __global__ void __launch_bounds__(RS_THREADS) rs_histogram(const K* __restrict__
 // desc layout (32-bit words): aggf[nblocks] flags, the ticket counter, the error word, gcount[ngroups], gxf[ngroups], padding to
 // rs_desc_header(nblocks), gt[ngroups][256] -- all of that cleared before every pass (rs_desc_clear words) -- then
 // agg[nblocks][256] and gx[ngroups][256], write-once per pass.
+// A wait is bounded: ~2.7 s of polling (every tile waited for holds a smaller ticket and is running, so this only fires on a
+// device fault) ends the kernel with a trap -- a sticky launch failure at the caller's next synchronisation, not a wrong sort.
+constexpr unsigned RS_SPIN_LIMIT = 1u << 26;
 constexpr int RS_G = 16;    // tiles per group
 constexpr int RS_GK = 8;    // groups looked back over per poll
 __host__ __device__ constexpr size_t rs_groups(int nblocks) { return ((size_t)nblocks + RS_G - 1) / RS_G; }
@@ -318,7 +321,7 @@ __global__ void __launch_bounds__(RS_THREADS, Pay2::ON ? 2 : 3) rs_scatter(const
             else if (lane == 16 && pgrp > 0) f = rs_ld_flag(gxf + pgrp);
             __syncwarp();
             if ((__ballot_sync(0xffffffffu, f != 0u) & want) == want) break;
-            if (++spins > (1u << 20)) { if (lane == 0) atomicExch(desc + nblocks + 1, 1u); break; }
+            if (++spins > RS_SPIN_LIMIT) { if (lane == 0) atomicExch(desc + nblocks + 1, 1u); __trap(); }
             __nanosleep(40);
           }
           uint32_t va[RS_G - 1];
@@ -371,7 +374,7 @@ __global__ void __launch_bounds__(RS_THREADS, Pay2::ON ? 2 : 3) rs_scatter(const
           for (int q = 0; q <= RS_GK; ++q) sum += vg[q];
           break;
         }
-        if (++spins > (1u << 20)) { if (lane == 0) atomicExch(desc + nblocks + 1, 1u); break; }
+        if (++spins > RS_SPIN_LIMIT) { if (lane == 0) atomicExch(desc + nblocks + 1, 1u); __trap(); }
         __nanosleep(40);
       }
       gx[(size_t)G1 * 256 + d] = sum;
