@@ -32,10 +32,15 @@ constexpr int sums_tile_elems(int tw, int tr) { return ((tw * tr * 8 + 127) / 12
 // factor -- and the by-parts advection splits its fcf / cff products in two: the u (v) equation's z part, whose cell weight
 // cancels the 1 / dz_c of the divergence, and the w equation's x (y) part with the dz_c-weighted advecting transport (the same
 // forms as ocb_budget_kernel<.., STR>, re-associated; oracle/kernels.py has the reference's area / volume weighted formulas).
-template <int MASK, int NW, int RY, int NS, int MINB, int TWK, bool STR = false>
+// NUF = true: the closure carries one eddy-viscosity field nu_e (ccc; SmagorinskyLilly / AMD) next to the constant part P.nu.  The
+// dissipation's items then carry their own viscosity -- nu at ccc for the diagonal strains, the four-point means of nu_e at
+// ffc / fcf / cff for the edges (Oceananigans' interpolation of the closure field, as K1c and the oracle form it) -- inside the
+// class sums instead of one factor after the loop; nu_e is a sixth input tile.
+template <int MASK, int NW, int RY, int NS, int MINB, int TWK, bool STR = false, bool NUF = false>
 __global__ void __launch_bounds__(NW * 32, MINB)
 ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_constant__ CUtensorMap mu, const __grid_constant__ CUtensorMap mv,
-                       const __grid_constant__ CUtensorMap mw, const __grid_constant__ CUtensorMap mb, const __grid_constant__ CUtensorMap mp) {
+                       const __grid_constant__ CUtensorMap mw, const __grid_constant__ CUtensorMap mb, const __grid_constant__ CUtensorMap mp,
+                       const __grid_constant__ CUtensorMap mn) {
   using G = Geo<NW, RY>;
   constexpr int TILE = sums_tile_elems(TWK, G::TR);
   constexpr bool H_K = MASK & (1 << FD_K), H_ADV = MASK & (1 << FD_ADV), H_PR = MASK & (1 << FD_PR), H_WB = MASK & (1 << FD_WB),
@@ -46,8 +51,9 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
   // constants) and the turbulent kinetic energy
   constexpr bool PZ = H_SP || H_EPSP || H_TKE;
   constexpr bool NEED_B = H_WB || H_CHI || H_CDF, NEED_P = H_PR, NEED_S = H_EPS || H_ADV || H_EPSP;
-  constexpr int NF = 3 + (NEED_B ? 1 : 0) + (NEED_P ? 1 : 0);
-  constexpr int F_B = 3, F_P = NEED_B ? 4 : 3;
+  constexpr int NF = 3 + (NEED_B ? 1 : 0) + (NEED_P ? 1 : 0) + (NUF ? 1 : 0);
+  constexpr int F_B = 3, F_P = NEED_B ? 4 : 3, F_N = NF - 1;
+  static_assert(!NUF || (H_EPS && !PZ), "the eddy-viscosity variant is the plain dissipation's");
 
   extern __shared__ __align__(1024) double smem_d[];
   double* tiles = smem_d;                                                      // [NS][NF][TILE]
@@ -91,6 +97,7 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
     tma_load_3d(dst + 2 * TILE, &mw, &full[s], px, py, pz);
     if (NEED_B) tma_load_3d(dst + F_B * TILE, &mb, &full[s], px, py, pz);
     if (NEED_P) tma_load_3d(dst + F_P * TILE, &mp, &full[s], px, py, pz);
+    if (NUF) tma_load_3d(dst + F_N * TILE, &mn, &full[s], px, py, pz);
   };
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) mbar_init(&full[s], 1);
@@ -137,9 +144,11 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
   // step to step (the plane loop is unrolled by two, so nothing is copied), and the in-plane + lower-face part of the
   // tracer Laplacian
   double cu[2][RY], cv[2][RY], cw[2][RY], cb[2][RY], cp[2][RY], CDacc[RY];
+  double cn[2][RY], xn[2][RY], yn[2][RY];                 // NUF: nu_e at the cell, and its sums with the west / south neighbour
 #pragma unroll
   for (int r = 0; r < RY; ++r) {
     cu[0][r] = cv[0][r] = cw[0][r] = cb[0][r] = cp[0][r] = cu[1][r] = cv[1][r] = cw[1][r] = cb[1][r] = cp[1][r] = CDacc[r] = 0.0;
+    cn[0][r] = cn[1][r] = xn[0][r] = xn[1][r] = yn[0][r] = yn[1][r] = 0.0;
   }
   // class sums, normalised to the interior weights (the closing lines of the kernel give each one its factor)
   double aEe = 0.0, aEx = 0.0, aEy = 0.0, aEz = 0.0;       // S12^2 + S13^2 + S23^2 | (dx u)^2 | (dy v)^2 | (dz w)^2   (undivided differences)
@@ -161,9 +170,10 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
     constexpr int C = decltype(par_tag)::value, Q = 1 - C;
     double (&uc)[RY] = cu[C], (&vc)[RY] = cv[C], (&wc)[RY] = cw[C], (&bc)[RY] = cb[C], (&pc)[RY] = cp[C];
     double (&up)[RY] = cu[Q], (&vp)[RY] = cv[Q], (&wp)[RY] = cw[Q], (&bp)[RY] = cb[Q], (&pp)[RY] = cp[Q];
+    double (&nc)[RY] = cn[C], (&np)[RY] = cn[Q], (&XNc)[RY] = xn[C], (&XNp)[RY] = xn[Q], (&YNc)[RY] = yn[C], (&YNp)[RY] = yn[Q];
     mbar_wait(&full[s], phase);
     const double* T = tiles + s * (NF * TILE);
-    const double* Tu = T, *Tv = T + TILE, *Tw = T + 2 * TILE, *Tb = T + F_B * TILE, *Tp = T + F_P * TILE;
+    const double* Tu = T, *Tv = T + TILE, *Tw = T + 2 * TILE, *Tb = T + F_B * TILE, *Tp = T + F_P * TILE, *Tn = T + F_N * TILE;
     if (++s == NS) { s = 0; phase ^= 1; }
     const int col = lane + xoff + 1;                       // tile column of this lane's cell
     const int row0 = jr0 + 1;                              // tile row of this thread's first cell
@@ -175,6 +185,7 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
       uc[r] = Tu[o]; vc[r] = Tv[o]; wc[r] = Tw[o];
       bc[r] = NEED_B ? Tb[o] : 0.0;
       pc[r] = NEED_P ? Tp[o] : 0.0;
+      if (NUF) { nc[r] = Tn[o]; XNc[r] = Tn[o - 1] + nc[r]; YNc[r] = Tn[o - TWK] + nc[r]; }   // (every step: the next one's face means need them)
     }
     if (n > n_first) {
       const int oS = (row0 - 1) * TWK + col, oN = (row0 + RY) * TWK + col;
@@ -259,6 +270,14 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
         // perturbations about the profiles: this plane's (u', v' at level n, w' at face n) and the previous plane's u', v'
         const double ucq = uc[r] - Un, vcq = vc[r] - Vn, wcq = wc[r] - Wn, upq = up[r] - Un1, vpq = vp[r] - Vn1;
         const double S13q = H_EPSP ? fma(-(STR ? rzf0 : rdz), dUz, S13) : 0.0, S23q = H_EPSP ? fma(-(STR ? rzf0 : rdz), dVz, S23) : 0.0, dwzq = dwz - dWz;
+        // first factors of the dissipation's items: the item's viscosity times the strain (NUF; otherwise nu is applied after the loop)
+        double s12w = S12, s13w = S13, s23w = S23, axw = ax, ayw = ay, dwzw = dwz;
+        if (NUF) {
+          const double nffc = fma(0.25, (Tn[o - TWK - 1] + Tn[o - TWK]) + XNc[r], P.nu);
+          const double nfcf = fma(0.25, XNp[r] + XNc[r], P.nu), ncff = fma(0.25, YNp[r] + YNc[r], P.nu);
+          const double ncc = P.nu + nc[r], nccp = P.nu + np[r];
+          s12w = nffc * S12; s13w = nfcf * S13; s23w = ncff * S23; axw = ncc * ax; ayw = ncc * ay; dwzw = nccp * dwz;
+        }
         if (FAST && STR) {
           if (H_EPSP) {
             aEeP = fma(c0 * S12, S12, aEeP); aEeP = fma(dzf0 * S13q, S13q, aEeP); aEeP = fma(dzf0 * S23q, S23q, aEeP);
@@ -272,8 +291,8 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
             aSw = fma(wcq * wcq, GWc + GWp, aSw);
           }
           if (H_EPS) {
-            aEe = fma(c0 * S12, S12, aEe); aEe = fma(dzf0 * S13, S13, aEe); aEe = fma(dzf0 * S23, S23, aEe);
-            aEx = fma(c0 * ax, ax, aEx); aEy = fma(c0 * ay, ay, aEy); aEz = fma(rzc1 * dwz, dwz, aEz);
+            aEe = fma(c0 * s12w, S12, aEe); aEe = fma(dzf0 * s13w, S13, aEe); aEe = fma(dzf0 * s23w, S23, aEe);
+            aEx = fma(c0 * axw, ax, aEx); aEy = fma(c0 * ayw, ay, aEy); aEz = fma(rzc1 * dwzw, dwz, aEz);
           }
           if (H_ADV) {
             aAe = fma(c0 * P12, S12, aAe);
@@ -299,8 +318,8 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
             aSw = fma(wcq * wcq, GWc + GWp, aSw);
           }
           if (H_EPS) {
-            aEe = fma(S12, S12, aEe); aEe = fma(S13, S13, aEe); aEe = fma(S23, S23, aEe);
-            aEx = fma(ax, ax, aEx); aEy = fma(ay, ay, aEy); aEz = fma(dwz, dwz, aEz);
+            aEe = fma(s12w, S12, aEe); aEe = fma(s13w, S13, aEe); aEe = fma(s23w, S23, aEe);
+            aEx = fma(axw, ax, aEx); aEy = fma(ayw, ay, aEy); aEz = fma(dwzw, dwz, aEz);
           }
           if (H_ADV) {
             aAe = fma(P12, S12, aAe); aAe = fma(P13, S13, aAe); aAe = fma(P23, S23, aAe);
@@ -319,10 +338,10 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
           const double hy = 0.5 * (al + be), hyn = 0.5 * (al + an);
           const double hz = 0.5 * (g0 + g1);                               // cells sharing face n, halved
           if (H_EPS) {
-            aEe = fma(hy * G0 * S12, S12, aEe); aEe = fma(al * (hz * dzf0) * S13, S13, aEe); aEe = fma(hy * (hz * dzf0) * S23, S23, aEe);
-            aEz = fma(al * g1 * rzc1 * dwz, dwz, aEz);
+            aEe = fma(hy * G0 * s12w, S12, aEe); aEe = fma(al * (hz * dzf0) * s13w, S13, aEe); aEe = fma(hy * (hz * dzf0) * s23w, S23, aEe);
+            aEz = fma(al * g1 * rzc1 * dwzw, dwz, aEz);
           }
-          if (H_EPS || H_EPSP) { aEx = fma(al * G0 * ax, ax, aEx); aEy = fma(al * G0 * ay, ay, aEy); }
+          if (H_EPS || H_EPSP) { aEx = fma(al * G0 * axw, ax, aEx); aEy = fma(al * G0 * ayw, ay, aEy); }
           if (H_EPSP) {
             aEeP = fma(hy * G0 * S12, S12, aEeP); aEeP = fma(al * (hz * dzf0) * S13q, S13q, aEeP); aEeP = fma(hy * (hz * dzf0) * S23q, S23q, aEeP);
             aEzP = fma(al * g1 * rzc1 * dwzq, dwzq, aEzP);
@@ -358,10 +377,10 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
           const double hy = 0.5 * (al + be), hyn = 0.5 * (al + an);        // y faces / corner rows j and j+1: half their cell count
           const double hz = 0.5 * (g0 + g1), hzp = 0.5 * (g1 + g2);        // z faces n and n-1
           if (H_EPS) {
-            aEe = fma(hy * g0 * S12, S12, aEe); aEe = fma(al * hz * S13, S13, aEe); aEe = fma(hy * hz * S23, S23, aEe);
-            aEz = fma(al * g1 * dwz, dwz, aEz);
+            aEe = fma(hy * g0 * s12w, S12, aEe); aEe = fma(al * hz * s13w, S13, aEe); aEe = fma(hy * hz * s23w, S23, aEe);
+            aEz = fma(al * g1 * dwzw, dwz, aEz);
           }
-          if (H_EPS || H_EPSP) { aEx = fma(al * g0 * ax, ax, aEx); aEy = fma(al * g0 * ay, ay, aEy); }
+          if (H_EPS || H_EPSP) { aEx = fma(al * g0 * axw, ax, aEx); aEy = fma(al * g0 * ayw, ay, aEy); }
           if (H_EPSP) {
             aEeP = fma(hy * g0 * S12, S12, aEeP); aEeP = fma(al * hz * S13q, S13q, aEeP); aEeP = fma(hy * hz * S23q, S23q, aEeP);
             aEzP = fma(al * g1 * dwzq, dwzq, aEzP);
@@ -424,7 +443,7 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
   acc[FD_ADV] = -0.25 * (aAe + (rdx * aAx + rdy * aAy + fz * aAz));
   acc[FD_PR] = rdx * aPx + rdy * aPy + fz * aPz;
   acc[FD_WB] = 0.5 * P.ghat_z * aW;
-  acc[FD_EPS] = P.nu * (aEe + 2.0 * (rdx2 * aEx + rdy2 * aEy + fz2 * aEz));
+  acc[FD_EPS] = (NUF ? 1.0 : P.nu) * (aEe + 2.0 * (rdx2 * aEx + rdy2 * aEy + fz2 * aEz));      // NUF: the viscosities are inside the sums
   acc[FD_CHI] = 2.0 * P.kappa * (rdx2 * aCx + rdy2 * aCy + fz2 * aCz);
   acc[FD_CDF] = 2.0 * P.kappa * aD;
   acc[FD_EPSP] = P.nu * (aEeP + 2.0 * (rdx2 * aEx + rdy2 * aEy + fz2 * aEzP));

@@ -245,14 +245,28 @@ static int finish_plan(ocb_plan* pl, const ocb_grid* grid, const ocb_sweep_input
   }
   const bool stretched_z = grid->dzc || grid->dzf;
   if (in->closure.n_nu_fields || in->closure.n_kappa_fields) {
-    // eddy-viscosity / diffusivity fields: the budget kernels keep the closure-independent terms (K, ADV, PR, w b); the
-    // dissipation goes to the velocity-gradient kernel, the tracer-variance terms to the generic one
-    int kept = 0;
-    for (int r = 0; r < nf; ++r) {
-      const int dg = fr[r].diag;
-      if (dg == OCB_DIAG_EPS || dg == OCB_DIAG_CHI || dg == OCB_DIAG_CDIFF) gr[ng++] = fr[r]; else fr[kept++] = fr[r];
+    // eddy-viscosity / diffusivity fields.  The budget kernels keep the closure-independent terms (K, ADV, PR, w b) and, as class
+    // sums, the dissipation with one nu_e field; what they decline goes to the velocity-gradient kernel (dissipation) and the
+    // generic one (tracer-variance terms).  Tried from the largest set down: everything, without the tracer-variance terms,
+    // without the dissipation too.
+    for (int stage = 0; stage < 3 && nf > 0 && !pl->fused; ++stage) {
+      if (stage >= 1) {
+        int kept = 0, moved = 0;
+        for (int r = 0; r < nf; ++r) {
+          const int dg = fr[r].diag;
+          const bool go = stage == 1 ? (dg == OCB_DIAG_CHI || dg == OCB_DIAG_CDIFF) : dg == OCB_DIAG_EPS;
+          if (go) { gr[ng++] = fr[r]; ++moved; } else fr[kept++] = fr[r];
+        }
+        nf = kept;
+        if (!moved || nf == 0) continue;
+      }
+      SweepParams<T> Pf;
+      rc = ocb_build_sweep_params<T>(grid, in, fr, nf, zt, &Pf);
+      if (rc != OCB_OK) return rc;
+      Pf.nslots = nslots;
+      rc = ocb_fused_try_create(grid, in, fr, nf, Pf, &pl->fused);
+      if (rc != OCB_OK) return rc;
     }
-    nf = kept;
   }
   for (int attempt = 0; attempt < 4 && nf > 0 && !pl->fused; ++attempt) {
     if (attempt >= 1) {

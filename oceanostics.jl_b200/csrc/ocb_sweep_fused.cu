@@ -116,7 +116,8 @@ struct Geo {
 template <int MASK, int NW, int RY, int NS, bool OUT, bool STR = false>
 __global__ void __launch_bounds__(NW * 32, (RY == 1 ? (NW <= 8 ? 2 : 1) : (RY == 2 && NW <= 6 ? 2 : 1)))
 ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__ CUtensorMap mu, const __grid_constant__ CUtensorMap mv,
-                  const __grid_constant__ CUtensorMap mw, const __grid_constant__ CUtensorMap mb, const __grid_constant__ CUtensorMap mp) {
+                  const __grid_constant__ CUtensorMap mw, const __grid_constant__ CUtensorMap mb, const __grid_constant__ CUtensorMap mp,
+                  const __grid_constant__ CUtensorMap /* nu_e: class-sum kernel only */) {
   using G = Geo<NW, RY>;
   constexpr bool H_K = MASK & (1 << FD_K), H_ADV = MASK & (1 << FD_ADV), H_PR = MASK & (1 << FD_PR), H_WB = MASK & (1 << FD_WB),
                  H_EPS = MASK & (1 << FD_EPS), H_CHI = MASK & (1 << FD_CHI), H_CDF = MASK & (1 << FD_CDF), H_SP = MASK & (1 << FD_SP),
@@ -660,14 +661,15 @@ EncodeTiledFn get_encode_fn() {
 
 struct ocb_fused_plan {
   FusedParams P;
-  CUtensorMap maps[5];
+  CUtensorMap maps[6];             // u, v, w, b, p, nu_e
   int mask, nw, ry, ns;
   bool sums;                       // ocb_budget_sums_kernel (integral-only class sums) instead of ocb_budget_kernel
   int minb;                        // resident blocks per SM the sums kernel was compiled for
   int tw;                          // tile row pitch in elements (the TMA box width)
   int nblocks;
   size_t smem;
-  void (*kernel)(FusedParams, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap);
+  void (*kernel)(FusedParams, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap);
+  bool nuf;                        // the eddy-viscosity variant of the class-sum kernel (nu_e as sixth input)
 };
 
 template <int MASK, int NW, int RY, int NS>
@@ -703,23 +705,23 @@ static int setup_variant_stretched(ocb_fused_plan* fp) {
   return OCB_OK;
 }
 
-template <int MASK, int NW, int RY, int NS, int MINB, int TWK = TW, bool STR = false>
+template <int MASK, int NW, int RY, int NS, int MINB, int TWK = TW, bool STR = false, bool NUF = false>
 static int setup_sums(ocb_fused_plan* fp) {
   using G = Geo<NW, RY>;
   constexpr bool NEED_B = MASK & ((1 << FD_WB) | (1 << FD_CHI) | (1 << FD_CDF)), NEED_P = MASK & (1 << FD_PR);
-  constexpr int NF = 3 + (NEED_B ? 1 : 0) + (NEED_P ? 1 : 0);
-  fp->nw = NW; fp->ry = RY; fp->ns = NS; fp->mask = MASK; fp->sums = true; fp->minb = MINB; fp->tw = TWK;
+  constexpr int NF = 3 + (NEED_B ? 1 : 0) + (NEED_P ? 1 : 0) + (NUF ? 1 : 0);
+  fp->nw = NW; fp->ry = RY; fp->ns = NS; fp->mask = MASK; fp->sums = true; fp->minb = MINB; fp->tw = TWK; fp->nuf = NUF;
   fp->smem = sizeof(double) * ((size_t)NS * NF * sums_tile_elems(TWK, G::TR) + NW) + sizeof(uint64_t) * NS;
-  auto kern = ocb_budget_sums_kernel<MASK, NW, RY, NS, MINB, TWK, STR>;
+  auto kern = ocb_budget_sums_kernel<MASK, NW, RY, NS, MINB, TWK, STR, NUF>;
   cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   fp->kernel = kern;
   OCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp->smem));
   return OCB_OK;
 }
 // the default shapes in both tile pitches: 34 columns when every tile starts on a 16-byte boundary (odd x halo)
-template <int MASK, int NW, int RY, int NS, int MINB, bool STR = false>
+template <int MASK, int NW, int RY, int NS, int MINB, bool STR = false, bool NUF = false>
 static int setup_sums_pitch(ocb_fused_plan* fp, bool narrow) {
-  return narrow ? setup_sums<MASK, NW, RY, NS, MINB, 34, STR>(fp) : setup_sums<MASK, NW, RY, NS, MINB, 36, STR>(fp);
+  return narrow ? setup_sums<MASK, NW, RY, NS, MINB, 34, STR, NUF>(fp) : setup_sums<MASK, NW, RY, NS, MINB, 36, STR, NUF>(fp);
 }
 
 static int make_map(EncodeTiledFn enc, const ocb_field& f, int rows, CUtensorMap* map, int tw = TW) {
@@ -860,8 +862,18 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
     else if (any_pert ? (rest & ~TKEM_S) != 0 : (rest & ~FD_BUDGET) != 0) return OCB_OK;
   }
   if (stretched && sums_convention && (mask & ~(FD_BUDGET | TKE_TERMS))) return OCB_OK;
+  // ... and, as class sums, the dissipation with ONE eddy-viscosity field (the nu_e of SmagorinskyLilly / AMD as a sixth input)
   constexpr int CLOSURE_TERMS = (1 << FD_EPS) | (1 << FD_EPSP) | (1 << FD_CHI) | (1 << FD_CDF);
-  if (closure_fields && (mask & CLOSURE_TERMS)) return OCB_OK;                  // those go to the velocity-gradient / generic kernels
+  bool nuf = false;
+  if (closure_fields && (mask & CLOSURE_TERMS)) {
+    const ocb_field& nf = in->closure.nu_fields[0];
+    const bool nu_ok = sums_convention && !any_pert && in->closure.n_nu_fields == 1 && tma_compatible(nf, grid) &&
+                       nf.loc[0] == OCB_CENTER && nf.loc[1] == OCB_CENTER && nf.loc[2] == OCB_CENTER && !getenv("OCB_DISABLE_SUMS_NUF");
+    const int kappa_terms = (1 << FD_CHI) | (1 << FD_CDF);
+    if (!nu_ok || (mask & (1 << FD_EPSP)) || ((mask & kappa_terms) && in->closure.n_kappa_fields)) return OCB_OK;   // velocity-gradient / generic kernels
+    nuf = (mask & (1 << FD_EPS)) != 0;
+    if (!nuf && in->closure.n_kappa_fields && (mask & kappa_terms)) return OCB_OK;
+  }
   if ((mask & (1 << FD_EPV)) && cell_req >= 0 && (SP.req[cell_req].lo[2] != 1 || SP.req[cell_req].hi[2] != grid->N[2])) return OCB_OK;
   const double *Uz = nullptr, *Vz = nullptr, *Wz = nullptr;
   if (any_pert) {
@@ -913,7 +925,12 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
   // OCB_SUMS_CONFIG="NW,RY,NS,MINB" picks another compiled shape of the all-terms kernel for tuning runs.
   const bool sums = sums_convention;
   const int njy = SP.req[0].hi[1] - SP.req[0].lo[1] + 1;
-  if (stretched && sums) {
+  if (sums && nuf) {
+    // eddy-viscosity dissipation: the all-terms class sums with nu_e inside (needs all five other inputs as well)
+    const bool narrow = (grid->H[0] & 1) && !getenv("OCB_SUMS_WIDE_TILES");
+    if (!tma_compatible(in->b, grid) || !tma_compatible(in->p, grid)) { delete fp; return OCB_OK; }
+    rc = stretched ? setup_sums_pitch<ALL, 4, 4, 3, 2, true, true>(fp, narrow) : setup_sums_pitch<ALL, 4, 4, 3, 2, false, true>(fp, narrow);
+  } else if (stretched && sums) {
     const bool narrow = (grid->H[0] & 1) && !getenv("OCB_SUMS_WIDE_TILES");
     constexpr int TKEB_S = (1 << FD_SP) | (1 << FD_EPSP) | (1 << FD_TKE);
     constexpr int TKEP_S = TKEB_S | (1 << FD_PR) | (1 << FD_K);
@@ -1039,8 +1056,8 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
     if (which_out[d] >= 0) P.o[d].out = (double*)SP.req[which_out[d]].out;
     if (which_slot[d] >= 0) P.o[d].slot = SP.req[which_slot[d]].slot;
   }
-  const ocb_field* f[5] = {&in->u, &in->v, &in->w, vneed_b ? &in->b : &in->u, vneed_p ? &in->p : &in->u};
-  for (int a = 0; a < 5; ++a) {
+  const ocb_field* f[6] = {&in->u, &in->v, &in->w, vneed_b ? &in->b : &in->u, vneed_p ? &in->p : &in->u, fp->nuf ? &in->closure.nu_fields[0] : &in->u};
+  for (int a = 0; a < 6; ++a) {
     rc = make_map(enc, *f[a], BR + 2, &fp->maps[a], fp->sums ? fp->tw : TW);
     if (rc != OCB_OK) { delete fp; return rc; }
   }
@@ -1063,7 +1080,7 @@ int ocb_fused_execute_gated(ocb_fused_plan* fp, double* partial, long long* flag
 int ocb_fused_execute(ocb_fused_plan* fp, double* partial, cudaStream_t st) {
   fp->P.partial = partial;
   dim3 block(32, fp->nw, 1), grid(fp->nblocks, 1, 1);
-  fp->kernel<<<grid, block, fp->smem, st>>>(fp->P, fp->maps[0], fp->maps[1], fp->maps[2], fp->maps[3], fp->maps[4]);
+  fp->kernel<<<grid, block, fp->smem, st>>>(fp->P, fp->maps[0], fp->maps[1], fp->maps[2], fp->maps[3], fp->maps[4], fp->maps[5]);
   OCB_CUDA(cudaGetLastError());
   return OCB_OK;
 }

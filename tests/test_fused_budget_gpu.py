@@ -155,7 +155,7 @@ def test_budget_kernel_envelope():
     oc, pc = st.closures()["smagorinsky_like"]
     m = st.model(closure=pc)
     grp = ocb.FusedDiagnostics(ocb.Integral(ocb.KineticEnergyEquation.DissipationRate(m)))
-    assert grp.plan.variant == 3          # eddy-viscosity field: velocity-gradient kernel
+    assert grp.plan.variant == 3          # eddy-viscosity field, dissipation alone (no b, p operands): velocity-gradient kernel
 
 
 @pytest.mark.parametrize("stretched", [False, True], ids=["regular", "stretched"])
@@ -171,14 +171,55 @@ def test_les_closure_budget_splits_over_the_pipelined_kernels(stretched):
     for op, g, w_, integ in zip(ops, vals, want, ints):
         assert_close(g, w_, 1e-12, op.name)
         assert abs(integ - K.integral(w_, st.og, "ccc")) <= 1e-12 * integral_scale(st.og, w_, "ccc"), op.name
-    grp, _, ints2 = run(ops, fields=False)                       # integrals only: the closure-independent class sums
-    assert grp.plan.variant == 6
+    grp, _, ints2 = run(ops, fields=False)     # integrals only: class sums with nu_e inside the dissipation's items; the
+    assert grp.plan.variant == 2               # tracer-variance terms (kappa_e field) on the generic kernel
     for op, w_, integ in zip(ops, want, ints2):
         assert abs(integ - K.integral(w_, st.og, "ccc")) <= 1e-12 * integral_scale(st.og, w_, "ccc"), op.name
     grp, vals, _ = run(ops[:5], integrals=False)                 # the KE budget alone: no generic launch
     assert grp.plan.variant == 5
     for op, g, w_ in zip(ops[:5], vals, want[:5]):
         assert_close(g, w_, 1e-12, op.name)
+
+
+@pytest.mark.parametrize("stretched", [False, True], ids=["regular", "stretched"])
+@pytest.mark.parametrize("closure", ["smagorinsky_like", "tuple"])
+def test_eddy_viscosity_dissipation_as_class_sums(stretched, closure):
+    """Integral(DissipationRate) under SmagorinskyLilly- / AMD-like closures (a nu_e field, alone or in a tuple with a constant
+    viscosity) on the class-sum kernel: nu at ccc for the diagonal strains, its four-point means at ffc / fcf / cff for the edges,
+    inside the sums.  Whole domain and random y / z windows against the oracle's per-cell values times their volumes and against
+    the velocity-gradient kernel; the closure-independent KE-budget terms ride in the same launch."""
+    st = State(size=(64, 40, 30), stretched=stretched, device="cuda")
+    ops, oc = budget(st, closure=closure)
+    want = oracle_budget(st, oc)
+    ii, jj, kk = st.og.indices("ccc")
+    vol = np.broadcast_to(st.og.V("ccc", ii, jj, kk), want[0].shape)
+    Nx, Ny, Nz = 64, 40, 30
+    rng = np.random.default_rng(7)
+    windows = [None, (1, Ny, 1, 1), (1, 1, 1, Nz), (2, Ny - 1, 2, Nz - 1), (Ny, Ny, Nz, Nz)]
+    for _ in range(3):
+        j = sorted(rng.integers(1, Ny + 1, 2)); k = sorted(rng.integers(1, Nz + 1, 2))
+        windows.append((int(j[0]), int(j[1]), int(k[0]), int(k[1])))
+    ke = ops[:5]                                                    # K, ADV, PR, w b, eps
+    os.environ["OCB_FUSED_KCHUNK"] = "16"
+    try:
+        for win in windows:
+            idx = None if win is None else (None, (win[0], win[1]), (win[2], win[3]))
+            jlo, jhi, klo, khi = win or (1, Ny, 1, Nz)
+            grp = ocb.FusedDiagnostics(*[ocb.Integral(o, indices=idx) for o in ke]).compute()
+            assert grp.plan.variant == 1 and grp.plan.n_launches == 2, (win, grp.plan.variant)
+            os.environ["OCB_DISABLE_SUMS_NUF"] = "1"
+            try:
+                split = ocb.FusedDiagnostics(*[ocb.Integral(o, indices=idx) for o in ke]).compute()
+            finally:
+                os.environ.pop("OCB_DISABLE_SUMS_NUF", None)
+            assert split.plan.variant == 5                          # budget kernel + velocity-gradient kernel
+            for o, w_, a, b_ in zip(ke, want, grp.integrals(), split.integrals()):
+                ww, vw = w_[:, jlo - 1:jhi, klo - 1:khi], vol[:, jlo - 1:jhi, klo - 1:khi]
+                ref, scale = float(np.sum(ww * vw)), float(np.sum(np.abs(ww) * vw))
+                assert abs(a - ref) <= 1e-12 * scale, (o.name, win, a, ref, scale)
+                assert abs(a - b_) <= 1e-12 * scale, (o.name, win, a, b_, scale)
+    finally:
+        os.environ.pop("OCB_FUSED_KCHUNK", None)
 
 
 @pytest.mark.parametrize("stretched", [False, True], ids=["regular", "stretched"])
