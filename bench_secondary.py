@@ -106,6 +106,21 @@ def run_secondary(ocb, torch, run, peak, steps=5):
                               workload=f"512^3 F64, stretched z (tanh faces), constant nu / kappa: KE + tracer-variance budget, {what}, one sweep "
                                        "(per-plane-metric variants of the class-sum / budget kernels)")
             del grp
+        # the same grid with a SmagorinskyLilly-like closure (nu_e field, kappa_e = nu_e / Pr): the LES budget integrals in one launch
+        nu_e = ocb.CenterField(grid)
+        nu_e.interior.copy_(1e-3 * (1 + 0.5 * torch.rand(nu_e.interior.shape, device=dev, dtype=torch.float64)))
+        nu_e.fill_halo_regions()
+        mles = ocb.NonhydrostaticModel(grid, closure=ocb.Closure(nu_fields=(nu_e,), kappa_fields=(nu_e,), kappa_scale=(1.0,), name="SmagorinskyLilly"))
+        for f, g_ in zip((mles.velocities.u, mles.velocities.v, mles.velocities.w, mles.tracers.b, mles.pressures.pNHS),
+                         (m.velocities.u, m.velocities.v, m.velocities.w, m.tracers.b, m.pressures.pNHS)):
+            f.data.copy_(g_.data)
+        grp = ocb.FusedDiagnostics(*[ocb.Integral(o) for o in budget_ops(ocb, mles)])
+        ms = _timed(torch, grp.plan.execute, reps=steps)
+        out["stretched_les_budget_integrals"] = _entry(
+            ms, n ** 3, grp.plan.algorithmic_bytes / n ** 3, peak, variant=VARIANTS.get(grp.plan.variant), launches=grp.plan.n_launches,
+            workload="512^3 F64, stretched z, eddy-viscosity closure (nu_e field, kappa_e = nu_e / Pr): the 7 budget integrals, one sweep "
+                     "(class sums with per-item viscosities / diffusivities)")
+        del grp, mles, nu_e
         del ops, m, grid
     except Exception as e:  # pragma: no cover
         out["stretched_budget"] = {"error": repr(e)[:300]}

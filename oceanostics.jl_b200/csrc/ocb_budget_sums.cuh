@@ -253,16 +253,24 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
         const double dpx = NEED_P ? pc[r] - Tp[o - 1] : 0.0, dpy = pc[r] - ps, dpz = pc[r] - pp[r];
         const double bs = r ? bc[r > 0 ? r - 1 : 0] : bS;
         const double dbx = NEED_B ? bc[r] - Tb[o - 1] : 0.0, dby = bc[r] - bs, dbz = bc[r] - bp[r];
+        // NUF: the diffusivity of each face (kappa_const + kappa_scale x the two-point mean of nu_e: kappa_e = nu_e / Pr) rides on
+        // the gradient of that face; otherwise kappa is one factor after the loop
+        double dbxw = dbx, dbyw = dby, dbzw = dbz, kxe = 1.0, kyn = 1.0;
+        if (NUF && (H_CHI || H_CDF)) {
+          const double hs = 0.5 * P.kappa_scale;
+          dbxw = fma(hs, XNc[r], P.kappa) * dbx; dbyw = fma(hs, YNc[r], P.kappa) * dby; dbzw = fma(hs, np[r] + nc[r], P.kappa) * dbz;
+          if (H_CDF) { kxe = fma(hs, nc[r] + Tn[o + 1], P.kappa); kyn = fma(hs, nc[r] + Tn[o + TWK], P.kappa); }
+        }
         double lap = 0.0;
         if (H_CDF) {
           const double bn = (r < RY - 1) ? bc[r < RY - 1 ? r + 1 : 0] : bN;
           const double de = Tb[o + 1] - bc[r], dn = bn - bc[r];
-          const double cdxy = fma(dbx - de, rdx2, (dby - dn) * rdy2);
+          const double cdxy = NUF ? fma(dbxw - kxe * de, rdx2, (dbyw - kyn * dn) * rdy2) : fma(dbx - de, rdx2, (dby - dn) * rdy2);
           if (!STR) {
-            lap = fma(-dbz, rdz2, CDacc[r]);               // Laplacian (sign of div q) of the cell below, closed by this face
-            CDacc[r] = fma(dbz, rdz2, cdxy);
+            lap = fma(-dbzw, rdz2, CDacc[r]);              // Laplacian (sign of div q) of the cell below, closed by this face
+            CDacc[r] = fma(dbzw, rdz2, cdxy);
           } else {                                         // dz_c x the Laplacian: dz_c (in-plane part) + the two face gradients
-            const double gl = dbz * rzf0;
+            const double gl = dbzw * rzf0;
             lap = CDacc[r] - gl;
             CDacc[r] = fma(c0, cdxy, gl);
           }
@@ -303,7 +311,7 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
           if (H_K) { aK = fma(c0 * uc[r], uc[r], aK); aK = fma(c0 * vc[r], vc[r], aK); aK = fma(hzw * wc[r], wc[r], aK); }
           if (H_PR) { aPx = fma(c0 * uc[r], dpx, aPx); aPy = fma(c0 * vc[r], dpy, aPy); aPz = fma(rho0 * wc[r], dpz, aPz); }
           if (H_WB) aW = fma(hzw * wc[r], bp[r] + bc[r], aW);
-          if (H_CHI) { aCx = fma(c0 * dbx, dbx, aCx); aCy = fma(c0 * dby, dby, aCy); aCz = fma(rzf0 * dbz, dbz, aCz); }
+          if (H_CHI) { aCx = fma(c0 * dbxw, dbx, aCx); aCy = fma(c0 * dbyw, dby, aCy); aCz = fma(rzf0 * dbzw, dbz, aCz); }
           if (H_CDF) aD = fma(bp[r], lap, aD);
         } else if (FAST) {
           if (H_EPSP) {
@@ -328,7 +336,7 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
           if (H_K) { aK = fma(uc[r], uc[r], aK); aK = fma(vc[r], vc[r], aK); aK = fma(wc[r], wc[r], aK); }
           if (H_PR) { aPx = fma(uc[r], dpx, aPx); aPy = fma(vc[r], dpy, aPy); aPz = fma(wc[r], dpz, aPz); }
           if (H_WB) aW = fma(wc[r], bp[r] + bc[r], aW);
-          if (H_CHI) { aCx = fma(dbx, dbx, aCx); aCy = fma(dby, dby, aCy); aCz = fma(dbz, dbz, aCz); }
+          if (H_CHI) { aCx = fma(dbxw, dbx, aCx); aCy = fma(dbyw, dby, aCy); aCz = fma(dbzw, dbz, aCz); }
           if (H_CDF) aD = fma(bp[r], lap, aD);
         } else if (lane_ok && STR) {
           // ---- GEN on a stretched axis: the class weights of the regular form below, times the metrics of their items ----
@@ -367,7 +375,7 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
           if (H_K) { aK = fma(al * G0 * uc[r], uc[r], aK); aK = fma(hy * G0 * vc[r], vc[r], aK); aK = fma(al * hzK * wc[r], wc[r], aK); }
           if (H_PR) { aPx = fma(al * G0 * uc[r], dpx, aPx); aPy = fma(hy * G0 * vc[r], dpy, aPy); aPz = fma(al * rho0g * wc[r], dpz, aPz); }
           if (H_WB) aW = fma(al * hzK * wc[r], bp[r] + bc[r], aW);
-          if (H_CHI) { aCx = fma(al * G0 * dbx, dbx, aCx); aCy = fma(hy * G0 * dby, dby, aCy); aCz = fma(al * (hz * rzf0) * dbz, dbz, aCz); }
+          if (H_CHI) { aCx = fma(al * G0 * dbxw, dbx, aCx); aCy = fma(hy * G0 * dbyw, dby, aCy); aCz = fma(al * (hz * rzf0) * dbzw, dbz, aCz); }
           if (H_CDF) aD = fma(al * g1 * bp[r], lap, aD);
         } else if (lane_ok) {
           // ---- GEN: a window-edge row or plane (or a partly filled x tile): explicit class weights (all one elsewhere) ----
@@ -409,7 +417,7 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
           if (H_K) { aK = fma(al * g0 * uc[r], uc[r], aK); aK = fma(hy * g0 * vc[r], vc[r], aK); aK = fma(al * hz * wc[r], wc[r], aK); }
           if (H_PR) { aPx = fma(al * g0 * uc[r], dpx, aPx); aPy = fma(hy * g0 * vc[r], dpy, aPy); aPz = fma(al * hz * wc[r], dpz, aPz); }
           if (H_WB) aW = fma(al * hz * wc[r], bp[r] + bc[r], aW);
-          if (H_CHI) { aCx = fma(al * g0 * dbx, dbx, aCx); aCy = fma(hy * g0 * dby, dby, aCy); aCz = fma(al * hz * dbz, dbz, aCz); }
+          if (H_CHI) { aCx = fma(al * g0 * dbxw, dbx, aCx); aCy = fma(hy * g0 * dbyw, dby, aCy); aCz = fma(al * hz * dbzw, dbz, aCz); }
           if (H_CDF) aD = fma(al * g1 * bp[r], lap, aD);
         }
       };
@@ -444,8 +452,8 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
   acc[FD_PR] = rdx * aPx + rdy * aPy + fz * aPz;
   acc[FD_WB] = 0.5 * P.ghat_z * aW;
   acc[FD_EPS] = (NUF ? 1.0 : P.nu) * (aEe + 2.0 * (rdx2 * aEx + rdy2 * aEy + fz2 * aEz));      // NUF: the viscosities are inside the sums
-  acc[FD_CHI] = 2.0 * P.kappa * (rdx2 * aCx + rdy2 * aCy + fz2 * aCz);
-  acc[FD_CDF] = 2.0 * P.kappa * aD;
+  acc[FD_CHI] = 2.0 * (NUF ? 1.0 : P.kappa) * (rdx2 * aCx + rdy2 * aCy + fz2 * aCz);
+  acc[FD_CDF] = 2.0 * (NUF ? 1.0 : P.kappa) * aD;
   acc[FD_EPSP] = P.nu * (aEeP + 2.0 * (rdx2 * aEx + rdy2 * aEy + fz2 * aEzP));
   acc[FD_TKE] = 0.5 * aKP;
   acc[FD_SP] = -fz * (0.25 * aSuv + 0.5 * aSw);

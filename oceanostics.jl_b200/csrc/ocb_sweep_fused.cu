@@ -50,6 +50,7 @@ struct FusedParams {
   int kz_lo, kz_hi;                // 1-based inclusive z window (the whole interior, or a z slab of it)
   int jy_lo, jy_hi;                // 1-based inclusive y window (rows next to a slab edge are swept separately)
   double rdx, rdy, rdz, nu, kappa, ghat_z, V;
+  double kappa_scale;              // class-sum NUF variant: kappa at a face = kappa + kappa_scale x mean of nu_e (kappa_e = nu_e / Pr)
   FusedOut o[FD_N];
   long long os[3];                 // element strides shared by every output field
   double* partial;
@@ -869,10 +870,13 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
     const ocb_field& nf = in->closure.nu_fields[0];
     const bool nu_ok = sums_convention && !any_pert && in->closure.n_nu_fields == 1 && tma_compatible(nf, grid) &&
                        nf.loc[0] == OCB_CENTER && nf.loc[1] == OCB_CENTER && nf.loc[2] == OCB_CENTER && !getenv("OCB_DISABLE_SUMS_NUF");
+    // the tracer-variance terms: a constant kappa, or kappa_e = scale x the SAME field (SmagorinskyLilly's nu_e / Pr)
+    const ocb_field& kf = in->closure.kappa_fields[0];
+    const bool kappa_ok = in->closure.n_kappa_fields == 0 ||
+                          (in->closure.n_kappa_fields == 1 && kf.data == nf.data && kf.stride[1] == nf.stride[1] && kf.stride[2] == nf.stride[2]);
     const int kappa_terms = (1 << FD_CHI) | (1 << FD_CDF);
-    if (!nu_ok || (mask & (1 << FD_EPSP)) || ((mask & kappa_terms) && in->closure.n_kappa_fields)) return OCB_OK;   // velocity-gradient / generic kernels
-    nuf = (mask & (1 << FD_EPS)) != 0;
-    if (!nuf && in->closure.n_kappa_fields && (mask & kappa_terms)) return OCB_OK;
+    if (!nu_ok || (mask & (1 << FD_EPSP)) || ((mask & kappa_terms) && !kappa_ok)) return OCB_OK;   // velocity-gradient / generic kernels
+    nuf = true;
   }
   if ((mask & (1 << FD_EPV)) && cell_req >= 0 && (SP.req[cell_req].lo[2] != 1 || SP.req[cell_req].hi[2] != grid->N[2])) return OCB_OK;
   const double *Uz = nullptr, *Vz = nullptr, *Wz = nullptr;
@@ -1046,6 +1050,7 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
   fp->nblocks = tiles * P.nchunks;
   P.rdx = 1.0 / grid->d[0]; P.rdy = 1.0 / grid->d[1]; P.rdz = stretched ? 1.0 : 1.0 / grid->d[2];
   P.nu = in->closure.nu_const; P.kappa = in->closure.kappa_const; P.ghat_z = in->ghat[2];
+  P.kappa_scale = in->closure.n_kappa_fields ? in->closure.kappa_scale[0] : 0.0;
   P.V = stretched ? grid->d[0] * grid->d[1] : grid->d[0] * grid->d[1] * grid->d[2];      // stretched: dz_c is the cell's integral weight
   P.dzc = SP.g.dzc; P.dzf = SP.g.dzf; P.rdzc = SP.g.rdzc; P.rdzf = SP.g.rdzf;
   P.nslots = SP.nslots;

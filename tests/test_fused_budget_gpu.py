@@ -171,8 +171,8 @@ def test_les_closure_budget_splits_over_the_pipelined_kernels(stretched):
     for op, g, w_, integ in zip(ops, vals, want, ints):
         assert_close(g, w_, 1e-12, op.name)
         assert abs(integ - K.integral(w_, st.og, "ccc")) <= 1e-12 * integral_scale(st.og, w_, "ccc"), op.name
-    grp, _, ints2 = run(ops, fields=False)     # integrals only: class sums with nu_e inside the dissipation's items; the
-    assert grp.plan.variant == 2               # tracer-variance terms (kappa_e field) on the generic kernel
+    grp, _, ints2 = run(ops, fields=False)     # integrals only: ONE launch of the class-sum kernel, nu_e inside the dissipation's
+    assert grp.plan.variant == 1               # items and kappa_e = nu_e / Pr on the tracer gradients' faces
     for op, w_, integ in zip(ops, want, ints2):
         assert abs(integ - K.integral(w_, st.og, "ccc")) <= 1e-12 * integral_scale(st.og, w_, "ccc"), op.name
     grp, vals, _ = run(ops[:5], integrals=False)                 # the KE budget alone: no generic launch
@@ -184,10 +184,11 @@ def test_les_closure_budget_splits_over_the_pipelined_kernels(stretched):
 @pytest.mark.parametrize("stretched", [False, True], ids=["regular", "stretched"])
 @pytest.mark.parametrize("closure", ["smagorinsky_like", "tuple"])
 def test_eddy_viscosity_dissipation_as_class_sums(stretched, closure):
-    """Integral(DissipationRate) under SmagorinskyLilly- / AMD-like closures (a nu_e field, alone or in a tuple with a constant
-    viscosity) on the class-sum kernel: nu at ccc for the diagonal strains, its four-point means at ffc / fcf / cff for the edges,
-    inside the sums.  Whole domain and random y / z windows against the oracle's per-cell values times their volumes and against
-    the velocity-gradient kernel; the closure-independent KE-budget terms ride in the same launch."""
+    """The KE + tracer-variance budget integrals under SmagorinskyLilly- / AMD-like closures (a nu_e field, alone or in a tuple
+    with constant coefficients; kappa_e = nu_e / Pr) on the class-sum kernel: nu at ccc for the diagonal strains, its four-point
+    means at ffc / fcf / cff for the edges, kappa on each tracer-gradient face, all inside the sums.  Whole domain and random
+    y / z windows against the oracle's per-cell values times their volumes and against the split plan (budget kernel +
+    velocity-gradient kernel + generic kernel)."""
     st = State(size=(64, 40, 30), stretched=stretched, device="cuda")
     ops, oc = budget(st, closure=closure)
     want = oracle_budget(st, oc)
@@ -199,7 +200,7 @@ def test_eddy_viscosity_dissipation_as_class_sums(stretched, closure):
     for _ in range(3):
         j = sorted(rng.integers(1, Ny + 1, 2)); k = sorted(rng.integers(1, Nz + 1, 2))
         windows.append((int(j[0]), int(j[1]), int(k[0]), int(k[1])))
-    ke = ops[:5]                                                    # K, ADV, PR, w b, eps
+    ke = ops                                                        # K, ADV, PR, w b, eps, chi, 2 c div(kappa grad c)
     os.environ["OCB_FUSED_KCHUNK"] = "16"
     try:
         for win in windows:
@@ -212,7 +213,7 @@ def test_eddy_viscosity_dissipation_as_class_sums(stretched, closure):
                 split = ocb.FusedDiagnostics(*[ocb.Integral(o, indices=idx) for o in ke]).compute()
             finally:
                 os.environ.pop("OCB_DISABLE_SUMS_NUF", None)
-            assert split.plan.variant == 5                          # budget kernel + velocity-gradient kernel
+            assert split.plan.variant == 6                          # budget kernel + velocity-gradient kernel + generic kernel
             for o, w_, a, b_ in zip(ke, want, grp.integrals(), split.integrals()):
                 ww, vw = w_[:, jlo - 1:jhi, klo - 1:khi], vol[:, jlo - 1:jhi, klo - 1:khi]
                 ref, scale = float(np.sum(ww * vw)), float(np.sum(np.abs(ww) * vw))
