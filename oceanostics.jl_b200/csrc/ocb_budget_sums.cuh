@@ -53,7 +53,7 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
   constexpr bool NEED_B = H_WB || H_CHI || H_CDF, NEED_P = H_PR, NEED_S = H_EPS || H_ADV || H_EPSP;
   constexpr int NF = 3 + (NEED_B ? 1 : 0) + (NEED_P ? 1 : 0) + (NUF ? 1 : 0);
   constexpr int F_B = 3, F_P = NEED_B ? 4 : 3, F_N = NF - 1;
-  static_assert(!NUF || (H_EPS && !PZ), "the eddy-viscosity variant is the plain dissipation's");
+  static_assert(!NUF || H_EPS || H_EPSP, "the eddy-viscosity variant needs a dissipation term");
 
   extern __shared__ __align__(1024) double smem_d[];
   double* tiles = smem_d;                                                      // [NS][NF][TILE]
@@ -279,19 +279,20 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
         const double ucq = uc[r] - Un, vcq = vc[r] - Vn, wcq = wc[r] - Wn, upq = up[r] - Un1, vpq = vp[r] - Vn1;
         const double S13q = H_EPSP ? fma(-(STR ? rzf0 : rdz), dUz, S13) : 0.0, S23q = H_EPSP ? fma(-(STR ? rzf0 : rdz), dVz, S23) : 0.0, dwzq = dwz - dWz;
         // first factors of the dissipation's items: the item's viscosity times the strain (NUF; otherwise nu is applied after the loop)
-        double s12w = S12, s13w = S13, s23w = S23, axw = ax, ayw = ay, dwzw = dwz;
+        double s12w = S12, s13w = S13, s23w = S23, axw = ax, ayw = ay, dwzw = dwz, s13qw = S13q, s23qw = S23q, dwzqw = dwzq;
         if (NUF) {
           const double nffc = fma(0.25, (Tn[o - TWK - 1] + Tn[o - TWK]) + XNc[r], P.nu);
           const double nfcf = fma(0.25, XNp[r] + XNc[r], P.nu), ncff = fma(0.25, YNp[r] + YNc[r], P.nu);
           const double ncc = P.nu + nc[r], nccp = P.nu + np[r];
           s12w = nffc * S12; s13w = nfcf * S13; s23w = ncff * S23; axw = ncc * ax; ayw = ncc * ay; dwzw = nccp * dwz;
+          if (H_EPSP) { s13qw = nfcf * S13q; s23qw = ncff * S23q; dwzqw = nccp * dwzq; }
         }
         if (FAST && STR) {
           if (H_EPSP) {
-            aEeP = fma(c0 * S12, S12, aEeP); aEeP = fma(dzf0 * S13q, S13q, aEeP); aEeP = fma(dzf0 * S23q, S23q, aEeP);
-            aEzP = fma(rzc1 * dwzq, dwzq, aEzP);
+            aEeP = fma(c0 * s12w, S12, aEeP); aEeP = fma(dzf0 * s13qw, S13q, aEeP); aEeP = fma(dzf0 * s23qw, S23q, aEeP);
+            aEzP = fma(rzc1 * dwzqw, dwzq, aEzP);
           }
-          if (H_EPSP && !H_EPS) { aEx = fma(c0 * ax, ax, aEx); aEy = fma(c0 * ay, ay, aEy); }
+          if (H_EPSP && !H_EPS) { aEx = fma(c0 * axw, ax, aEx); aEy = fma(c0 * ayw, ay, aEy); }
           if (H_TKE) { aKP = fma(c0 * ucq, ucq, aKP); aKP = fma(c0 * vcq, vcq, aKP); aKP = fma(hzw * wcq, wcq, aKP); }
           if (H_SP) {                                        // (the weights are in GU*, GV*; dz_c cancels in the W part)
             aSuv = fma((ww - Wn) + wcq, fma(GUc, ucq, GUp * upq), aSuv);
@@ -315,10 +316,10 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
           if (H_CDF) aD = fma(bp[r], lap, aD);
         } else if (FAST) {
           if (H_EPSP) {
-            aEeP = fma(S12, S12, aEeP); aEeP = fma(S13q, S13q, aEeP); aEeP = fma(S23q, S23q, aEeP);
-            aEzP = fma(dwzq, dwzq, aEzP);
+            aEeP = fma(s12w, S12, aEeP); aEeP = fma(s13qw, S13q, aEeP); aEeP = fma(s23qw, S23q, aEeP);
+            aEzP = fma(dwzqw, dwzq, aEzP);
           }
-          if (H_EPSP && !H_EPS) { aEx = fma(ax, ax, aEx); aEy = fma(ay, ay, aEy); }
+          if (H_EPSP && !H_EPS) { aEx = fma(axw, ax, aEx); aEy = fma(ayw, ay, aEy); }
           if (H_TKE) { aKP = fma(ucq, ucq, aKP); aKP = fma(vcq, vcq, aKP); aKP = fma(wcq, wcq, aKP); }
           if (H_SP) {
             aSuv = fma((ww - Wn) + wcq, fma(GUc, ucq, GUp * upq), aSuv);
@@ -351,8 +352,8 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
           }
           if (H_EPS || H_EPSP) { aEx = fma(al * G0 * axw, ax, aEx); aEy = fma(al * G0 * ayw, ay, aEy); }
           if (H_EPSP) {
-            aEeP = fma(hy * G0 * S12, S12, aEeP); aEeP = fma(al * (hz * dzf0) * S13q, S13q, aEeP); aEeP = fma(hy * (hz * dzf0) * S23q, S23q, aEeP);
-            aEzP = fma(al * g1 * rzc1 * dwzq, dwzq, aEzP);
+            aEeP = fma(hy * G0 * s12w, S12, aEeP); aEeP = fma(al * (hz * dzf0) * s13qw, S13q, aEeP); aEeP = fma(hy * (hz * dzf0) * s23qw, S23q, aEeP);
+            aEzP = fma(al * g1 * rzc1 * dwzqw, dwzq, aEzP);
           }
           if (H_TKE) { aKP = fma(al * G0 * ucq, ucq, aKP); aKP = fma(hy * G0 * vcq, vcq, aKP); aKP = fma(al * hzK * wcq, wcq, aKP); }
           if (H_SP) {
@@ -390,8 +391,8 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
           }
           if (H_EPS || H_EPSP) { aEx = fma(al * g0 * axw, ax, aEx); aEy = fma(al * g0 * ayw, ay, aEy); }
           if (H_EPSP) {
-            aEeP = fma(hy * g0 * S12, S12, aEeP); aEeP = fma(al * hz * S13q, S13q, aEeP); aEeP = fma(hy * hz * S23q, S23q, aEeP);
-            aEzP = fma(al * g1 * dwzq, dwzq, aEzP);
+            aEeP = fma(hy * g0 * s12w, S12, aEeP); aEeP = fma(al * hz * s13qw, S13q, aEeP); aEeP = fma(hy * hz * s23qw, S23q, aEeP);
+            aEzP = fma(al * g1 * dwzqw, dwzq, aEzP);
           }
           if (H_TKE) { aKP = fma(al * g0 * ucq, ucq, aKP); aKP = fma(hy * g0 * vcq, vcq, aKP); aKP = fma(al * hz * wcq, wcq, aKP); }
           if (H_SP) {
@@ -454,7 +455,7 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
   acc[FD_EPS] = (NUF ? 1.0 : P.nu) * (aEe + 2.0 * (rdx2 * aEx + rdy2 * aEy + fz2 * aEz));      // NUF: the viscosities are inside the sums
   acc[FD_CHI] = 2.0 * (NUF ? 1.0 : P.kappa) * (rdx2 * aCx + rdy2 * aCy + fz2 * aCz);
   acc[FD_CDF] = 2.0 * (NUF ? 1.0 : P.kappa) * aD;
-  acc[FD_EPSP] = P.nu * (aEeP + 2.0 * (rdx2 * aEx + rdy2 * aEy + fz2 * aEzP));
+  acc[FD_EPSP] = (NUF ? 1.0 : P.nu) * (aEeP + 2.0 * (rdx2 * aEx + rdy2 * aEy + fz2 * aEzP));
   acc[FD_TKE] = 0.5 * aKP;
   acc[FD_SP] = -fz * (0.25 * aSuv + 0.5 * aSw);
   if (P.nslots > 0) {

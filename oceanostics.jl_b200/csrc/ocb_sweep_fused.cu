@@ -868,14 +868,14 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
   bool nuf = false;
   if (closure_fields && (mask & CLOSURE_TERMS)) {
     const ocb_field& nf = in->closure.nu_fields[0];
-    const bool nu_ok = sums_convention && !any_pert && in->closure.n_nu_fields == 1 && tma_compatible(nf, grid) &&
+    const bool nu_ok = sums_convention && in->closure.n_nu_fields == 1 && tma_compatible(nf, grid) &&
                        nf.loc[0] == OCB_CENTER && nf.loc[1] == OCB_CENTER && nf.loc[2] == OCB_CENTER && !getenv("OCB_DISABLE_SUMS_NUF");
     // the tracer-variance terms: a constant kappa, or kappa_e = scale x the SAME field (SmagorinskyLilly's nu_e / Pr)
     const ocb_field& kf = in->closure.kappa_fields[0];
     const bool kappa_ok = in->closure.n_kappa_fields == 0 ||
                           (in->closure.n_kappa_fields == 1 && kf.data == nf.data && kf.stride[1] == nf.stride[1] && kf.stride[2] == nf.stride[2]);
     const int kappa_terms = (1 << FD_CHI) | (1 << FD_CDF);
-    if (!nu_ok || (mask & (1 << FD_EPSP)) || ((mask & kappa_terms) && !kappa_ok)) return OCB_OK;   // velocity-gradient / generic kernels
+    if (!nu_ok || ((mask & kappa_terms) && !kappa_ok)) return OCB_OK;   // velocity-gradient / generic kernels
     nuf = true;
   }
   if ((mask & (1 << FD_EPV)) && cell_req >= 0 && (SP.req[cell_req].lo[2] != 1 || SP.req[cell_req].hi[2] != grid->N[2])) return OCB_OK;
@@ -932,8 +932,15 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
   if (sums && nuf) {
     // eddy-viscosity dissipation: the all-terms class sums with nu_e inside (needs all five other inputs as well)
     const bool narrow = (grid->H[0] & 1) && !getenv("OCB_SUMS_WIDE_TILES");
-    if (!tma_compatible(in->b, grid) || !tma_compatible(in->p, grid)) { delete fp; return OCB_OK; }
-    rc = stretched ? setup_sums_pitch<ALL, 4, 4, 3, 2, true, true>(fp, narrow) : setup_sums_pitch<ALL, 4, 4, 3, 2, false, true>(fp, narrow);
+    constexpr int TKEB_N = (1 << FD_SP) | (1 << FD_EPSP) | (1 << FD_TKE), TKEP_N = TKEB_N | (1 << FD_PR) | (1 << FD_K);
+    if (mask & TKEB_N) {
+      // about mean profiles: the TKE budget with pressure redistribution {SP, eps(u - U), PR, K / TKE} (u, v, w, p, nu_e)
+      if ((mask & ~TKEP_N) || !tma_compatible(in->p, grid)) { delete fp; return OCB_OK; }
+      rc = stretched ? setup_sums_pitch<TKEP_N, 4, 4, 3, 2, true, true>(fp, narrow) : setup_sums_pitch<TKEP_N, 4, 4, 3, 2, false, true>(fp, narrow);
+    } else {
+      if (!tma_compatible(in->b, grid) || !tma_compatible(in->p, grid)) { delete fp; return OCB_OK; }
+      rc = stretched ? setup_sums_pitch<ALL, 4, 4, 3, 2, true, true>(fp, narrow) : setup_sums_pitch<ALL, 4, 4, 3, 2, false, true>(fp, narrow);
+    }
   } else if (stretched && sums) {
     const bool narrow = (grid->H[0] & 1) && !getenv("OCB_SUMS_WIDE_TILES");
     constexpr int TKEB_S = (1 << FD_SP) | (1 << FD_EPSP) | (1 << FD_TKE);

@@ -224,6 +224,37 @@ def test_eddy_viscosity_dissipation_as_class_sums(stretched, closure):
 
 
 @pytest.mark.parametrize("stretched", [False, True], ids=["regular", "stretched"])
+@pytest.mark.parametrize("closure", ["smagorinsky_like", "tuple"])
+def test_tke_budget_integrals_under_eddy_viscosity_closures(stretched, closure):
+    """The boundary-layer LES case: the TKE budget about horizontal-mean profiles {shear production, dissipation of u - U,
+    pressure redistribution, TKE} as integrals under an eddy-viscosity closure, regular or stretched z, in ONE launch of the
+    class-sum kernel (nu_e a TMA-fed input, its means on the strain edges); against the oracle and the generic kernel."""
+    from cases import build_cases
+    st = State(size=(64, 44, 26), stretched=stretched, device="cuda")
+    cases = {c[0]: c for c in build_cases(st, closure, mean="profile")}
+    names = ["ShearProductionRate", "DissipationRate_perturbation", "KineticEnergyPressureRedistribution", "TurbulentKineticEnergy"]
+    ops = [cases[nm][1] for nm in names]
+    ii, jj, kk = st.og.indices("ccc")
+    V = np.broadcast_to(st.og.V("ccc", ii, jj, kk), cases[names[0]][2].shape)
+    Ny, Nz = 44, 26
+    for win in (None, (3, 40, 2, 25), (1, 1, 1, Nz), (Ny, Ny, Nz, Nz), (10, 30, 13, 13)):
+        idx = None if win is None else (None, (win[0], win[1]), (win[2], win[3]))
+        jlo, jhi, klo, khi = win or (1, Ny, 1, Nz)
+        grp = ocb.FusedDiagnostics(*[ocb.Integral(o, indices=idx) for o in ops]).compute()
+        assert grp.plan.variant == 1 and grp.plan.n_launches == 2, (win, grp.plan.variant)
+        os.environ["OCB_DISABLE_FUSED"] = "1"
+        try:
+            gen = ocb.FusedDiagnostics(*[ocb.Integral(o, indices=idx) for o in ops]).compute()
+        finally:
+            os.environ.pop("OCB_DISABLE_FUSED", None)
+        for nm, a, b_ in zip(names, grp.integrals(), gen.integrals()):
+            w_, v_ = cases[nm][2][:, jlo - 1:jhi, klo - 1:khi], V[:, jlo - 1:jhi, klo - 1:khi]
+            ref, scale = float(np.sum(w_ * v_)), float(np.sum(np.abs(w_) * v_))
+            assert abs(a - ref) <= 1e-12 * scale, (nm, win, a, ref, scale)
+            assert abs(a - b_) <= 1e-12 * scale, (nm, win, a, b_, scale)
+
+
+@pytest.mark.parametrize("stretched", [False, True], ids=["regular", "stretched"])
 def test_windowed_budget_fields_match_the_full_fields(stretched):
     """Field(op, indices=(:, j-window, k-window)) of all seven terms in one sweep of the pipelined kernel: the window holds
     exactly the full field's values (the z window of a stretched grid starts at a plane with other metrics than plane 1)."""
