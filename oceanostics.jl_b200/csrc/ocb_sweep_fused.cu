@@ -1079,7 +1079,8 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
 
 int ocb_fused_nblocks(const ocb_fused_plan* fp) { return fp->nblocks; }
 
-bool ocb_fused_ring_capable(const ocb_fused_plan* fp) { return fp->sums && fp->P.y_ring; }
+// (the eddy-viscosity variant reads a sixth input whose halo rows the ring step does not push: not ring-capable)
+bool ocb_fused_ring_capable(const ocb_fused_plan* fp) { return fp->sums && fp->P.y_ring && !fp->nuf; }
 
 int ocb_fused_execute_gated(ocb_fused_plan* fp, double* partial, long long* flags, long long step, long long timeout_cycles, cudaStream_t st) {
   OCB_REQUIRE(ocb_fused_ring_capable(fp), "gated execution needs the class-sum kernel over a whole periodic y extent");
