@@ -147,7 +147,19 @@ def run_secondary(ocb, torch, run, peak, steps=5):
             ms = _timed(torch, grp.plan.execute, reps=steps)
             out[key] = _entry(ms, Nx * Ny * Nz, grp.plan.algorithmic_bytes / (Nx * Ny * Nz), peak, variant=VARIANTS.get(grp.plan.variant),
                               workload=f"768x768x384 F32 stretched z, {name}: eps + |S| fields")
-            del grp, m, eps, smod
+            del grp, eps, smod
+            if key == "config4_smagorinsky":
+                # the same Float32 LES state: the seven KE + tracer-variance budget integrals in one launch (Float32-input class sums)
+                for f in (m.tracers.b, m.pressures.pNHS):
+                    f.interior.copy_(torch.randn(f.interior.shape, device=dev, dtype=torch.float32))
+                m.fill_halo_regions()
+                grp = ocb.FusedDiagnostics(*[ocb.Integral(o) for o in budget_ops(ocb, m)])
+                ms = _timed(torch, grp.plan.execute, reps=steps)
+                out["config4_les_budget_integrals"] = _entry(
+                    ms, Nx * Ny * Nz, grp.plan.algorithmic_bytes / (Nx * Ny * Nz), peak, variant=VARIANTS.get(grp.plan.variant), launches=grp.plan.n_launches,
+                    workload="768x768x384 F32 stretched z, SmagorinskyLilly-like nu_e field: K, ADV, PR, w b, eps, chi, 2c div(kappa grad c) integrals, one sweep")
+                del grp
+            del m
         del nu_e, grid
     except Exception as e:  # pragma: no cover
         out["config4"] = {"error": repr(e)[:300]}

@@ -25,6 +25,7 @@
 // TWK = tile row pitch in elements: 34 (west halo + 32 + east halo) when the tile's first column is 16-byte aligned for every
 // tile (odd x halo), else 36 (one spare column either side of the aligned box start, as in ocb_budget_kernel).
 constexpr int sums_tile_elems(int tw, int tr) { return ((tw * tr * 8 + 127) / 128) * 128 / 8; }   // 128-byte aligned field tiles
+constexpr int sums_tile_elems_of(int tw, int tr, int esize) { return ((tw * tr * esize + 127) / 128) * 128 / esize; }
 
 // STR = true: z is a stretched axis (the seven budget terms only).  The class sums then carry per-plane weights -- the cell's dz_c
 // for the items of a cell plane, dz_f of the face for the fcf / cff strain edges, (dz_c(n-1) + dz_c(n)) / 2 for the z-face
@@ -36,13 +37,22 @@ constexpr int sums_tile_elems(int tw, int tr) { return ((tw * tr * 8 + 127) / 12
 // dissipation's items then carry their own viscosity -- nu at ccc for the diagonal strains, the four-point means of nu_e at
 // ffc / fcf / cff for the edges (Oceananigans' interpolation of the closure field, as K1c and the oracle form it) -- inside the
 // class sums instead of one factor after the loop; nu_e is a sixth input tile.
-template <int MASK, int NW, int RY, int NS, int MINB, int TWK, bool STR = false, bool NUF = false>
+// TIN = float: the INPUTS are Float32 fields (the sums, like every integral of the library, are Float64).  A Float32 parent row
+// is not a 16-byte multiple in general (Nx + 2H = 774 floats), which TMA cannot stride over; two rows are (Ny + 2H even), so the
+// tensor maps describe each plane as rows of 2 (Nx + 2H) elements and a tile comes as TWO boxes per field -- the parent rows of
+// one parity and those of the other, each with its own 16-byte-aligned start column -- into the two halves of the tile.  Every
+// access to the tile goes through the per-row offsets `ro[]`; nothing else of the kernel changes (TWK = 40 for this form).
+template <int MASK, int NW, int RY, int NS, int MINB, int TWK, bool STR = false, bool NUF = false, class TIN = double>
 __global__ void __launch_bounds__(NW * 32, MINB)
 ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_constant__ CUtensorMap mu, const __grid_constant__ CUtensorMap mv,
                        const __grid_constant__ CUtensorMap mw, const __grid_constant__ CUtensorMap mb, const __grid_constant__ CUtensorMap mp,
                        const __grid_constant__ CUtensorMap mn) {
   using G = Geo<NW, RY>;
-  constexpr int TILE = sums_tile_elems(TWK, G::TR);
+  constexpr bool F32IN = sizeof(TIN) == 4;
+  // (Float32: each of the two boxes of a tile starts on its own 128-byte boundary, as TMA destinations must)
+  constexpr int HALF = sums_tile_elems_of(TWK, G::TR / 2, (int)sizeof(TIN));
+  constexpr int TILE = F32IN ? 2 * HALF : sums_tile_elems_of(TWK, G::TR, (int)sizeof(TIN));
+  static_assert(!F32IN || G::TR % 2 == 0, "the two-box form needs an even number of tile rows");
   constexpr bool H_K = MASK & (1 << FD_K), H_ADV = MASK & (1 << FD_ADV), H_PR = MASK & (1 << FD_PR), H_WB = MASK & (1 << FD_WB),
                  H_EPS = MASK & (1 << FD_EPS), H_CHI = MASK & (1 << FD_CHI), H_CDF = MASK & (1 << FD_CDF),
                  H_SP = MASK & (1 << FD_SP), H_EPSP = MASK & (1 << FD_EPSP), H_TKE = MASK & (1 << FD_TKE);
@@ -56,8 +66,8 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
   static_assert(!NUF || H_EPS || H_EPSP, "the eddy-viscosity variant needs a dissipation term");
 
   extern __shared__ __align__(1024) double smem_d[];
-  double* tiles = smem_d;                                                      // [NS][NF][TILE]
-  double* red = tiles + NS * NF * TILE;                                     // [NW]
+  TIN* tiles = reinterpret_cast<TIN*>(smem_d);                                 // [NS][NF][TILE]
+  double* red = reinterpret_cast<double*>(tiles + NS * NF * TILE);             // [NW]
   uint64_t* full = reinterpret_cast<uint64_t*>(red + NW);                      // [NS]
 
   const int lane = threadIdx.x, warp = threadIdx.y;
@@ -84,20 +94,43 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
   const int jr0 = warp * RY;
 
   // ---- TMA ring (tiles of TWK x (BR + 2) elements per field, 16-byte aligned box start) -------------------------
-  constexpr uint32_t STAGE_BYTES = (uint32_t)(NF * TWK * G::TR * 8);
+  constexpr uint32_t STAGE_BYTES = (uint32_t)(NF * TWK * G::TR * sizeof(TIN));
   const int px_raw = i0 - 1 + P.hx - 1, py = j0 - 1 + P.hy - 1;
   const int xoff = px_raw & 1, px = px_raw - xoff;
+  // Float32 inputs: box b holds the tile rows b, b + 2, .. (parent rows py + b, py + b + 2, ..: one parity), read from the
+  // merged-row view at column (parity) * rowlen + px_raw, rounded down to a 16-byte boundary (4 elements)
+  int bx[2] = {0, 0}, by[2] = {0, 0}, bo[2] = {0, 0};
+  if (F32IN) {
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int xr = ((py + b) & 1) * P.rowlen + px_raw;
+      bx[b] = xr & ~3; bo[b] = xr & 3; by[b] = (py + b) >> 1;
+    }
+  }
   auto issue = [&](int n) {
     const int s = (n - n_first) % NS;
-    double* dst = tiles + s * (NF * TILE);
+    TIN* dst = tiles + s * (NF * TILE);
     mbar_expect_tx(&full[s], STAGE_BYTES);
     const int pz = n + P.hz - 1;
-    tma_load_3d(dst + 0 * TILE, &mu, &full[s], px, py, pz);
-    tma_load_3d(dst + 1 * TILE, &mv, &full[s], px, py, pz);
-    tma_load_3d(dst + 2 * TILE, &mw, &full[s], px, py, pz);
-    if (NEED_B) tma_load_3d(dst + F_B * TILE, &mb, &full[s], px, py, pz);
-    if (NEED_P) tma_load_3d(dst + F_P * TILE, &mp, &full[s], px, py, pz);
-    if (NUF) tma_load_3d(dst + F_N * TILE, &mn, &full[s], px, py, pz);
+    if (!F32IN) {
+      tma_load_3d(dst + 0 * TILE, &mu, &full[s], px, py, pz);
+      tma_load_3d(dst + 1 * TILE, &mv, &full[s], px, py, pz);
+      tma_load_3d(dst + 2 * TILE, &mw, &full[s], px, py, pz);
+      if (NEED_B) tma_load_3d(dst + F_B * TILE, &mb, &full[s], px, py, pz);
+      if (NEED_P) tma_load_3d(dst + F_P * TILE, &mp, &full[s], px, py, pz);
+      if (NUF) tma_load_3d(dst + F_N * TILE, &mn, &full[s], px, py, pz);
+    } else {
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        TIN* half = dst + b * HALF;
+        tma_load_3d(half + 0 * TILE, &mu, &full[s], bx[b], by[b], pz);
+        tma_load_3d(half + 1 * TILE, &mv, &full[s], bx[b], by[b], pz);
+        tma_load_3d(half + 2 * TILE, &mw, &full[s], bx[b], by[b], pz);
+        if (NEED_B) tma_load_3d(half + F_B * TILE, &mb, &full[s], bx[b], by[b], pz);
+        if (NEED_P) tma_load_3d(half + F_P * TILE, &mp, &full[s], bx[b], by[b], pz);
+        if (NUF) tma_load_3d(half + F_N * TILE, &mn, &full[s], bx[b], by[b], pz);
+      }
+    }
   };
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) mbar_init(&full[s], 1);
@@ -125,6 +158,13 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
 
   const double rdx = P.rdx, rdy = P.rdy, rdz = P.rdz;
   const double rdx2 = rdx * rdx, rdy2 = rdy * rdy, rdz2 = rdz * rdz;
+  // tile offsets of this lane's cell in the thread's rows, the row to the south (ro[0]) and the row to the north (ro[RY + 1])
+  int ro[RY + 2];
+#pragma unroll
+  for (int q = 0; q < RY + 2; ++q) {
+    const int tr = jr0 + q;                                  // tile row (row 0 = the south halo row of the block)
+    ro[q] = F32IN ? (tr & 1) * HALF + (tr >> 1) * TWK + bo[tr & 1] + lane + 1 : tr * TWK + lane + xoff + 1;
+  }
 
   // ---- per-row classes (functions of j only, warp-uniform) ----------------------------------------------------------
   // alpha = [row j in the window], beta = [row j-1 in it], alphan = [row j+1 in it]; rows jy_lo .. jy_hi+1 carry items
@@ -172,23 +212,21 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
     double (&up)[RY] = cu[Q], (&vp)[RY] = cv[Q], (&wp)[RY] = cw[Q], (&bp)[RY] = cb[Q], (&pp)[RY] = cp[Q];
     double (&nc)[RY] = cn[C], (&np)[RY] = cn[Q], (&XNc)[RY] = xn[C], (&XNp)[RY] = xn[Q], (&YNc)[RY] = yn[C], (&YNp)[RY] = yn[Q];
     mbar_wait(&full[s], phase);
-    const double* T = tiles + s * (NF * TILE);
-    const double* Tu = T, *Tv = T + TILE, *Tw = T + 2 * TILE, *Tb = T + F_B * TILE, *Tp = T + F_P * TILE, *Tn = T + F_N * TILE;
+    const TIN* T = tiles + s * (NF * TILE);
+    const TIN* Tu = T, *Tv = T + TILE, *Tw = T + 2 * TILE, *Tb = T + F_B * TILE, *Tp = T + F_P * TILE, *Tn = T + F_N * TILE;
     if (++s == NS) { s = 0; phase ^= 1; }
-    const int col = lane + xoff + 1;                       // tile column of this lane's cell
-    const int row0 = jr0 + 1;                              // tile row of this thread's first cell
 
     // ---- centre values of the thread's rows, the row to the south and the row to the north ----------------------------
 #pragma unroll
     for (int r = 0; r < RY; ++r) {
-      const int o = (row0 + r) * TWK + col;
+      const int o = ro[r + 1];
       uc[r] = Tu[o]; vc[r] = Tv[o]; wc[r] = Tw[o];
       bc[r] = NEED_B ? Tb[o] : 0.0;
       pc[r] = NEED_P ? Tp[o] : 0.0;
-      if (NUF) { nc[r] = Tn[o]; XNc[r] = Tn[o - 1] + nc[r]; YNc[r] = Tn[o - TWK] + nc[r]; }   // (every step: the next one's face means need them)
+      if (NUF) { nc[r] = Tn[o]; XNc[r] = Tn[o - 1] + nc[r]; YNc[r] = Tn[ro[r]] + nc[r]; }   // (every step: the next one's face means need them)
     }
     if (n > n_first) {
-      const int oS = (row0 - 1) * TWK + col, oN = (row0 + RY) * TWK + col;
+      const int oS = ro[0], oN = ro[RY + 1];
       const double uS = Tu[oS], wS = Tw[oS], vS = Tv[oS], vN = Tv[oN];
       const double bS = NEED_B ? Tb[oS] : 0.0, bN = (NEED_B && H_CDF) ? Tb[oN] : 0.0, pS = NEED_P ? Tp[oS] : 0.0;
       // plane classes (block-uniform): g0 = [this chunk owns step n and plane n is in the window], g1, g2: same for n-1, n-2
@@ -227,7 +265,7 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
       // one row of this thread at step n.  FAST (compile-time tag): every class weight is the interior one
       auto do_row = [&](auto fast_tag, const int r) {
         constexpr bool FAST = decltype(fast_tag)::value;
-        const int o = (row0 + r) * TWK + col;
+        const int o = ro[r + 1];
         const double us = r ? uc[r > 0 ? r - 1 : 0] : uS, ws = r ? wc[r > 0 ? r - 1 : 0] : wS;
         const double vn = (r < RY - 1) ? vc[r < RY - 1 ? r + 1 : 0] : vN;
         const double ue = Tu[o + 1], vw = Tv[o - 1], ww = Tw[o - 1];
@@ -259,7 +297,7 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
         if (NUF && (H_CHI || H_CDF)) {
           const double hs = 0.5 * P.kappa_scale;
           dbxw = fma(hs, XNc[r], P.kappa) * dbx; dbyw = fma(hs, YNc[r], P.kappa) * dby; dbzw = fma(hs, np[r] + nc[r], P.kappa) * dbz;
-          if (H_CDF) { kxe = fma(hs, nc[r] + Tn[o + 1], P.kappa); kyn = fma(hs, nc[r] + Tn[o + TWK], P.kappa); }
+          if (H_CDF) { kxe = fma(hs, nc[r] + Tn[o + 1], P.kappa); kyn = fma(hs, nc[r] + Tn[ro[r + 2]], P.kappa); }
         }
         double lap = 0.0;
         if (H_CDF) {
@@ -281,7 +319,7 @@ ocb_budget_sums_kernel(const __grid_constant__ FusedParams P, const __grid_const
         // first factors of the dissipation's items: the item's viscosity times the strain (NUF; otherwise nu is applied after the loop)
         double s12w = S12, s13w = S13, s23w = S23, axw = ax, ayw = ay, dwzw = dwz, s13qw = S13q, s23qw = S23q, dwzqw = dwzq;
         if (NUF) {
-          const double nffc = fma(0.25, (Tn[o - TWK - 1] + Tn[o - TWK]) + XNc[r], P.nu);
+          const double nffc = fma(0.25, (Tn[ro[r] - 1] + Tn[ro[r]]) + XNc[r], P.nu);
           const double nfcf = fma(0.25, XNp[r] + XNc[r], P.nu), ncff = fma(0.25, YNp[r] + YNc[r], P.nu);
           const double ncc = P.nu + nc[r], nccp = P.nu + np[r];
           s12w = nffc * S12; s13w = nfcf * S13; s23w = ncff * S23; axw = ncc * ax; ayw = ncc * ay; dwzw = nccp * dwz;

@@ -50,6 +50,7 @@ struct FusedParams {
   int kz_lo, kz_hi;                // 1-based inclusive z window (the whole interior, or a z slab of it)
   int jy_lo, jy_hi;                // 1-based inclusive y window (rows next to a slab edge are swept separately)
   double rdx, rdy, rdz, nu, kappa, ghat_z, V;
+  int rowlen;                      // Float32-input class sums: elements per parent row (the merged-row view's odd rows start there)
   double kappa_scale;              // class-sum NUF variant: kappa at a face = kappa + kappa_scale x mean of nu_e (kappa_e = nu_e / Pr)
   FusedOut o[FD_N];
   long long os[3];                 // element strides shared by every output field
@@ -671,6 +672,7 @@ struct ocb_fused_plan {
   size_t smem;
   void (*kernel)(FusedParams, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap);
   bool nuf;                        // the eddy-viscosity variant of the class-sum kernel (nu_e as sixth input)
+  double* ztab_d;                  // Float32 plans on a stretched axis: Float64 copies of the z-metric tables
 };
 
 template <int MASK, int NW, int RY, int NS>
@@ -706,14 +708,15 @@ static int setup_variant_stretched(ocb_fused_plan* fp) {
   return OCB_OK;
 }
 
-template <int MASK, int NW, int RY, int NS, int MINB, int TWK = TW, bool STR = false, bool NUF = false>
+template <int MASK, int NW, int RY, int NS, int MINB, int TWK = TW, bool STR = false, bool NUF = false, class TIN = double>
 static int setup_sums(ocb_fused_plan* fp) {
   using G = Geo<NW, RY>;
   constexpr bool NEED_B = MASK & ((1 << FD_WB) | (1 << FD_CHI) | (1 << FD_CDF)), NEED_P = MASK & (1 << FD_PR);
   constexpr int NF = 3 + (NEED_B ? 1 : 0) + (NEED_P ? 1 : 0) + (NUF ? 1 : 0);
   fp->nw = NW; fp->ry = RY; fp->ns = NS; fp->mask = MASK; fp->sums = true; fp->minb = MINB; fp->tw = TWK; fp->nuf = NUF;
-  fp->smem = sizeof(double) * ((size_t)NS * NF * sums_tile_elems(TWK, G::TR) + NW) + sizeof(uint64_t) * NS;
-  auto kern = ocb_budget_sums_kernel<MASK, NW, RY, NS, MINB, TWK, STR, NUF>;
+  constexpr int TILE_E = sizeof(TIN) == 4 ? 2 * sums_tile_elems_of(TWK, G::TR / 2, 4) : sums_tile_elems_of(TWK, G::TR, (int)sizeof(TIN));
+  fp->smem = sizeof(TIN) * (size_t)NS * NF * TILE_E + sizeof(double) * NW + sizeof(uint64_t) * NS;
+  auto kern = ocb_budget_sums_kernel<MASK, NW, RY, NS, MINB, TWK, STR, NUF, TIN>;
   cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   fp->kernel = kern;
   OCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp->smem));
@@ -764,6 +767,30 @@ static bool profile_pointer(const ocb_field& f, int zloc, const double** out) {
   return true;
 }
 
+// Float32 fields: the merged-row view (two parent rows per tensor row) must stride by 16-byte multiples
+static bool tma_compatible_f32(const ocb_field& f, const ocb_grid* g) {
+  if (f.kind != OCB_FIELD_ARRAY || !f.data) return false;
+  for (int d = 0; d < 3; ++d) if (f.loc[d] == OCB_NOTHING || f.halo[d] != g->H[d]) return false;
+  if (f.stride[0] != 1) return false;
+  if (f.stride[1] != f.size[0] || f.stride[2] != (long long)f.size[0] * f.size[1]) return false;   // dense parent
+  if (((uintptr_t)f.data & 15) || (f.size[0] & 1) || (f.size[1] & 1) || ((f.stride[2] * 4) & 15)) return false;
+  return true;
+}
+static int make_map_f32(EncodeTiledFn enc, const ocb_field& f, int rows, CUtensorMap* map, int tw) {
+  cuuint64_t dims[3] = {(cuuint64_t)f.size[0] * 2, (cuuint64_t)f.size[1] / 2, (cuuint64_t)f.size[2]};
+  cuuint64_t strides[2] = {(cuuint64_t)f.stride[1] * 2 * 4, (cuuint64_t)f.stride[2] * 4};
+  cuuint32_t box[3] = {(cuuint32_t)tw, (cuuint32_t)(rows / 2), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, f.data, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) OCB_FAIL(OCB_ERR_CUDA, "cuTensorMapEncodeTiled (Float32, merged rows) failed with CUresult %d", (int)r);
+  return OCB_OK;
+}
+__global__ void ocb_f32_to_f64_kernel(const float* __restrict__ a, double* __restrict__ b, int n) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) b[t] = (double)a[t];
+}
+
 static bool tma_compatible(const ocb_field& f, const ocb_grid* g) {
   if (f.kind != OCB_FIELD_ARRAY || !f.data) return false;
   for (int d = 0; d < 3; ++d) if (f.loc[d] == OCB_NOTHING || f.halo[d] != g->H[d]) return false;
@@ -773,17 +800,15 @@ static bool tma_compatible(const ocb_field& f, const ocb_grid* g) {
   return true;
 }
 
-int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const ocb_request* reqs, int n,
-                         const SweepParams<float>&, ocb_fused_plan** out) {
-  (void)grid; (void)in; (void)reqs; (void)n;
-  *out = nullptr;      // Float32 plans run on the generic kernel (parent rows are not 16-byte multiples in general)
-  return OCB_OK;
-}
-
-int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const ocb_request* reqs, int n,
-                         const SweepParams<double>& SP, ocb_fused_plan** out) {
+// T = float: only integral-only plans of the seven budget terms, on the Float32-input form of the class-sum kernel
+template <class T>
+static int fused_try_create_t(const ocb_grid* grid, const ocb_sweep_inputs* in, const ocb_request* reqs, int n,
+                              const SweepParams<T>& SP, ocb_fused_plan** out) {
+  constexpr bool F32 = sizeof(T) == 4;
+  auto tma_compatible = [](const ocb_field& f, const ocb_grid* g) { return F32 ? tma_compatible_f32(f, g) : ::tma_compatible(f, g); };
   *out = nullptr;
   if (getenv("OCB_DISABLE_FUSED")) return OCB_OK;
+  if (F32 && getenv("OCB_DISABLE_SUMS_F32")) return OCB_OK;
   // ---- envelope ------------------------------------------------------------------------------------------
   // stretched z: the seven budget terms (no mean-flow operands, no potential vorticity) on the per-plane-metric variant
   const bool stretched = grid->dzc || grid->dzf;
@@ -814,6 +839,7 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
   }
   bool sums_convention = !any_outq && grid->topo[0] == OCB_PERIODIC && !getenv("OCB_FUSED_CELL_INTEGRALS") && (!stretched || str_sums_ok);
   for (int r = 0; r < n; ++r) if (reqs[r].diag == OCB_DIAG_EPV) sums_convention = false;
+  if (F32 && !sums_convention) return OCB_OK;
   for (int r = 0; r < n; ++r) {
     int d = fused_diag_index(reqs[r].diag);
     if (d < 0) return OCB_OK;
@@ -853,6 +879,7 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
     if (R.slot >= 0) { if (which_slot[d] >= 0) return OCB_OK; which_slot[d] = r; }
     mask |= 1 << d;
   }
+  if (F32 && ((mask & ~FD_BUDGET) || any_pert)) return OCB_OK;            // Float32: the seven plain budget terms
   // stretched z: the cell-exact variant evaluates the seven plain budget terms; the class-sum form also the TKE-budget terms
   constexpr int TKE_TERMS = (1 << FD_SP) | (1 << FD_EPSP) | (1 << FD_TKE);
   // (cell-exact: the seven plain terms, or the TKE budget about mean profiles {eps(u - U), SP, PR, K} -- no potential vorticity)
@@ -929,6 +956,12 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
   // OCB_SUMS_CONFIG="NW,RY,NS,MINB" picks another compiled shape of the all-terms kernel for tuning runs.
   const bool sums = sums_convention;
   const int njy = SP.req[0].hi[1] - SP.req[0].lo[1] + 1;
+  if constexpr (F32) {
+    // Float32 inputs: the all-terms class sums in the two-box tile form (40-column pitch), with the stretched / eddy-viscosity forms
+    if (!tma_compatible(in->b, grid) || !tma_compatible(in->p, grid)) { delete fp; return OCB_OK; }
+    if (stretched) rc = nuf ? setup_sums<ALL, 4, 4, 3, 2, 40, true, true, float>(fp) : setup_sums<ALL, 4, 4, 3, 2, 40, true, false, float>(fp);
+    else rc = nuf ? setup_sums<ALL, 4, 4, 3, 2, 40, false, true, float>(fp) : setup_sums<ALL, 4, 4, 3, 2, 40, false, false, float>(fp);
+  } else {
   if (sums && nuf) {
     // eddy-viscosity dissipation: the all-terms class sums with nu_e inside (needs all five other inputs as well)
     const bool narrow = (grid->H[0] & 1) && !getenv("OCB_SUMS_WIDE_TILES");
@@ -1008,6 +1041,7 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
   else if (nw == 6 && ry == 2) rc = setup_variant<ALL, 6, 2, 3>(fp, any_out);
   else if (nw == 8 && ry == 2) rc = setup_variant<ALL, 8, 2, 3>(fp, any_out);
   else rc = setup_variant<ALL, 12, 2, 3>(fp, any_out);
+  }
   if (rc != OCB_OK) { delete fp; return rc; }
   const bool vneed_b = fp->mask & ((1 << FD_WB) | (1 << FD_CHI) | (1 << FD_CDF) | (1 << FD_EPV)), vneed_p = fp->mask & (1 << FD_PR);
   if ((vneed_b && !tma_compatible(in->b, grid)) || (vneed_p && !tma_compatible(in->p, grid))) { delete fp; return OCB_OK; }
@@ -1059,7 +1093,20 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
   P.nu = in->closure.nu_const; P.kappa = in->closure.kappa_const; P.ghat_z = in->ghat[2];
   P.kappa_scale = in->closure.n_kappa_fields ? in->closure.kappa_scale[0] : 0.0;
   P.V = stretched ? grid->d[0] * grid->d[1] : grid->d[0] * grid->d[1] * grid->d[2];      // stretched: dz_c is the cell's integral weight
-  P.dzc = SP.g.dzc; P.dzf = SP.g.dzf; P.rdzc = SP.g.rdzc; P.rdzf = SP.g.rdzf;
+  P.rowlen = in->u.size[0];
+  if constexpr (F32) {
+    P.dzc = P.dzf = P.rdzc = P.rdzf = nullptr;
+    if (stretched) {
+      // Float64 copies of the four metric tables (contiguous in the plan's Float32 table block, each nz entries, pre-offset by Hz - 1)
+      const int nz = grid->N[2] + 2 * grid->H[2] + 1, off = grid->H[2] - 1;
+      OCB_CUDA(cudaMalloc(&fp->ztab_d, sizeof(double) * 4 * nz));
+      ocb_f32_to_f64_kernel<<<(4 * nz + 127) / 128, 128>>>(SP.g.dzc - off, fp->ztab_d, 4 * nz);
+      OCB_CUDA(cudaGetLastError());
+      P.dzc = fp->ztab_d + 0 * nz + off; P.dzf = fp->ztab_d + 1 * nz + off; P.rdzc = fp->ztab_d + 2 * nz + off; P.rdzf = fp->ztab_d + 3 * nz + off;
+    }
+  } else {
+    P.dzc = SP.g.dzc; P.dzf = SP.g.dzf; P.rdzc = SP.g.rdzc; P.rdzf = SP.g.rdzf;
+  }
   P.nslots = SP.nslots;
   P.Uz = Uz; P.Vz = Vz; P.Wz = Wz; P.eps_pert = eps_pert ? 1 : 0;
   for (int a = 0; a < 3; ++a) P.os[a] = os[a];
@@ -1070,11 +1117,20 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
   }
   const ocb_field* f[6] = {&in->u, &in->v, &in->w, vneed_b ? &in->b : &in->u, vneed_p ? &in->p : &in->u, fp->nuf ? &in->closure.nu_fields[0] : &in->u};
   for (int a = 0; a < 6; ++a) {
-    rc = make_map(enc, *f[a], BR + 2, &fp->maps[a], fp->sums ? fp->tw : TW);
+    rc = F32 ? make_map_f32(enc, *f[a], BR + 2, &fp->maps[a], fp->tw) : make_map(enc, *f[a], BR + 2, &fp->maps[a], fp->sums ? fp->tw : TW);
     if (rc != OCB_OK) { delete fp; return rc; }
   }
   *out = fp;
   return OCB_OK;
+}
+
+int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const ocb_request* reqs, int n,
+                         const SweepParams<float>& SP, ocb_fused_plan** out) {
+  return fused_try_create_t<float>(grid, in, reqs, n, SP, out);
+}
+int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const ocb_request* reqs, int n,
+                         const SweepParams<double>& SP, ocb_fused_plan** out) {
+  return fused_try_create_t<double>(grid, in, reqs, n, SP, out);
 }
 
 int ocb_fused_nblocks(const ocb_fused_plan* fp) { return fp->nblocks; }
@@ -1098,4 +1154,7 @@ int ocb_fused_execute(ocb_fused_plan* fp, double* partial, cudaStream_t st) {
   return OCB_OK;
 }
 
-void ocb_fused_destroy(ocb_fused_plan* fp) { delete fp; }
+void ocb_fused_destroy(ocb_fused_plan* fp) {
+  if (fp && fp->ztab_d) cudaFree(fp->ztab_d);
+  delete fp;
+}

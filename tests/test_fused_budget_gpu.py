@@ -255,6 +255,37 @@ def test_tke_budget_integrals_under_eddy_viscosity_closures(stretched, closure):
 
 
 @pytest.mark.parametrize("stretched", [False, True], ids=["regular", "stretched"])
+@pytest.mark.parametrize("closure", ["scalar", "smagorinsky_like"])
+def test_float32_budget_integrals_on_the_class_sum_kernel(stretched, closure):
+    """Float32 fields (BASELINE configs[3]'s precision): the seven budget integrals on the class-sum kernel's Float32-input form --
+    TMA tiles as two boxes per field over the merged-row view (a 774-float row is not a 16-byte multiple), sums in Float64 --
+    regular / stretched z, constant / eddy-viscosity closure, whole domain and windows.  Against the oracle's Float32 per-cell
+    values times their volumes (1e-5 of the integrand scale, north_star's Float32 tolerance) and against the generic kernel."""
+    st = State(size=(64, 40, 30), stretched=stretched, dtype=np.float32, device="cuda")
+    ops, oc = budget(st, closure=closure)
+    want = [w.astype(np.float64) for w in oracle_budget(st, oc)]
+    ii, jj, kk = st.og.indices("ccc")
+    vol = np.broadcast_to(np.asarray(st.og.V("ccc", ii, jj, kk), dtype=np.float64), want[0].shape)
+    Ny, Nz = 40, 30
+    for win in (None, (3, 38, 2, 29), (1, 1, 1, Nz), (Ny, Ny, Nz, Nz), (7, 21, 11, 11)):
+        idx = None if win is None else (None, (win[0], win[1]), (win[2], win[3]))
+        jlo, jhi, klo, khi = win or (1, Ny, 1, Nz)
+        grp = ocb.FusedDiagnostics(*[ocb.Integral(o, indices=idx) for o in ops]).compute()
+        assert grp.plan.variant == 1 and grp.plan.n_launches == 2, (win, grp.plan.variant)
+        os.environ["OCB_DISABLE_SUMS_F32"] = "1"
+        try:
+            gen = ocb.FusedDiagnostics(*[ocb.Integral(o, indices=idx) for o in ops]).compute()
+        finally:
+            os.environ.pop("OCB_DISABLE_SUMS_F32", None)
+        assert gen.plan.variant != 1
+        for o, w_, a, b_ in zip(ops, want, grp.integrals(), gen.integrals()):
+            ww, vw = w_[:, jlo - 1:jhi, klo - 1:khi], vol[:, jlo - 1:jhi, klo - 1:khi]
+            ref, scale = float(np.sum(ww * vw)), float(np.sum(np.abs(ww) * vw))
+            assert abs(a - ref) <= 1e-5 * scale, (o.name, win, a, ref, scale)
+            assert abs(a - b_) <= 1e-5 * scale, (o.name, win, a, b_, scale)
+
+
+@pytest.mark.parametrize("stretched", [False, True], ids=["regular", "stretched"])
 def test_windowed_budget_fields_match_the_full_fields(stretched):
     """Field(op, indices=(:, j-window, k-window)) of all seven terms in one sweep of the pipelined kernel: the window holds
     exactly the full field's values (the z window of a stretched grid starts at a plane with other metrics than plane 1)."""
