@@ -673,6 +673,10 @@ struct ocb_fused_plan {
   void (*kernel)(FusedParams, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap);
   bool nuf;                        // the eddy-viscosity variant of the class-sum kernel (nu_e as sixth input)
   double* ztab_d;                  // Float32 plans on a stretched axis: Float64 copies of the z-metric tables
+  // Float32 plans about mean profiles: the profiles' Float32 arrays (whole parent extents) and their Float64 copies, refreshed at every execute
+  const float* prof_src[3];
+  double* prof_d;
+  int prof_n, prof_len[3];
 };
 
 template <int MASK, int NW, int RY, int NS>
@@ -879,7 +883,9 @@ static int fused_try_create_t(const ocb_grid* grid, const ocb_sweep_inputs* in, 
     if (R.slot >= 0) { if (which_slot[d] >= 0) return OCB_OK; which_slot[d] = r; }
     mask |= 1 << d;
   }
-  if (F32 && ((mask & ~FD_BUDGET) || any_pert)) return OCB_OK;            // Float32: the seven plain budget terms
+  // Float32: the seven plain budget terms, or the TKE budget with pressure redistribution about mean profiles
+  constexpr int TKEP_F = (1 << FD_SP) | (1 << FD_EPSP) | (1 << FD_TKE) | (1 << FD_PR) | (1 << FD_K);
+  if (F32 && (any_pert ? (mask & ~TKEP_F) != 0 : (mask & ~FD_BUDGET) != 0)) return OCB_OK;
   // stretched z: the cell-exact variant evaluates the seven plain budget terms; the class-sum form also the TKE-budget terms
   constexpr int TKE_TERMS = (1 << FD_SP) | (1 << FD_EPSP) | (1 << FD_TKE);
   // (cell-exact: the seven plain terms, or the TKE budget about mean profiles {eps(u - U), SP, PR, K} -- no potential vorticity)
@@ -958,9 +964,15 @@ static int fused_try_create_t(const ocb_grid* grid, const ocb_sweep_inputs* in, 
   const int njy = SP.req[0].hi[1] - SP.req[0].lo[1] + 1;
   if constexpr (F32) {
     // Float32 inputs: the all-terms class sums in the two-box tile form (40-column pitch), with the stretched / eddy-viscosity forms
-    if (!tma_compatible(in->b, grid) || !tma_compatible(in->p, grid)) { delete fp; return OCB_OK; }
-    if (stretched) rc = nuf ? setup_sums<ALL, 4, 4, 3, 2, 40, true, true, float>(fp) : setup_sums<ALL, 4, 4, 3, 2, 40, true, false, float>(fp);
-    else rc = nuf ? setup_sums<ALL, 4, 4, 3, 2, 40, false, true, float>(fp) : setup_sums<ALL, 4, 4, 3, 2, 40, false, false, float>(fp);
+    if (any_pert) {
+      if (!tma_compatible(in->p, grid)) { delete fp; return OCB_OK; }
+      if (stretched) rc = nuf ? setup_sums<TKEP_F, 4, 4, 3, 2, 40, true, true, float>(fp) : setup_sums<TKEP_F, 4, 4, 3, 2, 40, true, false, float>(fp);
+      else rc = nuf ? setup_sums<TKEP_F, 4, 4, 3, 2, 40, false, true, float>(fp) : setup_sums<TKEP_F, 4, 4, 3, 2, 40, false, false, float>(fp);
+    } else {
+      if (!tma_compatible(in->b, grid) || !tma_compatible(in->p, grid)) { delete fp; return OCB_OK; }
+      if (stretched) rc = nuf ? setup_sums<ALL, 4, 4, 3, 2, 40, true, true, float>(fp) : setup_sums<ALL, 4, 4, 3, 2, 40, true, false, float>(fp);
+      else rc = nuf ? setup_sums<ALL, 4, 4, 3, 2, 40, false, true, float>(fp) : setup_sums<ALL, 4, 4, 3, 2, 40, false, false, float>(fp);
+    }
   } else {
   if (sums && nuf) {
     // eddy-viscosity dissipation: the all-terms class sums with nu_e inside (needs all five other inputs as well)
@@ -1109,6 +1121,26 @@ static int fused_try_create_t(const ocb_grid* grid, const ocb_sweep_inputs* in, 
   }
   P.nslots = SP.nslots;
   P.Uz = Uz; P.Vz = Vz; P.Wz = Wz; P.eps_pert = eps_pert ? 1 : 0;
+  if constexpr (F32) {
+    if (any_pert) {
+      // the profiles are Float32 arrays that change from step to step: Float64 copies, refreshed by every execute
+      const int np_ = grid->N[2] + 2 * grid->H[2] + 1;
+      OCB_CUDA(cudaMalloc(&fp->prof_d, sizeof(double) * 3 * np_));
+      OCB_CUDA(cudaMemset(fp->prof_d, 0, sizeof(double) * 3 * np_));
+      fp->prof_n = np_;
+      const ocb_field* pf[3] = {&in->U, &in->V, &in->W};
+      const double** dst[3] = {&P.Uz, &P.Vz, &P.Wz};
+      for (int a = 0; a < 3; ++a) {
+        fp->prof_src[a] = nullptr;
+        if (*dst[a]) {                                   // (profile_pointer accepted it: an array reduced over x and y, contiguous in z)
+          fp->prof_src[a] = (const float*)pf[a]->data;
+          if (pf[a]->size[2] > np_) { delete fp; return OCB_OK; }
+          fp->prof_len[a] = pf[a]->size[2];
+          *dst[a] = fp->prof_d + a * np_ + (pf[a]->halo[2] - 1);
+        }
+      }
+    }
+  }
   for (int a = 0; a < 3; ++a) P.os[a] = os[a];
   for (int d = 0; d < FD_N; ++d) {
     P.o[d].out = nullptr; P.o[d].slot = -1;
@@ -1148,6 +1180,10 @@ int ocb_fused_execute_gated(ocb_fused_plan* fp, double* partial, long long* flag
 
 int ocb_fused_execute(ocb_fused_plan* fp, double* partial, cudaStream_t st) {
   fp->P.partial = partial;
+  if (fp->prof_d) {
+    for (int a = 0; a < 3; ++a)
+      if (fp->prof_src[a]) ocb_f32_to_f64_kernel<<<(fp->prof_len[a] + 127) / 128, 128, 0, st>>>(fp->prof_src[a], fp->prof_d + a * fp->prof_n, fp->prof_len[a]);
+  }
   dim3 block(32, fp->nw, 1), grid(fp->nblocks, 1, 1);
   fp->kernel<<<grid, block, fp->smem, st>>>(fp->P, fp->maps[0], fp->maps[1], fp->maps[2], fp->maps[3], fp->maps[4], fp->maps[5]);
   OCB_CUDA(cudaGetLastError());
@@ -1156,5 +1192,6 @@ int ocb_fused_execute(ocb_fused_plan* fp, double* partial, cudaStream_t st) {
 
 void ocb_fused_destroy(ocb_fused_plan* fp) {
   if (fp && fp->ztab_d) cudaFree(fp->ztab_d);
+  if (fp && fp->prof_d) cudaFree(fp->prof_d);
   delete fp;
 }

@@ -286,6 +286,41 @@ def test_float32_budget_integrals_on_the_class_sum_kernel(stretched, closure):
 
 
 @pytest.mark.parametrize("stretched", [False, True], ids=["regular", "stretched"])
+@pytest.mark.parametrize("closure", ["scalar", "smagorinsky_like"])
+def test_float32_tke_budget_integrals(stretched, closure):
+    """Float32 fields and Float32 mean profiles: the TKE budget {shear production, dissipation of u - U, pressure redistribution,
+    TKE} as integrals in one launch of the Float32-input class-sum kernel (the profiles are copied to Float64 by every execute);
+    recomputed after the state changes; against the Float32 oracle and the generic kernel to 1e-5 of the integrand scale."""
+    from cases import build_cases
+    st = State(size=(64, 44, 26), stretched=stretched, dtype=np.float32, device="cuda")
+    cases = {c[0]: c for c in build_cases(st, closure, mean="profile")}
+    names = ["ShearProductionRate", "DissipationRate_perturbation", "KineticEnergyPressureRedistribution", "TurbulentKineticEnergy"]
+    ops = [cases[nm][1] for nm in names]
+    ii, jj, kk = st.og.indices("ccc")
+    V = np.broadcast_to(np.asarray(st.og.V("ccc", ii, jj, kk), dtype=np.float64), cases[names[0]][2].shape)
+    grp = ocb.FusedDiagnostics(*[ocb.Integral(o) for o in ops]).compute()
+    assert grp.plan.variant == 1 and grp.plan.n_launches == 2
+    os.environ["OCB_DISABLE_SUMS_F32"] = "1"
+    try:
+        gen = ocb.FusedDiagnostics(*[ocb.Integral(o) for o in ops]).compute()
+    finally:
+        os.environ.pop("OCB_DISABLE_SUMS_F32", None)
+    assert gen.plan.variant != 1
+    for nm, a, b_ in zip(names, grp.integrals(), gen.integrals()):
+        w_ = cases[nm][2].astype(np.float64)
+        ref, scale = float(np.sum(w_ * V)), float(np.sum(np.abs(w_) * V))
+        assert abs(a - ref) <= 1e-5 * scale, (nm, a, ref, scale)
+        assert abs(a - b_) <= 1e-5 * scale, (nm, a, b_, scale)
+    # the profiles follow the state: scale u, recompute both ways
+    st.u.data.mul_(1.5)
+    a2 = grp.compute(time=1.0).integrals()
+    b2 = gen.compute(time=1.0).integrals()
+    for nm, a, b_, a0 in zip(names, a2, b2, grp.integrals()):
+        scale = float(np.sum(np.abs(cases[nm][2].astype(np.float64)) * V))
+        assert abs(a - b_) <= 2e-5 * 2.25 * scale, (nm, a, b_)
+
+
+@pytest.mark.parametrize("stretched", [False, True], ids=["regular", "stretched"])
 def test_windowed_budget_fields_match_the_full_fields(stretched):
     """Field(op, indices=(:, j-window, k-window)) of all seven terms in one sweep of the pipelined kernel: the window holds
     exactly the full field's values (the z window of a stretched grid starts at a plane with other metrics than plane 1)."""
