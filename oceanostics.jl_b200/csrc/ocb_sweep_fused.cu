@@ -672,6 +672,7 @@ struct ocb_fused_plan {
   size_t smem;
   void (*kernel)(FusedParams, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap);
   bool nuf;                        // the eddy-viscosity variant of the class-sum kernel (nu_e as sixth input)
+  bool f32;                        // Float32-input plan
   double* ztab_d;                  // Float32 plans on a stretched axis: Float64 copies of the z-metric tables
   // Float32 plans about mean profiles: the profiles' Float32 arrays (whole parent extents) and their Float64 copies, refreshed at every execute
   const float* prof_src[3];
@@ -1106,6 +1107,7 @@ static int fused_try_create_t(const ocb_grid* grid, const ocb_sweep_inputs* in, 
   P.kappa_scale = in->closure.n_kappa_fields ? in->closure.kappa_scale[0] : 0.0;
   P.V = stretched ? grid->d[0] * grid->d[1] : grid->d[0] * grid->d[1] * grid->d[2];      // stretched: dz_c is the cell's integral weight
   P.rowlen = in->u.size[0];
+  fp->f32 = F32;
   if constexpr (F32) {
     P.dzc = P.dzf = P.rdzc = P.rdzf = nullptr;
     if (stretched) {
@@ -1167,8 +1169,9 @@ int ocb_fused_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, const
 
 int ocb_fused_nblocks(const ocb_fused_plan* fp) { return fp->nblocks; }
 
-// (the eddy-viscosity variant reads a sixth input whose halo rows the ring step does not push: not ring-capable)
-bool ocb_fused_ring_capable(const ocb_fused_plan* fp) { return fp->sums && fp->P.y_ring && !fp->nuf; }
+// (the eddy-viscosity variant reads a sixth input whose halo rows the ring step does not push, and the ring step is only
+//  exercised on Float64 slabs: neither is ring-capable)
+bool ocb_fused_ring_capable(const ocb_fused_plan* fp) { return fp->sums && fp->P.y_ring && !fp->nuf && !fp->f32; }
 
 int ocb_fused_execute_gated(ocb_fused_plan* fp, double* partial, long long* flags, long long step, long long timeout_cycles, cudaStream_t st) {
   OCB_REQUIRE(ocb_fused_ring_capable(fp), "gated execution needs the class-sum kernel over a whole periodic y extent");
