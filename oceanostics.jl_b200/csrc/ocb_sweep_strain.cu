@@ -15,7 +15,11 @@
 // overlap by one cell in x and y.  Float32 parent rows are not 16-byte multiples in general (Nx + 2H = 774 floats in
 // config 4), so the plane tiles cannot come by TMA: they are brought into the shared-memory ring by per-element
 // cp.async (LDGSTS) copies issued NS planes ahead, committed per plane and awaited with cp.async.wait_group.
+// Round 2, Float32 with even parent row and column counts (TMAL = true): the tiles come by TMA after all -- two parent rows ARE a
+// 16-byte multiple, so the tensor maps describe each plane as rows of 2 (Nx + 2H) elements and a tile is two boxes per field (the
+// rows of one parity, the rows of the other; ocb_budget_sums.cuh has the same form) -- one thread issues them, nobody copies.
 #include "ocb_sweep_strain.cuh"
+#include "ocb_tma.cuh"
 #include <new>
 
 namespace {
@@ -58,13 +62,20 @@ __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0
 __device__ __forceinline__ float t_sqrt(float x) { return sqrtf(x); }
 __device__ __forceinline__ double t_sqrt(double x) { return sqrt(x); }
 
-template <class T, int FAM, int NNU, int NW, int RY, int NS, int MINB>
+struct StrainMaps { CUtensorMap m[NFMAX]; };
+constexpr int STWT = 40;                           // tile row pitch of the TMA form: 34 columns + up to 3 of box alignment, 16-byte rows
+constexpr int strain_half_elems(int tr) { return ((STWT * (tr / 2) * 4 + 127) / 128) * 128 / 4; }   // one box, 128-byte aligned
+
+template <class T, int FAM, int NNU, int NW, int RY, int NS, int MINB, bool TMAL = false>
 __global__ void __launch_bounds__(NW * 32, MINB)
-ocb_strain_kernel(const __grid_constant__ StrainParams<T> P) {
+ocb_strain_kernel(const __grid_constant__ StrainParams<T> P, const __grid_constant__ StrainMaps M) {
   constexpr bool F_E = FAM & FAM_E, F_P = FAM & FAM_P, F_M = FAM & FAM_M;
   constexpr int NFAM = (F_E ? 1 : 0) + (F_P ? 1 : 0) + (F_M ? 1 : 0);
   constexpr int IE = 0, IP = F_E ? 1 : 0, IM = IP + (F_P ? 1 : 0);       // family index -> slot in the small arrays
-  constexpr int NF = 3 + NNU, BR = NW * RY, TR = BR + 2, TILE = STW * TR + STPAD, NT = NW * 32;
+  constexpr int NF = 3 + NNU, BR = NW * RY, TR = BR + 2, NT = NW * 32;
+  constexpr int HALF = strain_half_elems(TR);
+  constexpr int TILE = TMAL ? 2 * HALF : STW * TR + STPAD;
+  static_assert(!TMAL || (sizeof(T) == 4 && TR % 2 == 0), "the TMA form is the Float32 one, two boxes of TR / 2 rows");
   constexpr int NXS = 2 * NFAM;                                          // exchanged per column: X12 and q23 of each family
   constexpr int NLD = ((STW / 2) * TR + NT - 1) / NT;                    // copies (element pairs) per thread, field and plane
 
@@ -73,6 +84,7 @@ ocb_strain_kernel(const __grid_constant__ StrainParams<T> P) {
   T* xch = tiles + NS * NF * TILE;                                       // [2][NW][NXS][32]
   double* red = reinterpret_cast<double*>(xch + 2 * NW * NXS * 32);      // [NW]
   T* zts = reinterpret_cast<T*>(red + NW);                               // [4][ZC]
+  uint64_t* full = reinterpret_cast<uint64_t*>(zts + 4 * ZC);              // [NS] (TMAL)
 
   const int lane = threadIdx.x, warp = threadIdx.y;
   const int tid = warp * 32 + lane;
@@ -106,8 +118,29 @@ ocb_strain_kernel(const __grid_constant__ StrainParams<T> P) {
     // every copy is then unconditional (no divergent branch around LDGSTS)
     sb[t] = (uint32_t)((ok ? row * STW + col : STW * TR) * sizeof(T));
   }
+  // TMA form: box b holds the tile rows b, b + 2, .. (one parity of parent rows), read from the merged-row view at column
+  // (parity) * rowlen + px_raw rounded down to 16 bytes; bo[b] = the columns lost to the rounding
+  int bx[2] = {0, 0}, by[2] = {0, 0}, bo[2] = {0, 0};
+  if (TMAL) {
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int xr = ((py + b) & 1) * P.sy + px_raw;
+      bx[b] = xr & ~3; bo[b] = xr & 3; by[b] = (py + b) >> 1;
+    }
+  }
   auto issue = [&](int n) {
     const int s = (n - n_first) % NS;
+    if (TMAL) {                                          // (called by thread 0 only)
+      mbar_expect_tx(&full[s], (uint32_t)(NF * STWT * TR * sizeof(T)));
+      const int pz = n + P.hz - 1;                       // (planes a field does not have arrive as zeros)
+#pragma unroll
+      for (int f = 0; f < NF; ++f) {
+        T* dst = tiles + (s * NF + f) * TILE;
+        tma_load_3d(dst, &M.m[f], &full[s], bx[0], by[0], pz);
+        tma_load_3d(dst + HALF, &M.m[f], &full[s], bx[1], by[1], pz);
+      }
+      return;
+    }
     const long long pz = min(n + P.hz - 1, P.cz);
 #pragma unroll
     for (int f = 0; f < NF; ++f) {
@@ -118,10 +151,27 @@ ocb_strain_kernel(const __grid_constant__ StrainParams<T> P) {
       for (int t = 0; t < NLD; ++t) cp_async<2 * sizeof(T)>(dst + sb[t], src + goff[t]);
     }
   };
-  for (int n = n_first; n < n_first + NS; ++n) {      // one group per plane, empty past the end so the counting stays uniform
-    if (n <= n_last) issue(n);
-    cp_commit();
+  if (TMAL) {
+    if (tid == 0) {
+      for (int q = 0; q < NS; ++q) mbar_init(&full[q], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) for (int n = n_first; n < n_first + NS && n <= n_last; ++n) issue(n);
+  } else {
+    for (int n = n_first; n < n_first + NS; ++n) {      // one group per plane, empty past the end so the counting stays uniform
+      if (n <= n_last) issue(n);
+      cp_commit();
+    }
   }
+  // tile offsets of this lane's cell in the thread's rows, the row to the south (ro[0]) and the row to the north (ro[RY + 1])
+  int ro[RY + 2];
+#pragma unroll
+  for (int q = 0; q < RY + 2; ++q) {
+    const int tr = jr0 + q;
+    ro[q] = TMAL ? (tr & 1) * HALF + (tr >> 1) * STWT + bo[tr & 1] + lane + 1 : tr * STW + lane + xoff + 1;
+  }
+  uint32_t phase = 0;
 
   const T rdx = P.rdx, rdy = P.rdy, nu_c = P.nu_c;
   const T Q4 = T(0.25), H2 = T(0.5);
@@ -162,11 +212,16 @@ ocb_strain_kernel(const __grid_constant__ StrainParams<T> P) {
       zts[0 * ZC + tid] = __ldg(P.rdzf + q); zts[1 * ZC + tid] = __ldg(P.dzf + q);
       zts[2 * ZC + tid] = __ldg(P.rdzc + km); zts[3 * ZC + tid] = __ldg(P.dzc + km);
     }
-    cp_wait<NS - 1>();                                  // this thread's copies of plane n have landed ...
-    __syncthreads();                                    // ... and everybody else's (and the z-metric window)
+    if (TMAL) {
+      if (zi == 0) __syncthreads();                     // the z-metric window (uniform branch)
+      mbar_wait(&full[s], phase);                       // plane n has landed
+    } else {
+      cp_wait<NS - 1>();                                // this thread's copies of plane n have landed ...
+      __syncthreads();                                  // ... and everybody else's (and the z-metric window)
+    }
     const T* Tt = tiles + s * (NF * TILE);
     const T* Tu = Tt, *Tv = Tt + TILE, *Tw = Tt + 2 * TILE;
-    if (++s == NS) s = 0;
+    if (++s == NS) { s = 0; phase ^= 1; }
     const T rzf = zts[0 * ZC + zi], dzf_n = zts[1 * ZC + zi], rzc1 = zts[2 * ZC + zi], dzc1 = zts[3 * ZC + zi];
     const bool pv1 = (n - 1) >= k0 && (n - 1) <= k1;
 
@@ -177,7 +232,7 @@ ocb_strain_kernel(const __grid_constant__ StrainParams<T> P) {
     // the thread's own column first: south / north neighbours inside the thread are then registers, not shared-memory reads
 #pragma unroll
     for (int r = 0; r < RY; ++r) {
-      const int o = (jr0 + 1 + r) * STW + lane + xoff + 1;
+      const int o = ro[r + 1];
       uc[r] = Tu[o]; vc[r] = Tv[o]; wc[r] = Tw[o];
       nuc[r] = nuw[r] = T(0);
 #pragma unroll
@@ -185,13 +240,10 @@ ocb_strain_kernel(const __grid_constant__ StrainParams<T> P) {
     }
 #pragma unroll
     for (int r = 0; r < RY; ++r) {
-      const int row = jr0 + 1 + r;
-      const T* ru = Tu + row * STW + lane + xoff;        // ru[0] west, ru[1] centre, ru[2] east
-      const T* rv = Tv + row * STW + lane + xoff;
-      const T* rw = Tw + row * STW + lane + xoff;
-      const T ue = ru[2], us = (r == 0) ? ru[1 - STW] : uc[r > 0 ? r - 1 : 0];
-      const T vw = rv[0], vn = (r == RY - 1) ? rv[1 + STW] : vc[r < RY - 1 ? r + 1 : r];
-      const T ww = rw[0], ws = (r == 0) ? rw[1 - STW] : wc[r > 0 ? r - 1 : 0];
+      const int oc = ro[r + 1];                           // this cell; oc - 1 west, oc + 1 east; ro[0] / ro[RY + 1]: the rows to the south / north
+      const T ue = Tu[oc + 1], us = (r == 0) ? Tu[ro[0]] : uc[r > 0 ? r - 1 : 0];
+      const T vw = Tv[oc - 1], vn = (r == RY - 1) ? Tv[ro[RY + 1]] : vc[r < RY - 1 ? r + 1 : r];
+      const T ww = Tw[oc - 1], ws = (r == 0) ? Tw[ro[0]] : wc[r > 0 ? r - 1 : 0];
       const T a = (uc[r] - us) * rdy, b = (vc[r] - vw) * rdx;               // ∂y u, ∂x v   at ffc (i, j, n)
       const T c = (uc[r] - up[r]) * rzf, d = (wc[r] - ww) * rdx;            // ∂z u, ∂x w   at fcf (i, j, face n)
       const T e = (vc[r] - vp[r]) * rzf, f = (wc[r] - ws) * rdy;            // ∂z v, ∂y w   at cff
@@ -205,8 +257,8 @@ ocb_strain_kernel(const __grid_constant__ StrainParams<T> P) {
         if (r == 0) {
 #pragma unroll
           for (int q = 0; q < NNU; ++q) {
-            const T* rn = Tt + (3 + q) * TILE + row * STW + lane + xoff;
-            ns += rn[1 - STW]; nsw += rn[-STW];
+            const T* tn = Tt + (3 + q) * TILE;
+            ns += tn[ro[0]]; nsw += tn[ro[0] - 1];
           }
         } else { ns = nuc[r > 0 ? r - 1 : 0]; nsw = nuw[r > 0 ? r - 1 : 0]; }
         nucc[r] = nu_c + nc;
@@ -233,8 +285,12 @@ ocb_strain_kernel(const __grid_constant__ StrainParams<T> P) {
     for (int m = 0; m < NFAM; ++m) { myx[(2 * m) * 32] = X12[0][m]; myx[(2 * m + 1) * 32] = q23[0][m]; }
     __syncthreads();
     // every thread is done with raw stage s: refill it (plane n + NS)
-    if (n + NS <= n_last) issue(n + NS);
-    cp_commit();
+    if (TMAL) {
+      if (tid == 0 && n + NS <= n_last) issue(n + NS);
+    } else {
+      if (n + NS <= n_last) issue(n + NS);
+      cp_commit();
+    }
     T X12N[NFAM > 0 ? NFAM : 1], q23N[NFAM > 0 ? NFAM : 1];
 #pragma unroll
     for (int m = 0; m < NFAM; ++m) { X12N[m] = T(0); q23N[m] = T(0); }
@@ -294,7 +350,7 @@ ocb_strain_kernel(const __grid_constant__ StrainParams<T> P) {
     }
     par ^= 1;
   }
-  cp_wait<0>();
+  if (!TMAL) cp_wait<0>();
 
   // ---- volume integrals: warp shuffle, then one partial per block and slot --------------------------------------------
   if (P.nslots > 0) {
@@ -332,10 +388,12 @@ struct ocb_strain_plan {
   int dtype;
   StrainParams<double> Pd;
   StrainParams<float> Pf;
+  StrainMaps maps;                 // TMA form (Float32): one merged-row tensor map per operand
+  bool tmal;
   int nw, ry, nblocks;
   size_t smem;
-  void (*kd)(StrainParams<double>);
-  void (*kf)(StrainParams<float>);
+  void (*kd)(StrainParams<double>, StrainMaps);
+  void (*kf)(StrainParams<float>, StrainMaps);
 };
 
 bool ocb_strain_handles_diag(int diag) { return strain_diag_index(diag) >= 0; }
@@ -344,9 +402,9 @@ template <class T> struct StrainShape;
 template <> struct StrainShape<float> { static constexpr int NW = 4, RY = 3, NS = 3, MINB = 4; };
 template <> struct StrainShape<double> { static constexpr int NW = 4, RY = 3, NS = 3, MINB = 2; };
 
-template <class T> static void set_kernel(ocb_strain_plan* sp, void (*k)(StrainParams<T>));
-template <> void set_kernel<double>(ocb_strain_plan* sp, void (*k)(StrainParams<double>)) { sp->kd = k; }
-template <> void set_kernel<float>(ocb_strain_plan* sp, void (*k)(StrainParams<float>)) { sp->kf = k; }
+template <class T> static void set_kernel(ocb_strain_plan* sp, void (*k)(StrainParams<T>, StrainMaps));
+template <> void set_kernel<double>(ocb_strain_plan* sp, void (*k)(StrainParams<double>, StrainMaps)) { sp->kd = k; }
+template <> void set_kernel<float>(ocb_strain_plan* sp, void (*k)(StrainParams<float>, StrainMaps)) { sp->kf = k; }
 
 static void keep_params(ocb_strain_plan* sp, const StrainParams<double>& P) { sp->Pd = P; }
 static void keep_params(ocb_strain_plan* sp, const StrainParams<float>& P) { sp->Pf = P; }
@@ -356,6 +414,18 @@ static int strain_setup_shape(ocb_strain_plan* sp) {
   constexpr int NFAM = ((FAM & 1) ? 1 : 0) + ((FAM & 2) ? 1 : 0) + ((FAM & 4) ? 1 : 0);
   constexpr int NF = 3 + NNU, TR = NW * RY + 2, TILE = STW * TR + STPAD;
   sp->nw = NW; sp->ry = RY;
+  if constexpr (sizeof(T) == 4 && (NW * RY) % 2 == 0) {
+    if (sp->tmal) {                                       // Float32, TMA form: two 128-byte-aligned boxes per field tile, and the ring's mbarriers
+      constexpr int TILE_T = 2 * strain_half_elems(TR);
+      sp->smem = sizeof(T) * ((size_t)NS * NF * TILE_T + 2 * NW * 2 * NFAM * 32 + 4 * ZC) + sizeof(double) * NW + sizeof(uint64_t) * NS;
+      auto kt = ocb_strain_kernel<T, FAM, NNU, NW, RY, NS, MINB, true>;
+      cudaFuncSetAttribute(kt, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+      OCB_CUDA(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp->smem));
+      set_kernel<T>(sp, kt);
+      return OCB_OK;
+    }
+  }
+  sp->tmal = false;
   sp->smem = sizeof(T) * ((size_t)NS * NF * TILE + 2 * NW * 2 * NFAM * 32 + 4 * ZC) + sizeof(double) * NW;
   auto k = ocb_strain_kernel<T, FAM, NNU, NW, RY, NS, MINB>;
   cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
@@ -436,6 +506,13 @@ static int strain_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, c
   if (!sp) OCB_FAIL(OCB_ERR_ALLOC, "out of host memory");
   memset((void*)sp, 0, sizeof(*sp));
   sp->dtype = grid->dtype;
+  // Float32 operands whose parent rows and row counts are even: the tiles come by TMA (two boxes per field over the merged-row view)
+  sp->tmal = false;
+  if (sizeof(T) == 4 && !getenv("OCB_STRAIN_NO_TMA") && get_encode_fn()) {
+    bool ok = tma_compatible_f32(in->u, grid) && tma_compatible_f32(in->v, grid) && tma_compatible_f32(in->w, grid);
+    for (int q = 0; q < nnu; ++q) ok = ok && tma_compatible_f32(in->closure.nu_fields[q], grid);
+    sp->tmal = ok;
+  }
   int rc;
   // families are compiled in the combinations the diagnostics ask for: {E}, {P}, {E,P} (config 4), {M}, {P,M}, {E,P,M}
   if (fam == FAM_E) rc = strain_pick_nu<T, FAM_E>(sp, nnu);
@@ -488,6 +565,15 @@ static int strain_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, c
     P.out[d] = which_out[d] >= 0 ? (T*)SP.req[which_out[d]].out : nullptr;
     P.slot[d] = which_slot[d] >= 0 ? SP.req[which_slot[d]].slot : -1;
   }
+  if (sp->tmal) {
+    EncodeTiledFn enc = get_encode_fn();
+    const int TR = sp->nw * sp->ry + 2;
+    for (int a = 0; a < NFMAX; ++a) {
+      const ocb_field* fa = a < 3 + nnu ? f[a] : f[0];
+      rc = make_map_f32(enc, *fa, TR, &sp->maps.m[a], STWT);
+      if (rc != OCB_OK) { delete sp; return rc; }
+    }
+  }
   keep_params(sp, P);
   *out = sp;
   return OCB_OK;
@@ -508,10 +594,10 @@ int ocb_strain_execute(ocb_strain_plan* sp, double* partial, cudaStream_t st) {
   dim3 block(32, sp->nw, 1), grid(sp->nblocks, 1, 1);
   if (sp->dtype == OCB_F64) {
     sp->Pd.partial = partial;
-    sp->kd<<<grid, block, sp->smem, st>>>(sp->Pd);
+    sp->kd<<<grid, block, sp->smem, st>>>(sp->Pd, sp->maps);
   } else {
     sp->Pf.partial = partial;
-    sp->kf<<<grid, block, sp->smem, st>>>(sp->Pf);
+    sp->kf<<<grid, block, sp->smem, st>>>(sp->Pf, sp->maps);
   }
   OCB_CUDA(cudaGetLastError());
   return OCB_OK;
