@@ -15,9 +15,10 @@
 // overlap by one cell in x and y.  Float32 parent rows are not 16-byte multiples in general (Nx + 2H = 774 floats in
 // config 4), so the plane tiles cannot come by TMA: they are brought into the shared-memory ring by per-element
 // cp.async (LDGSTS) copies issued NS planes ahead, committed per plane and awaited with cp.async.wait_group.
-// Round 2, Float32 with even parent row and column counts (TMAL = true): the tiles come by TMA after all -- two parent rows ARE a
+// Round 2 (TMAL = true): the tiles come by TMA after all.  Float32 with even parent row and column counts: two parent rows ARE a
 // 16-byte multiple, so the tensor maps describe each plane as rows of 2 (Nx + 2H) elements and a tile is two boxes per field (the
-// rows of one parity, the rows of the other; ocb_budget_sums.cuh has the same form) -- one thread issues them, nobody copies.
+// rows of one parity, the rows of the other; ocb_budget_sums.cuh has the same form).  Float64 rows of an even length are 16-byte
+// multiples themselves: one box.  One thread issues the loads, nobody copies: config 4 2.48 -> 1.61 ms, its Float64 twin 4.35 -> 2.72 ms.
 #include "ocb_sweep_strain.cuh"
 #include "ocb_tma.cuh"
 #include <new>
@@ -65,6 +66,7 @@ __device__ __forceinline__ double t_sqrt(double x) { return sqrt(x); }
 struct StrainMaps { CUtensorMap m[NFMAX]; };
 constexpr int STWT = 40;                           // tile row pitch of the TMA form: 34 columns + up to 3 of box alignment, 16-byte rows
 constexpr int strain_half_elems(int tr) { return ((STWT * (tr / 2) * 4 + 127) / 128) * 128 / 4; }   // one box, 128-byte aligned
+constexpr int strain_tile_f64(int tr) { return ((STW * tr * 8 + 127) / 128) * 128 / 8; }               // Float64: one box of STW x tr
 
 template <class T, int FAM, int NNU, int NW, int RY, int NS, int MINB, bool TMAL = false>
 __global__ void __launch_bounds__(NW * 32, MINB)
@@ -73,9 +75,10 @@ ocb_strain_kernel(const __grid_constant__ StrainParams<T> P, const __grid_consta
   constexpr int NFAM = (F_E ? 1 : 0) + (F_P ? 1 : 0) + (F_M ? 1 : 0);
   constexpr int IE = 0, IP = F_E ? 1 : 0, IM = IP + (F_P ? 1 : 0);       // family index -> slot in the small arrays
   constexpr int NF = 3 + NNU, BR = NW * RY, TR = BR + 2, NT = NW * 32;
+  constexpr bool F32T = TMAL && sizeof(T) == 4;                // two boxes per tile; Float64 rows are 16-byte multiples: one box
   constexpr int HALF = strain_half_elems(TR);
-  constexpr int TILE = TMAL ? 2 * HALF : STW * TR + STPAD;
-  static_assert(!TMAL || (sizeof(T) == 4 && TR % 2 == 0), "the TMA form is the Float32 one, two boxes of TR / 2 rows");
+  constexpr int TILE = F32T ? 2 * HALF : (TMAL ? strain_tile_f64(TR) : STW * TR + STPAD);
+  static_assert(!F32T || TR % 2 == 0, "the Float32 TMA form takes two boxes of TR / 2 rows");
   constexpr int NXS = 2 * NFAM;                                          // exchanged per column: X12 and q23 of each family
   constexpr int NLD = ((STW / 2) * TR + NT - 1) / NT;                    // copies (element pairs) per thread, field and plane
 
@@ -121,7 +124,7 @@ ocb_strain_kernel(const __grid_constant__ StrainParams<T> P, const __grid_consta
   // TMA form: box b holds the tile rows b, b + 2, .. (one parity of parent rows), read from the merged-row view at column
   // (parity) * rowlen + px_raw rounded down to 16 bytes; bo[b] = the columns lost to the rounding
   int bx[2] = {0, 0}, by[2] = {0, 0}, bo[2] = {0, 0};
-  if (TMAL) {
+  if (F32T) {
 #pragma unroll
     for (int b = 0; b < 2; ++b) {
       const int xr = ((py + b) & 1) * P.sy + px_raw;
@@ -131,13 +134,17 @@ ocb_strain_kernel(const __grid_constant__ StrainParams<T> P, const __grid_consta
   auto issue = [&](int n) {
     const int s = (n - n_first) % NS;
     if (TMAL) {                                          // (called by thread 0 only)
-      mbar_expect_tx(&full[s], (uint32_t)(NF * STWT * TR * sizeof(T)));
+      mbar_expect_tx(&full[s], (uint32_t)(NF * (F32T ? STWT : STW) * TR * sizeof(T)));
       const int pz = n + P.hz - 1;                       // (planes a field does not have arrive as zeros)
 #pragma unroll
       for (int f = 0; f < NF; ++f) {
         T* dst = tiles + (s * NF + f) * TILE;
-        tma_load_3d(dst, &M.m[f], &full[s], bx[0], by[0], pz);
-        tma_load_3d(dst + HALF, &M.m[f], &full[s], bx[1], by[1], pz);
+        if (F32T) {
+          tma_load_3d(dst, &M.m[f], &full[s], bx[0], by[0], pz);
+          tma_load_3d(dst + HALF, &M.m[f], &full[s], bx[1], by[1], pz);
+        } else {
+          tma_load_3d(dst, &M.m[f], &full[s], px, py, pz);
+        }
       }
       return;
     }
@@ -169,7 +176,7 @@ ocb_strain_kernel(const __grid_constant__ StrainParams<T> P, const __grid_consta
 #pragma unroll
   for (int q = 0; q < RY + 2; ++q) {
     const int tr = jr0 + q;
-    ro[q] = TMAL ? (tr & 1) * HALF + (tr >> 1) * STWT + bo[tr & 1] + lane + 1 : tr * STW + lane + xoff + 1;
+    ro[q] = F32T ? (tr & 1) * HALF + (tr >> 1) * STWT + bo[tr & 1] + lane + 1 : tr * STW + lane + xoff + 1;
   }
   uint32_t phase = 0;
 
@@ -414,9 +421,9 @@ static int strain_setup_shape(ocb_strain_plan* sp) {
   constexpr int NFAM = ((FAM & 1) ? 1 : 0) + ((FAM & 2) ? 1 : 0) + ((FAM & 4) ? 1 : 0);
   constexpr int NF = 3 + NNU, TR = NW * RY + 2, TILE = STW * TR + STPAD;
   sp->nw = NW; sp->ry = RY;
-  if constexpr (sizeof(T) == 4 && (NW * RY) % 2 == 0) {
-    if (sp->tmal) {                                       // Float32, TMA form: two 128-byte-aligned boxes per field tile, and the ring's mbarriers
-      constexpr int TILE_T = 2 * strain_half_elems(TR);
+  if constexpr ((NW * RY) % 2 == 0 || sizeof(T) == 8) {
+    if (sp->tmal) {                                       // TMA form: 128-byte-aligned boxes (two per field tile in Float32), and the ring's mbarriers
+      constexpr int TILE_T = sizeof(T) == 4 ? 2 * strain_half_elems(TR) : strain_tile_f64(TR);
       sp->smem = sizeof(T) * ((size_t)NS * NF * TILE_T + 2 * NW * 2 * NFAM * 32 + 4 * ZC) + sizeof(double) * NW + sizeof(uint64_t) * NS;
       auto kt = ocb_strain_kernel<T, FAM, NNU, NW, RY, NS, MINB, true>;
       cudaFuncSetAttribute(kt, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
@@ -508,9 +515,10 @@ static int strain_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, c
   sp->dtype = grid->dtype;
   // Float32 operands whose parent rows and row counts are even: the tiles come by TMA (two boxes per field over the merged-row view)
   sp->tmal = false;
-  if (sizeof(T) == 4 && !getenv("OCB_STRAIN_NO_TMA") && get_encode_fn()) {
-    bool ok = tma_compatible_f32(in->u, grid) && tma_compatible_f32(in->v, grid) && tma_compatible_f32(in->w, grid);
-    for (int q = 0; q < nnu; ++q) ok = ok && tma_compatible_f32(in->closure.nu_fields[q], grid);
+  if (!getenv("OCB_STRAIN_NO_TMA") && get_encode_fn()) {
+    auto compat = [&](const ocb_field& fl) { return sizeof(T) == 4 ? tma_compatible_f32(fl, grid) : tma_compatible_f64(fl, grid); };
+    bool ok = compat(in->u) && compat(in->v) && compat(in->w);
+    for (int q = 0; q < nnu; ++q) ok = ok && compat(in->closure.nu_fields[q]);
     sp->tmal = ok;
   }
   int rc;
@@ -570,7 +578,7 @@ static int strain_try_create(const ocb_grid* grid, const ocb_sweep_inputs* in, c
     const int TR = sp->nw * sp->ry + 2;
     for (int a = 0; a < NFMAX; ++a) {
       const ocb_field* fa = a < 3 + nnu ? f[a] : f[0];
-      rc = make_map_f32(enc, *fa, TR, &sp->maps.m[a], STWT);
+      rc = sizeof(T) == 4 ? make_map_f32(enc, *fa, TR, &sp->maps.m[a], STWT) : make_map_f64(enc, *fa, TR, &sp->maps.m[a], STW);
       if (rc != OCB_OK) { delete sp; return rc; }
     }
   }

@@ -46,6 +46,26 @@ EncodeTiledFn get_encode_fn() {
 }
 
 
+// Float64 fields: dense parents whose row pitch is a 16-byte multiple
+static bool tma_compatible_f64(const ocb_field& f, const ocb_grid* g) {
+  if (f.kind != OCB_FIELD_ARRAY || !f.data) return false;
+  for (int d = 0; d < 3; ++d) if (f.loc[d] == OCB_NOTHING || f.halo[d] != g->H[d]) return false;
+  if (f.stride[0] != 1) return false;
+  if (((uintptr_t)f.data & 15) || ((f.stride[1] * 8) & 15) || ((f.stride[2] * 8) & 15)) return false;
+  if (f.stride[1] != f.size[0] || f.stride[2] != (long long)f.size[0] * f.size[1]) return false;   // dense parent
+  return true;
+}
+static int make_map_f64(EncodeTiledFn enc, const ocb_field& f, int rows, CUtensorMap* map, int tw) {
+  cuuint64_t dims[3] = {(cuuint64_t)f.size[0], (cuuint64_t)f.size[1], (cuuint64_t)f.size[2]};
+  cuuint64_t strides[2] = {(cuuint64_t)f.stride[1] * 8, (cuuint64_t)f.stride[2] * 8};
+  cuuint32_t box[3] = {(cuuint32_t)tw, (cuuint32_t)rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, f.data, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) OCB_FAIL(OCB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return OCB_OK;
+}
+
 // Float32 fields: the merged-row view (two parent rows per tensor row) must stride by 16-byte multiples
 static bool tma_compatible_f32(const ocb_field& f, const ocb_grid* g) {
   if (f.kind != OCB_FIELD_ARRAY || !f.data) return false;
