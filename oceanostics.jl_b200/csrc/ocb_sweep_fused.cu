@@ -92,7 +92,9 @@ struct Geo {
 // forms, restated in oracle/kernels.py): face gradients take 1/dzf of their face, cell differences 1/dzc of their cell, the fcf / cff
 // strain edges and the z-face tracer gradients enter a cell with weight dzf(face) / dzc(cell), the advecting transports of the w
 // equation are dzc-weighted means (Ax = dy dzc), and integrals weigh a cell by dzc.  The metrics are uniform loads per plane.
-template <int MASK, int NW, int RY, int NS, bool OUT, bool STR = false>
+// TIN = float: Float32 fields in and out (the arithmetic and the integrals stay Float64): tiles as two TMA boxes per field over the
+// merged-row view, read through per-row offsets -- the form of ocb_budget_sums.cuh and ocb_sweep_strain.cu.
+template <int MASK, int NW, int RY, int NS, bool OUT, bool STR = false, class TIN = double>
 __global__ void __launch_bounds__(NW * 32, (RY == 1 ? (NW <= 8 ? 2 : 1) : (RY == 2 && NW <= 6 ? 2 : 1)))
 ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__ CUtensorMap mu, const __grid_constant__ CUtensorMap mv,
                   const __grid_constant__ CUtensorMap mw, const __grid_constant__ CUtensorMap mb, const __grid_constant__ CUtensorMap mp,
@@ -110,10 +112,15 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
   // the same way as for the cell terms (east by shuffle, north by register / exchange row); to reach the points
   // i = 1 and j = jy_lo the tiling then starts one cell earlier, in the halo.
   constexpr int SH = H_EPV ? 1 : 0;
+  constexpr bool F32IN = sizeof(TIN) == 4;
+  constexpr int TWK = F32IN ? 40 : TW;
+  constexpr int HALF = ((TWK * (G::TR / 2) * 4 + 127) / 128) * 128 / 4;      // Float32: one of the tile's two boxes, 128-byte aligned
+  constexpr int TILE = F32IN ? 2 * HALF : G::TILE;
+  static_assert(!F32IN || (G::TR % 2 == 0 && !H_EPV && OUT), "Float32: two boxes of TR / 2 rows, the seven budget terms, the cell-value form");
 
   extern __shared__ __align__(1024) double smem_d[];
-  double* tiles = smem_d;                                                      // [NS][NF][TILE]
-  double* xch = tiles + NS * NF * G::TILE;                                     // [2][NW][NX][32]
+  TIN* tiles = reinterpret_cast<TIN*>(smem_d);                                 // [NS][NF][TILE]
+  double* xch = reinterpret_cast<double*>(tiles + NS * NF * TILE);             // [2][NW][NX][32]
   double* red = xch + 2 * NW * NX * 32;                                        // [NW]
   uint64_t* full = reinterpret_cast<uint64_t*>(red + NW);                      // [NS]
 
@@ -131,22 +138,43 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
   const int jr0 = warp * RY;                           // first block-row of this thread
 
   // ---- TMA ring ------------------------------------------------------------------------------------------
-  constexpr uint32_t STAGE_BYTES = (uint32_t)(NF * TW * G::TR * 8);
+  constexpr uint32_t STAGE_BYTES = (uint32_t)(NF * TWK * G::TR * sizeof(TIN));
   // parent coordinates of the tile's first element; the TMA box start must be 16-byte aligned in x, so the box
   // starts at the even element at or before it and every shared-memory column index is shifted by xoff
   const int px_raw = i0 - 1 + P.hx - 1, py = j0 - 1 + P.hy - 1;
   const int xoff = px_raw & 1, px = px_raw - xoff;
+  int bx[2] = {0, 0}, by[2] = {0, 0}, bo[2] = {0, 0};      // Float32: the two boxes' start (merged-row view) and the columns lost to its alignment
+  if (F32IN) {
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int xr = ((py + b) & 1) * P.rowlen + px_raw;
+      bx[b] = xr & ~3; bo[b] = xr & 3; by[b] = (py + b) >> 1;
+    }
+  }
   auto issue = [&](int n) {
     const int s = (n - n_first) % NS;
-    double* dst = tiles + s * (NF * G::TILE);
+    TIN* dst = tiles + s * (NF * TILE);
     mbar_expect_tx(&full[s], STAGE_BYTES);
     const int pz = n + P.hz - 1;
-    tma_load_3d(dst + 0 * G::TILE, &mu, &full[s], px, py, pz);
-    tma_load_3d(dst + 1 * G::TILE, &mv, &full[s], px, py, pz);
-    tma_load_3d(dst + 2 * G::TILE, &mw, &full[s], px, py, pz);
-    if (NEED_B) tma_load_3d(dst + F_B * G::TILE, &mb, &full[s], px, py, pz);
-    if (NEED_P) tma_load_3d(dst + F_P * G::TILE, &mp, &full[s], px, py, pz);
+#pragma unroll
+    for (int b = 0; b < (F32IN ? 2 : 1); ++b) {
+      TIN* d = dst + b * HALF;
+      const int x = F32IN ? bx[b] : px, y = F32IN ? by[b] : py;
+      tma_load_3d(d + 0 * TILE, &mu, &full[s], x, y, pz);
+      tma_load_3d(d + 1 * TILE, &mv, &full[s], x, y, pz);
+      tma_load_3d(d + 2 * TILE, &mw, &full[s], x, y, pz);
+      if (NEED_B) tma_load_3d(d + F_B * TILE, &mb, &full[s], x, y, pz);
+      if (NEED_P) tma_load_3d(d + F_P * TILE, &mp, &full[s], x, y, pz);
+    }
   };
+  // tile offsets of the column WEST of this lane's cell in the rows jr0 .. jr0 + RY + 1 (south row, the thread's rows, north row):
+  // p = T + ro[q] gives p[0] west, p[1] centre, p[2] east
+  int ro[RY + 2];
+#pragma unroll
+  for (int q = 0; q < RY + 2; ++q) {
+    const int tr = jr0 + q;
+    ro[q] = F32IN ? (tr & 1) * HALF + (tr >> 1) * TWK + bo[tr & 1] + lane : tr * TW + lane + xoff;
+  }
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) mbar_init(&full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -227,7 +255,7 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
   auto emit = [&](int d, double raw, double scale, double w, int plane, int r) {
     acc[d] = fma(raw, w, acc[d]);
     if (OUT) {
-      if (w != 0.0 && P.o[d].out) P.o[d].out[orow[r] + (long long)plane * P.os[2]] = raw * scale;
+      if (w != 0.0 && P.o[d].out) reinterpret_cast<TIN*>(P.o[d].out)[orow[r] + (long long)plane * P.os[2]] = (TIN)(raw * scale);
     }
   };
 
@@ -239,8 +267,8 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
   auto plane_step = [&](auto steady_tag, const int n) {
     constexpr bool STEADY = decltype(steady_tag)::value;
     mbar_wait(&full[s], phase);
-    const double* T = tiles + s * (NF * G::TILE);
-    const double* Tu = T, *Tv = T + G::TILE, *Tw = T + 2 * G::TILE, *Tb = T + F_B * G::TILE, *Tp = T + F_P * G::TILE;
+    const TIN* T = tiles + s * (NF * TILE);
+    const TIN* Tu = T, *Tv = T + TILE, *Tw = T + 2 * TILE, *Tb = T + F_B * TILE, *Tp = T + F_P * TILE;
     if (++s == NS) { s = 0; phase ^= 1; }
     // plane validity (uniform): cells of plane n, n-1, n-2 inside this block's z chunk
     const double pv0 = STEADY ? 1.0 : ((n >= k0 && n <= k1) ? 1.0 : 0.0), pv1 = STEADY ? 1.0 : (((n - 1) >= k0 && (n - 1) <= k1) ? 1.0 : 0.0),
@@ -277,14 +305,14 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
     double XS23[RY], O13[RY], O12[RY], Dx[RY], Dy[RY], Sb[RY];
 #pragma unroll
     for (int r = 0; r < RY; ++r) {
-      const int row = jr0 + 1 + r;                       // tile row of this cell
-      const double* ru = Tu + row * TW + lane + xoff;           // ru[0] west, ru[1] centre, ru[2] east
-      const double* rv = Tv + row * TW + lane + xoff;
-      const double* rw = Tw + row * TW + lane + xoff;
+      const int oc = ro[r + 1], osr = ro[r], onr = ro[r + 2];   // this cell's tile row, the row to its south, to its north
+      const TIN* ru = Tu + oc, *ruS = Tu + osr;                 // ru[0] west, ru[1] centre, ru[2] east
+      const TIN* rv = Tv + oc, *rvS = Tv + osr, *rvN = Tv + onr;
+      const TIN* rw = Tw + oc, *rwS = Tw + osr;
       uc[r] = ru[1]; vc[r] = rv[1]; wc[r] = rw[1];
-      const double ue = ru[2], us = (r == 0) ? ru[1 - TW] : uc[r > 0 ? r - 1 : 0];
-      const double vw = rv[0], vn = rv[1 + TW];
-      const double ww = rw[0], ws = (r == 0) ? rw[1 - TW] : wc[r > 0 ? r - 1 : 0];
+      const double ue = ru[2], us = (r == 0) ? ruS[1] : uc[r > 0 ? r - 1 : 0];
+      const double vw = rv[0], vn = rvN[1];
+      const double ww = rw[0], ws = (r == 0) ? rwS[1] : wc[r > 0 ? r - 1 : 0];
       // ffc edge (i, j): scaled strain (nu/4 folded in) and the (Vu = Uv) momentum-flux product
       const double s12 = (uc[r] - us) * ey + (vc[r] - vw) * ex;
       P12[r] = (vw + vc[r]) * (us + uc[r]);
@@ -303,8 +331,8 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
         O13[r] = (uc[r] - up[r]) * rzf - (wc[r] - ww) * rdx;               // (rzf: 1 / dz_f of face n; rdz on a regular axis)
         const double o23 = (wc[r] - ws) * rdy - (vc[r] - vp[r]) * rzf;
         XS23[r] = o23 + __shfl_down_sync(FULLMASK, o23, 1);
-        const double* rb = Tb + row * TW + lane + xoff;
-        const double b00 = rb[1], b10 = rb[2], b01 = rb[1 + TW], b11 = rb[2 + TW];
+        const TIN* rb = Tb + oc, *rbN = Tb + onr;
+        const double b00 = rb[1], b10 = rb[2], b01 = rbN[1], b11 = rbN[2];
         Dx[r] = (b10 - b00) + (b11 - b01);
         Dy[r] = (b01 - b00) + (b11 - b10);
         Sb[r] = (b00 + b10) + (b01 + b11);
@@ -327,7 +355,7 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
         const double uw = ru[0];
         UuW[r] = (uw + uc[r]) * (uw + uc[r]);
         Vv[r] = (vc[r] + vn) * (vc[r] + vn);
-        if (r == 0) { const double vs = rv[1 - TW]; VvS[r] = (vs + vc[r]) * (vs + vc[r]); }
+        if (r == 0) { const double vs = rvS[1]; VvS[r] = (vs + vc[r]) * (vs + vc[r]); }
         else VvS[r] = Vv[r > 0 ? r - 1 : 0];
       }
       if (OUT) {
@@ -338,17 +366,17 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
         }
         if (H_K) Kxy[r] = fma(uc[r], uc[r], ue * ue) + fma(vc[r], vc[r], vn * vn);
         if (NEED_P) {
-          const double* rp = Tp + row * TW + lane + xoff;
+          const TIN* rp = Tp + oc;
           pc[r] = rp[1];
-          const double pw = rp[0], pe = rp[2], ps = rp[1 - TW], pn = rp[1 + TW];
+          const double pw = rp[0], pe = rp[2], ps = Tp[osr + 1], pn = Tp[onr + 1];
           const double tx_ = fma(ue, pe - pc[r], uc[r] * (pc[r] - pw));
           const double ty_ = fma(vn, pn - pc[r], vc[r] * (pc[r] - ps));
           PRxy[r] = fma(ty_, rdy, tx_ * rdx);
         }
         if (NEED_B) {
-          const double* rb = Tb + row * TW + lane + xoff;
+          const TIN* rb = Tb + oc;
           bc[r] = rb[1];
-          const double dw_ = bc[r] - rb[0], de = rb[2] - bc[r], ds = bc[r] - rb[1 - TW], dn = rb[1 + TW] - bc[r];
+          const double dw_ = bc[r] - rb[0], de = rb[2] - bc[r], ds = bc[r] - Tb[osr + 1], dn = Tb[onr + 1] - bc[r];
           if (H_CHI) CHxy[r] = fma(fma(dw_, dw_, de * de), rdx2, fma(ds, ds, dn * dn) * rdy2);
           if (H_CDF) CDxy[r] = fma(dw_ - de, rdx2, (ds - dn) * rdy2);
         }
@@ -376,16 +404,16 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
           accum(aK_z[r], wc[r], wc[r], fz);
         }
         if (NEED_P) {
-          const double* rp = Tp + row * TW + lane + xoff;
+          const TIN* rp = Tp + oc;
           pc[r] = rp[1];
           accum(aP_x[r], uc[r], pc[r] - rp[0], f0);
-          accum(aP_y[r], vc[r], pc[r] - rp[1 - TW], f0);
+          accum(aP_y[r], vc[r], pc[r] - Tp[osr + 1], f0);
           accum(aP_z[r], wc[r], pc[r] - pp[r], fz);
         }
         if (NEED_B) {
-          const double* rb = Tb + row * TW + lane + xoff;
+          const TIN* rb = Tb + oc;
           bc[r] = rb[1];
-          const double dw_ = bc[r] - rb[0], ds = bc[r] - rb[1 - TW], dbz = bc[r] - bp[r];
+          const double dw_ = bc[r] - rb[0], ds = bc[r] - Tb[osr + 1], dbz = bc[r] - bp[r];
           if (H_WB) accum(aW_z[r], wc[r], bp[r] + bc[r], fz);
           if (H_CHI) {
             accum(aC_x[r], dw_, dw_, f0);
@@ -393,7 +421,7 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
             accum(aC_z[r], dbz, dbz, fz);
           }
           if (H_CDF) {
-            const double de = rb[2] - bc[r], dn = rb[1 + TW] - bc[r];
+            const double de = rb[2] - bc[r], dn = Tb[onr + 1] - bc[r];
             const double cdxy = fma(dw_ - de, rdx2, (ds - dn) * rdy2);
             const double lap = fma(-dbz, rdz2, CDacc[r]);   // Laplacian of the cell below, completed by this face
             accum(aD_c[r], bp[r], lap, f1);
@@ -443,7 +471,7 @@ ocb_budget_kernel(const __grid_constant__ FusedParams P, const __grid_constant__
         const double w = STR ? (pvE * wE[r]) * dzf0 : pvE * wE[r];          // (STR: the fff point's volume is dx dy dz_f)
         acc[FD_EPV] = fma(raw, w, acc[FD_EPV]);
         if (OUT) {
-          if (w != 0.0 && P.o[FD_EPV].out) P.o[FD_EPV].out[orow[r] + P.os[0] + P.os[1] + (long long)n * P.os[2]] = raw;
+          if (w != 0.0 && P.o[FD_EPV].out) reinterpret_cast<TIN*>(P.o[FD_EPV].out)[orow[r] + P.os[0] + P.os[1] + (long long)n * P.os[2]] = (TIN)raw;
         }
       }
       if (OUT) {
@@ -675,6 +703,22 @@ static int setup_variant_stretched(ocb_fused_plan* fp) {
   return OCB_OK;
 }
 
+// Float32 fields in and out: the cell-value form with two-box tiles (40-column pitch)
+template <int MASK, int NW, int RY, int NS, bool STR>
+static int setup_variant_f32(ocb_fused_plan* fp) {
+  using G = Geo<NW, RY>;
+  constexpr bool NEED_B = MASK & ((1 << FD_WB) | (1 << FD_CHI) | (1 << FD_CDF)), NEED_P = MASK & (1 << FD_PR);
+  constexpr int NF = 3 + (NEED_B ? 1 : 0) + (NEED_P ? 1 : 0);
+  constexpr int TILE_F = 2 * (((40 * (G::TR / 2) * 4 + 127) / 128) * 128 / 4);
+  fp->nw = NW; fp->ry = RY; fp->ns = NS; fp->mask = MASK; fp->tw = 40;
+  fp->smem = sizeof(float) * (size_t)NS * NF * TILE_F + sizeof(double) * (2 * NW * NXCH * 32 + NW) + sizeof(uint64_t) * NS;
+  auto kern = ocb_budget_kernel<MASK, NW, RY, NS, true, STR, float>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  fp->kernel = kern;
+  OCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp->smem));
+  return OCB_OK;
+}
+
 template <int MASK, int NW, int RY, int NS, int MINB, int TWK = TW, bool STR = false, bool NUF = false, class TIN = double>
 static int setup_sums(ocb_fused_plan* fp) {
   using G = Geo<NW, RY>;
@@ -787,7 +831,7 @@ static int fused_try_create_t(const ocb_grid* grid, const ocb_sweep_inputs* in, 
   }
   bool sums_convention = !any_outq && grid->topo[0] == OCB_PERIODIC && !getenv("OCB_FUSED_CELL_INTEGRALS") && (!stretched || str_sums_ok);
   for (int r = 0; r < n; ++r) if (reqs[r].diag == OCB_DIAG_EPV) sums_convention = false;
-  if (F32 && !sums_convention) return OCB_OK;
+  if (F32 && !sums_convention && getenv("OCB_DISABLE_FIELDS_F32")) return OCB_OK;
   for (int r = 0; r < n; ++r) {
     int d = fused_diag_index(reqs[r].diag);
     if (d < 0) return OCB_OK;
@@ -830,6 +874,7 @@ static int fused_try_create_t(const ocb_grid* grid, const ocb_sweep_inputs* in, 
   // Float32: the seven plain budget terms, or the TKE budget with pressure redistribution about mean profiles
   constexpr int TKEP_F = (1 << FD_SP) | (1 << FD_EPSP) | (1 << FD_TKE) | (1 << FD_PR) | (1 << FD_K);
   if (F32 && (any_pert ? (mask & ~TKEP_F) != 0 : (mask & ~FD_BUDGET) != 0)) return OCB_OK;
+  if (F32 && !sums_convention && (any_pert || (mask & ~FD_BUDGET))) return OCB_OK;      // with output fields: the seven plain terms
   // stretched z: the cell-exact variant evaluates the seven plain budget terms; the class-sum form also the TKE-budget terms
   constexpr int TKE_TERMS = (1 << FD_SP) | (1 << FD_EPSP) | (1 << FD_TKE);
   // (cell-exact: the seven plain terms, or the TKE budget about mean profiles {eps(u - U), SP, PR, K} -- no potential vorticity)
@@ -907,8 +952,12 @@ static int fused_try_create_t(const ocb_grid* grid, const ocb_sweep_inputs* in, 
   const bool sums = sums_convention;
   const int njy = SP.req[0].hi[1] - SP.req[0].lo[1] + 1;
   if constexpr (F32) {
-    // Float32 inputs: the all-terms class sums in the two-box tile form (40-column pitch), with the stretched / eddy-viscosity forms
-    if (any_pert) {
+    // Float32 inputs: the all-terms class sums in the two-box tile form (40-column pitch), with the stretched / eddy-viscosity forms;
+    // plans with output fields (or a Bounded x): the cell-value kernel, all seven terms
+    if (!sums) {
+      if (!tma_compatible(in->b, grid) || !tma_compatible(in->p, grid)) { delete fp; return OCB_OK; }
+      rc = stretched ? setup_variant_f32<ALL, 8, 2, 3, true>(fp) : setup_variant_f32<ALL, 8, 2, 3, false>(fp);
+    } else if (any_pert) {
       if (!tma_compatible(in->p, grid)) { delete fp; return OCB_OK; }
       if (stretched) rc = nuf ? setup_sums<TKEP_F, 4, 4, 3, 2, 40, true, true, float>(fp) : setup_sums<TKEP_F, 4, 4, 3, 2, 40, true, false, float>(fp);
       else rc = nuf ? setup_sums<TKEP_F, 4, 4, 3, 2, 40, false, true, float>(fp) : setup_sums<TKEP_F, 4, 4, 3, 2, 40, false, false, float>(fp);

@@ -321,6 +321,30 @@ def test_float32_tke_budget_integrals(stretched, closure):
 
 
 @pytest.mark.parametrize("stretched", [False, True], ids=["regular", "stretched"])
+def test_float32_budget_fields_on_the_pipelined_kernel(stretched):
+    """Float32 fields in and out: all seven budget terms as fields and integrals in one launch of the budget kernel's Float32 form
+    (two-box TMA tiles, Float64 arithmetic, Float32 stores), regular and stretched z; 1e-5 relative L2 against the Float32 oracle
+    (north_star's Float32 tolerance), integrals to 1e-5 of the integrand scale, and a windowed output."""
+    st = State(size=(64, 40, 30), stretched=stretched, dtype=np.float32, device="cuda")
+    ops, oc = budget(st)
+    grp, vals, ints = run(ops)
+    assert grp.plan.variant == 1
+    want = [w.astype(np.float64) for w in oracle_budget(st, oc)]
+    ii, jj, kk = st.og.indices("ccc")
+    vol = np.broadcast_to(np.asarray(st.og.V("ccc", ii, jj, kk), dtype=np.float64), want[0].shape)
+    for op, g, w_, integ in zip(ops, vals, want, ints):
+        assert g.dtype == np.float32
+        err = np.linalg.norm(g.astype(np.float64) - w_) / np.linalg.norm(w_)
+        assert err <= 1e-5, (op.name, err)
+        assert abs(integ - float(np.sum(w_ * vol))) <= 1e-5 * float(np.sum(np.abs(w_) * vol)), op.name
+    win = ocb.FusedDiagnostics(*[ocb.Field(o, indices=(None, (5, 33), (4, 27))) for o in ops]).compute()
+    torch.cuda.synchronize()
+    assert win.plan.variant == 1
+    for o, f, w in zip(ops, vals, win.members):
+        np.testing.assert_array_equal(w.interior_ijk(), f[:, 4:33, 3:27])
+
+
+@pytest.mark.parametrize("stretched", [False, True], ids=["regular", "stretched"])
 def test_windowed_budget_fields_match_the_full_fields(stretched):
     """Field(op, indices=(:, j-window, k-window)) of all seven terms in one sweep of the pipelined kernel: the window holds
     exactly the full field's values (the z window of a stretched grid starts at a plane with other metrics than plane 1)."""
