@@ -5,9 +5,12 @@
 // HeavisideIntegral :428-466).
 //
 // The reference calls sortperm! (Base on the CPU, CUDA.jl's on the GPU).  Here the sort is a hand-written stable LSD
-// radix sort (8-bit digits) of order-preserving integer keys with a 32-bit index payload:
-//   per pass   histogram (per-tile digit counts, digit-major table)  ->  exclusive scan of the table  ->
-//              stable scatter (warp match-any ranking, per-warp digit counters, tile offsets from the scan)
+// radix sort (8-bit digits) of order-preserving integer keys with a 32-bit index payload ("onesweep"):
+//   once       histogram of all digits (the first pass's reader makes the keys from the caller's values / the field's interior)
+//   per digit  ONE persistent kernel: ticketed tiles, ranking through per-warp mask words in shared memory, a two-level chained
+//              scan over the tiles' digit counts (groups of 16 tickets, RED-accumulated group totals), software-pipelined so that a
+//              tile's prefix is asked for one tile later; the last pass writes values and permutation into the caller's arrays
+// (n >= 2^30 or OCB_SORT_TABLE_SCAN: per-pass histogram table + scan + scatter instead of the chained scan.)
 // Stable means ties keep their original (column-major) order, which is what Base.sortperm! does on the CPU; the
 // reference's GPU sort gives no such guarantee, hence only permutation-invariant results are compared.
 // Key transform: flip all bits of negative floats, set the sign bit of non-negative ones -- Julia's isless order on
