@@ -152,3 +152,101 @@ def test_tke_budget_class_sums_reproduce_the_cell_integrals(window):
             win = c[:, jlo - 1:jhi, klo - 1:khi]
             want, scale = float(np.sum(win)) * Vol, float(np.sum(np.abs(win))) * Vol
             assert abs(g - want) <= 1e-12 * scale, (name, ring, g, want, scale)
+
+
+def class_sums_stretched(st, nu, kappa, jlo, jhi, klo, khi, nu_e=None, kappa_scale=0.0):
+    """The kernel's stretched-z GEN forms (`ocb_budget_sums_kernel<..., STR>`), optionally with an eddy-viscosity field nu_e inside
+    the dissipation's items and kappa = kappa + kappa_scale x (two-point means of nu_e) on the tracer-gradient faces (`NUF`):
+    per-plane weights dz_c (items of a cell plane), dz_f (fcf / cff strain edges), (G0 + G1) / 2 with G = class x dz_c (z-face items
+    of K and w b), the by-parts advection split into the u / v equations' z parts (no metric left) and the w equation's parts with
+    the dz_c-weighted transports."""
+    og = st.og
+    Nx, Ny, Nz = og.N
+    H = og.H[0]
+    rdx, rdy = Nx / 1.0, Ny / 1.0
+    I = np.arange(1, Nx + 1)[:, None, None]
+    J = np.arange(jlo, jhi + 2)[None, :, None]
+    N = np.arange(klo, khi + 3)[None, None, :]
+    at = lambda f, di=0, dj=0, dk=0: f.data[I + di + H - 1, J + dj + H - 1, N + dk + H - 1]
+    lo_, hi_ = 1 - og.H[2], Nz + og.H[2]
+    zc = lambda dk=0: np.asarray(og.spacing(2, "c", np.clip(N[0, 0, :] + dk, lo_, hi_)), dtype=np.float64)[None, None, :]
+    zf = lambda dk=0: np.asarray(og.spacing(2, "f", np.clip(N[0, 0, :] + dk, lo_, hi_)), dtype=np.float64)[None, None, :]
+    c0, c1, c2, dzf0, rzf0, rzf1, rzc1 = zc(0), zc(-1), zc(-2), zf(0), 1.0 / zf(0), 1.0 / zf(-1), 1.0 / zc(-1)
+    u, v, w, b, p = st.ou, st.ov, st.ow, st.ob, st.op
+    inw = lambda a, lo, hi: ((a >= lo) & (a <= hi)).astype(np.float64)
+    al, be, an = inw(J, jlo, jhi), inw(J - 1, jlo, jhi), inw(J + 1, jlo, jhi)
+    g0, g1, g2 = inw(N, klo, khi), inw(N - 1, klo, khi), inw(N - 2, klo, khi)
+    G0, G1, G2 = g0 * c0, g1 * c1, g2 * c2
+    hy, hyn, hz = 0.5 * (al + be), 0.5 * (al + an), 0.5 * (g0 + g1)
+    hzK, rho0, rho1 = 0.5 * (G0 + G1), 0.5 * (G0 + G1) * rzf0, 0.5 * (G1 + G2) * rzf1
+    uc, us, up_, ue = at(u), at(u, dj=-1), at(u, dk=-1), at(u, di=1)
+    vc, vw, vp, vn, vs = at(v), at(v, di=-1), at(v, dk=-1), at(v, dj=1), at(v, dj=-1)
+    wc, ww, ws, wp = at(w), at(w, di=-1), at(w, dj=-1), at(w, dk=-1)
+    bc, bw, bs, bp, be_, bn = at(b), at(b, di=-1), at(b, dj=-1), at(b, dk=-1), at(b, di=1), at(b, dj=1)
+    pc, pw, ps, pp = at(p), at(p, di=-1), at(p, dj=-1), at(p, dk=-1)
+    duy, dvx, duz, dwx, dvz, dwy = uc - us, vc - vw, uc - up_, wc - ww, vc - vp, wc - ws
+    ax, ay, dwz = ue - uc, vn - vc, wc - wp
+    S12, S13, S23 = dvx * rdx + duy * rdy, dwx * rdx + duz * rzf0, dwy * rdy + dvz * rzf0
+    P12, P13, P23 = (vw + vc) * (us + uc), (ww + wc) * (up_ + uc), (ws + wc) * (vp + vc)
+    P13w, P23w = (ww + wc) * (c1 * up_ + c0 * uc), (ws + wc) * (c1 * vp + c0 * vc)
+    Uu, Vv, Ww, VvS = (uc + ue) ** 2, (vc + vn) ** 2, (wp + wc) ** 2, (vs + vc) ** 2
+    # viscosities / diffusivities of the items (one everywhere without a field: the constants are applied at the end)
+    one = np.ones_like(uc)
+    nffc = nfcf = ncff = ncc = nccp = one
+    kx = ky = kz = kxe = kyn = one
+    if nu_e is not None:
+        ncn, nw_, ns_, nsw, npv, npw, nps = at(nu_e), at(nu_e, di=-1), at(nu_e, dj=-1), at(nu_e, di=-1, dj=-1), at(nu_e, dk=-1), at(nu_e, di=-1, dk=-1), at(nu_e, dj=-1, dk=-1)
+        XN, YN, XNp, YNp = nw_ + ncn, ns_ + ncn, npw + npv, nps + npv
+        nffc, nfcf, ncff = nu + 0.25 * ((nsw + ns_) + XN), nu + 0.25 * (XNp + XN), nu + 0.25 * (YNp + YN)
+        ncc, nccp = nu + ncn, nu + npv
+        hs = 0.5 * kappa_scale
+        kx, ky, kz = kappa + hs * XN, kappa + hs * YN, kappa + hs * (npv + ncn)
+    S = np.sum
+    aEe = S(hy * G0 * nffc * S12 ** 2 + al * (hz * dzf0) * nfcf * S13 ** 2 + hy * (hz * dzf0) * ncff * S23 ** 2)
+    aEx, aEy, aEz = S(al * G0 * ncc * ax ** 2), S(al * G0 * ncc * ay ** 2), S(al * g1 * rzc1 * nccp * dwz ** 2)
+    aAe = S(G0 * P12 * (rdx * hy * dvx + rdy * (al * uc - be * us)) + al * P13w * (rdx * rho0) * dwx + al * P13 * (g0 * uc - g1 * up_) +
+            P23w * (rdy * rho0) * (al * wc - be * ws) + hy * P23 * (g0 * vc - g1 * vp))
+    aAx = S(al * G0 * Uu * ax)
+    aAy = S(G0 * Vv * (hyn * vn - hy * vc)) + S((J == jlo) * G0 * VvS * 0.5 * vc)
+    aAz = S(al * Ww * (rho0 * wc - rho1 * wp))
+    aK = S(al * G0 * uc ** 2 + hy * G0 * vc ** 2 + al * hzK * wc ** 2)
+    aPx, aPy, aPz = S(al * G0 * uc * (pc - pw)), S(hy * G0 * vc * (pc - ps)), S(al * rho0 * wc * (pc - pp))
+    aW = S(al * hzK * wc * (bp + bc))
+    dbx, dby, dbz = bc - bw, bc - bs, bc - bp
+    aCx, aCy, aCz = S(al * G0 * kx * dbx ** 2), S(hy * G0 * ky * dby ** 2), S(al * (hz * rzf0) * kz * dbz ** 2)
+    # dz_c x the Laplacian (sign of div q) of the cell below the face of step n
+    bpw, bpe, bps, bpn, bpp = at(b, di=-1, dk=-1), at(b, di=1, dk=-1), at(b, dj=-1, dk=-1), at(b, dj=1, dk=-1), at(b, dk=-2)
+    if nu_e is None:
+        kxp = kxep = kyp = kynp = kzp = one
+    else:
+        hs = 0.5 * kappa_scale
+        npe, npn, npp = at(nu_e, di=1, dk=-1), at(nu_e, dj=1, dk=-1), at(nu_e, dk=-2)
+        kxp, kxep, kyp, kynp, kzp = kappa + hs * (npw + npv), kappa + hs * (npv + npe), kappa + hs * (nps + npv), kappa + hs * (npv + npn), kappa + hs * (npp + npv)
+    lap = c1 * (rdx ** 2 * (kxp * (bp - bpw) - kxep * (bpe - bp)) + rdy ** 2 * (kyp * (bp - bps) - kynp * (bpn - bp))) + (kzp * (bp - bpp) * rzf1 - kz * dbz * rzf0)
+    aD = S(al * g1 * bp * lap)
+    V = 1.0 / (rdx * rdy)
+    fn, fk = (1.0, 1.0) if nu_e is not None else (nu, kappa)
+    return [V * 0.5 * aK, V * -0.25 * (aAe + rdx * aAx + rdy * aAy + aAz), V * (rdx * aPx + rdy * aPy + aPz), V * 0.5 * aW,
+            V * fn * (aEe + 2.0 * (rdx ** 2 * aEx + rdy ** 2 * aEy + aEz)), V * 2.0 * fk * (rdx ** 2 * aCx + rdy ** 2 * aCy + aCz), V * 2.0 * fk * aD]
+
+
+@pytest.mark.parametrize("window", [None, (3, 9, 1, 10), (1, 1, 2, 2), (12, 12, 10, 10), (1, 12, 4, 7), (2, 11, 1, 1)], ids=str)
+@pytest.mark.parametrize("closure", ["scalar", "smagorinsky_like"])
+def test_stretched_class_sums_reproduce_the_windowed_cell_integrals(window, closure):
+    """The stretched-z forms of the class sums (and their eddy-viscosity / eddy-diffusivity variant) against the oracle's per-cell
+    values times their cell volumes, on the reference's stretched test grid (test/test_utils.jl:17-24)."""
+    st = State(size=(16, 12, 10), stretched=True)
+    nu, kappa = 1e-6, 1e-7
+    if closure == "scalar":
+        oc, nu_e, nu0, ka0, ks = K.Closure(nu=nu, kappa=kappa), None, nu, kappa, 0.0
+    else:
+        oc, nu_e, nu0, ka0, ks = st.closures()[closure][0], st.onu, 0.0, 0.0, 1.0
+    cells = _budget_cells(st, oc)
+    ii, jj, kk = st.og.indices("ccc")
+    vol = np.broadcast_to(st.og.V("ccc", ii, jj, kk), cells[0].shape)
+    jlo, jhi, klo, khi = window or (1, 12, 1, 10)
+    got = class_sums_stretched(st, nu0, ka0, jlo, jhi, klo, khi, nu_e=nu_e, kappa_scale=ks)
+    for name, c, g in zip("K ADV PR WB EPS CHI CDF".split(), cells, got):
+        win, vw = c[:, jlo - 1:jhi, klo - 1:khi], vol[:, jlo - 1:jhi, klo - 1:khi]
+        want, scale = float(np.sum(win * vw)), float(np.sum(np.abs(win) * vw))
+        assert abs(g - want) <= 1e-12 * scale, (name, g, want, scale)
